@@ -1,0 +1,140 @@
+/*
+ * rz_b200.h -- C ABI of librz_b200.so: RadZero's VL-CABS similarity path on B200 (sm_100a).
+ *
+ * The reference (deepnoid-ai/RadZero) has no FFI: the path sits behind plain Python
+ * callables.  This header is the boundary the new build introduces
+ * below them; each entry point names the reference code it replaces.  radzero_b200's
+ * Python mirror of the reference surface (losses.py / modeling.py / inference.py) binds
+ * these with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors are dense row-major with the strides stated per function;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - functions enqueue work and return immediately: 0 (RZ_OK) or a negative RZ_ERR_*;
+ *     nothing is allocated, no global state is kept besides a launch counter;
+ *   - re-entrant; callers own every buffer (workspace sizes come from rz_*_workspace_bytes).
+ *   - hidden size D is fixed at 768 (RadZeroLoss.hidden_dim, radzero.yaml:40).
+ */
+#ifndef RZ_B200_H_
+#define RZ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RZ_OK 0
+#define RZ_ERR_INVALID (-1)     /* bad shape / null pointer / unsupported size */
+#define RZ_ERR_CUDA (-2)        /* a CUDA runtime call failed; see rz_last_cuda_error() */
+#define RZ_ERR_UNSUPPORTED (-3) /* valid request outside what this build implements */
+#define RZ_ERR_ALIGNMENT (-4)   /* pointer or stride not aligned as documented */
+
+/* element types of the *input* tensors (tokens / text); math is fp32, MMA operands fp16 */
+#define RZ_F32 0
+#define RZ_BF16 1
+#define RZ_F16 2
+
+#define RZ_LN_EPS 1e-5f  /* nn.LayerNorm default, exp/cxr_pt/model/losses.py:51 */
+#define RZ_L2_EPS 1e-12f /* F.normalize default, losses.py:212-213 */
+
+/* ---- library ---------------------------------------------------------------------- */
+int rz_version(void);                   /* 1000*major + minor */
+const char* rz_strerror(int code);
+const char* rz_last_cuda_error(void);   /* text of the last CUDA error seen, "" if none */
+long long rz_launch_count(void);        /* kernels launched by this library so far */
+int rz_device_sm_count(void);
+
+/* ---- K1+K2: LayerNorm + L2 normalisation of rows -------------------------------------
+ * Replaces nn.LayerNorm on text / vision tokens (losses.py:90-91, 163-164; the SAME
+ * gamma/beta for both, losses.py:51) followed by F.normalize (losses.py:212-213).
+ *   x        [rows, 768] of `dtype`, contiguous
+ *   gamma/beta fp32 [768], or both NULL for no LayerNorm (use_layer_norm=False)
+ *   out_f16  optional [groups, rows_per_group_padded, 768] fp16: row r of group g lands at
+ *            (g*rows_per_group_padded + r); padding rows are zero-filled.  With
+ *            rows_per_group = rows and rows_per_group_padded = rows this is plain [rows,768].
+ *   out_f32  optional [rows, 768] fp32 (unpadded)
+ *   stats    optional [rows, 3] fp32 = (mean, rstd, 1/max(|LN(x)|, eps)) kept for backward
+ *   l2       0 = LayerNorm only (sim_op "dot"), 1 = LayerNorm then L2 (sim_op "cos")
+ */
+int rz_prep_rows(const void* x, int dtype, const float* gamma, const float* beta,
+                 long long rows, int rows_per_group, int rows_per_group_padded,
+                 void* out_f16, float* out_f32, float* stats, int l2, void* stream);
+
+/* ---- K8+K9: bilinear upsample of patch-grid similarity maps ----------------------------
+ * Replaces F.interpolate(mode="bilinear", align_corners=False) in
+ * interpolate_similarity_scores (exp/cxr_pt/inference/segmentation_utils.py:36-122) and
+ * get_grounding_point (exp/cxr_pt/inference/grounding_utils.py:166-261), fused with the
+ * consumers torch.sigmoid (segmentation_utils.py:225), `> t` (:258) and the global argmax
+ * (grounding_utils.py:254-259).  One launch handles `maps` maps (the reference does one
+ * F.interpolate per (image, prompt)).
+ *   scores   [maps] grids of grid x grid fp32, map m at scores + m*map_stride (elements)
+ *   The grid is resized to (interp_h, interp_w) and pasted with its top-left corner at
+ *   (off_y, off_x) of the (out_h, out_w) canvas (offsets may be negative = crop); canvas
+ *   pixels outside the pasted area get `fill` (the reference's -999).  The four image
+ *   processor branches are parameter choices of this one kernel (see inference.py).
+ *   mode     RZ_UP_RAW      out fp32 [maps,out_h,out_w] = interpolated score
+ *            RZ_UP_SIGMOID  out fp32 = sigmoid(score)
+ *            RZ_UP_MASK     out uint8 = sigmoid(score) > threshold
+ *            RZ_UP_ARGMAX   out int64 [maps,2] = (x, y) of the first global maximum; no map
+ *                           is written
+ */
+#define RZ_UP_RAW 0
+#define RZ_UP_SIGMOID 1
+#define RZ_UP_MASK 2
+#define RZ_UP_ARGMAX 3
+int rz_upsample_maps(const float* scores, long long map_stride, int maps, int grid,
+                     int out_h, int out_w, int interp_h, int interp_w, int off_y, int off_x,
+                     float fill, int mode, float threshold, void* out, void* stream);
+
+/* ---- K10: multi-positive NCE loss, forward + backward ----------------------------------
+ * Replaces multi_positive_nce_loss + get_row_loss + get_col_loss (losses.py:243-344) and
+ * their autograd, for the image-sharded layout of SURVEY.md section 8e: this rank holds
+ * columns [col0, col0 + b_local) of the (n_total x b_global) logit matrix.
+ *
+ * Phase 1 (rz_mpnce_partials): E = exp(Z/tau); per-row local sums rowsum[i] = sum_b E_ib,
+ *   pos[i] = E[i, group_map[i]] if that column is local else 0, per-column sums
+ *   colneg[b] = sum_{i: g_i != b} E_ib and colpos[b] = sum_{i: g_i = b} E_ib, all in a fixed
+ *   summation order (no float atomics) so that 1-GPU and N-GPU runs agree.
+ *   With several ranks the caller all-reduces (sum) rowsum and pos between the phases.
+ *   scratch1: fp32 [2 * ceil(n_total/32) * b_local].
+ * Phase 2 (rz_mpnce_finish): loss terms and dL/dZ for the local columns.
+ *   loss_terms[0] = sum of the row terms this rank owns (rows whose positive column is
+ *   local; images, when row_sum), loss_terms[1] = sum of its column terms,
+ *   loss_terms[2] = sum_ib dZ_ib * Z_ib over the local block (= -dL/dlog(tau) share),
+ *   loss_terms[3] = unused (0).  loss = (sum_ranks terms[0]/n_row + sum_ranks terms[1]/n_col)/2
+ *   with n_row = b_global if row_sum else n_total, n_col = b_global if col_sum else n_total;
+ *   dZ already carries the 1/(2*n_row), 1/(2*n_col) factors.
+ *   row_sum / col_sum select the MIL-NCE variants (losses.py:303-315, 331-336).
+ *   z, dz    [n_total, ldz] fp32 (b_local valid columns per row); dz may be NULL (loss only)
+ *   group_map int64 [n_total] GLOBAL image index
+ *   scratch2 fp32 [4 * n_total + 3 * b_local + 2 * b_global]
+ */
+int rz_mpnce_partials(const float* z, long long ldz, int n_total, int b_local,
+                      const long long* group_map, int col0, float inv_tau,
+                      float* rowsum, float* pos, float* colneg, float* colpos,
+                      float* scratch1, void* stream);
+int rz_mpnce_finish(const float* z, long long ldz, int n_total, int b_local, int b_global,
+                    const long long* group_map, int col0, float inv_tau, float eps,
+                    int row_sum, int col_sum,
+                    const float* rowsum, const float* pos, const float* colneg,
+                    const float* colpos, float* scratch2, float* dz, float* loss_terms,
+                    void* stream);
+
+/* ---- diagnostics: one tcgen05.mma probe -------------------------------------------------
+ * Copies caller-built shared-memory images of A and B into smem, issues `k_steps`
+ * tcgen05.mma (kind::f16, fp32 accumulate) with the given descriptors and dumps all 128
+ * TMEM lanes x `ncols` columns.  Used by tests/test_umma_probe.py to pin the descriptor and
+ * TMEM layouts the production kernels rely on.  Not part of the reference surface.
+ */
+int rz_umma_probe(const void* a_image, int a_bytes, const void* b_image, int b_bytes,
+                  unsigned long long a_desc, unsigned long long b_desc,
+                  int a_step_bytes, int b_step_bytes, int k_steps, unsigned int idesc,
+                  unsigned int d_tmem_offset, int ncols, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RZ_B200_H_ */

@@ -1,0 +1,103 @@
+// K1+K2: row LayerNorm + L2 normalisation, fp16 / fp32 outputs and backward statistics.
+// HBM-bound: one warp per 768-wide row, 128-bit streaming loads, two-pass variance in
+// registers, warp-shuffle reductions, packed fp16 stores.  Replaces nn.LayerNorm
+// (exp/cxr_pt/model/losses.py:90-91,163-164) + F.normalize (losses.py:212-213).
+#include "rz_common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
+prep_rows_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, long long rows, int rows_per_group,
+                 int rows_per_group_padded, __half* __restrict__ out_h, float* __restrict__ out_f,
+                 float* __restrict__ stats, int l2, long long padded_rows_total) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  // iterate over PADDED row slots so that padding rows get zero-filled by the same grid
+  for (long long slot = warp0; slot < padded_rows_total; slot += nwarps) {
+    const unsigned g = (unsigned)slot / (unsigned)rows_per_group_padded;   // slots < 2^31 (checked on host)
+    const int r = (int)((unsigned)slot - g * (unsigned)rows_per_group_padded);
+    if (r >= rows_per_group) {
+      if (out_h != nullptr) {
+        uint2* o = reinterpret_cast<uint2*>(out_h + slot * RZ_HIDDEN) + lane;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) o[32 * j] = make_uint2(0u, 0u);
+      }
+      continue;
+    }
+    const long long row = (long long)g * rows_per_group + r;
+    if (row >= rows) continue;
+    float v[24];
+    rz::RowLoad<T>::load(x + row * RZ_HIDDEN, lane, v);
+    const rz::RowStats st = rz::ln_l2_row(v, gamma, beta, lane, RZ_LN_EPS, RZ_L2_EPS, l2 != 0);
+    if (out_h != nullptr) {
+      uint2* o = reinterpret_cast<uint2*>(out_h + slot * RZ_HIDDEN) + lane;
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        o[32 * j] = make_uint2(rz::pack_half2(v[4 * j], v[4 * j + 1]),
+                               rz::pack_half2(v[4 * j + 2], v[4 * j + 3]));
+    }
+    if (out_f != nullptr) {
+      float4* o = reinterpret_cast<float4*>(out_f + row * RZ_HIDDEN) + lane;
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        o[32 * j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    if (stats != nullptr && lane == 0) {
+      stats[row * 3 + 0] = st.mean;
+      stats[row * 3 + 1] = st.rstd;
+      stats[row * 3 + 2] = st.inv_norm;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int rz_prep_rows(const void* x, int dtype, const float* gamma, const float* beta,
+                            long long rows, int rows_per_group, int rows_per_group_padded,
+                            void* out_f16, float* out_f32, float* stats, int l2, void* stream) {
+  if (x == nullptr || rows < 0 || rows_per_group <= 0 || rows_per_group_padded < rows_per_group)
+    return RZ_ERR_INVALID;
+  if ((gamma == nullptr) != (beta == nullptr)) return RZ_ERR_INVALID;
+  if (rows == 0) return RZ_OK;
+  if (rows % rows_per_group != 0) return RZ_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out_f16) & 15) ||
+      (reinterpret_cast<uintptr_t>(out_f32) & 15) || (reinterpret_cast<uintptr_t>(gamma) & 15) ||
+      (reinterpret_cast<uintptr_t>(beta) & 15))
+    return RZ_ERR_ALIGNMENT;
+  const long long groups = rows / rows_per_group;
+  const long long slots = groups * rows_per_group_padded;
+  if (slots >= (1ll << 31)) return RZ_ERR_UNSUPPORTED;
+  long long blocks = (slots + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const long long cap = (long long)rz_sm_count() * 3;  // 3 resident CTAs per SM (launch bounds)
+  if (blocks > cap) blocks = cap;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)blocks), block(kWarpsPerBlock * 32);
+  __half* oh = static_cast<__half*>(out_f16);
+  switch (dtype) {
+    case RZ_F32:
+      prep_rows_kernel<float><<<grid, block, 0, s>>>(static_cast<const float*>(x), gamma, beta, rows,
+                                                     rows_per_group, rows_per_group_padded, oh,
+                                                     out_f32, stats, l2, slots);
+      break;
+    case RZ_BF16:
+      prep_rows_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(
+          static_cast<const __nv_bfloat16*>(x), gamma, beta, rows, rows_per_group,
+          rows_per_group_padded, oh, out_f32, stats, l2, slots);
+      break;
+    case RZ_F16:
+      prep_rows_kernel<__half><<<grid, block, 0, s>>>(static_cast<const __half*>(x), gamma, beta,
+                                                      rows, rows_per_group, rows_per_group_padded,
+                                                      oh, out_f32, stats, l2, slots);
+      break;
+    default:
+      return RZ_ERR_INVALID;
+  }
+  RZ_LAUNCH_OK();
+  rz_count_launch();
+  return RZ_OK;
+}

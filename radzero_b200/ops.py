@@ -1,0 +1,154 @@
+"""Thin torch-facing wrappers over the C ABI (device pointers + current CUDA stream).
+
+PyTorch is plumbing here: it owns device memory and streams.  Every function takes CUDA
+tensors, allocates its outputs, calls librz_b200.so on torch's current stream and returns.
+No CPU path exists -- CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import RzError
+
+HIDDEN = 768
+_DTYPES = {torch.float32: _lib.RZ_F32, torch.bfloat16: _lib.RZ_BF16, torch.float16: _lib.RZ_F16}
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RzError("radzero_b200 ops run on CUDA tensors only (there is no CPU fallback)")
+
+
+def _contig(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------- K1 + K2
+def prep_rows(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], *,
+              rows_per_group: Optional[int] = None, rows_per_group_padded: Optional[int] = None,
+              want_f16: bool = True, want_f32: bool = False, want_stats: bool = False,
+              l2: bool = True):
+    """LayerNorm + L2-normalise rows of ``x`` (..., 768).  Returns (f16, f32, stats)."""
+    _need_cuda(x, gamma, beta)
+    if x.shape[-1] != HIDDEN:
+        raise RzError(f"hidden size must be {HIDDEN}, got {x.shape[-1]}")
+    if x.dtype not in _DTYPES:
+        raise RzError(f"unsupported input dtype {x.dtype}")
+    x2 = _contig(x).view(-1, HIDDEN)
+    rows = x2.shape[0]
+    rpg = rows_per_group or max(rows, 1)
+    rpp = rows_per_group_padded or rpg
+    g = _contig(gamma.float()) if gamma is not None else None
+    b = _contig(beta.float()) if beta is not None else None
+    groups = rows // rpg if rows else 0
+    f16 = torch.empty((groups * rpp, HIDDEN), dtype=torch.float16, device=x.device) if want_f16 else None
+    f32 = torch.empty((rows, HIDDEN), dtype=torch.float32, device=x.device) if want_f32 else None
+    st = torch.empty((rows, 3), dtype=torch.float32, device=x.device) if want_stats else None
+    rc = _lib.load().rz_prep_rows(_p(x2), _DTYPES[x.dtype], _p(g), _p(b), rows, rpg, rpp,
+                                  _p(f16), _p(f32), _p(st), 1 if l2 else 0, _stream())
+    _lib.check(rc, "rz_prep_rows")
+    return f16, f32, st
+
+
+# ----------------------------------------------------------------------------- K8 + K9
+def upsample_maps(scores: torch.Tensor, out_hw: Tuple[int, int], *, mode: int = _lib.RZ_UP_RAW,
+                  interp_hw: Optional[Tuple[int, int]] = None, offset: Tuple[int, int] = (0, 0),
+                  fill: float = -999.0, threshold: float = 0.5, grid: Optional[int] = None):
+    """Upsample ``scores`` (maps, grid*grid) fp32 -> (maps, H, W) (or (maps, 2) for argmax)."""
+    _need_cuda(scores)
+    if scores.dtype != torch.float32:
+        raise RzError("scores must be fp32")
+    if scores.dim() != 2 or scores.stride(1) != 1:
+        scores = _contig(scores.reshape(-1, scores.shape[-1]))
+    maps, n = scores.shape
+    g = grid or int(round(n ** 0.5))
+    if g * g != n:
+        raise RzError(f"scores last dim {n} is not a square grid")
+    H, W = int(out_hw[0]), int(out_hw[1])
+    ih, iw = (H, W) if interp_hw is None else (int(interp_hw[0]), int(interp_hw[1]))
+    if mode in (_lib.RZ_UP_RAW, _lib.RZ_UP_SIGMOID):
+        out = torch.empty((maps, H, W), dtype=torch.float32, device=scores.device)
+    elif mode == _lib.RZ_UP_MASK:
+        out = torch.empty((maps, H, W), dtype=torch.uint8, device=scores.device)
+    elif mode == _lib.RZ_UP_ARGMAX:
+        out = torch.empty((maps, 2), dtype=torch.int64, device=scores.device)
+    else:
+        raise RzError(f"bad upsample mode {mode}")
+    lib = _lib.load()
+    step = 32768  # gridDim.y limit; chunk very large batches
+    for m0 in range(0, maps, step):
+        m1 = min(maps, m0 + step)
+        rc = lib.rz_upsample_maps(_p(scores[m0:]), scores.stride(0), m1 - m0, g, H, W, ih, iw,
+                                  int(offset[0]), int(offset[1]), float(fill), mode,
+                                  float(threshold), _p(out[m0:]), _stream())
+        _lib.check(rc, "rz_upsample_maps")
+    return out
+
+
+# ----------------------------------------------------------------------------- K10
+def mpnce_partials(z: torch.Tensor, group_map: torch.Tensor, col0: int, inv_tau: float):
+    """Phase 1 of MP-NCE on the local column block.  Returns (rowsum, pos, colneg, colpos)."""
+    _need_cuda(z, group_map)
+    assert z.dtype == torch.float32 and z.dim() == 2 and z.stride(1) == 1
+    n, bl = z.shape
+    gm = _contig(group_map.to(torch.int64))
+    dev = z.device
+    rowsum = torch.empty(n, dtype=torch.float32, device=dev)
+    pos = torch.empty(n, dtype=torch.float32, device=dev)
+    colneg = torch.empty(bl, dtype=torch.float32, device=dev)
+    colpos = torch.empty(bl, dtype=torch.float32, device=dev)
+    scratch = torch.empty(2 * ((n + 31) // 32) * bl, dtype=torch.float32, device=dev)
+    rc = _lib.load().rz_mpnce_partials(_p(z), z.stride(0), n, bl, _p(gm), int(col0), float(inv_tau),
+                                       _p(rowsum), _p(pos), _p(colneg), _p(colpos), _p(scratch),
+                                       _stream())
+    _lib.check(rc, "rz_mpnce_partials")
+    return rowsum, pos, colneg, colpos
+
+
+def mpnce_finish(z: torch.Tensor, group_map: torch.Tensor, col0: int, b_global: int, inv_tau: float,
+                 rowsum, pos, colneg, colpos, *, eps: float = 1e-8, row_sum: bool = False,
+                 col_sum: bool = False, want_dz: bool = True):
+    """Phase 2: returns (loss_terms[4], dz or None) for the local column block."""
+    _need_cuda(z, group_map, rowsum, pos, colneg, colpos)
+    n, bl = z.shape
+    gm = _contig(group_map.to(torch.int64))
+    dev = z.device
+    dz = torch.empty_like(z) if want_dz else None
+    if dz is not None:
+        assert dz.stride(0) == z.stride(0)
+    terms = torch.empty(4, dtype=torch.float32, device=dev)
+    scratch = torch.empty(4 * n + 3 * bl + 2 * b_global, dtype=torch.float32, device=dev)
+    rc = _lib.load().rz_mpnce_finish(_p(z), z.stride(0), n, bl, int(b_global), _p(gm), int(col0),
+                                     float(inv_tau), float(eps), int(row_sum), int(col_sum),
+                                     _p(rowsum), _p(pos), _p(colneg), _p(colpos), _p(scratch),
+                                     _p(dz), _p(terms), _stream())
+    _lib.check(rc, "rz_mpnce_finish")
+    return terms, dz
+
+
+# ----------------------------------------------------------------------------- diagnostics
+def umma_probe(a_image: torch.Tensor, b_image: torch.Tensor, a_desc: int, b_desc: int,
+               a_step_bytes: int, b_step_bytes: int, k_steps: int, idesc: int,
+               d_tmem_offset: int = 0, ncols: int = 32) -> torch.Tensor:
+    """Run the tcgen05 probe; a_image / b_image are uint8 CUDA tensors (smem byte images)."""
+    _need_cuda(a_image, b_image)
+    out = torch.empty((128, ncols), dtype=torch.float32, device=a_image.device)
+    rc = _lib.load().rz_umma_probe(_p(a_image), a_image.numel(), _p(b_image), b_image.numel(),
+                                   C.c_ulonglong(a_desc), C.c_ulonglong(b_desc), a_step_bytes,
+                                   b_step_bytes, k_steps, C.c_uint(idesc), C.c_uint(d_tmem_offset),
+                                   ncols, _p(out), _stream())
+    _lib.check(rc, "rz_umma_probe")
+    return out

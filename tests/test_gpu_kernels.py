@@ -1,0 +1,152 @@
+"""Parity of the HBM-bound CUDA kernels (prep, upsample, MP-NCE) against the oracle and
+the golden fixtures frozen from the reference.  All calls go through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from radzero_b200 import _lib, ops, synthetic
+from tests.golden_util import T, case_inputs, golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+# ------------------------------------------------------------------------------- prep
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("rows,L,Lp", [(7, 7, 7), (3 * 50, 50, 64), (2 * 1370, 1370, 1408)])
+def test_prep_rows(dtype, rows, L, Lp):
+    tok, text, gamma, beta, _ = synthetic.make_inputs(rows // L, 1, tokens_per_image=L, seed=5)
+    x = tok.reshape(rows, 768).to(dtype)
+    f16, f32, st = ops.prep_rows(x.to(DEV), gamma.to(DEV), beta.to(DEV), rows_per_group=L,
+                                 rows_per_group_padded=Lp, want_f32=True, want_stats=True)
+    xd = x.double()
+    ln = oracle.layer_norm_rows(xd, gamma.double(), beta.double())
+    want = oracle.l2_normalize_rows(ln)
+    assert (f32.cpu().double() - want).abs().max() < 2e-6          # fp32 math on identical inputs
+    h = f16.cpu().view(rows // L, Lp, 768)
+    assert (h[:, :L].double().reshape(rows, 768) - want).abs().max() < 6e-4  # fp16 rounding of |v|<=1
+    if Lp > L:
+        assert h[:, L:].abs().max() == 0                            # padding rows are zero
+    mu = xd.mean(-1)
+    rstd = 1 / torch.sqrt(xd.var(-1, unbiased=False) + 1e-5)
+    assert (st[:, 0].cpu().double() - mu).abs().max() < 1e-5
+    assert ((st[:, 1].cpu().double() - rstd) / rstd).abs().max() < 1e-5
+    assert ((st[:, 2].cpu().double() * ln.norm(dim=-1)) - 1).abs().max() < 1e-5
+
+
+def test_prep_rows_no_layernorm_and_no_l2():
+    x = torch.randn(33, 768, generator=torch.Generator().manual_seed(1))
+    _, f32, _ = ops.prep_rows(x.to(DEV), None, None, want_f16=False, want_f32=True)
+    assert (f32.cpu() - oracle.l2_normalize_rows(x)).abs().max() < 2e-6
+    g, b = torch.rand(768) + 0.5, torch.rand(768) - 0.5
+    _, f32, _ = ops.prep_rows(x.to(DEV), g.to(DEV), b.to(DEV), want_f16=False, want_f32=True, l2=False)
+    assert (f32.cpu() - oracle.layer_norm_rows(x, g, b)).abs().max() < 2e-5
+
+
+def test_cpu_tensors_are_rejected():
+    with pytest.raises(_lib.RzError):
+        ops.prep_rows(torch.zeros(2, 768), None, None)
+
+
+# ------------------------------------------------------------------------------- upsample
+@pytest.mark.parametrize("key", ["s64x80", "s518", "s1024", "s300x417"])
+def test_upsample_golden(key):
+    grid = T("upsample.grid").to(DEV)
+    h, w, stride = [int(v) for v in golden()[f"upsample.{key}.size_stride"]]
+    m = ops.upsample_maps(grid.view(1, -1), (h, w))[0].cpu()
+    assert (m[::stride, ::stride] - T(f"upsample.{key}.map")).abs().max() < 2e-4
+    assert abs(m.double().sum().item() - float(golden()[f"upsample.{key}.sum"])) < 0.05
+    pt = ops.upsample_maps(grid.view(1, -1), (h, w), mode=_lib.RZ_UP_ARGMAX)[0].cpu().tolist()
+    assert pt == [int(v) for v in golden()[f"upsample.{key}.point"]]
+    mask = ops.upsample_maps(grid.view(1, -1), (h, w), mode=_lib.RZ_UP_MASK, threshold=0.7)[0].cpu()
+    want_mask = torch.sigmoid(oracle.interpolate_similarity_scores(grid.cpu(), (h, w))[0]) > 0.7
+    band = (torch.sigmoid(oracle.interpolate_similarity_scores(grid.cpu(), (h, w))[0]) - 0.7).abs() < 1e-4
+    assert ((mask.bool() != want_mask) & ~band).sum() == 0          # identical outside the fp-noise band
+    assert abs(int(mask.sum()) - int(golden()[f"upsample.{key}.mask_gt0p7_count"])) <= int(band.sum())
+
+
+@pytest.mark.parametrize("kind", ["blip", "aspect_blip", "bit", "m3ae"])
+@pytest.mark.parametrize("size", [(300, 417), (417, 300), (518, 518)])
+def test_upsample_processor_variants(kind, size):
+    from radzero_b200.inference import interpolate_params
+    g = torch.Generator().manual_seed(8)
+    scores = torch.randn(5, 1369, generator=g) * 4
+    kw = interpolate_params(size, kind)
+    out = ops.upsample_maps(scores.to(DEV), size, **kw).cpu()
+    sig = ops.upsample_maps(scores.to(DEV), size, mode=_lib.RZ_UP_SIGMOID, **kw).cpu()
+    pts = ops.upsample_maps(scores.to(DEV), size, mode=_lib.RZ_UP_ARGMAX, **kw).cpu()
+    for i in range(5):
+        want = oracle.interpolate_similarity_scores(scores[i], size, kind)[0]
+        assert (out[i] - want).abs().max() < 2e-4
+        assert (sig[i] - torch.sigmoid(want)).abs().max() < 1e-4
+        x, y = pts[i].tolist()
+        assert want[y, x] >= want.max() - 2e-4
+
+
+def test_upsample_constant_and_strided_input():
+    s = torch.full((3, 1369), 2.5, device=DEV)
+    assert (ops.upsample_maps(s, (100, 333)) - 2.5).abs().max() < 1e-6
+    big = torch.randn(4, 6, 1370, device=DEV)
+    view = big[:, :, 1:].reshape(24, 1369)      # what compute_logits hands over (CLS dropped)
+    out = ops.upsample_maps(view, (74, 74)).cpu()
+    want = oracle.bilinear_upsample(view.cpu().view(24, 37, 37), 74, 74)
+    assert (out - want).abs().max() < 1e-4
+
+
+# ------------------------------------------------------------------------------- MP-NCE
+def _mpnce_cuda(z, gm, tau, b_global=None, col0=0, row_sum=False, col_sum=False):
+    b_global = b_global or z.shape[1]
+    rs, ps, cn, cp = ops.mpnce_partials(z, gm, col0, 1.0 / tau)
+    terms, dz = ops.mpnce_finish(z, gm, col0, b_global, 1.0 / tau, rs, ps, cn, cp,
+                                 row_sum=row_sum, col_sum=col_sum)
+    return terms, dz, (rs, ps, cn, cp)
+
+
+@pytest.mark.parametrize("rs,cs", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_mpnce_golden(rs, cs):
+    z = T("mpnce.z").to(DEV)
+    gm = T("mpnce.group_map").to(DEV)
+    terms, dz, _ = _mpnce_cuda(z, gm, 0.07, row_sum=bool(rs), col_sum=bool(cs))
+    n, b = z.shape
+    loss = (terms[0] / (b if rs else n) + terms[1] / (b if cs else n)) / 2
+    want = float(golden()[f"mpnce.loss_r{rs}c{cs}"])
+    assert abs(loss.item() - want) < 1e-3 * abs(want)
+    ref_dz = T(f"mpnce.dz_r{rs}c{cs}")
+    assert (dz.cpu() - ref_dz).abs().max() < 1e-3 * ref_dz.abs().max()
+
+
+@pytest.mark.parametrize("n,b", [(45, 8), (700, 300), (6144, 1024)])
+def test_mpnce_vs_oracle_and_sharded(n, b):
+    g = torch.Generator().manual_seed(n)
+    counts = torch.randint(1, 2 * n // b + 1, (b,), generator=g)
+    gm = torch.repeat_interleave(torch.arange(b), counts)[:n]
+    gm = torch.cat([gm, torch.full((n - gm.numel(),), b - 1)]) if gm.numel() < n else gm
+    z = (torch.rand(n, b, generator=g) * 2 - 1)
+    z[torch.arange(n), gm] += 0.5
+    z.clamp_(-1, 1)
+    zd = z.double().requires_grad_(True)
+    want = oracle.multi_positive_nce_loss(zd, gm, temperature=0.07)
+    want.backward()
+    terms, dz, _ = _mpnce_cuda(z.to(DEV), gm.to(DEV), 0.07)
+    loss = (terms[0] + terms[1]) / (2 * n)
+    assert abs(loss.item() - want.item()) < 1e-4 * abs(want.item())
+    assert (dz.cpu().double() - zd.grad).abs().max() < 1e-4 * zd.grad.abs().max()
+    # d loss / d log(tau) = -sum dZ*Z
+    assert abs(terms[2].item() - float((zd.grad * zd.detach()).sum())) < 1e-3 * abs(float((zd.grad * zd.detach()).sum())) + 1e-6
+    # image-sharded evaluation (emulating W ranks on one GPU): all-reduce = plain sum
+    W = 4 if b % 4 == 0 else 1
+    if W > 1:
+        bl = b // W
+        zc = z.to(DEV)
+        parts = [ops.mpnce_partials(zc[:, r * bl:(r + 1) * bl].contiguous(), gm.to(DEV), r * bl, 1 / 0.07)
+                 for r in range(W)]
+        rowsum = sum(p[0] for p in parts)
+        pos = sum(p[1] for p in parts)
+        tot = torch.zeros(4, device=DEV)
+        for r in range(W):
+            zr = zc[:, r * bl:(r + 1) * bl].contiguous()
+            t, dzr = ops.mpnce_finish(zr, gm.to(DEV), r * bl, b, 1 / 0.07, rowsum, pos, parts[r][2], parts[r][3])
+            tot += t
+            assert (dzr.cpu().double() - zd.grad[:, r * bl:(r + 1) * bl]).abs().max() < 1e-4 * zd.grad.abs().max()
+        assert abs(((tot[0] + tot[1]) / (2 * n)).item() - want.item()) < 1e-4 * abs(want.item())
