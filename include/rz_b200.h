@@ -63,6 +63,33 @@ int rz_prep_rows(const void* x, int dtype, const float* gamma, const float* beta
                  long long rows, int rows_per_group, int rows_per_group_padded,
                  void* out_f16, float* out_f32, float* stats, int l2, void* stream);
 
+/* ---- K3-K6: fused similarity GEMM + softmax pooling + pooled logit (tcgen05 / TMA) ------
+ * Replaces SimilarityLogit.forward (exp/cxr_pt/model/losses.py:187-240: bmm :219-221,
+ * softmax :222, matmul :224, normalize + batched dot :226-233) and the CLS drop / transpose
+ * of CxrAlignModel.compute_logits (exp/cxr_pt/model/modeling.py:311-328).  The (B,N,L)
+ * probability tensor and the (B,N,768) expanded query of the reference are never formed.
+ *   k_f16   [n_images, tokens_padded, 768] fp16 rows from rz_prep_rows (padding rows zero);
+ *           tokens_padded is a multiple of 64
+ *   q_f16   [n_text, 768] fp16 rows from rz_prep_rows
+ *   scale   1/tau for sim_op "cos" (losses.py:221), 1/sqrt(768) for "dot" (:215)
+ *   q_inv_norm optional fp32 [n_text]: Z is multiplied by it (sim_op "dot": 1/|q|, the
+ *           F.normalize(query) of losses.py:226; NULL for "cos" where |q| = 1)
+ *   scores  optional fp32: scores[b*stride_image + n*stride_text + (l - drop_cls)] =
+ *           scale * <k_bl, q_n> for tokens l >= drop_cls (drop_cls = 1 removes CLS as
+ *           modeling.py:316-317 does); CLS still takes part in the softmax
+ *   z       optional fp32: z[n*stride_text + b*stride_image] = <q_n, o_bn/|o_bn|>
+ *           (t2i_logits is stride_text = B, stride_image = 1; logits^T of compute_logits the
+ *           transpose)
+ *   lse / onorm optional fp32 [n_images, n_text]: log-sum-exp of the scores over tokens and
+ *           |o| of the softmax-weighted token mean -- kept for the backward pass
+ *   pooled_f16 optional fp16 [n_images, n_text, 768]: o_bn, kept for the backward pass
+ */
+int rz_sim_fwd(const void* k_f16, int n_images, int tokens, int tokens_padded,
+               const void* q_f16, int n_text, float scale, const float* q_inv_norm,
+               float* scores, long long scores_stride_image, long long scores_stride_text,
+               int drop_cls, float* z, long long z_stride_text, long long z_stride_image,
+               float* lse, float* onorm, void* pooled_f16, void* stream);
+
 /* ---- K8+K9: bilinear upsample of patch-grid similarity maps ----------------------------
  * Replaces F.interpolate(mode="bilinear", align_corners=False) in
  * interpolate_similarity_scores (exp/cxr_pt/inference/segmentation_utils.py:36-122) and

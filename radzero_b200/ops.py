@@ -63,6 +63,55 @@ def prep_rows(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[tor
     return f16, f32, st
 
 
+# ----------------------------------------------------------------------------- K3 - K6
+TOKEN_TILE = 64
+
+
+def padded_tokens(tokens: int) -> int:
+    return (tokens + TOKEN_TILE - 1) // TOKEN_TILE * TOKEN_TILE
+
+
+def sim_fwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, scale: float, *,
+            want_scores: bool = False, drop_cls: bool = True, want_z: bool = True,
+            want_stats: bool = False, want_pooled: bool = False,
+            q_inv_norm: Optional[torch.Tensor] = None, z_out: Optional[torch.Tensor] = None):
+    """Fused similarity forward.  k_f16 (B, Lp, 768) fp16, q_f16 (N, 768) fp16.
+
+    Returns dict(scores (B, N, L - drop) | None, z (N, B) | None, lse, onorm (B, N) | None,
+    pooled (B, N, 768) fp16 | None).  ``z_out`` lets the caller place Z directly into a
+    column block of a larger (N, ld) matrix.
+    """
+    _need_cuda(k_f16, q_f16, q_inv_norm, z_out)
+    if k_f16.dtype != torch.float16 or q_f16.dtype != torch.float16:
+        raise RzError("sim_fwd operands must be fp16 rows from prep_rows")
+    if k_f16.dim() != 3 or k_f16.shape[-1] != HIDDEN or not k_f16.is_contiguous():
+        raise RzError("k_f16 must be contiguous (B, Lp, 768)")
+    if q_f16.dim() != 2 or q_f16.shape[-1] != HIDDEN or not q_f16.is_contiguous():
+        raise RzError("q_f16 must be contiguous (N, 768)")
+    B, Lp, _ = k_f16.shape
+    N = q_f16.shape[0]
+    dev = k_f16.device
+    drop = 1 if drop_cls else 0
+    scores = torch.empty((B, N, tokens - drop), dtype=torch.float32, device=dev) if want_scores else None
+    z = None
+    if want_z:
+        z = z_out if z_out is not None else torch.empty((N, B), dtype=torch.float32, device=dev)
+        if z.dtype != torch.float32 or z.shape != (N, B):
+            raise RzError("z_out must be fp32 (N, B)")
+    lse = torch.empty((B, N), dtype=torch.float32, device=dev) if want_stats else None
+    onorm = torch.empty((B, N), dtype=torch.float32, device=dev) if want_stats else None
+    pooled = torch.empty((B, N, HIDDEN), dtype=torch.float16, device=dev) if want_pooled else None
+    qin = _contig(q_inv_norm.float()) if q_inv_norm is not None else None
+    rc = _lib.load().rz_sim_fwd(
+        _p(k_f16), B, int(tokens), Lp, _p(q_f16), N, float(scale), _p(qin),
+        _p(scores), scores.stride(0) if scores is not None else 0,
+        scores.stride(1) if scores is not None else 0, drop,
+        _p(z), z.stride(0) if z is not None else 0, z.stride(1) if z is not None else 0,
+        _p(lse), _p(onorm), _p(pooled), _stream())
+    _lib.check(rc, "rz_sim_fwd")
+    return dict(scores=scores, z=z, lse=lse, onorm=onorm, pooled=pooled)
+
+
 # ----------------------------------------------------------------------------- K8 + K9
 def upsample_maps(scores: torch.Tensor, out_hw: Tuple[int, int], *, mode: int = _lib.RZ_UP_RAW,
                   interp_hw: Optional[Tuple[int, int]] = None, offset: Tuple[int, int] = (0, 0),

@@ -1,0 +1,140 @@
+"""Parity of the fused tcgen05 similarity forward (rz_sim_fwd) against the oracle and the
+golden fixtures frozen from the reference.  Tolerances are BASELINE.json's: 2e-3 abs on
+cosine similarities / maps (at the 1/tau scale the reference emits), 1e-3 relative on
+similarity_prob; identical argmax labels."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from radzero_b200 import ops, synthetic
+from tests.golden_util import T, case_inputs, golden, split
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TAU = math.exp(math.log(0.07))
+
+
+def _run(tok, text, gamma, beta, scale=1.0 / TAU, **kw):
+    B, L, _ = tok.shape
+    Lp = ops.padded_tokens(L)
+    g = gamma.to(DEV) if gamma is not None else None
+    b = beta.to(DEV) if beta is not None else None
+    k16, _, _ = ops.prep_rows(tok.to(DEV), g, b, rows_per_group=L, rows_per_group_padded=Lp)
+    q16, _, _ = ops.prep_rows(text.to(DEV), g, b)
+    return ops.sim_fwd(k16.view(B, Lp, 768), q16, L, scale, **kw)
+
+
+def _oracle(tok, text, gamma, beta, tau=TAU):
+    tn = oracle.layer_norm_rows(text.double(), gamma.double(), beta.double())
+    xn = oracle.layer_norm_rows(tok.double(), gamma.double(), beta.double())
+    z, sc = oracle.similarity_logit(tn, xn, temperature=tau, need_scores=True, squeeze_quirk=False)
+    q = oracle.l2_normalize_rows(tn)
+    k = oracle.l2_normalize_rows(xn)
+    s = sc[0]
+    p = torch.softmax(s, dim=-1)
+    o = torch.einsum("bnl,bld->bnd", p, k)
+    return dict(z=z, scores=s, lse=torch.logsumexp(s, dim=-1), onorm=o.norm(dim=-1), pooled=o)
+
+
+@pytest.mark.parametrize("B,N,L", [(2, 3, 1370), (3, 14, 1370), (2, 16, 50), (1, 1, 130),
+                                   (2, 20, 200), (2, 40, 1370), (1, 64, 64), (2, 130, 333)])
+def test_sim_fwd_vs_oracle(B, N, L):
+    tok, text, gamma, beta, _ = synthetic.make_inputs(B, N, tokens_per_image=L, seed=100 + N)
+    out = _run(tok, text, gamma, beta, want_scores=True, drop_cls=True, want_stats=True,
+               want_pooled=True)
+    torch.cuda.synchronize()
+    want = _oracle(tok, text, gamma, beta)
+    sc = out["scores"].cpu().double()
+    assert sc.shape == (B, N, L - 1)
+    assert (sc - want["scores"][:, :, 1:]).abs().max() < 2e-3
+    z = out["z"].cpu().double()
+    assert z.shape == (N, B)
+    assert (z - want["z"]).abs().max() < 2e-4
+    assert (out["lse"].cpu().double() - want["lse"]).abs().max() < 2e-3
+    assert ((out["onorm"].cpu().double() - want["onorm"]) / want["onorm"]).abs().max() < 1e-3
+    assert (out["pooled"].cpu().double() - want["pooled"]).abs().max() < 2e-3
+    # similarity_prob = sigmoid(Z / tau): 1e-3 relative
+    pr = torch.sigmoid(z.T / TAU)
+    pw = torch.sigmoid(want["z"].T / TAU)
+    assert ((pr - pw) / pw).abs().max() < 1e-3
+    if N > 1:
+        assert torch.equal(pr.argmax(1), pw.argmax(1))
+
+
+def test_sim_fwd_keep_cls_and_z_only():
+    tok, text, gamma, beta, _ = synthetic.make_inputs(2, 5, tokens_per_image=70, seed=3)
+    out = _run(tok, text, gamma, beta, want_scores=True, drop_cls=False)
+    want = _oracle(tok, text, gamma, beta)
+    assert out["scores"].shape == (2, 5, 70)
+    assert (out["scores"].cpu().double() - want["scores"]).abs().max() < 2e-3
+    out2 = _run(tok, text, gamma, beta)
+    assert out2["scores"] is None and out2["lse"] is None
+    assert (out2["z"].cpu().double() - want["z"]).abs().max() < 2e-4
+
+
+def test_sim_fwd_lazy_rescale_path():
+    """Scores that keep growing along the token axis force the running maximum (and the
+    pooled accumulator rescale) to fire on many tiles."""
+    B, N, L = 2, 6, 700
+    tok, text, gamma, beta, _ = synthetic.make_inputs(B, N, tokens_per_image=L, seed=77)
+    g = torch.ones(768)
+    bta = torch.zeros(768)
+    ramp = torch.linspace(-1.0, 3.0, L).view(1, L, 1)
+    tok = tok + ramp * text[:1].view(1, 1, 768)          # similarity to prompt 0 rises with l
+    tok[:, :, :] = tok - tok.mean(-1, keepdim=True)
+    out = _run(tok, text, g, bta, want_scores=True, want_stats=True)
+    want = _oracle(tok, text, g, bta)
+    assert (out["scores"].cpu().double() - want["scores"][:, :, 1:]).abs().max() < 2e-3
+    assert (out["z"].cpu().double() - want["z"]).abs().max() < 2e-4
+    assert (out["lse"].cpu().double() - want["lse"]).abs().max() < 2e-3
+
+
+def test_sim_fwd_negated_queries_low_scores():
+    """All cosines strongly negative: a fixed-shift softmax would underflow fp16 here."""
+    B, N, L = 1, 4, 300
+    tok, text, gamma, beta, _ = synthetic.make_inputs(B, N, tokens_per_image=L, seed=5)
+    g, bta = torch.ones(768), torch.zeros(768)
+    tok = tok * 0.05 + text[0].view(1, 1, 768)           # every token ~ parallel to prompt 0
+    text = -text                                          # ... and prompt 0 points the other way
+    out = _run(tok, text, g, bta, want_stats=True)
+    want = _oracle(tok, text, g, bta)
+    assert (out["z"].cpu().double() - want["z"]).abs().max() < 2e-4
+    assert (out["lse"].cpu().double() - want["lse"]).abs().max() < 2e-3
+
+
+@pytest.mark.parametrize("name", ["full", "cls14"])
+def test_sim_fwd_golden(name):
+    """Against tensors frozen from the reference's own RadZeroLoss.forward (fp64)."""
+    tok, text, gamma, beta, log_tau, counts = case_inputs(name)
+    tau = float(torch.exp(log_tau))
+    out = _run(tok, text, gamma, beta, scale=1.0 / tau, want_scores=True, drop_cls=False)
+    z_ref = T(f"{name}.t2i_logits").double()
+    assert (out["z"].cpu().double() - z_ref).abs().max() < 2e-4
+    s_ref = T(f"{name}.scores_stride7").double()
+    assert (out["scores"].cpu().double()[:, :, ::7] - s_ref).abs().max() < 2e-3
+    logits = out["z"].T.cpu().double() / tau
+    l_ref = T(f"{name}.logits").double()
+    pr, pw = torch.sigmoid(logits), torch.sigmoid(l_ref)
+    assert ((pr - pw) / pw).abs().max() < 1e-3
+    assert torch.equal(logits.argmax(1), l_ref.argmax(1))
+
+
+def test_sim_fwd_dot_mode():
+    """sim_op='dot' (the RadZeroLoss constructor default, losses.py:45, 214-215)."""
+    B, N, L = 2, 7, 150
+    tok, text, gamma, beta, _ = synthetic.make_inputs(B, N, tokens_per_image=L, seed=9)
+    Lp = ops.padded_tokens(L)
+    k16, _, _ = ops.prep_rows(tok.to(DEV), gamma.to(DEV), beta.to(DEV), rows_per_group=L,
+                              rows_per_group_padded=Lp, l2=False)
+    q16, q32, _ = ops.prep_rows(text.to(DEV), gamma.to(DEV), beta.to(DEV), l2=False, want_f32=True)
+    qin = 1.0 / q16.float().norm(dim=-1)
+    out = ops.sim_fwd(k16.view(B, Lp, 768), q16, L, 1.0 / math.sqrt(768), q_inv_norm=qin,
+                      want_scores=True, drop_cls=False)
+    tn = oracle.layer_norm_rows(text.double(), gamma.double(), beta.double())
+    xn = oracle.layer_norm_rows(tok.double(), gamma.double(), beta.double())
+    z, sc = oracle.similarity_logit(tn, xn, sim_op="dot", need_scores=True, squeeze_quirk=False)
+    assert (out["scores"].cpu().double() - sc[0]).abs().max() < 2e-2   # |s| ~ 30: fp16 operand rounding
+    assert (out["z"].cpu().double() - z).abs().max() < 3e-4
