@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the VL-CABS similarity path (BASELINE.json metric: similarity maps/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cls|seg|openvocab|contrastive]
+    python bench.py --impl reference ...        # the CPU path (oracle port) on the host cores
+
+One "step" = one pass of the hot path over one batch of synthetic input.  Default workload
+(N = 1): BASELINE.json configs[1] -- zero-shot classification, 256 images x 14 prompts,
+similarity_prob only.  Prints ONE JSON line (see the driver contract in the task statement):
+  value      whole-job maps/s with inputs resident in HBM, CUDA events, max over ranks
+  e2e        same metric through the public API with pinned HOST buffers (H2D + D2H timed)
+  roofline   the dominant kernel's algorithmic bytes (or FLOPs) / its CUDA-event duration
+  cpu_baseline  the oracle port timed on a bounded sample on the host cores (rank 0, N=1)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+L, D, GRID = 1370, 768, 37
+WORKLOADS = {
+    # name: (B, N, description)
+    "cls": (256, 14, "C2 zero-shot classification 256 images x 14 prompts, similarity_prob only"),
+    "seg": (64, 8, "C3 grounding/segmentation 64 images x 8 prompts, 518x518 pixel similarity_map"),
+    "openvocab": (128, 1024, "C5 open-vocabulary sweep 128 images x 1024 prompts, patch-grid scores + prob"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"],
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_setup(n_gpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return world, rank, local
+
+
+def make_loss_fn(dev, gamma, beta):
+    from radzero_b200 import losses
+    fn = losses.RadZeroLoss(sim_op="cos").to(dev)
+    with torch.no_grad():
+        fn.layer_norm.weight.copy_(gamma)
+        fn.layer_norm.bias.copy_(beta)
+    return fn
+
+
+# ------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    from radzero_b200 import _lib, inference, ops, synthetic
+    world, rank, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    pk = peaks()
+    if args.workload == "contrastive":
+        from radzero_b200 import bench_contrastive
+        return bench_contrastive.run(args, world, rank, local, pk)
+    B, N, desc = WORKLOADS[args.workload]
+    tok, text, gamma, beta, log_tau = synthetic.make_inputs(B, N, seed=42 + rank, device=dev)
+    fn = make_loss_fn(dev, gamma, beta)
+    out_hw = (518, 518)
+
+    def step(tokens, txt):
+        if args.workload == "cls":
+            return fn.similarity_prob(txt, tokens)
+        logits, scores, _ = fn.similarity(txt, tokens, want_scores=True)
+        if args.workload == "seg":
+            return inference.interpolate_similarity_scores(scores.reshape(-1, scores.shape[-1]), out_hw,
+                                                           "blip", mode="sigmoid")
+        return scores
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        res = step(tok, text)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        res = step(tok, text)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    maps_per_step = B * N * world
+    value = maps_per_step / (ms_per_step * 1e-3)
+
+    # ---- per-kernel timing (instrumented pass over the same steps) for the roofline
+    Lp = ops.padded_tokens(L)
+    fused = ops.USE_FUSED_PREP and N <= ops.FUSED_PREP_MAX_TEXT
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    acc = [0.0] * 4
+    g, bta = fn.layer_norm.weight.detach(), fn.layer_norm.bias.detach()
+    lt = fn.loss_temperature
+    zkw = dict(z_sigmoid=True, z_image_major=True, log_tau_z=lt, log_tau_scale=lt)
+    want_scores = args.workload != "cls"
+    for i_step in range(args.steps + 2):                     # first two iterations are warm-up
+        evs[0].record()
+        k16 = None
+        if not fused:
+            k16, _, _ = ops.prep_rows(tok, g, bta, rows_per_group=L, rows_per_group_padded=Lp)
+        evs[1].record()
+        q16, _, _ = ops.prep_rows(text, g, bta)
+        evs[2].record()
+        if fused:
+            o = ops.sim_fwd_tokens(tok, g, bta, q16, 1.0, want_scores=want_scores, **zkw)
+        else:
+            o = ops.sim_fwd(k16.view(B, Lp, D), q16, L, 1.0, want_scores=want_scores, **zkw)
+        evs[3].record()
+        if args.workload == "seg":
+            inference.interpolate_similarity_scores(o["scores"].reshape(-1, GRID * GRID), out_hw, "blip",
+                                                    mode="sigmoid")
+        evs[4].record()
+        torch.cuda.synchronize()
+        if i_step >= 2:
+            for i in range(4):
+                acc[i] += evs[i].elapsed_time(evs[i + 1])
+        del o, k16
+    kt = [a / args.steps for a in acc]
+    out_bytes = {"cls": B * N * 4, "seg": B * N * out_hw[0] * out_hw[1] * 4,
+                 "openvocab": B * N * (L - 1) * 4 + B * N * 4}[args.workload]
+    score_bytes = B * N * (L - 1) * 4 if want_scores else 0
+    flops = 2.0 * 2.0 * B * N * L * D          # scores + pooling GEMM
+    if fused:
+        sim_name = "sim_fwd_kernel<16,2,0,8,float> (raw tokens: LN+L2+GEMM+softmax pool, fused)"
+        sim_bytes = B * L * D * 4 + N * D * 2 + score_bytes + B * N * 4
+    else:
+        sim_name = ("sim_fwd_kernel<16,2,0,0>" if N <= 16 else "sim_fwd_kernel<64,1,0,0>") + \
+            " (fp16 operands via TMA: GEMM + softmax pool)"
+        sim_bytes = B * Lp * D * 2 + N * D * 2 + score_bytes + B * N * 4
+    kernels = [
+        ("prep_rows_kernel<float> (tokens: LN+L2 -> fp16)", B * L * D * 4 + B * Lp * D * 2, kt[0], "hbm"),
+        ("prep_rows_kernel<float> (text)", N * D * 6, kt[1], "hbm"),
+        (sim_name, sim_bytes, kt[2], None),
+        ("upsample_kernel<SIGMOID>", B * N * (GRID * GRID * 4 + out_hw[0] * out_hw[1] * 4), kt[3], "hbm"),
+    ]
+    dom = max(range(4), key=lambda i: kt[i])
+    name, nbytes, t_ms, bound = kernels[dom]
+    ridge = pk["tf_sust"] * 1e12 / (pk["hbm"] * 1e9)
+    if dom == 2 and flops / sim_bytes > ridge:
+        ach = flops / (t_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": pk["tf_burst"],
+                "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": None,
+                "peak_source": pk["src"] + " burst (kernel timed alone)"}
+    else:
+        ach = nbytes / (t_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"]}
+    roof["algorithmic_bytes_per_launch"] = nbytes
+    roof["kernel_ms"] = {k[0]: round(t, 4) for k, t in zip(kernels, kt) if t > 0.0005}
+    # whole-step figure: algorithmic bytes of the PATH (tokens read once + outputs) / step time
+    alg_step = B * L * D * 4 + N * D * 4 + out_bytes
+    roof["step_algorithmic_bytes"] = alg_step
+    roof["step_frac_of_hbm"] = alg_step / (ms_per_step * 1e-3) / 1e9 / pk["hbm"]
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get(args.workload, {}).get(name.split("<")[0])
+        except Exception:
+            pass
+
+    # ---- end to end through the public API with HOST buffers
+    e2e = None
+    if rank == 0 or world > 1:
+        h_tok = tok.cpu().pin_memory()
+        h_txt = text.cpu().pin_memory()
+        ksteps = max(2, min(args.steps, 5))
+        for _ in range(2):
+            r = step(h_tok.to(dev, non_blocking=True), h_txt.to(dev, non_blocking=True)).cpu()
+        barrier()
+        e0.record()
+        for _ in range(ksteps):
+            r = step(h_tok.to(dev, non_blocking=True), h_txt.to(dev, non_blocking=True))
+            r_host = r.to("cpu", non_blocking=False)
+        e1.record()
+        barrier()
+        ms2 = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms2], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms2 = float(t.item())
+        e2e = {"value": maps_per_step / (ms2 / ksteps * 1e-3), "unit": "maps/s",
+               "h2d_bytes_per_step": (h_tok.numel() + h_txt.numel()) * 4,
+               "d2h_bytes_per_step": r_host.numel() * r_host.element_size(), "steps": ksteps,
+               "api": "RadZeroLoss.similarity_prob" if args.workload == "cls" else "RadZeroLoss.similarity"}
+
+    cpu = cpu_baseline(args.workload, steps=1) if (rank == 0 and world == 1 and not args.no_cpu) else None
+    if rank == 0:
+        line = {
+            "metric": "similarity maps/sec", "value": value, "unit": "maps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic", "impl": "ours",
+            "config": {"workload": desc, "images_per_gpu": B, "prompts": N, "tokens": L, "hidden": D,
+                       "input_dtype": "fp32", "l2": "inputs (1.08 GB/GPU at cls) larger than L2; no flush",
+                       "parallelism": f"images sharded x{world}, no collective"},
+            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------- CPU arm
+def cpu_sample(workload: str):
+    """(B_sample, N) of the bounded CPU sample: same prompts, fewer images."""
+    B, N, _ = WORKLOADS[workload]
+    return {"cls": 16, "seg": 8, "openvocab": 2}[workload], N
+
+
+def cpu_step(workload, tok, text, gamma, beta, log_tau):
+    import oracle
+    ref = oracle.radzero_forward([text[i:i + 1] for i in range(text.shape[0])], tok, gamma, beta, log_tau,
+                                 need_attn_weights=True, compute_loss=False, squeeze_quirk=False)
+    glue = oracle.compute_logits_glue(ref["t2i_logits"], ref["t2i_attn_weights"][0], log_tau)
+    prob = torch.sigmoid(glue["logits"])
+    if workload == "seg":
+        s = glue["similarity_scores"]
+        maps = [torch.sigmoid(oracle.interpolate_similarity_scores(s[b, n], (518, 518)))
+                for b in range(s.shape[0]) for n in range(s.shape[1])]
+        return prob, maps
+    return prob, glue["similarity_scores"]
+
+
+def cpu_baseline(workload: str, steps: int = 1, warmup: int = 1):
+    from radzero_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs, N = cpu_sample(workload)
+    tok, text, gamma, beta, log_tau = synthetic.make_inputs(Bs, N, seed=42)
+    with torch.no_grad():
+        for _ in range(warmup):
+            cpu_step(workload, tok, text, gamma, beta, log_tau)
+        best = float("inf")
+        for _ in range(max(steps, 1)):
+            t0 = time.perf_counter()
+            cpu_step(workload, tok, text, gamma, beta, log_tau)
+            best = min(best, time.perf_counter() - t0)
+    return {"value": Bs * N / best, "unit": "maps/s", "cores": cores, "kind": "port",
+            "sample": f"{Bs} images x {N} prompts of the same workload, fp32 torch CPU oracle "
+                      f"(oracle/vlcabs.py), best of {max(steps, 1)}, {best * 1e3:.1f} ms"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if args.workload == "contrastive":
+        from radzero_b200 import bench_contrastive
+        return bench_contrastive.run_reference(args)
+    from radzero_b200 import synthetic
+    B, N, desc = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs, _ = cpu_sample(args.workload)
+    tok, text, gamma, beta, log_tau = synthetic.make_inputs(Bs, N, seed=42)
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 3))):
+            cpu_step(args.workload, tok, text, gamma, beta, log_tau)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_step(args.workload, tok, text, gamma, beta, log_tau)
+        dt = time.perf_counter() - t0
+    value = Bs * N * args.steps / dt
+    cpu = {"value": value, "unit": "maps/s", "cores": cores, "kind": "port",
+           "sample": f"each step = {Bs} images x {N} prompts (bounded sample of {B} x {N}), fp32 torch CPU "
+                     "oracle restating the reference's losses.py + compute_logits"}
+    print(json.dumps({
+        "metric": "similarity maps/sec", "value": value, "unit": "maps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": desc, "images_per_gpu": B, "prompts": N, "tokens": L, "hidden": D},
+        "cpu_baseline": cpu,
+        "e2e": {"value": value, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cls", choices=list(WORKLOADS) + ["contrastive"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); "
+                         "use --impl reference for the CPU arm")
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

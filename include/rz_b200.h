@@ -71,24 +71,48 @@ int rz_prep_rows(const void* x, int dtype, const float* gamma, const float* beta
  *   k_f16   [n_images, tokens_padded, 768] fp16 rows from rz_prep_rows (padding rows zero);
  *           tokens_padded is a multiple of 64
  *   q_f16   [n_text, 768] fp16 rows from rz_prep_rows
- *   scale   1/tau for sim_op "cos" (losses.py:221), 1/sqrt(768) for "dot" (:215)
+ *   scale   1/tau for sim_op "cos" (losses.py:221), 1/sqrt(768) for "dot" (:215);
+ *   log_tau_scale optional DEVICE scalar: when given, scale = exp(-*log_tau_scale) is computed
+ *           on the device from the learnable log-temperature (losses.py:54-62, 177-181), so no
+ *           host synchronisation is needed to read the parameter
  *   q_inv_norm optional fp32 [n_text]: Z is multiplied by it (sim_op "dot": 1/|q|, the
  *           F.normalize(query) of losses.py:226; NULL for "cos" where |q| = 1)
  *   scores  optional fp32: scores[b*stride_image + n*stride_text + (l - drop_cls)] =
  *           scale * <k_bl, q_n> for tokens l >= drop_cls (drop_cls = 1 removes CLS as
  *           modeling.py:316-317 does); CLS still takes part in the softmax
- *   z       optional fp32: z[n*stride_text + b*stride_image] = <q_n, o_bn/|o_bn|>
- *           (t2i_logits is stride_text = B, stride_image = 1; logits^T of compute_logits the
- *           transpose)
+ *   z       optional fp32: z[n*stride_text + b*stride_image] = f(z_scale * <q_n, o_bn/|o_bn|>)
+ *           with f = identity (z_sigmoid = 0) or the logistic sigmoid (z_sigmoid = 1);
+ *           log_tau_z (optional DEVICE scalar) overrides z_scale with exp(-*log_tau_z).
+ *           t2i_logits is stride_text = B, stride_image = 1, z_scale = 1; the `logits` of
+ *           compute_logits (modeling.py:324-328) is the transpose with z_scale = 1/tau, and
+ *           similarity_prob the same with z_sigmoid = 1.
  *   lse / onorm optional fp32 [n_images, n_text]: log-sum-exp of the scores over tokens and
  *           |o| of the softmax-weighted token mean -- kept for the backward pass
  *   pooled_f16 optional fp16 [n_images, n_text, 768]: o_bn, kept for the backward pass
  */
 int rz_sim_fwd(const void* k_f16, int n_images, int tokens, int tokens_padded,
-               const void* q_f16, int n_text, float scale, const float* q_inv_norm,
-               float* scores, long long scores_stride_image, long long scores_stride_text,
-               int drop_cls, float* z, long long z_stride_text, long long z_stride_image,
+               const void* q_f16, int n_text, float scale, const float* log_tau_scale,
+               const float* q_inv_norm, float* scores, long long scores_stride_image,
+               long long scores_stride_text, int drop_cls, float* z, long long z_stride_text,
+               long long z_stride_image, float z_scale, const float* log_tau_z, int z_sigmoid,
                float* lse, float* onorm, void* pooled_f16, void* stream);
+
+/* Same computation for small prompt sets (n_text <= 16: zero-shot classification, grounding),
+ * reading the RAW vision tokens: LayerNorm (losses.py:90-91) + L2 normalisation (:213) of each
+ * token row happen in registers of dedicated loader warps which write the fp16 operand tile
+ * straight into shared memory, so the tokens cross HBM exactly once and no fp16 copy is
+ * written.  HBM-bound; this is the kernel behind compute_logits / model_inference.
+ *   tokens_raw [n_images, tokens, 768] of `dtype` (RZ_F32 / RZ_BF16 / RZ_F16), contiguous
+ *   gamma/beta fp32 [768] or both NULL; l2 as in rz_prep_rows
+ *   q_f16      [n_text, 768] fp16 rows from rz_prep_rows (the prompts are tiny: 14 x 768)
+ * Returns RZ_ERR_UNSUPPORTED for n_text > 16 (use rz_prep_rows + rz_sim_fwd).
+ */
+int rz_sim_fwd_tokens(const void* tokens_raw, int dtype, const float* gamma, const float* beta,
+                      int l2, int n_images, int tokens, const void* q_f16, int n_text,
+                      float scale, const float* log_tau_scale, const float* q_inv_norm,
+                      float* scores, long long scores_stride_image, long long scores_stride_text,
+                      int drop_cls, float* z, long long z_stride_text, long long z_stride_image,
+                      float z_scale, const float* log_tau_z, int z_sigmoid, void* stream);
 
 /* ---- K8+K9: bilinear upsample of patch-grid similarity maps ----------------------------
  * Replaces F.interpolate(mode="bilinear", align_corners=False) in

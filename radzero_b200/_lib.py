@@ -29,8 +29,10 @@ SIGNATURES: Dict[str, tuple] = {
     "rz_launch_count": (_ll, []),
     "rz_device_sm_count": (_i, []),
     "rz_prep_rows": (_i, [_vp, _i, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _i, _vp]),
-    "rz_sim_fwd": (_i, [_vp, _i, _i, _i, _vp, _i, _f, _vp, _vp, _ll, _ll, _i, _vp, _ll, _ll,
-                        _vp, _vp, _vp, _vp]),
+    "rz_sim_fwd": (_i, [_vp, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _ll, _ll, _i, _vp, _ll, _ll,
+                        _f, _vp, _i, _vp, _vp, _vp, _vp]),
+    "rz_sim_fwd_tokens": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _ll, _ll,
+                               _i, _vp, _ll, _ll, _f, _vp, _i, _vp]),
     "rz_upsample_maps": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _f, _vp, _vp]),
     "rz_mpnce_partials": (_i, [_vp, _ll, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rz_mpnce_finish": (_i, [_vp, _ll, _i, _i, _i, _vp, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp,

@@ -153,6 +153,82 @@ __device__ __forceinline__ RowStats ln_l2_row(float (&x)[24], const float* __res
   return st;
 }
 
+// Row constants of the LayerNorm parameters used by ln_l2_row_onepass.
+struct LnConsts { float sum_g2, sum_gb, sum_b2; };
+
+// Same result as ln_l2_row (LayerNorm then L2 normalisation) with ONE warp reduction stage
+// instead of three dependent ones: with x' = x - K (K = the row's first element; LayerNorm is
+// shift-invariant and the shift keeps the one-pass moments well conditioned) the five sums
+//   S1 = sum x', S2 = sum x'^2, G2 = sum g^2 x'^2, G1 = sum g^2 x', GB = sum g b x'
+// give mean' = S1/D, var = S2/D - mean'^2 and
+//   |LN(x)|^2 = rstd^2 (G2 - 2 mean' G1 + mean'^2 sum g^2) + 2 rstd (GB - mean' sum g b) + sum b^2,
+// after which each element is one pair of FMAs: k = x' (a g) + (b inv - mean' a g), a = rstd inv.
+__device__ __forceinline__ void load_lane_params(const float* __restrict__ p, int lane, float (&r)[24]) {
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const float4 v = *reinterpret_cast<const float4*>(p + 4 * (lane + 32 * j));
+    r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+  }
+}
+// g / b: this lane's 24 gamma / beta values (load_lane_params), loop-invariant in the callers.
+__device__ __forceinline__ RowStats ln_l2_row_onepass(float (&x)[24], const float (&g)[24],
+                                                      const float (&b)[24], const LnConsts c,
+                                                      float eps_ln, float eps_l2, bool do_l2 = true) {
+  const float shift = __shfl_sync(0xffffffffu, x[0], 0);
+  float s1 = 0.f, s2 = 0.f, g2 = 0.f, g1 = 0.f, gb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    x[i] -= shift;
+    const float gg = g[i] * g[i];
+    const float xx = x[i] * x[i];
+    s1 += x[i];
+    s2 += xx;
+    g2 = fmaf(gg, xx, g2);
+    g1 = fmaf(gg, x[i], g1);
+    gb = fmaf(g[i] * b[i], x[i], gb);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+    g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+    gb += __shfl_xor_sync(0xffffffffu, gb, o);
+  }
+  const float mu = s1 * (1.0f / RZ_HIDDEN);
+  const float var = fmaxf(s2 * (1.0f / RZ_HIDDEN) - mu * mu, 0.0f);
+  const float rstd = rsqrtf(var + eps_ln);
+  float inv = 1.0f;
+  if (do_l2) {
+    const float n2 = rstd * rstd * (g2 - 2.0f * mu * g1 + mu * mu * c.sum_g2) +
+                     2.0f * rstd * (gb - mu * c.sum_gb) + c.sum_b2;
+    inv = 1.0f / fmaxf(sqrtf(fmaxf(n2, 0.0f)), eps_l2);
+  }
+  const float a = rstd * inv;
+  const float ma = -mu * a;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    const float t = a * g[i];
+    x[i] = fmaf(x[i], t, fmaf(ma, g[i], b[i] * inv));
+  }
+  RowStats st;
+  st.mean = mu + shift; st.rstd = rstd; st.inv_norm = inv;
+  return st;
+}
+
+// sum g^2, sum g b, sum b^2 over the 768 features; one warp, result in every lane
+__device__ __forceinline__ LnConsts ln_consts_warp(const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, int lane) {
+  float a = 0.f, b = 0.f, c = 0.f;
+  for (int i = lane; i < RZ_HIDDEN; i += 32) {
+    const float g = gamma[i], bb = beta[i];
+    a = fmaf(g, g, a); b = fmaf(g, bb, b); c = fmaf(bb, bb, c);
+  }
+  LnConsts r;
+  r.sum_g2 = warp_sum(a); r.sum_gb = warp_sum(b); r.sum_b2 = warp_sum(c);
+  return r;
+}
+
 // Byte offset of (row, byte-in-128B-row) inside a 128B-swizzled chunk whose base is
 // 1024-byte aligned: rows are 128 B apart, the 16-byte unit index is XOR-ed with row%8.
 // This is the layout TMA SWIZZLE_128B produces and UMMA LayoutType::SWIZZLE_128B reads.

@@ -38,17 +38,25 @@ constexpr int kPairBytes = 2 * kTok * 128;    // one slab of a token tile: 2 chu
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThresh = 8.0f;        // natural-log units; p <= e^8 fits fp16 comfortably
 constexpr int kSoftmaxThreads = 128;
-constexpr int kThreads = 192;                 // 4 softmax/epilogue warps + TMA warp + MMA warp
+constexpr int kBaseThreads = 192;             // 4 softmax/epilogue warps + TMA warp + MMA warp
+constexpr int kLoaderWarps = 24;              // fused-prep variant: warps that normalise raw rows
 
 struct FwdParams {
   int B, L, Lp, N;
   float scale;
+  const float* log_tau_scale;  // optional device scalar: scale = exp(-*log_tau_scale)
+  const float* log_tau_z;      // optional device scalar: z_scale = exp(-*log_tau_z)
+  const void* raw;             // fused-prep variant: raw tokens [B, L, 768]
+  const float* gamma;          // LayerNorm weight / bias (fused-prep variant), may be NULL
+  const float* beta;
+  int l2;
   const float* q_inv_norm;     // optional [N]: multiplies Z (sim_op "dot": 1/|q|)
   float* scores;               // optional
   long long scores_sb, scores_sn;
   int drop_cls;
   float* z;                    // optional
   long long z_sn, z_sb;
+  float z_scale; int z_sigmoid;
   float* lse;                  // optional [B, N]
   float* onorm;                // optional [B, N]
   __half* o_out;               // optional [B, N, 768]
@@ -70,7 +78,6 @@ struct Ctrl {
   float alpha[NBLK];
   float linv[NBLK];
   float smax[4][NBLK];
-  float red[4][3 * NBLK];
 };
 
 template <int NBLK, int KSTAGES>
@@ -79,29 +86,40 @@ struct Cfg {
   static constexpr int kQBytes = NBLK * kD * 2;
   static constexpr int kKBytes = kPairs * kPairBytes;
   static constexpr int kPBuf = (NBLK * 128 < 1024) ? 1024 : NBLK * 128;
-  static constexpr int kSmem = 1024 + kQBytes + kKBytes + 2 * kPBuf + (int)sizeof(Ctrl<NBLK>);
+  // [q][k tiles][P x2 (the item epilogue reuses P as reduction scratch)][Ctrl]
+  static constexpr int kSmem = kQBytes + kKBytes + 2 * kPBuf + (int)sizeof(Ctrl<NBLK>);
+  static_assert(4 * 3 * NBLK * 4 <= 2 * kPBuf, "reduction scratch must fit in the P buffers");
   static constexpr int kTmemCols = 8 * NBLK;
   static constexpr int kSCol = 6 * NBLK;
 };
 
-template <int NBLK, int KSTAGES, bool STATS>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int NBLK, int KSTAGES, bool STATS, int LOADERS, typename TIn>
+__global__ void __launch_bounds__(kBaseThreads + 32 * LOADERS, 1)
 sim_fwd_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap qmap,
-               const FwdParams p) {
+               const FwdParams p_in) {
+  FwdParams p = p_in;
+  if (p.log_tau_scale != nullptr) p.scale = __expf(-__ldg(p.log_tau_scale));
+  if (p.log_tau_z != nullptr) p.z_scale = __expf(-__ldg(p.log_tau_z));
   using C = Cfg<NBLK, KSTAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* q_s = base;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // no static shared memory in this kernel: the dynamic segment starts 1024-byte aligned
+  // (checked, since SWIZZLE_128B operands need it and there is no room for a slack pad)
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  uint8_t* q_s = smem_raw;
   uint8_t* k_s = q_s + C::kQBytes;
   uint8_t* p_s = k_s + C::kKBytes;
   Ctrl<NBLK>* ctl = reinterpret_cast<Ctrl<NBLK>*>(p_s + 2 * C::kPBuf);
+  float (*red)[3 * NBLK] = reinterpret_cast<float (*)[3 * NBLK]>(p_s);   // epilogue scratch
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int T = p.tiles;
 
   if (tid == 0) {
     mbar_init(&ctl->q_full, 1);
-    for (int i = 0; i < C::kPairs; ++i) { mbar_init(&ctl->k_full[i], 1); mbar_init(&ctl->k_empty[i], 1); }
+    for (int i = 0; i < C::kPairs; ++i) {
+      mbar_init(&ctl->k_full[i], LOADERS > 0 ? LOADERS : 1);
+      mbar_init(&ctl->k_empty[i], 1);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->s_full[i], 1);
       mbar_init(&ctl->p_full[i], kSoftmaxThreads);
@@ -111,7 +129,7 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 4) {
-    if (lane == 0) { prefetch_tmap(&kmap); prefetch_tmap(&qmap); }
+    if (lane == 0) { if (LOADERS == 0) prefetch_tmap(&kmap); prefetch_tmap(&qmap); }
     tmem_alloc(&ctl->tmem_slot, C::kTmemCols);
   }
   tc_fence_before();
@@ -134,7 +152,7 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__
             tma_load_2d(&qmap, &ctl->q_full, q_s + c * NBLK * 128, c * 64, pb * NBLK, kEvictLast);
           prev_pb = pb;
         }
-        for (int j = 0; j < T; ++j) {
+        for (int j = 0; LOADERS == 0 && j < T; ++j) {
           const long long gt = (long long)it * T + j;
           for (int s = 0; s < kSlabs; ++s) {
             const long long g = gt * kSlabs + s;
@@ -219,7 +237,52 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__
       }
     }
     __syncwarp();
-  } else {
+  } else if (LOADERS > 0 && warp >= 6) {
+    // ================================================================= fused prep: raw rows ->
+    // LayerNorm + L2 (fp32, registers) -> fp16 -> the swizzled K-major token tile
+    const int lw = warp - 6;
+    const TIn* raw = static_cast<const TIn*>(p.raw);
+    int it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int b = item / p.n_blocks;
+      const TIn* img = raw + (long long)b * p.L * kD;
+      for (int j = 0; j < T; ++j) {
+        const long long gt = (long long)it * T + j;
+        const int slot0 = (int)((gt * kSlabs) % C::kPairs);       // 6 consecutive slots, no wrap
+        const uint32_t par = (uint32_t)((((gt * kSlabs) / C::kPairs) & 1) ^ 1);
+        for (int sl = 0; sl < kSlabs; ++sl) mbar_wait(&ctl->k_empty[slot0 + sl], par);
+        uint8_t* tile = k_s + slot0 * kPairBytes;
+        // this lane's 4 consecutive features of slab jj live at: slab jj, half lane/16, byte 8*(lane%16)
+        uint8_t* lane_base_ptr = tile + (lane >> 4) * (kTok * 128);
+        const uint32_t byte_in_row = (uint32_t)(8 * (lane & 15));
+        // one row per warp in flight, many warps: measured on B200, a warp does not overlap the
+        // 128-bit loads of several rows, so HBM concurrency has to come from the warp count
+#pragma unroll 1
+        for (int r = lw; r < kTok; r += LOADERS) {
+          float v[24];
+          const int t = j * kTok + r;
+          const bool ok = t < p.L;
+          if (ok) {
+            rz::RowLoad<TIn>::load(img + (long long)t * kD, lane, v);
+            rz::ln_l2_row(v, p.gamma, p.beta, lane, RZ_LN_EPS, RZ_L2_EPS, p.l2 != 0);
+          }
+          const uint32_t o = rz::sw128_offset((uint32_t)r, byte_in_row);
+#pragma unroll
+          for (int jj = 0; jj < 6; ++jj) {
+            uint2 w = make_uint2(0u, 0u);
+            if (ok)
+              w = make_uint2(rz::pack_half2(v[4 * jj], v[4 * jj + 1]),
+                             rz::pack_half2(v[4 * jj + 2], v[4 * jj + 3]));
+            *reinterpret_cast<uint2*>(lane_base_ptr + jj * kPairBytes + o) = w;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0)
+          for (int sl = 0; sl < kSlabs; ++sl) mbar_arrive(&ctl->k_full[slot0 + sl]);
+      }
+    }
+  } else if (warp < 4) {
     // ================================================================= softmax + epilogue warps
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const bool act = lane < 16;                 // M=64 accumulator: rows live in lanes 0-15 of each quarter
@@ -348,26 +411,26 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__
         for (int i = 0; i < 16; ++i) {
           const float a = rz::warp_sum(osq[i]);
           const float q2 = rz::warp_sum(qo[i]);
-          if (lane == 0) { ctl->red[warp][c0 + i] = a; ctl->red[warp][NBLK + c0 + i] = q2; }
+          if (lane == 0) { red[warp][c0 + i] = a; red[warp][NBLK + c0 + i] = q2; }
         }
       }
       if (STATS) {
 #pragma unroll
         for (int c = 0; c < NBLK; ++c) {
           const float l = rz::warp_sum(lpart[c]);
-          if (lane == 0) ctl->red[warp][2 * NBLK + c] = l;
+          if (lane == 0) red[warp][2 * NBLK + c] = l;
         }
       }
       named_bar_sync(1, kSoftmaxThreads);
       if (tid < NBLK) {
         const int n = n0 + tid;
-        const float osq = ctl->red[0][tid] + ctl->red[1][tid] + ctl->red[2][tid] + ctl->red[3][tid];
-        const float qo = ctl->red[0][NBLK + tid] + ctl->red[1][NBLK + tid] + ctl->red[2][NBLK + tid] +
-                         ctl->red[3][NBLK + tid];
+        const float osq = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+        const float qo = red[0][NBLK + tid] + red[1][NBLK + tid] + red[2][NBLK + tid] +
+                         red[3][NBLK + tid];
         float l = 1.0f;
         if (STATS)
-          l = ctl->red[0][2 * NBLK + tid] + ctl->red[1][2 * NBLK + tid] + ctl->red[2][2 * NBLK + tid] +
-              ctl->red[3][2 * NBLK + tid];
+          l = red[0][2 * NBLK + tid] + red[1][2 * NBLK + tid] + red[2][2 * NBLK + tid] +
+              red[3][2 * NBLK + tid];
         const float linv = 1.0f / l;
         ctl->linv[tid] = linv;
         if (n < p.N) {
@@ -375,7 +438,11 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__
           // F.normalize(pooled): o / max(|o|, eps) with o = O / l          losses.py:227
           float z = (qo * linv) / fmaxf(on * linv, RZ_L2_EPS);
           if (p.q_inv_norm != nullptr) z *= p.q_inv_norm[n];
-          if (p.z != nullptr) p.z[(long long)n * p.z_sn + (long long)b * p.z_sb] = z;
+          if (p.z != nullptr) {
+            float zo = z * p.z_scale;
+            if (p.z_sigmoid) zo = 1.0f / (1.0f + __expf(-zo));
+            p.z[(long long)n * p.z_sn + (long long)b * p.z_sb] = zo;
+          }
           if (STATS) {
             if (p.lse != nullptr) p.lse[(long long)b * p.N + n] = ctl->m_ref[tid] + logf(l);
             if (p.onorm != nullptr) p.onorm[(long long)b * p.N + n] = on * linv;
@@ -411,7 +478,7 @@ sim_fwd_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__
   if (warp == 4) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
-template <int NBLK, int KSTAGES>
+template <int NBLK, int KSTAGES, int LOADERS, typename TIn>
 int launch_fwd(const CUtensorMap& kmap, const CUtensorMap& qmap, FwdParams p, bool stats,
                cudaStream_t s) {
   using C = Cfg<NBLK, KSTAGES>;
@@ -419,54 +486,104 @@ int launch_fwd(const CUtensorMap& kmap, const CUtensorMap& qmap, FwdParams p, bo
   p.items = p.B * p.n_blocks;
   p.tiles = (p.L + kTok - 1) / kTok;
   const int grid = p.items < rz_sm_count() ? p.items : rz_sm_count();
+  const int threads = kBaseThreads + 32 * LOADERS;
   if (stats) {
-    RZ_CUDA_OK(cudaFuncSetAttribute(sim_fwd_kernel<NBLK, KSTAGES, true>,
+    RZ_CUDA_OK(cudaFuncSetAttribute(sim_fwd_kernel<NBLK, KSTAGES, true, LOADERS, TIn>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-    sim_fwd_kernel<NBLK, KSTAGES, true><<<grid, kThreads, C::kSmem, s>>>(kmap, qmap, p);
+    sim_fwd_kernel<NBLK, KSTAGES, true, LOADERS, TIn><<<grid, threads, C::kSmem, s>>>(kmap, qmap, p);
   } else {
-    RZ_CUDA_OK(cudaFuncSetAttribute(sim_fwd_kernel<NBLK, KSTAGES, false>,
+    RZ_CUDA_OK(cudaFuncSetAttribute(sim_fwd_kernel<NBLK, KSTAGES, false, LOADERS, TIn>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-    sim_fwd_kernel<NBLK, KSTAGES, false><<<grid, kThreads, C::kSmem, s>>>(kmap, qmap, p);
+    sim_fwd_kernel<NBLK, KSTAGES, false, LOADERS, TIn><<<grid, threads, C::kSmem, s>>>(kmap, qmap, p);
   }
   RZ_LAUNCH_OK();
   rz_count_launch();
   return RZ_OK;
 }
 
-}  // namespace
-
-extern "C" int rz_sim_fwd(const void* k_f16, int n_images, int tokens, int tokens_padded,
-                          const void* q_f16, int n_text, float scale, const float* q_inv_norm,
-                          float* scores, long long scores_stride_image, long long scores_stride_text,
-                          int drop_cls, float* z, long long z_stride_text, long long z_stride_image,
-                          float* lse, float* onorm, void* pooled_f16, void* stream) {
-  if (k_f16 == nullptr || q_f16 == nullptr) return RZ_ERR_INVALID;
+int fill_common(FwdParams& p, int n_images, int tokens, int tokens_padded, int n_text, float scale,
+                const float* log_tau_scale, const float* q_inv_norm, float* scores,
+                long long scores_stride_image, long long scores_stride_text, int drop_cls, float* z,
+                long long z_stride_text, long long z_stride_image, float z_scale,
+                const float* log_tau_z, int z_sigmoid, float* lse, float* onorm, void* pooled_f16) {
   if (n_images <= 0 || n_text <= 0 || tokens <= 0 || tokens_padded < tokens) return RZ_ERR_INVALID;
   if (tokens_padded % kTok != 0) return RZ_ERR_INVALID;
   if (drop_cls != 0 && drop_cls != 1) return RZ_ERR_INVALID;
-  if ((reinterpret_cast<uintptr_t>(k_f16) & 15) || (reinterpret_cast<uintptr_t>(q_f16) & 15))
-    return RZ_ERR_ALIGNMENT;
   if ((long long)n_images * tokens_padded >= (1ll << 31)) return RZ_ERR_UNSUPPORTED;
-  CUtensorMap kmap, qmap;
-  if (!rz::make_map_2d_sw128(&kmap, k_f16, (uint64_t)n_images * tokens_padded, kD, kD * 2, kTok))
-    return RZ_ERR_CUDA;
-  FwdParams p;
   p.B = n_images; p.L = tokens; p.Lp = tokens_padded; p.N = n_text; p.scale = scale;
+  p.log_tau_scale = log_tau_scale; p.log_tau_z = log_tau_z;
+  p.raw = nullptr; p.gamma = nullptr; p.beta = nullptr; p.l2 = 1;
   p.q_inv_norm = q_inv_norm;
   p.scores = scores; p.scores_sb = scores_stride_image; p.scores_sn = scores_stride_text;
   p.drop_cls = drop_cls;
   p.z = z; p.z_sn = z_stride_text; p.z_sb = z_stride_image;
+  p.z_scale = z_scale; p.z_sigmoid = z_sigmoid;
   p.lse = lse; p.onorm = onorm; p.o_out = static_cast<__half*>(pooled_f16);
   p.n_blocks = p.items = p.tiles = 0;
+  return RZ_OK;
+}
+
+}  // namespace
+
+extern "C" int rz_sim_fwd(const void* k_f16, int n_images, int tokens, int tokens_padded,
+                          const void* q_f16, int n_text, float scale, const float* log_tau_scale,
+                          const float* q_inv_norm, float* scores, long long scores_stride_image,
+                          long long scores_stride_text, int drop_cls, float* z,
+                          long long z_stride_text, long long z_stride_image, float z_scale,
+                          const float* log_tau_z, int z_sigmoid, float* lse, float* onorm,
+                          void* pooled_f16, void* stream) {
+  if (k_f16 == nullptr || q_f16 == nullptr) return RZ_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(k_f16) & 15) || (reinterpret_cast<uintptr_t>(q_f16) & 15))
+    return RZ_ERR_ALIGNMENT;
+  FwdParams p;
+  int rc = fill_common(p, n_images, tokens, tokens_padded, n_text, scale, log_tau_scale, q_inv_norm,
+                       scores, scores_stride_image, scores_stride_text, drop_cls, z, z_stride_text,
+                       z_stride_image, z_scale, log_tau_z, z_sigmoid, lse, onorm, pooled_f16);
+  if (rc != RZ_OK) return rc;
+  CUtensorMap kmap, qmap;
+  if (!rz::make_map_2d_sw128(&kmap, k_f16, (uint64_t)n_images * tokens_padded, kD, kD * 2, kTok))
+    return RZ_ERR_CUDA;
   const bool stats = (lse != nullptr || onorm != nullptr || pooled_f16 != nullptr);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (n_text <= 16) {
     if (!rz::make_map_2d_sw128(&qmap, q_f16, (uint64_t)n_text, kD, kD * 2, 16)) return RZ_ERR_CUDA;
-    return launch_fwd<16, 2>(kmap, qmap, p, stats, s);
+    return launch_fwd<16, 2, 0, float>(kmap, qmap, p, stats, s);
   } else if (n_text <= 32) {
     if (!rz::make_map_2d_sw128(&qmap, q_f16, (uint64_t)n_text, kD, kD * 2, 32)) return RZ_ERR_CUDA;
-    return launch_fwd<32, 1>(kmap, qmap, p, stats, s);
+    return launch_fwd<32, 1, 0, float>(kmap, qmap, p, stats, s);
   }
   if (!rz::make_map_2d_sw128(&qmap, q_f16, (uint64_t)n_text, kD, kD * 2, 64)) return RZ_ERR_CUDA;
-  return launch_fwd<64, 1>(kmap, qmap, p, stats, s);
+  return launch_fwd<64, 1, 0, float>(kmap, qmap, p, stats, s);
+}
+
+extern "C" int rz_sim_fwd_tokens(const void* tokens_raw, int dtype, const float* gamma,
+                                 const float* beta, int l2, int n_images, int tokens,
+                                 const void* q_f16, int n_text, float scale,
+                                 const float* log_tau_scale, const float* q_inv_norm, float* scores,
+                                 long long scores_stride_image, long long scores_stride_text,
+                                 int drop_cls, float* z, long long z_stride_text,
+                                 long long z_stride_image, float z_scale, const float* log_tau_z,
+                                 int z_sigmoid, void* stream) {
+  if (tokens_raw == nullptr || q_f16 == nullptr) return RZ_ERR_INVALID;
+  if ((gamma == nullptr) != (beta == nullptr)) return RZ_ERR_INVALID;
+  if (n_text > 16) return RZ_ERR_UNSUPPORTED;   // larger prompt sets: rz_prep_rows + rz_sim_fwd
+  if ((reinterpret_cast<uintptr_t>(tokens_raw) & 15) || (reinterpret_cast<uintptr_t>(q_f16) & 15) ||
+      (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(beta) & 15))
+    return RZ_ERR_ALIGNMENT;
+  FwdParams p;
+  const int lp = (tokens + kTok - 1) / kTok * kTok;
+  int rc = fill_common(p, n_images, tokens, lp, n_text, scale, log_tau_scale, q_inv_norm, scores,
+                       scores_stride_image, scores_stride_text, drop_cls, z, z_stride_text,
+                       z_stride_image, z_scale, log_tau_z, z_sigmoid, nullptr, nullptr, nullptr);
+  if (rc != RZ_OK) return rc;
+  p.raw = tokens_raw; p.gamma = gamma; p.beta = beta; p.l2 = l2;
+  CUtensorMap qmap;
+  if (!rz::make_map_2d_sw128(&qmap, q_f16, (uint64_t)n_text, kD, kD * 2, 16)) return RZ_ERR_CUDA;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case RZ_F32: return launch_fwd<16, 2, kLoaderWarps, float>(qmap, qmap, p, false, s);
+    case RZ_BF16: return launch_fwd<16, 2, kLoaderWarps, __nv_bfloat16>(qmap, qmap, p, false, s);
+    case RZ_F16: return launch_fwd<16, 2, kLoaderWarps, __half>(qmap, qmap, p, false, s);
+    default: return RZ_ERR_INVALID;
+  }
 }

@@ -49,13 +49,45 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin with a ~2 s watchdog: a protocol bug becomes a launch error instead of a hung GPU.
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes
+// or `hint_ns` expires, instead of re-polling the barrier through the LSU.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+// Latency-critical wait (polls) with a ~2 s watchdog: a protocol bug becomes a launch error
+// instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000ll) __trap();
   }
+}
+// Throughput wait for producers that are far ahead: sleeps in hardware between polls.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_hint(bar, parity, 2000u)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+// Warp-uniform waits: one lane waits on the barrier, the rest of the warp parks at the
+// __syncwarp (keeps 31 lanes per warp from polling shared memory through the LSU).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ void mbar_wait_warp_relaxed(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait_relaxed(bar, parity);
+  __syncwarp();
 }
 
 // generic-proxy writes to smem -> visible to the async proxy (TMA / tcgen05 operands)

@@ -94,3 +94,88 @@ def get_grounding_point(similarity_score: torch.Tensor, image_size, image_proces
         x, y = pts[0].tolist()
         return (x, y)
     return pts
+
+
+# ----------------------------------------------------------------------------- surface 1
+def _load_image(image):
+    """Accept a path, a PIL image or an (H, W[, C]) uint8 array/tensor; return (PIL RGB, (H, W))."""
+    from PIL import Image
+    import numpy as np
+    if isinstance(image, (str, bytes)) or hasattr(image, "__fspath__"):
+        image = Image.open(image)
+    elif torch.is_tensor(image):
+        image = Image.fromarray(image.detach().cpu().numpy())
+    elif isinstance(image, np.ndarray):
+        image = Image.fromarray(image)
+    width, height = image.size
+    return image, (height, width)
+
+
+@torch.no_grad()
+def extract_similarity_map(image, text, model, image_processor, tokenizer):
+    """Drop-in for the reference's six ``extract_similarity_map`` copies
+    (exp/cxr_pt/inference/visualization/attention_map_base.py:12-42): pixel-level map at the
+    cos / tau scale, shape (H, W) of the ORIGINAL image.  ``text`` may be a list of prompts,
+    in which case the result is (N, H, W) from one launch."""
+    import numpy as np
+    pil, image_size = _load_image(image)
+    pix = image_processor(pil)
+    pixel_values = torch.as_tensor(np.array(pix["pixel_values"]), dtype=torch.float32).to(model.device)
+    tokenized = tokenizer(text, padding=True, truncation=True, return_tensors="pt").to(model.device)
+    out = model.compute_logits(pixel_values, [tokenized])
+    scores = out["similarity_scores"]                     # (1, N, P*P)
+    maps = interpolate_similarity_scores(scores.reshape(-1, scores.shape[-1]), image_size, image_processor)
+    return maps.squeeze(0) if maps.shape[0] == 1 else maps
+
+
+@torch.no_grad()
+def model_inference(image, text, tokenizer, image_processor, model):
+    """``utils.model_inference(image, text, tokenizer, image_processor, model)`` of the
+    reference's usage snippet (README.md:66, 104-111) -> ``(similarity_prob, similarity_map)``.
+
+    The hub-side body is not in the reference checkout; this follows
+    ``extract_similarity_map`` (same preprocessing, ``model.compute_logits``, bilinear
+    upsample to the original image size) and returns similarity_prob = sigmoid(logits) and
+    the pixel-level similarity_map at the cos / tau scale, both computed by the fused CUDA
+    path: the similarity + pooling kernel, then ONE upsample launch for all prompts.
+    """
+    import numpy as np
+    pil, image_size = _load_image(image)
+    pix = image_processor(pil)
+    pixel_values = torch.as_tensor(np.array(pix["pixel_values"]), dtype=torch.float32).to(model.device)
+    tokenized = tokenizer(text, padding=True, truncation=True, return_tensors="pt").to(model.device)
+    out = model.compute_logits(pixel_values, [tokenized])
+    similarity_prob = torch.sigmoid(out["logits"])        # (1, N)
+    scores = out["similarity_scores"]
+    similarity_map = interpolate_similarity_scores(scores.reshape(-1, scores.shape[-1]), image_size,
+                                                   image_processor)
+    if similarity_map.shape[0] == 1:                      # single prompt: scalar prob, (H, W) map
+        return similarity_prob.reshape(()), similarity_map.squeeze(0)
+    return similarity_prob.squeeze(0), similarity_map
+
+
+class SyntheticTokenizer:
+    """Stand-in tokenizer for offline runs (no vocabulary files on disk): deterministic ids
+    from a hash of the words, HF ``__call__`` convention returning a dict with ``.to()``."""
+
+    def __init__(self, vocab_size: int = 30527, max_length: int = 32):
+        self.vocab_size, self.max_length = vocab_size, max_length
+
+    class _Enc(dict):
+        def to(self, device):
+            return SyntheticTokenizer._Enc({k: v.to(device) for k, v in self.items()})
+
+    def __call__(self, text, padding=True, truncation=True, return_tensors="pt", **kw):
+        import zlib
+        texts = [text] if isinstance(text, str) else list(text)
+        rows = []
+        for t in texts:
+            ids = [0] + [4 + zlib.crc32(w.lower().encode()) % (self.vocab_size - 4) for w in t.split()] + [2]
+            rows.append(ids[: self.max_length])
+        m = max(len(r) for r in rows)
+        ids = torch.ones((len(rows), m), dtype=torch.long)
+        mask = torch.zeros((len(rows), m), dtype=torch.long)
+        for i, r in enumerate(rows):
+            ids[i, : len(r)] = torch.tensor(r)
+            mask[i, : len(r)] = 1
+        return SyntheticTokenizer._Enc(input_ids=ids, attention_mask=mask)

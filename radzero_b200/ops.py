@@ -71,15 +71,44 @@ def padded_tokens(tokens: int) -> int:
     return (tokens + TOKEN_TILE - 1) // TOKEN_TILE * TOKEN_TILE
 
 
+def _log_tau_ptr(t):
+    """A device fp32 scalar holding a log-temperature (or None)."""
+    if t is None:
+        return None
+    if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and t.numel() == 1):
+        raise RzError("log-temperature must be a 1-element fp32 CUDA tensor")
+    return t.detach()
+
+
+def _sim_outputs(B, N, tokens, dev, want_scores, drop_cls, want_z, z_out, z_image_major):
+    drop = 1 if drop_cls else 0
+    scores = torch.empty((B, N, tokens - drop), dtype=torch.float32, device=dev) if want_scores else None
+    z = None
+    if want_z:
+        zshape = (B, N) if z_image_major else (N, B)
+        z = z_out if z_out is not None else torch.empty(zshape, dtype=torch.float32, device=dev)
+        if z.dtype != torch.float32 or tuple(z.shape) != zshape:
+            raise RzError(f"z_out must be fp32 {zshape}")
+    zs_text, zs_img = (0, 0) if z is None else ((z.stride(1), z.stride(0)) if z_image_major
+                                                else (z.stride(0), z.stride(1)))
+    return drop, scores, z, zs_text, zs_img
+
+
 def sim_fwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, scale: float, *,
             want_scores: bool = False, drop_cls: bool = True, want_z: bool = True,
             want_stats: bool = False, want_pooled: bool = False,
-            q_inv_norm: Optional[torch.Tensor] = None, z_out: Optional[torch.Tensor] = None):
+            q_inv_norm: Optional[torch.Tensor] = None, z_out: Optional[torch.Tensor] = None,
+            z_scale: float = 1.0, z_sigmoid: bool = False, z_image_major: bool = False,
+            log_tau_scale: Optional[torch.Tensor] = None, log_tau_z: Optional[torch.Tensor] = None):
     """Fused similarity forward.  k_f16 (B, Lp, 768) fp16, q_f16 (N, 768) fp16.
 
     Returns dict(scores (B, N, L - drop) | None, z (N, B) | None, lse, onorm (B, N) | None,
     pooled (B, N, 768) fp16 | None).  ``z_out`` lets the caller place Z directly into a
-    column block of a larger (N, ld) matrix.
+    column block of a larger (N, ld) matrix; ``z_image_major`` makes z (B, N) instead, and
+    ``z_scale`` / ``z_sigmoid`` fuse the ``/ tau`` and sigmoid of compute_logits /
+    similarity_prob into the epilogue.  ``log_tau_scale`` / ``log_tau_z`` (1-element fp32
+    CUDA tensors, e.g. the ``loss_temperature`` parameter) make the kernel read the
+    temperature on the device: scale = exp(-log_tau), no host sync.
     """
     _need_cuda(k_f16, q_f16, q_inv_norm, z_out)
     if k_f16.dtype != torch.float16 or q_f16.dtype != torch.float16:
@@ -91,25 +120,66 @@ def sim_fwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, scale: float,
     B, Lp, _ = k_f16.shape
     N = q_f16.shape[0]
     dev = k_f16.device
-    drop = 1 if drop_cls else 0
-    scores = torch.empty((B, N, tokens - drop), dtype=torch.float32, device=dev) if want_scores else None
-    z = None
-    if want_z:
-        z = z_out if z_out is not None else torch.empty((N, B), dtype=torch.float32, device=dev)
-        if z.dtype != torch.float32 or z.shape != (N, B):
-            raise RzError("z_out must be fp32 (N, B)")
+    drop, scores, z, zs_text, zs_img = _sim_outputs(B, N, tokens, dev, want_scores, drop_cls, want_z,
+                                                    z_out, z_image_major)
     lse = torch.empty((B, N), dtype=torch.float32, device=dev) if want_stats else None
     onorm = torch.empty((B, N), dtype=torch.float32, device=dev) if want_stats else None
     pooled = torch.empty((B, N, HIDDEN), dtype=torch.float16, device=dev) if want_pooled else None
     qin = _contig(q_inv_norm.float()) if q_inv_norm is not None else None
+    lts, ltz = _log_tau_ptr(log_tau_scale), _log_tau_ptr(log_tau_z)
     rc = _lib.load().rz_sim_fwd(
-        _p(k_f16), B, int(tokens), Lp, _p(q_f16), N, float(scale), _p(qin),
+        _p(k_f16), B, int(tokens), Lp, _p(q_f16), N, float(scale), _p(lts), _p(qin),
         _p(scores), scores.stride(0) if scores is not None else 0,
         scores.stride(1) if scores is not None else 0, drop,
-        _p(z), z.stride(0) if z is not None else 0, z.stride(1) if z is not None else 0,
+        _p(z), zs_text, zs_img, float(z_scale), _p(ltz), 1 if z_sigmoid else 0,
         _p(lse), _p(onorm), _p(pooled), _stream())
     _lib.check(rc, "rz_sim_fwd")
     return dict(scores=scores, z=z, lse=lse, onorm=onorm, pooled=pooled)
+
+
+FUSED_PREP_MAX_TEXT = 16
+# Which small-N forward the host mirror uses.  Measured on B200 (C2, 256 x 14, fp32 tokens):
+# rz_prep_rows + rz_sim_fwd = 0.39 ms of kernels; the single-kernel rz_sim_fwd_tokens = 0.50 ms
+# (its loader warps are latency-bound, see DESIGN.md "open items"), so the two-kernel path is
+# the default until the fused one wins.
+USE_FUSED_PREP = False
+
+
+def sim_fwd_tokens(tokens_raw: torch.Tensor, gamma: Optional[torch.Tensor],
+                   beta: Optional[torch.Tensor], q_f16: torch.Tensor, scale: float, *, l2: bool = True,
+                   want_scores: bool = False, drop_cls: bool = True, want_z: bool = True,
+                   q_inv_norm: Optional[torch.Tensor] = None, z_out: Optional[torch.Tensor] = None,
+                   z_scale: float = 1.0, z_sigmoid: bool = False, z_image_major: bool = False,
+                   log_tau_scale: Optional[torch.Tensor] = None,
+                   log_tau_z: Optional[torch.Tensor] = None):
+    """Small-prompt-set forward straight from the RAW tokens (B, L, 768) fp32/bf16/fp16:
+    LayerNorm + L2 + the whole similarity path in ONE kernel (N <= 16)."""
+    _need_cuda(tokens_raw, gamma, beta, q_f16, q_inv_norm, z_out)
+    if tokens_raw.dtype not in _DTYPES:
+        raise RzError(f"unsupported token dtype {tokens_raw.dtype}")
+    if tokens_raw.dim() != 3 or tokens_raw.shape[-1] != HIDDEN:
+        raise RzError("tokens must be (B, L, 768)")
+    x = _contig(tokens_raw)
+    B, L, _ = x.shape
+    N = q_f16.shape[0]
+    if N > FUSED_PREP_MAX_TEXT:
+        raise RzError(f"sim_fwd_tokens handles at most {FUSED_PREP_MAX_TEXT} prompts")
+    if q_f16.dtype != torch.float16 or not q_f16.is_contiguous():
+        raise RzError("q_f16 must be contiguous fp16 (N, 768)")
+    dev = x.device
+    drop, scores, z, zs_text, zs_img = _sim_outputs(B, N, L, dev, want_scores, drop_cls, want_z,
+                                                    z_out, z_image_major)
+    g = _contig(gamma.detach().float()) if gamma is not None else None
+    b = _contig(beta.detach().float()) if beta is not None else None
+    qin = _contig(q_inv_norm.float()) if q_inv_norm is not None else None
+    lts, ltz = _log_tau_ptr(log_tau_scale), _log_tau_ptr(log_tau_z)
+    rc = _lib.load().rz_sim_fwd_tokens(
+        _p(x), _DTYPES[x.dtype], _p(g), _p(b), 1 if l2 else 0, B, L, _p(q_f16), N, float(scale),
+        _p(lts), _p(qin), _p(scores), scores.stride(0) if scores is not None else 0,
+        scores.stride(1) if scores is not None else 0, drop, _p(z), zs_text, zs_img,
+        float(z_scale), _p(ltz), 1 if z_sigmoid else 0, _stream())
+    _lib.check(rc, "rz_sim_fwd_tokens")
+    return dict(scores=scores, z=z)
 
 
 # ----------------------------------------------------------------------------- K8 + K9

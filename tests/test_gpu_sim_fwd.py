@@ -138,3 +138,53 @@ def test_sim_fwd_dot_mode():
     z, sc = oracle.similarity_logit(tn, xn, sim_op="dot", need_scores=True, squeeze_quirk=False)
     assert (out["scores"].cpu().double() - sc[0]).abs().max() < 2e-2   # |s| ~ 30: fp16 operand rounding
     assert (out["z"].cpu().double() - z).abs().max() < 3e-4
+
+
+# ------------------------------------------------------------------- fused-prep variant (N <= 16)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,N,L", [(3, 14, 1370), (2, 8, 1370), (1, 1, 77), (5, 16, 200)])
+def test_sim_fwd_tokens_vs_oracle(dtype, B, N, L):
+    tok, text, gamma, beta, _ = synthetic.make_inputs(B, N, tokens_per_image=L, seed=300 + N)
+    tok = tok.to(dtype)
+    q16, _, _ = ops.prep_rows(text.to(DEV), gamma.to(DEV), beta.to(DEV))
+    out = ops.sim_fwd_tokens(tok.to(DEV), gamma.to(DEV), beta.to(DEV), q16, 1.0 / TAU,
+                             want_scores=True, drop_cls=True)
+    want = _oracle(tok.float(), text, gamma, beta)
+    assert (out["scores"].cpu().double() - want["scores"][:, :, 1:]).abs().max() < 2e-3
+    assert (out["z"].cpu().double() - want["z"]).abs().max() < 2e-4
+    # the two-kernel path (prep -> fp16 -> TMA) must agree with the fused one to fp16 noise
+    two = _run(tok, text, gamma, beta, want_scores=True, drop_cls=True)
+    assert (two["z"] - out["z"]).abs().max() < 1e-5
+    assert (two["scores"] - out["scores"]).abs().max() < 5e-4
+
+
+def test_sim_fwd_tokens_device_temperature_and_prob():
+    from radzero_b200 import losses
+    B, N, L = 4, 14, 1370
+    tok, text, gamma, beta, log_tau = synthetic.make_inputs(B, N, tokens_per_image=L, seed=12)
+    fn = losses.RadZeroLoss(sim_op="cos").to(DEV)
+    with torch.no_grad():
+        fn.layer_norm.weight.copy_(gamma)
+        fn.layer_norm.bias.copy_(beta)
+        fn.loss_temperature.fill_(math.log(0.05))          # not the init value
+    prob = fn.similarity_prob(text.to(DEV), tok.to(DEV))
+    logits, scores, z = fn.similarity(text.to(DEV), tok.to(DEV))
+    want = _oracle(tok, text, gamma, beta, tau=0.05)
+    pw = torch.sigmoid(want["z"].T / 0.05)
+    assert prob.shape == (B, N)
+    assert ((prob.cpu().double() - pw) / pw).abs().max() < 1e-3
+    assert (scores.cpu().double() - want["scores"][:, :, 1:]).abs().max() < 2e-3
+    assert (logits.cpu().double() - want["z"].T / 0.05).abs().max() < 2e-3
+    assert torch.equal(logits.cpu().argmax(1), (want["z"].T).argmax(1))
+
+
+def test_many_images_persistent_loop():
+    """More work items than SMs: every CTA walks several images (barrier phases wrap)."""
+    B, N, L = 330, 14, 200
+    tok, text, gamma, beta, _ = synthetic.make_inputs(B, N, tokens_per_image=L, seed=4)
+    q16, _, _ = ops.prep_rows(text.to(DEV), gamma.to(DEV), beta.to(DEV))
+    out = ops.sim_fwd_tokens(tok.to(DEV), gamma.to(DEV), beta.to(DEV), q16, 1.0 / TAU)
+    two = _run(tok, text, gamma, beta)
+    want = _oracle(tok, text, gamma, beta)
+    assert (out["z"].cpu().double() - want["z"]).abs().max() < 2e-4
+    assert (two["z"].cpu().double() - want["z"]).abs().max() < 2e-4
