@@ -114,6 +114,42 @@ int rz_sim_fwd_tokens(const void* tokens_raw, int dtype, const float* gamma, con
                       int drop_cls, float* z, long long z_stride_text, long long z_stride_image,
                       float z_scale, const float* log_tau_z, int z_sigmoid, void* stream);
 
+/* ---- backward of K3-K6 -------------------------------------------------------------------
+ * Replaces the autograd of SimilarityLogit.forward (losses.py:187-240: the backward of bmm,
+ * softmax, matmul, normalize and the batched dot) in closed form: three tcgen05 GEMM passes
+ * (recompute S and T = o.k^T with two accumulators -> fp16 coefficient matrices W1, W2;
+ * dq = sum_b W1_b k_b; dk_b = W1_b^T q + W2_b^T o_b).  Inputs are what rz_sim_fwd produced.
+ *   k_f16 [n_images, tokens_padded, 768], tokens_padded a multiple of 128
+ *   z, dz  fp32 [n_text, ldz]: pooled logits and dL/dZ for the local images (columns)
+ *   lse, onorm [n_images, n_text]; pooled_f16 [n_images, n_text, 768]
+ *   dq    fp32 [n_text, 768]  = dL/dq (normalised sentence embeddings), overwritten
+ *   dk    fp32 [n_images, tokens_padded, 768] = dL/dk (normalised tokens), overwritten
+ *   dlog_tau fp32 [1] = dL/dlog(tau_attn) through the softmax scores
+ *   inv_tau / log_tau as in rz_sim_fwd (log_tau: optional device scalar)
+ * workspace: rz_sim_bwd_workspace_bytes(...) bytes, 256-byte aligned.
+ */
+size_t rz_sim_bwd_workspace_bytes(int n_images, int n_text, int tokens_padded);
+int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int tokens_padded, const void* q_f16,
+               int n_text, float inv_tau, const float* log_tau, const float* z, const float* dz,
+               long long ldz, const float* lse, const float* onorm, const void* pooled_f16,
+               float* dq, float* dk, float* dlog_tau, void* workspace, size_t workspace_bytes,
+               void* stream);
+
+/* ---- backward of K1+K2 --------------------------------------------------------------------
+ * dL/dx and dL/dgamma, dL/dbeta from dL/d(normalised rows) (autograd of nn.LayerNorm +
+ * F.normalize, losses.py:90-91, 163-164, 212-213).  Row statistics are recomputed from x.
+ *   dnorm  fp32, padded group layout of rz_prep_rows' out_f16 ([groups, rows_per_group_padded, 768])
+ *   dx     fp32 [rows, 768]
+ *   partials fp32 [rz_prep_rows_bwd_blocks(rows), 2, 768] scratch (needed when gamma != NULL)
+ *   dgamma/dbeta fp32 [768]: overwritten, or accumulated into when accumulate = 1 (tokens
+ *   and text share one LayerNorm, losses.py:51); grad_scale multiplies the parameter grads.
+ */
+int rz_prep_rows_bwd_blocks(long long rows);
+int rz_prep_rows_bwd(const void* x, int dtype, const float* gamma, const float* beta,
+                     long long rows, int rows_per_group, int rows_per_group_padded,
+                     const float* dnorm, int l2, float* dx, float* partials, float* dgamma,
+                     float* dbeta, int accumulate, float grad_scale, void* stream);
+
 /* ---- K8+K9: bilinear upsample of patch-grid similarity maps ----------------------------
  * Replaces F.interpolate(mode="bilinear", align_corners=False) in
  * interpolate_similarity_scores (exp/cxr_pt/inference/segmentation_utils.py:36-122) and

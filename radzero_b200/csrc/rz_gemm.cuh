@@ -1,0 +1,181 @@
+// Persistent, warp-specialised tcgen05 GEMM skeleton shared by the large-N forward and the
+// backward kernels of the VL-CABS path.
+//
+//   warp 4 : TMA producer   (one elected lane; SWIZZLE_128B boxes into a kStages-deep ring)
+//   warp 5 : MMA issuer     (one elected lane; tcgen05.mma kind::f16, fp32 accumulate in TMEM)
+//   warps 0-3 : epilogue    (thread = accumulator row; tcgen05.ld -> policy functor -> global)
+//
+// Output tile: 128 rows x (kAccs * kBN) fp32 TMEM columns, double buffered (2 * kAccs * kBN
+// <= 512) so that the epilogue of tile i overlaps the MMAs of tile i+1.  K advances 64
+// elements (one 128-byte swizzle row) per pipeline stage = 4 MMAs of K=16.
+// A policy class V supplies the problem decomposition, the TMA loads and the epilogue:
+//   V::kBN, V::kAccs (1 or 2 A operands sharing one B), V::kAMn / V::kBMn (operand is
+//   MN-major in shared memory), V::Params,
+//   V::num_tiles(p), V::k_steps(p), V::load(p, maps, tile, ks, a_smem, a2_smem, b_smem, bar),
+//   V::epilogue(p, tile, tmem_acc, warp, lane, scratch)
+#pragma once
+
+#include "rz_common.cuh"
+#include "rz_tma.cuh"
+#include "rz_umma.cuh"
+
+namespace rz {
+namespace gemm {
+
+using namespace rz::umma;
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kABytes = kBM * 128;       // one A stage: 128 rows x 128 B (or 2 MN blocks of 8 KB)
+constexpr int kMnBlock = 64 * 128;       // MN-major block: 64 K-rows x 128 B
+constexpr int kThreads = 192;
+
+struct Maps {
+  CUtensorMap a, a2, b, b2;
+};
+
+template <class V>
+struct Layout {
+  static constexpr int kBBytes = V::kBN * 128;
+  static constexpr int kStageBytes = V::kAccs * kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 6 ? 6 : (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = 2 * V::kAccs * V::kBN;
+  static constexpr int kSmem = 1024 + kStages * kStageBytes + 1024;
+  static_assert(kTmemCols <= 512, "accumulators exceed TMEM");
+  static_assert(kStages >= 2, "pipeline too shallow");
+};
+
+struct Ctrl {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_slot;
+  float scratch[8];
+};
+
+template <class V>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
+  using L = Layout<V>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Ctrl* ctl = reinterpret_cast<Ctrl*>(base + L::kStages * L::kStageBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = V::num_tiles(p);
+  const int ksteps = V::k_steps(p);
+
+  if (tid == 0) {
+    for (int i = 0; i < L::kStages; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->acc_full[i], 1); mbar_init(&ctl->acc_empty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      prefetch_tmap(&maps.a); prefetch_tmap(&maps.b);
+      if (V::kAccs > 1 || V::kTwoPhase) { prefetch_tmap(&maps.a2); prefetch_tmap(&maps.b2); }
+    }
+    tmem_alloc(&ctl->tmem_slot, L::kTmemCols < 32 ? 32 : L::kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_slot;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      long long g = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int ks = 0; ks < ksteps; ++ks, ++g) {
+          const int st = (int)(g % L::kStages);
+          mbar_wait(&ctl->empty[st], (uint32_t)(((g / L::kStages) & 1) ^ 1));
+          mbar_arrive_expect_tx(&ctl->full[st], (uint32_t)L::kStageBytes);
+          uint8_t* sa = base + st * L::kStageBytes;
+          V::load(p, maps, tile, ks, sa, sa + kABytes, sa + V::kAccs * kABytes, &ctl->full[st]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_f16(kBM, V::kBN, V::kAMn ? 1 : 0, V::kBMn ? 1 : 0);
+      long long g = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&ctl->acc_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * (V::kAccs * V::kBN);
+        for (int ks = 0; ks < ksteps; ++ks, ++g) {
+          const int st = (int)(g % L::kStages);
+          mbar_wait(&ctl->full[st], (uint32_t)((g / L::kStages) & 1));
+          tc_fence_after();
+          const uint32_t sa = smem_u32(base + st * L::kStageBytes);
+          const uint32_t sb = sa + V::kAccs * kABytes;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t bd = V::kBMn ? make_smem_desc(sb + k4 * 2048, kMnBlock, 1024)
+                                        : make_smem_desc(sb + k4 * 32, 0, 1024);
+#pragma unroll
+            for (int a = 0; a < V::kAccs; ++a) {
+              const uint32_t aa = sa + a * kABytes;
+              const uint64_t ad = V::kAMn ? make_smem_desc(aa + k4 * 2048, kMnBlock, 1024)
+                                          : make_smem_desc(aa + k4 * 32, 0, 1024);
+              mma_f16_ss(d0 + a * V::kBN, ad, bd, idesc, (ks | k4) ? 1u : 0u);
+            }
+          }
+          mma_commit(&ctl->empty[st]);
+        }
+        mma_commit(&ctl->acc_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&ctl->acc_full[acc], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      V::epilogue(p, tile, tmem_base + acc * (V::kAccs * V::kBN), warp, lane, ctl->scratch);
+      tc_fence_before();
+      mbar_arrive(&ctl->acc_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, L::kTmemCols < 32 ? 32 : L::kTmemCols);
+}
+
+template <class V>
+int launch(const Maps& maps, const typename V::Params& p, cudaStream_t s) {
+  using L = Layout<V>;
+  const int tiles = V::num_tiles(p);
+  if (tiles <= 0) return RZ_OK;
+  const int grid = tiles < rz_sm_count() ? tiles : rz_sm_count();
+  RZ_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmem));
+  gemm_kernel<V><<<grid, kThreads, L::kSmem, s>>>(maps, p);
+  RZ_LAUNCH_OK();
+  rz_count_launch();
+  return RZ_OK;
+}
+
+// ---- helpers for policies ---------------------------------------------------------------
+// K-major operand tile: `rows` rows x 64 K-elements, one TMA box
+__device__ __forceinline__ void load_kmajor(const CUtensorMap* m, uint64_t* bar, void* dst, int k0,
+                                            int row0, int batch) {
+  tma_load_3d(m, bar, dst, k0, row0, batch, kEvictNormal);
+}
+// MN-major operand tile: `blocks` blocks of [64 K-rows x 64 MN-elements]
+__device__ __forceinline__ void load_mnmajor(const CUtensorMap* m, uint64_t* bar, uint8_t* dst,
+                                             int mn0, int k0, int batch, int blocks) {
+  for (int i = 0; i < blocks; ++i)
+    tma_load_3d(m, bar, dst + i * kMnBlock, mn0 + i * 64, k0, batch, kEvictNormal);
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+}  // namespace gemm
+}  // namespace rz

@@ -1,0 +1,196 @@
+// Backward of K1+K2 (row LayerNorm + L2 normalisation, losses.py:90-91, 163-164, 212-213):
+// given dL/dk for the normalised rows k = y/|y|, y = LN(x) = xhat*gamma + beta, produce dL/dx
+// and the LayerNorm parameter gradients.  One warp per row, the row statistics are recomputed
+// from x (cheaper than storing them), gamma/beta gradients are accumulated in registers per
+// warp, reduced per CTA in shared memory and summed by a second tiny kernel in a fixed order
+// (deterministic: no float atomics).
+#include "rz_common.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+prep_rows_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, long long rows, int rows_per_group,
+                     int rows_per_group_padded, const float* __restrict__ dnorm, int l2,
+                     float* __restrict__ dx, float* __restrict__ part /* [grid][2][768] */) {
+  __shared__ float red[kWarps][2 * RZ_HIDDEN / 4];   // reduced in 4 passes of 384 floats
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long warp0 = (long long)blockIdx.x * kWarps + warp;
+  const long long nwarps = (long long)gridDim.x * kWarps;
+  float dg[24], db[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+  const bool has_ln = gamma != nullptr;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const long long g = row / rows_per_group;
+    const long long slot = g * rows_per_group_padded + (row - g * rows_per_group);
+    float v[24], d[24];
+    rz::RowLoad<T>::load(x + row * RZ_HIDDEN, lane, v);
+    {
+      const float4* p = reinterpret_cast<const float4*>(dnorm + slot * RZ_HIDDEN) + lane;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const float4 t = rz::ldg_stream_f4(p + 32 * j);
+        d[4 * j] = t.x; d[4 * j + 1] = t.y; d[4 * j + 2] = t.z; d[4 * j + 3] = t.w;
+      }
+    }
+    float rstd = 1.f;
+    float gm[24];
+    if (has_ln) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 24; ++i) s += v[i];
+      const float mu = rz::warp_sum(s) * (1.0f / RZ_HIDDEN);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 24; ++i) { v[i] -= mu; q = fmaf(v[i], v[i], q); }
+      rstd = rsqrtf(rz::warp_sum(q) * (1.0f / RZ_HIDDEN) + RZ_LN_EPS);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const float4 t = *reinterpret_cast<const float4*>(gamma + 4 * (lane + 32 * j));
+        gm[4 * j] = t.x; gm[4 * j + 1] = t.y; gm[4 * j + 2] = t.z; gm[4 * j + 3] = t.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 24; ++i) v[i] *= rstd;            // v = xhat
+    }
+    if (l2) {
+      // y (LayerNorm output) -> k = y/|y|;  dy = (d - k <k,d>) / |y|
+      float y[24];
+      if (has_ln) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const float4 t = *reinterpret_cast<const float4*>(beta + 4 * (lane + 32 * j));
+          y[4 * j] = fmaf(v[4 * j], gm[4 * j], t.x);
+          y[4 * j + 1] = fmaf(v[4 * j + 1], gm[4 * j + 1], t.y);
+          y[4 * j + 2] = fmaf(v[4 * j + 2], gm[4 * j + 2], t.z);
+          y[4 * j + 3] = fmaf(v[4 * j + 3], gm[4 * j + 3], t.w);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 24; ++i) y[i] = v[i];
+      }
+      float n2 = 0.f, yd = 0.f;
+#pragma unroll
+      for (int i = 0; i < 24; ++i) { n2 = fmaf(y[i], y[i], n2); yd = fmaf(y[i], d[i], yd); }
+      n2 = rz::warp_sum(n2);
+      yd = rz::warp_sum(yd);
+      const float inv = 1.0f / fmaxf(sqrtf(n2), RZ_L2_EPS);
+      const float c = yd * inv * inv;                       // <k,d>/|y| = <y,d>/|y|^2
+#pragma unroll
+      for (int i = 0; i < 24; ++i) d[i] = (d[i] - y[i] * c) * inv;
+    }
+    if (has_ln) {
+      float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 24; ++i) {
+        dg[i] = fmaf(d[i], v[i], dg[i]);
+        db[i] += d[i];
+        d[i] *= gm[i];                                      // d = dxhat
+        m1 += d[i];
+        m2 = fmaf(d[i], v[i], m2);
+      }
+      m1 = rz::warp_sum(m1) * (1.0f / RZ_HIDDEN);
+      m2 = rz::warp_sum(m2) * (1.0f / RZ_HIDDEN);
+#pragma unroll
+      for (int i = 0; i < 24; ++i) d[i] = rstd * (d[i] - m1 - v[i] * m2);
+    }
+    float4* o = reinterpret_cast<float4*>(dx + row * RZ_HIDDEN) + lane;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) o[32 * j] = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+  }
+  if (part == nullptr) return;
+  // CTA reduction of the parameter gradients, 384 floats (= 12 of the 48 per-lane values) a pass
+  float* out = part + (long long)blockIdx.x * 2 * RZ_HIDDEN;
+  for (int pass = 0; pass < 4; ++pass) {
+    // pass 0,1: dgamma groups j = 0..2 / 3..5 ; pass 2,3: dbeta
+    const float* src = pass < 2 ? dg : db;
+    const int j0 = (pass & 1) * 3;
+#pragma unroll
+    for (int jj = 0; jj < 3; ++jj) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        red[warp][jj * 128 + lane * 4 + e] = (pass < 2 ? dg : db)[4 * (j0 + jj) + e];
+    }
+    (void)src;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 384; i += kWarps * 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += red[w][i];
+      // element index: group j = j0 + i/128, lane = (i%128)/4, e = i%4 -> feature 4*(lane+32*j)+e
+      const int jj = i >> 7, ln = (i & 127) >> 2, e = i & 3;
+      out[(pass < 2 ? 0 : RZ_HIDDEN) + 4 * (ln + 32 * (j0 + jj)) + e] = s;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void param_grad_sum_kernel(const float* __restrict__ part, int n_parts,
+                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                      int accumulate, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * RZ_HIDDEN) return;
+  float s = 0.f;
+  for (int k = 0; k < n_parts; ++k) s += part[(long long)k * 2 * RZ_HIDDEN + i];
+  s *= scale;
+  float* dst = i < RZ_HIDDEN ? dgamma + i : dbeta + (i - RZ_HIDDEN);
+  *dst = accumulate ? *dst + s : s;
+}
+
+}  // namespace
+
+extern "C" int rz_prep_rows_bwd_blocks(long long rows) {
+  if (rows <= 0) return 0;
+  long long blocks = (rows + kWarps - 1) / kWarps;
+  const long long cap = (long long)rz_sm_count() * 2;
+  return (int)(blocks > cap ? cap : blocks);
+}
+
+extern "C" int rz_prep_rows_bwd(const void* x, int dtype, const float* gamma, const float* beta,
+                                long long rows, int rows_per_group, int rows_per_group_padded,
+                                const float* dnorm, int l2, float* dx, float* partials,
+                                float* dgamma, float* dbeta, int accumulate, float grad_scale,
+                                void* stream) {
+  if (x == nullptr || dnorm == nullptr || dx == nullptr || rows < 0) return RZ_ERR_INVALID;
+  if (rows_per_group <= 0 || rows_per_group_padded < rows_per_group) return RZ_ERR_INVALID;
+  if ((gamma == nullptr) != (beta == nullptr)) return RZ_ERR_INVALID;
+  if (gamma != nullptr && (partials == nullptr || dgamma == nullptr || dbeta == nullptr)) return RZ_ERR_INVALID;
+  if (rows == 0) return RZ_OK;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dnorm) & 15) ||
+      (reinterpret_cast<uintptr_t>(dx) & 15))
+    return RZ_ERR_ALIGNMENT;
+  const int blocks = rz_prep_rows_bwd_blocks(rows);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* part = gamma != nullptr ? partials : nullptr;
+  switch (dtype) {
+    case RZ_F32:
+      prep_rows_bwd_kernel<float><<<blocks, kWarps * 32, 0, s>>>(
+          static_cast<const float*>(x), gamma, beta, rows, rows_per_group, rows_per_group_padded, dnorm,
+          l2, dx, part);
+      break;
+    case RZ_BF16:
+      prep_rows_bwd_kernel<__nv_bfloat16><<<blocks, kWarps * 32, 0, s>>>(
+          static_cast<const __nv_bfloat16*>(x), gamma, beta, rows, rows_per_group, rows_per_group_padded,
+          dnorm, l2, dx, part);
+      break;
+    case RZ_F16:
+      prep_rows_bwd_kernel<__half><<<blocks, kWarps * 32, 0, s>>>(
+          static_cast<const __half*>(x), gamma, beta, rows, rows_per_group, rows_per_group_padded, dnorm,
+          l2, dx, part);
+      break;
+    default:
+      return RZ_ERR_INVALID;
+  }
+  RZ_LAUNCH_OK();
+  rz_count_launch();
+  if (gamma != nullptr) {
+    param_grad_sum_kernel<<<(2 * RZ_HIDDEN + 255) / 256, 256, 0, s>>>(partials, blocks, dgamma, dbeta,
+                                                                      accumulate, grad_scale);
+    RZ_LAUNCH_OK();
+    rz_count_launch();
+  }
+  return RZ_OK;
+}

@@ -1,0 +1,363 @@
+// Backward of the VL-CABS similarity (SimilarityLogit, exp/cxr_pt/model/losses.py:187-240)
+// with respect to the normalised operands q (N x 768) and k (B x L x 768), in closed form, as
+// three tcgen05 GEMM passes over per-image (prompt x token) coefficient matrices.
+//
+// Per pair (b, n), with s_l = <q_n, k_bl>/tau, p = softmax_l(s), o = sum_l p_l k_bl,
+// Z = <q, o/|o|> and g = dL/dZ:
+//   a = g/|o|,  r = Z/|o|,   T_l = <o, k_bl>
+//   dL/ds_l = a tau p_l (s_l - (r/tau) T_l)                       (since <dL/do, o> = 0)
+//   W1_l = a p_l (1 + s_l - (r/tau) T_l),   W2_l = -a r p_l
+//   dL/dq_n  = sum_b sum_l W1_l k_bl                               (pass Q)
+//   dL/dk_bl = sum_n W1_l q_n + W2_l o_bn                          (pass K)
+//   dL/dlog tau_attn = -sum dL/ds_l s_l
+// Pass D recomputes S and T for a (128 prompts x 128 tokens) tile with TWO accumulators that
+// share the token tile as B operand, and writes W1 / W2 as fp16 (scaled by a power of two
+// `*scale` chosen on the device so that the small gradient values stay in fp16's normal range).
+#include "rz_gemm.cuh"
+
+namespace {
+
+using namespace rz::gemm;
+constexpr int kD = RZ_HIDDEN;
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ------------------------------------------------------------------------------------------
+// per-pair coefficients + the fp16 scale
+struct CoefParams {
+  const float* g; const float* z; long long ldz;    // [N, ldz] (column = local image)
+  const float* onorm;                               // [B, N]
+  float* coef_a; float* coef_r;                     // [B, N]
+  unsigned int* amax_bits;                          // max |a| as float bits
+  int B, N;
+};
+
+__global__ void pair_coef_kernel(CoefParams p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float a_abs = 0.f;
+  if (i < (long long)p.B * p.N) {
+    const int b = (int)(i / p.N), n = (int)(i - (long long)b * p.N);
+    const float on = fmaxf(p.onorm[i], RZ_L2_EPS);
+    const float a = p.g[(long long)n * p.ldz + b] / on;
+    p.coef_a[i] = a;
+    p.coef_r[i] = p.z[(long long)n * p.ldz + b] / on;
+    a_abs = fabsf(a);
+  }
+  a_abs = rz::warp_max(a_abs);
+  if ((threadIdx.x & 31) == 0 && a_abs > 0.f) atomicMax(p.amax_bits, __float_as_uint(a_abs));
+}
+
+// scale = 2^k with scale * max|a| in [256, 512)
+__global__ void pick_scale_kernel(const unsigned int* amax_bits, float* scale) {
+  const float m = __uint_as_float(*amax_bits);
+  float s = 1.0f;
+  if (m > 0.f && isfinite(m)) {
+    int e;
+    frexpf(m, &e);                // m = f * 2^e, f in [0.5, 1)
+    s = ldexpf(1.0f, 9 - e);      // s*m in [256, 512)
+  }
+  scale[0] = s;
+  scale[1] = 1.0f / s;
+}
+
+// ------------------------------------------------------------------------------------------
+// pass D: W1, W2 for every (image, prompt tile, token tile)
+struct DParams {
+  int B, N, L, Lp;
+  int m_tiles, n_tiles;
+  float inv_tau;                 // 1/tau (host value) ...
+  const float* log_tau;          // ... or device log-temperature
+  const float* lse;              // [B, N]
+  const float* coef_a; const float* coef_r;
+  const float* scale;            // [2] = S, 1/S
+  __half* w1; __half* w2;        // [B, N, Lp]
+  float* dtau_part;              // [tiles] partial sums of -dL/ds * s (unscaled)
+};
+
+struct PassD {
+  using Params = DParams;
+  static constexpr int kBN = 128, kAccs = 2;
+  static constexpr bool kAMn = false, kBMn = false, kTwoPhase = false;
+  __host__ __device__ static int num_tiles(const Params& p) { return p.B * p.m_tiles * p.n_tiles; }
+  __host__ __device__ static int k_steps(const Params&) { return kD / kBK; }
+  __device__ static void decode(const Params& p, int tile, int& b, int& mt, int& nt) {
+    nt = tile % p.n_tiles;
+    const int r = tile / p.n_tiles;
+    mt = r % p.m_tiles;
+    b = r / p.m_tiles;
+  }
+  __device__ static void load(const Params& p, const Maps& m, int tile, int ks, uint8_t* a,
+                              uint8_t* a2, uint8_t* bsm, uint64_t* bar) {
+    int b, mt, nt;
+    decode(p, tile, b, mt, nt);
+    load_kmajor(&m.a, bar, a, ks * kBK, mt * kBM, 0);        // q      [N, 768]
+    load_kmajor(&m.a2, bar, a2, ks * kBK, mt * kBM, b);      // pooled [B, N, 768]
+    load_kmajor(&m.b, bar, bsm, ks * kBK, nt * kBN, b);      // k      [B, Lp, 768]
+  }
+  __device__ static void epilogue(const Params& p, int tile, uint32_t tmem, int warp, int lane,
+                                  float* scratch) {
+    int b, mt, nt;
+    decode(p, tile, b, mt, nt);
+    const int n = mt * kBM + warp * 32 + lane;
+    const bool row_ok = n < p.N;
+    const float inv_tau = p.log_tau != nullptr ? __expf(-__ldg(p.log_tau)) : p.inv_tau;
+    const float tau = 1.0f / inv_tau;
+    const long long pi = (long long)b * p.N + (row_ok ? n : 0);
+    const float lse = row_ok ? p.lse[pi] : 0.f;
+    const float S = p.scale[0];
+    const float a = row_ok ? p.coef_a[pi] : 0.f;
+    const float aS = a * S;
+    const float r = row_ok ? p.coef_r[pi] : 0.f;
+    const float rt = r * inv_tau;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    __half* w1 = p.w1 + ((long long)b * p.N + n) * p.Lp + nt * kBN;
+    __half* w2 = p.w2 + ((long long)b * p.N + n) * p.Lp + nt * kBN;
+    float dls = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kBN; c0 += 16) {
+      uint32_t sv[16], tv[16];
+      tmem_ld_x16(tmem + lane_base + c0, sv);
+      tmem_ld_x16(tmem + lane_base + kBN + c0, tv);
+      tmem_ld_wait();
+      uint32_t o1[8], o2[8];
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        float w1v[2], w2v[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int l = nt * kBN + c0 + i + u;
+          const float s = __uint_as_float(sv[i + u]) * inv_tau;
+          const float t = __uint_as_float(tv[i + u]);
+          const float pr = (l < p.L) ? exp2f((s - lse) * kLog2e) : 0.f;
+          const float e = s - rt * t;               // (s - (r/tau) T)
+          w1v[u] = aS * pr * (1.0f + e);
+          w2v[u] = -aS * r * pr;
+          dls = fmaf(-a * tau * pr * e, s, dls);    // -dL/ds * s
+        }
+        o1[i >> 1] = pack_h2(w1v[0], w1v[1]);
+        o2[i >> 1] = pack_h2(w2v[0], w2v[1]);
+      }
+      if (row_ok) {
+        uint4* d1 = reinterpret_cast<uint4*>(w1 + c0);
+        uint4* d2 = reinterpret_cast<uint4*>(w2 + c0);
+        d1[0] = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+        d1[1] = make_uint4(o1[4], o1[5], o1[6], o1[7]);
+        d2[0] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+        d2[1] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
+      }
+    }
+    // deterministic per-tile partial of dL/dlog(tau_attn)
+    dls = rz::warp_sum(dls);
+    if (lane == 0) scratch[warp] = dls;
+    named_bar_sync(1, 128);
+    if (warp == 0 && lane == 0) p.dtau_part[tile] = scratch[0] + scratch[1] + scratch[2] + scratch[3];
+    named_bar_sync(1, 128);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// pass Q: dq[n, f] = (1/S) sum_b sum_l W1[b, n, l] k[b, l, f]
+struct QParams {
+  int B, N, Lp;
+  int m_tiles;
+  const float* scale;
+  float* dq;                      // [N, 768] fp32
+};
+
+struct PassQ {
+  using Params = QParams;
+  static constexpr int kBN = 256, kAccs = 1;
+  static constexpr bool kAMn = false, kBMn = true, kTwoPhase = false;
+  __host__ __device__ static int num_tiles(const Params& p) { return p.m_tiles * (kD / kBN); }
+  __host__ __device__ static int k_steps(const Params& p) { return p.B * (p.Lp / kBK); }
+  __device__ static void load(const Params& p, const Maps& m, int tile, int ks, uint8_t* a, uint8_t*,
+                              uint8_t* bsm, uint64_t* bar) {
+    const int ft = tile % (kD / kBN), mt = tile / (kD / kBN);
+    const int per = p.Lp / kBK;
+    const int b = ks / per, lc = ks - b * per;
+    load_kmajor(&m.a, bar, a, lc * kBK, mt * kBM, b);                     // W1 [B, N, Lp]
+    load_mnmajor(&m.b, bar, bsm, ft * kBN, lc * kBK, b, kBN / 64);        // k  [B, Lp, 768]
+  }
+  __device__ static void epilogue(const Params& p, int tile, uint32_t tmem, int warp, int lane, float*) {
+    const int ft = tile % (kD / kBN), mt = tile / (kD / kBN);
+    const int n = mt * kBM + warp * 32 + lane;
+    const float inv_s = p.scale[1];
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    float* dst = p.dq + (long long)n * kD + ft * kBN;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kBN; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(tmem + lane_base + c0, v);
+      tmem_ld_wait();
+      if (n < p.N) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(dst + c0 + i) =
+              make_float4(__uint_as_float(v[i]) * inv_s, __uint_as_float(v[i + 1]) * inv_s,
+                          __uint_as_float(v[i + 2]) * inv_s, __uint_as_float(v[i + 3]) * inv_s);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// pass K: dk[b, l, f] = (1/S) sum_n ( W1[b, n, l] q[n, f] + W2[b, n, l] o[b, n, f] )
+struct KParams {
+  int B, N, Lp;
+  int l_tiles, n_chunks;
+  const float* scale;
+  float* dk;                      // [B, Lp, 768] fp32
+};
+
+struct PassK {
+  using Params = KParams;
+  static constexpr int kBN = 256, kAccs = 1;
+  static constexpr bool kAMn = true, kBMn = true, kTwoPhase = true;
+  __host__ __device__ static int num_tiles(const Params& p) { return p.B * p.l_tiles * (kD / kBN); }
+  __host__ __device__ static int k_steps(const Params& p) { return 2 * p.n_chunks; }
+  __device__ static void decode(const Params& p, int tile, int& b, int& lt, int& ft) {
+    ft = tile % (kD / kBN);
+    const int r = tile / (kD / kBN);
+    lt = r % p.l_tiles;
+    b = r / p.l_tiles;
+  }
+  __device__ static void load(const Params& p, const Maps& m, int tile, int ks, uint8_t* a, uint8_t*,
+                              uint8_t* bsm, uint64_t* bar) {
+    int b, lt, ft;
+    decode(p, tile, b, lt, ft);
+    if (ks < p.n_chunks) {
+      load_mnmajor(&m.a, bar, a, lt * kBM, ks * kBK, b, kBM / 64);        // W1 [B, N, Lp] (M = l)
+      load_mnmajor(&m.b, bar, bsm, ft * kBN, ks * kBK, 0, kBN / 64);      // q  [N, 768]
+    } else {
+      const int nc = ks - p.n_chunks;
+      load_mnmajor(&m.a2, bar, a, lt * kBM, nc * kBK, b, kBM / 64);       // W2
+      load_mnmajor(&m.b2, bar, bsm, ft * kBN, nc * kBK, b, kBN / 64);     // pooled [B, N, 768]
+    }
+  }
+  __device__ static void epilogue(const Params& p, int tile, uint32_t tmem, int warp, int lane, float*) {
+    int b, lt, ft;
+    decode(p, tile, b, lt, ft);
+    const int l = lt * kBM + warp * 32 + lane;
+    const float inv_s = p.scale[1];
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    float* dst = p.dk + ((long long)b * p.Lp + l) * kD + ft * kBN;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kBN; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(tmem + lane_base + c0, v);
+      tmem_ld_wait();
+      if (l < p.Lp) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(dst + c0 + i) =
+              make_float4(__uint_as_float(v[i]) * inv_s, __uint_as_float(v[i + 1]) * inv_s,
+                          __uint_as_float(v[i + 2]) * inv_s, __uint_as_float(v[i + 3]) * inv_s);
+      }
+    }
+  }
+};
+
+__global__ void sum_partials_kernel(const float* part, int n, float* out) {
+  __shared__ float sh[1024];
+  float a = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) a += part[i];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+}  // namespace
+
+extern "C" size_t rz_sim_bwd_workspace_bytes(int n_images, int n_text, int tokens_padded) {
+  if (n_images <= 0 || n_text <= 0 || tokens_padded <= 0) return 0;
+  const size_t pairs = (size_t)n_images * n_text;
+  const size_t w = pairs * (size_t)tokens_padded * sizeof(__half);     // one of W1 / W2
+  const size_t tiles = (size_t)n_images * ((n_text + 127) / 128) * (tokens_padded / 128);
+  return 2 * w + 2 * pairs * sizeof(float) + tiles * sizeof(float) + 256;
+}
+
+extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int tokens_padded,
+                          const void* q_f16, int n_text, float inv_tau, const float* log_tau,
+                          const float* z, const float* dz, long long ldz, const float* lse,
+                          const float* onorm, const void* pooled_f16, float* dq, float* dk,
+                          float* dlog_tau, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!k_f16 || !q_f16 || !z || !dz || !lse || !onorm || !pooled_f16 || !dq || !dk || !dlog_tau ||
+      !workspace)
+    return RZ_ERR_INVALID;
+  if (n_images <= 0 || n_text <= 0 || tokens <= 0 || tokens_padded < tokens || ldz < n_images)
+    return RZ_ERR_INVALID;
+  if (tokens_padded % 128 != 0) return RZ_ERR_INVALID;
+  if (workspace_bytes < rz_sim_bwd_workspace_bytes(n_images, n_text, tokens_padded)) return RZ_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) || (reinterpret_cast<uintptr_t>(dq) & 15) ||
+      (reinterpret_cast<uintptr_t>(dk) & 15))
+    return RZ_ERR_ALIGNMENT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int B = n_images, N = n_text, Lp = tokens_padded;
+  const size_t pairs = (size_t)B * N;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  __half* w1 = reinterpret_cast<__half*>(ws);
+  __half* w2 = w1 + pairs * Lp;
+  float* coef_a = reinterpret_cast<float*>(w2 + pairs * Lp);
+  float* coef_r = coef_a + pairs;
+  float* dtau_part = coef_r + pairs;
+  const int m_tiles = (N + 127) / 128, n_tiles = Lp / 128;
+  const int d_tiles = B * m_tiles * n_tiles;
+  float* scale = dtau_part + d_tiles;                      // [2]
+  unsigned int* amax = reinterpret_cast<unsigned int*>(scale + 2);
+
+  RZ_CUDA_OK(cudaMemsetAsync(amax, 0, sizeof(unsigned int), s));
+  CoefParams cp;
+  cp.g = dz; cp.z = z; cp.ldz = ldz; cp.onorm = onorm; cp.coef_a = coef_a; cp.coef_r = coef_r;
+  cp.amax_bits = amax; cp.B = B; cp.N = N;
+  pair_coef_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, s>>>(cp);
+  RZ_LAUNCH_OK();
+  pick_scale_kernel<<<1, 1, 0, s>>>(amax, scale);
+  RZ_LAUNCH_OK();
+  rz_count_launch(2);
+
+  // ---- pass D
+  {
+    Maps m;
+    if (!rz::make_map_3d_sw128(&m.a, q_f16, 1, N, kD, kD * 2, (uint64_t)N * kD * 2, kBM)) return RZ_ERR_CUDA;
+    if (!rz::make_map_3d_sw128(&m.a2, pooled_f16, B, N, kD, kD * 2, (uint64_t)N * kD * 2, kBM)) return RZ_ERR_CUDA;
+    if (!rz::make_map_3d_sw128(&m.b, k_f16, B, Lp, kD, kD * 2, (uint64_t)Lp * kD * 2, 128)) return RZ_ERR_CUDA;
+    m.b2 = m.b;
+    DParams p;
+    p.B = B; p.N = N; p.L = tokens; p.Lp = Lp; p.m_tiles = m_tiles; p.n_tiles = n_tiles;
+    p.inv_tau = inv_tau; p.log_tau = log_tau; p.lse = lse; p.coef_a = coef_a; p.coef_r = coef_r;
+    p.scale = scale; p.w1 = w1; p.w2 = w2; p.dtau_part = dtau_part;
+    int rc = launch<PassD>(m, p, s);
+    if (rc != RZ_OK) return rc;
+    sum_partials_kernel<<<1, 1024, 0, s>>>(dtau_part, d_tiles, dlog_tau);
+    RZ_LAUNCH_OK();
+    rz_count_launch();
+  }
+  // ---- pass Q
+  {
+    Maps m;
+    if (!rz::make_map_3d_sw128(&m.a, w1, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, kBM)) return RZ_ERR_CUDA;
+    if (!rz::make_map_3d_sw128(&m.b, k_f16, B, Lp, kD, kD * 2, (uint64_t)Lp * kD * 2, 64)) return RZ_ERR_CUDA;
+    m.a2 = m.a; m.b2 = m.b;
+    QParams p;
+    p.B = B; p.N = N; p.Lp = Lp; p.m_tiles = m_tiles; p.scale = scale; p.dq = dq;
+    int rc = launch<PassQ>(m, p, s);
+    if (rc != RZ_OK) return rc;
+  }
+  // ---- pass K
+  {
+    Maps m;
+    if (!rz::make_map_3d_sw128(&m.a, w1, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, 64)) return RZ_ERR_CUDA;
+    if (!rz::make_map_3d_sw128(&m.a2, w2, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, 64)) return RZ_ERR_CUDA;
+    if (!rz::make_map_3d_sw128(&m.b, q_f16, 1, N, kD, kD * 2, (uint64_t)N * kD * 2, 64)) return RZ_ERR_CUDA;
+    if (!rz::make_map_3d_sw128(&m.b2, pooled_f16, B, N, kD, kD * 2, (uint64_t)N * kD * 2, 64)) return RZ_ERR_CUDA;
+    KParams p;
+    p.B = B; p.N = N; p.Lp = Lp; p.l_tiles = Lp / 128; p.n_chunks = (N + 63) / 64; p.scale = scale;
+    p.dk = dk;
+    int rc = launch<PassK>(m, p, s);
+    if (rc != RZ_OK) return rc;
+  }
+  return RZ_OK;
+}

@@ -182,6 +182,73 @@ def sim_fwd_tokens(tokens_raw: torch.Tensor, gamma: Optional[torch.Tensor],
     return dict(scores=scores, z=z)
 
 
+# ----------------------------------------------------------------------------- backward
+BWD_TOKEN_TILE = 128
+
+
+def padded_tokens_bwd(tokens: int) -> int:
+    return (tokens + BWD_TOKEN_TILE - 1) // BWD_TOKEN_TILE * BWD_TOKEN_TILE
+
+
+def sim_bwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, inv_tau: float, z: torch.Tensor,
+            dz: torch.Tensor, lse: torch.Tensor, onorm: torch.Tensor, pooled: torch.Tensor, *,
+            log_tau: Optional[torch.Tensor] = None):
+    """Closed-form backward of the fused similarity.  Returns (dq (N,768), dk (B,Lp,768), dlog_tau (1,))."""
+    _need_cuda(k_f16, q_f16, z, dz, lse, onorm, pooled)
+    B, Lp, _ = k_f16.shape
+    N = q_f16.shape[0]
+    if Lp % BWD_TOKEN_TILE:
+        raise RzError("training path needs tokens padded to a multiple of 128")
+    if z.shape != (N, B) or dz.shape != (N, B) or z.stride(1) != 1 or dz.stride() != z.stride():
+        raise RzError("z / dz must be fp32 (N, B) with identical row pitch")
+    dev = k_f16.device
+    lib = _lib.load()
+    nbytes = int(lib.rz_sim_bwd_workspace_bytes(B, N, Lp))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dq = torch.empty((N, HIDDEN), dtype=torch.float32, device=dev)
+    dk = torch.empty((B, Lp, HIDDEN), dtype=torch.float32, device=dev)
+    dlt = torch.empty(1, dtype=torch.float32, device=dev)
+    rc = lib.rz_sim_bwd(_p(k_f16), B, int(tokens), Lp, _p(q_f16), N, float(inv_tau),
+                        _p(_log_tau_ptr(log_tau)), _p(z), _p(dz), z.stride(0), _p(lse), _p(onorm),
+                        _p(pooled), _p(dq), _p(dk), _p(dlt), _p(ws), C.c_size_t(nbytes), _stream())
+    _lib.check(rc, "rz_sim_bwd")
+    return dq, dk, dlt
+
+
+def prep_rows_bwd(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor],
+                  dnorm: torch.Tensor, *, rows_per_group: Optional[int] = None,
+                  rows_per_group_padded: Optional[int] = None, l2: bool = True,
+                  dgamma: Optional[torch.Tensor] = None, dbeta: Optional[torch.Tensor] = None,
+                  accumulate: bool = False):
+    """Backward of prep_rows: returns (dx fp32 (rows, 768), dgamma, dbeta)."""
+    _need_cuda(x, gamma, beta, dnorm, dgamma, dbeta)
+    x2 = _contig(x).view(-1, HIDDEN)
+    rows = x2.shape[0]
+    rpg = rows_per_group or max(rows, 1)
+    rpp = rows_per_group_padded or rpg
+    if dnorm.dtype != torch.float32 or not dnorm.is_contiguous():
+        raise RzError("dnorm must be contiguous fp32")
+    if dnorm.numel() != (rows // rpg) * rpp * HIDDEN:
+        raise RzError("dnorm does not match the padded group layout")
+    dev = x.device
+    lib = _lib.load()
+    dx = torch.empty((rows, HIDDEN), dtype=torch.float32, device=dev)
+    g = _contig(gamma.detach().float()) if gamma is not None else None
+    b = _contig(beta.detach().float()) if beta is not None else None
+    part = None
+    if g is not None:
+        part = torch.empty((int(lib.rz_prep_rows_bwd_blocks(rows)), 2, HIDDEN), dtype=torch.float32, device=dev)
+        if dgamma is None:
+            dgamma = torch.zeros(HIDDEN, dtype=torch.float32, device=dev)
+            dbeta = torch.zeros(HIDDEN, dtype=torch.float32, device=dev)
+            accumulate = False
+    rc = lib.rz_prep_rows_bwd(_p(x2), _DTYPES[x.dtype], _p(g), _p(b), rows, rpg, rpp, _p(dnorm),
+                              1 if l2 else 0, _p(dx), _p(part), _p(dgamma), _p(dbeta),
+                              1 if accumulate else 0, 1.0, _stream())
+    _lib.check(rc, "rz_prep_rows_bwd")
+    return dx, dgamma, dbeta
+
+
 # ----------------------------------------------------------------------------- K8 + K9
 def upsample_maps(scores: torch.Tensor, out_hw: Tuple[int, int], *, mode: int = _lib.RZ_UP_RAW,
                   interp_hw: Optional[Tuple[int, int]] = None, offset: Tuple[int, int] = (0, 0),
