@@ -100,6 +100,7 @@ def dist_setup(n_gpus: int):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line)
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -124,7 +125,23 @@ def run_ours(args):
     pk = peaks()
     if args.workload == "contrastive":
         from radzero_b200 import bench_contrastive
-        return bench_contrastive.run(args, world, rank, local, pk)
+        sampler = ClockSampler(local)
+        sampler.start()
+        out = bench_contrastive.run(args, world, rank, local, pk, steps=args.steps, warmup=max(args.warmup, 3))
+        out["clocks"] = sampler.stop()
+        out.update({"higher_is_better": True, "vs_baseline": None, "data": "synthetic", "impl": "ours",
+                    "cpu_baseline": None})
+        if rank == 0 and world == 1 and not args.no_cpu:
+            dt, pairs = bench_contrastive.cpu_sample_step(16)
+            full = bench_contrastive.B_GLOBAL * sum(synthetic.sentence_counts(bench_contrastive.B_GLOBAL, seed=42))
+            out["cpu_baseline"] = {"value": pairs / dt / full, "unit": "steps/s", "cores": os.cpu_count(),
+                                   "kind": "port", "sample": f"fwd+bwd at 16 images x {pairs // 16} sentences on the "
+                                   "fp32 CPU oracle, extrapolated by pair count"}
+        if rank == 0:
+            print(json.dumps(out))
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
     B, N, desc = WORKLOADS[args.workload]
     tok, text, gamma, beta, log_tau = synthetic.make_inputs(B, N, seed=42 + rank, device=dev)
     fn = make_loss_fn(dev, gamma, beta)
@@ -268,6 +285,17 @@ def run_ours(args):
                "api": "RadZeroLoss.similarity_prob" if args.workload == "cls" else "RadZeroLoss.similarity"}
 
     cpu = cpu_baseline(args.workload, steps=1) if (rank == 0 and world == 1 and not args.no_cpu) else None
+    # the second half of BASELINE.json's metric ("contrastive steps/sec at 1/2/4/8 B200") rides
+    # along in the same line: a short run of the image-sharded contrastive step at this N
+    contrastive = None
+    if args.workload == "cls" and not args.no_contrastive:
+        del tok, res
+        torch.cuda.empty_cache()
+        try:
+            from radzero_b200 import bench_contrastive
+            contrastive = bench_contrastive.run(args, world, rank, local, pk, steps=3, warmup=3)
+        except Exception as e:  # never lose the main line to the add-on
+            contrastive = {"error": repr(e)}
     if rank == 0:
         line = {
             "metric": "similarity maps/sec", "value": value, "unit": "maps/s", "n_gpus": world,
@@ -278,7 +306,7 @@ def run_ours(args):
                        "input_dtype": "fp32", "l2": "inputs (1.08 GB/GPU at cls) larger than L2; no flush",
                        "parallelism": f"images sharded x{world}, no collective"},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "contrastive": contrastive,
         }
         print(json.dumps(line))
     if world > 1:
@@ -368,7 +396,26 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cls", choices=list(WORKLOADS) + ["contrastive"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-contrastive", action="store_true",
+                    help="skip the contrastive-step add-on of the default workload")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: route everything libraries print there (NCCL's
+    # version banner, warnings) to stderr and keep the real stdout for the result line only
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global print
+
+    def print(*a, **k):  # noqa: A001 -- result lines go to the saved descriptor
+        os.write(real_stdout, (" ".join(str(x) for x in a) + "\n").encode())
+
+    import builtins
+    builtins_print = builtins.print
+    try:
+        from radzero_b200 import bench_contrastive
+        bench_contrastive.print = print
+    except Exception:
+        builtins_print("bench_contrastive import failed", file=sys.stderr)
     if args.impl == "reference":
         return run_reference(args)
     if not torch.cuda.is_available():

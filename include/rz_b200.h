@@ -114,6 +114,22 @@ int rz_sim_fwd_tokens(const void* tokens_raw, int dtype, const float* gamma, con
                       int drop_cls, float* z, long long z_stride_text, long long z_stride_image,
                       float z_scale, const float* log_tau_z, int z_sigmoid, void* stream);
 
+/* Same computation for LARGE prompt sets (open-vocabulary sweeps, the contrastive step), as
+ * three full-rate tcgen05 GEMM passes (scores + log-sum-exp; normalised probabilities P as
+ * fp16; pooled vectors o = P k with |o|, <q,o> in the epilogue).  Arguments as rz_sim_fwd;
+ * tokens_padded must be a multiple of 128; want_pool = 0 with z = onorm = pooled = NULL stops
+ * after the first pass (scores and/or lse only).  workspace: 256-byte aligned,
+ * rz_sim_fwd_large_workspace_bytes(...) bytes.
+ */
+size_t rz_sim_fwd_large_workspace_bytes(int n_images, int n_text, int tokens_padded);
+int rz_sim_fwd_large(const void* k_f16, int n_images, int tokens, int tokens_padded,
+                     const void* q_f16, int n_text, float scale, const float* log_tau_scale,
+                     const float* q_inv_norm, float* scores, long long scores_stride_image,
+                     long long scores_stride_text, int drop_cls, float* z, long long z_stride_text,
+                     long long z_stride_image, float z_scale, const float* log_tau_z, int z_sigmoid,
+                     float* lse, float* onorm, void* pooled_f16, int want_pool, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 /* ---- backward of K3-K6 -------------------------------------------------------------------
  * Replaces the autograd of SimilarityLogit.forward (losses.py:187-240: the backward of bmm,
  * softmax, matmul, normalize and the batched dot) in closed form: three tcgen05 GEMM passes

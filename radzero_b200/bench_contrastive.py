@@ -1,0 +1,155 @@
+"""Benchmark of the contrastive training step (BASELINE.json configs[3]: 1024 images x ~6
+sentences each, image batch sharded over the GPUs with the text all-gather).
+
+One step = forward + backward of the fused node (radzero_b200/training.py) from
+``vision_tokens`` / ``text_features`` to their gradients (+ d gamma, d beta, d log tau);
+encoders and optimiser are outside the path.  STRONG scaling: the
+global batch is fixed, each of the W ranks owns 1024 / W images and their sentences.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import torch
+
+L, D = 1370, 768
+B_GLOBAL = 1024
+UNIT_FLOP = 2.0 * L * D            # one GEMM unit per (image, sentence) pair
+GEMM_UNITS = 6                     # fwd: S, P.K ; bwd: T, dQ, dK (x2)   (recompute of S not counted)
+
+
+def _inputs(rank, world, dev, dtype, b_global=B_GLOBAL):
+    from radzero_b200 import synthetic
+    counts_all = synthetic.sentence_counts(b_global, seed=42)
+    b_local = b_global // world
+    i0 = rank * b_local
+    counts = counts_all[i0:i0 + b_local]
+    n_local = sum(counts)
+    tok, text, gamma, beta, log_tau = synthetic.make_inputs(b_local, n_local, seed=1000 + rank, device=dev)
+    gm = synthetic.group_map_from_counts(counts, first_image=i0, device=dev)
+    return tok.to(dtype), text.to(dtype), gamma, beta, gm, sum(counts_all)
+
+
+def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
+    import torch.distributed as dist
+    from radzero_b200 import _lib, losses, training
+    dev = torch.device("cuda", local)
+    steps = steps or max(2, min(args.steps, 10))
+    warmup = warmup if warmup is not None else 3
+    dtype = torch.bfloat16
+    tok, text, gamma, beta, gm, n_total = _inputs(rank, world, dev, dtype)
+    fn = losses.RadZeroLoss(sim_op="cos").to(dev)
+    with torch.no_grad():
+        fn.layer_norm.weight.copy_(gamma)
+        fn.layer_norm.bias.copy_(beta)
+    distributed = world > 1
+
+    def step(tk, tx):
+        tk = tk.detach().requires_grad_(True)
+        tx = tx.detach().requires_grad_(True)
+        fn.zero_grad(set_to_none=True)
+        res = training.contrastive_step(fn, tx, gm, tk, distributed=distributed)
+        res["loss"].backward()
+        return res["loss"].detach(), tk.grad
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        loss, _ = step(tok, text)
+    barrier()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss, _ = step(tok, text)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    if distributed:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_step = ms / steps
+    flops = GEMM_UNITS * UNIT_FLOP * B_GLOBAL * n_total
+    ach = flops / (ms_step * 1e-3) / 1e12 / world            # per GPU
+    # end to end: host-resident inputs, loss read back
+    h_tok, h_txt = tok.cpu().pin_memory(), text.cpu().pin_memory()
+    for _ in range(1):
+        step(h_tok.to(dev, non_blocking=True), h_txt.to(dev, non_blocking=True))
+    barrier()
+    ks = 2
+    e0.record()
+    for _ in range(ks):
+        l, _ = step(h_tok.to(dev, non_blocking=True), h_txt.to(dev, non_blocking=True))
+        l_host = l.item()
+    e1.record()
+    barrier()
+    ms2 = e0.elapsed_time(e1)
+    if distributed:
+        t = torch.tensor([ms2], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms2 = float(t.item())
+    out = {
+        "metric": "contrastive steps/sec", "value": 1e3 / ms_step, "unit": "steps/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "scaling": "strong", "dtype": "f16",
+        "loss": float(loss.item()), "gpu_launches": int(launches),
+        "config": {"workload": f"C4 contrastive step, {B_GLOBAL} images x {n_total} sentences (n_i ~ U{{3..9}}), "
+                               f"image batch sharded x{world} with text all-gather",
+                   "input_dtype": "bf16", "tokens": L, "hidden": D},
+        "roofline": {"bound": "tensor", "kernel": "whole step (sim_fwd + rz_sim_bwd GEMM passes)",
+                     "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
+                     "algorithmic_flops_per_step": flops, "traffic": None,
+                     "peak_source": pk["src"] + " sustained (kernel timed inside a long step)"},
+        "e2e": {"value": 1e3 / (ms2 / ks), "unit": "steps/s",
+                "h2d_bytes_per_step": (h_tok.numel() + h_txt.numel()) * 2, "d2h_bytes_per_step": 4,
+                "api": "RadZeroLoss.forward + backward"},
+    }
+    return out
+
+
+def cpu_sample_step(b_g=16):
+    """Scaled-down CPU step on the oracle (the reference materialises (B,N,L) tensors: the full
+    size does not fit host memory)."""
+    import oracle
+    from radzero_b200 import synthetic
+    counts = synthetic.sentence_counts(b_g, seed=42)
+    n = sum(counts)
+    tok, text, gamma, beta, log_tau = synthetic.make_inputs(b_g, n, seed=1000)
+    gm = synthetic.group_map_from_counts(counts)
+    t0 = time.perf_counter()
+    oracle.contrastive_step_reference(text, gm, tok, gamma, beta, log_tau)
+    dt = time.perf_counter() - t0
+    return dt, b_g * n
+
+
+def run_reference(args):
+    import json
+    from radzero_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_total = sum(synthetic.sentence_counts(B_GLOBAL, seed=42))
+    cpu_sample_step(8)
+    t0 = time.perf_counter()
+    pairs = 0
+    for _ in range(args.steps):
+        dt, pr = cpu_sample_step(16)
+        pairs += pr
+    dt = time.perf_counter() - t0
+    full_pairs = B_GLOBAL * n_total
+    value = (pairs / dt) / full_pairs
+    print(json.dumps({
+        "metric": "contrastive steps/sec", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": 1, "ms_per_step": 1e3 / value, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"C4 contrastive step, {B_GLOBAL} images x {n_total} sentences"},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": "each step = forward+backward at 16 images x ~96 sentences on the fp32 "
+                                   "torch CPU oracle; steps/s extrapolated by the (image, sentence) pair count "
+                                   f"to {B_GLOBAL} x {n_total}"},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))

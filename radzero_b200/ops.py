@@ -64,7 +64,8 @@ def prep_rows(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[tor
 
 
 # ----------------------------------------------------------------------------- K3 - K6
-TOKEN_TILE = 64
+TOKEN_TILE = 128          # operands are padded to the GEMM token tile (1370 -> 1408)
+LARGE_N_THRESHOLD = 64    # above this many prompts the three-pass GEMM forward is used
 
 
 def padded_tokens(tokens: int) -> int:
@@ -127,7 +128,20 @@ def sim_fwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, scale: float,
     pooled = torch.empty((B, N, HIDDEN), dtype=torch.float16, device=dev) if want_pooled else None
     qin = _contig(q_inv_norm.float()) if q_inv_norm is not None else None
     lts, ltz = _log_tau_ptr(log_tau_scale), _log_tau_ptr(log_tau_z)
-    rc = _lib.load().rz_sim_fwd(
+    lib = _lib.load()
+    if N > LARGE_N_THRESHOLD and Lp % 128 == 0:
+        # more prompts than one SM's TMEM can pool (64 x 768 fp32): three full-rate GEMM passes
+        nbytes = int(lib.rz_sim_fwd_large_workspace_bytes(B, N, Lp))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        rc = lib.rz_sim_fwd_large(
+            _p(k_f16), B, int(tokens), Lp, _p(q_f16), N, float(scale), _p(lts), _p(qin),
+            _p(scores), scores.stride(0) if scores is not None else 0,
+            scores.stride(1) if scores is not None else 0, drop,
+            _p(z), zs_text, zs_img, float(z_scale), _p(ltz), 1 if z_sigmoid else 0,
+            _p(lse), _p(onorm), _p(pooled), 1 if want_z else 0, _p(ws), C.c_size_t(nbytes), _stream())
+        _lib.check(rc, "rz_sim_fwd_large")
+        return dict(scores=scores, z=z, lse=lse, onorm=onorm, pooled=pooled)
+    rc = lib.rz_sim_fwd(
         _p(k_f16), B, int(tokens), Lp, _p(q_f16), N, float(scale), _p(lts), _p(qin),
         _p(scores), scores.stride(0) if scores is not None else 0,
         scores.stride(1) if scores is not None else 0, drop,

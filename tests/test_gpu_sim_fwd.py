@@ -40,7 +40,7 @@ def _oracle(tok, text, gamma, beta, tau=TAU):
 
 
 @pytest.mark.parametrize("B,N,L", [(2, 3, 1370), (3, 14, 1370), (2, 16, 50), (1, 1, 130),
-                                   (2, 20, 200), (2, 40, 1370), (1, 64, 64), (2, 130, 333)])
+                                   (2, 20, 200), (2, 40, 1370), (1, 64, 64), (2, 130, 333), (2, 300, 1370)])
 def test_sim_fwd_vs_oracle(B, N, L):
     tok, text, gamma, beta, _ = synthetic.make_inputs(B, N, tokens_per_image=L, seed=100 + N)
     out = _run(tok, text, gamma, beta, want_scores=True, drop_cls=True, want_stats=True,

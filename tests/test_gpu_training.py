@@ -140,3 +140,20 @@ def test_similarity_logit_autograd():
     assert (z.detach().cpu().double() - zz.detach()).abs().max() < 2e-4
     assert _rel(q.grad, qd.grad) < 1e-2
     assert _rel(k.grad, kd.grad) < 1e-2
+
+
+def test_multi_gpu_sharded_step_equals_single_gpu():
+    """NCCL run of the image-sharded step on all visible GPUs (needs >= 2) vs one GPU."""
+    import os
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    world = 2 if n < 4 else 4
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                        f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(root, "tests", "multi_gpu_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert "MULTI_GPU_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
