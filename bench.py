@@ -265,13 +265,17 @@ def run_ours(args):
         h_tok = tok.cpu().pin_memory()
         h_txt = text.cpu().pin_memory()
         ksteps = max(2, min(args.steps, 5))
+        r_host = None
         for _ in range(2):
-            r = step(h_tok.to(dev, non_blocking=True), h_txt.to(dev, non_blocking=True)).cpu()
+            r = step(h_tok.to(dev, non_blocking=True), h_txt.to(dev, non_blocking=True))
+            if r_host is None:      # results land in pinned host memory (pageable D2H runs at ~3 GB/s)
+                r_host = torch.empty(r.shape, dtype=r.dtype, pin_memory=True)
+            r_host.copy_(r)
         barrier()
         e0.record()
         for _ in range(ksteps):
             r = step(h_tok.to(dev, non_blocking=True), h_txt.to(dev, non_blocking=True))
-            r_host = r.to("cpu", non_blocking=False)
+            r_host.copy_(r, non_blocking=True)
         e1.record()
         barrier()
         ms2 = e0.elapsed_time(e1)

@@ -115,8 +115,14 @@ int rz_sim_fwd_tokens(const void* tokens_raw, int dtype, const float* gamma, con
                       float z_scale, const float* log_tau_z, int z_sigmoid, void* stream);
 
 /* Same computation for LARGE prompt sets (open-vocabulary sweeps, the contrastive step), as
- * three full-rate tcgen05 GEMM passes (scores + log-sum-exp; normalised probabilities P as
- * fp16; pooled vectors o = P k with |o|, <q,o> in the epilogue).  Arguments as rz_sim_fwd;
+ * two full-rate tcgen05 GEMM passes: pass S computes the scores exactly once, one thread per
+ * prompt row keeping a lazy running maximum, and writes the similarity map plus UNNORMALISED
+ * probabilities P~ = exp(s - mref) as fp16; pass PK computes o = (P~ k) / lsum with |o| and
+ * <q,o> in the epilogue.  Arguments as rz_sim_fwd, plus
+ *   p_f16  optional fp16 [n_images, n_text, tokens_padded]: P~, kept for rz_sim_bwd (NULL: the
+ *          workspace holds it)
+ *   mref / lsum optional fp32 [n_images, n_text]: reference maximum and sum_l exp(s_l - mref)
+ *          of every (image, prompt) row (lse = mref + log lsum), kept for rz_sim_bwd
  * tokens_padded must be a multiple of 128; want_pool = 0 with z = onorm = pooled = NULL stops
  * after the first pass (scores and/or lse only).  workspace: 256-byte aligned,
  * rz_sim_fwd_large_workspace_bytes(...) bytes.
@@ -127,8 +133,9 @@ int rz_sim_fwd_large(const void* k_f16, int n_images, int tokens, int tokens_pad
                      const float* q_inv_norm, float* scores, long long scores_stride_image,
                      long long scores_stride_text, int drop_cls, float* z, long long z_stride_text,
                      long long z_stride_image, float z_scale, const float* log_tau_z, int z_sigmoid,
-                     float* lse, float* onorm, void* pooled_f16, int want_pool, void* workspace,
-                     size_t workspace_bytes, void* stream);
+                     float* lse, float* onorm, void* pooled_f16, void* p_f16, float* mref,
+                     float* lsum, int want_pool, void* workspace, size_t workspace_bytes,
+                     void* stream);
 
 /* ---- backward of K3-K6 -------------------------------------------------------------------
  * Replaces the autograd of SimilarityLogit.forward (losses.py:187-240: the backward of bmm,

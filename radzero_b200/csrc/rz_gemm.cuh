@@ -12,7 +12,11 @@
 //   V::kBN, V::kAccs (1 or 2 A operands sharing one B), V::kAMn / V::kBMn (operand is
 //   MN-major in shared memory), V::Params,
 //   V::num_tiles(p), V::k_steps(p), V::load(p, maps, tile, ks, a_smem, a2_smem, b_smem, bar),
-//   V::epilogue(p, tile, tmem_acc, warp, lane, scratch)
+//   V::epilogue(p, tile, tmem_acc, warp, lane, scratch, state, epi_smem)
+//   V::inner(p): tiles are handed to a CTA in runs of `inner` consecutive ids (one "item"), so an
+//     epilogue thread can carry V::State (registers) across the tiles of an item;
+//   V::tile_n(p, tile): MMA N of this tile (<= kBN; a narrower last tile of a run);
+//   V::kEpiSmem: bytes of shared memory reserved for the epilogue warps (staging / transposes).
 #pragma once
 
 #include "rz_common.cuh"
@@ -34,13 +38,22 @@ struct Maps {
   CUtensorMap a, a2, b, b2;
 };
 
+// defaults a policy inherits: one tile per item, full-width tiles, no epilogue state / scratch
+struct PolicyBase {
+  struct State {};
+  static constexpr int kEpiSmem = 0;
+  template <class P> __host__ __device__ static int inner(const P&) { return 1; }
+  template <class P> __host__ __device__ static int tile_n(const P&, int) { return 0; }
+};
+
 template <class V>
 struct Layout {
   static constexpr int kBBytes = V::kBN * 128;
   static constexpr int kStageBytes = V::kAccs * kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 6 ? 6 : (200 * 1024) / kStageBytes;
+  static constexpr int kBudget = 212 * 1024 - V::kEpiSmem;
+  static constexpr int kStages = kBudget / kStageBytes > 6 ? 6 : kBudget / kStageBytes;
   static constexpr int kTmemCols = 2 * V::kAccs * V::kBN;
-  static constexpr int kSmem = 1024 + kStages * kStageBytes + 1024;
+  static constexpr int kSmem = 1024 + kStages * kStageBytes + V::kEpiSmem + 1024;
   static_assert(kTmemCols <= 512, "accumulators exceed TMEM");
   static_assert(kStages >= 2, "pipeline too shallow");
 };
@@ -60,9 +73,11 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
   using L = Layout<V>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  Ctrl* ctl = reinterpret_cast<Ctrl*>(base + L::kStages * L::kStageBytes);
+  uint8_t* epi_smem = base + L::kStages * L::kStageBytes;
+  Ctrl* ctl = reinterpret_cast<Ctrl*>(epi_smem + V::kEpiSmem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_tiles = V::num_tiles(p);
+  const int inner = V::inner(p);
+  const int n_items = V::num_tiles(p) / inner;
   const int ksteps = V::k_steps(p);
 
   if (tid == 0) {
@@ -85,23 +100,29 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
   if (warp == 4) {
     if (elect_one()) {
       long long g = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int ks = 0; ks < ksteps; ++ks, ++g) {
-          const int st = (int)(g % L::kStages);
-          mbar_wait(&ctl->empty[st], (uint32_t)(((g / L::kStages) & 1) ^ 1));
-          mbar_arrive_expect_tx(&ctl->full[st], (uint32_t)L::kStageBytes);
-          uint8_t* sa = base + st * L::kStageBytes;
-          V::load(p, maps, tile, ks, sa, sa + kABytes, sa + V::kAccs * kABytes, &ctl->full[st]);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int sub = 0; sub < inner; ++sub) {
+          const int tile = item * inner + sub;
+          for (int ks = 0; ks < ksteps; ++ks, ++g) {
+            const int st = (int)(g % L::kStages);
+            mbar_wait(&ctl->empty[st], (uint32_t)(((g / L::kStages) & 1) ^ 1));
+            mbar_arrive_expect_tx(&ctl->full[st], (uint32_t)L::kStageBytes);
+            uint8_t* sa = base + st * L::kStageBytes;
+            V::load(p, maps, tile, ks, sa, sa + kABytes, sa + V::kAccs * kABytes, &ctl->full[st]);
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 5) {
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_f16(kBM, V::kBN, V::kAMn ? 1 : 0, V::kBMn ? 1 : 0);
       long long g = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+      for (int sub = 0; sub < inner; ++sub, ++it) {
+        const int tile = item * inner + sub;
+        const int tn = V::tile_n(p, tile);
+        const uint32_t idesc = make_idesc_f16(kBM, (uint32_t)(tn > 0 ? tn : V::kBN), V::kAMn ? 1 : 0, V::kBMn ? 1 : 0);
         const int acc = it & 1;
         mbar_wait(&ctl->acc_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
         tc_fence_after();
@@ -132,11 +153,14 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
     __syncwarp();
   } else {
     int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    typename V::State state;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+    for (int sub = 0; sub < inner; ++sub, ++it) {
+      const int tile = item * inner + sub;
       const int acc = it & 1;
       mbar_wait(&ctl->acc_full[acc], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      V::epilogue(p, tile, tmem_base + acc * (V::kAccs * V::kBN), warp, lane, ctl->scratch);
+      V::epilogue(p, tile, tmem_base + acc * (V::kAccs * V::kBN), warp, lane, ctl->scratch, state, epi_smem);
       tc_fence_before();
       mbar_arrive(&ctl->acc_empty[acc]);
     }
@@ -149,7 +173,7 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
 template <class V>
 int launch(const Maps& maps, const typename V::Params& p, cudaStream_t s) {
   using L = Layout<V>;
-  const int tiles = V::num_tiles(p);
+  const int tiles = V::num_tiles(p) / V::inner(p);
   if (tiles <= 0) return RZ_OK;
   const int grid = tiles < rz_sm_count() ? tiles : rz_sm_count();
   RZ_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmem));

@@ -73,7 +73,7 @@ struct DParams {
   float* dtau_part;              // [tiles] partial sums of -dL/ds * s (unscaled)
 };
 
-struct PassD {
+struct PassD : PolicyBase {
   using Params = DParams;
   static constexpr int kBN = 128, kAccs = 2;
   static constexpr bool kAMn = false, kBMn = false, kTwoPhase = false;
@@ -94,7 +94,7 @@ struct PassD {
     load_kmajor(&m.b, bar, bsm, ks * kBK, nt * kBN, b);      // k      [B, Lp, 768]
   }
   __device__ static void epilogue(const Params& p, int tile, uint32_t tmem, int warp, int lane,
-                                  float* scratch) {
+                                  float* scratch, State&, uint8_t*) {
     int b, mt, nt;
     decode(p, tile, b, mt, nt);
     const int n = mt * kBM + warp * 32 + lane;
@@ -163,7 +163,7 @@ struct QParams {
   float* dq;                      // [N, 768] fp32
 };
 
-struct PassQ {
+struct PassQ : PolicyBase {
   using Params = QParams;
   static constexpr int kBN = 256, kAccs = 1;
   static constexpr bool kAMn = false, kBMn = true, kTwoPhase = false;
@@ -177,7 +177,7 @@ struct PassQ {
     load_kmajor(&m.a, bar, a, lc * kBK, mt * kBM, b);                     // W1 [B, N, Lp]
     load_mnmajor(&m.b, bar, bsm, ft * kBN, lc * kBK, b, kBN / 64);        // k  [B, Lp, 768]
   }
-  __device__ static void epilogue(const Params& p, int tile, uint32_t tmem, int warp, int lane, float*) {
+  __device__ static void epilogue(const Params& p, int tile, uint32_t tmem, int warp, int lane, float*, State&, uint8_t*) {
     const int ft = tile % (kD / kBN), mt = tile / (kD / kBN);
     const int n = mt * kBM + warp * 32 + lane;
     const float inv_s = p.scale[1];
@@ -208,7 +208,7 @@ struct KParams {
   float* dk;                      // [B, Lp, 768] fp32
 };
 
-struct PassK {
+struct PassK : PolicyBase {
   using Params = KParams;
   static constexpr int kBN = 256, kAccs = 1;
   static constexpr bool kAMn = true, kBMn = true, kTwoPhase = true;
@@ -233,7 +233,7 @@ struct PassK {
       load_mnmajor(&m.b2, bar, bsm, ft * kBN, nc * kBK, b, kBN / 64);     // pooled [B, N, 768]
     }
   }
-  __device__ static void epilogue(const Params& p, int tile, uint32_t tmem, int warp, int lane, float*) {
+  __device__ static void epilogue(const Params& p, int tile, uint32_t tmem, int warp, int lane, float*, State&, uint8_t*) {
     int b, lt, ft;
     decode(p, tile, b, lt, ft);
     const int l = lt * kBM + warp * 32 + lane;

@@ -8,9 +8,12 @@
 
 namespace {
 
-constexpr int kBand = 8;       // canvas rows per CTA
+constexpr int kBand = 16;      // canvas rows per CTA
 constexpr int kThreads = 256;
 constexpr int kMaxGrid = 64;
+constexpr int kRowStride = kMaxGrid + 1;  // rowbuf pitch (compile-time: immediate LDS offsets)
+constexpr int kRowGroup = 4;               // rows per work item
+constexpr int kMaxOutW = 16384; // x-table lives in shared memory (8 B per canvas column)
 
 struct UpParams {
   const float* scores;
@@ -21,15 +24,21 @@ struct UpParams {
   unsigned long long* keys;
 };
 
-__device__ __forceinline__ void src_index(float scale, int dst, int n_in, int& i0, int& i1, float& w1) {
-  // ATen upsample_bilinear2d, align_corners=False: src = max(0, scale*(dst+0.5)-0.5)
+__device__ __forceinline__ void src_index(float scale, int dst, int n_in, int& i0, float& w1) {
+  // ATen upsample_bilinear2d, align_corners=False: src = max(0, scale*(dst+0.5)-0.5);
+  // i1 = i0 + (i0 < n_in-1) is realised by a duplicated last column / row in shared memory
   float src = fmaxf(fmaf(scale, (float)dst + 0.5f, -0.5f), 0.0f);
   i0 = min((int)src, n_in - 1);
-  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
   w1 = src - (float)i0;
 }
 
-__device__ __forceinline__ float fast_sigmoid(float v) { return 1.0f / (1.0f + __expf(-v)); }
+// 1 / (1 + 2^(-v log2 e)): two MUFU ops (ex2, rcp), ~3e-7 absolute error
+__device__ __forceinline__ float fast_sigmoid(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 
 __device__ __forceinline__ unsigned long long argmax_key(float v, unsigned int flat) {
   unsigned int u = __float_as_uint(v);
@@ -37,99 +46,149 @@ __device__ __forceinline__ unsigned long long argmax_key(float v, unsigned int f
   return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
 }
 
-template <int MODE, int V>
+// x-table entry: source column a (bit 31 set = outside the pasted area -> fill) and weight of
+// column a+1.  One CTA = one band of kBand canvas rows of one map:
+//   1. the grid rows the band touches are staged in shared memory,
+//   2. each canvas row is interpolated vertically ONCE into rowbuf[r][0..G] (last column
+//      duplicated so that a+1 is always readable),
+//   3. the x-table (a, w) of every canvas column is computed once per CTA,
+//   4. threads sweep the band's V-pixel vectors: 1 table load, 2 row loads and one lerp per
+//      pixel, the fused consumer, one coalesced streaming vector store.
+template <int MODE, int V, bool PLAIN>
 __global__ void __launch_bounds__(kThreads)
 upsample_kernel(UpParams p) {
-  extern __shared__ float smem[];
-  float* gbuf = smem;                                   // [rows_needed][grid]
-  float* rowbuf = smem + kMaxGrid * kMaxGrid;           // [kBand][grid]
+  extern __shared__ __align__(16) float smem[];
+  const int G = p.grid;
+  float2* xtab = reinterpret_cast<float2*>(smem);               // [out_w rounded up to V]
+  const int wpad = (p.out_w + V - 1) / V * V;
+  float* rowbuf = smem + 2 * wpad;                              // [kBand][kRowStride]
+  float* gbuf = rowbuf + kBand * kRowStride;                          // [rows needed <= G][G]
   const int map = blockIdx.y;
   const int y_first = blockIdx.x * kBand;
   const int rows_here = min(kBand, p.out_h - y_first);
   const float* g = p.scores + (long long)map * p.map_stride;
-  const int G = p.grid;
 
-  // grid rows this band touches
+  // grid rows this band touches (vertical source index is monotone in y)
   int ylo = G, yhi = -1;
-  for (int r = 0; r < rows_here; ++r) {
-    const int iy = y_first + r - p.off_y;
-    if (iy < 0 || iy >= p.interp_h) continue;
-    int a, b; float w;
-    src_index(p.scale_h, iy, G, a, b, w);
-    ylo = min(ylo, a); yhi = max(yhi, b);
+  {
+    const int iy0 = max(y_first - p.off_y, 0), iy1 = min(y_first + rows_here - 1 - p.off_y, p.interp_h - 1);
+    if (iy0 <= iy1) {
+      int a; float w;
+      src_index(p.scale_h, iy0, G, a, w); ylo = a;
+      src_index(p.scale_h, iy1, G, a, w); yhi = min(a + 1, G - 1);
+    }
   }
   if (yhi >= ylo) {
     const int n = (yhi - ylo + 1) * G;
     for (int i = threadIdx.x; i < n; i += kThreads) gbuf[i] = __ldg(g + ylo * G + i);
   }
+  for (int x = threadIdx.x; x < wpad; x += kThreads) {
+    const int ix = x - p.off_x;
+    int a = 0; float w = 0.f;
+    if (ix >= 0 && ix < p.interp_w && x < p.out_w) src_index(p.scale_w, ix, G, a, w);
+    else a = (int)0x80000000u;
+    xtab[x] = make_float2(__int_as_float(a), w);
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < rows_here * G; i += kThreads) {
-    const int r = i / G, c = i - r * G;
+  for (int i = threadIdx.x; i < rows_here * (G + 1); i += kThreads) {
+    const int r = i / (G + 1), c1 = i - r * (G + 1), c = min(c1, G - 1);
     const int iy = y_first + r - p.off_y;
     float v = 0.f;
     if (iy >= 0 && iy < p.interp_h) {
-      int a, b; float w;
-      src_index(p.scale_h, iy, G, a, b, w);
+      int a; float w;
+      src_index(p.scale_h, iy, G, a, w);
+      const int b = min(a + 1, G - 1);
       v = (1.0f - w) * gbuf[(a - ylo) * G + c] + w * gbuf[(b - ylo) * G + c];
     }
-    rowbuf[r * G + c] = v;
+    rowbuf[r * kRowStride + c1] = v;
   }
   __syncthreads();
 
-  const int vec_per_row = p.out_w / V;
+  // work item = V adjacent canvas columns x kRowGroup consecutive rows: the x-table entry is
+  // loaded once per item and the row loop is unrolled with immediate shared-memory offsets
+  const int vec_per_row = wpad / V;
+  const int n_groups = (rows_here + kRowGroup - 1) / kRowGroup;
+  const int items = vec_per_row * n_groups;
   unsigned long long best = 0ull;
-  for (int i = threadIdx.x; i < rows_here * vec_per_row; i += kThreads) {
-    const int r = i / vec_per_row;
-    const int xv = i - r * vec_per_row;
-    const int y = y_first + r;
-    const int iy = y - p.off_y;
-    const bool row_in = (iy >= 0 && iy < p.interp_h);
-    float val[V];
+  int grp = threadIdx.x / vec_per_row;
+  int xv = threadIdx.x - grp * vec_per_row;
+  for (int it = threadIdx.x; it < items; it += kThreads) {
+    float2 t[V];
+    if constexpr (V == 4) {
+      const float4 t0 = *reinterpret_cast<const float4*>(xtab + xv * 4);
+      const float4 t1 = *reinterpret_cast<const float4*>(xtab + xv * 4 + 2);
+      t[0] = make_float2(t0.x, t0.y); t[1] = make_float2(t0.z, t0.w);
+      t[2] = make_float2(t1.x, t1.y); t[3] = make_float2(t1.z, t1.w);
+    } else if constexpr (V == 2) {
+      const float4 t0 = *reinterpret_cast<const float4*>(xtab + xv * 2);
+      t[0] = make_float2(t0.x, t0.y); t[1] = make_float2(t0.z, t0.w);
+    } else {
+      t[0] = xtab[xv];
+    }
+    const float* src[V];
+    float w1[V], w0[V];
+    bool inside[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-      const int ix = xv * V + k - p.off_x;
-      float v = p.fill;
-      if (row_in && ix >= 0 && ix < p.interp_w) {
-        int a, b; float w;
-        src_index(p.scale_w, ix, G, a, b, w);
-        v = (1.0f - w) * rowbuf[r * G + a] + w * rowbuf[r * G + b];
-      }
-      val[k] = v;
+      const int a = __float_as_int(t[k].x);
+      inside[k] = PLAIN || a >= 0;
+      src[k] = rowbuf + (grp * kRowGroup) * kRowStride + (a & 0xffff);
+      w1[k] = t[k].y;
+      w0[k] = 1.0f - w1[k];
     }
-    const long long o = ((long long)map * p.out_h + y) * p.out_w + (long long)xv * V;
-    if constexpr (MODE == RZ_UP_RAW || MODE == RZ_UP_SIGMOID) {
-      if constexpr (MODE == RZ_UP_SIGMOID) {
+    const int y0 = y_first + grp * kRowGroup;
+    long long o = ((long long)map * p.out_h + y0) * p.out_w + (long long)xv * V;
 #pragma unroll
-        for (int k = 0; k < V; ++k) val[k] = fast_sigmoid(val[k]);
-      }
-      float* out = static_cast<float*>(p.out) + o;
-      if constexpr (V == 4) {
-        __stcs(reinterpret_cast<float4*>(out), make_float4(val[0], val[1], val[2], val[3]));
-      } else if constexpr (V == 2) {
-        __stcs(reinterpret_cast<float2*>(out), make_float2(val[0], val[1]));
-      } else {
-        __stcs(out, val[0]);
-      }
-    } else if constexpr (MODE == RZ_UP_MASK) {
-      // sigmoid(v) > t  <=>  v > logit(t) (monotone); compare in the score domain
-      unsigned char* out = static_cast<unsigned char*>(p.out) + o;
-      if constexpr (V == 4) {
-        unsigned int w = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) w |= (val[k] > p.thr_logit ? 1u : 0u) << (8 * k);
-        __stcs(reinterpret_cast<unsigned int*>(out), w);
-      } else {
-#pragma unroll
-        for (int k = 0; k < V; ++k) out[k] = val[k] > p.thr_logit ? 1 : 0;
-      }
-    } else {  // ARGMAX
+    for (int rr = 0; rr < kRowGroup; ++rr, o += p.out_w) {
+      const int y = y0 + rr;
+      if (y >= p.out_h) break;
+      bool row_in = true;
+      if constexpr (!PLAIN) { const int iy = y - p.off_y; row_in = (iy >= 0 && iy < p.interp_h); }
+      float val[V];
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        const unsigned int flat = (unsigned int)(y * p.out_w + xv * V + k);
-        const unsigned long long key = argmax_key(val[k], flat);
-        best = key > best ? key : best;
+        const float v = w0[k] * src[k][rr * kRowStride] + w1[k] * src[k][rr * kRowStride + 1];
+        val[k] = (PLAIN || (inside[k] && row_in)) ? v : p.fill;
+      }
+      if constexpr (MODE == RZ_UP_RAW || MODE == RZ_UP_SIGMOID) {
+        if constexpr (MODE == RZ_UP_SIGMOID) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) val[k] = fast_sigmoid(val[k]);
+        }
+        float* out = static_cast<float*>(p.out) + o;
+        if constexpr (V == 4) {
+          __stcs(reinterpret_cast<float4*>(out), make_float4(val[0], val[1], val[2], val[3]));
+        } else if constexpr (V == 2) {
+          __stcs(reinterpret_cast<float2*>(out), make_float2(val[0], val[1]));
+        } else {
+          __stcs(out, val[0]);
+        }
+      } else if constexpr (MODE == RZ_UP_MASK) {
+        // sigmoid(v) > t  <=>  v > logit(t) (monotone); compare in the score domain
+        unsigned char* out = static_cast<unsigned char*>(p.out) + o;
+        if constexpr (V == 4) {
+          unsigned int w = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) w |= (val[k] > p.thr_logit ? 1u : 0u) << (8 * k);
+          __stcs(reinterpret_cast<unsigned int*>(out), w);
+        } else if constexpr (V == 2) {
+          const unsigned short w = (unsigned short)((val[0] > p.thr_logit ? 1u : 0u) |
+                                                    ((val[1] > p.thr_logit ? 1u : 0u) << 8));
+          __stcs(reinterpret_cast<unsigned short*>(out), w);
+        } else {
+          out[0] = val[0] > p.thr_logit ? 1 : 0;
+        }
+      } else {  // ARGMAX
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const unsigned int flat = (unsigned int)(y * p.out_w + xv * V + k);
+          const unsigned long long key = argmax_key(val[k], flat);
+          best = key > best ? key : best;
+        }
       }
     }
+    xv += kThreads;
+    while (xv >= vec_per_row) { xv -= vec_per_row; ++grp; }
   }
   if constexpr (MODE == RZ_UP_ARGMAX) {
 #pragma unroll
@@ -158,28 +217,36 @@ __global__ void argmax_decode_kernel(long long* out, int maps, int out_w) {
   out[2 * i + 1] = (long long)(flat / (unsigned int)out_w);
 }
 
-template <int MODE>
-int launch_mode(const UpParams& p, int maps, cudaStream_t s) {
+template <int MODE, int V>
+int launch_v(const UpParams& p, int maps, cudaStream_t s) {
   dim3 grid((p.out_h + kBand - 1) / kBand, maps), block(kThreads);
-  const size_t smem = (size_t)(kMaxGrid * kMaxGrid + kBand * kMaxGrid) * sizeof(float);
-  const bool al16 = (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
-  int v = 1;
-  if (MODE == RZ_UP_ARGMAX) v = (p.out_w % 4 == 0) ? 4 : (p.out_w % 2 == 0 ? 2 : 1);
-  else if (al16 && p.out_w % 4 == 0) v = 4;
-  else if (al16 && p.out_w % 2 == 0 && MODE != RZ_UP_MASK) v = 2;
-  if (v == 4) {
-    cudaFuncSetAttribute(upsample_kernel<MODE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    upsample_kernel<MODE, 4><<<grid, block, smem, s>>>(p);
-  } else if (v == 2) {
-    cudaFuncSetAttribute(upsample_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    upsample_kernel<MODE, 2><<<grid, block, smem, s>>>(p);
+  const int wpad = (p.out_w + V - 1) / V * V;
+  const size_t smem = (size_t)(2 * wpad + kBand * kRowStride + p.grid * p.grid) * sizeof(float);
+  // PLAIN: the resized grid covers the canvas exactly (BlipImageProcessor branch) -- no fill
+  const bool plain = p.off_x == 0 && p.off_y == 0 && p.interp_h == p.out_h && p.interp_w == p.out_w;
+  if (plain) {
+    RZ_CUDA_OK(cudaFuncSetAttribute(upsample_kernel<MODE, V, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    upsample_kernel<MODE, V, true><<<grid, block, smem, s>>>(p);
   } else {
-    cudaFuncSetAttribute(upsample_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    upsample_kernel<MODE, 1><<<grid, block, smem, s>>>(p);
+    RZ_CUDA_OK(cudaFuncSetAttribute(upsample_kernel<MODE, V, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    upsample_kernel<MODE, V, false><<<grid, block, smem, s>>>(p);
   }
   RZ_LAUNCH_OK();
   rz_count_launch();
   return RZ_OK;
+}
+
+template <int MODE>
+int launch_mode(const UpParams& p, int maps, cudaStream_t s) {
+  if (MODE == RZ_UP_ARGMAX) return launch_v<MODE, 1>(p, maps, s);
+  // vector stores need every canvas row to start on a vector boundary
+  const uintptr_t base = reinterpret_cast<uintptr_t>(p.out);
+  const int esz = (MODE == RZ_UP_MASK) ? 1 : 4;
+  if (p.out_w % 4 == 0 && base % (4 * esz) == 0) return launch_v<MODE, 4>(p, maps, s);
+  if (p.out_w % 2 == 0 && base % (2 * esz) == 0) return launch_v<MODE, 2>(p, maps, s);
+  return launch_v<MODE, 1>(p, maps, s);
 }
 
 }  // namespace
@@ -192,6 +259,7 @@ extern "C" int rz_upsample_maps(const float* scores, long long map_stride, int m
   if (maps < 0 || grid <= 0 || grid > kMaxGrid || out_h <= 0 || out_w <= 0 || interp_h <= 0 ||
       interp_w <= 0)
     return RZ_ERR_INVALID;
+  if (out_w > kMaxOutW) return RZ_ERR_UNSUPPORTED;
   if (maps == 0) return RZ_OK;
   if (maps > 65535) return RZ_ERR_UNSUPPORTED;  // gridDim.y; callers chunk larger batches
   if ((long long)out_h * out_w >= (1ll << 32)) return RZ_ERR_UNSUPPORTED;

@@ -130,17 +130,24 @@ def sim_fwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, scale: float,
     lts, ltz = _log_tau_ptr(log_tau_scale), _log_tau_ptr(log_tau_z)
     lib = _lib.load()
     if N > LARGE_N_THRESHOLD and Lp % 128 == 0:
-        # more prompts than one SM's TMEM can pool (64 x 768 fp32): three full-rate GEMM passes
+        # more prompts than one SM's TMEM can pool (64 x 768 fp32): two full-rate GEMM passes
         nbytes = int(lib.rz_sim_fwd_large_workspace_bytes(B, N, Lp))
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        pt = mref = lsum = None
+        if want_pooled:     # the training path keeps P~ and its row statistics for rz_sim_bwd
+            pt = torch.empty((B, N, Lp), dtype=torch.float16, device=dev)
+            mref = torch.empty((B, N), dtype=torch.float32, device=dev)
+            lsum = torch.empty((B, N), dtype=torch.float32, device=dev)
+            nbytes -= B * N * Lp * 2
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
         rc = lib.rz_sim_fwd_large(
             _p(k_f16), B, int(tokens), Lp, _p(q_f16), N, float(scale), _p(lts), _p(qin),
             _p(scores), scores.stride(0) if scores is not None else 0,
             scores.stride(1) if scores is not None else 0, drop,
             _p(z), zs_text, zs_img, float(z_scale), _p(ltz), 1 if z_sigmoid else 0,
-            _p(lse), _p(onorm), _p(pooled), 1 if want_z else 0, _p(ws), C.c_size_t(nbytes), _stream())
+            _p(lse), _p(onorm), _p(pooled), _p(pt), _p(mref), _p(lsum), 1 if want_z else 0, _p(ws),
+            C.c_size_t(ws.numel()), _stream())
         _lib.check(rc, "rz_sim_fwd_large")
-        return dict(scores=scores, z=z, lse=lse, onorm=onorm, pooled=pooled)
+        return dict(scores=scores, z=z, lse=lse, onorm=onorm, pooled=pooled, p=pt, mref=mref, lsum=lsum)
     rc = lib.rz_sim_fwd(
         _p(k_f16), B, int(tokens), Lp, _p(q_f16), N, float(scale), _p(lts), _p(qin),
         _p(scores), scores.stride(0) if scores is not None else 0,
@@ -148,7 +155,7 @@ def sim_fwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, scale: float,
         _p(z), zs_text, zs_img, float(z_scale), _p(ltz), 1 if z_sigmoid else 0,
         _p(lse), _p(onorm), _p(pooled), _stream())
     _lib.check(rc, "rz_sim_fwd")
-    return dict(scores=scores, z=z, lse=lse, onorm=onorm, pooled=pooled)
+    return dict(scores=scores, z=z, lse=lse, onorm=onorm, pooled=pooled, p=None, mref=None, lsum=None)
 
 
 FUSED_PREP_MAX_TEXT = 16
