@@ -12,7 +12,7 @@
 //   V::kBN, V::kAccs (1 or 2 A operands sharing one B), V::kAMn / V::kBMn (operand is
 //   MN-major in shared memory), V::Params,
 //   V::num_tiles(p), V::k_steps(p), V::load(p, maps, tile, ks, a_smem, a2_smem, b_smem, bar),
-//   V::epilogue(p, tile, tmem_acc, warp, lane, scratch, state, epi_smem)
+//   V::epilogue(p, maps, tile, tmem_acc, warp, lane, scratch, state, epi_smem)
 //   V::inner(p): tiles are handed to a CTA in runs of `inner` consecutive ids (one "item"), so an
 //     epilogue thread can carry V::State (registers) across the tiles of an item;
 //   V::tile_n(p, tile): MMA N of this tile (<= kBN; a narrower last tile of a run);
@@ -35,7 +35,8 @@ constexpr int kMnBlock = 64 * 128;       // MN-major block: 64 K-rows x 128 B
 constexpr int kThreads = 192;
 
 struct Maps {
-  CUtensorMap a, a2, b, b2;
+  CUtensorMap a, a2, b, b2;   // operand loads
+  CUtensorMap c, c2;          // epilogue TMA stores
 };
 
 // defaults a policy inherits: one tile per item, full-width tiles, no epilogue state / scratch
@@ -50,7 +51,8 @@ template <class V>
 struct Layout {
   static constexpr int kBBytes = V::kBN * 128;
   static constexpr int kStageBytes = V::kAccs * kABytes + kBBytes;
-  static constexpr int kBudget = 212 * 1024 - V::kEpiSmem;
+  // 227 KB of dynamic shared memory per CTA, minus alignment slack + control block
+  static constexpr int kBudget = 232448 - 2048 - V::kEpiSmem;
   static constexpr int kStages = kBudget / kStageBytes > 6 ? 6 : kBudget / kStageBytes;
   static constexpr int kTmemCols = 2 * V::kAccs * V::kBN;
   static constexpr int kSmem = 1024 + kStages * kStageBytes + V::kEpiSmem + 1024;
@@ -153,17 +155,20 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
     __syncwarp();
   } else {
     int it = 0;
-    typename V::State state;
+    typename V::State state{};
     for (int item = blockIdx.x; item < n_items; item += gridDim.x)
     for (int sub = 0; sub < inner; ++sub, ++it) {
       const int tile = item * inner + sub;
       const int acc = it & 1;
       mbar_wait(&ctl->acc_full[acc], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      V::epilogue(p, tile, tmem_base + acc * (V::kAccs * V::kBN), warp, lane, ctl->scratch, state, epi_smem);
+      V::epilogue(p, maps, tile, tmem_base + acc * (V::kAccs * V::kBN), warp, lane, ctl->scratch, state,
+                  epi_smem);
       tc_fence_before();
       mbar_arrive(&ctl->acc_empty[acc]);
     }
+    // bulk stores issued by epilogue lanes must have read their staging buffers before exit
+    if (V::kEpiSmem > 0 && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -194,6 +199,16 @@ __device__ __forceinline__ void load_mnmajor(const CUtensorMap* m, uint64_t* bar
                                              int mn0, int k0, int batch, int blocks) {
   for (int i = 0; i < blocks; ++i)
     tma_load_3d(m, bar, dst + i * kMnBlock, mn0 + i * 64, k0, batch, kEvictNormal);
+}
+
+// byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a SWIZZLE_128B staging box
+// (rows of 128 B; the box base is 1024-byte aligned)
+__device__ __forceinline__ uint32_t stage_off(int row, int chunk) {
+  return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ void sts_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
 }
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {

@@ -77,6 +77,8 @@ struct PassD : PolicyBase {
   using Params = DParams;
   static constexpr int kBN = 128, kAccs = 2;
   static constexpr bool kAMn = false, kBMn = false, kTwoPhase = false;
+  // per-warp TMA-store staging: one 64-column fp16 box (32 rows x 128 B, SWIZZLE_128B) each for W1, W2
+  static constexpr int kEpiSmem = 4 * 8192;
   __host__ __device__ static int num_tiles(const Params& p) { return p.B * p.m_tiles * p.n_tiles; }
   __host__ __device__ static int k_steps(const Params&) { return kD / kBK; }
   __device__ static void decode(const Params& p, int tile, int& b, int& mt, int& nt) {
@@ -93,64 +95,93 @@ struct PassD : PolicyBase {
     load_kmajor(&m.a2, bar, a2, ks * kBK, mt * kBM, b);      // pooled [B, N, 768]
     load_kmajor(&m.b, bar, bsm, ks * kBK, nt * kBN, b);      // k      [B, Lp, 768]
   }
-  __device__ static void epilogue(const Params& p, int tile, uint32_t tmem, int warp, int lane,
-                                  float* scratch, State&, uint8_t*) {
-    int b, mt, nt;
-    decode(p, tile, b, mt, nt);
-    const int n = mt * kBM + warp * 32 + lane;
-    const bool row_ok = n < p.N;
-    const float inv_tau = p.log_tau != nullptr ? __expf(-__ldg(p.log_tau)) : p.inv_tau;
-    const float tau = 1.0f / inv_tau;
-    const long long pi = (long long)b * p.N + (row_ok ? n : 0);
-    const float lse = row_ok ? p.lse[pi] : 0.f;
-    const float S = p.scale[0];
-    const float a = row_ok ? p.coef_a[pi] : 0.f;
-    const float aS = a * S;
-    const float r = row_ok ? p.coef_r[pi] : 0.f;
-    const float rt = r * inv_tau;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    __half* w1 = p.w1 + ((long long)b * p.N + n) * p.Lp + nt * kBN;
-    __half* w2 = p.w2 + ((long long)b * p.N + n) * p.Lp + nt * kBN;
-    float dls = 0.f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < kBN; c0 += 16) {
-      uint32_t sv[16], tv[16];
-      tmem_ld_x16(tmem + lane_base + c0, sv);
-      tmem_ld_x16(tmem + lane_base + kBN + c0, tv);
-      tmem_ld_wait();
-      uint32_t o1[8], o2[8];
+  struct Row {
+    float inv_tau, lse2, aS, c2, rt;     // lse2 = lse * log2(e); c2 = -aS * r; rt = r / tau
+  };
+  // 32 columns of S and T of this thread's row -> half of a staged 64-column W1 / W2 box
+  __device__ static __forceinline__ void chunk(const Params& p, uint32_t (&sv)[32], uint32_t (&tv)[32],
+                                               int l0, int half, int lane, const Row& r, uint32_t stg,
+                                               float& u) {
+    const bool full = l0 + 32 <= p.L;
 #pragma unroll
-      for (int i = 0; i < 16; i += 2) {
+    for (int j = 0; j < 4; ++j) {
+      uint32_t o1[4], o2[4];
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
         float w1v[2], w2v[2];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int l = nt * kBN + c0 + i + u;
-          const float s = __uint_as_float(sv[i + u]) * inv_tau;
-          const float t = __uint_as_float(tv[i + u]);
-          const float pr = (l < p.L) ? exp2f((s - lse) * kLog2e) : 0.f;
-          const float e = s - rt * t;               // (s - (r/tau) T)
-          w1v[u] = aS * pr * (1.0f + e);
-          w2v[u] = -aS * r * pr;
-          dls = fmaf(-a * tau * pr * e, s, dls);    // -dL/ds * s
+        for (int q = 0; q < 2; ++q) {
+          const int c = 8 * j + i + q;
+          const float s = __uint_as_float(sv[c]) * r.inv_tau;
+          const float t = __uint_as_float(tv[c]);
+          float pr = exp2f(fmaf(s, kLog2e, -r.lse2));
+          if (!full && l0 + c >= p.L) pr = 0.f;
+          const float e = fmaf(-r.rt, t, s);        // s - (r/tau) T
+          const float x = r.aS * pr;
+          w1v[q] = fmaf(x, e, x);                   // aS p (1 + e)
+          w2v[q] = r.c2 * pr;                       // -aS r p
+          u = fmaf(pr * e, s, u);                   // dL/dlog tau = -a tau sum p e s
         }
         o1[i >> 1] = pack_h2(w1v[0], w1v[1]);
         o2[i >> 1] = pack_h2(w2v[0], w2v[1]);
       }
-      if (row_ok) {
-        uint4* d1 = reinterpret_cast<uint4*>(w1 + c0);
-        uint4* d2 = reinterpret_cast<uint4*>(w2 + c0);
-        d1[0] = make_uint4(o1[0], o1[1], o1[2], o1[3]);
-        d1[1] = make_uint4(o1[4], o1[5], o1[6], o1[7]);
-        d2[0] = make_uint4(o2[0], o2[1], o2[2], o2[3]);
-        d2[1] = make_uint4(o2[4], o2[5], o2[6], o2[7]);
+      sts_v4(stg + stage_off(lane, 4 * half + j), o1[0], o1[1], o1[2], o1[3]);
+      sts_v4(stg + 4096 + stage_off(lane, 4 * half + j), o2[0], o2[1], o2[2], o2[3]);
+    }
+  }
+  __device__ static __forceinline__ void ld2(uint32_t taddr, int c0, uint32_t (&sv)[32], uint32_t (&tv)[32]) {
+    tmem_ld_x32(taddr + c0, sv);
+    tmem_ld_x32(taddr + kBN + c0, tv);
+  }
+  __device__ static __forceinline__ void wait2(uint32_t (&sv)[32], uint32_t (&tv)[32]) {
+    tmem_ld_wait_x32(sv);
+    tmem_ld_wait_x32(tv);
+  }
+  __device__ static void epilogue(const Params& p, const Maps& maps, int tile, uint32_t tmem, int warp,
+                                  int lane, float*, State&, uint8_t* epi_smem) {
+    int b, mt, nt;
+    decode(p, tile, b, mt, nt);
+    const int row0 = mt * kBM + warp * 32;
+    const int n = row0 + lane;
+    const bool row_ok = n < p.N;
+    const long long pi = (long long)b * p.N + (row_ok ? n : 0);
+    Row r;
+    r.inv_tau = p.log_tau != nullptr ? __expf(-__ldg(p.log_tau)) : p.inv_tau;
+    const float tau = 1.0f / r.inv_tau;
+    r.lse2 = (row_ok ? p.lse[pi] : 0.f) * kLog2e;
+    const float a = row_ok ? p.coef_a[pi] : 0.f;
+    const float rr = row_ok ? p.coef_r[pi] : 0.f;
+    r.aS = a * p.scale[0];
+    r.c2 = -r.aS * rr;
+    r.rt = rr * r.inv_tau;
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t stg = smem_u32(epi_smem) + warp * 8192;
+    const int tok0 = nt * kBN;
+    float u = 0.f;
+    uint32_t sa[32], ta[32], sb[32], tb[32];
+    ld2(taddr, 0, sa, ta);
+#pragma unroll 1
+    for (int c = 0; c < kBN; c += 64) {
+      wait2(sa, ta);
+      ld2(taddr, c + 32, sb, tb);
+      // the staging boxes were last read by the bulk stores of the previous 64 columns
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+      chunk(p, sa, ta, tok0 + c, 0, lane, r, stg, u);
+      wait2(sb, tb);
+      if (c + 64 < kBN) ld2(taddr, c + 64, sa, ta);
+      chunk(p, sb, tb, tok0 + c + 32, 1, lane, r, stg, u);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&maps.c, stg, tok0 + c, row0, b);             // W1 [B, N, Lp]
+        tma_store_3d(&maps.c2, stg + 4096, tok0 + c, row0, b);     // W2 [B, N, Lp]
+        tma_store_commit();
       }
     }
-    // deterministic per-tile partial of dL/dlog(tau_attn)
-    dls = rz::warp_sum(dls);
-    if (lane == 0) scratch[warp] = dls;
-    named_bar_sync(1, 128);
-    if (warp == 0 && lane == 0) p.dtau_part[tile] = scratch[0] + scratch[1] + scratch[2] + scratch[3];
-    named_bar_sync(1, 128);
+    // deterministic per-(tile, warp) partial of dL/dlog(tau_attn) = -a tau sum_l p e s
+    u = rz::warp_sum(-a * tau * u);
+    if (lane == 0) p.dtau_part[(long long)tile * 4 + warp] = u;
   }
 };
 
@@ -177,7 +208,8 @@ struct PassQ : PolicyBase {
     load_kmajor(&m.a, bar, a, lc * kBK, mt * kBM, b);                     // W1 [B, N, Lp]
     load_mnmajor(&m.b, bar, bsm, ft * kBN, lc * kBK, b, kBN / 64);        // k  [B, Lp, 768]
   }
-  __device__ static void epilogue(const Params& p, int tile, uint32_t tmem, int warp, int lane, float*, State&, uint8_t*) {
+  __device__ static void epilogue(const Params& p, const Maps&, int tile, uint32_t tmem, int warp, int lane,
+                                  float*, State&, uint8_t*) {
     const int ft = tile % (kD / kBN), mt = tile / (kD / kBN);
     const int n = mt * kBM + warp * 32 + lane;
     const float inv_s = p.scale[1];
@@ -233,7 +265,8 @@ struct PassK : PolicyBase {
       load_mnmajor(&m.b2, bar, bsm, ft * kBN, nc * kBK, b, kBN / 64);     // pooled [B, N, 768]
     }
   }
-  __device__ static void epilogue(const Params& p, int tile, uint32_t tmem, int warp, int lane, float*, State&, uint8_t*) {
+  __device__ static void epilogue(const Params& p, const Maps&, int tile, uint32_t tmem, int warp, int lane,
+                                  float*, State&, uint8_t*) {
     int b, lt, ft;
     decode(p, tile, b, lt, ft);
     const int l = lt * kBM + warp * 32 + lane;
@@ -276,7 +309,7 @@ extern "C" size_t rz_sim_bwd_workspace_bytes(int n_images, int n_text, int token
   const size_t pairs = (size_t)n_images * n_text;
   const size_t w = pairs * (size_t)tokens_padded * sizeof(__half);     // one of W1 / W2
   const size_t tiles = (size_t)n_images * ((n_text + 127) / 128) * (tokens_padded / 128);
-  return 2 * w + 2 * pairs * sizeof(float) + tiles * sizeof(float) + 256;
+  return 2 * w + 2 * pairs * sizeof(float) + 4 * tiles * sizeof(float) + 256;
 }
 
 extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int tokens_padded,
@@ -305,7 +338,7 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
   float* dtau_part = coef_r + pairs;
   const int m_tiles = (N + 127) / 128, n_tiles = Lp / 128;
   const int d_tiles = B * m_tiles * n_tiles;
-  float* scale = dtau_part + d_tiles;                      // [2]
+  float* scale = dtau_part + 4 * (size_t)d_tiles;          // [2]
   unsigned int* amax = reinterpret_cast<unsigned int*>(scale + 2);
 
   RZ_CUDA_OK(cudaMemsetAsync(amax, 0, sizeof(unsigned int), s));
@@ -320,24 +353,26 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
 
   // ---- pass D
   {
-    Maps m;
+    Maps m = {};
     if (!rz::make_map_3d_sw128(&m.a, q_f16, 1, N, kD, kD * 2, (uint64_t)N * kD * 2, kBM)) return RZ_ERR_CUDA;
     if (!rz::make_map_3d_sw128(&m.a2, pooled_f16, B, N, kD, kD * 2, (uint64_t)N * kD * 2, kBM)) return RZ_ERR_CUDA;
     if (!rz::make_map_3d_sw128(&m.b, k_f16, B, Lp, kD, kD * 2, (uint64_t)Lp * kD * 2, 128)) return RZ_ERR_CUDA;
     m.b2 = m.b;
+    if (!rz::make_map_3d_sw128(&m.c, w1, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, 32)) return RZ_ERR_CUDA;
+    if (!rz::make_map_3d_sw128(&m.c2, w2, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, 32)) return RZ_ERR_CUDA;
     DParams p;
     p.B = B; p.N = N; p.L = tokens; p.Lp = Lp; p.m_tiles = m_tiles; p.n_tiles = n_tiles;
     p.inv_tau = inv_tau; p.log_tau = log_tau; p.lse = lse; p.coef_a = coef_a; p.coef_r = coef_r;
     p.scale = scale; p.w1 = w1; p.w2 = w2; p.dtau_part = dtau_part;
     int rc = launch<PassD>(m, p, s);
     if (rc != RZ_OK) return rc;
-    sum_partials_kernel<<<1, 1024, 0, s>>>(dtau_part, d_tiles, dlog_tau);
+    sum_partials_kernel<<<1, 1024, 0, s>>>(dtau_part, 4 * d_tiles, dlog_tau);
     RZ_LAUNCH_OK();
     rz_count_launch();
   }
   // ---- pass Q
   {
-    Maps m;
+    Maps m = {};
     if (!rz::make_map_3d_sw128(&m.a, w1, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, kBM)) return RZ_ERR_CUDA;
     if (!rz::make_map_3d_sw128(&m.b, k_f16, B, Lp, kD, kD * 2, (uint64_t)Lp * kD * 2, 64)) return RZ_ERR_CUDA;
     m.a2 = m.a; m.b2 = m.b;
@@ -348,7 +383,7 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
   }
   // ---- pass K
   {
-    Maps m;
+    Maps m = {};
     if (!rz::make_map_3d_sw128(&m.a, w1, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, 64)) return RZ_ERR_CUDA;
     if (!rz::make_map_3d_sw128(&m.a2, w2, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, 64)) return RZ_ERR_CUDA;
     if (!rz::make_map_3d_sw128(&m.b, q_f16, 1, N, kD, kD * 2, (uint64_t)N * kD * 2, 64)) return RZ_ERR_CUDA;

@@ -29,19 +29,36 @@ struct S2Params {
   int B, N, L, Lp, m_tiles, n_tiles;
   float scale;
   const float* log_tau_scale;
-  float* scores; long long scores_sb, scores_sn; int drop_cls;
-  __half* p_out;               // [B, N, Lp]  exp(s - mref)
+  __half* p_out;               // [B, N, Lp]  exp(s - mref)   (written through maps.a2)
   float* mref;                 // [B, N]
   float* lsum;                 // [B, N]      sum_l exp(s - mref)
   float* lse;                  // optional [B, N] = mref + log(lsum)
 };
 
+// 64 accumulator columns of this thread's row: two tcgen05.ld.x32 in flight
+struct Cols64 {
+  uint32_t lo[32], hi[32];
+};
+__device__ __forceinline__ void ld64(uint32_t taddr, Cols64& v) {
+  tmem_ld_x32(taddr, v.lo);
+  tmem_ld_x32(taddr + 32, v.hi);
+}
+__device__ __forceinline__ void wait64(Cols64& v) {
+  tmem_ld_wait_x32(v.lo);
+  tmem_ld_wait_x32(v.hi);
+}
+
+// kScores: also emit the fp32 similarity map (maps.b2 = [B, N, L] fp32 store map)
+template <bool kScores>
 struct PassS2 : PolicyBase {
   using Params = S2Params;
-  struct State { float m, l; };
+  struct State { float m, l, scale; };
   static constexpr int kBN = 256, kAccs = 1;
   static constexpr bool kAMn = false, kBMn = false, kTwoPhase = false;
-  static constexpr int kEpiSmem = 4 * 32 * 33 * 4;     // one 32x33 fp32 transpose buffer per warp
+  // per-warp TMA-store staging (SWIZZLE_128B boxes of 32 rows x 128 B):
+  //   [scores cols 0-31][scores cols 32-63] (kScores) [P~ 64 cols fp16]
+  static constexpr int kWarpStage = kScores ? 12288 : 4096;
+  static constexpr int kEpiSmem = 4 * kWarpStage;
   __host__ __device__ static int num_tiles(const Params& p) { return p.B * p.m_tiles * p.n_tiles; }
   __host__ __device__ static int inner(const Params& p) { return p.n_tiles; }
   __host__ __device__ static int k_steps(const Params&) { return kD / kBK; }
@@ -62,86 +79,120 @@ struct PassS2 : PolicyBase {
     load_kmajor(&m.a, bar, a, ks * kBK, mt * kBM, 0);        // q [N, 768]
     load_kmajor(&m.b, bar, bsm, ks * kBK, nt * kBN, b);      // k [B, Lp, 768] (rows >= Lp: zero fill)
   }
-  __device__ static void epilogue(const Params& p, int tile, uint32_t tmem, int warp, int lane, float*,
-                                  State& st, uint8_t* epi_smem) {
-    int b, mt, nt;
-    decode(p, tile, b, mt, nt);
-    const int n = mt * kBM + warp * 32 + lane;
-    const bool row_ok = n < p.N;
-    const float scale = p.log_tau_scale != nullptr ? __expf(-__ldg(p.log_tau_scale)) : p.scale;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const long long pi = (long long)b * p.N + (row_ok ? n : 0);
-    __half* prow = p.p_out + pi * p.Lp;
-    float* tbuf = reinterpret_cast<float*>(epi_smem) + warp * (32 * 33);
-    if (nt == 0) { st.m = -INFINITY; st.l = 0.f; }
-    const int cols = tile_n(p, tile);
-#pragma unroll 1
-    for (int c0 = 0; c0 < cols; c0 += 32) {
-      const int l0 = nt * kBN + c0;
-      uint32_t v[32];
-      tmem_ld_x32(tmem + lane_base + c0, v);
-      tmem_ld_wait();
-      float cmax = -INFINITY;
+
+  // one 64-column chunk of this thread's row: scale, lazy maximum, exp, stage, TMA store
+  __device__ static __forceinline__ void chunk(const Params& p, const Maps& maps, Cols64& v, int l0,
+                                               int b, int row0, int lane, bool row_ok, long long pi,
+                                               uint32_t stg, State& st) {
+    const float scale = st.scale;
+    const bool full = l0 + 64 <= p.L;
+    float cmax = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float s = __uint_as_float(v[i]) * scale;
-        v[i] = __float_as_uint(s);
-        if (l0 + i < p.L) cmax = fmaxf(cmax, s);
+    for (int i = 0; i < 32; ++i) {
+      const float s0 = __uint_as_float(v.lo[i]) * scale, s1 = __uint_as_float(v.hi[i]) * scale;
+      v.lo[i] = __float_as_uint(s0);
+      v.hi[i] = __float_as_uint(s1);
+      if (full) {
+        cmax = fmaxf(cmax, fmaxf(s0, s1));
+      } else {
+        if (l0 + i < p.L) cmax = fmaxf(cmax, s0);
+        if (l0 + 32 + i < p.L) cmax = fmaxf(cmax, s1);
       }
-      if (p.scores != nullptr) {
-        // warp transpose: lane = row in, lane = token out -> 128-byte coalesced row segments
-        __syncwarp();
+    }
+    const bool grow = cmax > st.m + kGrow;          // true for the first chunk (m = -inf)
+    const bool resc = grow && st.l > 0.f;
+    if (__any_sync(0xffffffffu, resc)) {
+      // rare: some row's maximum grew by more than e^10 -- rescale what that row has accumulated
+      // and what it has already written.  The bulk stores of this warp must have landed first.
+      if (lane == 0) tma_store_wait_all();
+      __syncwarp();
+      if (resc) {
+        const float alpha = exp2f((st.m - cmax) * kLog2e);
+        st.l *= alpha;
+        if (row_ok) {
+          __half* prow = p.p_out + pi * p.Lp;
+          for (int c = 0; c < l0; c += 8) {
+            uint4 w = __ldcg(reinterpret_cast<const uint4*>(prow + c));
+            __half2* h = reinterpret_cast<__half2*>(&w);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) tbuf[lane * 33 + i] = __uint_as_float(v[i]);
-        __syncwarp();
-        const int l = l0 + lane;
-        const bool col_ok = l < p.L && l >= p.drop_cls;
-        float* dst = p.scores + (long long)b * p.scores_sb + (long long)(l - p.drop_cls);
-        const int row0 = mt * kBM + warp * 32;
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-          if (col_ok && row0 + rr < p.N) __stcs(dst + (long long)(row0 + rr) * p.scores_sn, tbuf[rr * 33 + lane]);
-        }
-      }
-      if (cmax > st.m + kGrow) {          // always true for the first chunk (m = -inf)
-        if (st.l > 0.f) {
-          // rare: the maximum grew by more than e^10 -- rescale what this row has accumulated
-          // and what it has already written (same thread wrote it: program order suffices)
-          const float alpha = exp2f((st.m - cmax) * kLog2e);
-          st.l *= alpha;
-          if (row_ok) {
-            for (int c = 0; c < l0; c += 8) {
-              uint4 w = *reinterpret_cast<uint4*>(prow + c);
-              __half2* h = reinterpret_cast<__half2*>(&w);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f = __half22float2(h[j]);
-                h[j] = __floats2half2_rn(f.x * alpha, f.y * alpha);
-              }
-              *reinterpret_cast<uint4*>(prow + c) = w;
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(h[j]);
+              h[j] = __floats2half2_rn(f.x * alpha, f.y * alpha);
             }
+            *reinterpret_cast<uint4*>(prow + c) = w;
           }
         }
-        st.m = cmax;
       }
-      const float mb = st.m * kLog2e;
-      uint32_t o[16];
-      float lacc = 0.f;
+      __syncwarp();
+    }
+    if (grow) st.m = cmax;
+    // the staging boxes were last read by the bulk stores of the previous chunk
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+    if (kScores) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float p0 = (l0 + i < p.L) ? exp2f(fmaf(__uint_as_float(v[i]), kLog2e, -mb)) : 0.f;
-        const float p1 = (l0 + i + 1 < p.L) ? exp2f(fmaf(__uint_as_float(v[i + 1]), kLog2e, -mb)) : 0.f;
-        lacc += p0 + p1;
-        o[i >> 1] = pack_h2(p0, p1);
+      for (int j = 0; j < 8; ++j) {
+        sts_v4(stg + stage_off(lane, j), v.lo[4 * j], v.lo[4 * j + 1], v.lo[4 * j + 2], v.lo[4 * j + 3]);
+        sts_v4(stg + 4096 + stage_off(lane, j), v.hi[4 * j], v.hi[4 * j + 1], v.hi[4 * j + 2], v.hi[4 * j + 3]);
       }
-      st.l += lacc;
-      if (row_ok) {
-        uint4* d = reinterpret_cast<uint4*>(prow + l0);
-        d[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        d[1] = make_uint4(o[4], o[5], o[6], o[7]);
-        d[2] = make_uint4(o[8], o[9], o[10], o[11]);
-        d[3] = make_uint4(o[12], o[13], o[14], o[15]);
+    }
+    const uint32_t stg_p = stg + (kScores ? 8192 : 0);
+    const float mb = st.m * kLog2e;
+    float lacc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                    // 8 columns -> one 16-byte chunk of the P~ row
+      uint32_t* src = j < 4 ? &v.lo[8 * j] : &v.hi[8 * (j - 4)];
+      const int lc = l0 + 8 * j;
+      float e[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        e[i] = exp2f(fmaf(__uint_as_float(src[i]), kLog2e, -mb));
+        if (!full && lc + i >= p.L) e[i] = 0.f;
+        lacc += e[i];
       }
+      sts_v4(stg_p + stage_off(lane, j), pack_h2(e[0], e[1]), pack_h2(e[2], e[3]), pack_h2(e[4], e[5]),
+             pack_h2(e[6], e[7]));
+    }
+    st.l += lacc;
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (kScores) {
+        tma_store_3d(&maps.c2, stg, l0, row0, b);
+        if (l0 + 32 < p.L) tma_store_3d(&maps.c2, stg + 4096, l0 + 32, row0, b);
+      }
+      tma_store_3d(&maps.c, stg_p, l0, row0, b);
+      tma_store_commit();
+    }
+  }
+
+  __device__ static void epilogue(const Params& p, const Maps& maps, int tile, uint32_t tmem, int warp,
+                                  int lane, float*, State& st, uint8_t* epi_smem) {
+    int b, mt, nt;
+    decode(p, tile, b, mt, nt);
+    const int row0 = mt * kBM + warp * 32;
+    const int n = row0 + lane;
+    const bool row_ok = n < p.N;
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    const long long pi = (long long)b * p.N + (row_ok ? n : 0);
+    const uint32_t stg = smem_u32(epi_smem) + warp * kWarpStage;
+    if (nt == 0) {
+      st.m = -INFINITY;
+      st.l = 0.f;
+      st.scale = p.log_tau_scale != nullptr ? __expf(-__ldg(p.log_tau_scale)) : p.scale;
+    }
+    const int nch = tile_n(p, tile) / 64;            // 4, or 2 for the narrow last tile
+    const int tok0 = nt * kBN;
+    Cols64 va, vb;
+    ld64(taddr, va);
+#pragma unroll 1
+    for (int c = 0; c < nch; c += 2) {
+      wait64(va);
+      ld64(taddr + (c + 1) * 64, vb);
+      chunk(p, maps, va, tok0 + c * 64, b, row0, lane, row_ok, pi, stg, st);
+      wait64(vb);
+      if (c + 2 < nch) ld64(taddr + (c + 2) * 64, va);
+      chunk(p, maps, vb, tok0 + (c + 1) * 64, b, row0, lane, row_ok, pi, stg, st);
     }
     if (nt == p.n_tiles - 1 && row_ok) {
       p.mref[pi] = st.m;
@@ -164,7 +215,11 @@ struct PassPK : PolicyBase {
   using Params = PKParams;
   static constexpr int kBN = 256, kAccs = 1;
   static constexpr bool kAMn = false, kBMn = true, kTwoPhase = false;
+  static constexpr int kEpiSmem = 4 * 4096;          // per warp: one 64-column fp16 box of pooled rows
   __host__ __device__ static int num_tiles(const Params& p) { return p.B * p.m_tiles * (kD / kBN); }
+  // the three feature tiles of one (image, prompt tile) run back to back on one CTA: the P~ tile
+  // they share as A operand is fetched from HBM once and re-read from L2
+  __host__ __device__ static int inner(const Params&) { return kD / kBN; }
   __host__ __device__ static int k_steps(const Params& p) { return p.Lp / kBK; }
   __device__ static void decode(const Params& p, int tile, int& b, int& mt, int& ft) {
     ft = tile % (kD / kBN);
@@ -179,39 +234,71 @@ struct PassPK : PolicyBase {
     load_kmajor(&m.a, bar, a, ks * kBK, mt * kBM, b);                     // P [B, N, Lp]
     load_mnmajor(&m.b, bar, bsm, ft * kBN, ks * kBK, b, kBN / 64);        // k [B, Lp, 768]
   }
-  __device__ static void epilogue(const Params& p, int tile, uint32_t tmem, int warp, int lane, float*, State&, uint8_t*) {
-    int b, mt, ft;
-    decode(p, tile, b, mt, ft);
-    const int n = mt * kBM + warp * 32 + lane;
-    const bool row_ok = n < p.N;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const long long pi = (long long)b * p.N + (row_ok ? n : 0);
-    const __half* qrow = p.q + (long long)(row_ok ? n : 0) * kD + ft * kBN;
-    __half* orow = p.pooled != nullptr ? p.pooled + pi * kD + ft * kBN : nullptr;
-    const float linv = row_ok ? 1.0f / p.lsum[pi] : 0.f;
-    float osq = 0.f, qo = 0.f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < kBN; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld_x16(tmem + lane_base + c0, v);
-      tmem_ld_wait();
-      const uint4 q0 = *reinterpret_cast<const uint4*>(qrow + c0);
-      const uint4 q1 = *reinterpret_cast<const uint4*>(qrow + c0 + 8);
-      const uint32_t qw[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-      uint32_t o[8];
+  __device__ static __forceinline__ void chunk(const Params& p, const Maps& maps, Cols64& v,
+                                               const uint4 (&qv)[8], int f0, int b, int row0, int lane,
+                                               float linv, uint32_t stg, float& osq, float& qo) {
+    const bool store = p.pooled != nullptr;
+    if (store) {
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+    }
 #pragma unroll
-      for (int i = 0; i < 16; i += 2) {
-        const float a0 = __uint_as_float(v[i]) * linv, a1 = __uint_as_float(v[i + 1]) * linv;
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t* src = j < 4 ? &v.lo[8 * j] : &v.hi[8 * (j - 4)];
+      const uint32_t qw[4] = {qv[j].x, qv[j].y, qv[j].z, qv[j].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        const float a0 = __uint_as_float(src[i]) * linv, a1 = __uint_as_float(src[i + 1]) * linv;
         const float2 qq = __half22float2(*reinterpret_cast<const __half2*>(&qw[i >> 1]));
         osq = fmaf(a0, a0, fmaf(a1, a1, osq));
         qo = fmaf(a0, qq.x, fmaf(a1, qq.y, qo));
         o[i >> 1] = pack_h2(a0, a1);
       }
-      if (row_ok && orow != nullptr) {
-        uint4* d = reinterpret_cast<uint4*>(orow + c0);
-        d[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      if (store) sts_v4(stg + stage_off(lane, j), o[0], o[1], o[2], o[3]);
+    }
+    if (store) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&maps.c, stg, f0, row0, b);
+        tma_store_commit();
       }
+    }
+  }
+  __device__ static __forceinline__ void ldq(const __half* qrow, int c0, uint4 (&qv)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) qv[j] = __ldg(reinterpret_cast<const uint4*>(qrow + c0) + j);
+  }
+  __device__ static void epilogue(const Params& p, const Maps& maps, int tile, uint32_t tmem, int warp,
+                                  int lane, float*, State&, uint8_t* epi_smem) {
+    int b, mt, ft;
+    decode(p, tile, b, mt, ft);
+    const int row0 = mt * kBM + warp * 32;
+    const int n = row0 + lane;
+    const bool row_ok = n < p.N;
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    const long long pi = (long long)b * p.N + (row_ok ? n : 0);
+    const __half* qrow = p.q + (long long)(row_ok ? n : 0) * kD + ft * kBN;
+    const uint32_t stg = smem_u32(epi_smem) + warp * 4096;
+    const float linv = row_ok ? 1.0f / p.lsum[pi] : 0.f;
+    float osq = 0.f, qo = 0.f;
+    Cols64 va, vb;
+    uint4 qa[8], qb[8];
+    ld64(taddr, va);
+    ldq(qrow, 0, qa);
+#pragma unroll 1
+    for (int c = 0; c < kBN / 64; c += 2) {
+      wait64(va);
+      ld64(taddr + (c + 1) * 64, vb);
+      ldq(qrow, (c + 1) * 64, qb);
+      chunk(p, maps, va, qa, ft * kBN + c * 64, b, row0, lane, linv, stg, osq, qo);
+      wait64(vb);
+      if (c + 2 < kBN / 64) {
+        ld64(taddr + (c + 2) * 64, va);
+        ldq(qrow, (c + 2) * 64, qa);
+      }
+      chunk(p, maps, vb, qb, ft * kBN + (c + 1) * 64, b, row0, lane, linv, stg, osq, qo);
     }
     if (row_ok) {
       float2* d = reinterpret_cast<float2*>(p.part) + (pi * (kD / kBN) + ft);
@@ -291,26 +378,43 @@ extern "C" int rz_sim_fwd_large(const void* k_f16, int n_images, int tokens, int
   if (lsum == nullptr) lsum = lsum_ws;
   const bool pool = want_pool != 0 || z != nullptr || onorm != nullptr || pooled_f16 != nullptr;
 
-  Maps m;
+  const bool tma_scores = scores != nullptr;
+  if (tma_scores) {
+    // the similarity map is written by TMA: rows hold all `tokens` columns (CLS at column 0; the
+    // caller slices it off), 16-byte aligned base and pitches
+    if (drop_cls != 0) return RZ_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(scores) & 15) || (scores_stride_text % 4) || (scores_stride_image % 4) ||
+        scores_stride_text < tokens)
+      return RZ_ERR_ALIGNMENT;
+  }
+  Maps m = {};
   if (!rz::make_map_3d_sw128(&m.a, q_f16, 1, N, kD, kD * 2, (uint64_t)N * kD * 2, kBM)) return RZ_ERR_CUDA;
-  if (!rz::make_map_3d_sw128(&m.b, k_f16, B, Lp, kD, kD * 2, (uint64_t)Lp * kD * 2, PassS2::kBN)) return RZ_ERR_CUDA;
+  if (!rz::make_map_3d_sw128(&m.b, k_f16, B, Lp, kD, kD * 2, (uint64_t)Lp * kD * 2, 256)) return RZ_ERR_CUDA;
   m.a2 = m.a; m.b2 = m.b;
+  if (!rz::make_map_3d_sw128(&m.c, pbuf, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, 32)) return RZ_ERR_CUDA;
+  m.c2 = m.c;
+  if (tma_scores &&
+      !rz::make_map_3d_f32_sw128(&m.c2, scores, B, N, tokens, (uint64_t)scores_stride_text * 4,
+                                 (uint64_t)scores_stride_image * 4, 32))
+    return RZ_ERR_CUDA;
   S2Params sp;
   sp.B = B; sp.N = N; sp.L = tokens; sp.Lp = Lp; sp.m_tiles = m_tiles;
-  sp.n_tiles = (Lp + PassS2::kBN - 1) / PassS2::kBN;
+  sp.n_tiles = (Lp + 255) / 256;
   sp.scale = scale; sp.log_tau_scale = log_tau_scale;
-  sp.scores = scores; sp.scores_sb = scores_stride_image; sp.scores_sn = scores_stride_text;
-  sp.drop_cls = drop_cls; sp.p_out = pbuf; sp.mref = mref; sp.lsum = lsum; sp.lse = lse;
+  sp.p_out = pbuf; sp.mref = mref; sp.lsum = lsum; sp.lse = lse;
   {
-    int rc = launch<PassS2>(m, sp, s);
+    int rc = tma_scores ? launch<PassS2<true>>(m, sp, s) : launch<PassS2<false>>(m, sp, s);
     if (rc != RZ_OK) return rc;
   }
   if (!pool) return RZ_OK;
   {
-    Maps mk;
+    Maps mk = {};
     if (!rz::make_map_3d_sw128(&mk.a, pbuf, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, kBM)) return RZ_ERR_CUDA;
     if (!rz::make_map_3d_sw128(&mk.b, k_f16, B, Lp, kD, kD * 2, (uint64_t)Lp * kD * 2, 64)) return RZ_ERR_CUDA;
-    mk.a2 = mk.a; mk.b2 = mk.b;
+    mk.a2 = mk.a; mk.b2 = mk.b; mk.c = mk.a; mk.c2 = mk.a;
+    if (pooled_f16 != nullptr &&
+        !rz::make_map_3d_sw128(&mk.c, pooled_f16, B, N, kD, kD * 2, (uint64_t)N * kD * 2, 32))
+      return RZ_ERR_CUDA;
     PKParams kp;
     kp.B = B; kp.N = N; kp.Lp = Lp; kp.m_tiles = m_tiles; kp.q = static_cast<const __half*>(q_f16);
     kp.lsum = lsum; kp.pooled = static_cast<__half*>(pooled_f16); kp.part = part_o;

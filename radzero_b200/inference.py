@@ -71,9 +71,7 @@ def interpolate_similarity_scores(similarity_scores: torch.Tensor, origin_size, 
     kw = interpolate_params(origin_size, kind)
     m = {"raw": _lib.RZ_UP_RAW, "sigmoid": _lib.RZ_UP_SIGMOID, "mask": _lib.RZ_UP_MASK}[mode]
     s = similarity_scores
-    single = s.dim() == 1
-    s2 = s.reshape(1, -1) if single else s.reshape(-1, s.shape[-1])
-    out = ops.upsample_maps(s2.float(), (int(origin_size[0]), int(origin_size[1])), mode=m,
+    out = ops.upsample_maps(s.float(), (int(origin_size[0]), int(origin_size[1])), mode=m,
                             threshold=threshold, **kw)
     return out  # (1, H, W) for a single map, like the reference's squeeze(1)
 
@@ -87,8 +85,7 @@ def get_grounding_point(similarity_score: torch.Tensor, image_size, image_proces
     kw = interpolate_params(image_size, kind)
     s = similarity_score
     single = s.dim() == 1
-    s2 = s.reshape(1, -1) if single else s.reshape(-1, s.shape[-1])
-    pts = ops.upsample_maps(s2.float(), (int(image_size[0]), int(image_size[1])),
+    pts = ops.upsample_maps(s.float(), (int(image_size[0]), int(image_size[1])),
                             mode=_lib.RZ_UP_ARGMAX, **kw)
     if single:
         x, y = pts[0].tolist()

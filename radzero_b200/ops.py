@@ -121,8 +121,9 @@ def sim_fwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, scale: float,
     B, Lp, _ = k_f16.shape
     N = q_f16.shape[0]
     dev = k_f16.device
-    drop, scores, z, zs_text, zs_img = _sim_outputs(B, N, tokens, dev, want_scores, drop_cls, want_z,
-                                                    z_out, z_image_major)
+    large = N > LARGE_N_THRESHOLD and Lp % 128 == 0
+    drop, scores, z, zs_text, zs_img = _sim_outputs(B, N, tokens, dev, want_scores and not large, drop_cls,
+                                                    want_z, z_out, z_image_major)
     lse = torch.empty((B, N), dtype=torch.float32, device=dev) if want_stats else None
     onorm = torch.empty((B, N), dtype=torch.float32, device=dev) if want_stats else None
     pooled = torch.empty((B, N, HIDDEN), dtype=torch.float16, device=dev) if want_pooled else None
@@ -130,7 +131,14 @@ def sim_fwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, scale: float,
     lts, ltz = _log_tau_ptr(log_tau_scale), _log_tau_ptr(log_tau_z)
     lib = _lib.load()
     if N > LARGE_N_THRESHOLD and Lp % 128 == 0:
-        # more prompts than one SM's TMEM can pool (64 x 768 fp32): two full-rate GEMM passes
+        # more prompts than one SM's TMEM can pool (64 x 768 fp32): two full-rate GEMM passes.
+        # The similarity map leaves the kernel through TMA stores: rows of `pitch` floats (a
+        # multiple of 32 = 128 B) holding all tokens, CLS at column 0; the caller gets a view.
+        store = None
+        if want_scores:
+            pitch = (int(tokens) + 31) // 32 * 32
+            store = torch.empty((B, N, pitch), dtype=torch.float32, device=dev)
+            scores = store[:, :, drop:int(tokens)]
         nbytes = int(lib.rz_sim_fwd_large_workspace_bytes(B, N, Lp))
         pt = mref = lsum = None
         if want_pooled:     # the training path keeps P~ and its row statistics for rz_sim_bwd
@@ -141,8 +149,8 @@ def sim_fwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, scale: float,
         ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
         rc = lib.rz_sim_fwd_large(
             _p(k_f16), B, int(tokens), Lp, _p(q_f16), N, float(scale), _p(lts), _p(qin),
-            _p(scores), scores.stride(0) if scores is not None else 0,
-            scores.stride(1) if scores is not None else 0, drop,
+            _p(store), store.stride(0) if store is not None else 0,
+            store.stride(1) if store is not None else 0, 0,
             _p(z), zs_text, zs_img, float(z_scale), _p(ltz), 1 if z_sigmoid else 0,
             _p(lse), _p(onorm), _p(pooled), _p(pt), _p(mref), _p(lsum), 1 if want_z else 0, _p(ws),
             C.c_size_t(ws.numel()), _stream())
@@ -271,6 +279,25 @@ def prep_rows_bwd(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional
 
 
 # ----------------------------------------------------------------------------- K8 + K9
+def _as_maps(t: torch.Tensor) -> torch.Tensor:
+    """View (..., G*G) as (maps, G*G) with unit inner stride and ONE map stride, without copying
+    when the leading dims collapse (e.g. the padded-pitch similarity map of the large-N forward)."""
+    if t.dim() == 1:
+        t = t.unsqueeze(0)
+    if t.stride(-1) != 1:
+        return t.reshape(-1, t.shape[-1]).contiguous()
+    if t.dim() == 2:
+        return t
+    lead, strides = list(t.shape[:-1]), list(t.stride()[:-1])
+    ok = all(strides[i] == strides[i + 1] * lead[i + 1] for i in range(len(lead) - 1))
+    if not ok:
+        return t.reshape(-1, t.shape[-1]).contiguous()
+    maps = 1
+    for d in lead:
+        maps *= d
+    return t.as_strided((maps, t.shape[-1]), (strides[-1], 1), t.storage_offset())
+
+
 def upsample_maps(scores: torch.Tensor, out_hw: Tuple[int, int], *, mode: int = _lib.RZ_UP_RAW,
                   interp_hw: Optional[Tuple[int, int]] = None, offset: Tuple[int, int] = (0, 0),
                   fill: float = -999.0, threshold: float = 0.5, grid: Optional[int] = None):
@@ -278,8 +305,7 @@ def upsample_maps(scores: torch.Tensor, out_hw: Tuple[int, int], *, mode: int = 
     _need_cuda(scores)
     if scores.dtype != torch.float32:
         raise RzError("scores must be fp32")
-    if scores.dim() != 2 or scores.stride(1) != 1:
-        scores = _contig(scores.reshape(-1, scores.shape[-1]))
+    scores = _as_maps(scores)
     maps, n = scores.shape
     g = grid or int(round(n ** 0.5))
     if g * g != n:

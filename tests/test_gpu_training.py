@@ -69,7 +69,10 @@ def test_sim_bwd_vs_autograd(B, N, L):
     assert _rel(dq, q.grad) < 5e-3
     assert _rel(dk[:, :L], k.grad) < 5e-3
     assert float(dk[:, L:].abs().max()) == 0.0 if Lp > L else True
-    assert abs(dlt.item() - lt.grad.item()) < 5e-3 * abs(lt.grad.item()) + 1e-9
+    # d/dlog(tau) = -sum_l dL/ds_l * s_l with sum_l dL/ds_l = 0 per row: a heavily cancelling sum, so the
+    # fp16 rounding of the pooled vectors (5e-4 relative on T = <o, k>) shows up amplified; the reference
+    # computes this gradient under bf16 autocast (4e-3 relative per operand element)
+    assert abs(dlt.item() - lt.grad.item()) < 1e-2 * abs(lt.grad.item()) + 1e-9
 
 
 # ------------------------------------------------------------------------------ the fused step
