@@ -11,7 +11,7 @@
 // A policy class V supplies the problem decomposition, the TMA loads and the epilogue:
 //   V::kBN, V::kAccs (1 or 2 A operands sharing one B), V::kAMn / V::kBMn (operand is
 //   MN-major in shared memory), V::Params,
-//   V::num_tiles(p), V::k_steps(p), V::load(p, maps, tile, ks, a_smem, a2_smem, b_smem, bar),
+//   V::num_tiles(p), V::k_steps(p), V::load(p, maps, tile, ks, a_smem, a2_smem, b_smem, bar, rank),
 //   V::epilogue(p, maps, tile, tmem_acc, warp, lane, scratch, state, epi_smem)
 //   V::inner(p): tiles are handed to a CTA in runs of `inner` consecutive ids (one "item"), so an
 //     epilogue thread can carry V::State (registers) across the tiles of an item;
@@ -39,10 +39,12 @@ struct Maps {
   CUtensorMap c, c2;          // epilogue TMA stores
 };
 
-// defaults a policy inherits: one tile per item, full-width tiles, no epilogue state / scratch
+// defaults a policy inherits: one tile per item, full-width tiles, no epilogue state / scratch,
+// no cluster
 struct PolicyBase {
   struct State {};
   static constexpr int kEpiSmem = 0;
+  static constexpr int kCluster = 1;
   template <class P> __host__ __device__ static int inner(const P&) { return 1; }
   template <class P> __host__ __device__ static int tile_n(const P&, int) { return 0; }
 };
@@ -69,21 +71,29 @@ struct Ctrl {
   float scratch[8];
 };
 
+// V::kCluster == 2: the CTAs of a cluster pair run tiles (2i, 2i+1) of an item in lockstep.  The
+// two tiles share their B operand: each CTA fetches HALF of it and multicasts it into both shared
+// memories, so the L2 -> SM traffic of B halves.  A stage may be refilled only when BOTH CTAs'
+// MMAs have consumed it, hence the `empty` barriers count kCluster multicast commits.
 template <class V>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
   using L = Layout<V>;
+  constexpr int C = V::kCluster;
   extern __shared__ uint8_t smem_raw[];
+  // the dynamic segment starts at the same offset in every CTA, so the aligned base does too
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_smem = base + L::kStages * L::kStageBytes;
   Ctrl* ctl = reinterpret_cast<Ctrl*>(epi_smem + V::kEpiSmem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = C > 1 ? (int)cluster_ctarank() : 0;
+  const int cid = (int)blockIdx.x / C, ncl = (int)gridDim.x / C;
   const int inner = V::inner(p);
-  const int n_items = V::num_tiles(p) / inner;
+  const int n_items = V::num_tiles(p) / (inner * C);
   const int ksteps = V::k_steps(p);
 
   if (tid == 0) {
-    for (int i = 0; i < L::kStages; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
+    for (int i = 0; i < L::kStages; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], C); }
     for (int i = 0; i < 2; ++i) { mbar_init(&ctl->acc_full[i], 1); mbar_init(&ctl->acc_empty[i], 128); }
     fence_barrier_init();
   }
@@ -95,22 +105,22 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
     tmem_alloc(&ctl->tmem_slot, L::kTmemCols < 32 ? 32 : L::kTmemCols);
   }
   tc_fence_before();
-  __syncthreads();
+  if (C > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_slot;
 
   if (warp == 4) {
     if (elect_one()) {
       long long g = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = cid; item < n_items; item += ncl) {
         for (int sub = 0; sub < inner; ++sub) {
-          const int tile = item * inner + sub;
+          const int tile = (item * C + rank) * inner + sub;
           for (int ks = 0; ks < ksteps; ++ks, ++g) {
             const int st = (int)(g % L::kStages);
             mbar_wait(&ctl->empty[st], (uint32_t)(((g / L::kStages) & 1) ^ 1));
             mbar_arrive_expect_tx(&ctl->full[st], (uint32_t)L::kStageBytes);
             uint8_t* sa = base + st * L::kStageBytes;
-            V::load(p, maps, tile, ks, sa, sa + kABytes, sa + V::kAccs * kABytes, &ctl->full[st]);
+            V::load(p, maps, tile, ks, sa, sa + kABytes, sa + V::kAccs * kABytes, &ctl->full[st], rank);
           }
         }
       }
@@ -120,9 +130,9 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
     if (elect_one()) {
       long long g = 0;
       int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+      for (int item = cid; item < n_items; item += ncl)
       for (int sub = 0; sub < inner; ++sub, ++it) {
-        const int tile = item * inner + sub;
+        const int tile = (item * C + rank) * inner + sub;
         const int tn = V::tile_n(p, tile);
         const uint32_t idesc = make_idesc_f16(kBM, (uint32_t)(tn > 0 ? tn : V::kBN), V::kAMn ? 1 : 0, V::kBMn ? 1 : 0);
         const int acc = it & 1;
@@ -147,7 +157,8 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
               mma_f16_ss(d0 + a * V::kBN, ad, bd, idesc, (ks | k4) ? 1u : 0u);
             }
           }
-          mma_commit(&ctl->empty[st]);
+          if (C > 1) mma_commit_mc(&ctl->empty[st], (uint16_t)((1u << C) - 1u));
+          else mma_commit(&ctl->empty[st]);
         }
         mma_commit(&ctl->acc_full[acc]);
       }
@@ -156,9 +167,9 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
   } else {
     int it = 0;
     typename V::State state{};
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+    for (int item = cid; item < n_items; item += ncl)
     for (int sub = 0; sub < inner; ++sub, ++it) {
-      const int tile = item * inner + sub;
+      const int tile = (item * C + rank) * inner + sub;
       const int acc = it & 1;
       mbar_wait(&ctl->acc_full[acc], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
@@ -171,19 +182,45 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
     if (V::kEpiSmem > 0 && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
-  __syncthreads();
+  // (cluster) nobody leaves while the partner may still multicast into this CTA or signal it
+  if (C > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_base, L::kTmemCols < 32 ? 32 : L::kTmemCols);
+}
+
+// resident clusters of gemm_kernel<V> on this device (persistent grid size / kCluster)
+template <class V>
+int max_clusters(cudaLaunchConfig_t* cfg) {
+  static int cached = 0;
+  if (cached > 0) return cached;
+  int n = 0;
+  if (V::kCluster > 1) {
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<V>, cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = rz_sm_count() / V::kCluster;
+    }
+  } else {
+    n = rz_sm_count();
+  }
+  cached = n;
+  return n;
 }
 
 template <class V>
 int launch(const Maps& maps, const typename V::Params& p, cudaStream_t s) {
   using L = Layout<V>;
-  const int tiles = V::num_tiles(p) / V::inner(p);
-  if (tiles <= 0) return RZ_OK;
-  const int grid = tiles < rz_sm_count() ? tiles : rz_sm_count();
+  const int items = V::num_tiles(p) / (V::inner(p) * V::kCluster);
+  if (items <= 0) return RZ_OK;
   RZ_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmem));
-  gemm_kernel<V><<<grid, kThreads, L::kSmem, s>>>(maps, p);
-  RZ_LAUNCH_OK();
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = V::kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = L::kSmem; cfg.stream = s;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.gridDim = dim3((unsigned)(rz_sm_count() / V::kCluster * V::kCluster));
+  const int cap = max_clusters<V>(&cfg);
+  cfg.gridDim = dim3((unsigned)((items < cap ? items : cap) * V::kCluster));
+  RZ_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<V>, maps, p));
   rz_count_launch();
   return RZ_OK;
 }
@@ -199,6 +236,32 @@ __device__ __forceinline__ void load_mnmajor(const CUtensorMap* m, uint64_t* bar
                                              int mn0, int k0, int batch, int blocks) {
   for (int i = 0; i < blocks; ++i)
     tma_load_3d(m, bar, dst + i * kMnBlock, mn0 + i * 64, k0, batch, kEvictNormal);
+}
+// The same tiles when the C CTAs of a cluster share the operand: CTA `rank` fetches its 1/C of the
+// rows (K-major; the tensor map's box holds rows / C rows) or of the blocks (MN-major) and
+// multicasts it to all of them.
+template <int C>
+__device__ __forceinline__ void load_kmajor_shared(const CUtensorMap* m, uint64_t* bar, uint8_t* dst,
+                                                   int k0, int row0, int batch, int rows, int rank) {
+  if (C == 1) {
+    tma_load_3d(m, bar, dst, k0, row0, batch, kEvictNormal);
+  } else {
+    const int part = rows / C;
+    tma_load_3d_mc(m, bar, dst + rank * part * 128, k0, row0 + rank * part, batch,
+                   (uint16_t)((1u << C) - 1u), kEvictNormal);
+  }
+}
+template <int C>
+__device__ __forceinline__ void load_mnmajor_shared(const CUtensorMap* m, uint64_t* bar, uint8_t* dst,
+                                                    int mn0, int k0, int batch, int blocks, int rank) {
+  if (C == 1) {
+    load_mnmajor(m, bar, dst, mn0, k0, batch, blocks);
+  } else {
+    const int part = blocks / C;
+    for (int i = rank * part; i < (rank + 1) * part; ++i)
+      tma_load_3d_mc(m, bar, dst + i * kMnBlock, mn0 + i * 64, k0, batch, (uint16_t)((1u << C) - 1u),
+                     kEvictNormal);
+  }
 }
 
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a SWIZZLE_128B staging box

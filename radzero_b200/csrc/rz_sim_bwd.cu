@@ -73,7 +73,9 @@ struct DParams {
   float* dtau_part;              // [tiles] partial sums of -dL/ds * s (unscaled)
 };
 
+template <int C>
 struct PassD : PolicyBase {
+  static constexpr int kCluster = C;   // prompt tiles (2i, 2i+1) share the token tile
   using Params = DParams;
   static constexpr int kBN = 128, kAccs = 2;
   static constexpr bool kAMn = false, kBMn = false, kTwoPhase = false;
@@ -81,28 +83,29 @@ struct PassD : PolicyBase {
   static constexpr int kEpiSmem = 4 * 8192;
   __host__ __device__ static int num_tiles(const Params& p) { return p.B * p.m_tiles * p.n_tiles; }
   __host__ __device__ static int k_steps(const Params&) { return kD / kBK; }
+  // prompt tile fastest: consecutive tile ids (a cluster pair) share image and token tile
   __device__ static void decode(const Params& p, int tile, int& b, int& mt, int& nt) {
-    nt = tile % p.n_tiles;
-    const int r = tile / p.n_tiles;
-    mt = r % p.m_tiles;
-    b = r / p.m_tiles;
+    mt = tile % p.m_tiles;
+    const int r = tile / p.m_tiles;
+    nt = r % p.n_tiles;
+    b = r / p.n_tiles;
   }
   __device__ static void load(const Params& p, const Maps& m, int tile, int ks, uint8_t* a,
-                              uint8_t* a2, uint8_t* bsm, uint64_t* bar) {
+                              uint8_t* a2, uint8_t* bsm, uint64_t* bar, int rank) {
     int b, mt, nt;
     decode(p, tile, b, mt, nt);
     load_kmajor(&m.a, bar, a, ks * kBK, mt * kBM, 0);        // q      [N, 768]
     load_kmajor(&m.a2, bar, a2, ks * kBK, mt * kBM, b);      // pooled [B, N, 768]
-    load_kmajor(&m.b, bar, bsm, ks * kBK, nt * kBN, b);      // k      [B, Lp, 768]
+    load_kmajor_shared<C>(&m.b, bar, bsm, ks * kBK, nt * kBN, b, kBN, rank);   // k [B, Lp, 768]
   }
   struct Row {
     float inv_tau, lse2, aS, c2, rt;     // lse2 = lse * log2(e); c2 = -aS * r; rt = r / tau
   };
   // 32 columns of S and T of this thread's row -> half of a staged 64-column W1 / W2 box
+  template <bool kMasked>
   __device__ static __forceinline__ void chunk(const Params& p, uint32_t (&sv)[32], uint32_t (&tv)[32],
                                                int l0, int half, int lane, const Row& r, uint32_t stg,
                                                float& u) {
-    const bool full = l0 + 32 <= p.L;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint32_t o1[4], o2[4];
@@ -115,7 +118,7 @@ struct PassD : PolicyBase {
           const float s = __uint_as_float(sv[c]) * r.inv_tau;
           const float t = __uint_as_float(tv[c]);
           float pr = exp2f(fmaf(s, kLog2e, -r.lse2));
-          if (!full && l0 + c >= p.L) pr = 0.f;
+          if (kMasked && l0 + c >= p.L) pr = 0.f;
           const float e = fmaf(-r.rt, t, s);        // s - (r/tau) T
           const float x = r.aS * pr;
           w1v[q] = fmaf(x, e, x);                   // aS p (1 + e)
@@ -167,10 +170,12 @@ struct PassD : PolicyBase {
       // the staging boxes were last read by the bulk stores of the previous 64 columns
       if (lane == 0) tma_store_wait_read();
       __syncwarp();
-      chunk(p, sa, ta, tok0 + c, 0, lane, r, stg, u);
+      if (tok0 + c + 32 <= p.L) chunk<false>(p, sa, ta, tok0 + c, 0, lane, r, stg, u);
+      else chunk<true>(p, sa, ta, tok0 + c, 0, lane, r, stg, u);
       wait2(sb, tb);
       if (c + 64 < kBN) ld2(taddr, c + 64, sa, ta);
-      chunk(p, sb, tb, tok0 + c + 32, 1, lane, r, stg, u);
+      if (tok0 + c + 64 <= p.L) chunk<false>(p, sb, tb, tok0 + c + 32, 1, lane, r, stg, u);
+      else chunk<true>(p, sb, tb, tok0 + c + 32, 1, lane, r, stg, u);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -194,23 +199,25 @@ struct QParams {
   float* dq;                      // [N, 768] fp32
 };
 
+template <int C>
 struct PassQ : PolicyBase {
+  static constexpr int kCluster = C;   // prompt tiles (2i, 2i+1) share the token operand
   using Params = QParams;
   static constexpr int kBN = 256, kAccs = 1;
   static constexpr bool kAMn = false, kBMn = true, kTwoPhase = false;
   __host__ __device__ static int num_tiles(const Params& p) { return p.m_tiles * (kD / kBN); }
   __host__ __device__ static int k_steps(const Params& p) { return p.B * (p.Lp / kBK); }
   __device__ static void load(const Params& p, const Maps& m, int tile, int ks, uint8_t* a, uint8_t*,
-                              uint8_t* bsm, uint64_t* bar) {
-    const int ft = tile % (kD / kBN), mt = tile / (kD / kBN);
+                              uint8_t* bsm, uint64_t* bar, int rank) {
+    const int mt = tile % p.m_tiles, ft = tile / p.m_tiles;
     const int per = p.Lp / kBK;
     const int b = ks / per, lc = ks - b * per;
-    load_kmajor(&m.a, bar, a, lc * kBK, mt * kBM, b);                     // W1 [B, N, Lp]
-    load_mnmajor(&m.b, bar, bsm, ft * kBN, lc * kBK, b, kBN / 64);        // k  [B, Lp, 768]
+    load_kmajor(&m.a, bar, a, lc * kBK, mt * kBM, b);                                  // W1 [B, N, Lp]
+    load_mnmajor_shared<C>(&m.b, bar, bsm, ft * kBN, lc * kBK, b, kBN / 64, rank);     // k  [B, Lp, 768]
   }
   __device__ static void epilogue(const Params& p, const Maps&, int tile, uint32_t tmem, int warp, int lane,
                                   float*, State&, uint8_t*) {
-    const int ft = tile % (kD / kBN), mt = tile / (kD / kBN);
+    const int mt = tile % p.m_tiles, ft = tile / p.m_tiles;
     const int n = mt * kBM + warp * 32 + lane;
     const float inv_s = p.scale[1];
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
@@ -253,7 +260,7 @@ struct PassK : PolicyBase {
     b = r / p.l_tiles;
   }
   __device__ static void load(const Params& p, const Maps& m, int tile, int ks, uint8_t* a, uint8_t*,
-                              uint8_t* bsm, uint64_t* bar) {
+                              uint8_t* bsm, uint64_t* bar, int) {
     int b, lt, ft;
     decode(p, tile, b, lt, ft);
     if (ks < p.n_chunks) {
@@ -337,6 +344,7 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
   float* coef_r = coef_a + pairs;
   float* dtau_part = coef_r + pairs;
   const int m_tiles = (N + 127) / 128, n_tiles = Lp / 128;
+  const int C = (m_tiles % 2 == 0) ? 2 : 1;     // cluster pairs need an even number of prompt tiles
   const int d_tiles = B * m_tiles * n_tiles;
   float* scale = dtau_part + 4 * (size_t)d_tiles;          // [2]
   unsigned int* amax = reinterpret_cast<unsigned int*>(scale + 2);
@@ -356,7 +364,7 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
     Maps m = {};
     if (!rz::make_map_3d_sw128(&m.a, q_f16, 1, N, kD, kD * 2, (uint64_t)N * kD * 2, kBM)) return RZ_ERR_CUDA;
     if (!rz::make_map_3d_sw128(&m.a2, pooled_f16, B, N, kD, kD * 2, (uint64_t)N * kD * 2, kBM)) return RZ_ERR_CUDA;
-    if (!rz::make_map_3d_sw128(&m.b, k_f16, B, Lp, kD, kD * 2, (uint64_t)Lp * kD * 2, 128)) return RZ_ERR_CUDA;
+    if (!rz::make_map_3d_sw128(&m.b, k_f16, B, Lp, kD, kD * 2, (uint64_t)Lp * kD * 2, 128 / C)) return RZ_ERR_CUDA;
     m.b2 = m.b;
     if (!rz::make_map_3d_sw128(&m.c, w1, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, 32)) return RZ_ERR_CUDA;
     if (!rz::make_map_3d_sw128(&m.c2, w2, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, 32)) return RZ_ERR_CUDA;
@@ -364,7 +372,7 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
     p.B = B; p.N = N; p.L = tokens; p.Lp = Lp; p.m_tiles = m_tiles; p.n_tiles = n_tiles;
     p.inv_tau = inv_tau; p.log_tau = log_tau; p.lse = lse; p.coef_a = coef_a; p.coef_r = coef_r;
     p.scale = scale; p.w1 = w1; p.w2 = w2; p.dtau_part = dtau_part;
-    int rc = launch<PassD>(m, p, s);
+    int rc = C == 2 ? launch<PassD<2>>(m, p, s) : launch<PassD<1>>(m, p, s);
     if (rc != RZ_OK) return rc;
     sum_partials_kernel<<<1, 1024, 0, s>>>(dtau_part, 4 * d_tiles, dlog_tau);
     RZ_LAUNCH_OK();
@@ -378,7 +386,7 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
     m.a2 = m.a; m.b2 = m.b;
     QParams p;
     p.B = B; p.N = N; p.Lp = Lp; p.m_tiles = m_tiles; p.scale = scale; p.dq = dq;
-    int rc = launch<PassQ>(m, p, s);
+    int rc = C == 2 ? launch<PassQ<2>>(m, p, s) : launch<PassQ<1>>(m, p, s);
     if (rc != RZ_OK) return rc;
   }
   // ---- pass K

@@ -49,8 +49,9 @@ __device__ __forceinline__ void wait64(Cols64& v) {
 }
 
 // kScores: also emit the fp32 similarity map (maps.b2 = [B, N, L] fp32 store map)
-template <bool kScores>
+template <bool kScores, int C>
 struct PassS2 : PolicyBase {
+  static constexpr int kCluster = C;   // the pair sweeps prompt tiles (2i, 2i+1) over the same tokens
   using Params = S2Params;
   struct State { float m, l, scale; };
   static constexpr int kBN = 256, kAccs = 1;
@@ -73,32 +74,33 @@ struct PassS2 : PolicyBase {
     b = r / p.m_tiles;
   }
   __device__ static void load(const Params& p, const Maps& m, int tile, int ks, uint8_t* a, uint8_t*,
-                              uint8_t* bsm, uint64_t* bar) {
+                              uint8_t* bsm, uint64_t* bar, int rank) {
     int b, mt, nt;
     decode(p, tile, b, mt, nt);
     load_kmajor(&m.a, bar, a, ks * kBK, mt * kBM, 0);        // q [N, 768]
-    load_kmajor(&m.b, bar, bsm, ks * kBK, nt * kBN, b);      // k [B, Lp, 768] (rows >= Lp: zero fill)
+    // k [B, Lp, 768] (rows >= Lp: zero fill), shared by the pair
+    load_kmajor_shared<C>(&m.b, bar, bsm, ks * kBK, nt * kBN, b, kBN, rank);
   }
 
-  // one 64-column chunk of this thread's row: scale, lazy maximum, exp, stage, TMA store
+  // one 64-column chunk of this thread's row: lazy maximum, exp, stage, TMA store.  kMasked: the
+  // chunk straddles the last real token (columns >= L are padding); the common case runs mask-free.
+  template <bool kMasked>
   __device__ static __forceinline__ void chunk(const Params& p, const Maps& maps, Cols64& v, int l0,
                                                int b, int row0, int lane, bool row_ok, long long pi,
                                                uint32_t stg, State& st) {
-    const float scale = st.scale;
-    const bool full = l0 + 64 <= p.L;
-    float cmax = -INFINITY;
+    const float scale = st.scale;                    // > 0: the maximum commutes with it
+    float amax = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      const float s0 = __uint_as_float(v.lo[i]) * scale, s1 = __uint_as_float(v.hi[i]) * scale;
-      v.lo[i] = __float_as_uint(s0);
-      v.hi[i] = __float_as_uint(s1);
-      if (full) {
-        cmax = fmaxf(cmax, fmaxf(s0, s1));
+      const float a0 = __uint_as_float(v.lo[i]), a1 = __uint_as_float(v.hi[i]);
+      if (!kMasked) {
+        amax = fmaxf(amax, fmaxf(a0, a1));
       } else {
-        if (l0 + i < p.L) cmax = fmaxf(cmax, s0);
-        if (l0 + 32 + i < p.L) cmax = fmaxf(cmax, s1);
+        if (l0 + i < p.L) amax = fmaxf(amax, a0);
+        if (l0 + 32 + i < p.L) amax = fmaxf(amax, a1);
       }
     }
+    const float cmax = amax * scale;
     const bool grow = cmax > st.m + kGrow;          // true for the first chunk (m = -inf)
     const bool resc = grow && st.l > 0.f;
     if (__any_sync(0xffffffffu, resc)) {
@@ -132,28 +134,36 @@ struct PassS2 : PolicyBase {
     if (kScores) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        sts_v4(stg + stage_off(lane, j), v.lo[4 * j], v.lo[4 * j + 1], v.lo[4 * j + 2], v.lo[4 * j + 3]);
-        sts_v4(stg + 4096 + stage_off(lane, j), v.hi[4 * j], v.hi[4 * j + 1], v.hi[4 * j + 2], v.hi[4 * j + 3]);
+        sts_v4(stg + stage_off(lane, j), __float_as_uint(__uint_as_float(v.lo[4 * j]) * scale),
+               __float_as_uint(__uint_as_float(v.lo[4 * j + 1]) * scale),
+               __float_as_uint(__uint_as_float(v.lo[4 * j + 2]) * scale),
+               __float_as_uint(__uint_as_float(v.lo[4 * j + 3]) * scale));
+        sts_v4(stg + 4096 + stage_off(lane, j), __float_as_uint(__uint_as_float(v.hi[4 * j]) * scale),
+               __float_as_uint(__uint_as_float(v.hi[4 * j + 1]) * scale),
+               __float_as_uint(__uint_as_float(v.hi[4 * j + 2]) * scale),
+               __float_as_uint(__uint_as_float(v.hi[4 * j + 3]) * scale));
       }
     }
     const uint32_t stg_p = stg + (kScores ? 8192 : 0);
+    const float sl2 = scale * kLog2e;                // exp(s - m) = 2^(a * scale*log2e - m*log2e)
     const float mb = st.m * kLog2e;
-    float lacc = 0.f;
+    float lacc0 = 0.f, lacc1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {                    // 8 columns -> one 16-byte chunk of the P~ row
-      uint32_t* src = j < 4 ? &v.lo[8 * j] : &v.hi[8 * (j - 4)];
+      const uint32_t* src = j < 4 ? &v.lo[8 * j] : &v.hi[8 * (j - 4)];
       const int lc = l0 + 8 * j;
       float e[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        e[i] = exp2f(fmaf(__uint_as_float(src[i]), kLog2e, -mb));
-        if (!full && lc + i >= p.L) e[i] = 0.f;
-        lacc += e[i];
+        e[i] = exp2f(fmaf(__uint_as_float(src[i]), sl2, -mb));
+        if (kMasked && lc + i >= p.L) e[i] = 0.f;
       }
+      lacc0 += (e[0] + e[1]) + (e[2] + e[3]);
+      lacc1 += (e[4] + e[5]) + (e[6] + e[7]);
       sts_v4(stg_p + stage_off(lane, j), pack_h2(e[0], e[1]), pack_h2(e[2], e[3]), pack_h2(e[4], e[5]),
              pack_h2(e[6], e[7]));
     }
-    st.l += lacc;
+    st.l += lacc0 + lacc1;
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -164,6 +174,12 @@ struct PassS2 : PolicyBase {
       tma_store_3d(&maps.c, stg_p, l0, row0, b);
       tma_store_commit();
     }
+  }
+  __device__ static __forceinline__ void chunk_any(const Params& p, const Maps& maps, Cols64& v, int l0,
+                                                   int b, int row0, int lane, bool row_ok, long long pi,
+                                                   uint32_t stg, State& st) {
+    if (l0 + 64 <= p.L) chunk<false>(p, maps, v, l0, b, row0, lane, row_ok, pi, stg, st);
+    else chunk<true>(p, maps, v, l0, b, row0, lane, row_ok, pi, stg, st);
   }
 
   __device__ static void epilogue(const Params& p, const Maps& maps, int tile, uint32_t tmem, int warp,
@@ -189,10 +205,10 @@ struct PassS2 : PolicyBase {
     for (int c = 0; c < nch; c += 2) {
       wait64(va);
       ld64(taddr + (c + 1) * 64, vb);
-      chunk(p, maps, va, tok0 + c * 64, b, row0, lane, row_ok, pi, stg, st);
+      chunk_any(p, maps, va, tok0 + c * 64, b, row0, lane, row_ok, pi, stg, st);
       wait64(vb);
       if (c + 2 < nch) ld64(taddr + (c + 2) * 64, va);
-      chunk(p, maps, vb, tok0 + (c + 1) * 64, b, row0, lane, row_ok, pi, stg, st);
+      chunk_any(p, maps, vb, tok0 + (c + 1) * 64, b, row0, lane, row_ok, pi, stg, st);
     }
     if (nt == p.n_tiles - 1 && row_ok) {
       p.mref[pi] = st.m;
@@ -211,7 +227,9 @@ struct PKParams {
   float* part;                 // [B, N, 3, 2] (|o|^2, <q,o>) per 256-feature slab
 };
 
+template <int C>
 struct PassPK : PolicyBase {
+  static constexpr int kCluster = C;   // prompt tiles (2i, 2i+1) of one image share the token operand
   using Params = PKParams;
   static constexpr int kBN = 256, kAccs = 1;
   static constexpr bool kAMn = false, kBMn = true, kTwoPhase = false;
@@ -228,11 +246,11 @@ struct PassPK : PolicyBase {
     b = r / p.m_tiles;
   }
   __device__ static void load(const Params& p, const Maps& m, int tile, int ks, uint8_t* a, uint8_t*,
-                              uint8_t* bsm, uint64_t* bar) {
+                              uint8_t* bsm, uint64_t* bar, int rank) {
     int b, mt, ft;
     decode(p, tile, b, mt, ft);
-    load_kmajor(&m.a, bar, a, ks * kBK, mt * kBM, b);                     // P [B, N, Lp]
-    load_mnmajor(&m.b, bar, bsm, ft * kBN, ks * kBK, b, kBN / 64);        // k [B, Lp, 768]
+    load_kmajor(&m.a, bar, a, ks * kBK, mt * kBM, b);                                 // P [B, N, Lp]
+    load_mnmajor_shared<C>(&m.b, bar, bsm, ft * kBN, ks * kBK, b, kBN / 64, rank);    // k [B, Lp, 768]
   }
   __device__ static __forceinline__ void chunk(const Params& p, const Maps& maps, Cols64& v,
                                                const uint4 (&qv)[8], int f0, int b, int row0, int lane,
@@ -389,7 +407,8 @@ extern "C" int rz_sim_fwd_large(const void* k_f16, int n_images, int tokens, int
   }
   Maps m = {};
   if (!rz::make_map_3d_sw128(&m.a, q_f16, 1, N, kD, kD * 2, (uint64_t)N * kD * 2, kBM)) return RZ_ERR_CUDA;
-  if (!rz::make_map_3d_sw128(&m.b, k_f16, B, Lp, kD, kD * 2, (uint64_t)Lp * kD * 2, 256)) return RZ_ERR_CUDA;
+  const int C = (m_tiles % 2 == 0) ? 2 : 1;     // cluster pairs need an even number of prompt tiles
+  if (!rz::make_map_3d_sw128(&m.b, k_f16, B, Lp, kD, kD * 2, (uint64_t)Lp * kD * 2, 256 / C)) return RZ_ERR_CUDA;
   m.a2 = m.a; m.b2 = m.b;
   if (!rz::make_map_3d_sw128(&m.c, pbuf, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, 32)) return RZ_ERR_CUDA;
   m.c2 = m.c;
@@ -403,7 +422,8 @@ extern "C" int rz_sim_fwd_large(const void* k_f16, int n_images, int tokens, int
   sp.scale = scale; sp.log_tau_scale = log_tau_scale;
   sp.p_out = pbuf; sp.mref = mref; sp.lsum = lsum; sp.lse = lse;
   {
-    int rc = tma_scores ? launch<PassS2<true>>(m, sp, s) : launch<PassS2<false>>(m, sp, s);
+    int rc = tma_scores ? (C == 2 ? launch<PassS2<true, 2>>(m, sp, s) : launch<PassS2<true, 1>>(m, sp, s))
+                        : (C == 2 ? launch<PassS2<false, 2>>(m, sp, s) : launch<PassS2<false, 1>>(m, sp, s));
     if (rc != RZ_OK) return rc;
   }
   if (!pool) return RZ_OK;
@@ -418,7 +438,7 @@ extern "C" int rz_sim_fwd_large(const void* k_f16, int n_images, int tokens, int
     PKParams kp;
     kp.B = B; kp.N = N; kp.Lp = Lp; kp.m_tiles = m_tiles; kp.q = static_cast<const __half*>(q_f16);
     kp.lsum = lsum; kp.pooled = static_cast<__half*>(pooled_f16); kp.part = part_o;
-    int rc = launch<PassPK>(mk, kp, s);
+    int rc = C == 2 ? launch<PassPK<2>>(mk, kp, s) : launch<PassPK<1>>(mk, kp, s);
     if (rc != RZ_OK) return rc;
     FinParams fp;
     fp.part = part_o; fp.B = B; fp.N = N; fp.q_inv_norm = q_inv_norm;
