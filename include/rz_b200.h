@@ -145,6 +145,10 @@ int rz_sim_fwd_large(const void* k_f16, int n_images, int tokens, int tokens_pad
  *   k_f16 [n_images, tokens_padded, 768], tokens_padded a multiple of 128
  *   z, dz  fp32 [n_text, ldz]: pooled logits and dL/dZ for the local images (columns)
  *   lse, onorm [n_images, n_text]; pooled_f16 [n_images, n_text, 768]
+ *   p_f16, mref, lsum  optional: the unnormalised probabilities and row statistics kept by
+ *          rz_sim_fwd_large.  When given, the scores are not recomputed (p = P~/lsum,
+ *          s = mref + ln P~) and the coefficient pass is ONE GEMM (T = o.k^T) instead of two;
+ *          lse may then be NULL.
  *   dq    fp32 [n_text, 768]  = dL/dq (normalised sentence embeddings), overwritten
  *   dk    fp32 [n_images, tokens_padded, 768] = dL/dk (normalised tokens), overwritten
  *   dlog_tau fp32 [1] = dL/dlog(tau_attn) through the softmax scores
@@ -155,6 +159,7 @@ size_t rz_sim_bwd_workspace_bytes(int n_images, int n_text, int tokens_padded);
 int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int tokens_padded, const void* q_f16,
                int n_text, float inv_tau, const float* log_tau, const float* z, const float* dz,
                long long ldz, const float* lse, const float* onorm, const void* pooled_f16,
+               const void* p_f16, const float* mref, const float* lsum,
                float* dq, float* dk, float* dlog_tau, void* workspace, size_t workspace_bytes,
                void* stream);
 

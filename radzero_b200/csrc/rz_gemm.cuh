@@ -12,7 +12,7 @@
 //   V::kBN, V::kAccs (1 or 2 A operands sharing one B), V::kAMn / V::kBMn (operand is
 //   MN-major in shared memory), V::Params,
 //   V::num_tiles(p), V::k_steps(p), V::load(p, maps, tile, ks, a_smem, a2_smem, b_smem, bar, rank),
-//   V::epilogue(p, maps, tile, tmem_acc, warp, lane, scratch, state, epi_smem)
+//   V::epilogue(p, maps, tile, next_tile, tmem_acc, warp, lane, epi_bar, state, epi_smem)
 //   V::inner(p): tiles are handed to a CTA in runs of `inner` consecutive ids (one "item"), so an
 //     epilogue thread can carry V::State (registers) across the tiles of an item;
 //   V::tile_n(p, tile): MMA N of this tile (<= kBN; a narrower last tile of a run);
@@ -47,6 +47,9 @@ struct PolicyBase {
   static constexpr int kCluster = 1;
   template <class P> __host__ __device__ static int inner(const P&) { return 1; }
   template <class P> __host__ __device__ static int tile_n(const P&, int) { return 0; }
+  // called by the epilogue warps before they wait for the tile's accumulator
+  template <class P, class S>
+  __device__ static void prologue(const P&, const Maps&, int, int, int, uint64_t*, S&, uint8_t*) {}
 };
 
 template <class V>
@@ -67,8 +70,8 @@ struct Ctrl {
   uint64_t empty[8];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
+  uint64_t epi_bar[8];      // two per epilogue warp: TMA loads issued by the epilogue itself
   uint32_t tmem_slot;
-  float scratch[8];
 };
 
 // V::kCluster == 2: the CTAs of a cluster pair run tiles (2i, 2i+1) of an item in lockstep.  The
@@ -95,6 +98,7 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
   if (tid == 0) {
     for (int i = 0; i < L::kStages; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], C); }
     for (int i = 0; i < 2; ++i) { mbar_init(&ctl->acc_full[i], 1); mbar_init(&ctl->acc_empty[i], 128); }
+    for (int i = 0; i < 8; ++i) mbar_init(&ctl->epi_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 4) {
@@ -170,11 +174,15 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
     for (int item = cid; item < n_items; item += ncl)
     for (int sub = 0; sub < inner; ++sub, ++it) {
       const int tile = (item * C + rank) * inner + sub;
+      // the tile this CTA handles next (-1: none), for epilogues that prefetch their own inputs
+      const int next_tile = sub + 1 < inner ? tile + 1
+                            : (item + ncl < n_items ? ((item + ncl) * C + rank) * inner : -1);
       const int acc = it & 1;
+      V::prologue(p, maps, tile, warp, lane, ctl->epi_bar, state, epi_smem);
       mbar_wait(&ctl->acc_full[acc], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      V::epilogue(p, maps, tile, tmem_base + acc * (V::kAccs * V::kBN), warp, lane, ctl->scratch, state,
-                  epi_smem);
+      V::epilogue(p, maps, tile, next_tile, tmem_base + acc * (V::kAccs * V::kBN), warp, lane, ctl->epi_bar,
+                  state, epi_smem);
       tc_fence_before();
       mbar_arrive(&ctl->acc_empty[acc]);
     }
@@ -272,6 +280,19 @@ __device__ __forceinline__ uint32_t stage_off(int row, int chunk) {
 __device__ __forceinline__ void sts_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d)
                : "memory");
+}
+
+// 64 accumulator columns of this thread's row: two tcgen05.ld.x32 in flight
+struct Cols64 {
+  uint32_t lo[32], hi[32];
+};
+__device__ __forceinline__ void ld64(uint32_t taddr, Cols64& v) {
+  tmem_ld_x32(taddr, v.lo);
+  tmem_ld_x32(taddr + 32, v.hi);
+}
+__device__ __forceinline__ void wait64(Cols64& v) {
+  tmem_ld_wait_x32(v.lo);
+  tmem_ld_wait_x32(v.hi);
 }
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {

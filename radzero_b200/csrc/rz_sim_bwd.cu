@@ -140,8 +140,8 @@ struct PassD : PolicyBase {
     tmem_ld_wait_x32(sv);
     tmem_ld_wait_x32(tv);
   }
-  __device__ static void epilogue(const Params& p, const Maps& maps, int tile, uint32_t tmem, int warp,
-                                  int lane, float*, State&, uint8_t* epi_smem) {
+  __device__ static void epilogue(const Params& p, const Maps& maps, int tile, int, uint32_t tmem,
+                                  int warp, int lane, uint64_t*, State&, uint8_t* epi_smem) {
     int b, mt, nt;
     decode(p, tile, b, mt, nt);
     const int row0 = mt * kBM + warp * 32;
@@ -191,6 +191,187 @@ struct PassD : PolicyBase {
 };
 
 // ------------------------------------------------------------------------------------------
+// pass D2: the same W1, W2 from ONE GEMM.  When the forward kept its unnormalised probabilities
+// P~ = exp(s - m) (fp16) and the row statistics (m, l), the scores need not be recomputed:
+//   p_l = P~_l / l,     s_l = m + ln P~_l     (|error| <= 2^-11 from the fp16 rounding of P~; where
+//   P~ underflowed to 0 the weight p_l is 0 and s_l is irrelevant)
+// so only T = o k^T is left for the tensor cores: (128 prompts x 256 tokens) tiles like the
+// forward's pass S.  The epilogue warps fetch their own P~ boxes by TMA, two chunks ahead.
+struct D2Params {
+  int B, N, L, Lp;
+  int m_tiles, n_tiles;
+  float inv_tau;
+  const float* log_tau;
+  const float* mref; const float* lsum;   // [B, N]
+  const float* coef_a; const float* coef_r;
+  const float* scale;            // [2] = S, 1/S
+  float* dtau_part;              // [tiles * 4]
+};
+
+template <int C>
+struct PassD2 : PolicyBase {
+  static constexpr int kCluster = C;   // prompt tiles (2i, 2i+1) sweep the same tokens
+  using Params = D2Params;
+  struct State { uint32_t g; int primed; };     // chunks consumed so far by this warp
+  static constexpr int kBN = 256, kAccs = 1;
+  static constexpr bool kAMn = false, kBMn = false, kTwoPhase = false;
+  // per warp: [P~ in, buffer 0][P~ in, buffer 1][W1 out][W2 out], boxes of 32 rows x 128 B
+  static constexpr int kWarpStage = 16384;
+  static constexpr int kEpiSmem = 4 * kWarpStage;
+  __host__ __device__ static int num_tiles(const Params& p) { return p.B * p.m_tiles * p.n_tiles; }
+  __host__ __device__ static int inner(const Params& p) { return p.n_tiles; }
+  __host__ __device__ static int k_steps(const Params&) { return kD / kBK; }
+  __host__ __device__ static int tile_n(const Params& p, int tile) {
+    const int rem = p.Lp - (tile % p.n_tiles) * kBN;
+    return rem < kBN ? rem : kBN;
+  }
+  __device__ static void decode(const Params& p, int tile, int& b, int& mt, int& nt) {
+    nt = tile % p.n_tiles;
+    const int r = tile / p.n_tiles;
+    mt = r % p.m_tiles;
+    b = r / p.m_tiles;
+  }
+  __device__ static void load(const Params& p, const Maps& m, int tile, int ks, uint8_t* a, uint8_t*,
+                              uint8_t* bsm, uint64_t* bar, int rank) {
+    int b, mt, nt;
+    decode(p, tile, b, mt, nt);
+    load_kmajor(&m.a, bar, a, ks * kBK, mt * kBM, b);                            // pooled [B, N, 768]
+    load_kmajor_shared<C>(&m.b, bar, bsm, ks * kBK, nt * kBN, b, kBN, rank);     // k [B, Lp, 768]
+  }
+  // lane 0: fetch the P~ box of chunk `c` (64 tokens) of `tile` for this warp's 32 rows
+  __device__ static __forceinline__ void fetch(const Params& p, const Maps& maps, int tile, int c, int warp,
+                                               uint32_t stg, uint64_t* bars, uint32_t g) {
+    int b, mt, nt;
+    decode(p, tile, b, mt, nt);
+    uint64_t* bar = bars + warp * 2 + (g & 1);
+    mbar_arrive_expect_tx(bar, 4096u);
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            stg + (g & 1) * 4096u),
+        "l"(reinterpret_cast<uint64_t>(&maps.a2)), "r"(smem_u32(bar)), "r"(nt * kBN + c * 64),
+        "r"(mt * kBM + warp * 32), "r"(b)
+        : "memory");
+  }
+  template <class S>
+  __device__ static void prologue(const Params& p, const Maps& maps, int tile, int warp, int lane,
+                                  uint64_t* bars, S& st, uint8_t* epi_smem) {
+    if (st.primed) return;
+    st.primed = 1;
+    st.g = 0;
+    if (lane == 0) {
+      const uint32_t stg = smem_u32(epi_smem) + warp * kWarpStage;
+      fetch(p, maps, tile, 0, warp, stg, bars, 0);
+      fetch(p, maps, tile, 1, warp, stg, bars, 1);
+    }
+  }
+  struct Row {
+    float m, linv, aS, c2, rt;     // m = reference maximum; c2 = -aS * r; rt = r / tau
+  };
+  // one 64-token chunk of this thread's row
+  __device__ static __forceinline__ void chunk(const Params& p, const Maps& maps, Cols64& v, int tile,
+                                               int next_tile, int c, int nch, int tok0, int b, int row0,
+                                               int warp, int lane, const Row& r, uint32_t stg,
+                                               uint64_t* bars, State& st, float& u) {
+    // this chunk's P~ box: 64 halves of this thread's row
+    const uint32_t g = st.g;
+    const uint32_t in = stg + (g & 1) * 4096u;
+    mbar_wait(bars + warp * 2 + (g & 1), (g >> 1) & 1);
+    uint32_t pw[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(pw[4 * j]), "=r"(pw[4 * j + 1]), "=r"(pw[4 * j + 2]), "=r"(pw[4 * j + 3])
+                   : "r"(in + stage_off(lane, j)));
+    __syncwarp();
+    // the buffer is free again: fetch the box two chunks ahead (possibly of the next tile)
+    if (lane == 0) {
+      if (c + 2 < nch) fetch(p, maps, tile, c + 2, warp, stg, bars, g + 2);
+      else if (next_tile >= 0) fetch(p, maps, next_tile, c + 2 - nch, warp, stg, bars, g + 2);
+    }
+    st.g = g + 1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                      // two halves of 32 columns
+      uint32_t o1[16], o2[16];
+      const uint32_t* tv = h == 0 ? v.lo : v.hi;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float2 pp = __half22float2(*reinterpret_cast<const __half2*>(&pw[16 * h + (i >> 1)]));
+        float w1v[2], w2v[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float pt = q == 0 ? pp.x : pp.y;
+          const float t = __uint_as_float(tv[i + q]);
+          const float s = fmaf(__log2f(fmaxf(pt, 5.9604645e-8f)), 0.6931471805599453f, r.m);
+          const float pr = pt * r.linv;
+          const float e = fmaf(-r.rt, t, s);          // s - (r/tau) T
+          const float x = r.aS * pr;
+          w1v[q] = fmaf(x, e, x);                     // aS p (1 + e)
+          w2v[q] = r.c2 * pr;                         // -aS r p
+          u = fmaf(pr * e, s, u);                     // dL/dlog tau = -a tau sum p e s
+        }
+        o1[i >> 1] = pack_h2(w1v[0], w1v[1]);
+        o2[i >> 1] = pack_h2(w2v[0], w2v[1]);
+      }
+      if (h == 0) {
+        // the output boxes were last read by the bulk stores of the previous chunk
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sts_v4(stg + 8192 + stage_off(lane, 4 * h + j), o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
+        sts_v4(stg + 12288 + stage_off(lane, 4 * h + j), o2[4 * j], o2[4 * j + 1], o2[4 * j + 2], o2[4 * j + 3]);
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(&maps.c, stg + 8192, tok0 + c * 64, row0, b);       // W1 [B, N, Lp]
+      tma_store_3d(&maps.c2, stg + 12288, tok0 + c * 64, row0, b);     // W2 [B, N, Lp]
+      tma_store_commit();
+    }
+  }
+  __device__ static void epilogue(const Params& p, const Maps& maps, int tile, int next_tile, uint32_t tmem,
+                                  int warp, int lane, uint64_t* bars, State& st, uint8_t* epi_smem) {
+    int b, mt, nt;
+    decode(p, tile, b, mt, nt);
+    const int row0 = mt * kBM + warp * 32;
+    const int n = row0 + lane;
+    const bool row_ok = n < p.N;
+    const long long pi = (long long)b * p.N + (row_ok ? n : 0);
+    const float inv_tau = p.log_tau != nullptr ? __expf(-__ldg(p.log_tau)) : p.inv_tau;
+    const float tau = 1.0f / inv_tau;
+    Row r;
+    r.m = row_ok ? p.mref[pi] : 0.f;
+    r.linv = row_ok ? 1.0f / p.lsum[pi] : 0.f;
+    const float a = row_ok ? p.coef_a[pi] : 0.f;
+    const float rr = row_ok ? p.coef_r[pi] : 0.f;
+    r.aS = a * p.scale[0];
+    r.c2 = -r.aS * rr;
+    r.rt = rr * inv_tau;
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t stg = smem_u32(epi_smem) + warp * kWarpStage;
+    const int nch = tile_n(p, tile) / 64;              // 4, or 2 for the narrow last tile
+    const int tok0 = nt * kBN;
+    float u = 0.f;
+    Cols64 va, vb;
+    ld64(taddr, va);
+#pragma unroll 1
+    for (int c = 0; c < nch; c += 2) {
+      wait64(va);
+      ld64(taddr + (c + 1) * 64, vb);
+      chunk(p, maps, va, tile, next_tile, c, nch, tok0, b, row0, warp, lane, r, stg, bars, st, u);
+      wait64(vb);
+      if (c + 2 < nch) ld64(taddr + (c + 2) * 64, va);
+      chunk(p, maps, vb, tile, next_tile, c + 1, nch, tok0, b, row0, warp, lane, r, stg, bars, st, u);
+    }
+    // deterministic per-(tile, warp) partial of dL/dlog(tau_attn) = -a tau sum_l p e s
+    u = rz::warp_sum(-a * tau * u);
+    if (lane == 0) p.dtau_part[(long long)tile * 4 + warp] = u;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
 // pass Q: dq[n, f] = (1/S) sum_b sum_l W1[b, n, l] k[b, l, f]
 struct QParams {
   int B, N, Lp;
@@ -215,8 +396,8 @@ struct PassQ : PolicyBase {
     load_kmajor(&m.a, bar, a, lc * kBK, mt * kBM, b);                                  // W1 [B, N, Lp]
     load_mnmajor_shared<C>(&m.b, bar, bsm, ft * kBN, lc * kBK, b, kBN / 64, rank);     // k  [B, Lp, 768]
   }
-  __device__ static void epilogue(const Params& p, const Maps&, int tile, uint32_t tmem, int warp, int lane,
-                                  float*, State&, uint8_t*) {
+  __device__ static void epilogue(const Params& p, const Maps&, int tile, int, uint32_t tmem, int warp,
+                                  int lane, uint64_t*, State&, uint8_t*) {
     const int mt = tile % p.m_tiles, ft = tile / p.m_tiles;
     const int n = mt * kBM + warp * 32 + lane;
     const float inv_s = p.scale[1];
@@ -272,8 +453,8 @@ struct PassK : PolicyBase {
       load_mnmajor(&m.b2, bar, bsm, ft * kBN, nc * kBK, b, kBN / 64);     // pooled [B, N, 768]
     }
   }
-  __device__ static void epilogue(const Params& p, const Maps&, int tile, uint32_t tmem, int warp, int lane,
-                                  float*, State&, uint8_t*) {
+  __device__ static void epilogue(const Params& p, const Maps&, int tile, int, uint32_t tmem, int warp,
+                                  int lane, uint64_t*, State&, uint8_t*) {
     int b, lt, ft;
     decode(p, tile, b, lt, ft);
     const int l = lt * kBM + warp * 32 + lane;
@@ -322,9 +503,10 @@ extern "C" size_t rz_sim_bwd_workspace_bytes(int n_images, int n_text, int token
 extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int tokens_padded,
                           const void* q_f16, int n_text, float inv_tau, const float* log_tau,
                           const float* z, const float* dz, long long ldz, const float* lse,
-                          const float* onorm, const void* pooled_f16, float* dq, float* dk,
+                          const float* onorm, const void* pooled_f16, const void* p_f16,
+                          const float* mref, const float* lsum, float* dq, float* dk,
                           float* dlog_tau, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!k_f16 || !q_f16 || !z || !dz || !lse || !onorm || !pooled_f16 || !dq || !dk || !dlog_tau ||
+  if (!k_f16 || !q_f16 || !z || !dz || !onorm || !pooled_f16 || !dq || !dk || !dlog_tau ||
       !workspace)
     return RZ_ERR_INVALID;
   if (n_images <= 0 || n_text <= 0 || tokens <= 0 || tokens_padded < tokens || ldz < n_images)
@@ -360,7 +542,28 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
   rz_count_launch(2);
 
   // ---- pass D
-  {
+  const bool have_p = p_f16 != nullptr && mref != nullptr && lsum != nullptr;
+  if (have_p) {
+    if (reinterpret_cast<uintptr_t>(p_f16) & 15) return RZ_ERR_ALIGNMENT;
+    Maps m = {};
+    if (!rz::make_map_3d_sw128(&m.a, pooled_f16, B, N, kD, kD * 2, (uint64_t)N * kD * 2, kBM)) return RZ_ERR_CUDA;
+    if (!rz::make_map_3d_sw128(&m.b, k_f16, B, Lp, kD, kD * 2, (uint64_t)Lp * kD * 2, 256 / C)) return RZ_ERR_CUDA;
+    m.b2 = m.b;
+    if (!rz::make_map_3d_sw128(&m.a2, p_f16, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, 32)) return RZ_ERR_CUDA;
+    if (!rz::make_map_3d_sw128(&m.c, w1, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, 32)) return RZ_ERR_CUDA;
+    if (!rz::make_map_3d_sw128(&m.c2, w2, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, 32)) return RZ_ERR_CUDA;
+    D2Params p;
+    p.B = B; p.N = N; p.L = tokens; p.Lp = Lp; p.m_tiles = m_tiles; p.n_tiles = (Lp + 255) / 256;
+    p.inv_tau = inv_tau; p.log_tau = log_tau; p.mref = mref; p.lsum = lsum; p.coef_a = coef_a;
+    p.coef_r = coef_r; p.scale = scale; p.dtau_part = dtau_part;
+    const int t2 = B * m_tiles * p.n_tiles;
+    int rc = C == 2 ? launch<PassD2<2>>(m, p, s) : launch<PassD2<1>>(m, p, s);
+    if (rc != RZ_OK) return rc;
+    sum_partials_kernel<<<1, 1024, 0, s>>>(dtau_part, 4 * t2, dlog_tau);
+    RZ_LAUNCH_OK();
+    rz_count_launch();
+  } else {
+    if (!lse) return RZ_ERR_INVALID;
     Maps m = {};
     if (!rz::make_map_3d_sw128(&m.a, q_f16, 1, N, kD, kD * 2, (uint64_t)N * kD * 2, kBM)) return RZ_ERR_CUDA;
     if (!rz::make_map_3d_sw128(&m.a2, pooled_f16, B, N, kD, kD * 2, (uint64_t)N * kD * 2, kBM)) return RZ_ERR_CUDA;

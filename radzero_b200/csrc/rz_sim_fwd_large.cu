@@ -35,19 +35,6 @@ struct S2Params {
   float* lse;                  // optional [B, N] = mref + log(lsum)
 };
 
-// 64 accumulator columns of this thread's row: two tcgen05.ld.x32 in flight
-struct Cols64 {
-  uint32_t lo[32], hi[32];
-};
-__device__ __forceinline__ void ld64(uint32_t taddr, Cols64& v) {
-  tmem_ld_x32(taddr, v.lo);
-  tmem_ld_x32(taddr + 32, v.hi);
-}
-__device__ __forceinline__ void wait64(Cols64& v) {
-  tmem_ld_wait_x32(v.lo);
-  tmem_ld_wait_x32(v.hi);
-}
-
 // kScores: also emit the fp32 similarity map (maps.b2 = [B, N, L] fp32 store map)
 template <bool kScores, int C>
 struct PassS2 : PolicyBase {
@@ -182,8 +169,8 @@ struct PassS2 : PolicyBase {
     else chunk<true>(p, maps, v, l0, b, row0, lane, row_ok, pi, stg, st);
   }
 
-  __device__ static void epilogue(const Params& p, const Maps& maps, int tile, uint32_t tmem, int warp,
-                                  int lane, float*, State& st, uint8_t* epi_smem) {
+  __device__ static void epilogue(const Params& p, const Maps& maps, int tile, int, uint32_t tmem,
+                                  int warp, int lane, uint64_t*, State& st, uint8_t* epi_smem) {
     int b, mt, nt;
     decode(p, tile, b, mt, nt);
     const int row0 = mt * kBM + warp * 32;
@@ -288,8 +275,8 @@ struct PassPK : PolicyBase {
 #pragma unroll
     for (int j = 0; j < 8; ++j) qv[j] = __ldg(reinterpret_cast<const uint4*>(qrow + c0) + j);
   }
-  __device__ static void epilogue(const Params& p, const Maps& maps, int tile, uint32_t tmem, int warp,
-                                  int lane, float*, State&, uint8_t* epi_smem) {
+  __device__ static void epilogue(const Params& p, const Maps& maps, int tile, int, uint32_t tmem,
+                                  int warp, int lane, uint64_t*, State&, uint8_t* epi_smem) {
     int b, mt, ft;
     decode(p, tile, b, mt, ft);
     const int row0 = mt * kBM + warp * 32;

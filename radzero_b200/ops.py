@@ -220,9 +220,11 @@ def padded_tokens_bwd(tokens: int) -> int:
 
 
 def sim_bwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, inv_tau: float, z: torch.Tensor,
-            dz: torch.Tensor, lse: torch.Tensor, onorm: torch.Tensor, pooled: torch.Tensor, *,
-            log_tau: Optional[torch.Tensor] = None):
-    """Closed-form backward of the fused similarity.  Returns (dq (N,768), dk (B,Lp,768), dlog_tau (1,))."""
+            dz: torch.Tensor, lse: Optional[torch.Tensor], onorm: torch.Tensor, pooled: torch.Tensor, *,
+            log_tau: Optional[torch.Tensor] = None, p: Optional[torch.Tensor] = None,
+            mref: Optional[torch.Tensor] = None, lsum: Optional[torch.Tensor] = None):
+    """Closed-form backward of the fused similarity.  Returns (dq (N,768), dk (B,Lp,768), dlog_tau (1,)).
+    ``p`` / ``mref`` / ``lsum`` (kept by the large-N forward) select the single-GEMM coefficient pass."""
     _need_cuda(k_f16, q_f16, z, dz, lse, onorm, pooled)
     B, Lp, _ = k_f16.shape
     N = q_f16.shape[0]
@@ -239,7 +241,8 @@ def sim_bwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, inv_tau: floa
     dlt = torch.empty(1, dtype=torch.float32, device=dev)
     rc = lib.rz_sim_bwd(_p(k_f16), B, int(tokens), Lp, _p(q_f16), N, float(inv_tau),
                         _p(_log_tau_ptr(log_tau)), _p(z), _p(dz), z.stride(0), _p(lse), _p(onorm),
-                        _p(pooled), _p(dq), _p(dk), _p(dlt), _p(ws), C.c_size_t(nbytes), _stream())
+                        _p(pooled), _p(p), _p(mref), _p(lsum), _p(dq), _p(dk), _p(dlt), _p(ws),
+                        C.c_size_t(nbytes), _stream())
     _lib.check(rc, "rz_sim_bwd")
     return dq, dk, dlt
 

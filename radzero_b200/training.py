@@ -96,7 +96,8 @@ class _ContrastiveStep(torch.autograd.Function):
         ctx.cfg = dict(cfg)
         ctx.meta = (B, L, Lp, n_local, row0, world, attn_log_tau is not None)
         ctx.save_for_backward(text, tokens, gamma, beta, log_tau, attn_log_tau, k16, q16, z, dz,
-                              fwd["lse"], fwd["onorm"], fwd["pooled"], terms)
+                              fwd["lse"], fwd["onorm"], fwd["pooled"], terms, fwd.get("p"), fwd.get("mref"),
+                              fwd.get("lsum"))
         ctx.mark_non_differentiable(z)
         scores = fwd["scores"]
         if scores is None:
@@ -109,7 +110,7 @@ class _ContrastiveStep(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, _gz, _gs):
         (text, tokens, gamma, beta, log_tau, attn_log_tau, k16, q16, z, dz, lse, onorm, pooled,
-         terms) = ctx.saved_tensors
+         terms, p_un, mref, lsum) = ctx.saved_tensors
         K = ctx.K
         B, L, Lp, n_local, row0, world, has_attn = ctx.meta
         if dz is None:
@@ -119,7 +120,8 @@ class _ContrastiveStep(torch.autograd.Function):
         gl = g_loss.reshape(()).float() * ddp_scale
         dzs = dz * gl
         a_lt = attn_log_tau if has_attn else log_tau
-        dq, dk, dlt_attn = K.sim_bwd(k16, q16, L, 1.0, z, dzs, lse, onorm, pooled, log_tau=a_lt.detach())
+        dq, dk, dlt_attn = K.sim_bwd(k16, q16, L, 1.0, z, dzs, lse, onorm, pooled, log_tau=a_lt.detach(),
+                                     p=p_un, mref=mref, lsum=lsum)
         if distributed:
             dist.all_reduce(dq)
         dq_local = dq[row0: row0 + n_local].contiguous()
@@ -173,7 +175,8 @@ class _SimilarityLogitFn(torch.autograd.Function):
         q16, _, _ = ops.prep_rows(queries.detach(), None, None)
         fwd = ops.sim_fwd(k16, q16, L, scale, want_scores=need_scores, drop_cls=False, want_stats=True,
                           want_pooled=True)
-        ctx.save_for_backward(queries, tokens, k16, q16, fwd["z"], fwd["lse"], fwd["onorm"], fwd["pooled"])
+        ctx.save_for_backward(queries, tokens, k16, q16, fwd["z"], fwd["lse"], fwd["onorm"], fwd["pooled"],
+                              fwd.get("p"), fwd.get("mref"), fwd.get("lsum"))
         ctx.meta = (B, L, Lp, scale)
         scores = fwd["scores"] if fwd["scores"] is not None else fwd["z"].new_empty(0)
         ctx.mark_non_differentiable(scores)
@@ -181,9 +184,10 @@ class _SimilarityLogitFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gz, _gs):
-        queries, tokens, k16, q16, z, lse, onorm, pooled = ctx.saved_tensors
+        queries, tokens, k16, q16, z, lse, onorm, pooled, p_un, mref, lsum = ctx.saved_tensors
         B, L, Lp, scale = ctx.meta
-        dq, dk, _ = ops.sim_bwd(k16, q16, L, scale, z, gz.float().contiguous(), lse, onorm, pooled)
+        dq, dk, _ = ops.sim_bwd(k16, q16, L, scale, z, gz.float().contiguous(), lse, onorm, pooled,
+                                p=p_un, mref=mref, lsum=lsum)
         dxt, _, _ = ops.prep_rows_bwd(tokens.detach(), None, None, dk, rows_per_group=L,
                                       rows_per_group_padded=Lp)
         dxq, _, _ = ops.prep_rows_bwd(queries.detach(), None, None, dq)

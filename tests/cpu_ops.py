@@ -92,7 +92,7 @@ def _mpnce_finish(z, group_map, col0, inv_tau, rowsum, pos, eps):
     return terms, dz
 
 
-def sim_bwd(k16, q16, tokens, inv_tau, z, dz, lse, onorm, pooled, *, log_tau=None):
+def sim_bwd(k16, q16, tokens, inv_tau, z, dz, lse, onorm, pooled, *, log_tau=None, p=None, mref=None, lsum=None):
     with torch.enable_grad():
         return _sim_bwd(k16, q16, tokens, inv_tau, dz, log_tau)
 

@@ -43,8 +43,11 @@ def test_prep_rows_bwd(use_ln, l2, dtype):
 
 
 # ------------------------------------------------------------------------------ similarity backward
-@pytest.mark.parametrize("B,N,L", [(2, 5, 50), (3, 130, 200), (2, 70, 1370)])
-def test_sim_bwd_vs_autograd(B, N, L):
+@pytest.mark.parametrize("use_p", [False, True])
+@pytest.mark.parametrize("B,N,L", [(2, 5, 50), (3, 130, 200), (2, 70, 1370), (2, 256, 1370)])
+def test_sim_bwd_vs_autograd(B, N, L, use_p):
+    """use_p: the single-GEMM coefficient pass fed by the forward's unnormalised probabilities
+    (large-N forward only); otherwise the pass that recomputes the scores."""
     tok, text, gamma, beta, _ = synthetic.make_inputs(B, N, tokens_per_image=L, seed=50 + N)
     tau = 0.07
     Lp = ops.padded_tokens_bwd(L)
@@ -55,8 +58,11 @@ def test_sim_bwd_vs_autograd(B, N, L):
     fwd = ops.sim_fwd(k16, q16, L, 1.0 / tau, want_stats=True, want_pooled=True)
     g = torch.Generator().manual_seed(9)
     dz = torch.randn(N, B, generator=g) * 1e-3
+    if use_p and fwd["p"] is None:
+        pytest.skip("the small-N forward keeps no probabilities")
+    extra = dict(p=fwd["p"], mref=fwd["mref"], lsum=fwd["lsum"]) if use_p else {}
     dq, dk, dlt = ops.sim_bwd(k16, q16, L, 1.0 / tau, fwd["z"], dz.to(DEV), fwd["lse"], fwd["onorm"],
-                              fwd["pooled"])
+                              fwd["pooled"], **extra)
     # checker: fp64 autograd through the same (fp16-rounded) normalised operands
     k = k16[:, :L].double().cpu().requires_grad_(True)
     q = q16.double().cpu().requires_grad_(True)
