@@ -236,14 +236,15 @@ int launch(const Maps& maps, const typename V::Params& p, cudaStream_t s) {
 // ---- helpers for policies ---------------------------------------------------------------
 // K-major operand tile: `rows` rows x 64 K-elements, one TMA box
 __device__ __forceinline__ void load_kmajor(const CUtensorMap* m, uint64_t* bar, void* dst, int k0,
-                                            int row0, int batch) {
-  tma_load_3d(m, bar, dst, k0, row0, batch, kEvictNormal);
+                                            int row0, int batch, uint64_t hint = kEvictNormal) {
+  tma_load_3d(m, bar, dst, k0, row0, batch, hint);
 }
 // MN-major operand tile: `blocks` blocks of [64 K-rows x 64 MN-elements]
 __device__ __forceinline__ void load_mnmajor(const CUtensorMap* m, uint64_t* bar, uint8_t* dst,
-                                             int mn0, int k0, int batch, int blocks) {
+                                             int mn0, int k0, int batch, int blocks,
+                                             uint64_t hint = kEvictNormal) {
   for (int i = 0; i < blocks; ++i)
-    tma_load_3d(m, bar, dst + i * kMnBlock, mn0 + i * 64, k0, batch, kEvictNormal);
+    tma_load_3d(m, bar, dst + i * kMnBlock, mn0 + i * 64, k0, batch, hint);
 }
 // The same tiles when the C CTAs of a cluster share the operand: CTA `rank` fetches its 1/C of the
 // rows (K-major; the tensor map's box holds rows / C rows) or of the blocks (MN-major) and

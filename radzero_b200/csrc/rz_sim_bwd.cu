@@ -246,10 +246,10 @@ struct PassD2 : PolicyBase {
     uint64_t* bar = bars + warp * 2 + (g & 1);
     mbar_arrive_expect_tx(bar, 4096u);
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-            stg + (g & 1) * 4096u),
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(stg + (g & 1) * 4096u),
         "l"(reinterpret_cast<uint64_t>(&maps.a2)), "r"(smem_u32(bar)), "r"(nt * kBN + c * 64),
-        "r"(mt * kBM + warp * 32), "r"(b)
+        "r"(mt * kBM + warp * 32), "r"(b), "l"(kEvictFirst)
         : "memory");
   }
   template <class S>

@@ -16,6 +16,8 @@
 //            vectors (fp16, kept for the backward) + per-tile |o|^2 and <q, o> partials -> Z
 // S is computed exactly once: 2 GEMM units of MMA work for the 2 algorithmic ones.
 // Replaces SimilarityLogit.forward (exp/cxr_pt/model/losses.py:187-240).
+#include <cstdlib>
+
 #include "rz_gemm.cuh"
 
 namespace {
@@ -33,6 +35,7 @@ struct S2Params {
   float* mref;                 // [B, N]
   float* lsum;                 // [B, N]      sum_l exp(s - mref)
   float* lse;                  // optional [B, N] = mref + log(lsum)
+  int debug;                   // RZ_DEBUG experiments: 1 = epilogue does nothing, 2 = no bulk stores
 };
 
 // kScores: also emit the fp32 similarity map (maps.b2 = [B, N, L] fp32 store map)
@@ -44,8 +47,8 @@ struct PassS2 : PolicyBase {
   static constexpr int kBN = 256, kAccs = 1;
   static constexpr bool kAMn = false, kBMn = false, kTwoPhase = false;
   // per-warp TMA-store staging (SWIZZLE_128B boxes of 32 rows x 128 B):
-  //   [scores cols 0-31][scores cols 32-63] (kScores) [P~ 64 cols fp16]
-  static constexpr int kWarpStage = kScores ? 12288 : 4096;
+  //   [scores, 32 columns fp32] (kScores) [P~, 64 columns fp16]
+  static constexpr int kWarpStage = kScores ? 8192 : 4096;
   static constexpr int kEpiSmem = 4 * kWarpStage;
   __host__ __device__ static int num_tiles(const Params& p) { return p.B * p.m_tiles * p.n_tiles; }
   __host__ __device__ static int inner(const Params& p) { return p.n_tiles; }
@@ -115,26 +118,30 @@ struct PassS2 : PolicyBase {
       __syncwarp();
     }
     if (grow) st.m = cmax;
-    // the staging boxes were last read by the bulk stores of the previous chunk
-    if (lane == 0) tma_store_wait_read();
-    __syncwarp();
+    // Staging: one box for the scores (used for columns 0-31, then 32-63) and one for P~; the work
+    // is ordered so that every wait for a staging box comes after a long stretch of arithmetic.
+    const uint32_t stg_p = stg + (kScores ? 4096 : 0);
     if (kScores) {
+      if (lane == 0) tma_store_wait_read();          // previous chunk's stores (issued long ago)
+      __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 8; ++j)
         sts_v4(stg + stage_off(lane, j), __float_as_uint(__uint_as_float(v.lo[4 * j]) * scale),
                __float_as_uint(__uint_as_float(v.lo[4 * j + 1]) * scale),
                __float_as_uint(__uint_as_float(v.lo[4 * j + 2]) * scale),
                __float_as_uint(__uint_as_float(v.lo[4 * j + 3]) * scale));
-        sts_v4(stg + 4096 + stage_off(lane, j), __float_as_uint(__uint_as_float(v.hi[4 * j]) * scale),
-               __float_as_uint(__uint_as_float(v.hi[4 * j + 1]) * scale),
-               __float_as_uint(__uint_as_float(v.hi[4 * j + 2]) * scale),
-               __float_as_uint(__uint_as_float(v.hi[4 * j + 3]) * scale));
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && p.debug != 2) {
+        tma_store_3d(&maps.c2, stg, l0, row0, b);
+        tma_store_commit();
       }
     }
-    const uint32_t stg_p = stg + (kScores ? 8192 : 0);
+    // exponentials into registers (the scores box drains meanwhile)
     const float sl2 = scale * kLog2e;                // exp(s - m) = 2^(a * scale*log2e - m*log2e)
     const float mb = st.m * kLog2e;
     float lacc0 = 0.f, lacc1 = 0.f;
+    uint32_t pk[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {                    // 8 columns -> one 16-byte chunk of the P~ row
       const uint32_t* src = j < 4 ? &v.lo[8 * j] : &v.hi[8 * (j - 4)];
@@ -147,17 +154,27 @@ struct PassS2 : PolicyBase {
       }
       lacc0 += (e[0] + e[1]) + (e[2] + e[3]);
       lacc1 += (e[4] + e[5]) + (e[6] + e[7]);
-      sts_v4(stg_p + stage_off(lane, j), pack_h2(e[0], e[1]), pack_h2(e[2], e[3]), pack_h2(e[4], e[5]),
-             pack_h2(e[6], e[7]));
+      pk[4 * j] = pack_h2(e[0], e[1]); pk[4 * j + 1] = pack_h2(e[2], e[3]);
+      pk[4 * j + 2] = pack_h2(e[4], e[5]); pk[4 * j + 3] = pack_h2(e[6], e[7]);
     }
     st.l += lacc0 + lacc1;
+    if (lane == 0) tma_store_wait_read();            // !kScores: the previous chunk's P~ store
+    __syncwarp();
+    if (kScores) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        sts_v4(stg + stage_off(lane, j), __float_as_uint(__uint_as_float(v.hi[4 * j]) * scale),
+               __float_as_uint(__uint_as_float(v.hi[4 * j + 1]) * scale),
+               __float_as_uint(__uint_as_float(v.hi[4 * j + 2]) * scale),
+               __float_as_uint(__uint_as_float(v.hi[4 * j + 3]) * scale));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts_v4(stg_p + stage_off(lane, j), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) {
-      if (kScores) {
-        tma_store_3d(&maps.c2, stg, l0, row0, b);
-        if (l0 + 32 < p.L) tma_store_3d(&maps.c2, stg + 4096, l0 + 32, row0, b);
-      }
+    if (lane == 0 && p.debug != 2) {
+      if (kScores && l0 + 32 < p.L) tma_store_3d(&maps.c2, stg, l0 + 32, row0, b);
       tma_store_3d(&maps.c, stg_p, l0, row0, b);
       tma_store_commit();
     }
@@ -186,6 +203,7 @@ struct PassS2 : PolicyBase {
     }
     const int nch = tile_n(p, tile) / 64;            // 4, or 2 for the narrow last tile
     const int tok0 = nt * kBN;
+    if (p.debug == 1) return;
     Cols64 va, vb;
     ld64(taddr, va);
 #pragma unroll 1
@@ -408,6 +426,7 @@ extern "C" int rz_sim_fwd_large(const void* k_f16, int n_images, int tokens, int
   sp.n_tiles = (Lp + 255) / 256;
   sp.scale = scale; sp.log_tau_scale = log_tau_scale;
   sp.p_out = pbuf; sp.mref = mref; sp.lsum = lsum; sp.lse = lse;
+  sp.debug = getenv("RZ_DEBUG") ? atoi(getenv("RZ_DEBUG")) : 0;
   {
     int rc = tma_scores ? (C == 2 ? launch<PassS2<true, 2>>(m, sp, s) : launch<PassS2<true, 1>>(m, sp, s))
                         : (C == 2 ? launch<PassS2<false, 2>>(m, sp, s) : launch<PassS2<false, 1>>(m, sp, s));

@@ -145,12 +145,15 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 
 // TMA stores (shared -> global, bulk-group completion).  The issuing thread owns the group.
+// The outputs of these kernels are streams far larger than L2 that the NEXT kernel reads:
+// evict-first keeps them from pushing the re-used operands (q, k, pooled) out of L2.
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src_saddr, int c0, int c1,
                                              int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(src_saddr), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(src_saddr), "r"(c0), "r"(c1), "r"(c2), "l"(0x12F0000000000000ull)
+      : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -158,6 +161,11 @@ __device__ __forceinline__ void tma_store_commit() {
 // all committed groups have finished READING their shared-memory source (buffer reusable)
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// at most N of the most recently committed groups may still be reading shared memory
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_n() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 // all committed groups are complete (global writes performed)
 __device__ __forceinline__ void tma_store_wait_all() {
