@@ -152,8 +152,7 @@ def run_ours(args):
             return fn.similarity_prob(txt, tokens)
         logits, scores, _ = fn.similarity(txt, tokens, want_scores=True)
         if args.workload == "seg":
-            return inference.interpolate_similarity_scores(scores.reshape(-1, scores.shape[-1]), out_hw,
-                                                           "blip", mode="sigmoid")
+            return inference.interpolate_similarity_scores(scores, out_hw, "blip", mode="sigmoid")
         return scores
 
     def barrier():
@@ -208,8 +207,7 @@ def run_ours(args):
             o = ops.sim_fwd(k16.view(B, Lp, D), q16, L, 1.0, want_scores=want_scores, **zkw)
         evs[3].record()
         if args.workload == "seg":
-            inference.interpolate_similarity_scores(o["scores"].reshape(-1, GRID * GRID), out_hw, "blip",
-                                                    mode="sigmoid")
+            inference.interpolate_similarity_scores(o["scores"], out_hw, "blip", mode="sigmoid")
         evs[4].record()
         torch.cuda.synchronize()
         if i_step >= 2:

@@ -121,7 +121,7 @@ def extract_similarity_map(image, text, model, image_processor, tokenizer):
     tokenized = tokenizer(text, padding=True, truncation=True, return_tensors="pt").to(model.device)
     out = model.compute_logits(pixel_values, [tokenized])
     scores = out["similarity_scores"]                     # (1, N, P*P)
-    maps = interpolate_similarity_scores(scores.reshape(-1, scores.shape[-1]), image_size, image_processor)
+    maps = interpolate_similarity_scores(scores, image_size, image_processor)   # strided views are fine
     return maps.squeeze(0) if maps.shape[0] == 1 else maps
 
 
@@ -144,8 +144,7 @@ def model_inference(image, text, tokenizer, image_processor, model):
     out = model.compute_logits(pixel_values, [tokenized])
     similarity_prob = torch.sigmoid(out["logits"])        # (1, N)
     scores = out["similarity_scores"]
-    similarity_map = interpolate_similarity_scores(scores.reshape(-1, scores.shape[-1]), image_size,
-                                                   image_processor)
+    similarity_map = interpolate_similarity_scores(scores, image_size, image_processor)
     if similarity_map.shape[0] == 1:                      # single prompt: scalar prob, (H, W) map
         return similarity_prob.reshape(()), similarity_map.squeeze(0)
     return similarity_prob.squeeze(0), similarity_map
