@@ -8,10 +8,10 @@
 
 namespace {
 
-constexpr int kBand = 16;      // canvas rows per CTA
+constexpr int kBand = 64;      // canvas rows per CTA (amortises the x-table and the row interpolation)
 constexpr int kThreads = 256;
 constexpr int kMaxGrid = 64;
-constexpr int kRowStride = kMaxGrid + 1;  // rowbuf pitch (compile-time: immediate LDS offsets)
+constexpr int kRowStride = kMaxGrid + 1;  // rowbuf pitch in float2 pairs (compile-time: immediate LDS offsets)
 constexpr int kRowGroup = 4;               // rows per work item
 constexpr int kMaxOutW = 16384; // x-table lives in shared memory (8 B per canvas column)
 
@@ -32,12 +32,14 @@ __device__ __forceinline__ void src_index(float scale, int dst, int n_in, int& i
   w1 = src - (float)i0;
 }
 
-// 1 / (1 + 2^(-v log2 e)): two MUFU ops (ex2, rcp), ~3e-7 absolute error
-__device__ __forceinline__ float fast_sigmoid(float v) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return r;
+// sigmoid(v) = 0.5 + 0.5 tanh(v / 2), given h = v / 2: ONE MUFU op (the kernel is otherwise bound by
+// the 16 lanes/clk MUFU pipe: ex2 + rcp would be two).  tanh.approx has 2^-11 relative error, i.e.
+// <= 2.5e-4 absolute on the probability -- inside the 2e-3 map tolerance; thresholded masks never
+// go through it (RZ_UP_MASK compares in the score domain).
+__device__ __forceinline__ float sigmoid_from_half(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(t, 0.5f, 0.5f);
 }
 
 __device__ __forceinline__ unsigned long long argmax_key(float v, unsigned int flat) {
@@ -49,11 +51,11 @@ __device__ __forceinline__ unsigned long long argmax_key(float v, unsigned int f
 // x-table entry: source column a (bit 31 set = outside the pasted area -> fill) and weight of
 // column a+1.  One CTA = one band of kBand canvas rows of one map:
 //   1. the grid rows the band touches are staged in shared memory,
-//   2. each canvas row is interpolated vertically ONCE into rowbuf[r][0..G] (last column
-//      duplicated so that a+1 is always readable),
+//   2. each canvas row is interpolated vertically ONCE into rowbuf[r][0..G) as PAIRS
+//      (v[a], v[a+1] - v[a]) (a+1 clamped to the last column),
 //   3. the x-table (a, w) of every canvas column is computed once per CTA,
-//   4. threads sweep the band's V-pixel vectors: 1 table load, 2 row loads and one lerp per
-//      pixel, the fused consumer, one coalesced streaming vector store.
+//   4. threads sweep the band's V-pixel vectors: 1 table load per item, then ONE 64-bit shared
+//      load and ONE fma per pixel, the fused consumer, one coalesced streaming vector store.
 template <int MODE, int V, bool PLAIN>
 __global__ void __launch_bounds__(kThreads)
 upsample_kernel(UpParams p) {
@@ -61,8 +63,8 @@ upsample_kernel(UpParams p) {
   const int G = p.grid;
   float2* xtab = reinterpret_cast<float2*>(smem);               // [out_w rounded up to V]
   const int wpad = (p.out_w + V - 1) / V * V;
-  float* rowbuf = smem + 2 * wpad;                              // [kBand][kRowStride]
-  float* gbuf = rowbuf + kBand * kRowStride;                          // [rows needed <= G][G]
+  float2* rowbuf = reinterpret_cast<float2*>(smem + 2 * wpad);  // [kBand][kRowStride] (v[a], v[a+1]-v[a])
+  float* gbuf = smem + 2 * wpad + 2 * kBand * kRowStride;       // [rows needed <= G][G]
   const int map = blockIdx.y;
   const int y_first = blockIdx.x * kBand;
   const int rows_here = min(kBand, p.out_h - y_first);
@@ -90,17 +92,21 @@ upsample_kernel(UpParams p) {
     xtab[x] = make_float2(__int_as_float(a), w);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < rows_here * (G + 1); i += kThreads) {
-    const int r = i / (G + 1), c1 = i - r * (G + 1), c = min(c1, G - 1);
+  for (int i = threadIdx.x; i < rows_here * G; i += kThreads) {
+    const int r = i / G, c = i - r * G, c1 = min(c + 1, G - 1);
     const int iy = y_first + r - p.off_y;
-    float v = 0.f;
+    float v0 = 0.f, v1 = 0.f;
     if (iy >= 0 && iy < p.interp_h) {
       int a; float w;
       src_index(p.scale_h, iy, G, a, w);
       const int b = min(a + 1, G - 1);
-      v = (1.0f - w) * gbuf[(a - ylo) * G + c] + w * gbuf[(b - ylo) * G + c];
+      const float* ga = gbuf + (a - ylo) * G;
+      const float* gb = gbuf + (b - ylo) * G;
+      v0 = (1.0f - w) * ga[c] + w * gb[c];
+      v1 = (1.0f - w) * ga[c1] + w * gb[c1];
     }
-    rowbuf[r * kRowStride + c1] = v;
+    if (MODE == RZ_UP_SIGMOID) { v0 *= 0.5f; v1 *= 0.5f; }     // the consumer wants v / 2
+    rowbuf[r * kRowStride + c] = make_float2(v0, v1 - v0);
   }
   __syncthreads();
 
@@ -125,8 +131,8 @@ upsample_kernel(UpParams p) {
     } else {
       t[0] = xtab[xv];
     }
-    const float* src[V];
-    float w1[V], w0[V];
+    const float2* src[V];
+    float w1[V];
     bool inside[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) {
@@ -134,7 +140,6 @@ upsample_kernel(UpParams p) {
       inside[k] = PLAIN || a >= 0;
       src[k] = rowbuf + (grp * kRowGroup) * kRowStride + (a & 0xffff);
       w1[k] = t[k].y;
-      w0[k] = 1.0f - w1[k];
     }
     const int y0 = y_first + grp * kRowGroup;
     long long o = ((long long)map * p.out_h + y0) * p.out_w + (long long)xv * V;
@@ -147,13 +152,14 @@ upsample_kernel(UpParams p) {
       float val[V];
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        const float v = w0[k] * src[k][rr * kRowStride] + w1[k] * src[k][rr * kRowStride + 1];
-        val[k] = (PLAIN || (inside[k] && row_in)) ? v : p.fill;
+        const float2 pd = src[k][rr * kRowStride];
+        const float v = fmaf(w1[k], pd.y, pd.x);
+        val[k] = (PLAIN || (inside[k] && row_in)) ? v : (MODE == RZ_UP_SIGMOID ? 0.5f * p.fill : p.fill);
       }
       if constexpr (MODE == RZ_UP_RAW || MODE == RZ_UP_SIGMOID) {
         if constexpr (MODE == RZ_UP_SIGMOID) {
 #pragma unroll
-          for (int k = 0; k < V; ++k) val[k] = fast_sigmoid(val[k]);
+          for (int k = 0; k < V; ++k) val[k] = sigmoid_from_half(val[k]);
         }
         float* out = static_cast<float*>(p.out) + o;
         if constexpr (V == 4) {
@@ -221,7 +227,7 @@ template <int MODE, int V>
 int launch_v(const UpParams& p, int maps, cudaStream_t s) {
   dim3 grid((p.out_h + kBand - 1) / kBand, maps), block(kThreads);
   const int wpad = (p.out_w + V - 1) / V * V;
-  const size_t smem = (size_t)(2 * wpad + kBand * kRowStride + p.grid * p.grid) * sizeof(float);
+  const size_t smem = (size_t)(2 * wpad + 2 * kBand * kRowStride + p.grid * p.grid) * sizeof(float);
   // PLAIN: the resized grid covers the canvas exactly (BlipImageProcessor branch) -- no fill
   const bool plain = p.off_x == 0 && p.off_y == 0 && p.interp_h == p.out_h && p.interp_w == p.out_w;
   if (plain) {

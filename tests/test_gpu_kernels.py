@@ -79,7 +79,8 @@ def test_upsample_processor_variants(kind, size):
     for i in range(5):
         want = oracle.interpolate_similarity_scores(scores[i], size, kind)[0]
         assert (out[i] - want).abs().max() < 2e-4
-        assert (sig[i] - torch.sigmoid(want)).abs().max() < 1e-4
+        # sigmoid through ONE tanh.approx (2^-11 relative): <= 2.5e-4 absolute; the path's tolerance is 2e-3
+        assert (sig[i] - torch.sigmoid(want)).abs().max() < 4e-4
         x, y = pts[i].tolist()
         assert want[y, x] >= want.max() - 2e-4
 
