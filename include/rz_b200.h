@@ -97,22 +97,28 @@ int rz_sim_fwd(const void* k_f16, int n_images, int tokens, int tokens_padded,
                long long z_stride_image, float z_scale, const float* log_tau_z, int z_sigmoid,
                float* lse, float* onorm, void* pooled_f16, void* stream);
 
-/* Same computation for small prompt sets (n_text <= 16: zero-shot classification, grounding),
- * reading the RAW vision tokens: LayerNorm (losses.py:90-91) + L2 normalisation (:213) of each
- * token row happen in registers of dedicated loader warps which write the fp16 operand tile
- * straight into shared memory, so the tokens cross HBM exactly once and no fp16 copy is
- * written.  HBM-bound; this is the kernel behind compute_logits / model_inference.
+/* Same computation for small prompt sets (n_text <= 16: zero-shot classification, grounding,
+ * model_inference), reading the RAW vision tokens exactly once: TMA streams the raw rows into a
+ * shared-memory ring, converter warps apply LayerNorm (losses.py:90-91) + L2 normalisation (:213)
+ * in registers and write the fp16 operand tile, tcgen05 computes S^T = q k^T and the pooled sums.
+ * No fp16 copy of the tokens is written.  HBM-bound; this is the kernel behind compute_logits /
+ * model_inference.  The (image, 32-token tile) sequence is cut into equal contiguous ranges, one
+ * per SM, so any batch size (including ONE image) uses the whole GPU; images split across ranges
+ * are finished by a small merge kernel through `workspace`.
  *   tokens_raw [n_images, tokens, 768] of `dtype` (RZ_F32 / RZ_BF16 / RZ_F16), contiguous
  *   gamma/beta fp32 [768] or both NULL; l2 as in rz_prep_rows
  *   q_f16      [n_text, 768] fp16 rows from rz_prep_rows (the prompts are tiny: 14 x 768)
+ *   workspace  rz_sim_fwd_tokens_workspace_bytes(...) bytes, 16-byte aligned
  * Returns RZ_ERR_UNSUPPORTED for n_text > 16 (use rz_prep_rows + rz_sim_fwd).
  */
+size_t rz_sim_fwd_tokens_workspace_bytes(int n_images, int n_text);
 int rz_sim_fwd_tokens(const void* tokens_raw, int dtype, const float* gamma, const float* beta,
                       int l2, int n_images, int tokens, const void* q_f16, int n_text,
                       float scale, const float* log_tau_scale, const float* q_inv_norm,
                       float* scores, long long scores_stride_image, long long scores_stride_text,
                       int drop_cls, float* z, long long z_stride_text, long long z_stride_image,
-                      float z_scale, const float* log_tau_z, int z_sigmoid, void* stream);
+                      float z_scale, const float* log_tau_z, int z_sigmoid, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* Same computation for LARGE prompt sets (open-vocabulary sweeps, the contrastive step), as
  * two full-rate tcgen05 GEMM passes: pass S computes the scores exactly once, one thread per

@@ -216,6 +216,64 @@ __device__ __forceinline__ RowStats ln_l2_row_onepass(float (&x)[24], const floa
   return st;
 }
 
+// ln_l2_row_onepass for register-starved callers: gamma / beta are re-read (L1-resident float4
+// loads) in both sweeps instead of living in 48 registers.
+__device__ __forceinline__ RowStats ln_l2_row_onepass_mem(float (&x)[24], const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, int lane,
+                                                          const LnConsts c, float eps_ln, float eps_l2,
+                                                          bool do_l2 = true) {
+  const float shift = __shfl_sync(0xffffffffu, x[0], 0);
+  float s1 = 0.f, s2 = 0.f, g2 = 0.f, g1 = 0.f, gb = 0.f;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * j);
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * j);
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float& xv = x[4 * j + i];
+      xv -= shift;
+      const float g2v = gg[i] * gg[i], xx = xv * xv;
+      s1 += xv;
+      s2 += xx;
+      g2 = fmaf(g2v, xx, g2);
+      g1 = fmaf(g2v, xv, g1);
+      gb = fmaf(gg[i] * bb[i], xv, gb);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+    g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+    gb += __shfl_xor_sync(0xffffffffu, gb, o);
+  }
+  const float mu = s1 * (1.0f / RZ_HIDDEN);
+  const float var = fmaxf(s2 * (1.0f / RZ_HIDDEN) - mu * mu, 0.0f);
+  const float rstd = rsqrtf(var + eps_ln);
+  float inv = 1.0f;
+  if (do_l2) {
+    const float n2 = rstd * rstd * (g2 - 2.0f * mu * g1 + mu * mu * c.sum_g2) +
+                     2.0f * rstd * (gb - mu * c.sum_gb) + c.sum_b2;
+    inv = 1.0f / fmaxf(sqrtf(fmaxf(n2, 0.0f)), eps_l2);
+  }
+  const float a = rstd * inv;
+  const float ma = -mu * a;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * j);
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * j);
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      x[4 * j + i] = fmaf(x[4 * j + i], a * gg[i], fmaf(ma, gg[i], bb[i] * inv));
+  }
+  RowStats st;
+  st.mean = mu + shift; st.rstd = rstd; st.inv_norm = inv;
+  return st;
+}
+
 // sum g^2, sum g b, sum b^2 over the 768 features; one warp, result in every lane
 __device__ __forceinline__ LnConsts ln_consts_warp(const float* __restrict__ gamma,
                                                    const float* __restrict__ beta, int lane) {

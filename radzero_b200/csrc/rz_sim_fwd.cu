@@ -555,35 +555,3 @@ extern "C" int rz_sim_fwd(const void* k_f16, int n_images, int tokens, int token
   if (!rz::make_map_2d_sw128(&qmap, q_f16, (uint64_t)n_text, kD, kD * 2, 64)) return RZ_ERR_CUDA;
   return launch_fwd<64, 1, 0, float>(kmap, qmap, p, stats, s);
 }
-
-extern "C" int rz_sim_fwd_tokens(const void* tokens_raw, int dtype, const float* gamma,
-                                 const float* beta, int l2, int n_images, int tokens,
-                                 const void* q_f16, int n_text, float scale,
-                                 const float* log_tau_scale, const float* q_inv_norm, float* scores,
-                                 long long scores_stride_image, long long scores_stride_text,
-                                 int drop_cls, float* z, long long z_stride_text,
-                                 long long z_stride_image, float z_scale, const float* log_tau_z,
-                                 int z_sigmoid, void* stream) {
-  if (tokens_raw == nullptr || q_f16 == nullptr) return RZ_ERR_INVALID;
-  if ((gamma == nullptr) != (beta == nullptr)) return RZ_ERR_INVALID;
-  if (n_text > 16) return RZ_ERR_UNSUPPORTED;   // larger prompt sets: rz_prep_rows + rz_sim_fwd
-  if ((reinterpret_cast<uintptr_t>(tokens_raw) & 15) || (reinterpret_cast<uintptr_t>(q_f16) & 15) ||
-      (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(beta) & 15))
-    return RZ_ERR_ALIGNMENT;
-  FwdParams p;
-  const int lp = (tokens + kTok - 1) / kTok * kTok;
-  int rc = fill_common(p, n_images, tokens, lp, n_text, scale, log_tau_scale, q_inv_norm, scores,
-                       scores_stride_image, scores_stride_text, drop_cls, z, z_stride_text,
-                       z_stride_image, z_scale, log_tau_z, z_sigmoid, nullptr, nullptr, nullptr);
-  if (rc != RZ_OK) return rc;
-  p.raw = tokens_raw; p.gamma = gamma; p.beta = beta; p.l2 = l2;
-  CUtensorMap qmap;
-  if (!rz::make_map_2d_sw128(&qmap, q_f16, (uint64_t)n_text, kD, kD * 2, 16)) return RZ_ERR_CUDA;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  switch (dtype) {
-    case RZ_F32: return launch_fwd<16, 2, kLoaderWarps, float>(qmap, qmap, p, false, s);
-    case RZ_BF16: return launch_fwd<16, 2, kLoaderWarps, __nv_bfloat16>(qmap, qmap, p, false, s);
-    case RZ_F16: return launch_fwd<16, 2, kLoaderWarps, __half>(qmap, qmap, p, false, s);
-    default: return RZ_ERR_INVALID;
-  }
-}

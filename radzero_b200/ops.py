@@ -167,11 +167,9 @@ def sim_fwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, scale: float,
 
 
 FUSED_PREP_MAX_TEXT = 16
-# Which small-N forward the host mirror uses.  Measured on B200 (C2, 256 x 14, fp32 tokens):
-# rz_prep_rows + rz_sim_fwd = 0.39 ms of kernels; the single-kernel rz_sim_fwd_tokens = 0.50 ms
-# (its loader warps are latency-bound, see DESIGN.md "open items"), so the two-kernel path is
-# the default until the fused one wins.
-USE_FUSED_PREP = False
+# Small prompt sets (N <= 16) go through the single-kernel rz_sim_fwd_tokens: the raw tokens cross
+# HBM once (no fp16 copy is written) and the work is balanced over all SMs for any batch size.
+USE_FUSED_PREP = True
 
 
 def sim_fwd_tokens(tokens_raw: torch.Tensor, gamma: Optional[torch.Tensor],
@@ -202,11 +200,14 @@ def sim_fwd_tokens(tokens_raw: torch.Tensor, gamma: Optional[torch.Tensor],
     b = _contig(beta.detach().float()) if beta is not None else None
     qin = _contig(q_inv_norm.float()) if q_inv_norm is not None else None
     lts, ltz = _log_tau_ptr(log_tau_scale), _log_tau_ptr(log_tau_z)
-    rc = _lib.load().rz_sim_fwd_tokens(
+    lib = _lib.load()
+    nbytes = int(lib.rz_sim_fwd_tokens_workspace_bytes(B, N))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    rc = lib.rz_sim_fwd_tokens(
         _p(x), _DTYPES[x.dtype], _p(g), _p(b), 1 if l2 else 0, B, L, _p(q_f16), N, float(scale),
         _p(lts), _p(qin), _p(scores), scores.stride(0) if scores is not None else 0,
         scores.stride(1) if scores is not None else 0, drop, _p(z), zs_text, zs_img,
-        float(z_scale), _p(ltz), 1 if z_sigmoid else 0, _stream())
+        float(z_scale), _p(ltz), 1 if z_sigmoid else 0, _p(ws), C.c_size_t(nbytes), _stream())
     _lib.check(rc, "rz_sim_fwd_tokens")
     return dict(scores=scores, z=z)
 

@@ -142,8 +142,11 @@ def test_sim_fwd_dot_mode():
 
 # ------------------------------------------------------------------- fused-prep variant (N <= 16)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("B,N,L", [(3, 14, 1370), (2, 8, 1370), (1, 1, 77), (5, 16, 200)])
+@pytest.mark.parametrize("B,N,L", [(3, 14, 1370), (2, 8, 1370), (1, 1, 77), (5, 16, 200), (1, 14, 1370),
+                                   (37, 5, 333)])
 def test_sim_fwd_tokens_vs_oracle(dtype, B, N, L):
+    """One kernel from the raw tokens.  The shapes cover the stream-K partition: one image cut into
+    many pieces (B = 1), pieces + whole images in one CTA range (B = 37), short images, N = 1."""
     tok, text, gamma, beta, _ = synthetic.make_inputs(B, N, tokens_per_image=L, seed=300 + N)
     tok = tok.to(dtype)
     q16, _, _ = ops.prep_rows(text.to(DEV), gamma.to(DEV), beta.to(DEV))
@@ -154,7 +157,8 @@ def test_sim_fwd_tokens_vs_oracle(dtype, B, N, L):
     assert (out["z"].cpu().double() - want["z"]).abs().max() < 2e-4
     # the two-kernel path (prep -> fp16 -> TMA) must agree with the fused one to fp16 noise
     two = _run(tok, text, gamma, beta, want_scores=True, drop_cls=True)
-    assert (two["z"] - out["z"]).abs().max() < 1e-5
+    # (same fp16 operands up to the LayerNorm's summation order; different tile / merge order)
+    assert (two["z"] - out["z"]).abs().max() < 5e-5
     assert (two["scores"] - out["scores"]).abs().max() < 5e-4
 
 
