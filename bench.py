@@ -220,7 +220,7 @@ def run_ours(args):
     score_bytes = B * N * (L - 1) * 4 if want_scores else 0
     flops = 2.0 * 2.0 * B * N * L * D          # scores + pooling GEMM
     if fused:
-        sim_name = "sim_fwd_kernel<16,2,0,8,float> (raw tokens: LN+L2+GEMM+softmax pool, fused)"
+        sim_name = "sim_small_kernel<float> (raw tokens -> LN+L2 -> tcgen05 S/O GEMMs + softmax pool, one kernel)"
         sim_bytes = B * L * D * 4 + N * D * 2 + score_bytes + B * N * 4
     else:
         sim_name = ("sim_fwd_kernel<16,2,0,0>" if N <= 16 else "sim_fwd_kernel<64,1,0,0>") + \

@@ -226,19 +226,33 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
       const uint32_t q_addr = smem_u32(q_s), k_addr = smem_u32(k_s), p_addr = smem_u32(p_s);
       mbar_wait(&ctl->q_full, 0);
       const int n_local = g_end - g_begin;
+      // One thread issues 54 MMAs per 16-token tile: descriptors advance by 32-bit adds on the low
+      // word (the high word -- stride, version, swizzle -- never changes).
+      const uint64_t qd0 = make_smem_desc(q_addr, 0, 1024);
+      const uint32_t qd_lo = (uint32_t)qd0, d_hi = (uint32_t)(qd0 >> 32);   // high word: SBO, version, swizzle
+      auto mma = [](uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                    uint32_t acc) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(d),
+            "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc)
+            : "memory");
+      };
       auto issue_s = [&](int lt) {
         const int st = lt % kStages, sb = lt & 1;
         mbar_wait(&ctl->k_full[st], (uint32_t)((lt / kStages) & 1));
         tc_fence_after();
         const uint32_t d = tmem_base + kSCol + sb * kTokT;
+        const uint32_t kd_lo = ((k_addr + st * kKStage) & 0x3FFFFu) >> 4;
+        uint32_t alo = qd_lo, blo = kd_lo;
 #pragma unroll 1
-        for (int c = 0; c < kChunks; ++c) {
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const uint64_t ad = make_smem_desc(q_addr + c * (kNB * 128) + k4 * 32, 0, 1024);
-            const uint64_t bd = make_smem_desc(k_addr + st * kKStage + c * kKChunk + k4 * 32, 0, 1024);
-            mma_f16_ss(d, ad, bd, idesc_s, (c | k4) ? 1u : 0u);
-          }
+        for (int c = 0; c < kChunks; ++c, alo += (kNB * 128) >> 4, blo += kKChunk >> 4) {
+          mma(d, alo, d_hi, blo, d_hi, idesc_s, c > 0 ? 1u : 0u);
+          mma(d, alo + 2, d_hi, blo + 2, d_hi, idesc_s, 1u);      // +32 B = 16 features per K step
+          mma(d, alo + 4, d_hi, blo + 4, d_hi, idesc_s, 1u);
+          mma(d, alo + 6, d_hi, blo + 6, d_hi, idesc_s, 1u);
         }
         mma_commit(&ctl->s_full[sb]);
       };
@@ -261,15 +275,15 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
           const int st = lt % kStages, sb = lt & 1;
           mbar_wait(&ctl->p_full[sb], (uint32_t)((lt >> 1) & 1));
           tc_fence_after();
-#pragma unroll 1
-          for (int s = 0; s < kSlabs; ++s) {
+          {
+            // A = k_tile^T (MN-major): two 64-feature blocks kKChunk apart; the whole tile is one K step
+            // (the leading-dimension offset = kKChunk sits in bits 16-29 of the LOW descriptor word)
+            const uint32_t ka_lo = (((k_addr + st * kKStage) & 0x3FFFFu) >> 4) | ((uint32_t)(kKChunk >> 4) << 16);
+            const uint32_t pb_lo = ((p_addr + sb * kPBuf) & 0x3FFFFu) >> 4;
 #pragma unroll
-            for (int k2 = 0; k2 < kTokT / 16; ++k2) {
-              // A = k_tile^T (MN-major): two 64-feature blocks kKChunk apart, 16 tokens per step
-              const uint64_t ad = make_smem_desc(k_addr + st * kKStage + (2 * s) * kKChunk + k2 * 2048, kKChunk, 1024);
-              const uint64_t bd = make_smem_desc(p_addr + sb * kPBuf + k2 * 32, 0, 1024);
-              mma_f16_ss(tmem_base + s * kNB, ad, bd, idesc_o, (i > 0 || k2 > 0) ? 1u : 0u);
-            }
+            for (int s = 0; s < kSlabs; ++s)
+              mma(tmem_base + s * kNB, ka_lo + ((2 * s * kKChunk) >> 4), d_hi, pb_lo, d_hi, idesc_o,
+                  i > 0 ? 1u : 0u);
           }
           mma_commit(&ctl->k_empty[st]);
           mma_commit(&ctl->o_done[sb]);
