@@ -94,6 +94,28 @@ def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
         t = torch.tensor([ms2], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms2 = float(t.item())
+    # the MP-NCE loss kernels on their own (K10): algorithmic bytes = read Z + write dZ
+    from radzero_b200 import ops
+    b_local = B_GLOBAL // world
+    zt = torch.randn(n_total, b_local, device=dev) * 0.3
+    gm_all = gm if not distributed else torch.arange(n_total, device=dev) % B_GLOBAL
+    def nce():
+        rs, ps, cn, cp = ops.mpnce_partials(zt, gm_all, rank * b_local, 1.0 / 0.07)
+        return ops.mpnce_finish(zt, gm_all, rank * b_local, B_GLOBAL, 1.0 / 0.07, rs, ps, cn, cp)
+    for _ in range(3):
+        nce()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        nce()
+    e1.record()
+    torch.cuda.synchronize()
+    nce_ms = e0.elapsed_time(e1) / 10
+    nce_bytes = 2 * n_total * b_local * 4
+    mpnce = {"ms": nce_ms, "algorithmic_bytes": nce_bytes, "achieved_gbs": nce_bytes / (nce_ms * 1e-3) / 1e9,
+             "frac_of_hbm": nce_bytes / (nce_ms * 1e-3) / 1e9 / pk["hbm"],
+             "note": "7 small kernels (two phases + coefficient vectors); Z is 25 MB at C4 and stays in L2, "
+                     "so this is launch/latency-bound, not HBM-bound"}
     out = {
         "metric": "contrastive steps/sec", "value": 1e3 / ms_step, "unit": "steps/s", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "scaling": "strong", "dtype": "f16",
@@ -108,6 +130,7 @@ def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
         "e2e": {"value": 1e3 / (ms2 / ks), "unit": "steps/s",
                 "h2d_bytes_per_step": (h_tok.numel() + h_txt.numel()) * 2, "d2h_bytes_per_step": 4,
                 "api": "RadZeroLoss.forward + backward"},
+        "mpnce": mpnce,
     }
     return out
 

@@ -40,13 +40,23 @@ mpnce_partials_kernel(const float* __restrict__ z, long long ldz, int n_total, i
   for (int c0 = 0; c0 < b_local; c0 += kThreads) {
     const int c = c0 + t;
     float cneg = 0.f, cpos = 0.f;
-    for (int r = 0; r < nrows; ++r) {
-      float e = 0.f;
-      if (c < b_local) {
-        e = __expf(z[(long long)(r0 + r) * ldz + c] * inv_tau);
-        if (gcol[r] == c) { cpos += e; pos[r0 + r] = e; } else { cneg += e; }
+    // loads of 8 rows are issued before their exponentials (memory-level parallelism)
+    for (int rb = 0; rb < nrows; rb += 8) {
+      float zz[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        zz[u] = (c < b_local && rb + u < nrows) ? __ldg(z + (long long)(r0 + rb + u) * ldz + c) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = rb + u;
+        if (r >= nrows) break;
+        float e = 0.f;
+        if (c < b_local) {
+          e = __expf(zz[u] * inv_tau);
+          if (gcol[r] == c) { cpos += e; pos[r0 + r] = e; } else { cneg += e; }
+        }
+        tile[r][t] = e;
       }
-      tile[r][t] = e;
     }
     if (c < b_local) {
       colpart[((long long)chunk * 2 + 0) * b_local + c] = cneg;
@@ -109,9 +119,12 @@ __global__ void mpnce_image_sums_kernel(FinishParams p) {
 }
 
 // per local column: coefficient applied to the negatives / positives of that column and the
-// column loss terms it owns.
-__global__ void mpnce_col_coeff_kernel(FinishParams p) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// column loss terms it owns.  One WARP per column: the lanes stride over the sentences and are
+// combined in a fixed order (bit-reproducible, independent of the number of ranks).
+__global__ void __launch_bounds__(256)
+mpnce_col_coeff_kernel(FinishParams p) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (c >= p.b_local) return;
   const long long gcol = (long long)p.col0 + c;
   float a = 0.f, ap = 0.f, l = 0.f;
@@ -126,7 +139,7 @@ __global__ void mpnce_col_coeff_kernel(FinishParams p) {
   } else {
     // MP-NCE: one term per sentence i of this image: p = pos_i/(pos_i + Cneg + eps)  :337-342
     const float cn = p.colneg[c];
-    for (int i = 0; i < p.n_total; ++i) {
+    for (int i = lane; i < p.n_total; i += 32) {
       if (p.group_map[i] != gcol) continue;
       const float ps = p.pos[i];
       const float den = ps + cn + p.eps;
@@ -135,11 +148,15 @@ __global__ void mpnce_col_coeff_kernel(FinishParams p) {
       l += -logf(pc + p.eps);
       a += u * ps / (den * den);
     }
+    a = rz::warp_sum(a);          // xor-butterfly: the same order on every lane and every run
+    l = rz::warp_sum(l);
     a *= p.inv_2ncol;
   }
-  p.acol[c] = a;
-  p.apos[c] = ap;
-  p.lcol[c] = l;
+  if (lane == 0) {
+    p.acol[c] = a;
+    p.apos[c] = ap;
+    p.lcol[c] = l;
+  }
 }
 
 // per row: coefficients of the row term (and, for MP-NCE columns, the positive's own
@@ -288,7 +305,7 @@ extern "C" int rz_mpnce_finish(const float* z, long long ldz, int n_total, int b
     mpnce_image_sums_kernel<<<(b_global + 127) / 128, 128, 0, s>>>(p);
     RZ_LAUNCH_OK(); ++launches;
   }
-  mpnce_col_coeff_kernel<<<(b_local + 127) / 128, 128, 0, s>>>(p);
+  mpnce_col_coeff_kernel<<<(b_local + 7) / 8, 256, 0, s>>>(p);
   RZ_LAUNCH_OK(); ++launches;
   mpnce_row_coeff_kernel<<<(n_total + 127) / 128, 128, 0, s>>>(p, lrow);
   RZ_LAUNCH_OK(); ++launches;
