@@ -18,6 +18,7 @@ import argparse
 import json
 import math
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -58,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -175,7 +176,6 @@ def run_ours(args):
     barrier()
     launches = _lib.launch_count() - n0
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
     if world > 1:
         t = torch.tensor([ms], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -187,34 +187,47 @@ def run_ours(args):
     # ---- per-kernel timing (instrumented pass over the same steps) for the roofline
     Lp = ops.padded_tokens(L)
     fused = ops.USE_FUSED_PREP and N <= ops.FUSED_PREP_MAX_TEXT
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    acc = [0.0] * 4
+    # every kernel of the step is launched `reps` times back to back between two events on the
+    # launching stream (no host synchronisation inside): pure device time per launch
+    reps = max(5, min(args.steps, 50))
+    want_scores = args.workload != "cls"
     g, bta = fn.layer_norm.weight.detach(), fn.layer_norm.bias.detach()
     lt = fn.loss_temperature
     zkw = dict(z_sigmoid=True, z_image_major=True, log_tau_z=lt, log_tau_scale=lt)
-    want_scores = args.workload != "cls"
-    for i_step in range(args.steps + 2):                     # first two iterations are warm-up
-        evs[0].record()
-        k16 = None
-        if not fused:
-            k16, _, _ = ops.prep_rows(tok, g, bta, rows_per_group=L, rows_per_group_padded=Lp)
-        evs[1].record()
-        q16, _, _ = ops.prep_rows(text, g, bta)
-        evs[2].record()
+    k16 = None
+    if not fused:
+        k16, _, _ = ops.prep_rows(tok, g, bta, rows_per_group=L, rows_per_group_padded=Lp)
+    q16, _, _ = ops.prep_rows(text, g, bta)
+
+    def run_sim():
         if fused:
-            o = ops.sim_fwd_tokens(tok, g, bta, q16, 1.0, want_scores=want_scores, **zkw)
-        else:
-            o = ops.sim_fwd(k16.view(B, Lp, D), q16, L, 1.0, want_scores=want_scores, **zkw)
-        evs[3].record()
-        if args.workload == "seg":
-            inference.interpolate_similarity_scores(o["scores"], out_hw, "blip", mode="sigmoid")
-        evs[4].record()
+            return ops.sim_fwd_tokens(tok, g, bta, q16, 1.0, want_scores=want_scores, **zkw)
+        return ops.sim_fwd(k16.view(B, Lp, D), q16, L, 1.0, want_scores=want_scores, **zkw)
+
+    o = run_sim()
+    stages = [
+        (lambda: ops.prep_rows(tok, g, bta, rows_per_group=L, rows_per_group_padded=Lp)) if not fused else None,
+        lambda: ops.prep_rows(text, g, bta),
+        run_sim,
+        (lambda: inference.interpolate_similarity_scores(o["scores"], out_hw, "blip", mode="sigmoid"))
+        if args.workload == "seg" else None,
+    ]
+    kt = []
+    for stage in stages:
+        if stage is None:
+            kt.append(0.0)
+            continue
+        for _ in range(2):
+            stage()
         torch.cuda.synchronize()
-        if i_step >= 2:
-            for i in range(4):
-                acc[i] += evs[i].elapsed_time(evs[i + 1])
-        del o, k16
-    kt = [a / args.steps for a in acc]
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(reps):
+            stage()
+        eb.record()
+        torch.cuda.synchronize()
+        kt.append(ea.elapsed_time(eb) / reps)
+    del o, k16
     out_bytes = {"cls": B * N * 4, "seg": B * N * out_hw[0] * out_hw[1] * 4,
                  "openvocab": B * N * (L - 1) * 4 + B * N * 4}[args.workload]
     score_bytes = B * N * (L - 1) * 4 if want_scores else 0
@@ -223,8 +236,10 @@ def run_ours(args):
         sim_name = "sim_small_kernel<float> (raw tokens -> LN+L2 -> tcgen05 S/O GEMMs + softmax pool, one kernel)"
         sim_bytes = B * L * D * 4 + N * D * 2 + score_bytes + B * N * 4
     else:
-        sim_name = ("sim_fwd_kernel<16,2,0,0>" if N <= 16 else "sim_fwd_kernel<64,1,0,0>") + \
-            " (fp16 operands via TMA: GEMM + softmax pool)"
+        if N > ops.LARGE_N_THRESHOLD:
+            sim_name = "rz_sim_fwd_large: gemm_kernel<PassS2> + gemm_kernel<PassPK> (two tcgen05 GEMM passes)"
+        else:
+            sim_name = "sim_fwd_kernel<%d> (fp16 operands via TMA: GEMM + softmax pool)" % (16 if N <= 16 else 64)
         sim_bytes = B * Lp * D * 2 + N * D * 2 + score_bytes + B * N * 4
     kernels = [
         ("prep_rows_kernel<float> (tokens: LN+L2 -> fp16)", B * L * D * 4 + B * Lp * D * 2, kt[0], "hbm"),
@@ -253,7 +268,7 @@ def run_ours(args):
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roof["traffic"] = json.load(open(tr)).get(args.workload, {}).get(name.split("<")[0])
+            roof["traffic"] = json.load(open(tr)).get(args.workload, {}).get(re.split(r"[<:]", name)[0])
         except Exception:
             pass
 
@@ -286,7 +301,10 @@ def run_ours(args):
                "d2h_bytes_per_step": r_host.numel() * r_host.element_size(), "steps": ksteps,
                "api": "RadZeroLoss.similarity_prob" if args.workload == "cls" else "RadZeroLoss.similarity"}
 
-    cpu = cpu_baseline(args.workload, steps=1) if (rank == 0 and world == 1 and not args.no_cpu) else None
+    # clocks / throttle reasons were sampled from the start of the timed region to here: the timed
+    # steps, the per-kernel pass and the end-to-end pass (all of them GPU under load)
+    clocks = sampler.stop()
+    cpu = cpu_baseline(args.workload, steps=3) if (rank == 0 and world == 1 and not args.no_cpu) else None
     # the second half of BASELINE.json's metric ("contrastive steps/sec at 1/2/4/8 B200") rides
     # along in the same line: a short run of the image-sharded contrastive step at this N
     contrastive = None
@@ -317,9 +335,10 @@ def run_ours(args):
 
 # ------------------------------------------------------------------------------- CPU arm
 def cpu_sample(workload: str):
-    """(B_sample, N) of the bounded CPU sample: same prompts, fewer images."""
+    """(B_sample, N) of the CPU sample.  The reference's path is cheap enough on these configs that
+    the CPU arm runs the FULL workload (0.2 - 1.5 s per step on 16 cores): no extrapolation."""
     B, N, _ = WORKLOADS[workload]
-    return {"cls": 16, "seg": 8, "openvocab": 2}[workload], N
+    return B, N
 
 
 def cpu_step(workload, tok, text, gamma, beta, log_tau):
@@ -351,7 +370,7 @@ def cpu_baseline(workload: str, steps: int = 1, warmup: int = 1):
             cpu_step(workload, tok, text, gamma, beta, log_tau)
             best = min(best, time.perf_counter() - t0)
     return {"value": Bs * N / best, "unit": "maps/s", "cores": cores, "kind": "port",
-            "sample": f"{Bs} images x {N} prompts of the same workload, fp32 torch CPU oracle "
+            "sample": f"the full workload ({Bs} images x {N} prompts), fp32 torch CPU oracle "
                       f"(oracle/vlcabs.py), best of {max(steps, 1)}, {best * 1e3:.1f} ms"}
 
 
@@ -369,15 +388,20 @@ def run_reference(args):
     Bs, _ = cpu_sample(args.workload)
     tok, text, gamma, beta, log_tau = synthetic.make_inputs(Bs, N, seed=42)
     with torch.no_grad():
+        t0 = time.perf_counter()
         for _ in range(max(1, min(args.warmup, 3))):
             cpu_step(args.workload, tok, text, gamma, beta, log_tau)
+        t_step = (time.perf_counter() - t0) / max(1, min(args.warmup, 3))
+        # bounded: the whole run stays within about a minute whatever K the caller asked for
+        steps = max(3, min(args.steps, int(60.0 / max(t_step, 1e-3))))
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             cpu_step(args.workload, tok, text, gamma, beta, log_tau)
         dt = time.perf_counter() - t0
+    args.steps = steps
     value = Bs * N * args.steps / dt
     cpu = {"value": value, "unit": "maps/s", "cores": cores, "kind": "port",
-           "sample": f"each step = {Bs} images x {N} prompts (bounded sample of {B} x {N}), fp32 torch CPU "
+           "sample": f"each step = the full workload ({Bs} images x {N} prompts), fp32 torch CPU "
                      "oracle restating the reference's losses.py + compute_logits"}
     print(json.dumps({
         "metric": "similarity maps/sec", "value": value, "unit": "maps/s", "n_gpus": args.gpus,
@@ -393,7 +417,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cls", choices=list(WORKLOADS) + ["contrastive"])

@@ -173,7 +173,7 @@ int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int tokens_padded, c
  * dL/dx and dL/dgamma, dL/dbeta from dL/d(normalised rows) (autograd of nn.LayerNorm +
  * F.normalize, losses.py:90-91, 163-164, 212-213).  Row statistics are recomputed from x.
  *   dnorm  fp32, padded group layout of rz_prep_rows' out_f16 ([groups, rows_per_group_padded, 768])
- *   dx     fp32 [rows, 768]
+ *   dx     [rows, 768]: fp32, or -- dx_native = 1 and a 16-bit input dtype -- the input's own type
  *   partials fp32 [rz_prep_rows_bwd_blocks(rows), 2, 768] scratch (needed when gamma != NULL)
  *   dgamma/dbeta fp32 [768]: overwritten, or accumulated into when accumulate = 1 (tokens
  *   and text share one LayerNorm, losses.py:51); grad_scale multiplies the parameter grads.
@@ -181,8 +181,8 @@ int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int tokens_padded, c
 int rz_prep_rows_bwd_blocks(long long rows);
 int rz_prep_rows_bwd(const void* x, int dtype, const float* gamma, const float* beta,
                      long long rows, int rows_per_group, int rows_per_group_padded,
-                     const float* dnorm, int l2, float* dx, float* partials, float* dgamma,
-                     float* dbeta, int accumulate, float grad_scale, void* stream);
+                     const float* dnorm, int l2, void* dx, int dx_native, float* partials,
+                     float* dgamma, float* dbeta, int accumulate, float grad_scale, void* stream);
 
 /* ---- K8+K9: bilinear upsample of patch-grid similarity maps ----------------------------
  * Replaces F.interpolate(mode="bilinear", align_corners=False) in

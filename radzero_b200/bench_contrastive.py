@@ -19,6 +19,16 @@ UNIT_FLOP = 2.0 * L * D            # one GEMM unit per (image, sentence) pair
 GEMM_UNITS = 6                     # fwd: S, P.K ; bwd: T, dQ, dK (x2)   (recompute of S not counted)
 
 
+def _traffic():
+    """DRAM bytes of one step from the committed ncu capture (profiles/traffic.json), 1 GPU."""
+    import json
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    try:
+        return json.load(open(p))["contrastive"]["step"]
+    except Exception:
+        return None
+
+
 def _inputs(rank, world, dev, dtype, b_global=B_GLOBAL):
     from radzero_b200 import synthetic
     counts_all = synthetic.sentence_counts(b_global, seed=42)
@@ -125,7 +135,7 @@ def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
                    "input_dtype": "bf16", "tokens": L, "hidden": D},
         "roofline": {"bound": "tensor", "kernel": "whole step (sim_fwd + rz_sim_bwd GEMM passes)",
                      "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                     "algorithmic_flops_per_step": flops, "traffic": None,
+                     "algorithmic_flops_per_step": flops, "traffic": _traffic(),
                      "peak_source": pk["src"] + " sustained (kernel timed inside a long step)"},
         "e2e": {"value": 1e3 / (ms2 / ks), "unit": "steps/s",
                 "h2d_bytes_per_step": (h_tok.numel() + h_txt.numel()) * 2, "d2h_bytes_per_step": 4,

@@ -49,6 +49,17 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// four floats -> four 16-bit values of type T (bf16 / fp16), packed
+template <typename T> __device__ __forceinline__ uint2 pack4(float a, float b, float c, float d);
+template <> __device__ __forceinline__ uint2 pack4<__half>(float a, float b, float c, float d) {
+  return make_uint2(pack_half2(a, b), pack_half2(c, d));
+}
+template <> __device__ __forceinline__ uint2 pack4<__nv_bfloat16>(float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  return make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+template <> __device__ __forceinline__ uint2 pack4<float>(float, float, float, float) { return make_uint2(0u, 0u); }
+
 // streaming 128-bit global load (read once, do not pollute L1)
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   float4 r;

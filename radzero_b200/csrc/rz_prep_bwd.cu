@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2)
 prep_rows_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, long long rows, int rows_per_group,
                      int rows_per_group_padded, const float* __restrict__ dnorm, int l2,
-                     float* __restrict__ dx, float* __restrict__ part /* [grid][2][768] */) {
+                     void* __restrict__ dx_out, int dx_native, float* __restrict__ part /* [grid][2][768] */) {
   __shared__ float red[kWarps][2 * RZ_HIDDEN / 4];   // reduced in 4 passes of 384 floats
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long warp0 = (long long)blockIdx.x * kWarps + warp;
@@ -97,9 +97,16 @@ prep_rows_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
 #pragma unroll
       for (int i = 0; i < 24; ++i) d[i] = rstd * (d[i] - m1 - v[i] * m2);
     }
-    float4* o = reinterpret_cast<float4*>(dx + row * RZ_HIDDEN) + lane;
+    if (dx_native && sizeof(T) == 2) {
+      // dL/dx in the input's own 16-bit type: no fp32 round trip + conversion pass afterwards
+      uint2* o = reinterpret_cast<uint2*>(static_cast<T*>(dx_out) + row * RZ_HIDDEN) + lane;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) o[32 * j] = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+      for (int j = 0; j < 6; ++j) o[32 * j] = rz::pack4<T>(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+    } else {
+      float4* o = reinterpret_cast<float4*>(static_cast<float*>(dx_out) + row * RZ_HIDDEN) + lane;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) o[32 * j] = make_float4(d[4 * j], d[4 * j + 1], d[4 * j + 2], d[4 * j + 3]);
+    }
   }
   if (part == nullptr) return;
   // CTA reduction of the parameter gradients, 384 floats (= 12 of the 48 per-lane values) a pass
@@ -151,7 +158,7 @@ extern "C" int rz_prep_rows_bwd_blocks(long long rows) {
 
 extern "C" int rz_prep_rows_bwd(const void* x, int dtype, const float* gamma, const float* beta,
                                 long long rows, int rows_per_group, int rows_per_group_padded,
-                                const float* dnorm, int l2, float* dx, float* partials,
+                                const float* dnorm, int l2, void* dx, int dx_native, float* partials,
                                 float* dgamma, float* dbeta, int accumulate, float grad_scale,
                                 void* stream) {
   if (x == nullptr || dnorm == nullptr || dx == nullptr || rows < 0) return RZ_ERR_INVALID;
@@ -169,17 +176,17 @@ extern "C" int rz_prep_rows_bwd(const void* x, int dtype, const float* gamma, co
     case RZ_F32:
       prep_rows_bwd_kernel<float><<<blocks, kWarps * 32, 0, s>>>(
           static_cast<const float*>(x), gamma, beta, rows, rows_per_group, rows_per_group_padded, dnorm,
-          l2, dx, part);
+          l2, dx, dx_native, part);
       break;
     case RZ_BF16:
       prep_rows_bwd_kernel<__nv_bfloat16><<<blocks, kWarps * 32, 0, s>>>(
           static_cast<const __nv_bfloat16*>(x), gamma, beta, rows, rows_per_group, rows_per_group_padded,
-          dnorm, l2, dx, part);
+          dnorm, l2, dx, dx_native, part);
       break;
     case RZ_F16:
       prep_rows_bwd_kernel<__half><<<blocks, kWarps * 32, 0, s>>>(
           static_cast<const __half*>(x), gamma, beta, rows, rows_per_group, rows_per_group_padded, dnorm,
-          l2, dx, part);
+          l2, dx, dx_native, part);
       break;
     default:
       return RZ_ERR_INVALID;

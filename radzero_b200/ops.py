@@ -252,8 +252,9 @@ def prep_rows_bwd(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional
                   dnorm: torch.Tensor, *, rows_per_group: Optional[int] = None,
                   rows_per_group_padded: Optional[int] = None, l2: bool = True,
                   dgamma: Optional[torch.Tensor] = None, dbeta: Optional[torch.Tensor] = None,
-                  accumulate: bool = False):
-    """Backward of prep_rows: returns (dx fp32 (rows, 768), dgamma, dbeta)."""
+                  accumulate: bool = False, native_dx: bool = False):
+    """Backward of prep_rows: returns (dx (rows, 768), dgamma, dbeta).  dx is fp32, or -- with
+    ``native_dx`` and a 16-bit input -- written directly in the input's dtype."""
     _need_cuda(x, gamma, beta, dnorm, dgamma, dbeta)
     x2 = _contig(x).view(-1, HIDDEN)
     rows = x2.shape[0]
@@ -265,7 +266,8 @@ def prep_rows_bwd(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional
         raise RzError("dnorm does not match the padded group layout")
     dev = x.device
     lib = _lib.load()
-    dx = torch.empty((rows, HIDDEN), dtype=torch.float32, device=dev)
+    native = bool(native_dx) and x.dtype in (torch.bfloat16, torch.float16)
+    dx = torch.empty((rows, HIDDEN), dtype=x.dtype if native else torch.float32, device=dev)
     g = _contig(gamma.detach().float()) if gamma is not None else None
     b = _contig(beta.detach().float()) if beta is not None else None
     part = None
@@ -276,7 +278,7 @@ def prep_rows_bwd(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional
             dbeta = torch.zeros(HIDDEN, dtype=torch.float32, device=dev)
             accumulate = False
     rc = lib.rz_prep_rows_bwd(_p(x2), _DTYPES[x.dtype], _p(g), _p(b), rows, rpg, rpp, _p(dnorm),
-                              1 if l2 else 0, _p(dx), _p(part), _p(dgamma), _p(dbeta),
+                              1 if l2 else 0, _p(dx), 1 if native else 0, _p(part), _p(dgamma), _p(dbeta),
                               1 if accumulate else 0, 1.0, _stream())
     _lib.check(rc, "rz_prep_rows_bwd")
     return dx, dgamma, dbeta

@@ -129,9 +129,9 @@ class _ContrastiveStep(torch.autograd.Function):
         g = gamma.detach() if gamma is not None else None
         b = beta.detach() if beta is not None else None
         dx_tok, dgamma, dbeta = K.prep_rows_bwd(tokens.detach(), g, b, dk, rows_per_group=L,
-                                                rows_per_group_padded=Lp)
+                                                rows_per_group_padded=Lp, native_dx=True)
         dx_txt, dgamma, dbeta = K.prep_rows_bwd(text.detach(), g, b, dq_local, dgamma=dgamma,
-                                                dbeta=dbeta, accumulate=True)
+                                                dbeta=dbeta, accumulate=True, native_dx=True)
         # d/dlog(tau): the loss temperature through exp(Z/tau) (= -sum dZ*Z) and, when the
         # attention shares it (attn_temperature: null, radzero.yaml:43), the softmax scores
         d_loss_lt = -(terms[2] * gl).reshape(1)

@@ -108,7 +108,7 @@ def _sim_bwd(k16, q16, tokens, inv_tau, dz, log_tau):
 
 
 def prep_rows_bwd(x, gamma, beta, dnorm, *, rows_per_group=None, rows_per_group_padded=None, l2=True,
-                  dgamma=None, dbeta=None, accumulate=False):
+                  dgamma=None, dbeta=None, accumulate=False, native_dx=False):
     with torch.enable_grad():
         return _prep_rows_bwd(x, gamma, beta, dnorm, rows_per_group, rows_per_group_padded, l2, dgamma,
                               dbeta, accumulate)
