@@ -29,16 +29,28 @@ def _traffic():
         return None
 
 
+CHUNKS = 8                         # the global batch is generated in 8 fixed chunks of 128 images
+
+
 def _inputs(rank, world, dev, dtype, b_global=B_GLOBAL):
+    """This rank's slice of ONE fixed global problem: the same 1024 images / 6084 sentences whatever
+    the number of ranks (chunk c = images [128c, 128c+128) from seed 1000 + c), so the loss printed
+    at 1, 2, 4 and 8 GPUs is the same number."""
     from radzero_b200 import synthetic
+    assert CHUNKS % world == 0, "world size must divide 8"
     counts_all = synthetic.sentence_counts(b_global, seed=42)
+    per = b_global // CHUNKS
+    toks, texts, counts = [], [], []
+    gamma = beta = None
+    for c in range(rank * CHUNKS // world, (rank + 1) * CHUNKS // world):
+        cc = counts_all[c * per:(c + 1) * per]
+        tok, text, gamma, beta, _ = synthetic.make_inputs(per, sum(cc), seed=1000 + c, device=dev)
+        toks.append(tok.to(dtype)); texts.append(text.to(dtype)); counts += cc
     b_local = b_global // world
-    i0 = rank * b_local
-    counts = counts_all[i0:i0 + b_local]
-    n_local = sum(counts)
-    tok, text, gamma, beta, log_tau = synthetic.make_inputs(b_local, n_local, seed=1000 + rank, device=dev)
-    gm = synthetic.group_map_from_counts(counts, first_image=i0, device=dev)
-    return tok.to(dtype), text.to(dtype), gamma, beta, gm, sum(counts_all)
+    gm = synthetic.group_map_from_counts(counts, first_image=rank * b_local, device=dev)
+    # one LayerNorm for the whole job: gamma / beta from a fixed seed so that all ranks agree
+    _, _, gamma, beta, _ = synthetic.make_inputs(1, 1, seed=999, device=dev)
+    return torch.cat(toks), torch.cat(texts), gamma, beta, gm, sum(counts_all)
 
 
 def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
