@@ -16,8 +16,6 @@
 //            vectors (fp16, kept for the backward) + per-tile |o|^2 and <q, o> partials -> Z
 // S is computed exactly once: 2 GEMM units of MMA work for the 2 algorithmic ones.
 // Replaces SimilarityLogit.forward (exp/cxr_pt/model/losses.py:187-240).
-#include <cstdlib>
-
 #include "rz_gemm.cuh"
 
 namespace {
@@ -35,7 +33,6 @@ struct S2Params {
   float* mref;                 // [B, N]
   float* lsum;                 // [B, N]      sum_l exp(s - mref)
   float* lse;                  // optional [B, N] = mref + log(lsum)
-  int debug;                   // RZ_DEBUG experiments: 1 = epilogue does nothing, 2 = no bulk stores
 };
 
 // kScores: also emit the fp32 similarity map (maps.b2 = [B, N, L] fp32 store map)
@@ -132,7 +129,7 @@ struct PassS2 : PolicyBase {
                __float_as_uint(__uint_as_float(v.lo[4 * j + 3]) * scale));
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0 && p.debug != 2) {
+      if (lane == 0) {
         tma_store_3d(&maps.c2, stg, l0, row0, b);
         tma_store_commit();
       }
@@ -173,7 +170,7 @@ struct PassS2 : PolicyBase {
       sts_v4(stg_p + stage_off(lane, j), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0 && p.debug != 2) {
+    if (lane == 0) {
       if (kScores && l0 + 32 < p.L) tma_store_3d(&maps.c2, stg, l0 + 32, row0, b);
       tma_store_3d(&maps.c, stg_p, l0, row0, b);
       tma_store_commit();
@@ -203,7 +200,6 @@ struct PassS2 : PolicyBase {
     }
     const int nch = tile_n(p, tile) / 64;            // 4, or 2 for the narrow last tile
     const int tok0 = nt * kBN;
-    if (p.debug == 1) return;
     Cols64 va, vb;
     ld64(taddr, va);
 #pragma unroll 1
@@ -426,7 +422,6 @@ extern "C" int rz_sim_fwd_large(const void* k_f16, int n_images, int tokens, int
   sp.n_tiles = (Lp + 255) / 256;
   sp.scale = scale; sp.log_tau_scale = log_tau_scale;
   sp.p_out = pbuf; sp.mref = mref; sp.lsum = lsum; sp.lse = lse;
-  sp.debug = getenv("RZ_DEBUG") ? atoi(getenv("RZ_DEBUG")) : 0;
   {
     int rc = tma_scores ? (C == 2 ? launch<PassS2<true, 2>>(m, sp, s) : launch<PassS2<true, 1>>(m, sp, s))
                         : (C == 2 ? launch<PassS2<false, 2>>(m, sp, s) : launch<PassS2<false, 1>>(m, sp, s));

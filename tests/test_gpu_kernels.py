@@ -85,6 +85,18 @@ def test_upsample_processor_variants(kind, size):
         assert want[y, x] >= want.max() - 2e-4
 
 
+def test_upsample_padded_pitch_batch():
+    """(B, N, G*G) views of a padded-pitch buffer (the large-N similarity map) are upsampled in place."""
+    g = torch.Generator().manual_seed(11)
+    store = torch.randn(3, 5, 1376, generator=g).to(DEV)
+    view = store[:, :, 1:1370]
+    assert not view.is_contiguous()
+    got = ops.upsample_maps(view, (70, 90))
+    want = ops.upsample_maps(view.reshape(-1, 1369).contiguous(), (70, 90))
+    assert got.shape == (15, 70, 90)
+    assert torch.equal(got, want)
+
+
 def test_upsample_constant_and_strided_input():
     s = torch.full((3, 1369), 2.5, device=DEV)
     assert (ops.upsample_maps(s, (100, 333)) - 2.5).abs().max() < 1e-6

@@ -40,6 +40,14 @@ def test_prep_rows_bwd(use_ln, l2, dtype):
     if use_ln:
         assert _rel(dg, gd.grad) < 2e-5
         assert _rel(db, bd.grad) < 2e-5
+    # dx written straight in the input's 16-bit type (what the training step uses): same values,
+    # rounded once
+    if dtype != torch.float32:
+        dx16, _, _ = ops.prep_rows_bwd(x.to(DEV), gm.to(DEV) if use_ln else None,
+                                       bt.to(DEV) if use_ln else None, d_pad.to(DEV), rows_per_group=L,
+                                       rows_per_group_padded=Lp, l2=l2, native_dx=True)
+        assert dx16.dtype == dtype
+        assert torch.equal(dx16, dx.to(dtype))
 
 
 # ------------------------------------------------------------------------------ similarity backward
