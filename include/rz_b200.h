@@ -210,6 +210,26 @@ int rz_upsample_maps(const float* scores, long long map_stride, int maps, int gr
                      int out_h, int out_w, int interp_h, int interp_w, int off_y, int off_x,
                      float fill, int mode, float threshold, void* out, void* stream);
 
+/* ---- fused consumer of the similarity map: threshold statistics ---------------------------
+ * The reference evaluates segmentation by upsampling every map, taking the sigmoid, copying it to
+ * the host and thresholding it 101 times (Dice sweep, exp/cxr_pt/inference/segmentation_utils.py:
+ * 255-261; compute_specificity :136-158).  This entry point computes the sufficient statistics of
+ * that sweep in one pass without writing the pixel map.  Geometry arguments as rz_upsample_maps.
+ *   gt_masks          optional uint8 [maps, out_h, out_w] (non-zero = ground truth)
+ *   thresholds_logit  fp32 [n_thresholds] ascending, in the SCORE domain (logit of the probability
+ *                     thresholds; sigmoid(v) > t  <=>  v > logit(t)); n_thresholds <= 127
+ *   hist_all, hist_gt uint32 [maps, n_thresholds + 1]: bin k counts the canvas pixels (all / ground
+ *                     truth only) whose score exceeds exactly k thresholds, so
+ *                     |P_t_j| = sum_{k > j} hist_all[k] and |P_t_j & G| = sum_{k > j} hist_gt[k]
+ *   max_score         fp32 [maps]: maximum interpolated score (a map has a pixel above t iff
+ *                     max_score > logit(t))
+ */
+int rz_map_threshold_stats(const float* scores, long long map_stride, int maps, int grid, int out_h,
+                           int out_w, int interp_h, int interp_w, int off_y, int off_x, float fill,
+                           const unsigned char* gt_masks, const float* thresholds_logit,
+                           int n_thresholds, unsigned int* hist_all, unsigned int* hist_gt,
+                           float* max_score, void* stream);
+
 /* ---- K10: multi-positive NCE loss, forward + backward ----------------------------------
  * Replaces multi_positive_nce_loss + get_row_loss + get_col_loss (losses.py:243-344) and
  * their autograd, for the image-sharded layout of SURVEY.md section 8e: this rank holds

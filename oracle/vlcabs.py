@@ -39,6 +39,8 @@ __all__ = [
     "interpolate_similarity_scores",
     "grounding_point",
     "zero_shot_labels",
+    "dice_sweep_stats",
+    "compute_specificity",
     "contrastive_step_reference",
 ]
 
@@ -321,3 +323,31 @@ def contrastive_step_reference(text: torch.Tensor, group_map: torch.Tensor,
         "text": t.grad, "vision_tokens": x.grad, "gamma": g.grad, "beta": b.grad,
         "log_tau": lt.grad, "t2i_logits": z.detach(),
     }
+
+
+# --------------------------------------------------------------------------- a7 consumers
+def dice_sweep_stats(similarity_scores: torch.Tensor, masks: torch.Tensor, origin_size: Tuple[int, int],
+                     image_processor="blip", thresholds=None) -> Dict[str, torch.Tensor]:
+    """Counts behind the Dice threshold sweep of exp/cxr_pt/inference/segmentation_utils.py:255-261:
+    for every map, prob = sigmoid(interpolate(scores)) (:222-225) and, for every
+    t in np.arange(0, 1.01, 0.01), pred_t = (prob > t) (:258); returns |pred_t|, |pred_t & mask|, |mask|
+    and max prob per map.  (The reference feeds pred_t to torchmetrics' DiceScore, which is not
+    vendored; the counts are what any Dice aggregation is computed from.)"""
+    import numpy as np
+    thresholds = np.arange(0, 1.01, 0.01) if thresholds is None else np.asarray(thresholds, dtype=np.float64)
+    s = similarity_scores.reshape(-1, similarity_scores.shape[-1])
+    pred, inter, mx = [], [], []
+    for m in range(s.shape[0]):
+        prob = torch.sigmoid(interpolate_similarity_scores(s[m], origin_size, image_processor)[0])
+        g = masks[m] != 0
+        pred.append(torch.stack([(prob > float(t)).sum() for t in thresholds]))
+        inter.append(torch.stack([((prob > float(t)) & g).sum() for t in thresholds]))
+        mx.append(prob.max())
+    return {"pred": torch.stack(pred), "inter": torch.stack(inter), "gt": (masks != 0).flatten(1).sum(1),
+            "max_prob": torch.stack(mx), "thresholds": torch.as_tensor(thresholds)}
+
+
+def compute_specificity(negative_probs: torch.Tensor, threshold: float) -> float:
+    """segmentation_utils.py:136-158: share of negative images with no pixel above the threshold."""
+    tn = ((negative_probs > threshold).long().flatten(1).sum(-1) == 0).sum()
+    return (tn / len(negative_probs)).item()

@@ -43,6 +43,7 @@ SIGNATURES: Dict[str, tuple] = {
     "rz_prep_rows_bwd_blocks": (_i, [_ll]),
     "rz_prep_rows_bwd": (_i, [_vp, _i, _vp, _vp, _ll, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _f, _vp]),
     "rz_upsample_maps": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _f, _vp, _vp]),
+    "rz_map_threshold_stats": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "rz_mpnce_partials": (_i, [_vp, _ll, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rz_mpnce_finish": (_i, [_vp, _ll, _i, _i, _i, _vp, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp,
                              _vp, _vp, _vp, _vp]),

@@ -22,6 +22,9 @@ struct UpParams {
   float fill, scale_h, scale_w, thr_logit;
   void* out;
   unsigned long long* keys;
+  // threshold statistics (rz_map_threshold_stats)
+  const unsigned char* gt; const float* thr; int n_thr;
+  unsigned int* hist_all; unsigned int* hist_gt; unsigned int* vmax_bits;
 };
 
 __device__ __forceinline__ void src_index(float scale, int dst, int n_in, int& i0, float& w1) {
@@ -48,28 +51,11 @@ __device__ __forceinline__ unsigned long long argmax_key(float v, unsigned int f
   return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
 }
 
-// x-table entry: source column a (bit 31 set = outside the pasted area -> fill) and weight of
-// column a+1.  One CTA = one band of kBand canvas rows of one map:
-//   1. the grid rows the band touches are staged in shared memory,
-//   2. each canvas row is interpolated vertically ONCE into rowbuf[r][0..G) as PAIRS
-//      (v[a], v[a+1] - v[a]) (a+1 clamped to the last column),
-//   3. the x-table (a, w) of every canvas column is computed once per CTA,
-//   4. threads sweep the band's V-pixel vectors: 1 table load per item, then ONE 64-bit shared
-//      load and ONE fma per pixel, the fused consumer, one coalesced streaming vector store.
-template <int MODE, int V, bool PLAIN>
-__global__ void __launch_bounds__(kThreads)
-upsample_kernel(UpParams p) {
-  extern __shared__ __align__(16) float smem[];
-  const int G = p.grid;
-  float2* xtab = reinterpret_cast<float2*>(smem);               // [out_w rounded up to V]
-  const int wpad = (p.out_w + V - 1) / V * V;
-  float2* rowbuf = reinterpret_cast<float2*>(smem + 2 * wpad);  // [kBand][kRowStride] (v[a], v[a+1]-v[a])
-  float* gbuf = smem + 2 * wpad + 2 * kBand * kRowStride;       // [rows needed <= G][G]
-  const int map = blockIdx.y;
-  const int y_first = blockIdx.x * kBand;
-  const int rows_here = min(kBand, p.out_h - y_first);
-  const float* g = p.scores + (long long)map * p.map_stride;
-
+// Stage one band: the grid rows it touches, the x-table and the vertically interpolated pair rows.
+template <bool kHalf>
+__device__ __forceinline__ void band_setup(const UpParams& p, const float* __restrict__ g, int G, int wpad,
+                                           int y_first, int rows_here, float2* xtab, float2* rowbuf,
+                                           float* gbuf) {
   // grid rows this band touches (vertical source index is monotone in y)
   int ylo = G, yhi = -1;
   {
@@ -105,10 +91,36 @@ upsample_kernel(UpParams p) {
       v0 = (1.0f - w) * ga[c] + w * gb[c];
       v1 = (1.0f - w) * ga[c1] + w * gb[c1];
     }
-    if (MODE == RZ_UP_SIGMOID) { v0 *= 0.5f; v1 *= 0.5f; }     // the consumer wants v / 2
+    if (kHalf) { v0 *= 0.5f; v1 *= 0.5f; }                     // the consumer wants v / 2
     rowbuf[r * kRowStride + c] = make_float2(v0, v1 - v0);
   }
   __syncthreads();
+
+}
+
+// x-table entry: source column a (bit 31 set = outside the pasted area -> fill) and weight of
+// column a+1.  One CTA = one band of kBand canvas rows of one map:
+//   1. the grid rows the band touches are staged in shared memory,
+//   2. each canvas row is interpolated vertically ONCE into rowbuf[r][0..G) as PAIRS
+//      (v[a], v[a+1] - v[a]) (a+1 clamped to the last column),
+//   3. the x-table (a, w) of every canvas column is computed once per CTA,
+//   4. threads sweep the band's V-pixel vectors: 1 table load per item, then ONE 64-bit shared
+//      load and ONE fma per pixel, the fused consumer, one coalesced streaming vector store.
+template <int MODE, int V, bool PLAIN>
+__global__ void __launch_bounds__(kThreads)
+upsample_kernel(UpParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int G = p.grid;
+  float2* xtab = reinterpret_cast<float2*>(smem);               // [out_w rounded up to V]
+  const int wpad = (p.out_w + V - 1) / V * V;
+  float2* rowbuf = reinterpret_cast<float2*>(smem + 2 * wpad);  // [kBand][kRowStride] (v[a], v[a+1]-v[a])
+  float* gbuf = smem + 2 * wpad + 2 * kBand * kRowStride;       // [rows needed <= G][G]
+  const int map = blockIdx.y;
+  const int y_first = blockIdx.x * kBand;
+  const int rows_here = min(kBand, p.out_h - y_first);
+  const float* g = p.scores + (long long)map * p.map_stride;
+
+  band_setup<MODE == RZ_UP_SIGMOID>(p, g, G, wpad, y_first, rows_here, xtab, rowbuf, gbuf);
 
   // work item = V adjacent canvas columns x kRowGroup consecutive rows: the x-table entry is
   // loaded once per item and the row loop is unrolled with immediate shared-memory offsets
@@ -223,6 +235,98 @@ __global__ void argmax_decode_kernel(long long* out, int maps, int out_w) {
   out[2 * i + 1] = (long long)(flat / (unsigned int)out_w);
 }
 
+
+// ---- fused consumer: threshold statistics without ever writing the pixel map ------------------
+// For every map: hist_all[k] = number of canvas pixels whose interpolated score v satisfies
+// (#thresholds below v) == k, hist_gt[k] = the same restricted to ground-truth pixels, and max v.
+// A suffix sum over k gives |P_t| and |P_t & G| for all thresholds at once -- the Dice sweep of
+// exp/cxr_pt/inference/segmentation_utils.py:255-261 and compute_specificity (:136-158) -- from one
+// pass that reads 5.5 KB of scores + H*W bytes of mask per map instead of writing H*W*4 bytes,
+// copying them to the host and thresholding them 101 times.
+constexpr int kMaxThr = 127;
+constexpr int kBins = kMaxThr + 1;
+
+__device__ __forceinline__ unsigned int order_bits(float v) {
+  const unsigned int u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(kThreads)
+map_stats_kernel(UpParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int G = p.grid;
+  float2* xtab = reinterpret_cast<float2*>(smem);
+  const int wpad = p.out_w;
+  float2* rowbuf = reinterpret_cast<float2*>(smem + 2 * wpad);
+  float* gbuf = smem + 2 * wpad + 2 * kBand * kRowStride;
+  float* thr = gbuf + G * G;                                          // [kBins]: thresholds, then +inf
+  unsigned int* hist = reinterpret_cast<unsigned int*>(thr + kBins);  // [warps][2][kBins]
+  const int map = blockIdx.y;
+  const int y_first = blockIdx.x * kBand;
+  const int rows_here = min(kBand, p.out_h - y_first);
+  const float* g = p.scores + (long long)map * p.map_stride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kBins; i += kThreads) thr[i] = i < p.n_thr ? __ldg(p.thr + i) : INFINITY;
+  for (int i = threadIdx.x; i < (kThreads / 32) * 2 * kBins; i += kThreads) hist[i] = 0u;
+  band_setup<false>(p, g, G, wpad, y_first, rows_here, xtab, rowbuf, gbuf);   // ends with __syncthreads
+  unsigned int* hw = hist + warp * 2 * kBins;
+  const unsigned char* gt = p.gt != nullptr ? p.gt + (long long)map * p.out_h * p.out_w : nullptr;
+  const int items = rows_here * p.out_w;
+  float vmax = -INFINITY;
+  for (int it0 = warp * 32; it0 < items; it0 += kThreads) {           // warp-uniform trip count
+    const int it = it0 + lane;
+    const bool valid = it < items;
+    int k = -1;
+    bool isgt = false;
+    if (valid) {
+      const int r = it / p.out_w, x = it - r * p.out_w;
+      const int y = y_first + r;
+      const float2 t = xtab[x];
+      const int a = __float_as_int(t.x);
+      const int iy = y - p.off_y;
+      float v = p.fill;
+      if (a >= 0 && iy >= 0 && iy < p.interp_h) {
+        const float2 pd = rowbuf[r * kRowStride + (a & 0xffff)];
+        v = fmaf(t.y, pd.y, pd.x);
+      }
+      vmax = fmaxf(vmax, v);
+      // k = number of thresholds strictly below v (thr ascending, padded with +inf): 7 probes
+      int lo = 0;
+#pragma unroll
+      for (int step = kBins / 2; step > 0; step >>= 1)
+        if (thr[lo + step - 1] < v) lo += step;
+      k = lo;
+      if (gt != nullptr) isgt = gt[(long long)y * p.out_w + x] != 0;
+    }
+    // warp-aggregated histogram update: neighbouring pixels mostly share a bin
+    const unsigned int peers = __match_any_sync(0xffffffffu, k);
+    const unsigned int gtb = __ballot_sync(0xffffffffu, isgt);
+    if (k >= 0 && lane == __ffs(peers) - 1) {
+      hw[k] += __popc(peers);
+      hw[kBins + k] += __popc(peers & gtb);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) {
+    unsigned int s = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) s += hist[w * 2 * kBins + i];
+    const int k = i % kBins;
+    if (s != 0u && k <= p.n_thr)
+      atomicAdd((i < kBins ? p.hist_all : p.hist_gt) + (long long)map * (p.n_thr + 1) + k, s);
+  }
+  vmax = rz::warp_max(vmax);
+  if (lane == 0 && vmax > -INFINITY) atomicMax(p.vmax_bits + map, order_bits(vmax));
+}
+
+__global__ void decode_max_kernel(unsigned int* bits, int maps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= maps) return;
+  const unsigned int u = bits[i];
+  bits[i] = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;       // back to the float's bit pattern
+}
+
 template <int MODE, int V>
 int launch_v(const UpParams& p, int maps, cudaStream_t s) {
   dim3 grid((p.out_h + kBand - 1) / kBand, maps), block(kThreads);
@@ -299,4 +403,44 @@ extern "C" int rz_upsample_maps(const float* scores, long long map_stride, int m
     }
     default: return RZ_ERR_INVALID;
   }
+}
+
+extern "C" int rz_map_threshold_stats(const float* scores, long long map_stride, int maps, int grid,
+                                      int out_h, int out_w, int interp_h, int interp_w, int off_y,
+                                      int off_x, float fill, const unsigned char* gt_masks,
+                                      const float* thresholds_logit, int n_thresholds,
+                                      unsigned int* hist_all, unsigned int* hist_gt, float* max_score,
+                                      void* stream) {
+  if (scores == nullptr || thresholds_logit == nullptr || hist_all == nullptr || hist_gt == nullptr ||
+      max_score == nullptr)
+    return RZ_ERR_INVALID;
+  if (maps < 0 || grid <= 0 || grid > kMaxGrid || out_h <= 0 || out_w <= 0 || interp_h <= 0 ||
+      interp_w <= 0 || n_thresholds <= 0)
+    return RZ_ERR_INVALID;
+  if (n_thresholds > kMaxThr || out_w > kMaxOutW || maps > 65535) return RZ_ERR_UNSUPPORTED;
+  if (maps == 0) return RZ_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  UpParams p;
+  p.scores = scores; p.map_stride = map_stride; p.grid = grid;
+  p.out_h = out_h; p.out_w = out_w; p.interp_h = interp_h; p.interp_w = interp_w;
+  p.off_y = off_y; p.off_x = off_x; p.fill = fill;
+  p.scale_h = (float)grid / (float)interp_h;
+  p.scale_w = (float)grid / (float)interp_w;
+  p.thr_logit = 0.f; p.out = nullptr; p.keys = nullptr;
+  p.gt = gt_masks; p.thr = thresholds_logit; p.n_thr = n_thresholds;
+  p.hist_all = hist_all; p.hist_gt = hist_gt; p.vmax_bits = reinterpret_cast<unsigned int*>(max_score);
+  const size_t bins = (size_t)maps * (n_thresholds + 1) * sizeof(unsigned int);
+  RZ_CUDA_OK(cudaMemsetAsync(hist_all, 0, bins, s));
+  RZ_CUDA_OK(cudaMemsetAsync(hist_gt, 0, bins, s));
+  RZ_CUDA_OK(cudaMemsetAsync(max_score, 0, (size_t)maps * sizeof(float), s));
+  const size_t smem = (size_t)(2 * out_w + 2 * kBand * kRowStride + grid * grid + kBins) * sizeof(float) +
+                      (size_t)(kThreads / 32) * 2 * kBins * sizeof(unsigned int);
+  RZ_CUDA_OK(cudaFuncSetAttribute(map_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid_dim((out_h + kBand - 1) / kBand, maps);
+  map_stats_kernel<<<grid_dim, kThreads, smem, s>>>(p);
+  RZ_LAUNCH_OK();
+  decode_max_kernel<<<(maps + 255) / 256, 256, 0, s>>>(reinterpret_cast<unsigned int*>(max_score), maps);
+  RZ_LAUNCH_OK();
+  rz_count_launch(2);
+  return RZ_OK;
 }

@@ -93,6 +93,60 @@ def get_grounding_point(similarity_score: torch.Tensor, image_size, image_proces
     return pts
 
 
+# ----------------------------------------------------------------------------- fused consumers
+def threshold_logits(thresholds, device) -> torch.Tensor:
+    """Probability thresholds -> score-domain thresholds: sigmoid(v) > t  <=>  v > logit(t).
+    t <= 0 maps to -ln(FLT_MAX) (below it fp32 sigmoid is exactly 0, so `prob > 0` is false, as for
+    the reference's -999 fill), t >= 1 to +inf (never exceeded)."""
+    import math
+    out = []
+    for t in thresholds:
+        t = float(t)
+        out.append(-88.72283905206835 if t <= 0.0 else (math.inf if t >= 1.0 else math.log(t / (1.0 - t))))
+    return torch.tensor(out, dtype=torch.float32, device=device)
+
+
+@torch.no_grad()
+def dice_sweep_stats(similarity_scores: torch.Tensor, masks: torch.Tensor, origin_size, image_processor,
+                     thresholds=None):
+    """Sufficient statistics of the reference's Dice threshold sweep and specificity
+    (exp/cxr_pt/inference/segmentation_utils.py:255-261, 136-158) for a batch of maps, computed on
+    the GPU from the patch-grid scores: the pixel maps are never written, copied or re-thresholded.
+
+    similarity_scores (..., P*P); masks uint8 (M, H, W).  Returns a dict of tensors indexed
+    [map, threshold]: ``pred`` = |prob > t|, ``inter`` = |(prob > t) & mask|, plus ``gt`` = |mask|
+    per map, ``max_prob`` per map and ``thresholds``.  Dice_t = 2 inter / (pred + gt); a negative
+    image is a true negative at t iff max_prob <= t."""
+    import numpy as np
+    thresholds = np.arange(0, 1.01, 0.01) if thresholds is None else np.asarray(thresholds, dtype=np.float64)
+    kind = processor_kind(image_processor)
+    kw = interpolate_params(origin_size, kind)
+    dev = similarity_scores.device
+    thr = threshold_logits(thresholds, dev)
+    ha, hg, mx = ops.map_threshold_stats(similarity_scores, (int(origin_size[0]), int(origin_size[1])), thr,
+                                         gt_masks=masks, **kw)
+    # bin k = pixels above exactly k thresholds  ->  above threshold j  <=>  k > j
+    pred = ha.flip(1).cumsum(1).flip(1)[:, 1:]
+    inter = hg.flip(1).cumsum(1).flip(1)[:, 1:]
+    return {"pred": pred, "inter": inter, "gt": hg.sum(1), "max_prob": torch.sigmoid(mx),
+            "thresholds": torch.as_tensor(thresholds)}
+
+
+def best_dice_and_specificity(pos_stats, neg_stats=None):
+    """The reference's selection loop (segmentation_utils.py:255-270) on the statistics above: the
+    threshold maximising the Dice of the positive maps -- micro-averaged over the batch, i.e. the
+    confusion counts are summed over images before the ratio -- and the image-level specificity
+    of the negative maps at that threshold."""
+    pred, inter, gt = pos_stats["pred"].sum(0).double(), pos_stats["inter"].sum(0).double(), pos_stats["gt"].sum().double()
+    dice = 2.0 * inter / (pred + gt).clamp_min(1.0)
+    j = int(dice.argmax())                      # first maximum, as `if cur_dice > best_dice`
+    t = float(pos_stats["thresholds"][j])
+    out = {"dice": float(dice[j]), "best_threshold": t}
+    if neg_stats is not None:
+        out["specificity"] = float((neg_stats["pred"][:, j] == 0).double().mean())
+    return out
+
+
 # ----------------------------------------------------------------------------- surface 1
 def _load_image(image):
     """Accept a path, a PIL image or an (H, W[, C]) uint8 array/tensor; return (PIL RGB, (H, W))."""

@@ -337,6 +337,43 @@ def upsample_maps(scores: torch.Tensor, out_hw: Tuple[int, int], *, mode: int = 
     return out
 
 
+def map_threshold_stats(scores: torch.Tensor, out_hw: Tuple[int, int], thresholds_logit: torch.Tensor, *,
+                        gt_masks: Optional[torch.Tensor] = None,
+                        interp_hw: Optional[Tuple[int, int]] = None, offset: Tuple[int, int] = (0, 0),
+                        fill: float = -999.0, grid: Optional[int] = None):
+    """Threshold statistics of upsampled maps without materialising them.
+
+    Returns (hist_all, hist_gt) int64 (maps, T + 1) and max_score fp32 (maps,); see
+    rz_map_threshold_stats in include/rz_b200.h."""
+    _need_cuda(scores, thresholds_logit, gt_masks)
+    scores = _as_maps(scores.float() if scores.dtype != torch.float32 else scores)
+    maps, n = scores.shape
+    g = grid or int(round(n ** 0.5))
+    if g * g != n:
+        raise RzError(f"scores last dim {n} is not a square grid")
+    H, W = int(out_hw[0]), int(out_hw[1])
+    ih, iw = (H, W) if interp_hw is None else (int(interp_hw[0]), int(interp_hw[1]))
+    thr = _contig(thresholds_logit.float())
+    T = thr.numel()
+    if gt_masks is not None:
+        if gt_masks.dtype != torch.uint8 or tuple(gt_masks.shape) != (maps, H, W) or not gt_masks.is_contiguous():
+            raise RzError("gt_masks must be contiguous uint8 (maps, H, W)")
+    dev = scores.device
+    ha = torch.empty((maps, T + 1), dtype=torch.int32, device=dev)
+    hg = torch.empty((maps, T + 1), dtype=torch.int32, device=dev)
+    mx = torch.empty(maps, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    step = 32768
+    for m0 in range(0, maps, step):
+        m1 = min(maps, m0 + step)
+        rc = lib.rz_map_threshold_stats(_p(scores[m0:]), scores.stride(0), m1 - m0, g, H, W, ih, iw,
+                                        int(offset[0]), int(offset[1]), float(fill),
+                                        _p(gt_masks[m0:]) if gt_masks is not None else None, _p(thr), T,
+                                        _p(ha[m0:]), _p(hg[m0:]), _p(mx[m0:]), _stream())
+        _lib.check(rc, "rz_map_threshold_stats")
+    return ha.long(), hg.long(), mx
+
+
 # ----------------------------------------------------------------------------- K10
 def mpnce_partials(z: torch.Tensor, group_map: torch.Tensor, col0: int, inv_tau: float):
     """Phase 1 of MP-NCE on the local column block.  Returns (rowsum, pos, colneg, colpos)."""

@@ -163,3 +163,37 @@ def test_mpnce_vs_oracle_and_sharded(n, b):
             tot += t
             assert (dzr.cpu().double() - zd.grad[:, r * bl:(r + 1) * bl]).abs().max() < 1e-4 * zd.grad.abs().max()
         assert abs(((tot[0] + tot[1]) / (2 * n)).item() - want.item()) < 1e-4 * abs(want.item())
+
+
+# ------------------------------------------------------------------------------ fused consumers
+@pytest.mark.parametrize("kind,size", [("blip", (97, 131)), ("bit", (150, 120)), ("blip", (518, 518))])
+def test_dice_sweep_stats_vs_oracle(kind, size):
+    """Dice threshold sweep / specificity statistics straight from the patch-grid scores
+    (segmentation_utils.py:255-261, 136-158) against the oracle's upsample -> sigmoid -> `> t` loop."""
+    from radzero_b200 import inference
+    g = torch.Generator().manual_seed(21)
+    M = 6 if size[0] < 500 else 2
+    scores = torch.randn(M, 1369, generator=g) * 3.0
+    yy, xx = torch.meshgrid(torch.arange(size[0]), torch.arange(size[1]), indexing="ij")
+    masks = torch.stack([(((yy - size[0] * (0.3 + 0.1 * m)) ** 2 + (xx - size[1] * 0.5) ** 2) < (8 + 4 * m) ** 2)
+                         for m in range(M)]).to(torch.uint8)
+    masks[-1] = 0                                                  # a negative image
+    got = inference.dice_sweep_stats(scores.to(DEV), masks.to(DEV), size, kind)
+    want = oracle.dice_sweep_stats(scores, masks, size, kind)
+    assert torch.equal(got["gt"].cpu(), want["gt"])
+    assert (got["max_prob"].cpu() - want["max_prob"]).abs().max() < 1e-5
+    # counts agree except for pixels whose probability sits within fp32 noise of a threshold
+    thr = want["thresholds"]
+    for m in range(M):
+        prob = torch.sigmoid(oracle.interpolate_similarity_scores(scores[m], size, kind)[0])
+        near = torch.stack([((prob - float(t)).abs() < 2e-5).sum() for t in thr])
+        assert ((got["pred"][m].cpu() - want["pred"][m]).abs() <= near).all()
+        assert ((got["inter"][m].cpu() - want["inter"][m]).abs() <= near).all()
+    pos = {k: (v[:-1] if v.dim() and v.shape[0] == M else v) for k, v in got.items()}
+    neg = {k: (v[-1:] if v.dim() and v.shape[0] == M else v) for k, v in got.items()}
+    res = inference.best_dice_and_specificity(pos, neg)
+    wp, wi, wg = want["pred"][:-1].sum(0).double(), want["inter"][:-1].sum(0).double(), want["gt"][:-1].sum().double()
+    wdice = 2 * wi / (wp + wg).clamp_min(1.0)
+    assert abs(res["dice"] - float(wdice.max())) < 1e-3
+    negprob = torch.sigmoid(oracle.interpolate_similarity_scores(scores[-1], size, kind))
+    assert res["specificity"] == oracle.compute_specificity(negprob, res["best_threshold"])
