@@ -278,17 +278,49 @@ def run_ours(args):
         h_tok = tok.cpu().pin_memory()
         h_txt = text.cpu().pin_memory()
         ksteps = max(2, min(args.steps, 5))
+        # every step uploads ITS inputs from pinned host memory and downloads ITS result; as in any
+        # serving loop the upload of step i+1 runs on a copy stream while step i computes / downloads
+        # (PCIe is full duplex), all inside the timed region
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
         r_host = None
-        for _ in range(2):
-            r = step(h_tok.to(dev, non_blocking=True), h_txt.to(dev, non_blocking=True))
-            if r_host is None:      # results land in pinned host memory (pageable D2H runs at ~3 GB/s)
-                r_host = torch.empty(r.shape, dtype=r.dtype, pin_memory=True)
-            r_host.copy_(r)
+
+        # two static device buffers (ping-pong): no allocator traffic inside the timed region
+        d_tok = [torch.empty(h_tok.shape, dtype=h_tok.dtype, device=dev) for _ in range(2)]
+        d_txt = [torch.empty(h_txt.shape, dtype=h_txt.dtype, device=dev) for _ in range(2)]
+        used = [None, None]            # event: the step that last read buffer k has been enqueued and finished
+
+        def upload(k):
+            with torch.cuda.stream(copy_stream):
+                if used[k] is not None:
+                    copy_stream.wait_event(used[k])
+                d_tok[k].copy_(h_tok, non_blocking=True)
+                d_txt[k].copy_(h_txt, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return ev
+
+        def e2e_loop(n):
+            nonlocal r_host
+            ev = upload(0)
+            for i in range(n):
+                k = i & 1
+                main.wait_event(ev)
+                if i + 1 < n:
+                    ev = upload(k ^ 1)
+                a, b = d_tok[k], d_txt[k]
+                r = step(a, b)
+                if r_host is None:          # results land in pinned host memory (pageable D2H is ~3 GB/s)
+                    r_host = torch.empty(r.shape, dtype=r.dtype, pin_memory=True)
+                r_host.copy_(r, non_blocking=True)
+                used[k] = torch.cuda.Event()
+                used[k].record(main)
+            main.synchronize()
+
+        e2e_loop(2)
         barrier()
         e0.record()
-        for _ in range(ksteps):
-            r = step(h_tok.to(dev, non_blocking=True), h_txt.to(dev, non_blocking=True))
-            r_host.copy_(r, non_blocking=True)
+        e2e_loop(ksteps)
         e1.record()
         barrier()
         ms2 = e0.elapsed_time(e1)
@@ -299,6 +331,8 @@ def run_ours(args):
         e2e = {"value": maps_per_step / (ms2 / ksteps * 1e-3), "unit": "maps/s",
                "h2d_bytes_per_step": (h_tok.numel() + h_txt.numel()) * 4,
                "d2h_bytes_per_step": r_host.numel() * r_host.element_size(), "steps": ksteps,
+               "pcie_gbs": ((h_tok.numel() + h_txt.numel()) * 4 + r_host.numel() * r_host.element_size())
+               / (ms2 / ksteps * 1e-3) / 1e9,
                "api": "RadZeroLoss.similarity_prob" if args.workload == "cls" else "RadZeroLoss.similarity"}
 
     # clocks / throttle reasons were sampled from the start of the timed region to here: the timed

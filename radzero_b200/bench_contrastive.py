@@ -99,16 +99,48 @@ def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
     ms_step = ms / steps
     flops = GEMM_UNITS * UNIT_FLOP * B_GLOBAL * n_total
     ach = flops / (ms_step * 1e-3) / 1e12 / world            # per GPU
-    # end to end: host-resident inputs, loss read back
+    # end to end: host-resident (pinned) inputs, loss read back every step.  As in a real training loop
+    # the NEXT step's inputs are copied on a side stream while the current step computes (double
+    # buffering); every step's H2D copy and D2H read still happen inside the timed region.
     h_tok, h_txt = tok.cpu().pin_memory(), text.cpu().pin_memory()
-    for _ in range(1):
-        step(h_tok.to(dev, non_blocking=True), h_txt.to(dev, non_blocking=True))
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+
+    # two static device buffers (ping-pong): no allocator traffic inside the timed region
+    d_tok = [torch.empty(h_tok.shape, dtype=h_tok.dtype, device=dev) for _ in range(2)]
+    d_txt = [torch.empty(h_txt.shape, dtype=h_txt.dtype, device=dev) for _ in range(2)]
+    used = [None, None]            # event: the step that last read buffer k has been enqueued and finished
+
+    def upload(k):
+        with torch.cuda.stream(copy_stream):
+            if used[k] is not None:
+                copy_stream.wait_event(used[k])
+            d_tok[k].copy_(h_tok, non_blocking=True)
+            d_txt[k].copy_(h_txt, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
+    def e2e_loop(n):
+        last = None
+        ev = upload(0)
+        for i in range(n):
+            k = i & 1
+            main.wait_event(ev)
+            if i + 1 < n:
+                ev = upload(k ^ 1)
+            a, b = d_tok[k], d_txt[k]
+            l, _ = step(a, b)
+            last = l.item()                     # D2H read of the step's loss
+            used[k] = torch.cuda.Event()
+            used[k].record(main)
+        return last
+
+    e2e_loop(2)
     barrier()
-    ks = 2
+    ks = 4
     e0.record()
-    for _ in range(ks):
-        l, _ = step(h_tok.to(dev, non_blocking=True), h_txt.to(dev, non_blocking=True))
-        l_host = l.item()
+    l_host = e2e_loop(ks)
     e1.record()
     barrier()
     ms2 = e0.elapsed_time(e1)
@@ -151,7 +183,8 @@ def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
                      "peak_source": pk["src"] + " sustained (kernel timed inside a long step)"},
         "e2e": {"value": 1e3 / (ms2 / ks), "unit": "steps/s",
                 "h2d_bytes_per_step": (h_tok.numel() + h_txt.numel()) * 2, "d2h_bytes_per_step": 4,
-                "api": "RadZeroLoss.forward + backward"},
+                "api": "RadZeroLoss.forward + backward", "steps": ks,
+                "note": "inputs of step i+1 are uploaded on a copy stream while step i computes"},
         "mpnce": mpnce,
     }
     return out
