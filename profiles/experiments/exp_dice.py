@@ -1,5 +1,5 @@
 import torch, sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from radzero_b200 import inference, ops, _lib
 import oracle
 dev = torch.device("cuda:0")

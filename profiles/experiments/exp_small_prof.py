@@ -1,5 +1,5 @@
 import torch, sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from radzero_b200 import ops, synthetic
 dev = torch.device("cuda:0")
 B, N = 256, 14
