@@ -54,7 +54,7 @@ struct PolicyBase {
 
 template <class V>
 struct Layout {
-  static constexpr int kBBytes = V::kBN * 128;
+  static constexpr int kBBytes = V::kBN * 128 / V::kCluster;      // a CTA pair splits B between its CTAs
   static constexpr int kStageBytes = V::kAccs * kABytes + kBBytes;
   // 227 KB of dynamic shared memory per CTA, minus alignment slack + control block
   static constexpr int kBudget = 232448 - 2048 - V::kEpiSmem;
@@ -74,10 +74,16 @@ struct Ctrl {
   uint32_t tmem_slot;
 };
 
-// V::kCluster == 2: the CTAs of a cluster pair run tiles (2i, 2i+1) of an item in lockstep.  The
-// two tiles share their B operand: each CTA fetches HALF of it and multicasts it into both shared
-// memories, so the L2 -> SM traffic of B halves.  A stage may be refilled only when BOTH CTAs'
-// MMAs have consumed it, hence the `empty` barriers count kCluster multicast commits.
+// V::kCluster == 2: CTA-PAIR mode (tcgen05 cta_group::2).  The two CTAs of a cluster run tiles
+// (2i, 2i+1) of an item -- two 128-row A tiles that share their B operand -- as ONE 256 x kBN MMA:
+// each CTA loads its own A tile and HALF of B into its own shared memory, the leader's elected thread
+// issues the MMAs for both, and each CTA's tensor core reads the other half of B from its partner.
+// Per CTA and k-step this moves 16 + kBN/4 KB instead of 16 + kBN/2 KB into shared memory (6 stages
+// instead of 4 at kBN = 256), which is what the single-CTA main loop was short of.
+//   full[st]      lives in the leader: its own arrive.expect_tx (bytes of BOTH CTAs) + the partner's
+//                 remote arrive; both CTAs' TMA loads complete_tx on it
+//   empty[st], acc_full[a]   per CTA, signalled by the leader's multicast commits
+//   acc_empty[a]  lives in the leader: one arrival per epilogue warp of BOTH CTAs (4 local + 4 remote)
 template <class V>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
@@ -94,10 +100,11 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
   const int inner = V::inner(p);
   const int n_items = V::num_tiles(p) / (inner * C);
   const int ksteps = V::k_steps(p);
+  constexpr uint32_t kTmem = L::kTmemCols < 32 ? 32 : L::kTmemCols;
 
   if (tid == 0) {
-    for (int i = 0; i < L::kStages; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], C); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->acc_full[i], 1); mbar_init(&ctl->acc_empty[i], 128); }
+    for (int i = 0; i < L::kStages; ++i) { mbar_init(&ctl->full[i], C); mbar_init(&ctl->empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->acc_full[i], 1); mbar_init(&ctl->acc_empty[i], 4 * C); }
     for (int i = 0; i < 8; ++i) mbar_init(&ctl->epi_bar[i], 1);
     fence_barrier_init();
   }
@@ -106,7 +113,7 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
       prefetch_tmap(&maps.a); prefetch_tmap(&maps.b);
       if (V::kAccs > 1 || V::kTwoPhase) { prefetch_tmap(&maps.a2); prefetch_tmap(&maps.b2); }
     }
-    tmem_alloc(&ctl->tmem_slot, L::kTmemCols < 32 ? 32 : L::kTmemCols);
+    if (C > 1) tmem_alloc_pair(&ctl->tmem_slot, kTmem); else tmem_alloc(&ctl->tmem_slot, kTmem);
   }
   tc_fence_before();
   if (C > 1) cluster_sync_all(); else __syncthreads();
@@ -122,7 +129,8 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
           for (int ks = 0; ks < ksteps; ++ks, ++g) {
             const int st = (int)(g % L::kStages);
             mbar_wait(&ctl->empty[st], (uint32_t)(((g / L::kStages) & 1) ^ 1));
-            mbar_arrive_expect_tx(&ctl->full[st], (uint32_t)L::kStageBytes);
+            if (rank == 0) mbar_arrive_expect_tx(&ctl->full[st], (uint32_t)(L::kStageBytes * C));
+            else mbar_arrive_cluster(mapa_u32(smem_u32(&ctl->full[st]), 0));
             uint8_t* sa = base + st * L::kStageBytes;
             V::load(p, maps, tile, ks, sa, sa + kABytes, sa + V::kAccs * kABytes, &ctl->full[st], rank);
           }
@@ -131,14 +139,14 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
     }
     __syncwarp();
   } else if (warp == 5) {
-    if (elect_one()) {
+    if (rank == 0 && elect_one()) {
       long long g = 0;
       int it = 0;
       for (int item = cid; item < n_items; item += ncl)
       for (int sub = 0; sub < inner; ++sub, ++it) {
-        const int tile = (item * C + rank) * inner + sub;
+        const int tile = (item * C) * inner + sub;
         const int tn = V::tile_n(p, tile);
-        const uint32_t idesc = make_idesc_f16(kBM, (uint32_t)(tn > 0 ? tn : V::kBN), V::kAMn ? 1 : 0, V::kBMn ? 1 : 0);
+        const uint32_t idesc = make_idesc_f16(kBM * C, (uint32_t)(tn > 0 ? tn : V::kBN), V::kAMn ? 1 : 0, V::kBMn ? 1 : 0);
         const int acc = it & 1;
         mbar_wait(&ctl->acc_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
         tc_fence_after();
@@ -158,19 +166,21 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
               const uint32_t aa = sa + a * kABytes;
               const uint64_t ad = V::kAMn ? make_smem_desc(aa + k4 * 2048, kMnBlock, 1024)
                                           : make_smem_desc(aa + k4 * 32, 0, 1024);
-              mma_f16_ss(d0 + a * V::kBN, ad, bd, idesc, (ks | k4) ? 1u : 0u);
+              if (C > 1) mma_f16_ss_pair(d0 + a * V::kBN, ad, bd, idesc, (ks | k4) ? 1u : 0u);
+              else mma_f16_ss(d0 + a * V::kBN, ad, bd, idesc, (ks | k4) ? 1u : 0u);
             }
           }
-          if (C > 1) mma_commit_mc(&ctl->empty[st], (uint16_t)((1u << C) - 1u));
-          else mma_commit(&ctl->empty[st]);
+          if (C > 1) mma_commit_pair(&ctl->empty[st]); else mma_commit(&ctl->empty[st]);
         }
-        mma_commit(&ctl->acc_full[acc]);
+        if (C > 1) mma_commit_pair(&ctl->acc_full[acc]); else mma_commit(&ctl->acc_full[acc]);
       }
     }
     __syncwarp();
   } else {
     int it = 0;
     typename V::State state{};
+    const uint32_t acc_empty_leader[2] = {C > 1 ? mapa_u32(smem_u32(&ctl->acc_empty[0]), 0) : 0u,
+                                          C > 1 ? mapa_u32(smem_u32(&ctl->acc_empty[1]), 0) : 0u};
     for (int item = cid; item < n_items; item += ncl)
     for (int sub = 0; sub < inner; ++sub, ++it) {
       const int tile = (item * C + rank) * inner + sub;
@@ -184,15 +194,18 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
       V::epilogue(p, maps, tile, next_tile, tmem_base + acc * (V::kAccs * V::kBN), warp, lane, ctl->epi_bar,
                   state, epi_smem);
       tc_fence_before();
-      mbar_arrive(&ctl->acc_empty[acc]);
+      __syncwarp();                       // one arrival per epilogue warp
+      if (lane == 0) {
+        if (C > 1) mbar_arrive_cluster(acc_empty_leader[acc]); else mbar_arrive(&ctl->acc_empty[acc]);
+      }
     }
     // bulk stores issued by epilogue lanes must have read their staging buffers before exit
     if (V::kEpiSmem > 0 && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
-  // (cluster) nobody leaves while the partner may still multicast into this CTA or signal it
+  // (pair) nobody leaves while the partner may still read this CTA's operands or signal its barriers
   if (C > 1) cluster_sync_all(); else __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, L::kTmemCols < 32 ? 32 : L::kTmemCols);
+  if (warp == 4) { if (C > 1) tmem_dealloc_pair(tmem_base, kTmem); else tmem_dealloc(tmem_base, kTmem); }
 }
 
 // resident clusters of gemm_kernel<V> on this device (persistent grid size / kCluster)
@@ -234,43 +247,42 @@ int launch(const Maps& maps, const typename V::Params& p, cudaStream_t s) {
 }
 
 // ---- helpers for policies ---------------------------------------------------------------
+// One TMA box into this CTA's shared memory.  C == 2 (CTA pair): the completion is signalled on the
+// LEADER's copy of `bar` (the MMA-issuing thread waits there for both CTAs' halves).
+template <int C>
+__device__ __forceinline__ void tma_ld(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                       uint64_t hint) {
+  if (C == 1) tma_load_3d(m, bar, dst, c0, c1, c2, hint);
+  else tma_load_3d_pair(m, mapa_u32(smem_u32(bar), 0), dst, c0, c1, c2, hint);
+}
 // K-major operand tile: `rows` rows x 64 K-elements, one TMA box
+template <int C = 1>
 __device__ __forceinline__ void load_kmajor(const CUtensorMap* m, uint64_t* bar, void* dst, int k0,
                                             int row0, int batch, uint64_t hint = kEvictNormal) {
-  tma_load_3d(m, bar, dst, k0, row0, batch, hint);
+  tma_ld<C>(m, bar, dst, k0, row0, batch, hint);
 }
 // MN-major operand tile: `blocks` blocks of [64 K-rows x 64 MN-elements]
+template <int C = 1>
 __device__ __forceinline__ void load_mnmajor(const CUtensorMap* m, uint64_t* bar, uint8_t* dst,
                                              int mn0, int k0, int batch, int blocks,
                                              uint64_t hint = kEvictNormal) {
   for (int i = 0; i < blocks; ++i)
-    tma_load_3d(m, bar, dst + i * kMnBlock, mn0 + i * 64, k0, batch, hint);
+    tma_ld<C>(m, bar, dst + i * kMnBlock, mn0 + i * 64, k0, batch, hint);
 }
-// The same tiles when the C CTAs of a cluster share the operand: CTA `rank` fetches its 1/C of the
-// rows (K-major; the tensor map's box holds rows / C rows) or of the blocks (MN-major) and
-// multicasts it to all of them.
+// The B operand of a CTA pair: CTA `rank` loads ITS half -- rows [rank * rows / C, ...) of a K-major
+// tile (the tensor map's box holds kBN / C rows) or blocks [rank * blocks / C, ...) of an MN-major one
+// -- to the start of its own B buffer; the pair's MMA reads both halves.
 template <int C>
 __device__ __forceinline__ void load_kmajor_shared(const CUtensorMap* m, uint64_t* bar, uint8_t* dst,
                                                    int k0, int row0, int batch, int rows, int rank) {
-  if (C == 1) {
-    tma_load_3d(m, bar, dst, k0, row0, batch, kEvictNormal);
-  } else {
-    const int part = rows / C;
-    tma_load_3d_mc(m, bar, dst + rank * part * 128, k0, row0 + rank * part, batch,
-                   (uint16_t)((1u << C) - 1u), kEvictNormal);
-  }
+  tma_ld<C>(m, bar, dst, k0, row0 + rank * (rows / C), batch, kEvictNormal);
 }
 template <int C>
 __device__ __forceinline__ void load_mnmajor_shared(const CUtensorMap* m, uint64_t* bar, uint8_t* dst,
                                                     int mn0, int k0, int batch, int blocks, int rank) {
-  if (C == 1) {
-    load_mnmajor(m, bar, dst, mn0, k0, batch, blocks);
-  } else {
-    const int part = blocks / C;
-    for (int i = rank * part; i < (rank + 1) * part; ++i)
-      tma_load_3d_mc(m, bar, dst + i * kMnBlock, mn0 + i * 64, k0, batch, (uint16_t)((1u << C) - 1u),
-                     kEvictNormal);
-  }
+  const int part = blocks / C;
+  for (int i = 0; i < part; ++i)
+    tma_ld<C>(m, bar, dst + i * kMnBlock, mn0 + (rank * part + i) * 64, k0, batch, kEvictNormal);
 }
 
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a SWIZZLE_128B staging box

@@ -94,8 +94,8 @@ struct PassD : PolicyBase {
                               uint8_t* a2, uint8_t* bsm, uint64_t* bar, int rank) {
     int b, mt, nt;
     decode(p, tile, b, mt, nt);
-    load_kmajor(&m.a, bar, a, ks * kBK, mt * kBM, 0);        // q      [N, 768]
-    load_kmajor(&m.a2, bar, a2, ks * kBK, mt * kBM, b);      // pooled [B, N, 768]
+    load_kmajor<C>(&m.a, bar, a, ks * kBK, mt * kBM, 0);     // q      [N, 768]
+    load_kmajor<C>(&m.a2, bar, a2, ks * kBK, mt * kBM, b);   // pooled [B, N, 768]
     load_kmajor_shared<C>(&m.b, bar, bsm, ks * kBK, nt * kBN, b, kBN, rank);   // k [B, Lp, 768]
   }
   struct Row {
@@ -235,8 +235,8 @@ struct PassD2 : PolicyBase {
                               uint8_t* bsm, uint64_t* bar, int rank) {
     int b, mt, nt;
     decode(p, tile, b, mt, nt);
-    load_kmajor(&m.a, bar, a, ks * kBK, mt * kBM, b);                            // pooled [B, N, 768]
-    load_kmajor_shared<C>(&m.b, bar, bsm, ks * kBK, nt * kBN, b, kBN, rank);     // k [B, Lp, 768]
+    load_kmajor<C>(&m.a, bar, a, ks * kBK, mt * kBM, b);                         // pooled [B, N, 768]
+    load_kmajor_shared<C>(&m.b, bar, bsm, ks * kBK, nt * kBN, b, tile_n(p, tile), rank);   // k [B, Lp, 768]
   }
   // lane 0: fetch the P~ box of chunk `c` (64 tokens) of `tile` for this warp's 32 rows
   __device__ static __forceinline__ void fetch(const Params& p, const Maps& maps, int tile, int c, int warp,
@@ -393,7 +393,7 @@ struct PassQ : PolicyBase {
     const int mt = tile % p.m_tiles, ft = tile / p.m_tiles;
     const int per = p.Lp / kBK;
     const int b = ks / per, lc = ks - b * per;
-    load_kmajor(&m.a, bar, a, lc * kBK, mt * kBM, b);                                  // W1 [B, N, Lp]
+    load_kmajor<C>(&m.a, bar, a, lc * kBK, mt * kBM, b);                               // W1 [B, N, Lp]
     load_mnmajor_shared<C>(&m.b, bar, bsm, ft * kBN, lc * kBK, b, kBN / 64, rank);     // k  [B, Lp, 768]
   }
   __device__ static void epilogue(const Params& p, const Maps&, int tile, int, uint32_t tmem, int warp,

@@ -38,7 +38,7 @@ struct S2Params {
 // kScores: also emit the fp32 similarity map (maps.b2 = [B, N, L] fp32 store map)
 template <bool kScores, int C>
 struct PassS2 : PolicyBase {
-  static constexpr int kCluster = C;   // the pair sweeps prompt tiles (2i, 2i+1) over the same tokens
+  static constexpr int kCluster = C;   // CTA pair: prompt tiles (2i, 2i+1) over the same tokens, one 256-row MMA
   using Params = S2Params;
   struct State { float m, l, scale; };
   static constexpr int kBN = 256, kAccs = 1;
@@ -64,9 +64,9 @@ struct PassS2 : PolicyBase {
                               uint8_t* bsm, uint64_t* bar, int rank) {
     int b, mt, nt;
     decode(p, tile, b, mt, nt);
-    load_kmajor(&m.a, bar, a, ks * kBK, mt * kBM, 0);        // q [N, 768]
-    // k [B, Lp, 768] (rows >= Lp: zero fill), shared by the pair
-    load_kmajor_shared<C>(&m.b, bar, bsm, ks * kBK, nt * kBN, b, kBN, rank);
+    load_kmajor<C>(&m.a, bar, a, ks * kBK, mt * kBM, 0);     // q [N, 768]
+    // k [B, Lp, 768] (rows >= Lp: zero fill): each CTA of a pair loads half of the token tile
+    load_kmajor_shared<C>(&m.b, bar, bsm, ks * kBK, nt * kBN, b, tile_n(p, tile), rank);
   }
 
   // one 64-column chunk of this thread's row: lazy maximum, exp, stage, TMA store.  kMasked: the
@@ -250,7 +250,7 @@ struct PassPK : PolicyBase {
                               uint8_t* bsm, uint64_t* bar, int rank) {
     int b, mt, ft;
     decode(p, tile, b, mt, ft);
-    load_kmajor(&m.a, bar, a, ks * kBK, mt * kBM, b);                                 // P [B, N, Lp]
+    load_kmajor<C>(&m.a, bar, a, ks * kBK, mt * kBM, b);                              // P [B, N, Lp]
     load_mnmajor_shared<C>(&m.b, bar, bsm, ft * kBN, ks * kBK, b, kBN / 64, rank);    // k [B, Lp, 768]
   }
   __device__ static __forceinline__ void chunk(const Params& p, const Maps& maps, Cols64& v,
