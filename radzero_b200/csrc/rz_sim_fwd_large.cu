@@ -64,7 +64,7 @@ struct PassS2 : PolicyBase {
                               uint8_t* bsm, uint64_t* bar, int rank) {
     int b, mt, nt;
     decode(p, tile, b, mt, nt);
-    load_kmajor<C>(&m.a, bar, a, ks * kBK, mt * kBM, 0);     // q [N, 768]
+    load_kmajor<C>(&m.a, bar, a, ks * kBK, mt * kBM, 0, kEvictLast);     // q [N, 768], re-read per token tile
     // k [B, Lp, 768] (rows >= Lp: zero fill): each CTA of a pair loads half of the token tile
     load_kmajor_shared<C>(&m.b, bar, bsm, ks * kBK, nt * kBN, b, tile_n(p, tile), rank);
   }
