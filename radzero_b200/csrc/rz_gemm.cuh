@@ -275,14 +275,14 @@ __device__ __forceinline__ void load_mnmajor(const CUtensorMap* m, uint64_t* bar
 template <int C>
 __device__ __forceinline__ void load_kmajor_shared(const CUtensorMap* m, uint64_t* bar, uint8_t* dst,
                                                    int k0, int row0, int batch, int rows, int rank) {
-  tma_ld<C>(m, bar, dst, k0, row0 + rank * (rows / C), batch, kEvictLast);   // small, re-used by many CTAs
+  tma_ld<C>(m, bar, dst, k0, row0 + rank * (rows / C), batch, kEvictNormal);
 }
 template <int C>
 __device__ __forceinline__ void load_mnmajor_shared(const CUtensorMap* m, uint64_t* bar, uint8_t* dst,
                                                     int mn0, int k0, int batch, int blocks, int rank) {
   const int part = blocks / C;
   for (int i = 0; i < part; ++i)
-    tma_ld<C>(m, bar, dst + i * kMnBlock, mn0 + (rank * part + i) * 64, k0, batch, kEvictLast);
+    tma_ld<C>(m, bar, dst + i * kMnBlock, mn0 + (rank * part + i) * 64, k0, batch, kEvictNormal);
 }
 
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a SWIZZLE_128B staging box

@@ -235,7 +235,7 @@ struct PassD2 : PolicyBase {
                               uint8_t* bsm, uint64_t* bar, int rank) {
     int b, mt, nt;
     decode(p, tile, b, mt, nt);
-    load_kmajor<C>(&m.a, bar, a, ks * kBK, mt * kBM, b, kEvictLast);             // pooled [B, N, 768], re-read per token tile
+    load_kmajor<C>(&m.a, bar, a, ks * kBK, mt * kBM, b);                         // pooled [B, N, 768]
     load_kmajor_shared<C>(&m.b, bar, bsm, ks * kBK, nt * kBN, b, tile_n(p, tile), rank);   // k [B, Lp, 768]
   }
   // lane 0: fetch the P~ box of chunk `c` (64 tokens) of `tile` for this warp's 32 rows
@@ -446,11 +446,11 @@ struct PassK : PolicyBase {
     decode(p, tile, b, lt, ft);
     if (ks < p.n_chunks) {
       load_mnmajor(&m.a, bar, a, lt * kBM, ks * kBK, b, kBM / 64);        // W1 [B, N, Lp] (M = l)
-      load_mnmajor(&m.b, bar, bsm, ft * kBN, ks * kBK, 0, kBN / 64, kEvictLast);      // q  [N, 768]
+      load_mnmajor(&m.b, bar, bsm, ft * kBN, ks * kBK, 0, kBN / 64);      // q  [N, 768]
     } else {
       const int nc = ks - p.n_chunks;
       load_mnmajor(&m.a2, bar, a, lt * kBM, nc * kBK, b, kBM / 64);       // W2
-      load_mnmajor(&m.b2, bar, bsm, ft * kBN, nc * kBK, b, kBN / 64, kEvictLast);     // pooled [B, N, 768]
+      load_mnmajor(&m.b2, bar, bsm, ft * kBN, nc * kBK, b, kBN / 64);     // pooled [B, N, 768]
     }
   }
   __device__ static void epilogue(const Params& p, const Maps&, int tile, int, uint32_t tmem, int warp,
@@ -526,7 +526,9 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
   float* coef_r = coef_a + pairs;
   float* dtau_part = coef_r + pairs;
   const int m_tiles = (N + 127) / 128, n_tiles = Lp / 128;
-  const int C = (m_tiles % 2 == 0) ? 2 : 1;     // cluster pairs need an even number of prompt tiles
+  // CTA pairs need an even number of prompt tiles, and pay off only while the streamed P~ / W1
+  // operands are small enough for their re-reads to hit L2 (see rz_sim_fwd_large.cu)
+  const int C = (m_tiles % 2 == 0 && pairs * Lp * sizeof(__half) <= ((size_t)2 << 30)) ? 2 : 1;
   const int d_tiles = B * m_tiles * n_tiles;
   float* scale = dtau_part + 4 * (size_t)d_tiles;          // [2]
   unsigned int* amax = reinterpret_cast<unsigned int*>(scale + 2);

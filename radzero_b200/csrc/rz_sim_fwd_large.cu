@@ -64,7 +64,7 @@ struct PassS2 : PolicyBase {
                               uint8_t* bsm, uint64_t* bar, int rank) {
     int b, mt, nt;
     decode(p, tile, b, mt, nt);
-    load_kmajor<C>(&m.a, bar, a, ks * kBK, mt * kBM, 0, kEvictLast);     // q [N, 768], re-read per token tile
+    load_kmajor<C>(&m.a, bar, a, ks * kBK, mt * kBM, 0);     // q [N, 768]
     // k [B, Lp, 768] (rows >= Lp: zero fill): each CTA of a pair loads half of the token tile
     load_kmajor_shared<C>(&m.b, bar, bsm, ks * kBK, nt * kBN, b, tile_n(p, tile), rank);
   }
@@ -439,7 +439,10 @@ extern "C" int rz_sim_fwd_large(const void* k_f16, int n_images, int tokens, int
     PKParams kp;
     kp.B = B; kp.N = N; kp.Lp = Lp; kp.m_tiles = m_tiles; kp.q = static_cast<const __half*>(q_f16);
     kp.lsum = lsum; kp.pooled = static_cast<__half*>(pooled_f16); kp.part = part_o;
-    int rc = C == 2 ? launch<PassPK<2>>(mk, kp, s) : launch<PassPK<1>>(mk, kp, s);
+    // CTA pairs pay off while the re-read P~ stream still hits L2; on multi-GB streams (the C4 step)
+    // the pair kernels were measured to re-read more from HBM (46 vs 27 GB) and to be slower
+    const bool pair_pk = C == 2 && pairs * Lp * sizeof(__half) <= ((size_t)2 << 30);
+    int rc = pair_pk ? launch<PassPK<2>>(mk, kp, s) : launch<PassPK<1>>(mk, kp, s);
     if (rc != RZ_OK) return rc;
     FinParams fp;
     fp.part = part_o; fp.B = B; fp.N = N; fp.q_inv_norm = q_inv_norm;
