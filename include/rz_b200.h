@@ -264,6 +264,37 @@ int rz_mpnce_finish(const float* z, long long ldz, int n_total, int b_local, int
                     const float* colpos, float* scratch2, float* dz, float* loss_terms,
                     void* stream);
 
+/* ---- A0-A2: the AlignTransformer in front of the path ------
+ * The vision tokens the VL-CABS path consumes are produced by AlignTransformer.forward
+ * (exp/cxr_pt/model/align_transformers.py:37-45): a transformers `Dinov2Encoder` of two layers
+ * (radzero.yaml:29-33), each   h = x + ls1 * attn(norm1(x));  y = h + ls2 * fc2(gelu(fc1(norm2(h)))).
+ * These three entry points are the kernels of that forward (inference); the layer sequencing is
+ * host code (radzero_b200/align.py).  All operands are fp16 with fp32 accumulation; the residual
+ * stream stays fp32.
+ *
+ * rz_ln_rows   nn.LayerNorm with the caller's eps (Dinov2Layer.norm1 / norm2, eps 1e-6):
+ *              x [rows, 768] of `dtype` -> out_f16 [rows, 768].
+ * rz_linear    out = epilogue(a . w^T + bias): a fp16 [m, k], w fp16 [n, k] (nn.Linear.weight
+ *              layout), bias fp32 [n] or NULL; k % 64 == 0, n % 256 == 0.
+ *                RZ_LIN_BIAS      out fp16 [m, n] = acc + bias            (query/key/value fused)
+ *                RZ_LIN_GELU      out fp16 [m, n] = gelu_erf(acc + bias)  (mlp.fc1 + activation)
+ *                RZ_LIN_RESIDUAL  out fp32 [m, n] = residual + scale * (acc + bias)
+ *                                 (attention.output.dense / mlp.fc2 + Dinov2LayerScale + the
+ *                                 residual add; scale fp32 [n] or NULL; out may alias residual)
+ * rz_attention softmax(q k^T) v per (image, head), head dim 64, no mask (Dinov2SelfAttention):
+ *              qkv fp16 [n_images, tokens, 3 * heads * 64] = [q | k | v] column blocks with the
+ *              1/sqrt(64) scale already folded into q; out fp16 [n_images, tokens, heads * 64].
+ */
+#define RZ_LIN_BIAS 0
+#define RZ_LIN_GELU 1
+#define RZ_LIN_RESIDUAL 2
+int rz_ln_rows(const void* x, int dtype, const float* gamma, const float* beta, float eps,
+               long long rows, void* out_f16, void* stream);
+int rz_linear(const void* a_f16, long long m, int k, const void* w_f16, int n, const float* bias,
+              int epilogue, const float* scale, const float* residual, void* out, void* stream);
+int rz_attention(const void* qkv_f16, int n_images, int tokens, int heads, void* out_f16,
+                 void* stream);
+
 /* ---- diagnostics: one tcgen05.mma probe -------------------------------------------------
  * Copies caller-built shared-memory images of A and B into smem, issues `k_steps`
  * tcgen05.mma (kind::f16, fp32 accumulate) with the given descriptors and dumps all 128

@@ -17,6 +17,7 @@ HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "rz_b200.h")
 RZ_OK = 0
 RZ_F32, RZ_BF16, RZ_F16 = 0, 1, 2
 RZ_UP_RAW, RZ_UP_SIGMOID, RZ_UP_MASK, RZ_UP_ARGMAX = 0, 1, 2, 3
+RZ_LIN_BIAS, RZ_LIN_GELU, RZ_LIN_RESIDUAL = 0, 1, 2
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 _ull, _u = C.c_ulonglong, C.c_uint
@@ -47,6 +48,9 @@ SIGNATURES: Dict[str, tuple] = {
     "rz_mpnce_partials": (_i, [_vp, _ll, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rz_mpnce_finish": (_i, [_vp, _ll, _i, _i, _i, _vp, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp,
                              _vp, _vp, _vp, _vp]),
+    "rz_ln_rows": (_i, [_vp, _i, _vp, _vp, _f, _ll, _vp, _vp]),
+    "rz_linear": (_i, [_vp, _ll, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "rz_attention": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "rz_umma_probe": (_i, [_vp, _i, _vp, _i, _ull, _ull, _i, _i, _i, _u, _u, _i, _vp, _vp]),
 }
 

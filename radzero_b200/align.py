@@ -1,0 +1,115 @@
+"""Mirror of the reference's ``AlignTransformer`` (exp/cxr_pt/model/align_transformers.py:23-45).
+
+The reference wraps a transformers ``Dinov2Encoder`` of ``num_hidden_layers`` layers (2 in
+radzero.yaml:29-33) and an optional final ``nn.LayerNorm`` (``use_layer_norm``, False in the released
+configuration); ``forward(vision_tokens) -> vision_tokens``.  It is the only trainable vision
+compute and the producer of the VL-CABS path's input.
+
+Here the module keeps the SAME sub-module names (``transformer_layers`` = the HF encoder object,
+``layer_norm``), so a reference state dict loads unchanged, but its forward never calls them: the
+weights are packed once to fp16 GEMM operands and every layer runs on the hand-written sm_100a
+kernels behind the C ABI (``rz_ln_rows``, ``rz_linear``, ``rz_attention``):
+
+    h16 = LN1(x)                       rz_ln_rows          (eps 1e-6)
+    qkv = h16 [Wq/8 | Wk | Wv]^T + b   rz_linear  "bias"   (one GEMM, 1/sqrt(64) folded into Wq, bq)
+    a16 = softmax(q k^T) v             rz_attention        (tcgen05, online softmax)
+    x   = x + ls1 * (a16 Wo^T + bo)    rz_linear  "residual" (in place on the fp32 residual stream)
+    h16 = LN2(x)                       rz_ln_rows
+    g16 = gelu(h16 W1^T + b1)          rz_linear  "gelu"
+    x   = x + ls2 * (g16 W2^T + b2)    rz_linear  "residual"
+
+Inference only (the packed weights are detached); training through the AlignTransformer still
+uses the stock HF module.  No CPU fallback: CPU tensors raise ``RzError``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import RzError
+
+HEAD_DIM = 64
+
+
+def pack_layer(layer: nn.Module, device=None) -> Dict[str, torch.Tensor]:
+    """fp16 GEMM operands + fp32 vectors of one ``Dinov2Layer`` (transformers modeling_dinov2)."""
+    att = layer.attention.attention
+    if att.attention_head_size != HEAD_DIM:
+        raise RzError(f"the attention kernel is built for head dim {HEAD_DIM}")
+    if not hasattr(layer.mlp, "fc1"):
+        raise RzError("SwiGLU feed-forward layers are not on the RadZero path (use_swiglu_ffn=False)")
+    s = float(att.scaling)            # 1/8: a power of two, so folding it into Wq / bq is exact
+    dev = device or att.query.weight.device
+    f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+    f16 = lambda t: t.detach().to(device=dev, dtype=torch.float32).to(torch.float16).contiguous()
+
+    def bias_of(lin):
+        return lin.bias if lin.bias is not None else torch.zeros(lin.out_features, device=lin.weight.device)
+
+    return {
+        "heads": att.num_attention_heads,
+        "eps1": layer.norm1.eps, "g1": f32(layer.norm1.weight), "b1": f32(layer.norm1.bias),
+        "eps2": layer.norm2.eps, "g2": f32(layer.norm2.weight), "b2": f32(layer.norm2.bias),
+        "wqkv": f16(torch.cat([att.query.weight * s, att.key.weight, att.value.weight], dim=0)),
+        "bqkv": f32(torch.cat([bias_of(att.query) * s, bias_of(att.key), bias_of(att.value)], dim=0)),
+        "wo": f16(layer.attention.output.dense.weight), "bo": f32(layer.attention.output.dense.bias),
+        "ls1": f32(layer.layer_scale1.lambda1),
+        "w1": f16(layer.mlp.fc1.weight), "bf1": f32(layer.mlp.fc1.bias),
+        "w2": f16(layer.mlp.fc2.weight), "bf2": f32(layer.mlp.fc2.bias),
+        "ls2": f32(layer.layer_scale2.lambda1),
+    }
+
+
+def layer_forward(x: torch.Tensor, w: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """One Dinov2Layer on the fp32 residual stream ``x`` (B, L, 768), updated IN PLACE."""
+    B, L, D = x.shape
+    x2 = x.view(B * L, D)
+    h = ops.ln_rows(x2, w["g1"], w["b1"], w["eps1"])
+    qkv = ops.linear(h, w["wqkv"], w["bqkv"], "bias")
+    a = ops.attention(qkv.view(B, L, 3 * D), w["heads"])
+    ops.linear(a.view(B * L, D), w["wo"], w["bo"], "residual", scale=w["ls1"], residual=x2, out=x2)
+    h = ops.ln_rows(x2, w["g2"], w["b2"], w["eps2"])
+    g = ops.linear(h, w["w1"], w["bf1"], "gelu")
+    ops.linear(g, w["w2"], w["bf2"], "residual", scale=w["ls2"], residual=x2, out=x2)
+    return x
+
+
+class AlignTransformer(nn.Module):
+    """Drop-in for align_transformers.py:23-45 (inference forward on the B200 kernels)."""
+
+    def __init__(self, transformer_layers: Optional[nn.Module] = None, layer_norm: Optional[nn.LayerNorm] = None):
+        super().__init__()
+        self.transformer_layers = transformer_layers     # transformers Dinov2Encoder (weights only)
+        self.layer_norm = layer_norm
+        self._packed: Optional[List[Dict[str, torch.Tensor]]] = None
+
+    def refresh(self) -> None:
+        """Drop the packed fp16 operands (call after loading / changing the weights)."""
+        self._packed = None
+
+    def _weights(self, device) -> List[Dict[str, torch.Tensor]]:
+        if self._packed is None or (self._packed and self._packed[0]["wo"].device != device):
+            layers = [] if self.transformer_layers is None else list(self.transformer_layers.layer)
+            self._packed = [pack_layer(l, device) for l in layers]
+        return self._packed
+
+    @torch.no_grad()
+    def forward(self, vision_tokens: torch.Tensor) -> torch.Tensor:
+        if not vision_tokens.is_cuda:
+            raise RzError("radzero_b200 ops run on CUDA tensors only (there is no CPU fallback)")
+        if vision_tokens.dim() != 3 or vision_tokens.shape[-1] != ops.HIDDEN:
+            raise RzError("vision tokens must be (B, L, 768)")
+        x = vision_tokens.detach().to(torch.float32).contiguous().clone()     # the fp32 residual stream
+        for w in self._weights(x.device):
+            layer_forward(x, w)
+        if self.layer_norm is not None:
+            # use_layer_norm=True (not the released configuration): one more row LayerNorm, fp32 out
+            g, b = self.layer_norm.weight.detach(), self.layer_norm.bias.detach()
+            if abs(self.layer_norm.eps - 1e-5) > 1e-12:
+                raise RzError("AlignTransformer.layer_norm: only the nn.LayerNorm default eps is supported")
+            _, x32, _ = ops.prep_rows(x, g, b, want_f16=False, want_f32=True, l2=False)
+            x = x32.view(x.shape)
+        return x

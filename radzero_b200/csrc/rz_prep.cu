@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
 prep_rows_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, long long rows, int rows_per_group,
                  int rows_per_group_padded, __half* __restrict__ out_h, float* __restrict__ out_f,
-                 float* __restrict__ stats, int l2, long long padded_rows_total) {
+                 float* __restrict__ stats, int l2, long long padded_rows_total, float eps_ln) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
@@ -33,7 +33,7 @@ prep_rows_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
     if (row >= rows) continue;
     float v[24];
     rz::RowLoad<T>::load(x + row * RZ_HIDDEN, lane, v);
-    const rz::RowStats st = rz::ln_l2_row(v, gamma, beta, lane, RZ_LN_EPS, RZ_L2_EPS, l2 != 0);
+    const rz::RowStats st = rz::ln_l2_row(v, gamma, beta, lane, eps_ln, RZ_L2_EPS, l2 != 0);
     if (out_h != nullptr) {
       uint2* o = reinterpret_cast<uint2*>(out_h + slot * RZ_HIDDEN) + lane;
 #pragma unroll
@@ -57,9 +57,10 @@ prep_rows_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
 
 }  // namespace
 
-extern "C" int rz_prep_rows(const void* x, int dtype, const float* gamma, const float* beta,
-                            long long rows, int rows_per_group, int rows_per_group_padded,
-                            void* out_f16, float* out_f32, float* stats, int l2, void* stream) {
+static int prep_rows_impl(const void* x, int dtype, const float* gamma, const float* beta,
+                          long long rows, int rows_per_group, int rows_per_group_padded,
+                          void* out_f16, float* out_f32, float* stats, int l2, float eps_ln,
+                          void* stream) {
   if (x == nullptr || rows < 0 || rows_per_group <= 0 || rows_per_group_padded < rows_per_group)
     return RZ_ERR_INVALID;
   if ((gamma == nullptr) != (beta == nullptr)) return RZ_ERR_INVALID;
@@ -82,17 +83,17 @@ extern "C" int rz_prep_rows(const void* x, int dtype, const float* gamma, const 
     case RZ_F32:
       prep_rows_kernel<float><<<grid, block, 0, s>>>(static_cast<const float*>(x), gamma, beta, rows,
                                                      rows_per_group, rows_per_group_padded, oh,
-                                                     out_f32, stats, l2, slots);
+                                                     out_f32, stats, l2, slots, eps_ln);
       break;
     case RZ_BF16:
       prep_rows_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(
           static_cast<const __nv_bfloat16*>(x), gamma, beta, rows, rows_per_group,
-          rows_per_group_padded, oh, out_f32, stats, l2, slots);
+          rows_per_group_padded, oh, out_f32, stats, l2, slots, eps_ln);
       break;
     case RZ_F16:
       prep_rows_kernel<__half><<<grid, block, 0, s>>>(static_cast<const __half*>(x), gamma, beta,
                                                       rows, rows_per_group, rows_per_group_padded,
-                                                      oh, out_f32, stats, l2, slots);
+                                                      oh, out_f32, stats, l2, slots, eps_ln);
       break;
     default:
       return RZ_ERR_INVALID;
@@ -100,4 +101,22 @@ extern "C" int rz_prep_rows(const void* x, int dtype, const float* gamma, const 
   RZ_LAUNCH_OK();
   rz_count_launch();
   return RZ_OK;
+}
+
+extern "C" int rz_prep_rows(const void* x, int dtype, const float* gamma, const float* beta,
+                            long long rows, int rows_per_group, int rows_per_group_padded,
+                            void* out_f16, float* out_f32, float* stats, int l2, void* stream) {
+  return prep_rows_impl(x, dtype, gamma, beta, rows, rows_per_group, rows_per_group_padded, out_f16,
+                        out_f32, stats, l2, RZ_LN_EPS, stream);
+}
+
+// A0: plain LayerNorm with the caller's eps -> fp16 GEMM operand rows (Dinov2Layer.norm1 / norm2,
+// layer_norm_eps = 1e-6)
+extern "C" int rz_ln_rows(const void* x, int dtype, const float* gamma, const float* beta, float eps,
+                          long long rows, void* out_f16, void* stream) {
+  if (gamma == nullptr || beta == nullptr || out_f16 == nullptr || !(eps > 0.f)) return RZ_ERR_INVALID;
+  if (rows == 0) return RZ_OK;
+  const int rpg = rows < (1 << 30) ? (int)rows : 0;
+  if (rpg == 0) return RZ_ERR_UNSUPPORTED;
+  return prep_rows_impl(x, dtype, gamma, beta, rows, rpg, rpg, out_f16, nullptr, nullptr, 0, eps, stream);
 }

@@ -428,3 +428,66 @@ def umma_probe(a_image: torch.Tensor, b_image: torch.Tensor, a_desc: int, b_desc
                                    ncols, _p(out), _stream())
     _lib.check(rc, "rz_umma_probe")
     return out
+
+
+# ----------------------------------------------------------------------------- A0 - A2
+def ln_rows(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> torch.Tensor:
+    """nn.LayerNorm(768, eps) of the rows of ``x`` (..., 768) -> fp16 rows (a GEMM operand)."""
+    _need_cuda(x, gamma, beta)
+    if x.shape[-1] != HIDDEN or x.dtype not in _DTYPES:
+        raise RzError(f"ln_rows needs (..., {HIDDEN}) fp32/bf16/fp16 rows, got {tuple(x.shape)} {x.dtype}")
+    x2 = _contig(x).view(-1, HIDDEN)
+    out = torch.empty(x2.shape, dtype=torch.float16, device=x.device)
+    rc = _lib.load().rz_ln_rows(_p(x2), _DTYPES[x.dtype], _p(_contig(gamma.float())), _p(_contig(beta.float())),
+                                float(eps), x2.shape[0], _p(out), _stream())
+    _lib.check(rc, "rz_ln_rows")
+    return out.view(x.shape)
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogue: str = "bias", *,
+           scale: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``epilogue(a @ w.T + bias)`` on the tcgen05 GEMM skeleton.
+
+    a (M, K) fp16, w (N, K) fp16 (nn.Linear.weight layout), bias fp32 (N,).  ``epilogue``:
+    "bias" / "gelu" -> fp16 (M, N); "residual" -> fp32 ``residual + scale * (a @ w.T + bias)``
+    (``out`` may be ``residual`` itself: in-place update of the residual stream).
+    """
+    _need_cuda(a, w, bias, scale, residual, out)
+    if a.dtype != torch.float16 or w.dtype != torch.float16 or a.dim() != 2 or w.dim() != 2:
+        raise RzError("linear operands must be 2-d fp16")
+    if not (a.is_contiguous() and w.is_contiguous()) or a.shape[1] != w.shape[1]:
+        raise RzError("linear operands must be contiguous (M, K) and (N, K)")
+    m, k = a.shape
+    n = w.shape[0]
+    ep = {"bias": _lib.RZ_LIN_BIAS, "gelu": _lib.RZ_LIN_GELU, "residual": _lib.RZ_LIN_RESIDUAL}[epilogue]
+    for v in (bias, scale):
+        if v is not None and (v.dtype != torch.float32 or v.numel() != n or not v.is_contiguous()):
+            raise RzError("bias / scale must be contiguous fp32 (N,)")
+    if ep == _lib.RZ_LIN_RESIDUAL:
+        if residual is None or residual.dtype != torch.float32 or tuple(residual.shape) != (m, n) \
+                or not residual.is_contiguous():
+            raise RzError("residual must be contiguous fp32 (M, N)")
+        odt = torch.float32
+    else:
+        odt = torch.float16
+    if out is None:
+        out = torch.empty((m, n), dtype=odt, device=a.device)
+    elif out.dtype != odt or tuple(out.shape) != (m, n) or not out.is_contiguous():
+        raise RzError(f"out must be contiguous {odt} ({m}, {n})")
+    rc = _lib.load().rz_linear(_p(a), m, k, _p(w), n, _p(bias), ep, _p(scale), _p(residual), _p(out), _stream())
+    _lib.check(rc, "rz_linear")
+    return out
+
+
+def attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
+    """softmax(q k^T) v per (image, head); qkv (B, L, 3 * heads * 64) fp16 = [q | k | v] with the
+    1/sqrt(64) scale folded into q.  Returns (B, L, heads * 64) fp16."""
+    _need_cuda(qkv)
+    if qkv.dtype != torch.float16 or qkv.dim() != 3 or qkv.shape[-1] != 3 * heads * 64 or not qkv.is_contiguous():
+        raise RzError("qkv must be contiguous fp16 (B, L, 3 * heads * 64)")
+    B, L, _ = qkv.shape
+    out = torch.empty((B, L, heads * 64), dtype=torch.float16, device=qkv.device)
+    rc = _lib.load().rz_attention(_p(qkv), B, L, heads, _p(out), _stream())
+    _lib.check(rc, "rz_attention")
+    return out

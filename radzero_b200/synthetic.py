@@ -78,3 +78,49 @@ def checksum(t: torch.Tensor) -> Tuple[float, float]:
     """(sum, abs-sum) in float64 -- used by the golden fixtures to detect RNG drift."""
     d = t.detach().double()
     return float(d.sum().item()), float(d.abs().sum().item())
+
+
+def align_layer_weights(seed: int = 42, layers: int = 2, hidden: int = HIDDEN, mlp_ratio: int = 4):
+    """Seeded weights of the AlignTransformer's Dinov2 layers, keyed like ``Dinov2Layer.state_dict()``.
+
+    Linear weights N(0, 0.02) (the HF ``_init_weights`` the reference trains from,
+    exp/cxr_pt/model/common_layers.py:13-28), but query / key at std 0.08 so that the attention is
+    not a uniform average, small non-zero biases, LayerNorm gamma ~ U(0.5, 1.5), beta ~ U(-0.2, 0.2)
+    and LayerScale lambda ~ U(0.5, 1.5) (not the 1 / 0 inits, to exercise every term).
+    """
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(seed + 7919)
+    n = lambda *s, std=0.02: std * torch.randn(*s, generator=gen)
+    u = lambda lo, hi, *s: lo + (hi - lo) * torch.rand(*s, generator=gen)
+    out = []
+    for _ in range(layers):
+        w = {}
+        for nm in ("norm1", "norm2"):
+            w[f"{nm}.weight"] = u(0.5, 1.5, hidden)
+            w[f"{nm}.bias"] = u(-0.2, 0.2, hidden)
+        for nm, std in (("query", 0.08), ("key", 0.08), ("value", 0.02)):
+            w[f"attention.attention.{nm}.weight"] = n(hidden, hidden, std=std)
+            w[f"attention.attention.{nm}.bias"] = n(hidden, std=0.05)
+        w["attention.output.dense.weight"] = n(hidden, hidden)
+        w["attention.output.dense.bias"] = n(hidden, std=0.05)
+        w["layer_scale1.lambda1"] = u(0.5, 1.5, hidden)
+        w["mlp.fc1.weight"] = n(mlp_ratio * hidden, hidden)
+        w["mlp.fc1.bias"] = n(mlp_ratio * hidden, std=0.05)
+        w["mlp.fc2.weight"] = n(hidden, mlp_ratio * hidden)
+        w["mlp.fc2.bias"] = n(hidden, std=0.05)
+        w["layer_scale2.lambda1"] = u(0.5, 1.5, hidden)
+        out.append(w)
+    return out
+
+
+def build_align_encoder(seed: int = 42, layers: int = 2, device="cpu"):
+    """A transformers ``Dinov2Encoder`` (the reference's AlignTransformer body,
+    align_transformers.py:27-28) loaded with :func:`align_layer_weights`."""
+    from transformers import Dinov2Config
+    from transformers.models.dinov2.modeling_dinov2 import Dinov2Encoder
+    cfg = Dinov2Config(hidden_size=HIDDEN, num_hidden_layers=layers, num_attention_heads=12)
+    enc = Dinov2Encoder(cfg)
+    for layer, w in zip(enc.layer, align_layer_weights(seed, layers)):
+        missing = layer.load_state_dict(w, strict=True)
+        del missing
+    return enc.to(device).eval()

@@ -1,0 +1,180 @@
+"""Parity of the AlignTransformer kernels (rz_ln_rows, rz_linear, rz_attention) and of the
+assembled ``radzero_b200.align.AlignTransformer`` against the CPU oracle (oracle/align.py) and the
+golden vectors.  Tolerances: the kernels take fp16 operands with fp32 accumulation, so element
+errors are ~1e-3 relative; the end-to-end bar is BASELINE.json's (cosine similarities <= 2e-3)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import align as oalign
+from oracle import vlcabs as orc
+from radzero_b200 import ops, synthetic
+from radzero_b200.align import AlignTransformer, pack_layer
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "align_golden.npz")
+
+
+def _h(t):   # fp16-rounded copy in fp64: what the kernel's operand actually holds
+    return t.to(torch.float16).double()
+
+
+@pytest.mark.parametrize("rows", [1, 37, 2740])
+def test_ln_rows(rows):
+    torch.manual_seed(rows)
+    x = torch.randn(rows, 768, device=DEV) * 3 + 0.5
+    g, b = torch.rand(768, device=DEV) + 0.5, torch.rand(768, device=DEV) - 0.5
+    got = ops.ln_rows(x, g, b, 1e-6).float()
+    want = torch.nn.functional.layer_norm(x.double(), (768,), g.double(), b.double(), 1e-6).float()
+    assert (got - want).abs().max().item() <= 4e-3 * want.abs().max().item()
+    assert (got - want).abs().mean().item() <= 4e-4
+
+
+@pytest.mark.parametrize("m", [1, 128, 200, 257, 1370, 2 * 1370 + 5])
+@pytest.mark.parametrize("epi,k,n", [("bias", 768, 2304), ("gelu", 768, 3072), ("residual", 768, 768),
+                                     ("residual", 3072, 768), ("bias", 64, 256)])
+def test_linear(m, epi, k, n):
+    torch.manual_seed(m * 7 + k + n)
+    a = torch.randn(m, k, device=DEV).half()
+    w = (torch.randn(n, k, device=DEV) * 0.05).half()
+    bias = torch.randn(n, device=DEV) * 0.1
+    acc = a.double() @ w.double().T + bias.double()
+    if epi == "bias":
+        got = ops.linear(a, w, bias, "bias").double()
+        want = acc
+    elif epi == "gelu":
+        got = ops.linear(a, w, bias, "gelu").double()
+        want = oalign.gelu_erf(acc)
+    else:
+        res = torch.randn(m, n, device=DEV)
+        scale = torch.rand(n, device=DEV) + 0.5
+        want = res.double() + scale.double() * acc
+        keep = res.clone()
+        got = ops.linear(a, w, bias, "residual", scale=scale, residual=res).double()
+        assert torch.equal(res, keep)                      # not in place unless asked
+        inplace = ops.linear(a, w, bias, "residual", scale=scale, residual=res, out=res)
+        assert inplace.data_ptr() == res.data_ptr() and torch.equal(inplace.double(), got)
+    tol = 2e-3 if epi != "residual" else 1e-4              # fp16 output rounding vs fp32 output
+    err = (got - want).abs().max().item()
+    assert err <= tol * max(1.0, want.abs().max().item()), err
+
+
+def test_linear_no_bias_no_scale():
+    a = torch.randn(300, 768, device=DEV).half()
+    w = (torch.randn(768, 768, device=DEV) * 0.05).half()
+    res = torch.randn(300, 768, device=DEV)
+    got = ops.linear(a, w, None, "residual", residual=res).double()
+    want = res.double() + a.double() @ w.double().T
+    assert (got - want).abs().max().item() <= 1e-4 * want.abs().max().item()
+
+
+def _attn_ref(qkv, heads):
+    B, L, W = qkv.shape
+    d = W // 3
+    q, k, v = [t.view(B, L, heads, 64).transpose(1, 2).double() for t in qkv.split(d, dim=-1)]
+    p = torch.softmax(q @ k.transpose(2, 3), dim=-1)       # the scale is already folded into q
+    return (p @ v).transpose(1, 2).reshape(B, L, d)
+
+
+@pytest.mark.parametrize("B,L,heads", [(1, 1, 12), (2, 90, 12), (1, 128, 12), (1, 129, 3), (2, 1370, 12),
+                                       (3, 257, 1)])
+def test_attention(B, L, heads):
+    torch.manual_seed(L + heads)
+    qkv = torch.randn(B, L, 3 * heads * 64, device=DEV)
+    qkv[..., : heads * 64] *= 0.6                          # scores ~ N(0, (0.6*8)^2): a peaked softmax
+    qkv = qkv.half()
+    got = ops.attention(qkv, heads).double()
+    want = _attn_ref(qkv, heads)
+    assert (got - want).abs().max().item() <= 3e-3, (got - want).abs().max().item()
+
+
+def test_attention_growing_scores():
+    """Keys ordered so that the running maximum rises in every tile (the online-softmax rescale of
+    the register accumulator is exercised at every step), plus a query whose scores fall."""
+    B, L, heads = 1, 1000, 2
+    torch.manual_seed(3)
+    qkv = torch.randn(B, L, 3 * heads * 64, device=DEV) * 0.05
+    ramp = torch.linspace(0.0, 6.0, L, device=DEV)
+    qkv[0, :, 0] = 4.0                                     # q[:, head 0, dim 0]
+    qkv[0, : L // 2, 0] = -4.0                             # first half of the queries: falling scores
+    qkv[0, :, heads * 64 + 0] = ramp                       # k[:, head 0, dim 0] grows with the key index
+    qkv = qkv.half()
+    got = ops.attention(qkv, heads).double()
+    want = _attn_ref(qkv, heads)
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max().item() <= 2e-3
+
+
+def _gpu_weights(seed):
+    enc = synthetic.build_align_encoder(seed=seed, device=DEV)
+    return enc, synthetic.align_layer_weights(seed)
+
+
+@pytest.mark.parametrize("name", ["small", "ragged"])
+def test_align_transformer_golden(name):
+    g = np.load(GOLDEN)
+    B, L, seed = [int(v) for v in g[f"{name}.meta"]]
+    enc, _ = _gpu_weights(seed)
+    tok = synthetic.make_inputs(B, 1, tokens_per_image=L, seed=seed)[0].to(DEV)
+    keep = tok.clone()
+    got = AlignTransformer(enc)(tok)
+    assert torch.equal(tok, keep)                          # the caller's tokens are not modified
+    want = torch.from_numpy(g[f"{name}.out"]).to(DEV)
+    err = (got - want).abs()
+    assert err.max().item() <= 2e-2 and err.mean().item() <= 2e-3, (err.max().item(), err.mean().item())
+    cos = torch.nn.functional.cosine_similarity(got, want, dim=-1)
+    assert (1 - cos).max().item() <= 2e-5
+
+
+def test_align_then_similarity_full_size():
+    """AlignTransformer -> VL-CABS similarity at the real token count against the oracle chain:
+    the cosine similarities must stay within BASELINE.json's 2e-3."""
+    B, N, seed = 2, 14, 21
+    enc, w = _gpu_weights(seed)
+    tok, text, gamma, beta, log_tau = [t.to(DEV) for t in synthetic.make_inputs(B, N, seed=seed)]
+    x_got = AlignTransformer(enc)(tok)
+    x_ref = oalign.align_transformer(tok.double(), [{k: v.to(DEV) for k, v in l.items()} for l in w])
+    assert (x_got.double() - x_ref).abs().max().item() <= 3e-2
+    k_got = orc.l2_normalize_rows(orc.layer_norm_rows(x_got.double(), gamma.double(), beta.double()))
+    k_ref = orc.l2_normalize_rows(orc.layer_norm_rows(x_ref, gamma.double(), beta.double()))
+    q = orc.l2_normalize_rows(orc.layer_norm_rows(text.double(), gamma.double(), beta.double()))
+    cos_err = (k_got @ q.T - k_ref @ q.T).abs().max().item()
+    assert cos_err <= 2e-3, cos_err
+    # and through the fused kernel of the path itself
+    q16, _, _ = ops.prep_rows(text, gamma, beta)
+    out = ops.sim_fwd_tokens(x_got, gamma, beta, q16, 1.0, want_scores=True, drop_cls=False)
+    assert (out["scores"].double() - (k_ref @ q.T).transpose(1, 2)).abs().max().item() <= 2e-3
+
+
+def test_final_layer_norm_and_refresh():
+    enc, w = _gpu_weights(9)
+    ln = torch.nn.LayerNorm(768).to(DEV)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.2, 0.2)
+    tok = synthetic.make_inputs(1, 1, tokens_per_image=200, seed=9)[0].to(DEV)
+    mod = AlignTransformer(enc, ln)
+    got = mod(tok)
+    want = oalign.align_transformer(tok.double(), [{k: v.to(DEV) for k, v in l.items()} for l in w],
+                                    final_ln=(ln.weight.detach().double(), ln.bias.detach().double()))
+    assert (got.double() - want).abs().max().item() <= 2e-2
+    with torch.no_grad():
+        enc.layer[0].layer_scale1.lambda1.zero_()
+        enc.layer[0].layer_scale2.lambda1.zero_()
+    mod.refresh()
+    w[0]["layer_scale1.lambda1"].zero_()
+    w[0]["layer_scale2.lambda1"].zero_()
+    want2 = oalign.align_transformer(tok.double(), [{k: v.to(DEV) for k, v in l.items()} for l in w],
+                                     final_ln=(ln.weight.detach().double(), ln.bias.detach().double()))
+    assert (mod(tok).double() - want2).abs().max().item() <= 2e-2
+
+
+def test_cpu_tensors_raise():
+    from radzero_b200._lib import RzError
+    with pytest.raises(RzError):
+        AlignTransformer(None)(torch.zeros(1, 4, 768))
+    with pytest.raises(RzError):
+        ops.attention(torch.zeros(1, 4, 2304, dtype=torch.float16), 12)
