@@ -12,13 +12,15 @@
 //   warp 4  TMA producer: Q once, then K / V tiles into two-stage rings (separate barriers: S can
 //           start as soon as K has landed)
 //   warp 5  MMA issuer (one elected lane): S = Q K^T (M 128, N 128, K 64) into TMEM, and
-//           O_j = P_j V_j (M 128, N 64, K 128; V tile read as an MN-major B operand) into one of two
-//           TMEM buffers -- S of tile j+1 is issued before waiting for P of tile j
-//   warps 0-3  softmax, one query row per thread (TMEM lane = row, no shuffles): exact online
-//           softmax in the log2 domain; S is read from TMEM twice (maximum, then exponentials) to
-//           keep the register file small enough for two CTAs per SM; P goes to shared memory as the
-//           fp16 K-major A operand; the per-tile products O_j are accumulated in REGISTERS with the
-//           running rescale (so TMEM is never read-modify-written), one tile behind the MMAs.
+//           O += P_j V_j (M 128, N 64, K 128; V tile read as an MN-major B operand) accumulated in
+//           TMEM over all key tiles -- S of tile j+1 is issued before waiting for P of tile j
+//   warps 0-3  softmax, one query row per thread (TMEM lane = row, no shuffles).  The 128 scores of
+//           the row are read from TMEM ONCE into registers (S is released to the MMA warp right
+//           away), reduced with FMNMX3, exponentiated in the log2 domain with packed FFMA2 / FADD2
+//           and written to shared memory as the fp16 K-major A operand.  The running reference
+//           maximum is LAZY (FlashAttention-4 style): it only moves when the tile maximum exceeds it
+//           by more than 2^8, so P <= 256 stays comfortably inside fp16 and the accumulator in TMEM
+//           is rescaled (tcgen05.ld / st by the row's own thread) only on those rare tiles.
 // Keys >= L of the last tile are masked to probability 0; rows >= L are zero-filled by the TMA
 // loads and clipped by the TMA store.
 #include "rz_common.cuh"
@@ -33,7 +35,8 @@ constexpr int kHd = 64;                    // head dim
 constexpr int kTile = 128;                 // query rows per CTA = keys per tile
 constexpr int kTileBytes = kTile * 128;    // 128 rows x 64 halfs
 constexpr int kThreads = 192;
-constexpr int kTmemCols = 256;             // S [0,128)  O0 [128,192)  O1 [192,256)
+constexpr int kTmemCols = 256;             // S [0,128)  O [128,192)
+constexpr float kLazy = 8.0f;              // log2 units: the reference maximum moves when exceeded by 2^8
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct AttnParams {
@@ -44,7 +47,7 @@ struct Ctrl {
   uint64_t q_full;
   uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
   uint64_t s_full, s_empty, p_full;
-  uint64_t o_full[2], o_empty[2];
+  uint64_t o_full;
   uint32_t tmem_slot;
 };
 
@@ -60,6 +63,31 @@ __device__ __forceinline__ void sts_v4(uint32_t saddr, uint32_t a, uint32_t b, u
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// packed fp32 pairs (sm_100 FFMA2 / FADD2): d = a * b + c, d += a
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+  uint64_t A, B, C, D;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(B) : "f"(b));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(C) : "f"(c));
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(D) : "l"(A), "l"(B), "l"(C));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(D));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) {
+  uint64_t A, D;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(D) : "f"(d0), "f"(d1));
+  asm("add.rn.ftz.f32x2 %0, %0, %1;" : "+l"(D) : "l"(A));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(D));
+}
+__device__ __forceinline__ void tmem_ld_wait_x16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                 "+r"(r[15])
+               :
+               : "memory");
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
@@ -85,8 +113,8 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->k_full[i], 1); mbar_init(&ctl->k_empty[i], 1);
       mbar_init(&ctl->v_full[i], 1); mbar_init(&ctl->v_empty[i], 1);
-      mbar_init(&ctl->o_full[i], 1); mbar_init(&ctl->o_empty[i], 128);
     }
+    mbar_init(&ctl->o_full, 1);
     mbar_init(&ctl->s_full, 1);
     mbar_init(&ctl->s_empty, 128);
     mbar_init(&ctl->p_full, 128);
@@ -138,17 +166,16 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
       issue_s(0);
       for (int j = 0; j < T; ++j) {
         if (j + 1 < T) issue_s(j + 1);
-        const int st = j & 1, ob = j & 1;
+        const int st = j & 1;
         mbar_wait(&ctl->v_full[st], (uint32_t)((j >> 1) & 1));
-        mbar_wait(&ctl->o_empty[ob], (uint32_t)(((j >> 1) & 1) ^ 1));
-        mbar_wait(&ctl->p_full, (uint32_t)(j & 1));
+        mbar_wait(&ctl->p_full, (uint32_t)(j & 1));     // also orders any rescale of O before these MMAs
         tc_fence_after();
 #pragma unroll
         for (int k8 = 0; k8 < 8; ++k8)
-          mma_f16_ss(tmem_base + 128 + ob * kHd,
+          mma_f16_ss(tmem_base + 128,
                      make_smem_desc(pa + (k8 >> 2) * kTileBytes + (k8 & 3) * 32, 0, 1024),
-                     make_smem_desc(va + st * kTileBytes + k8 * 2048, 8192, 1024), idesc_o, k8 ? 1u : 0u);
-        mma_commit(&ctl->o_full[ob]);
+                     make_smem_desc(va + st * kTileBytes + k8 * 2048, 8192, 1024), idesc_o, (j | k8) ? 1u : 0u);
+        mma_commit(&ctl->o_full);
         mma_commit(&ctl->v_empty[st]);
       }
     }
@@ -158,77 +185,74 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
     const uint32_t t_s = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t t_o = t_s + 128;
     const uint32_t prow = smem_u32(p_s);
-    float acc[kHd];
-#pragma unroll
-    for (int i = 0; i < kHd; ++i) acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-
-    auto add_o = [&](int jo, float alpha) {
-      // acc = acc * alpha + O_jo  (O_jo is at the scale of the running maximum after tile jo)
-      const int ob = jo & 1;
-      mbar_wait(&ctl->o_full[ob], (uint32_t)((jo >> 1) & 1));
-      tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld_x32(t_o + ob * kHd, o0);
-      tmem_ld_x32(t_o + ob * kHd + 32, o1);
-      tmem_ld_wait_x32(o0);
-      tmem_ld_wait_x32(o1);
-      tc_fence_before();
-      mbar_arrive(&ctl->o_empty[ob]);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        acc[i] = fmaf(acc[i], alpha, __uint_as_float(o0[i]));
-        acc[32 + i] = fmaf(acc[32 + i], alpha, __uint_as_float(o1[i]));
-      }
-    };
+    float m_run = -INFINITY, l_run = 0.f;
 
     for (int j = 0; j < T; ++j) {
       const int valid = min(kTile, p.L - j * kTile);    // real keys in this tile
+      uint32_t v[4][32];
       mbar_wait(&ctl->s_full, (uint32_t)(j & 1));
       tc_fence_after();
-      // pass 1: row maximum of the tile
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_x32(t_s + c * 32, v);
-        tmem_ld_wait_x32(v);
-        if (c * 32 + 32 <= valid) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
+      for (int c = 0; c < 4; ++c) tmem_ld_x32(t_s + c * 32, v[c]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_wait_x32(v[c]);
+      tc_fence_before();
+      mbar_arrive(&ctl->s_empty);                      // S is in registers: the next S = Q K^T may start
+      if (valid < kTile) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
+            if (c * 32 + i >= valid) v[c][i] = 0xff800000u;   // -inf: probability 0
       }
-      const float m_new = fmaxf(m_run, mx * kLog2e);
-      const float alpha = exp2f(m_run - m_new);          // 0 for the first tile
-      // the product of the previous tile: its MMAs are done long before; this also frees the P buffer
-      if (j > 0) add_o(j - 1, alpha_prev);
-      // pass 2: exponentials -> P (fp16, K-major SWIZZLE_128B A operand: two boxes of 64 keys)
-      float rs0 = 0.f, rs1 = 0.f;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+          mx = fmaxf(mx, fmaxf(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])));
+      const float mxs = mx * kLog2e;
+      const bool need = mxs > m_run + kLazy;           // always true for the first tile
+      float alpha = 1.f;
+      if (need) {
+        alpha = exp2f(m_run - mxs);                    // 0 for the first tile
+        m_run = mxs;
+      }
+      if (j > 0) {
+        // the MMAs of tile j-1 must be done before P (single buffer) is overwritten / O is rescaled
+        mbar_wait(&ctl->o_full, (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+      }
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        // rare: rescale this row of the accumulator in TMEM
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_x32(t_s + c * 32, v);
-        tmem_ld_wait_x32(v);
-        if (c == 3) {                                    // S of this tile is fully drained
-          tc_fence_before();
-          mbar_arrive(&ctl->s_empty);
+        for (int q = 0; q < kHd / 16; ++q) {
+          uint32_t o[16];
+          tmem_ld_x16(t_o + q * 16, o);
+          tmem_ld_wait_x16(o);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_x16(t_o + q * 16, o);
         }
+        tmem_st_wait();
+        tc_fence_before();
+      }
+      // exponentials -> P (fp16, K-major SWIZZLE_128B A operand: two boxes of 64 keys)
+      float rs0 = 0.f, rs1 = 0.f;
+      const float nm = -m_run;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
         const uint32_t box = prow + (uint32_t)((c >> 1) * kTileBytes);
-        const bool full = c * 32 + 32 <= valid;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float e[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            e[i] = exp2f(fmaf(__uint_as_float(v[8 * g + i]), kLog2e, -m_new));
-            if (!full && c * 32 + 8 * g + i >= valid) e[i] = 0.f;
+          for (int i = 0; i < 8; i += 2) {
+            ffma2(e[i], e[i + 1], __uint_as_float(v[c][8 * g + i]), __uint_as_float(v[c][8 * g + i + 1]), kLog2e, nm);
+            e[i] = exp2f(e[i]);
+            e[i + 1] = exp2f(e[i + 1]);
+            fadd2(rs0, rs1, e[i], e[i + 1]);
           }
-          rs0 += (e[0] + e[1]) + (e[2] + e[3]);
-          rs1 += (e[4] + e[5]) + (e[6] + e[7]);
           sts_v4(box + p_off(r, (c & 1) * 4 + g), pack_h2(e[0], e[1]), pack_h2(e[2], e[3]),
                  pack_h2(e[4], e[5]), pack_h2(e[6], e[7]));
         }
@@ -236,20 +260,32 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
       fence_proxy_async_smem();
       mbar_arrive(&ctl->p_full);
       l_run = fmaf(l_run, alpha, rs0 + rs1);
-      m_run = m_new;
-      alpha_prev = alpha;
     }
-    add_o(T - 1, alpha_prev);
-    // normalise, fp16, TMA store through this warp's staging box (the P buffer is free now)
+    // all MMAs done: normalise, fp16, TMA store through this warp's staging box (P is free now)
+    mbar_wait(&ctl->o_full, (uint32_t)((T - 1) & 1));
+    tc_fence_after();
     const float inv = 1.0f / l_run;
     const uint32_t stg = prow + (uint32_t)(warp * 4096);
-    __syncwarp();
+    {
+      uint32_t o0[32], o1[32];
+      tmem_ld_x32(t_o, o0);
+      tmem_ld_x32(t_o + 32, o1);
+      tmem_ld_wait_x32(o0);
+      tmem_ld_wait_x32(o1);
 #pragma unroll
-    for (int g = 0; g < 8; ++g)
-      sts_v4(stg + p_off(lane, g), pack_h2(acc[8 * g] * inv, acc[8 * g + 1] * inv),
-             pack_h2(acc[8 * g + 2] * inv, acc[8 * g + 3] * inv),
-             pack_h2(acc[8 * g + 4] * inv, acc[8 * g + 5] * inv),
-             pack_h2(acc[8 * g + 6] * inv, acc[8 * g + 7] * inv));
+      for (int g = 0; g < 4; ++g) {
+        sts_v4(stg + p_off(lane, g),
+               pack_h2(__uint_as_float(o0[8 * g]) * inv, __uint_as_float(o0[8 * g + 1]) * inv),
+               pack_h2(__uint_as_float(o0[8 * g + 2]) * inv, __uint_as_float(o0[8 * g + 3]) * inv),
+               pack_h2(__uint_as_float(o0[8 * g + 4]) * inv, __uint_as_float(o0[8 * g + 5]) * inv),
+               pack_h2(__uint_as_float(o0[8 * g + 6]) * inv, __uint_as_float(o0[8 * g + 7]) * inv));
+        sts_v4(stg + p_off(lane, 4 + g),
+               pack_h2(__uint_as_float(o1[8 * g]) * inv, __uint_as_float(o1[8 * g + 1]) * inv),
+               pack_h2(__uint_as_float(o1[8 * g + 2]) * inv, __uint_as_float(o1[8 * g + 3]) * inv),
+               pack_h2(__uint_as_float(o1[8 * g + 4]) * inv, __uint_as_float(o1[8 * g + 5]) * inv),
+               pack_h2(__uint_as_float(o1[8 * g + 6]) * inv, __uint_as_float(o1[8 * g + 7]) * inv));
+      }
+    }
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {

@@ -9,9 +9,9 @@
 //   RZ_LIN_RESIDUAL  out fp32 [M, N] = residual + scale * (acc + bias)  (attention.output.dense / mlp.fc2
 //                                       + LayerScale + the residual add; out may alias residual)
 //
-// Tiles are 128 x 256; a CTA walks the N tiles of one 128-row block back to back (the A block comes
-// from HBM once, the weights stay in L2), and two CTAs of a cluster pair (cta_group::2) take row
-// blocks (2i, 2i+1) so that each loads half of the weight tile.  Rows >= M are zero-filled by the TMA
+// Tiles are 128 x 256; the N tiles of one 128-row block run on neighbouring CTAs at the same time (the
+// A block comes from HBM once, the weights stay in L2), and two CTAs of a cluster pair
+// (cta_group::2) take row blocks (2i, 2i+1) so that each loads half of the weight tile.  Rows >= M are zero-filled by the TMA
 // loads and clipped by the TMA stores.
 #include "rz_gemm.cuh"
 
@@ -23,11 +23,25 @@ struct LinParams {
   int M, N, K, m_tiles, n_tiles;
   const float* bias;        // [N] or NULL
   const float* scale;       // [N] or NULL (RZ_LIN_RESIDUAL)
-  const float* residual;    // [M, N] fp32 (RZ_LIN_RESIDUAL)
+  const float* residual;    // [M, N] fp32 (RZ_LIN_RESIDUAL; read through maps.c2)
 };
 
-// erf-GELU (torch.nn.functional.gelu default, Dinov2MLP hidden_act = "gelu")
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-GELU (torch.nn.functional.gelu default, Dinov2MLP hidden_act = "gelu") in 13 FP32 + 2 MUFU
+// instructions:  gelu(x) = relu(x) - 0.5 |x| erfc(|x| / sqrt 2),  erfc(z) = poly5(t) exp(-z^2),
+// t = 1 / (1 + p z)  (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7: far below the fp16 output ulp).
+// libdevice erff costs ~2.5x as many instructions and made the fc1 epilogue slower than its MMAs.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float q = fmaf(1.061405429f, t, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  q *= t;
+  const float e = exp2f(x * x * -0.72134752044448170f);       // exp(-z^2) = 2^(-x^2 / 2 * log2 e)
+  return fmaxf(x, 0.f) - (z * 0.70710678118654752f) * (q * e);
+}
 
 template <int EPI, int C>
 struct Lin : PolicyBase {
@@ -35,15 +49,27 @@ struct Lin : PolicyBase {
   using Params = LinParams;
   static constexpr int kBN = 256, kAccs = 1;
   static constexpr bool kAMn = false, kBMn = false, kTwoPhase = false;
-  // per warp: fp16 outputs one [32 rows x 64 cols] box; fp32 outputs two [32 rows x 32 cols] boxes
-  static constexpr int kWarpStage = EPI == RZ_LIN_RESIDUAL ? 8192 : 4096;
-  static constexpr int kEpiSmem = 4 * kWarpStage;
+  // per warp: fp16 outputs one [32 rows x 64 cols] box; the residual epilogue a ring of four
+  // [32 rows x 32 cols] fp32 boxes (residual in by TMA, result out by TMA from the same box) plus
+  // one mbarrier per box
+  static constexpr int kWarpStage = EPI == RZ_LIN_RESIDUAL ? 16384 : 4096;
+  static constexpr int kEpiSmem = 4 * kWarpStage + (EPI == RZ_LIN_RESIDUAL ? 128 : 0);
+  struct State { uint32_t g; int ready; };     // g: 32-column boxes this warp has consumed so far
   __host__ __device__ static int num_tiles(const Params& p) { return p.m_tiles * p.n_tiles; }
-  __host__ __device__ static int inner(const Params& p) { return p.n_tiles; }
   __host__ __device__ static int k_steps(const Params& p) { return p.K / kBK; }
+  // Tile order: the N tiles of one row block (pair of row blocks) are consecutive ITEMS, i.e. they run
+  // on neighbouring CTAs at the same time, so the A block is fetched from HBM once and hit in L2 by
+  // the others while it is hot.  (Walking them back to back on one CTA instead re-read the 786 KB
+  // A blocks of fc2 from HBM: 148 of them in flight exceed L2.)
+  __device__ static void decode(const Params& p, int tile, int& mt, int& nt) {
+    const int item = tile / C, rank = tile % C;
+    nt = item % p.n_tiles;
+    mt = (item / p.n_tiles) * C + rank;
+  }
   __device__ static void load(const Params& p, const Maps& m, int tile, int ks, uint8_t* a, uint8_t*,
                               uint8_t* bsm, uint64_t* bar, int rank) {
-    const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+    int mt, nt;
+    decode(p, tile, mt, nt);
     load_kmajor<C>(&m.a, bar, a, ks * kBK, mt * kBM, 0);                            // A [M, K]
     load_kmajor_shared<C>(&m.b, bar, bsm, ks * kBK, nt * kBN, 0, kBN, rank);        // W [N, K]
   }
@@ -79,25 +105,66 @@ struct Lin : PolicyBase {
     }
   }
 
-  // one 32-column half of a chunk: out = residual + scale * (acc + bias), fp32
-  __device__ static __forceinline__ void half_res(const Params& p, const Maps& maps, const uint32_t (&a)[32],
-                                                  int col0, int row0, int lane, bool row_ok,
-                                                  const float* rrow, uint32_t stg) {
-    float4 r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      r[j] = row_ok ? __ldcs(reinterpret_cast<const float4*>(rrow + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane == 0) tma_store_wait_read_n<1>();       // the box written two stores ago is free again
+  // ---- residual epilogue -------------------------------------------------------------------
+  // The residual tile is streamed through shared memory by TMA, two boxes ahead of the arithmetic
+  // (a thread-per-row global load would touch 32 different 128-byte lines per instruction and
+  // leave the DRAM latency exposed once per box).  Box i of a warp's ring: TMA load (residual) ->
+  // in-place update by the 32 lanes -> TMA store (result).  Coordinates of running box index g are
+  // those of (tile, g % 8) -- a warp consumes exactly 8 boxes per tile.
+  __device__ static __forceinline__ uint64_t* res_bar(uint8_t* epi_smem, int warp, int box) {
+    return reinterpret_cast<uint64_t*>(epi_smem + 4 * kWarpStage) + warp * 4 + box;
+  }
+  __device__ static __forceinline__ void res_load(const Params& p, const Maps& maps, int tile, int h, uint32_t g,
+                                                  int warp, uint8_t* epi_smem) {
+    int mt, nt;
+    decode(p, tile, mt, nt);
+    const int box = (int)(g & 3u);
+    uint64_t* bar = res_bar(epi_smem, warp, box);
+    mbar_arrive_expect_tx(bar, 4096u);
+    tma_load_3d(&maps.c2, bar, epi_smem + warp * kWarpStage + box * 4096, nt * kBN + h * 32,
+                mt * kBM + warp * 32, 0, kEvictFirst);
+  }
+  template <class S>
+  __device__ static void prologue(const Params& p, const Maps& maps, int tile, int warp, int lane, uint64_t*,
+                                  S& st, uint8_t* epi_smem) {
+    if (EPI != RZ_LIN_RESIDUAL || st.ready) return;
+    st.ready = 1;
+    if (lane == 0) {
+      for (int i = 0; i < 4; ++i) mbar_init(res_bar(epi_smem, warp, i), 1);
+      fence_barrier_init();
+      res_load(p, maps, tile, 0, st.g, warp, epi_smem);
+      res_load(p, maps, tile, 1, st.g + 1, warp, epi_smem);
+    }
     __syncwarp();
+  }
+  __device__ static __forceinline__ void half_res(const Params& p, const Maps& maps, const uint32_t (&a)[32],
+                                                  int tile, int next_tile, int h, int col0, int row0, int warp,
+                                                  int lane, State& st, uint8_t* epi_smem) {
+    const uint32_t g = st.g;
+    if (lane == 0) {
+      // prefetch two boxes ahead; its box was last used by the store of box g - 2
+      const int h2 = h + 2;
+      const int t2 = h2 < 8 ? tile : next_tile;
+      if (t2 >= 0) {
+        tma_store_wait_read_n<1>();
+        res_load(p, maps, t2, h2 & 7, g + 2, warp, epi_smem);
+      }
+    }
+    const int box = (int)(g & 3u);
+    const uint32_t stg = smem_u32(epi_smem) + warp * kWarpStage + box * 4096;
+    mbar_wait(res_bar(epi_smem, warp, box), (g >> 2) & 1u);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      float4 r;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(stg + stage_off(lane, j)));
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f), s = make_float4(1.f, 1.f, 1.f, 1.f);
       if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
       if (p.scale != nullptr) s = __ldg(reinterpret_cast<const float4*>(p.scale + col0) + j);
-      const float o0 = fmaf(s.x, __uint_as_float(a[4 * j]) + b.x, r[j].x);
-      const float o1 = fmaf(s.y, __uint_as_float(a[4 * j + 1]) + b.y, r[j].y);
-      const float o2 = fmaf(s.z, __uint_as_float(a[4 * j + 2]) + b.z, r[j].z);
-      const float o3 = fmaf(s.w, __uint_as_float(a[4 * j + 3]) + b.w, r[j].w);
+      const float o0 = fmaf(s.x, __uint_as_float(a[4 * j]) + b.x, r.x);
+      const float o1 = fmaf(s.y, __uint_as_float(a[4 * j + 1]) + b.y, r.y);
+      const float o2 = fmaf(s.z, __uint_as_float(a[4 * j + 2]) + b.z, r.z);
+      const float o3 = fmaf(s.w, __uint_as_float(a[4 * j + 3]) + b.w, r.w);
       sts_v4(stg + stage_off(lane, j), __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2),
              __float_as_uint(o3));
     }
@@ -107,17 +174,16 @@ struct Lin : PolicyBase {
       tma_store_3d(&maps.c, stg, col0, row0, 0);
       tma_store_commit();
     }
+    st.g = g + 1;
   }
 
-  __device__ static void epilogue(const Params& p, const Maps& maps, int tile, int, uint32_t tmem, int warp,
-                                  int lane, uint64_t*, State&, uint8_t* epi_smem) {
-    const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+  __device__ static void epilogue(const Params& p, const Maps& maps, int tile, int next_tile, uint32_t tmem,
+                                  int warp, int lane, uint64_t*, State& st, uint8_t* epi_smem) {
+    int mt, nt;
+    decode(p, tile, mt, nt);
     const int row0 = mt * kBM + warp * 32;
-    const int row = row0 + lane;
-    const bool row_ok = row < p.M;
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
     const uint32_t stg = smem_u32(epi_smem) + warp * kWarpStage;
-    const float* rrow = EPI == RZ_LIN_RESIDUAL ? p.residual + (long long)(row_ok ? row : 0) * p.N : nullptr;
     Cols64 va, vb;
     ld64(taddr, va);
 #pragma unroll 1
@@ -126,16 +192,16 @@ struct Lin : PolicyBase {
       wait64(va);
       ld64(taddr + (c + 1) * 64, vb);
       if (EPI == RZ_LIN_RESIDUAL) {
-        half_res(p, maps, va.lo, col, row0, lane, row_ok, rrow, stg);
-        half_res(p, maps, va.hi, col + 32, row0, lane, row_ok, rrow, stg + 4096);
+        half_res(p, maps, va.lo, tile, next_tile, 2 * c, col, row0, warp, lane, st, epi_smem);
+        half_res(p, maps, va.hi, tile, next_tile, 2 * c + 1, col + 32, row0, warp, lane, st, epi_smem);
       } else {
         chunk_f16(p, maps, va, col, row0, lane, stg);
       }
       wait64(vb);
       if (c + 2 < kBN / 64) ld64(taddr + (c + 2) * 64, va);
       if (EPI == RZ_LIN_RESIDUAL) {
-        half_res(p, maps, vb.lo, col + 64, row0, lane, row_ok, rrow, stg);
-        half_res(p, maps, vb.hi, col + 96, row0, lane, row_ok, rrow, stg + 4096);
+        half_res(p, maps, vb.lo, tile, next_tile, 2 * c + 2, col + 64, row0, warp, lane, st, epi_smem);
+        half_res(p, maps, vb.hi, tile, next_tile, 2 * c + 3, col + 96, row0, warp, lane, st, epi_smem);
       } else {
         chunk_f16(p, maps, vb, col + 64, row0, lane, stg);
       }
@@ -186,6 +252,9 @@ extern "C" int rz_linear(const void* a_f16, long long m, int k, const void* w_f1
       return RZ_ERR_CUDA;
   }
   mp.c2 = mp.c;
+  if (epilogue == RZ_LIN_RESIDUAL &&
+      !rz::make_map_3d_f32_sw128(&mp.c2, residual, 1, (uint64_t)m, (uint64_t)n, (uint64_t)n * 4, (uint64_t)m * n * 4, 32))
+    return RZ_ERR_CUDA;
   switch (epilogue) {
     case RZ_LIN_BIAS: return launch_lin<RZ_LIN_BIAS>(mp, p, pair, s);
     case RZ_LIN_GELU: return launch_lin<RZ_LIN_GELU>(mp, p, pair, s);
