@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the VL-CABS similarity path (BASELINE.json metric: similarity maps/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cls|seg|openvocab|contrastive]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cls|seg|openvocab|contrastive|align]
     python bench.py --impl reference ...        # the CPU path (oracle port) on the host cores
 
 One "step" = one pass of the hot path over one batch of synthetic input.  Default workload
@@ -138,6 +138,26 @@ def run_ours(args):
             out["cpu_baseline"] = {"value": pairs / dt / full, "unit": "steps/s", "cores": os.cpu_count(),
                                    "kind": "port", "sample": f"fwd+bwd at 16 images x {pairs // 16} sentences on the "
                                    "fp32 CPU oracle, extrapolated by pair count"}
+        if rank == 0:
+            print(json.dumps(out))
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    if args.workload == "align":
+        # the widened path: AlignTransformer -> similarity_prob
+        from radzero_b200 import bench_align
+        sampler = ClockSampler(local)
+        sampler.start()
+        out = bench_align.run(args, world, rank, local, pk)
+        out["clocks"] = sampler.stop()
+        out.update({"higher_is_better": True, "vs_baseline": None, "data": "synthetic", "impl": "ours",
+                    "cpu_baseline": None})
+        if rank == 0 and world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            dt = bench_align.cpu_step_sample(8, cores)
+            out["cpu_baseline"] = {"value": 8 * bench_align.N / dt, "unit": "maps/s", "cores": cores, "kind": "port",
+                                   "sample": f"8 of the {bench_align.B} images x {bench_align.N} prompts (fp32 torch CPU "
+                                   f"oracle: oracle/align.py + oracle/vlcabs.py), best of 2, {dt * 1e3:.0f} ms"}
         if rank == 0:
             print(json.dumps(out))
         if world > 1:
@@ -415,6 +435,9 @@ def run_reference(args):
     if args.workload == "contrastive":
         from radzero_b200 import bench_contrastive
         return bench_contrastive.run_reference(args)
+    if args.workload == "align":
+        from radzero_b200 import bench_align
+        return bench_align.run_reference(args, print)
     from radzero_b200 import synthetic
     B, N, desc = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
@@ -454,7 +477,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cls", choices=list(WORKLOADS) + ["contrastive"])
+    ap.add_argument("--workload", default="cls", choices=list(WORKLOADS) + ["contrastive", "align"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-contrastive", action="store_true",
                     help="skip the contrastive-step add-on of the default workload")

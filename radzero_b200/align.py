@@ -18,8 +18,9 @@ kernels behind the C ABI (``rz_ln_rows``, ``rz_linear``, ``rz_attention``):
     g16 = gelu(h16 W1^T + b1)          rz_linear  "gelu"
     x   = x + ls2 * (g16 W2^T + b2)    rz_linear  "residual"
 
-Inference only (the packed weights are detached); training through the AlignTransformer still
-uses the stock HF module.  No CPU fallback: CPU tensors raise ``RzError``.
+Inference only (the packed weights are detached): when the module is in train mode and autograd needs
+gradients through it (`module_to_update: [align_transformer, ...]`) ``forward`` runs the reference's own stock
+forward instead (``stock_forward``), which is outside this round's scope.  No CPU fallback: CPU tensors raise ``RzError``.
 """
 from __future__ import annotations
 
@@ -96,13 +97,43 @@ class AlignTransformer(nn.Module):
             self._packed = [pack_layer(l, device) for l in layers]
         return self._packed
 
-    @torch.no_grad()
-    def forward(self, vision_tokens: torch.Tensor) -> torch.Tensor:
+    def stock_forward(self, vision_tokens: torch.Tensor) -> torch.Tensor:
+        """The reference's own forward (align_transformers.py:37-45) through the stock HF modules: used
+        when gradients are needed -- training THROUGH the AlignTransformer is outside this round's scope."""
+        x = vision_tokens
+        if self.transformer_layers is not None:
+            x = self.transformer_layers(x)["last_hidden_state"]
+        if self.layer_norm is not None:
+            x = self.layer_norm(x)
+        return x
+
+    def _needs_grad(self, vision_tokens: torch.Tensor) -> bool:
+        # only a module in TRAIN mode under autograd takes the stock path; in eval mode (the state
+        # every inference script of the reference puts the model in) the kernels always run, so a
+        # missing torch.no_grad() cannot silently select the slow path
+        if not (self.training and torch.is_grad_enabled()):
+            return False
+        return vision_tokens.requires_grad or any(p.requires_grad for p in self.parameters())
+
+    def forward(self, vision_tokens: torch.Tensor, inplace: bool = False) -> torch.Tensor:
+        """``inplace=True`` lets the kernels update the caller's fp32 token buffer (no copy)."""
+        if self._needs_grad(vision_tokens):
+            return self.stock_forward(vision_tokens)
+        with torch.no_grad():
+            return self._forward_kernels(vision_tokens, inplace)
+
+    def _forward_kernels(self, vision_tokens: torch.Tensor, inplace: bool) -> torch.Tensor:
         if not vision_tokens.is_cuda:
             raise RzError("radzero_b200 ops run on CUDA tensors only (there is no CPU fallback)")
         if vision_tokens.dim() != 3 or vision_tokens.shape[-1] != ops.HIDDEN:
             raise RzError("vision tokens must be (B, L, 768)")
-        x = vision_tokens.detach().to(torch.float32).contiguous().clone()     # the fp32 residual stream
+        x = vision_tokens.detach()
+        if inplace and x.dtype == torch.float32 and x.is_contiguous():
+            pass                                                  # the fp32 residual stream IS the input
+        else:
+            x = x.to(torch.float32).contiguous()
+            if x.data_ptr() == vision_tokens.data_ptr():
+                x = x.clone()
         for w in self._weights(x.device):
             layer_forward(x, w)
         if self.layer_norm is not None:

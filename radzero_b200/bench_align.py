@@ -1,0 +1,215 @@
+"""Benchmark of the widened path: AlignTransformer (two DINOv2 layers,
+exp/cxr_pt/model/align_transformers.py:37-45) -> VL-CABS ``similarity_prob`` at BASELINE.json
+configs[1] (256 images x 14 prompts), i.e. the zero-shot classification step starting from the
+vision encoder's output instead of from ``vision_tokens``.
+
+One step = ``AlignTransformer.forward`` + ``RadZeroLoss.similarity_prob``.  The step is tensor-bound:
+its algorithmic work is the twelve 768-wide GEMM units of the two layers plus the attention products,
+2 * (24 * M * 768^2 + 4 * B * 12 * L^2 * 64) FLOP with M = B * L rows.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import torch
+
+L, D, HEADS, LAYERS = 1370, 768, 12, 2
+B, N = 256, 14
+DESC = ("C2 upstream: AlignTransformer (2 DINOv2 layers, 12 heads) + similarity_prob, "
+        "256 images x 14 prompts from the vision encoder's output tokens")
+
+
+def align_flops(b: int) -> float:
+    m = b * L
+    return LAYERS * (24.0 * m * D * D + 4.0 * b * HEADS * L * L * 64)
+
+
+def _model(dev, seed=42):
+    from radzero_b200 import losses, synthetic
+    from radzero_b200.align import AlignTransformer
+    enc = synthetic.build_align_encoder(seed=seed, device=dev)
+    _, text, gamma, beta, _ = synthetic.make_inputs(1, N, seed=seed, device=dev)
+    fn = losses.RadZeroLoss(sim_op="cos").to(dev)
+    with torch.no_grad():
+        fn.layer_norm.weight.copy_(gamma)
+        fn.layer_norm.bias.copy_(beta)
+    return AlignTransformer(enc).eval(), fn, text
+
+
+def run(args, world, rank, local, pk, steps=None, warmup=None):
+    import torch.distributed as dist
+    from radzero_b200 import _lib, ops, synthetic
+    from radzero_b200.align import pack_layer
+    dev = torch.device("cuda", local)
+    steps = steps or max(3, min(args.steps, 20))
+    warmup = max(warmup or args.warmup, 3)
+    align, fn, text = _model(dev)
+    tok = synthetic.make_inputs(B, 1, seed=42 + rank, device=dev)[0]
+
+    def step(t):
+        return fn.similarity_prob(text, align(t))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        res = step(tok)
+    barrier()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        res = step(tok)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / steps
+    value = B * N * world / (ms_per_step * 1e-3)
+
+    # per-kernel device times (each launched `reps` times back to back between two events)
+    w = pack_layer(align.transformer_layers.layer[0], dev)
+    m = B * L
+    x2 = tok.view(m, D).clone()
+    h = ops.ln_rows(x2, w["g1"], w["b1"], w["eps1"])
+    qkv = ops.linear(h, w["wqkv"], w["bqkv"], "bias")
+    a = ops.attention(qkv.view(B, L, 3 * D), HEADS)
+    g = ops.linear(h, w["w1"], w["bf1"], "gelu")
+    stages = [
+        ("prep_rows_kernel (LayerNorm -> fp16, x2 per layer)", lambda: ops.ln_rows(x2, w["g1"], w["b1"], w["eps1"]),
+         None, m * D * 6.0),
+        ("gemm_kernel<Lin BIAS> qkv 768->2304", lambda: ops.linear(h, w["wqkv"], w["bqkv"], "bias"), 2.0 * m * D * 3 * D, None),
+        ("attn_kernel (tcgen05 flash attention, 12 heads x 64)", lambda: ops.attention(qkv.view(B, L, 3 * D), HEADS),
+         4.0 * B * HEADS * L * L * 64, None),
+        ("gemm_kernel<Lin RESIDUAL> proj 768->768", lambda: ops.linear(a.view(m, D), w["wo"], w["bo"], "residual",
+                                                                        scale=w["ls1"], residual=x2, out=x2), 2.0 * m * D * D, None),
+        ("gemm_kernel<Lin GELU> fc1 768->3072", lambda: ops.linear(h, w["w1"], w["bf1"], "gelu"), 2.0 * m * D * 4 * D, None),
+        ("gemm_kernel<Lin RESIDUAL> fc2 3072->768", lambda: ops.linear(g, w["w2"], w["bf2"], "residual", scale=w["ls2"],
+                                                                        residual=x2, out=x2), 2.0 * m * D * 4 * D, None),
+    ]
+    kms, detail = {}, {}
+    for name, fnk, fl, by in stages:
+        for _ in range(2):
+            fnk()
+        torch.cuda.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(5):
+            fnk()
+        eb.record()
+        torch.cuda.synchronize()
+        t = ea.elapsed_time(eb) / 5
+        kms[name] = round(t, 4)
+        detail[name] = ({"tflops": round(fl / t / 1e9, 1)} if fl else {"gbs": round(by / t / 1e6, 1)})
+    del x2, h, qkv, a, g
+    flops = align_flops(B)
+    ach = flops / (ms_per_step * 1e-3) / 1e12
+    roof = {"bound": "tensor", "kernel": "whole step (6 GEMM-shaped kernels per layer x 2 layers + similarity)",
+            "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
+            "traffic": None, "peak_source": pk["src"] + " sustained (kernels timed inside a long step)",
+            "algorithmic_flops_per_step": flops, "kernel_ms": kms, "kernel_rates": detail}
+
+    # end to end: pinned host tokens -> H2D -> AlignTransformer (in place on the upload) -> prob -> D2H
+    h_tok = tok.cpu().pin_memory()
+    d_tok = [torch.empty_like(tok) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    r_host = torch.empty((B, N), dtype=torch.float32, pin_memory=True)
+    used = [None, None]
+
+    def upload(k):
+        with torch.cuda.stream(copy_stream):
+            if used[k] is not None:
+                copy_stream.wait_event(used[k])
+            d_tok[k].copy_(h_tok, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
+    def e2e_loop(n):
+        ev = upload(0)
+        for i in range(n):
+            k = i & 1
+            main.wait_event(ev)
+            if i + 1 < n:
+                ev = upload(k ^ 1)
+            r_host.copy_(fn.similarity_prob(text, align(d_tok[k], inplace=True)), non_blocking=True)
+            used[k] = torch.cuda.Event()
+            used[k].record(main)
+        main.synchronize()
+
+    ksteps = max(2, min(steps, 5))
+    e2e_loop(2)
+    barrier()
+    e0.record()
+    e2e_loop(ksteps)
+    e1.record()
+    barrier()
+    ms2 = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms2], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms2 = float(t.item())
+    e2e = {"value": B * N * world / (ms2 / ksteps * 1e-3), "unit": "maps/s",
+           "h2d_bytes_per_step": h_tok.numel() * 4, "d2h_bytes_per_step": r_host.numel() * 4, "steps": ksteps,
+           "api": "AlignTransformer.forward + RadZeroLoss.similarity_prob"}
+    return {"metric": "similarity maps/sec", "value": value, "unit": "maps/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "scaling": "weak", "dtype": "f16",
+            "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
+            "config": {"workload": DESC, "images_per_gpu": B, "prompts": N, "tokens": L, "hidden": D,
+                       "input_dtype": "fp32", "l2": "activations (>= 0.5 GB per kernel) larger than L2; no flush",
+                       "parallelism": f"images sharded x{world}, no collective"},
+            "prob_checksum": float(res.double().sum().item())}
+
+
+def cpu_step_sample(b: int = 4, threads=None):
+    """The CPU oracle (oracle/align.py + oracle/vlcabs.py, fp32 torch) on ``b`` images: seconds per
+    step (best of 2 after one warm-up).  bench.py's cpu_baseline / --impl reference legs only."""
+    import oracle
+    from oracle import align as oalign
+    from radzero_b200 import synthetic
+    if threads:
+        torch.set_num_threads(threads)
+    w = synthetic.align_layer_weights(42)
+    tok, text, gamma, beta, log_tau = synthetic.make_inputs(b, N, seed=42)
+
+    def once():
+        x = oalign.align_transformer(tok, w)
+        ref = oracle.radzero_forward([text[i:i + 1] for i in range(N)], x, gamma, beta, log_tau,
+                                     need_attn_weights=False, compute_loss=False, squeeze_quirk=False)
+        return torch.sigmoid(ref["t2i_logits"].T / torch.exp(log_tau))
+
+    with torch.no_grad():
+        once()
+        best = float("inf")
+        for _ in range(2):
+            t0 = time.perf_counter()
+            once()
+            best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def run_reference(args, emit):
+    """bench.py --impl reference --workload align: the CPU oracle on a bounded sample of the workload."""
+    import json
+    cores = os.cpu_count() or 1
+    bs = 8
+    dt = cpu_step_sample(bs, cores)
+    value = bs * N / dt
+    cpu = {"value": value, "unit": "maps/s", "cores": cores, "kind": "port",
+           "sample": f"{bs} of the {B} images x {N} prompts per step (fp32 torch CPU oracle: oracle/align.py "
+                     "restating transformers' Dinov2Encoder + oracle/vlcabs.py), best of 2"}
+    emit(json.dumps({
+        "metric": "similarity maps/sec", "value": value, "unit": "maps/s", "n_gpus": args.gpus, "steps": 2,
+        "warmup": 1, "ms_per_step": dt * 1e3 * B / bs, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": DESC, "images_per_gpu": B, "prompts": N, "tokens": L, "hidden": D},
+        "cpu_baseline": cpu,
+        "e2e": {"value": value, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))

@@ -136,10 +136,10 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
       for (int j = 0; j < T; ++j) {
         const int st = j & 1;
         const uint32_t ph = (uint32_t)((j >> 1) & 1);
-        mbar_wait(&ctl->k_empty[st], ph ^ 1u);
+        mbar_wait_relaxed(&ctl->k_empty[st], ph ^ 1u);
         mbar_arrive_expect_tx(&ctl->k_full[st], kTileBytes);
         tma_load_3d(&qkv_map, &ctl->k_full[st], k_s + st * kTileBytes, width + h * kHd, j * kTile, b, kEvictNormal);
-        mbar_wait(&ctl->v_empty[st], ph ^ 1u);
+        mbar_wait_relaxed(&ctl->v_empty[st], ph ^ 1u);
         mbar_arrive_expect_tx(&ctl->v_full[st], kTileBytes);
         tma_load_3d(&qkv_map, &ctl->v_full[st], v_s + st * kTileBytes, 2 * width + h * kHd, j * kTile, b, kEvictNormal);
       }
@@ -153,7 +153,7 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
       auto issue_s = [&](int j) {
         const int st = j & 1;
         mbar_wait(&ctl->k_full[st], (uint32_t)((j >> 1) & 1));
-        mbar_wait(&ctl->s_empty, (uint32_t)((j & 1) ^ 1));        // softmax has drained S of tile j-1
+        mbar_wait_relaxed(&ctl->s_empty, (uint32_t)((j & 1) ^ 1));        // softmax has drained S of tile j-1
         tc_fence_after();
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4)
@@ -168,7 +168,7 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
         if (j + 1 < T) issue_s(j + 1);
         const int st = j & 1;
         mbar_wait(&ctl->v_full[st], (uint32_t)((j >> 1) & 1));
-        mbar_wait(&ctl->p_full, (uint32_t)(j & 1));     // also orders any rescale of O before these MMAs
+        mbar_wait_relaxed(&ctl->p_full, (uint32_t)(j & 1));     // also orders any rescale of O before these MMAs
         tc_fence_after();
 #pragma unroll
         for (int k8 = 0; k8 < 8; ++k8)
@@ -218,6 +218,22 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
         alpha = exp2f(m_run - mxs);                    // 0 for the first tile
         m_run = mxs;
       }
+      // exponentials -> packed fp16 in registers (the MMAs of tile j-1 finish meanwhile)
+      float rs0 = 0.f, rs1 = 0.f;
+      const float nm = -m_run;
+      uint32_t pk[64];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float e0, e1;
+          ffma2(e0, e1, __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]), kLog2e, nm);
+          e0 = exp2f(e0);
+          e1 = exp2f(e1);
+          fadd2(rs0, rs1, e0, e1);
+          pk[c * 16 + (i >> 1)] = pack_h2(e0, e1);
+        }
+      }
       if (j > 0) {
         // the MMAs of tile j-1 must be done before P (single buffer) is overwritten / O is rescaled
         mbar_wait(&ctl->o_full, (uint32_t)((j - 1) & 1));
@@ -237,25 +253,14 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
         tmem_st_wait();
         tc_fence_before();
       }
-      // exponentials -> P (fp16, K-major SWIZZLE_128B A operand: two boxes of 64 keys)
-      float rs0 = 0.f, rs1 = 0.f;
-      const float nm = -m_run;
+      // P: fp16, K-major SWIZZLE_128B A operand, two boxes of 64 keys
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint32_t box = prow + (uint32_t)((c >> 1) * kTileBytes);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float e[8];
-#pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            ffma2(e[i], e[i + 1], __uint_as_float(v[c][8 * g + i]), __uint_as_float(v[c][8 * g + i + 1]), kLog2e, nm);
-            e[i] = exp2f(e[i]);
-            e[i + 1] = exp2f(e[i + 1]);
-            fadd2(rs0, rs1, e[i], e[i + 1]);
-          }
-          sts_v4(box + p_off(r, (c & 1) * 4 + g), pack_h2(e[0], e[1]), pack_h2(e[2], e[3]),
-                 pack_h2(e[4], e[5]), pack_h2(e[6], e[7]));
-        }
+        for (int g = 0; g < 4; ++g)
+          sts_v4(box + p_off(r, (c & 1) * 4 + g), pk[c * 16 + 4 * g], pk[c * 16 + 4 * g + 1],
+                 pk[c * 16 + 4 * g + 2], pk[c * 16 + 4 * g + 3]);
       }
       fence_proxy_async_smem();
       mbar_arrive(&ctl->p_full);

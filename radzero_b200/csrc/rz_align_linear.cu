@@ -26,21 +26,61 @@ struct LinParams {
   const float* residual;    // [M, N] fp32 (RZ_LIN_RESIDUAL; read through maps.c2)
 };
 
-// erf-GELU (torch.nn.functional.gelu default, Dinov2MLP hidden_act = "gelu") in 13 FP32 + 2 MUFU
-// instructions:  gelu(x) = relu(x) - 0.5 |x| erfc(|x| / sqrt 2),  erfc(z) = poly5(t) exp(-z^2),
-// t = 1 / (1 + p z)  (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7: far below the fp16 output ulp).
-// libdevice erff costs ~2.5x as many instructions and made the fc1 epilogue slower than its MMAs.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float q = fmaf(1.061405429f, t, -1.453152027f);
-  q = fmaf(q, t, 1.421413741f);
-  q = fmaf(q, t, -0.284496736f);
-  q = fmaf(q, t, 0.254829592f);
-  q *= t;
-  const float e = exp2f(x * x * -0.72134752044448170f);       // exp(-z^2) = 2^(-x^2 / 2 * log2 e)
-  return fmaxf(x, 0.f) - (z * 0.70710678118654752f) * (q * e);
+// packed fp32 pairs (sm_100 FFMA2 / FMUL2): the epilogues are bound by the FP32 instruction count of
+// their four warps, so everything that can is done two columns per instruction
+struct F2 { uint64_t v; };
+__device__ __forceinline__ F2 f2(float a, float b) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ F2 f2(float a) { return f2(a, a); }
+__device__ __forceinline__ void unpack(F2 x, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v));
+}
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
+  F2 r;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) {
+  F2 r;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ F2 add2(F2 a, F2 b) {
+  F2 r;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// erf-GELU (torch.nn.functional.gelu default, Dinov2MLP hidden_act = "gelu") of two columns:
+//   gelu(x) = relu(x) - 0.5 |x| erfc(|x| / sqrt 2),   erfc(z) = poly5(t) exp(-z^2),  t = 1 / (1 + p z)
+// (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7: far below the fp16 output ulp); 8 packed FP32 + 4
+// scalar + 4 MUFU instructions per pair.  libdevice erff costs ~3x as many and made the fc1 epilogue
+// several times slower than its MMAs.
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const float kS = 0.70710678118654752f;
+  const float z0 = fabsf(x0) * kS, z1 = fabsf(x1) * kS;
+  const F2 z = f2(z0, z1), x = f2(x0, x1);
+  float d0, d1;
+  unpack(fma2(z, f2(0.3275911f), f2(1.0f)), d0, d1);
+  const F2 t = f2(rcp_approx(d0), rcp_approx(d1));
+  F2 q = fma2(t, f2(1.061405429f), f2(-1.453152027f));
+  q = fma2(q, t, f2(1.421413741f));
+  q = fma2(q, t, f2(-0.284496736f));
+  q = fma2(q, t, f2(0.254829592f));
+  q = mul2(q, t);
+  float u0, u1;
+  unpack(mul2(mul2(x, x), f2(-0.72134752044448170f)), u0, u1);   // exp(-z^2) = 2^(-x^2 / 2 * log2 e)
+  const F2 e = f2(exp2f(u0), exp2f(u1));
+  const F2 w = mul2(mul2(q, e), mul2(z, f2(-kS)));                // -0.5 |x| erfc
+  unpack(add2(f2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)), w), x0, x1);
 }
 
 template <int EPI, int C>
@@ -49,10 +89,10 @@ struct Lin : PolicyBase {
   using Params = LinParams;
   static constexpr int kBN = 256, kAccs = 1;
   static constexpr bool kAMn = false, kBMn = false, kTwoPhase = false;
-  // per warp: fp16 outputs one [32 rows x 64 cols] box; the residual epilogue a ring of four
+  // per warp: fp16 outputs two alternating [32 rows x 64 cols] boxes; the residual epilogue a ring of four
   // [32 rows x 32 cols] fp32 boxes (residual in by TMA, result out by TMA from the same box) plus
   // one mbarrier per box
-  static constexpr int kWarpStage = EPI == RZ_LIN_RESIDUAL ? 16384 : 4096;
+  static constexpr int kWarpStage = EPI == RZ_LIN_RESIDUAL ? 16384 : 8192;
   static constexpr int kEpiSmem = 4 * kWarpStage + (EPI == RZ_LIN_RESIDUAL ? 128 : 0);
   struct State { uint32_t g; int ready; };     // g: 32-column boxes this warp has consumed so far
   __host__ __device__ static int num_tiles(const Params& p) { return p.m_tiles * p.n_tiles; }
@@ -74,10 +114,11 @@ struct Lin : PolicyBase {
     load_kmajor_shared<C>(&m.b, bar, bsm, ks * kBK, nt * kBN, 0, kBN, rank);        // W [N, K]
   }
 
+  // one 64-column chunk -> fp16.  The arithmetic runs BEFORE the wait for the staging box (two boxes
+  // per warp, alternating), so the previous chunk's TMA store drains behind it.
   __device__ static __forceinline__ void chunk_f16(const Params& p, const Maps& maps, Cols64& v, int col0,
                                                    int row0, int lane, uint32_t stg) {
-    if (lane == 0) tma_store_wait_read();
-    __syncwarp();
+    uint32_t pk[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint32_t* src = j < 4 ? &v.lo[8 * j] : &v.hi[8 * (j - 4)];
@@ -87,16 +128,23 @@ struct Lin : PolicyBase {
       if (p.bias != nullptr) {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * j));
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * j + 4));
-        x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-        x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+        unpack(add2(f2(x[0], x[1]), f2(b0.x, b0.y)), x[0], x[1]);
+        unpack(add2(f2(x[2], x[3]), f2(b0.z, b0.w)), x[2], x[3]);
+        unpack(add2(f2(x[4], x[5]), f2(b1.x, b1.y)), x[4], x[5]);
+        unpack(add2(f2(x[6], x[7]), f2(b1.z, b1.w)), x[6], x[7]);
       }
       if (EPI == RZ_LIN_GELU) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = gelu_erf(x[i]);
+        for (int i = 0; i < 8; i += 2) gelu_erf2(x[i], x[i + 1]);
       }
-      sts_v4(stg + stage_off(lane, j), pack_h2(x[0], x[1]), pack_h2(x[2], x[3]), pack_h2(x[4], x[5]),
-             pack_h2(x[6], x[7]));
+      pk[4 * j] = pack_h2(x[0], x[1]); pk[4 * j + 1] = pack_h2(x[2], x[3]);
+      pk[4 * j + 2] = pack_h2(x[4], x[5]); pk[4 * j + 3] = pack_h2(x[6], x[7]);
     }
+    if (lane == 0) tma_store_wait_read_n<1>();       // the box written two stores ago is free again
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts_v4(stg + stage_off(lane, j), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -203,7 +251,7 @@ struct Lin : PolicyBase {
         half_res(p, maps, vb.lo, tile, next_tile, 2 * c + 2, col + 64, row0, warp, lane, st, epi_smem);
         half_res(p, maps, vb.hi, tile, next_tile, 2 * c + 3, col + 96, row0, warp, lane, st, epi_smem);
       } else {
-        chunk_f16(p, maps, vb, col + 64, row0, lane, stg);
+        chunk_f16(p, maps, vb, col + 64, row0, lane, stg + 4096);
       }
     }
   }

@@ -134,7 +134,8 @@ def build_random_init_model(device="cuda", dtype=torch.float32, seed: int = 42,
                         image_size=518, patch_size=14)
     vision = Dinov2Model(vcfg)
     acfg = Dinov2Config(hidden_size=768, num_hidden_layers=2, num_attention_heads=12)
-    align = Dinov2Encoder(acfg)
+    from .align import AlignTransformer
+    align = AlignTransformer(Dinov2Encoder(acfg))     # align_transformers.py:23-45, use_layer_norm=False
     tcfg = MPNetConfig(num_hidden_layers=text_layers)
     text = MPNetModel(tcfg)
     model = CxrAlignModel(vision, align, text)

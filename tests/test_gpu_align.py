@@ -178,3 +178,48 @@ def test_cpu_tensors_raise():
         AlignTransformer(None)(torch.zeros(1, 4, 768))
     with pytest.raises(RzError):
         ops.attention(torch.zeros(1, 4, 2304, dtype=torch.float16), 12)
+
+
+def test_inplace_and_grad_dispatch():
+    enc, w = _gpu_weights(13)
+    mod = AlignTransformer(enc).eval()
+    tok = synthetic.make_inputs(1, 1, tokens_per_image=300, seed=13)[0].to(DEV)
+    want = mod(tok)
+    buf = tok.clone()
+    got = mod(buf, inplace=True)
+    assert got.data_ptr() == buf.data_ptr() and torch.equal(got, want)
+    # bf16 tokens (the reference's training / bf16_full_eval dtype) are accepted; output is fp32
+    got16 = mod(tok.to(torch.bfloat16))
+    assert got16.dtype == torch.float32 and (got16 - want).abs().max().item() <= 0.25
+    # eval mode never leaves the kernels, with or without torch.no_grad()
+    with torch.enable_grad():
+        assert not mod(tok).requires_grad
+    # train mode + gradients needed -> the reference's own stock forward (out of this round's scope)
+    mod.train()
+    with torch.enable_grad():
+        y = mod(tok)
+    assert y.requires_grad
+    assert (y.detach() - want).abs().max().item() <= 3e-2
+    with torch.no_grad():
+        assert not mod(tok).requires_grad
+
+
+def test_model_vision_tokens_match_stock_modules():
+    """The random-init RadZero architecture (BASELINE configs[0]): the tokens the kernels hand to the
+    VL-CABS path against the stock HF AlignTransformer forward on the same ViT output, and the cosine
+    similarities that follow."""
+    from radzero_b200 import modeling
+    model = modeling.build_random_init_model(device=DEV, vision_layers=2, text_layers=1)
+    torch.manual_seed(0)
+    vit_out = torch.randn(2, 1370, 768, device=DEV)
+    with torch.no_grad():
+        got = model.align_transformer(vit_out)
+        want = model.align_transformer.stock_forward(vit_out.double().float())
+    assert (got - want).abs().max().item() <= 2e-2
+    fn = model.loss_fns["RadZeroLoss"]
+    g, b = fn.layer_norm.weight.detach().double(), fn.layer_norm.bias.detach().double()
+    text = torch.randn(14, 768, device=DEV, dtype=torch.float64)
+    q = orc.l2_normalize_rows(orc.layer_norm_rows(text, g, b))
+    kg = orc.l2_normalize_rows(orc.layer_norm_rows(got.double(), g, b))
+    kw = orc.l2_normalize_rows(orc.layer_norm_rows(want.double(), g, b))
+    assert (kg @ q.T - kw @ q.T).abs().max().item() <= 2e-3
