@@ -37,7 +37,7 @@ rep("attention", timeit(lambda: ops.attention(qkv.view(B, L, 3 * D), 12)), 4.0 *
 rep("linear proj+res (768->768)", timeit(lambda: ops.linear(a.view(M, D), w["wo"], w["bo"], "residual", scale=w["ls1"], residual=x2, out=x2)), 2.0 * M * D * D)
 rep("linear fc1+gelu (768->3072)", timeit(lambda: ops.linear(h, w["w1"], w["bf1"], "gelu")), 2.0 * M * D * 4 * D)
 rep("linear fc2+res (3072->768)", timeit(lambda: ops.linear(g, w["w2"], w["bf2"], "residual", scale=w["ls2"], residual=x2, out=x2)), 2.0 * M * D * 4 * D)
-mod = AlignTransformer(enc)
+mod = AlignTransformer(enc).eval()
 flops2 = 2 * (2.0 * M * D * D * 12 + 4.0 * B * 12 * L * L * 64)
 rep("AlignTransformer (2 layers)", timeit(lambda: mod(tok), 3), flops2)
 with torch.no_grad():

@@ -5,8 +5,8 @@
 //
 // Q, K, V are column blocks of the fused projection output qkv [B, L, 3 * H * 64] fp16 (Q already
 // carries the 1/sqrt(64) scale: it is folded into the projection weights on the host, exactly, since
-// it is a power of two).  One CTA owns (image, head, 128 query rows) and streams the image's keys in
-// tiles of 128; two CTAs are resident per SM (256 TMEM columns and ~113 KB of shared memory each) so
+// it is a power of two).  A work item is (image, head, 128 query rows): its CTA streams the image's keys in
+// tiles of 128.  The kernel is persistent, two CTAs resident per SM (256 TMEM columns and ~113 KB of shared memory each) so
 // that one CTA's exponentials overlap the other's MMAs.
 //
 //   warp 4  TMA producer: Q once, then K / V tiles into two-stage rings (separate barriers: S can
@@ -35,23 +35,23 @@ constexpr int kHd = 64;                    // head dim
 constexpr int kTile = 128;                 // query rows per CTA = keys per tile
 constexpr int kTileBytes = kTile * 128;    // 128 rows x 64 halfs
 constexpr int kThreads = 192;
-constexpr int kTmemCols = 256;             // S [0,128)  O [128,192)
+constexpr int kTmemCols = 256;             // S [0,128)  O [128,192)  P [192,256) (fp16 pairs)
 constexpr float kLazy = 8.0f;              // log2 units: the reference maximum moves when exceeded by 2^8
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct AttnParams {
-  int B, L, H, q_tiles, kv_tiles;
+  int B, L, H, q_tiles, kv_tiles, items;     // items = B * H * q_tiles (image, head, query tile)
 };
 
 struct Ctrl {
-  uint64_t q_full;
+  uint64_t q_full, q_empty;
   uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
   uint64_t s_full, s_empty, p_full;
   uint64_t o_full;
   uint32_t tmem_slot;
 };
 
-constexpr int kSmem = 5 * kTileBytes + 2 * kTileBytes + 256;   // Q, K x2, V x2, P (two 64-key boxes), Ctrl
+constexpr int kSmem = 5 * kTileBytes + kTileBytes + 256;   // Q, K x2, V x2, output staging (4 x 4 KB), Ctrl
 static_assert(sizeof(Ctrl) <= 256, "control block");
 
 __device__ __forceinline__ uint32_t p_off(int row, int chunk) {
@@ -81,6 +81,27 @@ __device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) 
   asm("add.rn.ftz.f32x2 %0, %0, %1;" : "+l"(D) : "l"(A));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(D));
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (here the fp16 probabilities, two K elements per 32-bit
+// column, row = TMEM lane) is read from tensor memory, so P never goes through shared memory
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+      "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait_x16(uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
@@ -99,17 +120,27 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
   uint8_t* k_s = q_s + kTileBytes;
   uint8_t* v_s = k_s + 2 * kTileBytes;
   uint8_t* p_s = v_s + 2 * kTileBytes;
-  Ctrl* ctl = reinterpret_cast<Ctrl*>(p_s + 2 * kTileBytes);
+  Ctrl* ctl = reinterpret_cast<Ctrl*>(p_s + kTileBytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int qt = (int)blockIdx.x % p.q_tiles;
-  const int bh = (int)blockIdx.x / p.q_tiles;
-  const int h = bh % p.H, b = bh / p.H;
   const int T = p.kv_tiles;
   const int width = p.H * kHd;
+  // PERSISTENT: this CTA walks items blockIdx.x, blockIdx.x + gridDim.x, ... (query tile fastest, so
+  // the CTAs resident at one time share their K / V in L2); every pipeline barrier keeps counting
+  // across items (G = running key-tile index, it = running item index), so the next item's Q load
+  // and first S = Q K^T overlap the softmax of this item's last tile and its output store.
+  const int my_items = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto decode = [&](int it, int& b, int& h, int& qt) {
+    const int item = (int)blockIdx.x + it * (int)gridDim.x;
+    qt = item % p.q_tiles;
+    const int bh = item / p.q_tiles;
+    h = bh % p.H;
+    b = bh / p.H;
+  };
 
   if (tid == 0) {
     mbar_init(&ctl->q_full, 1);
+    mbar_init(&ctl->q_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->k_full[i], 1); mbar_init(&ctl->k_empty[i], 1);
       mbar_init(&ctl->v_full[i], 1); mbar_init(&ctl->v_empty[i], 1);
@@ -131,17 +162,23 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
 
   if (warp == 4) {
     if (elect_one()) {
-      mbar_arrive_expect_tx(&ctl->q_full, kTileBytes);
-      tma_load_3d(&qkv_map, &ctl->q_full, q_s, h * kHd, qt * kTile, b, kEvictNormal);
-      for (int j = 0; j < T; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (uint32_t)((j >> 1) & 1);
-        mbar_wait_relaxed(&ctl->k_empty[st], ph ^ 1u);
-        mbar_arrive_expect_tx(&ctl->k_full[st], kTileBytes);
-        tma_load_3d(&qkv_map, &ctl->k_full[st], k_s + st * kTileBytes, width + h * kHd, j * kTile, b, kEvictNormal);
-        mbar_wait_relaxed(&ctl->v_empty[st], ph ^ 1u);
-        mbar_arrive_expect_tx(&ctl->v_full[st], kTileBytes);
-        tma_load_3d(&qkv_map, &ctl->v_full[st], v_s + st * kTileBytes, 2 * width + h * kHd, j * kTile, b, kEvictNormal);
+      int G = 0;
+      for (int it = 0; it < my_items; ++it) {
+        int b, h, qt;
+        decode(it, b, h, qt);
+        mbar_wait_relaxed(&ctl->q_empty, (uint32_t)((it & 1) ^ 1));   // all S MMAs of the previous item issued + done
+        mbar_arrive_expect_tx(&ctl->q_full, kTileBytes);
+        tma_load_3d(&qkv_map, &ctl->q_full, q_s, h * kHd, qt * kTile, b, kEvictNormal);
+        for (int j = 0; j < T; ++j, ++G) {
+          const int st = G & 1;
+          const uint32_t ph = (uint32_t)((G >> 1) & 1);
+          mbar_wait_relaxed(&ctl->k_empty[st], ph ^ 1u);
+          mbar_arrive_expect_tx(&ctl->k_full[st], kTileBytes);
+          tma_load_3d(&qkv_map, &ctl->k_full[st], k_s + st * kTileBytes, width + h * kHd, j * kTile, b, kEvictNormal);
+          mbar_wait_relaxed(&ctl->v_empty[st], ph ^ 1u);
+          mbar_arrive_expect_tx(&ctl->v_full[st], kTileBytes);
+          tma_load_3d(&qkv_map, &ctl->v_full[st], v_s + st * kTileBytes, 2 * width + h * kHd, j * kTile, b, kEvictNormal);
+        }
       }
     }
     __syncwarp();
@@ -149,11 +186,13 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_f16(kTile, kTile, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_f16(kTile, kHd, 0, 1);
-      const uint32_t qa = smem_u32(q_s), ka = smem_u32(k_s), va = smem_u32(v_s), pa = smem_u32(p_s);
-      auto issue_s = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&ctl->k_full[st], (uint32_t)((j >> 1) & 1));
-        mbar_wait_relaxed(&ctl->s_empty, (uint32_t)((j & 1) ^ 1));        // softmax has drained S of tile j-1
+      const uint32_t qa = smem_u32(q_s), ka = smem_u32(k_s), va = smem_u32(v_s);
+      const int total = my_items * T;
+      auto issue_s = [&](int G) {
+        const int st = G & 1, j = G % T, it = G / T;
+        if (j == 0) mbar_wait(&ctl->q_full, (uint32_t)(it & 1));
+        mbar_wait(&ctl->k_full[st], (uint32_t)((G >> 1) & 1));
+        mbar_wait_relaxed(&ctl->s_empty, (uint32_t)((G & 1) ^ 1));        // softmax has drained S of tile G-1
         tc_fence_after();
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4)
@@ -161,143 +200,159 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
                      make_smem_desc(ka + st * kTileBytes + k4 * 32, 0, 1024), idesc_s, k4 ? 1u : 0u);
         mma_commit(&ctl->s_full);
         mma_commit(&ctl->k_empty[st]);
+        if (j == T - 1) mma_commit(&ctl->q_empty);     // Q may be replaced by the next item's
       };
-      mbar_wait(&ctl->q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) issue_s(j + 1);
-        const int st = j & 1;
-        mbar_wait(&ctl->v_full[st], (uint32_t)((j >> 1) & 1));
-        mbar_wait_relaxed(&ctl->p_full, (uint32_t)(j & 1));     // also orders any rescale of O before these MMAs
+      if (total > 0) issue_s(0);
+      for (int G = 0; G < total; ++G) {
+        // S of the next tile goes first (it overlaps this tile's softmax) -- except across an item
+        // boundary, where it has to wait for the next Q anyway and would hold back these MMAs
+        const bool next_same_item = (G + 1) % T != 0;
+        if (G + 1 < total && next_same_item) issue_s(G + 1);
+        const int st = G & 1, j = G % T;
+        mbar_wait(&ctl->v_full[st], (uint32_t)((G >> 1) & 1));
+        // P of this tile is ready; this also orders the rescale of O (and, for j == 0, the read-out of
+        // the previous item's O by the softmax warps) before these MMAs
+        mbar_wait_relaxed(&ctl->p_full, (uint32_t)(G & 1));
         tc_fence_after();
 #pragma unroll
         for (int k8 = 0; k8 < 8; ++k8)
-          mma_f16_ss(tmem_base + 128,
-                     make_smem_desc(pa + (k8 >> 2) * kTileBytes + (k8 & 3) * 32, 0, 1024),
+          mma_f16_ts(tmem_base + 128, tmem_base + 192 + k8 * 8,
                      make_smem_desc(va + st * kTileBytes + k8 * 2048, 8192, 1024), idesc_o, (j | k8) ? 1u : 0u);
         mma_commit(&ctl->o_full);
         mma_commit(&ctl->v_empty[st]);
+        if (G + 1 < total && !next_same_item) issue_s(G + 1);
       }
     }
     __syncwarp();
   } else {
     const int r = warp * 32 + lane;                     // query row of this thread = TMEM lane
     const uint32_t t_s = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const uint32_t t_o = t_s + 128;
-    const uint32_t prow = smem_u32(p_s);
-    float m_run = -INFINITY, l_run = 0.f;
-
-    for (int j = 0; j < T; ++j) {
-      const int valid = min(kTile, p.L - j * kTile);    // real keys in this tile
-      uint32_t v[4][32];
-      mbar_wait(&ctl->s_full, (uint32_t)(j & 1));
-      tc_fence_after();
+    const uint32_t t_o = t_s + 128, t_p = t_s + 192;
+    const uint32_t stg = smem_u32(p_s) + (uint32_t)(warp * 4096);   // this warp's output staging box
+    int G = 0;
+    for (int it = 0; it < my_items; ++it) {
+      int b, h, qt;
+      decode(it, b, h, qt);
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < T; ++j, ++G) {
+        const int valid = min(kTile, p.L - j * kTile);    // real keys in this tile
+        uint32_t v[4][32];
+        mbar_wait(&ctl->s_full, (uint32_t)(G & 1));
+        tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_x32(t_s + c * 32, v[c]);
+        for (int c = 0; c < 4; ++c) tmem_ld_x32(t_s + c * 32, v[c]);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_wait_x32(v[c]);
-      tc_fence_before();
-      mbar_arrive(&ctl->s_empty);                      // S is in registers: the next S = Q K^T may start
-      if (valid < kTile) {
+        for (int c = 0; c < 4; ++c) tmem_ld_wait_x32(v[c]);
+        tc_fence_before();
+        mbar_arrive(&ctl->s_empty);                      // S is in registers: the next S = Q K^T may start
+        if (valid < kTile) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) v[c][i] = 0xff800000u;   // -inf: probability 0
+        }
+        // row maximum: eight independent FMNMX3 chains (one serial chain of 64 costs ~300 cycles)
+        float mq[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) mq[q] = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= valid) v[c][i] = 0xff800000u;   // -inf: probability 0
-      }
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; i += 2)
-          mx = fmaxf(mx, fmaxf(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])));
-      const float mxs = mx * kLog2e;
-      const bool need = mxs > m_run + kLazy;           // always true for the first tile
-      float alpha = 1.f;
-      if (need) {
-        alpha = exp2f(m_run - mxs);                    // 0 for the first tile
-        m_run = mxs;
-      }
-      // exponentials -> packed fp16 in registers (the MMAs of tile j-1 finish meanwhile)
-      float rs0 = 0.f, rs1 = 0.f;
-      const float nm = -m_run;
-      uint32_t pk[64];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float e0, e1;
-          ffma2(e0, e1, __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]), kLog2e, nm);
-          e0 = exp2f(e0);
-          e1 = exp2f(e1);
-          fadd2(rs0, rs1, e0, e1);
-          pk[c * 16 + (i >> 1)] = pack_h2(e0, e1);
+          for (int i = 0; i < 32; i += 2)
+            mq[(i >> 1) & 7] = fmaxf(mq[(i >> 1) & 7], fmaxf(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])));
+        const float mx = fmaxf(fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3])),
+                               fmaxf(fmaxf(mq[4], mq[5]), fmaxf(mq[6], mq[7])));
+        const float mxs = mx * kLog2e;
+        const bool need = mxs > m_run + kLazy;           // always true for the first tile
+        float alpha = 1.f;
+        if (need) {
+          alpha = exp2f(m_run - mxs);                    // 0 for the first tile
+          m_run = mxs;
         }
-      }
-      if (j > 0) {
-        // the MMAs of tile j-1 must be done before P (single buffer) is overwritten / O is rescaled
-        mbar_wait(&ctl->o_full, (uint32_t)((j - 1) & 1));
-        tc_fence_after();
-      }
-      if (j > 0 && __any_sync(0xffffffffu, need)) {
-        // rare: rescale this row of the accumulator in TMEM
+        // exponentials -> packed fp16 in registers (the MMAs of tile j-1 finish meanwhile)
+        float rs[8];                                     // four independent FADD2 chains
+#pragma unroll
+        for (int q = 0; q < 8; ++q) rs[q] = 0.f;
+        const float nm = -m_run;
+        // (packed IN PLACE: pair i of chunk c lands in v[c][i / 2], a register that is already consumed,
+        // so the 128 scores and the 64 packed probabilities never coexist -- no spills at 168 registers)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float e0, e1;
+            ffma2(e0, e1, __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]), kLog2e, nm);
+            e0 = exp2f(e0);
+            e1 = exp2f(e1);
+            fadd2(rs[i & 6], rs[(i & 6) + 1], e0, e1);
+            v[c][i >> 1] = pack_h2(e0, e1);
+          }
+        }
+        if (j > 0) {
+          // the MMAs of tile j-1 must be done before P (single buffer) is overwritten / O is rescaled
+          mbar_wait(&ctl->o_full, (uint32_t)((G - 1) & 1));
+          tc_fence_after();
+        }
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          // rare: rescale this row of the accumulator in TMEM
 #pragma unroll 1
-        for (int q = 0; q < kHd / 16; ++q) {
-          uint32_t o[16];
-          tmem_ld_x16(t_o + q * 16, o);
-          tmem_ld_wait_x16(o);
+          for (int q = 0; q < kHd / 16; ++q) {
+            uint32_t o[16];
+            tmem_ld_x16(t_o + q * 16, o);
+            tmem_ld_wait_x16(o);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_x16(t_o + q * 16, o);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x16(t_o + q * 16, o);
+          }
         }
+        // P -> TMEM as the A operand of O += P V: row = this thread's lane, keys (2c, 2c + 1) in column c
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          tmem_st_x16(t_p + c * 16, *reinterpret_cast<const uint32_t(*)[16]>(&v[c][0]));
         tmem_st_wait();
         tc_fence_before();
+        mbar_arrive(&ctl->p_full);
+        l_run = fmaf(l_run, alpha, ((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7])));
       }
-      // P: fp16, K-major SWIZZLE_128B A operand, two boxes of 64 keys
+      // all MMAs of the item done: normalise, fp16, TMA store through this warp's staging rows
+      mbar_wait(&ctl->o_full, (uint32_t)((G - 1) & 1));
+      tc_fence_after();
+      const float inv = 1.0f / l_run;
+      {
+        uint32_t o0[32], o1[32];
+        tmem_ld_x32(t_o, o0);
+        tmem_ld_x32(t_o + 32, o1);
+        tmem_ld_wait_x32(o0);
+        tmem_ld_wait_x32(o1);
+        tc_fence_before();
+        if (it > 0) {
+          // the previous item's output store must have read this staging box
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+        }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t box = prow + (uint32_t)((c >> 1) * kTileBytes);
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          sts_v4(box + p_off(r, (c & 1) * 4 + g), pk[c * 16 + 4 * g], pk[c * 16 + 4 * g + 1],
-                 pk[c * 16 + 4 * g + 2], pk[c * 16 + 4 * g + 3]);
+        for (int g = 0; g < 4; ++g) {
+          sts_v4(stg + p_off(lane, g),
+                 pack_h2(__uint_as_float(o0[8 * g]) * inv, __uint_as_float(o0[8 * g + 1]) * inv),
+                 pack_h2(__uint_as_float(o0[8 * g + 2]) * inv, __uint_as_float(o0[8 * g + 3]) * inv),
+                 pack_h2(__uint_as_float(o0[8 * g + 4]) * inv, __uint_as_float(o0[8 * g + 5]) * inv),
+                 pack_h2(__uint_as_float(o0[8 * g + 6]) * inv, __uint_as_float(o0[8 * g + 7]) * inv));
+          sts_v4(stg + p_off(lane, 4 + g),
+                 pack_h2(__uint_as_float(o1[8 * g]) * inv, __uint_as_float(o1[8 * g + 1]) * inv),
+                 pack_h2(__uint_as_float(o1[8 * g + 2]) * inv, __uint_as_float(o1[8 * g + 3]) * inv),
+                 pack_h2(__uint_as_float(o1[8 * g + 4]) * inv, __uint_as_float(o1[8 * g + 5]) * inv),
+                 pack_h2(__uint_as_float(o1[8 * g + 6]) * inv, __uint_as_float(o1[8 * g + 7]) * inv));
+        }
       }
       fence_proxy_async_smem();
-      mbar_arrive(&ctl->p_full);
-      l_run = fmaf(l_run, alpha, rs0 + rs1);
-    }
-    // all MMAs done: normalise, fp16, TMA store through this warp's staging box (P is free now)
-    mbar_wait(&ctl->o_full, (uint32_t)((T - 1) & 1));
-    tc_fence_after();
-    const float inv = 1.0f / l_run;
-    const uint32_t stg = prow + (uint32_t)(warp * 4096);
-    {
-      uint32_t o0[32], o1[32];
-      tmem_ld_x32(t_o, o0);
-      tmem_ld_x32(t_o + 32, o1);
-      tmem_ld_wait_x32(o0);
-      tmem_ld_wait_x32(o1);
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        sts_v4(stg + p_off(lane, g),
-               pack_h2(__uint_as_float(o0[8 * g]) * inv, __uint_as_float(o0[8 * g + 1]) * inv),
-               pack_h2(__uint_as_float(o0[8 * g + 2]) * inv, __uint_as_float(o0[8 * g + 3]) * inv),
-               pack_h2(__uint_as_float(o0[8 * g + 4]) * inv, __uint_as_float(o0[8 * g + 5]) * inv),
-               pack_h2(__uint_as_float(o0[8 * g + 6]) * inv, __uint_as_float(o0[8 * g + 7]) * inv));
-        sts_v4(stg + p_off(lane, 4 + g),
-               pack_h2(__uint_as_float(o1[8 * g]) * inv, __uint_as_float(o1[8 * g + 1]) * inv),
-               pack_h2(__uint_as_float(o1[8 * g + 2]) * inv, __uint_as_float(o1[8 * g + 3]) * inv),
-               pack_h2(__uint_as_float(o1[8 * g + 4]) * inv, __uint_as_float(o1[8 * g + 5]) * inv),
-               pack_h2(__uint_as_float(o1[8 * g + 6]) * inv, __uint_as_float(o1[8 * g + 7]) * inv));
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&out_map, stg, h * kHd, qt * kTile + warp * 32, b);
+        tma_store_commit();
       }
     }
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_3d(&out_map, stg, h * kHd, qt * kTile + warp * 32, b);
-      tma_store_commit();
-      tma_store_wait_all();
-    }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -317,8 +372,11 @@ extern "C" int rz_attention(const void* qkv_f16, int n_images, int tokens, int h
   p.B = n_images; p.L = tokens; p.H = heads;
   p.q_tiles = (tokens + kTile - 1) / kTile;
   p.kv_tiles = p.q_tiles;
-  const long long ctas = (long long)n_images * heads * p.q_tiles;
-  if (ctas >= (1ll << 31)) return RZ_ERR_UNSUPPORTED;
+  const long long items = (long long)n_images * heads * p.q_tiles;
+  if (items * p.kv_tiles >= (1ll << 31)) return RZ_ERR_UNSUPPORTED;
+  p.items = (int)items;
+  const long long resident = 2ll * rz_sm_count();      // two CTAs per SM (launch bounds, 113 KB smem each)
+  const long long ctas = items < resident ? items : resident;
   CUtensorMap qkv_map, out_map;
   if (!rz::make_map_3d_sw128(&qkv_map, qkv_f16, (uint64_t)n_images, (uint64_t)tokens, (uint64_t)3 * width,
                              (uint64_t)3 * width * 2, (uint64_t)tokens * 3 * width * 2, kTile))
