@@ -93,7 +93,10 @@ struct Lin : PolicyBase {
   // [32 rows x 32 cols] fp32 boxes (residual in by TMA, result out by TMA from the same box) plus
   // one mbarrier per box
   static constexpr int kWarpStage = EPI == RZ_LIN_RESIDUAL ? 16384 : 8192;
-  static constexpr int kEpiSmem = 4 * kWarpStage + (EPI == RZ_LIN_RESIDUAL ? 128 : 0);
+  // the fp16 epilogues (bias add, GELU) are bound by the instruction issue of their warps: eight
+  // epilogue warps, two per TMEM lane quarter, each taking one 128-column half of the tile
+  static constexpr int kEpiWarps = EPI == RZ_LIN_RESIDUAL ? 4 : 8;
+  static constexpr int kEpiSmem = kEpiWarps * kWarpStage + (EPI == RZ_LIN_RESIDUAL ? 128 : 0);
   struct State { uint32_t g; int ready; };     // g: 32-column boxes this warp has consumed so far
   __host__ __device__ static int num_tiles(const Params& p) { return p.m_tiles * p.n_tiles; }
   __host__ __device__ static int k_steps(const Params& p) { return p.K / kBK; }
@@ -229,30 +232,35 @@ struct Lin : PolicyBase {
                                   int warp, int lane, uint64_t*, State& st, uint8_t* epi_smem) {
     int mt, nt;
     decode(p, tile, mt, nt);
-    const int row0 = mt * kBM + warp * 32;
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    const int quarter = warp & 3;                     // TMEM lanes 32 * quarter .. + 31 = rows of this warp
+    const int row0 = mt * kBM + quarter * 32;
+    const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16);
     const uint32_t stg = smem_u32(epi_smem) + warp * kWarpStage;
     Cols64 va, vb;
+    if (EPI != RZ_LIN_RESIDUAL) {
+      // eight warps: warp w takes columns [128 * (w / 4), + 128) of the tile
+      const int c0 = (warp >> 2) * 2;
+      const int col = nt * kBN + c0 * 64;
+      ld64(taddr + c0 * 64, va);
+      wait64(va);
+      ld64(taddr + (c0 + 1) * 64, vb);
+      chunk_f16(p, maps, va, col, row0, lane, stg);
+      wait64(vb);
+      chunk_f16(p, maps, vb, col + 64, row0, lane, stg + 4096);
+      return;
+    }
     ld64(taddr, va);
 #pragma unroll 1
     for (int c = 0; c < kBN / 64; c += 2) {
       const int col = nt * kBN + c * 64;
       wait64(va);
       ld64(taddr + (c + 1) * 64, vb);
-      if (EPI == RZ_LIN_RESIDUAL) {
-        half_res(p, maps, va.lo, tile, next_tile, 2 * c, col, row0, warp, lane, st, epi_smem);
-        half_res(p, maps, va.hi, tile, next_tile, 2 * c + 1, col + 32, row0, warp, lane, st, epi_smem);
-      } else {
-        chunk_f16(p, maps, va, col, row0, lane, stg);
-      }
+      half_res(p, maps, va.lo, tile, next_tile, 2 * c, col, row0, warp, lane, st, epi_smem);
+      half_res(p, maps, va.hi, tile, next_tile, 2 * c + 1, col + 32, row0, warp, lane, st, epi_smem);
       wait64(vb);
       if (c + 2 < kBN / 64) ld64(taddr + (c + 2) * 64, va);
-      if (EPI == RZ_LIN_RESIDUAL) {
-        half_res(p, maps, vb.lo, tile, next_tile, 2 * c + 2, col + 64, row0, warp, lane, st, epi_smem);
-        half_res(p, maps, vb.hi, tile, next_tile, 2 * c + 3, col + 96, row0, warp, lane, st, epi_smem);
-      } else {
-        chunk_f16(p, maps, vb, col + 64, row0, lane, stg + 4096);
-      }
+      half_res(p, maps, vb.lo, tile, next_tile, 2 * c + 2, col + 64, row0, warp, lane, st, epi_smem);
+      half_res(p, maps, vb.hi, tile, next_tile, 2 * c + 3, col + 96, row0, warp, lane, st, epi_smem);
     }
   }
 };

@@ -1,9 +1,11 @@
 // Persistent, warp-specialised tcgen05 GEMM skeleton shared by the large-N forward and the
 // backward kernels of the VL-CABS path.
 //
-//   warp 4 : TMA producer   (one elected lane; SWIZZLE_128B boxes into a kStages-deep ring)
-//   warp 5 : MMA issuer     (one elected lane; tcgen05.mma kind::f16, fp32 accumulate in TMEM)
-//   warps 0-3 : epilogue    (thread = accumulator row; tcgen05.ld -> policy functor -> global)
+//   warp EW     : TMA producer   (one elected lane; SWIZZLE_128B boxes into a kStages-deep ring)
+//   warp EW + 1 : MMA issuer     (one elected lane; tcgen05.mma kind::f16, fp32 accumulate in TMEM)
+//   warps 0..EW-1 : epilogue     (thread = accumulator row; tcgen05.ld -> policy functor -> global)
+// EW = V::kEpiWarps = 4, or 8 for epilogues that are bound by their own instruction issue (warps w and
+// w + 4 share the TMEM lane quarter w % 4 and split the tile's columns)
 //
 // Output tile: 128 rows x (kAccs * kBN) fp32 TMEM columns, double buffered (2 * kAccs * kBN
 // <= 512) so that the epilogue of tile i overlaps the MMAs of tile i+1.  K advances 64
@@ -45,6 +47,7 @@ struct PolicyBase {
   struct State {};
   static constexpr int kEpiSmem = 0;
   static constexpr int kCluster = 1;
+  static constexpr int kEpiWarps = 4;
   template <class P> __host__ __device__ static int inner(const P&) { return 1; }
   template <class P> __host__ __device__ static int tile_n(const P&, int) { return 0; }
   // called by the epilogue warps before they wait for the tile's accumulator
@@ -85,10 +88,11 @@ struct Ctrl {
 //   empty[st], acc_full[a]   per CTA, signalled by the leader's multicast commits
 //   acc_empty[a]  lives in the leader: one arrival per epilogue warp of BOTH CTAs (4 local + 4 remote)
 template <class V>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(32 * (V::kEpiWarps + 2), 1)
 gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
   using L = Layout<V>;
   constexpr int C = V::kCluster;
+  constexpr int EW = V::kEpiWarps;
   extern __shared__ uint8_t smem_raw[];
   // the dynamic segment starts at the same offset in every CTA, so the aligned base does too
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -104,11 +108,11 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
 
   if (tid == 0) {
     for (int i = 0; i < L::kStages; ++i) { mbar_init(&ctl->full[i], C); mbar_init(&ctl->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->acc_full[i], 1); mbar_init(&ctl->acc_empty[i], 4 * C); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->acc_full[i], 1); mbar_init(&ctl->acc_empty[i], EW * C); }
     for (int i = 0; i < 8; ++i) mbar_init(&ctl->epi_bar[i], 1);
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == EW) {
     if (lane == 0) {
       prefetch_tmap(&maps.a); prefetch_tmap(&maps.b);
       if (V::kAccs > 1 || V::kTwoPhase) { prefetch_tmap(&maps.a2); prefetch_tmap(&maps.b2); }
@@ -120,7 +124,7 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_slot;
 
-  if (warp == 4) {
+  if (warp == EW) {
     if (elect_one()) {
       long long g = 0;
       for (int item = cid; item < n_items; item += ncl) {
@@ -138,7 +142,7 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == EW + 1) {
     if (rank == 0 && elect_one()) {
       long long g = 0;
       int it = 0;
@@ -205,7 +209,7 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
   tc_fence_before();
   // (pair) nobody leaves while the partner may still read this CTA's operands or signal its barriers
   if (C > 1) cluster_sync_all(); else __syncthreads();
-  if (warp == 4) { if (C > 1) tmem_dealloc_pair(tmem_base, kTmem); else tmem_dealloc(tmem_base, kTmem); }
+  if (warp == EW) { if (C > 1) tmem_dealloc_pair(tmem_base, kTmem); else tmem_dealloc(tmem_base, kTmem); }
 }
 
 // resident clusters of gemm_kernel<V> on this device (persistent grid size / kCluster)
@@ -236,7 +240,7 @@ int launch(const Maps& maps, const typename V::Params& p, cudaStream_t s) {
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = V::kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = L::kSmem; cfg.stream = s;
+  cfg.blockDim = dim3(32 * (V::kEpiWarps + 2)); cfg.dynamicSmemBytes = L::kSmem; cfg.stream = s;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cfg.gridDim = dim3((unsigned)(rz_sm_count() / V::kCluster * V::kCluster));
   const int cap = max_clusters<V>(&cfg);
