@@ -264,6 +264,21 @@ int rz_mpnce_finish(const float* z, long long ldz, int n_total, int b_local, int
                     const float* colpos, float* scratch2, float* dz, float* loss_terms,
                     void* stream);
 
+/* ---- T0: text side ------------------------------------------
+ * Masked mean pooling of the text encoder's token embeddings (exp/cxr_pt/model/modeling.py:147-156,
+ * text_encoders.py:32-41) fused with the path's LayerNorm + L2 normalisation of the pooled vector
+ * (losses.py:163-164, 212-213), for ALL prompts / sentences in one launch (the reference calls the
+ * text model once per prompt, modeling.py:290-298, and normalises afterwards).
+ *   hidden          [n_sentences, tokens, 768] of `dtype` (last_hidden_state, padded batch)
+ *   attention_mask  int64 [n_sentences, tokens]; tokens whose mask is 0 are never read
+ *   feats_f32       optional fp32 [n_sentences, 768] = text_features_wo_l2_norm
+ *   q_f16           optional fp16 [n_sentences, 768] = rows as rz_prep_rows would write them from
+ *                   feats_f32 (gamma/beta NULL: no LayerNorm; l2 as in rz_prep_rows)
+ */
+int rz_text_pool(const void* hidden, int dtype, const long long* attention_mask, int n_sentences,
+                 int tokens, const float* gamma, const float* beta, int l2, float* feats_f32,
+                 void* q_f16, void* stream);
+
 /* ---- A0-A2: the AlignTransformer in front of the path ------
  * The vision tokens the VL-CABS path consumes are produced by AlignTransformer.forward
  * (exp/cxr_pt/model/align_transformers.py:37-45): a transformers `Dinov2Encoder` of two layers

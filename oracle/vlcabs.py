@@ -27,6 +27,7 @@ __all__ = [
     "LN_EPS",
     "L2_EPS",
     "NCE_EPS",
+    "masked_mean_pool",
     "layer_norm_rows",
     "l2_normalize_rows",
     "similarity_logit",
@@ -47,6 +48,15 @@ __all__ = [
 LN_EPS = 1e-5  # nn.LayerNorm default, exp/cxr_pt/model/losses.py:51
 L2_EPS = 1e-12  # F.normalize default, losses.py:212-213
 NCE_EPS = 1e-8  # multi_positive_nce_loss default, losses.py:247
+
+
+# --------------------------------------------------------------------------- a9 / T0
+def masked_mean_pool(token_embeddings: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+    """Sentence embedding of the MPNet branch -- modeling.py:147-156 (``use_cls_token: False``,
+    radzero.yaml:26): sum of the token embeddings weighted by the float attention mask over
+    ``clamp(mask.sum, min=1e-9)``.  (n, T, D), (n, T) -> (n, D) = ``text_features_wo_l2_norm``."""
+    m = attention_mask.unsqueeze(-1).expand(token_embeddings.size()).float().to(token_embeddings.dtype)
+    return torch.sum(token_embeddings * m, 1) / torch.clamp(m.sum(1), min=1e-9)
 
 
 # --------------------------------------------------------------------------- a1 / K1

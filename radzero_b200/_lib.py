@@ -48,6 +48,7 @@ SIGNATURES: Dict[str, tuple] = {
     "rz_mpnce_partials": (_i, [_vp, _ll, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rz_mpnce_finish": (_i, [_vp, _ll, _i, _i, _i, _vp, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp,
                              _vp, _vp, _vp, _vp]),
+    "rz_text_pool": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "rz_ln_rows": (_i, [_vp, _i, _vp, _vp, _f, _ll, _vp, _vp]),
     "rz_linear": (_i, [_vp, _ll, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "rz_attention": (_i, [_vp, _i, _i, _i, _vp, _vp]),

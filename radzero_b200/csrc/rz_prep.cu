@@ -55,6 +55,48 @@ prep_rows_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
   }
 }
 
+// T0: masked mean pooling of the text encoder's token embeddings (one warp per sentence; masked-out
+// tokens are never read) fused with the path's LayerNorm + L2 normalisation of the pooled vector.
+//   feats[i] = sum_t m[i,t] h[i,t,:] / max(sum_t m[i,t], 1e-9)          modeling.py:147-156
+//   q16[i]   = L2(LN(feats[i]))  as fp16                                  losses.py:163-164, 212-213
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+text_pool_kernel(const T* __restrict__ hidden, const long long* __restrict__ mask, int n, int tokens,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, int l2,
+                 float* __restrict__ feats, __half* __restrict__ q16) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (i >= n) return;
+  float acc[24];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) acc[k] = 0.f;
+  float msum = 0.f;
+  for (int t = 0; t < tokens; ++t) {
+    const float m = (float)__ldg(mask + (long long)i * tokens + t);
+    if (m == 0.f) continue;                                  // warp-uniform: padding tokens cost nothing
+    float v[24];
+    rz::RowLoad<T>::load(hidden + ((long long)i * tokens + t) * RZ_HIDDEN, lane, v);
+#pragma unroll
+    for (int k = 0; k < 24; ++k) acc[k] = fmaf(m, v[k], acc[k]);
+    msum += m;
+  }
+  const float inv = 1.0f / fmaxf(msum, 1e-9f);
+#pragma unroll
+  for (int k = 0; k < 24; ++k) acc[k] *= inv;
+  if (feats != nullptr) {
+    float4* o = reinterpret_cast<float4*>(feats + (long long)i * RZ_HIDDEN) + lane;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) o[32 * j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+  }
+  if (q16 != nullptr) {
+    rz::ln_l2_row(acc, gamma, beta, lane, RZ_LN_EPS, RZ_L2_EPS, l2 != 0);
+    uint2* o = reinterpret_cast<uint2*>(q16 + (long long)i * RZ_HIDDEN) + lane;
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      o[32 * j] = make_uint2(rz::pack_half2(acc[4 * j], acc[4 * j + 1]), rz::pack_half2(acc[4 * j + 2], acc[4 * j + 3]));
+  }
+}
+
 }  // namespace
 
 static int prep_rows_impl(const void* x, int dtype, const float* gamma, const float* beta,
@@ -119,4 +161,39 @@ extern "C" int rz_ln_rows(const void* x, int dtype, const float* gamma, const fl
   const int rpg = rows < (1 << 30) ? (int)rows : 0;
   if (rpg == 0) return RZ_ERR_UNSUPPORTED;
   return prep_rows_impl(x, dtype, gamma, beta, rows, rpg, rpg, out_f16, nullptr, nullptr, 0, eps, stream);
+}
+
+extern "C" int rz_text_pool(const void* hidden, int dtype, const long long* attention_mask, int n_sentences,
+                            int tokens, const float* gamma, const float* beta, int l2, float* feats_f32,
+                            void* q_f16, void* stream) {
+  if (hidden == nullptr || attention_mask == nullptr || n_sentences < 0 || tokens <= 0) return RZ_ERR_INVALID;
+  if ((gamma == nullptr) != (beta == nullptr)) return RZ_ERR_INVALID;
+  if (feats_f32 == nullptr && q_f16 == nullptr) return RZ_ERR_INVALID;
+  if (n_sentences == 0) return RZ_OK;
+  if ((reinterpret_cast<uintptr_t>(hidden) & 15) || (reinterpret_cast<uintptr_t>(feats_f32) & 15) ||
+      (reinterpret_cast<uintptr_t>(q_f16) & 15) || (reinterpret_cast<uintptr_t>(gamma) & 15) ||
+      (reinterpret_cast<uintptr_t>(beta) & 15) || (reinterpret_cast<uintptr_t>(attention_mask) & 7))
+    return RZ_ERR_ALIGNMENT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)((n_sentences + kWarpsPerBlock - 1) / kWarpsPerBlock)), block(kWarpsPerBlock * 32);
+  __half* q = static_cast<__half*>(q_f16);
+  switch (dtype) {
+    case RZ_F32:
+      text_pool_kernel<float><<<grid, block, 0, s>>>(static_cast<const float*>(hidden), attention_mask, n_sentences,
+                                                     tokens, gamma, beta, l2, feats_f32, q);
+      break;
+    case RZ_BF16:
+      text_pool_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(static_cast<const __nv_bfloat16*>(hidden), attention_mask,
+                                                             n_sentences, tokens, gamma, beta, l2, feats_f32, q);
+      break;
+    case RZ_F16:
+      text_pool_kernel<__half><<<grid, block, 0, s>>>(static_cast<const __half*>(hidden), attention_mask, n_sentences,
+                                                      tokens, gamma, beta, l2, feats_f32, q);
+      break;
+    default:
+      return RZ_ERR_INVALID;
+  }
+  RZ_LAUNCH_OK();
+  rz_count_launch();
+  return RZ_OK;
 }

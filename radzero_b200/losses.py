@@ -87,14 +87,15 @@ class SimilarityLogit(nn.Module):
 
 
 def _similarity_forward(text: torch.Tensor, tokens: torch.Tensor, gamma, beta, scale: float,
-                        l2: bool, want_scores: bool, drop_cls: bool, **zkw):
+                        l2: bool, want_scores: bool, drop_cls: bool, q16: Optional[torch.Tensor] = None, **zkw):
     """The inference forward.  N <= 16 prompts: prep(text) + ONE kernel that reads the raw
     tokens (LayerNorm + L2 fused into the GEMM's loader warps).  Larger prompt sets:
     prep of both operands to fp16, then the TMA-fed fused forward.  Returns (Z, scores)."""
     if tokens.dim() != 3:
         raise RzError("vision tokens must be (B, L, 768)")
     B, L, _ = tokens.shape
-    q16, _, _ = ops.prep_rows(text, gamma, beta, l2=l2)
+    if q16 is None:      # else: rows already normalised by ops.text_pool (fused with the mean pooling)
+        q16, _, _ = ops.prep_rows(text, gamma, beta, l2=l2)
     qin = None
     if not l2:
         qin = 1.0 / q16.float().norm(dim=-1).clamp_min(1e-12)   # F.normalize(query), losses.py:226
@@ -310,12 +311,14 @@ class RadZeroLoss(nn.Module):
 
     @torch.no_grad()
     def similarity(self, text_features: torch.Tensor, vision_tokens: torch.Tensor, *,
-                   want_scores: bool = True, drop_cls: Optional[bool] = None):
+                   want_scores: bool = True, drop_cls: Optional[bool] = None,
+                   q16: Optional[torch.Tensor] = None):
         """Everything ``compute_logits`` needs in one fused pass.
 
         Returns ``(logits (B, N) = Z^T / tau, similarity_scores (B, N, L - drop) | None,
         t2i_logits (N, B))`` -- modeling.py:300-328 without the intermediate (B, N, L+1)
-        tensor, the CLS-dropping copy or the stack/mean over a one-element list.
+        tensor, the CLS-dropping copy or the stack/mean over a one-element list.  ``q16``: the
+        prompts' rows already LayerNorm-ed + normalised by ``ops.text_pool`` (skips their prep launch).
         """
         tokens = vision_tokens if self.use_vision_cls_token else vision_tokens[:, 1:]
         if drop_cls is None:
@@ -325,6 +328,6 @@ class RadZeroLoss(nn.Module):
         zkw = {"log_tau_scale": self._attn_log_tau()} if l2 else {}
         scale = 1.0 if l2 else 1.0 / math.sqrt(self.hidden_dim)
         z, scores = _similarity_forward(text_features, tokens, gamma, beta, scale, l2, want_scores,
-                                        drop_cls, **zkw)
+                                        drop_cls, q16=q16, **zkw)
         logits = z.T / self.loss_temperature.exp()
         return logits, scores, z

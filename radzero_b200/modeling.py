@@ -57,11 +57,21 @@ class CxrAlignModel(nn.Module):
         return {"vision_tokens": vision_tokens, "image_cls_token": cls_token,
                 "image_patch_tokens": patch_tokens, "image_features": image_features}
 
-    def forward_text_model(self, encoded_input):
+    def _text_hidden(self, encoded_input):
         out = self.text_model(input_ids=encoded_input["input_ids"],
                               attention_mask=encoded_input["attention_mask"])
-        hidden = out["last_hidden_state"] if not torch.is_tensor(out) else out
-        feats = mean_pooling(hidden, encoded_input["attention_mask"])
+        return out["last_hidden_state"] if not torch.is_tensor(out) else out
+
+    def forward_text_model(self, encoded_input):
+        hidden = self._text_hidden(encoded_input)
+        mask = encoded_input["attention_mask"]
+        if hidden.is_cuda and hidden.shape[-1] == 768 and not (torch.is_grad_enabled() and hidden.requires_grad):
+            # one fused launch for the whole padded batch (rz_text_pool); autograd keeps the torch formula
+            from . import ops
+            feats, _ = ops.text_pool(hidden, mask, want_q16=False)
+            feats = feats.to(hidden.dtype)
+        else:
+            feats = mean_pooling(hidden, mask)
         return {"text_features_wo_l2_norm": feats, "text_features": F.normalize(feats, p=2, dim=1)}
 
     # ------------------------------------------------------------------ training forward
@@ -95,11 +105,20 @@ class CxrAlignModel(nn.Module):
         if self.compute_logits_type != "radzero":
             raise NotImplementedError(self.compute_logits_type)
         vision = self.forward_vision_model(pixel_values)
-        text = self.forward_text_model(encoded_key_phrases[0])["text_features_wo_l2_norm"]
         loss_fn: RadZeroLoss = self.loss_fns["RadZeroLoss"]
-        if text.shape[-1] == 2 * loss_fn.hidden_dim:
-            text = text[:, loss_fn.hidden_dim:]
-        logits, scores, z = loss_fn.similarity(text, vision["vision_tokens"], want_scores=True)
+        enc = encoded_key_phrases[0]
+        hidden = self._text_hidden(enc)
+        q16 = None
+        if hidden.is_cuda and hidden.shape[-1] == loss_fn.hidden_dim and loss_fn.sim_op in ("cos", "dot"):
+            # mean pooling + the loss's LayerNorm + L2 of ALL prompts in one launch
+            from . import ops
+            g, b = loss_fn._ln()
+            text, q16 = ops.text_pool(hidden, enc["attention_mask"], g, b, l2=loss_fn.sim_op == "cos")
+        else:
+            text = mean_pooling(hidden, enc["attention_mask"])
+            if text.shape[-1] == 2 * loss_fn.hidden_dim:
+                text = text[:, loss_fn.hidden_dim:]
+        logits, scores, z = loss_fn.similarity(text, vision["vision_tokens"], want_scores=True, q16=q16)
         scores_with_cls = None  # the reference also returns the pre-drop tensor; not materialised here
         return {"logits": logits, "similarity_scores": scores, "t2i_logits": z,
                 "t2i_attn_weights": scores_with_cls}

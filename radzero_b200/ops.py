@@ -491,3 +491,29 @@ def attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
     rc = _lib.load().rz_attention(_p(qkv), B, L, heads, _p(out), _stream())
     _lib.check(rc, "rz_attention")
     return out
+
+
+# ----------------------------------------------------------------------------- T0
+def text_pool(hidden: torch.Tensor, attention_mask: torch.Tensor, gamma: Optional[torch.Tensor] = None,
+              beta: Optional[torch.Tensor] = None, *, l2: bool = True, want_feats: bool = True,
+              want_q16: bool = True):
+    """Masked mean pooling of ``hidden`` (n, T, 768) + LayerNorm + L2 of the pooled rows, one launch.
+
+    Returns ``(text_features_wo_l2_norm fp32 (n, 768) | None, q16 fp16 (n, 768) | None)``.
+    """
+    _need_cuda(hidden, attention_mask, gamma, beta)
+    if hidden.dim() != 3 or hidden.shape[-1] != HIDDEN or hidden.dtype not in _DTYPES:
+        raise RzError("hidden must be (n, T, 768) fp32/bf16/fp16")
+    if tuple(attention_mask.shape) != tuple(hidden.shape[:2]):
+        raise RzError("attention_mask must be (n, T)")
+    h = _contig(hidden)
+    m = _contig(attention_mask.to(torch.int64))
+    n, t, _ = h.shape
+    g = _contig(gamma.detach().float()) if gamma is not None else None
+    b = _contig(beta.detach().float()) if beta is not None else None
+    feats = torch.empty((n, HIDDEN), dtype=torch.float32, device=h.device) if want_feats else None
+    q16 = torch.empty((n, HIDDEN), dtype=torch.float16, device=h.device) if want_q16 else None
+    rc = _lib.load().rz_text_pool(_p(h), _DTYPES[h.dtype], _p(m), n, t, _p(g), _p(b), 1 if l2 else 0,
+                                  _p(feats), _p(q16), _stream())
+    _lib.check(rc, "rz_text_pool")
+    return feats, q16

@@ -197,3 +197,34 @@ def test_dice_sweep_stats_vs_oracle(kind, size):
     assert abs(res["dice"] - float(wdice.max())) < 1e-3
     negprob = torch.sigmoid(oracle.interpolate_similarity_scores(scores[-1], size, kind))
     assert res["specificity"] == oracle.compute_specificity(negprob, res["best_threshold"])
+
+
+# ------------------------------------------------------------------------------- T0 text pooling
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n,T", [(1, 1), (14, 9), (37, 32), (600, 17)])
+def test_text_pool_matches_oracle(n, T, dtype):
+    """rz_text_pool against the oracle's masked mean (modeling.py:147-156) + LN + L2 (ragged masks, a
+    fully masked sentence, padding tokens holding garbage that must never be read into the mean)."""
+    import oracle
+    from radzero_b200 import ops
+    torch.manual_seed(n * 31 + T)
+    hidden = (torch.randn(n, T, 768, device="cuda") * 2 + 0.3).to(dtype)
+    lens = torch.randint(1, T + 1, (n,), device="cuda")
+    if n > 2:
+        lens[1] = 0                                              # all-masked sentence: clamp(min=1e-9) branch
+    mask = (torch.arange(T, device="cuda")[None, :] < lens[:, None]).long()
+    hidden = torch.where(mask.bool()[..., None], hidden, torch.full_like(hidden, float("nan")))
+    gamma = torch.rand(768, device="cuda") + 0.5
+    beta = torch.rand(768, device="cuda") * 0.4 - 0.2
+    feats, q16 = ops.text_pool(hidden, mask, gamma, beta)
+    clean = torch.nan_to_num(hidden.double(), nan=0.0)
+    want = oracle.masked_mean_pool(clean, mask)
+    assert torch.isfinite(feats).all() and (feats.double() - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
+    wq = oracle.l2_normalize_rows(oracle.layer_norm_rows(feats.double(), gamma.double(), beta.double()))
+    assert (q16.double() - wq).abs().max().item() <= 1e-3
+    # identical to the two-step path of the product (prep_rows on the pooled rows)
+    q_two, _, _ = ops.prep_rows(feats, gamma, beta)
+    assert (q16.float() - q_two.float()).abs().max().item() <= 2e-3
+    # no LayerNorm / no L2 variants
+    _, q_plain = ops.text_pool(hidden, mask, None, None, l2=False, want_feats=False)
+    assert (q_plain.double() - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())

@@ -101,3 +101,16 @@ def test_known_answers():
     l = oracle.multi_positive_nce_loss(zi, torch.arange(B), temperature=0.07)
     import math
     assert abs(l.item() - math.log(1 + (B - 1) * math.exp(-2 / 0.07))) < 1e-7
+
+
+def test_masked_mean_pool_known_answers():
+    """oracle.masked_mean_pool (modeling.py:147-156): mean over the unmasked tokens; an all-masked
+    sentence gives 0 (sum 0 over clamp(0, min=1e-9)); a full mask is the plain mean."""
+    import oracle
+    torch.manual_seed(0)
+    h = torch.randn(3, 5, 8, dtype=torch.float64)
+    m = torch.tensor([[1, 1, 1, 0, 0], [0, 0, 0, 0, 0], [1, 1, 1, 1, 1]])
+    out = oracle.masked_mean_pool(h, m)
+    assert torch.allclose(out[0], h[0, :3].mean(0))
+    assert torch.equal(out[1], torch.zeros(8, dtype=torch.float64))
+    assert torch.allclose(out[2], h[2].mean(0))
