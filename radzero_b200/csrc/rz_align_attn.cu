@@ -34,7 +34,8 @@ using namespace rz::umma;
 constexpr int kHd = 64;                    // head dim
 constexpr int kTile = 128;                 // query rows per CTA = keys per tile
 constexpr int kTileBytes = kTile * 128;    // 128 rows x 64 halfs
-constexpr int kThreads = 192;
+constexpr int kSoftmaxWarps = 8;            // two per TMEM lane quarter: warp w and w + 4 split a row's 128 keys
+constexpr int kThreads = 32 * (kSoftmaxWarps + 2);
 constexpr int kTmemCols = 256;             // S [0,128)  O [128,192)  P [192,256) (fp16 pairs)
 constexpr float kLazy = 8.0f;              // log2 units: the reference maximum moves when exceeded by 2^8
 constexpr float kLog2e = 1.4426950408889634f;
@@ -49,10 +50,12 @@ struct Ctrl {
   uint64_t s_full, s_empty, p_full;
   uint64_t o_full;
   uint32_t tmem_slot;
+  float xmax[2][2][kTile];     // [tile parity][half][row]: the two threads of a row exchange their half maxima
+  float xsum[2][kTile];        // [half][row]: ... and their half row sums at the end of an item
 };
 
-constexpr int kSmem = 5 * kTileBytes + kTileBytes + 256;   // Q, K x2, V x2, output staging (4 x 4 KB), Ctrl
-static_assert(sizeof(Ctrl) <= 256, "control block");
+constexpr int kSmem = 5 * kTileBytes + kTileBytes + 4096;   // Q, K x2, V x2, output staging (4 x 4 KB), Ctrl
+static_assert(sizeof(Ctrl) <= 4096, "control block");
 
 __device__ __forceinline__ uint32_t p_off(int row, int chunk) {
   return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
@@ -147,11 +150,11 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
     }
     mbar_init(&ctl->o_full, 1);
     mbar_init(&ctl->s_full, 1);
-    mbar_init(&ctl->s_empty, 128);
-    mbar_init(&ctl->p_full, 128);
+    mbar_init(&ctl->s_empty, 32 * kSoftmaxWarps);
+    mbar_init(&ctl->p_full, 32 * kSoftmaxWarps);
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == kSoftmaxWarps) {
     if (lane == 0) { prefetch_tmap(&qkv_map); prefetch_tmap(&out_map); }
     tmem_alloc(&ctl->tmem_slot, kTmemCols);
   }
@@ -160,7 +163,7 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_slot;
 
-  if (warp == 4) {
+  if (warp == kSoftmaxWarps) {
     if (elect_one()) {
       int G = 0;
       for (int it = 0; it < my_items; ++it) {
@@ -182,7 +185,7 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == kSoftmaxWarps + 1) {
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_f16(kTile, kTile, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_f16(kTile, kHd, 0, 1);
@@ -225,67 +228,76 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
     }
     __syncwarp();
   } else {
-    const int r = warp * 32 + lane;                     // query row of this thread = TMEM lane
-    const uint32_t t_s = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const uint32_t t_o = t_s + 128, t_p = t_s + 192;
-    const uint32_t stg = smem_u32(p_s) + (uint32_t)(warp * 4096);   // this warp's output staging box
+    // Two threads per query row: warp w (half 0) and warp w + 4 (half 1) share the TMEM lane quarter
+    // q = w % 4 and split the row's 128 keys of every tile 64 / 64 (and the 64 output columns 32 / 32).
+    // Four softmax warps per scheduler instead of two is what keeps the MUFU pipe fed: with one
+    // thread per row the exponential phase of one warp could not cover the latency-bound phase
+    // (TMEM load, maximum, P store) of the only other one.
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = q * 32 + lane;                        // query row of this thread = TMEM lane
+    const int pair_bar = 1 + q;                         // named barrier of the row's two warps (64 threads)
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_s = t_lane + hf * 64;              // this thread's 64 score columns
+    const uint32_t t_o = t_lane + 128 + hf * 32;        // ... 32 accumulator columns
+    const uint32_t t_p = t_lane + 192 + hf * 32;        // ... 32 packed probability columns (64 keys)
+    const uint32_t stg = smem_u32(p_s) + (uint32_t)(q * 4096);   // output staging box of the quarter
     int G = 0;
     for (int it = 0; it < my_items; ++it) {
       int b, h, qt;
       decode(it, b, h, qt);
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < T; ++j, ++G) {
-        const int valid = min(kTile, p.L - j * kTile);    // real keys in this tile
-        uint32_t v[4][32];
+        const int valid = min(kTile, p.L - j * kTile) - hf * 64;    // real keys among this thread's 64
+        uint32_t v[2][32];
         mbar_wait(&ctl->s_full, (uint32_t)(G & 1));
         tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_x32(t_s + c * 32, v[c]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_wait_x32(v[c]);
+        tmem_ld_x32(t_s, v[0]);
+        tmem_ld_x32(t_s + 32, v[1]);
+        tmem_ld_wait_x32(v[0]);
+        tmem_ld_wait_x32(v[1]);
         tc_fence_before();
         mbar_arrive(&ctl->s_empty);                      // S is in registers: the next S = Q K^T may start
-        if (valid < kTile) {
+        if (valid < 64) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (c * 32 + i >= valid) v[c][i] = 0xff800000u;   // -inf: probability 0
         }
-        // row maximum: eight independent FMNMX3 chains (one serial chain of 64 costs ~300 cycles)
-        float mq[8];
+        // half-row maximum: four independent FMNMX3 chains, then the exchange with the other half
+        float mq[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) mq[q] = -INFINITY;
+        for (int k = 0; k < 4; ++k) mq[k] = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int i = 0; i < 32; i += 2)
-            mq[(i >> 1) & 7] = fmaxf(mq[(i >> 1) & 7], fmaxf(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])));
-        const float mx = fmaxf(fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3])),
-                               fmaxf(fmaxf(mq[4], mq[5]), fmaxf(mq[6], mq[7])));
+            mq[(i >> 1) & 3] = fmaxf(mq[(i >> 1) & 3], fmaxf(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])));
+        float mx = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
+        ctl->xmax[G & 1][hf][r] = mx;
+        named_bar_sync(pair_bar, 64);
+        mx = fmaxf(mx, ctl->xmax[G & 1][hf ^ 1][r]);
         const float mxs = mx * kLog2e;
-        const bool need = mxs > m_run + kLazy;           // always true for the first tile
+        const bool need = mxs > m_run + kLazy;           // always true for the first tile; same in both halves
         float alpha = 1.f;
         if (need) {
           alpha = exp2f(m_run - mxs);                    // 0 for the first tile
           m_run = mxs;
         }
-        // exponentials -> packed fp16 in registers (the MMAs of tile j-1 finish meanwhile)
-        float rs[8];                                     // four independent FADD2 chains
+        // exponentials -> fp16 pairs, packed IN PLACE (pair i of chunk c lands in v[c][i / 2])
+        float rs[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) rs[q] = 0.f;
+        for (int k = 0; k < 4; ++k) rs[k] = 0.f;
         const float nm = -m_run;
-        // (packed IN PLACE: pair i of chunk c lands in v[c][i / 2], a register that is already consumed,
-        // so the 128 scores and the 64 packed probabilities never coexist -- no spills at 168 registers)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float e0, e1;
             ffma2(e0, e1, __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]), kLog2e, nm);
             e0 = exp2f(e0);
             e1 = exp2f(e1);
-            fadd2(rs[i & 6], rs[(i & 6) + 1], e0, e1);
+            fadd2(rs[i & 2], rs[(i & 2) + 1], e0, e1);
             v[c][i >> 1] = pack_h2(e0, e1);
           }
         }
@@ -295,68 +307,62 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
           tc_fence_after();
         }
         if (j > 0 && __any_sync(0xffffffffu, need)) {
-          // rare: rescale this row of the accumulator in TMEM
+          // rare: rescale this row's half of the accumulator in TMEM
 #pragma unroll 1
-          for (int q = 0; q < kHd / 16; ++q) {
+          for (int k = 0; k < 2; ++k) {
             uint32_t o[16];
-            tmem_ld_x16(t_o + q * 16, o);
+            tmem_ld_x16(t_o + k * 16, o);
             tmem_ld_wait_x16(o);
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_x16(t_o + q * 16, o);
+            tmem_st_x16(t_o + k * 16, o);
           }
         }
         // P -> TMEM as the A operand of O += P V: row = this thread's lane, keys (2c, 2c + 1) in column c
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 2; ++c)
           tmem_st_x16(t_p + c * 16, *reinterpret_cast<const uint32_t(*)[16]>(&v[c][0]));
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&ctl->p_full);
-        l_run = fmaf(l_run, alpha, ((rs[0] + rs[1]) + (rs[2] + rs[3])) + ((rs[4] + rs[5]) + (rs[6] + rs[7])));
+        l_run = fmaf(l_run, alpha, (rs[0] + rs[1]) + (rs[2] + rs[3]));
       }
-      // all MMAs of the item done: normalise, fp16, TMA store through this warp's staging rows
+      // all MMAs of the item done: normalise, fp16, TMA store through the quarter's staging box
       mbar_wait(&ctl->o_full, (uint32_t)((G - 1) & 1));
       tc_fence_after();
-      const float inv = 1.0f / l_run;
+      if (it > 0 && hf == 0) {
+        // the previous item's output store (issued by this warp) must have read the staging box
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
+      ctl->xsum[hf][r] = l_run;
+      named_bar_sync(pair_bar, 64);
+      const float inv = 1.0f / (l_run + ctl->xsum[hf ^ 1][r]);
       {
-        uint32_t o0[32], o1[32];
-        tmem_ld_x32(t_o, o0);
-        tmem_ld_x32(t_o + 32, o1);
-        tmem_ld_wait_x32(o0);
-        tmem_ld_wait_x32(o1);
+        uint32_t o[32];
+        tmem_ld_x32(t_o, o);
+        tmem_ld_wait_x32(o);
         tc_fence_before();
-        if (it > 0) {
-          // the previous item's output store must have read this staging box
-          if (lane == 0) tma_store_wait_read();
-          __syncwarp();
-        }
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          sts_v4(stg + p_off(lane, g),
-                 pack_h2(__uint_as_float(o0[8 * g]) * inv, __uint_as_float(o0[8 * g + 1]) * inv),
-                 pack_h2(__uint_as_float(o0[8 * g + 2]) * inv, __uint_as_float(o0[8 * g + 3]) * inv),
-                 pack_h2(__uint_as_float(o0[8 * g + 4]) * inv, __uint_as_float(o0[8 * g + 5]) * inv),
-                 pack_h2(__uint_as_float(o0[8 * g + 6]) * inv, __uint_as_float(o0[8 * g + 7]) * inv));
-          sts_v4(stg + p_off(lane, 4 + g),
-                 pack_h2(__uint_as_float(o1[8 * g]) * inv, __uint_as_float(o1[8 * g + 1]) * inv),
-                 pack_h2(__uint_as_float(o1[8 * g + 2]) * inv, __uint_as_float(o1[8 * g + 3]) * inv),
-                 pack_h2(__uint_as_float(o1[8 * g + 4]) * inv, __uint_as_float(o1[8 * g + 5]) * inv),
-                 pack_h2(__uint_as_float(o1[8 * g + 6]) * inv, __uint_as_float(o1[8 * g + 7]) * inv));
-        }
+        for (int g = 0; g < 4; ++g)
+          sts_v4(stg + p_off(lane, hf * 4 + g),
+                 pack_h2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv),
+                 pack_h2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv),
+                 pack_h2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv),
+                 pack_h2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv));
       }
       fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_3d(&out_map, stg, h * kHd, qt * kTile + warp * 32, b);
+      named_bar_sync(pair_bar, 64);                      // both halves of the box are written (and xsum is read)
+      if (hf == 0 && lane == 0) {
+        tma_store_3d(&out_map, stg, h * kHd, qt * kTile + q * 32, b);
         tma_store_commit();
       }
     }
-    if (lane == 0) tma_store_wait_all();
+    if (hf == 0 && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == kSoftmaxWarps) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 }  // namespace
@@ -375,7 +381,7 @@ extern "C" int rz_attention(const void* qkv_f16, int n_images, int tokens, int h
   const long long items = (long long)n_images * heads * p.q_tiles;
   if (items * p.kv_tiles >= (1ll << 31)) return RZ_ERR_UNSUPPORTED;
   p.items = (int)items;
-  const long long resident = 2ll * rz_sm_count();      // two CTAs per SM (launch bounds, 113 KB smem each)
+  const long long resident = 2ll * rz_sm_count();      // two CTAs per SM (launch bounds, ~100 KB smem each)
   const long long ctas = items < resident ? items : resident;
   CUtensorMap qkv_map, out_map;
   if (!rz::make_map_3d_sw128(&qkv_map, qkv_f16, (uint64_t)n_images, (uint64_t)tokens, (uint64_t)3 * width,
