@@ -9,18 +9,18 @@
 // tiles of 128.  The kernel is persistent, two CTAs resident per SM (256 TMEM columns and ~113 KB of shared memory each) so
 // that one CTA's exponentials overlap the other's MMAs.
 //
-//   warp 4  TMA producer: Q once, then K / V tiles into two-stage rings (separate barriers: S can
-//           start as soon as K has landed)
-//   warp 5  MMA issuer (one elected lane): S = Q K^T (M 128, N 128, K 64) into TMEM, and
-//           O += P_j V_j (M 128, N 64, K 128; V tile read as an MN-major B operand) accumulated in
-//           TMEM over all key tiles -- S of tile j+1 is issued before waiting for P of tile j
-//   warps 0-3  softmax, one query row per thread (TMEM lane = row, no shuffles).  The 128 scores of
-//           the row are read from TMEM ONCE into registers (S is released to the MMA warp right
-//           away), reduced with FMNMX3, exponentiated in the log2 domain with packed FFMA2 / FADD2
-//           and written to shared memory as the fp16 K-major A operand.  The running reference
-//           maximum is LAZY (FlashAttention-4 style): it only moves when the tile maximum exceeds it
-//           by more than 2^8, so P <= 256 stays comfortably inside fp16 and the accumulator in TMEM
-//           is rescaled (tcgen05.ld / st by the row's own thread) only on those rare tiles.
+//   producer warp: lane 0 loads Q and the K tiles, lane 1 the V tiles, into two-stage rings
+//   MMA warp (one elected lane): S = Q K^T (M 128, N 128, K 64) into TMEM, and O += P_j V_j (M 128,
+//           N 64, K 128; P read from TMEM as the A operand, the V tile as an MN-major B operand)
+//           accumulated in TMEM over all key tiles -- S of tile j+1 is issued before waiting for P_j
+//   8 softmax warps, TWO threads per query row (warps w and w + 4 share the TMEM lane quarter w % 4
+//           and split the row's 128 keys 64 / 64).  A thread reads its 64 scores from TMEM ONCE (S is
+//           released to the MMA warp right away), reduces them with FMNMX3, exchanges the half maximum
+//           with its partner through shared memory, exponentiates in the log2 domain with packed
+//           FFMA2 / FADD2, packs the fp16 probabilities in place and stores them to TMEM.  The running
+//           reference maximum is LAZY (FlashAttention-4 style): it only moves when the tile maximum
+//           exceeds it by more than 2^8, so P <= 256 stays comfortably inside fp16 and the accumulator
+//           in TMEM is rescaled (tcgen05.ld / st by the row's own threads) only on those rare tiles.
 // Keys >= L of the last tile are masked to probability 0; rows >= L are zero-filled by the TMA
 // loads and clipped by the TMA store.
 #include "rz_common.cuh"
@@ -164,7 +164,10 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
   const uint32_t tmem_base = ctl->tmem_slot;
 
   if (warp == kSoftmaxWarps) {
-    if (elect_one()) {
+    // Two producer lanes with their own loops: lane 0 loads Q and the K tiles, lane 1 the V tiles.  (One
+    // thread doing K(j), V(j), K(j+1), ... in order would hold K(j+1) back until the P V product of
+    // tile j-2 has released its V stage, which leaves the next S = Q K^T about one TMA latency short.)
+    if (lane == 0) {
       int G = 0;
       for (int it = 0; it < my_items; ++it) {
         int b, h, qt;
@@ -174,11 +177,19 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
         tma_load_3d(&qkv_map, &ctl->q_full, q_s, h * kHd, qt * kTile, b, kEvictNormal);
         for (int j = 0; j < T; ++j, ++G) {
           const int st = G & 1;
-          const uint32_t ph = (uint32_t)((G >> 1) & 1);
-          mbar_wait_relaxed(&ctl->k_empty[st], ph ^ 1u);
+          mbar_wait_relaxed(&ctl->k_empty[st], (uint32_t)(((G >> 1) & 1) ^ 1));
           mbar_arrive_expect_tx(&ctl->k_full[st], kTileBytes);
           tma_load_3d(&qkv_map, &ctl->k_full[st], k_s + st * kTileBytes, width + h * kHd, j * kTile, b, kEvictNormal);
-          mbar_wait_relaxed(&ctl->v_empty[st], ph ^ 1u);
+        }
+      }
+    } else if (lane == 1) {
+      int G = 0;
+      for (int it = 0; it < my_items; ++it) {
+        int b, h, qt;
+        decode(it, b, h, qt);
+        for (int j = 0; j < T; ++j, ++G) {
+          const int st = G & 1;
+          mbar_wait_relaxed(&ctl->v_empty[st], (uint32_t)(((G >> 1) & 1) ^ 1));
           mbar_arrive_expect_tx(&ctl->v_full[st], kTileBytes);
           tma_load_3d(&qkv_map, &ctl->v_full[st], v_s + st * kTileBytes, 2 * width + h * kHd, j * kTile, b, kEvictNormal);
         }
@@ -195,7 +206,7 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
         const int st = G & 1, j = G % T, it = G / T;
         if (j == 0) mbar_wait(&ctl->q_full, (uint32_t)(it & 1));
         mbar_wait(&ctl->k_full[st], (uint32_t)((G >> 1) & 1));
-        mbar_wait_relaxed(&ctl->s_empty, (uint32_t)((G & 1) ^ 1));        // softmax has drained S of tile G-1
+        mbar_wait(&ctl->s_empty, (uint32_t)((G & 1) ^ 1));        // softmax has drained S of tile G-1
         tc_fence_after();
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4)
@@ -215,7 +226,7 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
         mbar_wait(&ctl->v_full[st], (uint32_t)((G >> 1) & 1));
         // P of this tile is ready; this also orders the rescale of O (and, for j == 0, the read-out of
         // the previous item's O by the softmax warps) before these MMAs
-        mbar_wait_relaxed(&ctl->p_full, (uint32_t)(G & 1));
+        mbar_wait(&ctl->p_full, (uint32_t)(G & 1));
         tc_fence_after();
 #pragma unroll
         for (int k8 = 0; k8 < 8; ++k8)
