@@ -23,6 +23,9 @@
 //           in TMEM is rescaled (tcgen05.ld / st by the row's own threads) only on those rare tiles.
 // Keys >= L of the last tile are masked to probability 0; rows >= L are zero-filled by the TMA
 // loads and clipped by the TMA store.
+#ifndef RZ_ATTN_EMU
+#define RZ_ATTN_EMU 2
+#endif
 #include "rz_common.cuh"
 #include "rz_tma.cuh"
 #include "rz_umma.cuh"
@@ -35,8 +38,10 @@ constexpr int kHd = 64;                    // head dim
 constexpr int kTile = 128;                 // query rows per CTA = keys per tile
 constexpr int kTileBytes = kTile * 128;    // 128 rows x 64 halfs
 constexpr int kSoftmaxWarps = 8;            // two per TMEM lane quarter: warp w and w + 4 split a row's 128 keys
-constexpr int kThreads = 32 * (kSoftmaxWarps + 2);
-constexpr int kTmemCols = 256;             // S [0,128)  O [128,192)  P [192,256) (fp16 pairs)
+constexpr int kGroupThreads = 32 * (kSoftmaxWarps + 2);   // one pipeline: 8 softmax warps + producer + MMA warp
+constexpr int kThreads = 2 * kGroupThreads;              // TWO independent pipelines (groups) per CTA, see below
+constexpr int kTmemCols = 256;             // per group: S [0,128)  O [128,192)  P [192,256) (fp16 pairs)
+constexpr int kEmuPeriod = 8, kEmuCount = RZ_ATTN_EMU;   // RZ_ATTN_EMU of every 8 pairs: exp2 on the FMA pipe
 constexpr float kLazy = 8.0f;              // log2 units: the reference maximum moves when exceeded by 2^8
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -54,7 +59,9 @@ struct Ctrl {
   float xsum[2][kTile];        // [half][row]: ... and their half row sums at the end of an item
 };
 
-constexpr int kSmem = 5 * kTileBytes + kTileBytes + 4096;   // Q, K x2, V x2, output staging (4 x 4 KB), Ctrl
+constexpr int kGroupSmem = 5 * kTileBytes + kTileBytes + 4096;   // Q, K x2, V x2, output staging (4 x 4 KB), Ctrl
+constexpr int kSmem = 2 * kGroupSmem;
+constexpr int kPingPongBar = 9;             // named barriers 9, 10: the groups take turns in the exponential phase
 static_assert(sizeof(Ctrl) <= 4096, "control block");
 
 __device__ __forceinline__ uint32_t p_off(int row, int chunk) {
@@ -105,6 +112,50 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* r) {
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// mbarrier wait of the softmax warps: a try_wait with a short suspend-time hint parks the warp in
+// hardware instead of re-polling through the MIO queue, which the other group's MUFU instructions share
+__device__ __forceinline__ void mbar_wait_soft(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_hint(bar, parity, 128u)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+// 2^x for a PAIR of arguments (x <= 8) on the FMA / ALU pipes instead of the MUFU: Cody-Waite split
+// x = n + f (round to nearest through the 1.5 * 2^23 magic add, f in [-0.5, 0.5]), a degree-3 minimax
+// polynomial for 2^f (relative error 7.5e-5, below the fp16 rounding of the probabilities) and n added
+// into the exponent field with one integer multiply-add.  The MUFU-bound exponential phase also floods
+// the MIO queue that the TMEM loads / stores and barrier polls of the other warps go through, so moving
+// part of the exponentials off the MUFU shortens both phases (FlashAttention-4 does the same).
+__device__ __forceinline__ void exp2_pair_fma(float& x0, float& x1) {
+  const float kMagic = 12582912.0f;                   // 1.5 * 2^23
+  x0 = fmaxf(x0, -126.0f);                            // masked keys carry -inf
+  x1 = fmaxf(x1, -126.0f);
+  float t0 = x0, t1 = x1, n0, n1;
+  fadd2(t0, t1, kMagic, kMagic);                      // integer part in the low mantissa bits
+  n0 = t0; n1 = t1;
+  fadd2(n0, n1, -kMagic, -kMagic);
+  float f0, f1;
+  ffma2(f0, f1, n0, n1, -1.0f, 0.f);                  // -n
+  fadd2(f0, f1, x0, x1);                              // f = x - n
+  float p0, p1;
+  ffma2(p0, p1, f0, f1, 0.05517083778977394f, 0.24260935187339783f);
+  {
+    uint64_t P, F, C, D;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(P) : "f"(p0), "f"(p1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(F) : "f"(f0), "f"(f1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(C) : "f"(0.6932609677314758f));
+    asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(D) : "l"(P), "l"(F), "l"(C));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(C) : "f"(0.9999281764030457f));
+    asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(P) : "l"(D), "l"(F), "l"(C));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(p0), "=f"(p1) : "l"(P));
+  }
+  x0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  x1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
 __device__ __forceinline__ void tmem_ld_wait_x16(uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
@@ -114,31 +165,46 @@ __device__ __forceinline__ void tmem_ld_wait_x16(uint32_t (&r)[16]) {
                : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__ CUtensorMap out_map,
             const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
-  uint8_t* q_s = smem;
+  // One CTA per SM holds TWO complete pipelines ("groups" of 10 warps, each with its own shared memory,
+  // barriers and 256 TMEM columns) working on two different items.  Being in one CTA lets them take
+  // turns: named barriers 9 / 10 let only one group at a time run its exponential phase (MUFU-bound),
+  // while the other does its latency-bound part (P store, wait for S, TMEM load, maximum, exchange) --
+  // the FlashAttention-3 ping-pong.  As two independent CTAs per SM the phases drifted into each other
+  // and the MUFU pipe idled 40 % of the time.
+  const int grp = (int)threadIdx.x / kGroupThreads;
+  const int tid = (int)threadIdx.x % kGroupThreads, warp = tid >> 5, lane = tid & 31;
+  uint8_t* gbase = smem + grp * kGroupSmem;
+  uint8_t* q_s = gbase;
   uint8_t* k_s = q_s + kTileBytes;
   uint8_t* v_s = k_s + 2 * kTileBytes;
   uint8_t* p_s = v_s + 2 * kTileBytes;
   Ctrl* ctl = reinterpret_cast<Ctrl*>(p_s + kTileBytes);
+  Ctrl* ctl0 = reinterpret_cast<Ctrl*>(smem + 6 * kTileBytes);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int T = p.kv_tiles;
   const int width = p.H * kHd;
-  // PERSISTENT: this CTA walks items blockIdx.x, blockIdx.x + gridDim.x, ... (query tile fastest, so
-  // the CTAs resident at one time share their K / V in L2); every pipeline barrier keeps counting
+  // PERSISTENT: CTA c walks item PAIRS c, c + gridDim.x, ...; group g takes item 2 * pair + g (the two
+  // items are neighbouring query tiles, so they share their K / V in L2).  Both groups always run the
+  // same number of items -- an odd item count gives group 1 a duplicate of the last item whose output
+  // is not stored -- which keeps the ping-pong barriers balanced.  Every pipeline barrier keeps counting
   // across items (G = running key-tile index, it = running item index), so the next item's Q load
   // and first S = Q K^T overlap the softmax of this item's last tile and its output store.
-  const int my_items = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_pairs = (p.items + 1) / 2;
+  const int my_items = (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   auto decode = [&](int it, int& b, int& h, int& qt) {
-    const int item = (int)blockIdx.x + it * (int)gridDim.x;
+    int item = 2 * ((int)blockIdx.x + it * (int)gridDim.x) + grp;
+    const bool real = item < p.items;
+    if (!real) item = p.items - 1;
     qt = item % p.q_tiles;
     const int bh = item / p.q_tiles;
     h = bh % p.H;
     b = bh / p.H;
+    return real;
   };
 
   if (tid == 0) {
@@ -154,14 +220,15 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
     mbar_init(&ctl->p_full, 32 * kSoftmaxWarps);
     fence_barrier_init();
   }
-  if (warp == kSoftmaxWarps) {
+  if (warp == kSoftmaxWarps && grp == 0) {
     if (lane == 0) { prefetch_tmap(&qkv_map); prefetch_tmap(&out_map); }
-    tmem_alloc(&ctl->tmem_slot, kTmemCols);
+    tmem_alloc(&ctl0->tmem_slot, 2 * kTmemCols);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = ctl->tmem_slot;
+  const uint32_t tmem_all = ctl0->tmem_slot;
+  const uint32_t tmem_base = tmem_all + grp * kTmemCols;
 
   if (warp == kSoftmaxWarps) {
     // Two producer lanes with their own loops: lane 0 loads Q and the K tiles, lane 1 the V tiles.  (One
@@ -244,23 +311,26 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
     // Four softmax warps per scheduler instead of two is what keeps the MUFU pipe fed: with one
     // thread per row the exponential phase of one warp could not cover the latency-bound phase
     // (TMEM load, maximum, P store) of the only other one.
-    const int q = warp & 3, hf = warp >> 2;
+    // the TMEM lane quarter a warp may touch is fixed by its CTA-level warp id (group 1 starts at warp 10)
+    const int q = ((int)threadIdx.x >> 5) & 3, hf = warp >> 2;
     const int r = q * 32 + lane;                        // query row of this thread = TMEM lane
-    const int pair_bar = 1 + q;                         // named barrier of the row's two warps (64 threads)
+    const int pair_bar = 1 + q + 4 * grp;               // named barrier of the row's two warps (64 threads)
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t t_s = t_lane + hf * 64;              // this thread's 64 score columns
     const uint32_t t_o = t_lane + 128 + hf * 32;        // ... 32 accumulator columns
     const uint32_t t_p = t_lane + 192 + hf * 32;        // ... 32 packed probability columns (64 keys)
     const uint32_t stg = smem_u32(p_s) + (uint32_t)(q * 4096);   // output staging box of the quarter
+    const int n_phases = my_items * T;                  // the same in both groups
+    if (grp == 1 && n_phases > 0) named_bar_arrive(kPingPongBar, 512);     // group 0 goes first
     int G = 0;
     for (int it = 0; it < my_items; ++it) {
       int b, h, qt;
-      decode(it, b, h, qt);
+      const bool real = decode(it, b, h, qt);
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < T; ++j, ++G) {
         const int valid = min(kTile, p.L - j * kTile) - hf * 64;    // real keys among this thread's 64
         uint32_t v[2][32];
-        mbar_wait(&ctl->s_full, (uint32_t)(G & 1));
+        mbar_wait_soft(&ctl->s_full, (uint32_t)(G & 1));
         tc_fence_after();
         tmem_ld_x32(t_s, v[0]);
         tmem_ld_x32(t_s + 32, v[1]);
@@ -295,7 +365,9 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
           alpha = exp2f(m_run - mxs);                    // 0 for the first tile
           m_run = mxs;
         }
-        // exponentials -> fp16 pairs, packed IN PLACE (pair i of chunk c lands in v[c][i / 2])
+        // exponentials -> fp16 pairs, packed IN PLACE (pair i of chunk c lands in v[c][i / 2]).
+        // Only one group at a time is in this MUFU-bound phase.
+        named_bar_sync(kPingPongBar + grp, 512);
         float rs[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) rs[k] = 0.f;
@@ -306,15 +378,20 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
           for (int i = 0; i < 32; i += 2) {
             float e0, e1;
             ffma2(e0, e1, __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]), kLog2e, nm);
-            e0 = exp2f(e0);
-            e1 = exp2f(e1);
+            if (((i >> 1) % kEmuPeriod) < kEmuCount) {   // this share of the pairs bypasses the MUFU
+              exp2_pair_fma(e0, e1);
+            } else {
+              e0 = exp2f(e0);
+              e1 = exp2f(e1);
+            }
             fadd2(rs[i & 2], rs[(i & 2) + 1], e0, e1);
             v[c][i >> 1] = pack_h2(e0, e1);
           }
         }
+        if (!(grp == 1 && G == n_phases - 1)) named_bar_arrive(kPingPongBar + (grp ^ 1), 512);   // the other group's turn
         if (j > 0) {
           // the MMAs of tile j-1 must be done before P (single buffer) is overwritten / O is rescaled
-          mbar_wait(&ctl->o_full, (uint32_t)((G - 1) & 1));
+          mbar_wait_soft(&ctl->o_full, (uint32_t)((G - 1) & 1));
           tc_fence_after();
         }
         if (j > 0 && __any_sync(0xffffffffu, need)) {
@@ -339,7 +416,7 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
         l_run = fmaf(l_run, alpha, (rs[0] + rs[1]) + (rs[2] + rs[3]));
       }
       // all MMAs of the item done: normalise, fp16, TMA store through the quarter's staging box
-      mbar_wait(&ctl->o_full, (uint32_t)((G - 1) & 1));
+      mbar_wait_soft(&ctl->o_full, (uint32_t)((G - 1) & 1));
       tc_fence_after();
       if (it > 0 && hf == 0) {
         // the previous item's output store (issued by this warp) must have read the staging box
@@ -364,7 +441,7 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
       }
       fence_proxy_async_smem();
       named_bar_sync(pair_bar, 64);                      // both halves of the box are written (and xsum is read)
-      if (hf == 0 && lane == 0) {
+      if (hf == 0 && lane == 0 && real) {
         tma_store_3d(&out_map, stg, h * kHd, qt * kTile + q * 32, b);
         tma_store_commit();
       }
@@ -373,7 +450,7 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kSoftmaxWarps) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == kSoftmaxWarps && grp == 0) tmem_dealloc(tmem_all, 2 * kTmemCols);
 }
 
 }  // namespace
@@ -392,8 +469,8 @@ extern "C" int rz_attention(const void* qkv_f16, int n_images, int tokens, int h
   const long long items = (long long)n_images * heads * p.q_tiles;
   if (items * p.kv_tiles >= (1ll << 31)) return RZ_ERR_UNSUPPORTED;
   p.items = (int)items;
-  const long long resident = 2ll * rz_sm_count();      // two CTAs per SM (launch bounds, ~100 KB smem each)
-  const long long ctas = items < resident ? items : resident;
+  const long long pairs = (items + 1) / 2;              // a CTA works on two items at a time (one per group)
+  const long long ctas = pairs < rz_sm_count() ? pairs : rz_sm_count();
   CUtensorMap qkv_map, out_map;
   if (!rz::make_map_3d_sw128(&qkv_map, qkv_f16, (uint64_t)n_images, (uint64_t)tokens, (uint64_t)3 * width,
                              (uint64_t)3 * width * 2, (uint64_t)tokens * 3 * width * 2, kTile))
