@@ -64,18 +64,23 @@ def pack_layer(layer: nn.Module, device=None) -> Dict[str, torch.Tensor]:
     }
 
 
-def layer_forward(x: torch.Tensor, w: Dict[str, torch.Tensor]) -> torch.Tensor:
-    """One Dinov2Layer on the fp32 residual stream ``x`` (B, L, 768), updated IN PLACE."""
+def layer_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One Dinov2Layer on the fp32 residual stream ``x`` (B, L, 768).
+
+    ``out`` None: ``x`` is updated in place.  Otherwise ``x`` is only read and the new residual stream
+    is written to ``out`` (the first residual GEMM goes out of place, which is how the caller's tokens
+    stay untouched without a copy)."""
     B, L, D = x.shape
     x2 = x.view(B * L, D)
+    y2 = x2 if out is None else out.view(B * L, D)
     h = ops.ln_rows(x2, w["g1"], w["b1"], w["eps1"])
     qkv = ops.linear(h, w["wqkv"], w["bqkv"], "bias")
     a = ops.attention(qkv.view(B, L, 3 * D), w["heads"])
-    ops.linear(a.view(B * L, D), w["wo"], w["bo"], "residual", scale=w["ls1"], residual=x2, out=x2)
-    h = ops.ln_rows(x2, w["g2"], w["b2"], w["eps2"])
+    ops.linear(a.view(B * L, D), w["wo"], w["bo"], "residual", scale=w["ls1"], residual=x2, out=y2)
+    h = ops.ln_rows(y2, w["g2"], w["b2"], w["eps2"])
     g = ops.linear(h, w["w1"], w["bf1"], "gelu")
-    ops.linear(g, w["w2"], w["bf2"], "residual", scale=w["ls2"], residual=x2, out=x2)
-    return x
+    ops.linear(g, w["w2"], w["bf2"], "residual", scale=w["ls2"], residual=y2, out=y2)
+    return x if out is None else out
 
 
 class AlignTransformer(nn.Module):
@@ -128,14 +133,19 @@ class AlignTransformer(nn.Module):
         if vision_tokens.dim() != 3 or vision_tokens.shape[-1] != ops.HIDDEN:
             raise RzError("vision tokens must be (B, L, 768)")
         x = vision_tokens.detach()
-        if inplace and x.dtype == torch.float32 and x.is_contiguous():
-            pass                                                  # the fp32 residual stream IS the input
-        else:
-            x = x.to(torch.float32).contiguous()
-            if x.data_ptr() == vision_tokens.data_ptr():
-                x = x.clone()
-        for w in self._weights(x.device):
-            layer_forward(x, w)
+        layers = self._weights(x.device)
+        fresh = None
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.to(torch.float32).contiguous()                  # already a private copy
+        elif not inplace and layers:
+            fresh = torch.empty_like(x)                           # first layer writes here: no copy of the input
+        elif not inplace:
+            x = x.clone()
+        for i, w in enumerate(layers):
+            if i == 0 and fresh is not None:
+                x = layer_forward(x, w, out=fresh)
+            else:
+                layer_forward(x, w)
         if self.layer_norm is not None:
             # use_layer_norm=True (not the released configuration): one more row LayerNorm, fp32 out
             g, b = self.layer_norm.weight.detach(), self.layer_norm.bias.detach()

@@ -93,9 +93,10 @@ struct Lin : PolicyBase {
   // [32 rows x 32 cols] fp32 boxes (residual in by TMA, result out by TMA from the same box) plus
   // one mbarrier per box
   static constexpr int kWarpStage = EPI == RZ_LIN_RESIDUAL ? 16384 : 8192;
-  // the fp16 epilogues (bias add, GELU) are bound by the instruction issue of their warps: eight
-  // epilogue warps, two per TMEM lane quarter, each taking one 128-column half of the tile
-  static constexpr int kEpiWarps = EPI == RZ_LIN_RESIDUAL ? 4 : 8;
+  // the GELU epilogue is bound by the instruction issue of its warps: eight epilogue warps, two per
+  // TMEM lane quarter, each taking one 128-column half of the tile (fc1 1.51 -> 1.41 ms); the plain
+  // bias epilogue is not, and the extra warps cost it tensor-pipe time (90 % -> 81 % active)
+  static constexpr int kEpiWarps = EPI == RZ_LIN_GELU ? 8 : 4;
   static constexpr int kEpiSmem = kEpiWarps * kWarpStage + (EPI == RZ_LIN_RESIDUAL ? 128 : 0);
   struct State { uint32_t g; int ready; };     // g: 32-column boxes this warp has consumed so far
   __host__ __device__ static int num_tiles(const Params& p) { return p.m_tiles * p.n_tiles; }
@@ -238,15 +239,21 @@ struct Lin : PolicyBase {
     const uint32_t stg = smem_u32(epi_smem) + warp * kWarpStage;
     Cols64 va, vb;
     if (EPI != RZ_LIN_RESIDUAL) {
-      // eight warps: warp w takes columns [128 * (w / 4), + 128) of the tile
-      const int c0 = (warp >> 2) * 2;
-      const int col = nt * kBN + c0 * 64;
+      // warp w takes 64-column chunks [c0, c0 + kChunks) of the tile: all four with 4 epilogue warps,
+      // one 128-column half with 8
+      constexpr int kChunks = 16 / kEpiWarps;
+      const int c0 = (warp >> 2) * kChunks;
       ld64(taddr + c0 * 64, va);
-      wait64(va);
-      ld64(taddr + (c0 + 1) * 64, vb);
-      chunk_f16(p, maps, va, col, row0, lane, stg);
-      wait64(vb);
-      chunk_f16(p, maps, vb, col + 64, row0, lane, stg + 4096);
+#pragma unroll 1
+      for (int c = c0; c < c0 + kChunks; c += 2) {
+        const int col = nt * kBN + c * 64;
+        wait64(va);
+        ld64(taddr + (c + 1) * 64, vb);
+        chunk_f16(p, maps, va, col, row0, lane, stg);
+        wait64(vb);
+        if (c + 2 < c0 + kChunks) ld64(taddr + (c + 2) * 64, va);
+        chunk_f16(p, maps, vb, col + 64, row0, lane, stg + 4096);
+      }
       return;
     }
     ld64(taddr, va);
