@@ -438,6 +438,8 @@ def ln_rows(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float
         raise RzError(f"ln_rows needs (..., {HIDDEN}) fp32/bf16/fp16 rows, got {tuple(x.shape)} {x.dtype}")
     x2 = _contig(x).view(-1, HIDDEN)
     out = torch.empty(x2.shape, dtype=torch.float16, device=x.device)
+    if x2.shape[0] == 0:
+        return out.view(x.shape)
     rc = _lib.load().rz_ln_rows(_p(x2), _DTYPES[x.dtype], _p(_contig(gamma.float())), _p(_contig(beta.float())),
                                 float(eps), x2.shape[0], _p(out), _stream())
     _lib.check(rc, "rz_ln_rows")
@@ -475,6 +477,8 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilo
         out = torch.empty((m, n), dtype=odt, device=a.device)
     elif out.dtype != odt or tuple(out.shape) != (m, n) or not out.is_contiguous():
         raise RzError(f"out must be contiguous {odt} ({m}, {n})")
+    if m == 0:
+        return out
     rc = _lib.load().rz_linear(_p(a), m, k, _p(w), n, _p(bias), ep, _p(scale), _p(residual), _p(out), _stream())
     _lib.check(rc, "rz_linear")
     return out
@@ -488,6 +492,8 @@ def attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
         raise RzError("qkv must be contiguous fp16 (B, L, 3 * heads * 64)")
     B, L, _ = qkv.shape
     out = torch.empty((B, L, heads * 64), dtype=torch.float16, device=qkv.device)
+    if B == 0 or L == 0:
+        return out
     rc = _lib.load().rz_attention(_p(qkv), B, L, heads, _p(out), _stream())
     _lib.check(rc, "rz_attention")
     return out
@@ -513,6 +519,8 @@ def text_pool(hidden: torch.Tensor, attention_mask: torch.Tensor, gamma: Optiona
     b = _contig(beta.detach().float()) if beta is not None else None
     feats = torch.empty((n, HIDDEN), dtype=torch.float32, device=h.device) if want_feats else None
     q16 = torch.empty((n, HIDDEN), dtype=torch.float16, device=h.device) if want_q16 else None
+    if n == 0:
+        return feats, q16
     rc = _lib.load().rz_text_pool(_p(h), _DTYPES[h.dtype], _p(m), n, t, _p(g), _p(b), 1 if l2 else 0,
                                   _p(feats), _p(q16), _stream())
     _lib.check(rc, "rz_text_pool")

@@ -223,3 +223,41 @@ def test_model_vision_tokens_match_stock_modules():
     kg = orc.l2_normalize_rows(orc.layer_norm_rows(got.double(), g, b))
     kw = orc.l2_normalize_rows(orc.layer_norm_rows(want.double(), g, b))
     assert (kg @ q.T - kw @ q.T).abs().max().item() <= 2e-3
+
+
+def test_empty_inputs_and_validation():
+    """Empty batches return empty outputs; malformed operands raise instead of launching."""
+    from radzero_b200._lib import RzError
+    g = torch.ones(768, device=DEV)
+    assert ops.ln_rows(torch.empty(0, 768, device=DEV), g, g, 1e-6).shape == (0, 768)
+    w = torch.zeros(768, 768, device=DEV, dtype=torch.float16)
+    assert ops.linear(torch.empty(0, 768, device=DEV, dtype=torch.float16), w, None).shape == (0, 768)
+    assert ops.attention(torch.empty(0, 5, 2304, device=DEV, dtype=torch.float16), 12).shape == (0, 5, 768)
+    f, q = ops.text_pool(torch.empty(0, 4, 768, device=DEV), torch.empty(0, 4, device=DEV, dtype=torch.int64), g, g)
+    assert f.shape == (0, 768) and q.shape == (0, 768)
+    assert AlignTransformer(synthetic.build_align_encoder(seed=1, layers=1, device=DEV)).eval()(
+        torch.empty(0, 7, 768, device=DEV)).shape == (0, 7, 768)
+    with pytest.raises(RzError):
+        ops.linear(torch.zeros(4, 100, device=DEV, dtype=torch.float16),
+                   torch.zeros(256, 100, device=DEV, dtype=torch.float16), None)       # K % 64 != 0
+    with pytest.raises(RzError):
+        ops.linear(torch.zeros(4, 64, device=DEV, dtype=torch.float16),
+                   torch.zeros(100, 64, device=DEV, dtype=torch.float16), None)        # N % 256 != 0
+    with pytest.raises(RzError):
+        ops.linear(torch.zeros(4, 64, device=DEV), torch.zeros(256, 64, device=DEV), None)   # fp32 operands
+    with pytest.raises(RzError):
+        ops.attention(torch.zeros(1, 4, 2304, device=DEV, dtype=torch.float16), 11)    # width != 3 * heads * 64
+    with pytest.raises(RzError):
+        ops.linear(torch.zeros(4, 64, device=DEV, dtype=torch.float16),
+                   torch.zeros(256, 64, device=DEV, dtype=torch.float16), None, "residual")  # no residual given
+
+
+def test_attention_many_items_odd_count():
+    """An odd number of (image, head, query tile) items: the second pipeline of the last CTA runs a
+    duplicate item whose output must not be stored; and more item pairs than SMs (persistent loop)."""
+    for B, L, heads in [(1, 100, 1), (1, 300, 1), (3, 300, 1), (13, 300, 12)]:
+        torch.manual_seed(B * L)
+        qkv = (torch.randn(B, L, 3 * heads * 64, device=DEV) * 0.7).half()
+        got = ops.attention(qkv, heads).double()
+        want = _attn_ref(qkv, heads)
+        assert (got - want).abs().max().item() <= 3e-3, (B, L, heads)
