@@ -105,15 +105,6 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-// mbarrier wait of the softmax warps: a try_wait with a short suspend-time hint parks the warp in
-// hardware instead of re-polling through the MIO queue, which the other group's MUFU instructions share
-__device__ __forceinline__ void mbar_wait_soft(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_hint(bar, parity, 128u)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
-  }
-}
 // 2^x for a PAIR of arguments (x <= 8) on the FMA / ALU pipes instead of the MUFU: Cody-Waite split
 // x = n + f (round to nearest through the 1.5 * 2^23 magic add, f in [-0.5, 0.5]), a degree-3 minimax
 // polynomial for 2^f (relative error 7.5e-5, below the fp16 rounding of the probabilities) and n added

@@ -79,6 +79,16 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
     if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
+// Wait with a SHORT suspend-time hint: the warp is parked in hardware between polls instead of
+// re-issuing try_wait through the MIO queue (which LDS / STS / MUFU / tcgen05.ld of the other warps
+// share), yet wakes within ~0.1 us of the phase completing.  For consumer warps that wait often.
+__device__ __forceinline__ void mbar_wait_soft(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_hint(bar, parity, 128u)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
 // Warp-uniform waits: one lane waits on the barrier, the rest of the warp parks at the
 // __syncwarp (keeps 31 lanes per warp from polling shared memory through the LSU).
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
