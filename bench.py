@@ -370,6 +370,15 @@ def run_ours(args):
             contrastive = bench_contrastive.run(args, world, rank, local, pk, steps=3, warmup=3)
         except Exception as e:  # never lose the main line to the add-on
             contrastive = {"error": repr(e)}
+    # the widened row rides along the same way: AlignTransformer + similarity_prob
+    upstream = None
+    if args.workload == "cls" and not args.no_align:
+        torch.cuda.empty_cache()
+        try:
+            from radzero_b200 import bench_align
+            upstream = bench_align.run(args, world, rank, local, pk, steps=5, warmup=3)
+        except Exception as e:
+            upstream = {"error": repr(e)}
     if rank == 0:
         line = {
             "metric": "similarity maps/sec", "value": value, "unit": "maps/s", "n_gpus": world,
@@ -380,7 +389,7 @@ def run_ours(args):
                        "input_dtype": "fp32", "l2": "inputs (1.08 GB/GPU at cls) larger than L2; no flush",
                        "parallelism": f"images sharded x{world}, no collective"},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
-            "cpu_baseline": cpu, "contrastive": contrastive,
+            "cpu_baseline": cpu, "contrastive": contrastive, "upstream_align": upstream,
         }
         print(json.dumps(line))
     if world > 1:
@@ -479,6 +488,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cls", choices=list(WORKLOADS) + ["contrastive", "align"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-align", action="store_true",
+                    help="skip the AlignTransformer add-on of the default workload")
     ap.add_argument("--no-contrastive", action="store_true",
                     help="skip the contrastive-step add-on of the default workload")
     args = ap.parse_args()
