@@ -261,3 +261,18 @@ def test_attention_many_items_odd_count():
         got = ops.attention(qkv, heads).double()
         want = _attn_ref(qkv, heads)
         assert (got - want).abs().max().item() <= 3e-3, (B, L, heads)
+
+
+@pytest.mark.parametrize("scale", [0.05, 2.0, 5.0])
+def test_attention_score_ranges(scale):
+    """Near-uniform, peaked and almost one-hot softmax rows (|scores| up to ~150): the lazy maximum, the
+    -126 clamp of the emulated exp2 and the fp16 probabilities must hold over the whole range."""
+    torch.manual_seed(int(scale * 100))
+    B, L, heads = 2, 700, 4
+    qkv = torch.randn(B, L, 3 * heads * 64, device=DEV)
+    qkv[..., : 2 * heads * 64] *= scale
+    qkv = qkv.half()
+    got = ops.attention(qkv, heads).double()
+    want = _attn_ref(qkv, heads)
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max().item() <= 4e-3, (got - want).abs().max().item()
