@@ -210,6 +210,9 @@ class RadZeroLoss(nn.Module):
         # the attribute CxrAlignModel.compute_logits reads (modeling.py:320) but the
         # reference's __init__ never sets; False = released behaviour
         self.compute_i2t_loss = False
+        # one text-model call for all sentences of the local batch instead of one per image
+        self.batch_text_calls = bool(kwargs.get("batch_text_calls", True))
+        self.text_pad_token_id = int(kwargs.get("text_pad_token_id", 1))      # MPNet / RoBERTa <pad>
 
     # -- helpers -------------------------------------------------------------------------
     def _ln(self):
@@ -227,11 +230,45 @@ class RadZeroLoss(nn.Module):
             return 1.0 / math.sqrt(self.hidden_dim)
         raise NotImplementedError
 
+    @staticmethod
+    def _merge_encodings(key_phrases, pad_token_id: int = 1):
+        """The per-image tokenised sentence batches (dataset.py:172-181: ``input_ids (n_i, T_i)``,
+        ``attention_mask (n_i, T_i)``) as ONE padded batch, or None when they are not plain tensors.
+        Padding positions carry ``attention_mask`` 0, so they take no part in attention or pooling."""
+        try:
+            ids = [kp["input_ids"] for kp in key_phrases]
+            ams = [kp["attention_mask"] for kp in key_phrases]
+        except (KeyError, TypeError, IndexError):
+            return None
+        if not ids or not all(torch.is_tensor(t) and t.dim() == 2 for t in ids + ams):
+            return None
+        if any(set(kp.keys()) - {"input_ids", "attention_mask"} for kp in key_phrases if hasattr(kp, "keys")):
+            return None                               # token_type_ids etc.: keep the reference's call pattern
+        t_max = max(t.shape[1] for t in ids)
+        pad = lambda t, v: t if t.shape[1] == t_max else torch.nn.functional.pad(t, (0, t_max - t.shape[1]), value=v)
+        return {"input_ids": torch.cat([pad(t, pad_token_id) for t in ids], dim=0),
+                "attention_mask": torch.cat([pad(t, 0) for t in ams], dim=0)}, [int(t.shape[0]) for t in ids]
+
     def collect_text_features(self, key_phrases, forward_text_model, rank: int = 0):
-        """Raw (pre-LayerNorm) sentence embeddings + group_map, losses.py:126-153."""
+        """Raw (pre-LayerNorm) sentence embeddings + group_map, losses.py:126-153.
+
+        The reference calls the text model once per image (B_local sequential calls, :135-151).  With
+        ``batch_text_calls`` (default) the per-image token batches are merged into one padded batch and
+        the text model runs ONCE; rows are independent, so the features
+        are the same.  Inputs that are not plain ``input_ids`` / ``attention_mask`` tensors fall back
+        to the reference's call pattern."""
+        b_local = len(key_phrases)
+        merged = self._merge_encodings(key_phrases, self.text_pad_token_id) if self.batch_text_calls else None
+        if merged is not None:
+            enc, counts = merged
+            f = forward_text_model(enc)
+            feat = f["text_features"] if self.text_features_l2_norm else f["text_features_wo_l2_norm"]
+            if feat.shape[-1] == 2 * self.hidden_dim:
+                feat = feat[:, self.hidden_dim:]
+            group = [i + rank * b_local for i, c in enumerate(counts) for _ in range(c)]
+            return feat, torch.tensor(group, device=feat.device, dtype=torch.int64)
         feats: List[torch.Tensor] = []
         group: List[int] = []
-        b_local = len(key_phrases)
         for i, kp in enumerate(key_phrases):
             f = forward_text_model(kp)
             feat = f["text_features"] if self.text_features_l2_norm else f["text_features_wo_l2_norm"]
