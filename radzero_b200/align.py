@@ -91,15 +91,25 @@ class AlignTransformer(nn.Module):
         self.transformer_layers = transformer_layers     # transformers Dinov2Encoder (weights only)
         self.layer_norm = layer_norm
         self._packed: Optional[List[Dict[str, torch.Tensor]]] = None
+        self._packed_stamp = None
 
     def refresh(self) -> None:
-        """Drop the packed fp16 operands (call after loading / changing the weights)."""
+        """Drop the packed fp16 operands.  Not normally needed: in-place weight changes (load_state_dict,
+        optimizer steps) are detected through the parameters' version counters."""
         self._packed = None
 
+    def _stamp(self):
+        # (identity, in-place version) of every parameter: load_state_dict / optimizer steps bump versions
+        return tuple((id(p), p._version) for p in self.parameters())
+
     def _weights(self, device) -> List[Dict[str, torch.Tensor]]:
-        if self._packed is None or (self._packed and self._packed[0]["wo"].device != device):
+        stamp = self._stamp()
+        stale = self._packed is None or self._packed_stamp != stamp or (
+            self._packed and self._packed[0]["wo"].device != device)
+        if stale:
             layers = [] if self.transformer_layers is None else list(self.transformer_layers.layer)
             self._packed = [pack_layer(l, device) for l in layers]
+            self._packed_stamp = stamp
         return self._packed
 
     def stock_forward(self, vision_tokens: torch.Tensor) -> torch.Tensor:
