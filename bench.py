@@ -133,7 +133,7 @@ def run_ours(args):
         out.update({"higher_is_better": True, "vs_baseline": None, "data": "synthetic", "impl": "ours",
                     "cpu_baseline": None})
         if rank == 0 and world == 1 and not args.no_cpu:
-            dt, pairs = bench_contrastive.cpu_sample_step(16)
+            dt, pairs = contrastive_cpu_sample_step(16)
             full = bench_contrastive.B_GLOBAL * sum(synthetic.sentence_counts(bench_contrastive.B_GLOBAL, seed=42))
             out["cpu_baseline"] = {"value": pairs / dt / full, "unit": "steps/s", "cores": os.cpu_count(),
                                    "kind": "port", "sample": f"fwd+bwd at 16 images x {pairs // 16} sentences on the "
@@ -154,7 +154,7 @@ def run_ours(args):
                     "cpu_baseline": None})
         if rank == 0 and world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            dt = bench_align.cpu_step_sample(8, cores)
+            dt = align_cpu_step_sample(8, cores)
             out["cpu_baseline"] = {"value": 8 * bench_align.N / dt, "unit": "maps/s", "cores": cores, "kind": "port",
                                    "sample": f"8 of the {bench_align.B} images x {bench_align.N} prompts (fp32 torch CPU "
                                    f"oracle: oracle/align.py + oracle/vlcabs.py), best of 2, {dt * 1e3:.0f} ms"}
@@ -437,16 +437,106 @@ def cpu_baseline(workload: str, steps: int = 1, warmup: int = 1):
                       f"(oracle/vlcabs.py), best of {max(steps, 1)}, {best * 1e3:.1f} ms"}
 
 
+# --- CPU arms of the add-on workloads.  They live HERE (not in the radzero_b200 package) because only
+# bench.py's cpu_baseline / --impl reference legs, tests/ and smoke() may execute anything under oracle/.
+def contrastive_cpu_sample_step(b_g=16):
+    """Scaled-down CPU step on the oracle (the reference materialises (B,N,L) tensors: the full
+    size does not fit host memory)."""
+    import oracle
+    from radzero_b200 import synthetic
+    counts = synthetic.sentence_counts(b_g, seed=42)
+    n = sum(counts)
+    tok, text, gamma, beta, log_tau = synthetic.make_inputs(b_g, n, seed=1000)
+    gm = synthetic.group_map_from_counts(counts)
+    t0 = time.perf_counter()
+    oracle.contrastive_step_reference(text, gm, tok, gamma, beta, log_tau)
+    dt = time.perf_counter() - t0
+    return dt, b_g * n
+
+
+def contrastive_run_reference(args):
+    from radzero_b200 import bench_contrastive, synthetic
+    B_GLOBAL = bench_contrastive.B_GLOBAL
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_total = sum(synthetic.sentence_counts(B_GLOBAL, seed=42))
+    contrastive_cpu_sample_step(8)
+    t0 = time.perf_counter()
+    pairs = 0
+    for _ in range(args.steps):
+        dt, pr = contrastive_cpu_sample_step(16)
+        pairs += pr
+    dt = time.perf_counter() - t0
+    full_pairs = B_GLOBAL * n_total
+    value = (pairs / dt) / full_pairs
+    print(json.dumps({
+        "metric": "contrastive steps/sec", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": 1, "ms_per_step": 1e3 / value, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"C4 contrastive step, {B_GLOBAL} images x {n_total} sentences"},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": "each step = forward+backward at 16 images x ~96 sentences on the fp32 "
+                                   "torch CPU oracle; steps/s extrapolated by the (image, sentence) pair count "
+                                   f"to {B_GLOBAL} x {n_total}"},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def align_cpu_step_sample(b: int = 8, threads=None):
+    """The CPU oracle (oracle/align.py + oracle/vlcabs.py, fp32 torch) on ``b`` images of the align
+    workload: seconds per step (best of 2 after one warm-up)."""
+    import oracle
+    from oracle import align as oalign
+    from radzero_b200 import bench_align, synthetic
+    if threads:
+        torch.set_num_threads(threads)
+    N = bench_align.N
+    w = synthetic.align_layer_weights(42)
+    tok, text, gamma, beta, log_tau = synthetic.make_inputs(b, N, seed=42)
+
+    def once():
+        x = oalign.align_transformer(tok, w)
+        ref = oracle.radzero_forward([text[i:i + 1] for i in range(N)], x, gamma, beta, log_tau,
+                                     need_attn_weights=False, compute_loss=False, squeeze_quirk=False)
+        return torch.sigmoid(ref["t2i_logits"].T / torch.exp(log_tau))
+
+    with torch.no_grad():
+        once()
+        best = float("inf")
+        for _ in range(2):
+            t0 = time.perf_counter()
+            once()
+            best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def align_run_reference(args):
+    from radzero_b200 import bench_align
+    B, N, DESC = bench_align.B, bench_align.N, bench_align.DESC
+    cores = os.cpu_count() or 1
+    bs = 8
+    dt = align_cpu_step_sample(bs, cores)
+    value = bs * N / dt
+    cpu = {"value": value, "unit": "maps/s", "cores": cores, "kind": "port",
+           "sample": f"{bs} of the {B} images x {N} prompts per step (fp32 torch CPU oracle: oracle/align.py "
+                     "restating transformers' Dinov2Encoder + oracle/vlcabs.py), best of 2"}
+    print(json.dumps({
+        "metric": "similarity maps/sec", "value": value, "unit": "maps/s", "n_gpus": args.gpus, "steps": 2,
+        "warmup": 1, "ms_per_step": dt * 1e3 * B / bs, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": DESC, "images_per_gpu": B, "prompts": N, "tokens": bench_align.L, "hidden": bench_align.D},
+        "cpu_baseline": cpu,
+        "e2e": {"value": value, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     if args.workload == "contrastive":
-        from radzero_b200 import bench_contrastive
-        return bench_contrastive.run_reference(args)
+        return contrastive_run_reference(args)
     if args.workload == "align":
-        from radzero_b200 import bench_align
-        return bench_align.run_reference(args, print)
+        return align_run_reference(args)
     from radzero_b200 import synthetic
     B, N, desc = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1

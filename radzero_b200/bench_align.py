@@ -167,49 +167,3 @@ def run(args, world, rank, local, pk, steps=None, warmup=None):
                        "input_dtype": "fp32", "l2": "activations (>= 0.5 GB per kernel) larger than L2; no flush",
                        "parallelism": f"images sharded x{world}, no collective"},
             "prob_checksum": float(res.double().sum().item())}
-
-
-def cpu_step_sample(b: int = 4, threads=None):
-    """The CPU oracle (oracle/align.py + oracle/vlcabs.py, fp32 torch) on ``b`` images: seconds per
-    step (best of 2 after one warm-up).  bench.py's cpu_baseline / --impl reference legs only."""
-    import oracle
-    from oracle import align as oalign
-    from radzero_b200 import synthetic
-    if threads:
-        torch.set_num_threads(threads)
-    w = synthetic.align_layer_weights(42)
-    tok, text, gamma, beta, log_tau = synthetic.make_inputs(b, N, seed=42)
-
-    def once():
-        x = oalign.align_transformer(tok, w)
-        ref = oracle.radzero_forward([text[i:i + 1] for i in range(N)], x, gamma, beta, log_tau,
-                                     need_attn_weights=False, compute_loss=False, squeeze_quirk=False)
-        return torch.sigmoid(ref["t2i_logits"].T / torch.exp(log_tau))
-
-    with torch.no_grad():
-        once()
-        best = float("inf")
-        for _ in range(2):
-            t0 = time.perf_counter()
-            once()
-            best = min(best, time.perf_counter() - t0)
-    return best
-
-
-def run_reference(args, emit):
-    """bench.py --impl reference --workload align: the CPU oracle on a bounded sample of the workload."""
-    import json
-    cores = os.cpu_count() or 1
-    bs = 8
-    dt = cpu_step_sample(bs, cores)
-    value = bs * N / dt
-    cpu = {"value": value, "unit": "maps/s", "cores": cores, "kind": "port",
-           "sample": f"{bs} of the {B} images x {N} prompts per step (fp32 torch CPU oracle: oracle/align.py "
-                     "restating transformers' Dinov2Encoder + oracle/vlcabs.py), best of 2"}
-    emit(json.dumps({
-        "metric": "similarity maps/sec", "value": value, "unit": "maps/s", "n_gpus": args.gpus, "steps": 2,
-        "warmup": 1, "ms_per_step": dt * 1e3 * B / bs, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": DESC, "images_per_gpu": B, "prompts": N, "tokens": L, "hidden": D},
-        "cpu_baseline": cpu,
-        "e2e": {"value": value, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))

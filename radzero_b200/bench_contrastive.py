@@ -188,46 +188,3 @@ def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
         "mpnce": mpnce,
     }
     return out
-
-
-def cpu_sample_step(b_g=16):
-    """Scaled-down CPU step on the oracle (the reference materialises (B,N,L) tensors: the full
-    size does not fit host memory)."""
-    import oracle
-    from radzero_b200 import synthetic
-    counts = synthetic.sentence_counts(b_g, seed=42)
-    n = sum(counts)
-    tok, text, gamma, beta, log_tau = synthetic.make_inputs(b_g, n, seed=1000)
-    gm = synthetic.group_map_from_counts(counts)
-    t0 = time.perf_counter()
-    oracle.contrastive_step_reference(text, gm, tok, gamma, beta, log_tau)
-    dt = time.perf_counter() - t0
-    return dt, b_g * n
-
-
-def run_reference(args):
-    import json
-    from radzero_b200 import synthetic
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    n_total = sum(synthetic.sentence_counts(B_GLOBAL, seed=42))
-    cpu_sample_step(8)
-    t0 = time.perf_counter()
-    pairs = 0
-    for _ in range(args.steps):
-        dt, pr = cpu_sample_step(16)
-        pairs += pr
-    dt = time.perf_counter() - t0
-    full_pairs = B_GLOBAL * n_total
-    value = (pairs / dt) / full_pairs
-    print(json.dumps({
-        "metric": "contrastive steps/sec", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": 1, "ms_per_step": 1e3 / value, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"C4 contrastive step, {B_GLOBAL} images x {n_total} sentences"},
-        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
-                         "sample": "each step = forward+backward at 16 images x ~96 sentences on the fp32 "
-                                   "torch CPU oracle; steps/s extrapolated by the (image, sentence) pair count "
-                                   f"to {B_GLOBAL} x {n_total}"},
-        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
