@@ -23,6 +23,9 @@
 //           in TMEM is rescaled (tcgen05.ld / st by the row's own threads) only on those rare tiles.
 // Keys >= L of the last tile are masked to probability 0; rows >= L are zero-filled by the TMA
 // loads and clipped by the TMA store.
+#ifndef RZ_ATTN_PINGPONG
+#define RZ_ATTN_PINGPONG 0
+#endif
 #ifndef RZ_ATTN_EMU
 #define RZ_ATTN_EMU 2
 #endif
@@ -152,11 +155,10 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   // One CTA per SM holds TWO complete pipelines ("groups" of 10 warps, each with its own shared memory,
-  // barriers and 256 TMEM columns) working on two different items.  Being in one CTA lets them take
-  // turns: named barriers 9 / 10 let only one group at a time run its exponential phase (MUFU-bound),
-  // while the other does its latency-bound part (P store, wait for S, TMEM load, maximum, exchange) --
-  // the FlashAttention-3 ping-pong.  As two independent CTAs per SM the phases drifted into each other
-  // and the MUFU pipe idled 40 % of the time.
+  // barriers and 256 TMEM columns) working on two neighbouring items; 16 softmax warps per SM keep the
+  // MUFU / FMA pipes busier than two independent 2-CTA/SM launches of one pipeline did.  Named barriers
+  // 9 / 10 can make the groups take turns in the exponential phase (the FlashAttention-3 ping-pong,
+  // RZ_ATTN_PINGPONG=1); measured on B200 the free-running groups are ~5 % faster, so it is off.
   const int grp = (int)threadIdx.x / kGroupThreads;
   const int tid = (int)threadIdx.x % kGroupThreads, warp = tid >> 5, lane = tid & 31;
   uint8_t* gbase = smem + grp * kGroupSmem;
@@ -302,7 +304,7 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
     const uint32_t t_p = t_lane + 192 + hf * 32;        // ... 32 packed probability columns (64 keys)
     const uint32_t stg = smem_u32(p_s) + (uint32_t)(q * 4096);   // output staging box of the quarter
     const int n_phases = my_items * T;                  // the same in both groups
-    if (grp == 1 && n_phases > 0) named_bar_arrive(kPingPongBar, 512);     // group 0 goes first
+    if (RZ_ATTN_PINGPONG && grp == 1 && n_phases > 0) named_bar_arrive(kPingPongBar, 512);     // group 0 goes first
     int G = 0;
     for (int it = 0; it < my_items; ++it) {
       int b, h, qt;
@@ -348,7 +350,7 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
         }
         // exponentials -> fp16 pairs, packed IN PLACE (pair i of chunk c lands in v[c][i / 2]).
         // Only one group at a time is in this MUFU-bound phase.
-        named_bar_sync(kPingPongBar + grp, 512);
+        if (RZ_ATTN_PINGPONG) named_bar_sync(kPingPongBar + grp, 512);
         float rs[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) rs[k] = 0.f;
@@ -369,7 +371,7 @@ attn_kernel(const __grid_constant__ CUtensorMap qkv_map, const __grid_constant__
             v[c][i >> 1] = pack_h2(e0, e1);
           }
         }
-        if (!(grp == 1 && G == n_phases - 1)) named_bar_arrive(kPingPongBar + (grp ^ 1), 512);   // the other group's turn
+        if (RZ_ATTN_PINGPONG && !(grp == 1 && G == n_phases - 1)) named_bar_arrive(kPingPongBar + (grp ^ 1), 512);   // the other group's turn
         if (j > 0) {
           // the MMAs of tile j-1 must be done before P (single buffer) is overwritten / O is rescaled
           mbar_wait_soft(&ctl->o_full, (uint32_t)((G - 1) & 1));
