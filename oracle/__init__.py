@@ -13,5 +13,10 @@ executing the reference's own ``exp/cxr_pt/model/losses.py`` and ``F.interpolate
 call sites in the build container (``tests/test_oracle_vs_reference.py``, skipped
 where ``/root/reference`` is absent) and by the golden fixtures generated from the
 reference by ``tests/golden/make_golden.py`` (committed, checked everywhere).
+
+``oracle/align.py`` restates the AlignTransformer forward, whose
+body is third-party code (transformers ``Dinov2Encoder``, pinned 4.39.0 by the reference, not
+vendored): it is pinned against the installed transformers module and the committed golden
+vectors ``tests/golden/align_golden.npz`` (``tests/test_oracle_align.py``).
 """
 from .vlcabs import *  # noqa: F401,F403

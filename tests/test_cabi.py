@@ -33,3 +33,26 @@ def test_argument_validation_without_gpu():
                                  None, 0, 0, 1.0, None, 0, None, 0, None) == -1
     assert lib.rz_sim_fwd_tokens_workspace_bytes(0, 14) == 0
     assert lib.rz_sim_fwd_large_workspace_bytes(2, 100, 1408) > 2 * 100 * 1408 * 2
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under radzero_b200/ may import it (only tests/,
+    __graft_entry__.smoke() and bench.py's CPU legs do)."""
+    import ast
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "radzero_b200")
+    bad = []
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            tree = ast.parse(open(os.path.join(dirpath, f)).read())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom) and node.module:
+                    names = [node.module]
+                if any(n == "oracle" or n.startswith("oracle.") for n in names):
+                    bad.append(f)
+    assert not bad, f"product modules importing the oracle: {bad}"
