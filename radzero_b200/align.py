@@ -42,7 +42,7 @@ def pack_layer(layer: nn.Module, device=None) -> Dict[str, torch.Tensor]:
         raise RzError(f"the attention kernel is built for head dim {HEAD_DIM}")
     if not hasattr(layer.mlp, "fc1"):
         raise RzError("SwiGLU feed-forward layers are not on the RadZero path (use_swiglu_ffn=False)")
-    s = float(att.scaling)            # 1/8: a power of two, so folding it into Wq / bq is exact
+    s = float(att.scaling)            # 1/8: a power of two, so folding it into Wq / bq is exact (up to fp16 subnormals)
     dev = device or att.query.weight.device
     f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
     f16 = lambda t: t.detach().to(device=dev, dtype=torch.float32).to(torch.float16).contiguous()

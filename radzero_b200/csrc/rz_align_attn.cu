@@ -5,7 +5,7 @@
 //
 // Q, K, V are column blocks of the fused projection output qkv [B, L, 3 * H * 64] fp16 (Q already
 // carries the 1/sqrt(64) scale: it is folded into the projection weights on the host, exactly, since
-// it is a power of two).  A work item is (image, head, 128 query rows): its CTA streams the image's keys in
+// it is a power of two, up to fp16 subnormals).  A work item is (image, head, 128 query rows): its CTA streams the image's keys in
 // tiles of 128.  The kernel is persistent, two CTAs resident per SM (256 TMEM columns and ~113 KB of shared memory each) so
 // that one CTA's exponentials overlap the other's MMAs.
 //
