@@ -229,3 +229,52 @@ class SyntheticTokenizer:
             ids[i, : len(r)] = torch.tensor(r)
             mask[i, : len(r)] = 1
         return SyntheticTokenizer._Enc(input_ids=ids, attention_mask=mask)
+
+
+# ----------------------------------------------------------------------------- result formats
+# the on-disk formats of the zero-shot evaluation, so that a whole-dataset
+# run through the CUDA path leaves the same files as the reference's evaluators.
+def process_class_prompts(text_prompt: Dict, tokenizer, model) -> Dict:
+    """inference/utils.py:40-66: class ``i`` -> its first prompt (``text_prompt[str(i)][0]``) and the
+    negated prompt (``"There is" -> "There is no"``), both tokenised as one padded batch on the
+    model's device."""
+    pos = [text_prompt[str(i)][0] for i in range(len(text_prompt))]
+    neg = [p.replace("There is", "There is no") for p in pos]
+    tok = lambda texts: tokenizer(texts, padding=True, truncation=True, return_tensors="pt").to(model.device)
+    return {"encoded_key_phrases": tok(pos), "encoded_negative_phrases": tok(neg)}
+
+
+@torch.no_grad()
+def calculate_similarities(pixel_batches, text_batch: Dict, model):
+    """inference/utils.py:69-107 without the DataLoader: ``pixel_batches`` is any iterable of
+    ``pixel_values`` batches; returns the (images, classes) float32 numpy matrix of ``logits`` the
+    reference concatenates (``compute_logits(...)["logits"]`` per batch, :94-103)."""
+    rows = []
+    for image in pixel_batches:
+        image = image.to(model.device)
+        rows.append(model.compute_logits(pixel_values=image,
+                                         encoded_key_phrases=[text_batch["encoded_key_phrases"]],
+                                         encoded_negative_phrases=[text_batch.get("encoded_negative_phrases")])["logits"])
+    return torch.cat(rows, dim=0).float().detach().cpu().numpy()
+
+
+def save_similarities_csv(similarities, save_root_dir: str, sel_dataset: str) -> str:
+    """``pd.DataFrame(similarities).to_csv(<save_root_dir>/<dataset>.csv, index=False)``
+    (inference/utils.py:213-215): header ``0,1,...``, one row per image, pandas' float formatting."""
+    import os
+    import pandas as pd
+    path = os.path.join(save_root_dir, sel_dataset) + ".csv"
+    pd.DataFrame(similarities).to_csv(path, index=False)
+    return path
+
+
+def save_result_json(result: Dict, save_root_dir: str) -> str:
+    """``save_json(result, <save_root_dir>/result.json)`` (inference/inference.py:62, 109, 166;
+    common/utils.py:123-125: utf-8, indent 2)."""
+    import json
+    import os
+    os.makedirs(save_root_dir, exist_ok=True)
+    path = os.path.join(save_root_dir, "result.json")
+    with open(path, "w", encoding="utf-8") as f:
+        json.dump(result, f, indent=2)
+    return path
