@@ -234,32 +234,38 @@ int rz_map_threshold_stats(const float* scores, long long map_stride, int maps, 
  * Replaces multi_positive_nce_loss + get_row_loss + get_col_loss (losses.py:243-344) and
  * their autograd, for the image-sharded layout of SURVEY.md section 8e: this rank holds
  * columns [col0, col0 + b_local) of the (n_total x b_global) logit matrix.
+ * TWO launches (one persistent cooperative kernel each), one on either side of the cross-rank
+ * reduction.  The temperature is exp(*log_tau) read ON THE DEVICE when `log_tau` is non-NULL
+ * (the loss_temperature parameter: no host synchronisation), else 1 / inv_tau.
  *
- * Phase 1 (rz_mpnce_partials): E = exp(Z/tau); per-row local sums rowsum[i] = sum_b E_ib,
+ * Launch 1 (rz_mpnce_partials): E = exp(Z/tau); per-row local sums rowsum[i] = sum_b E_ib,
  *   pos[i] = E[i, group_map[i]] if that column is local else 0, per-column sums
  *   colneg[b] = sum_{i: g_i != b} E_ib and colpos[b] = sum_{i: g_i = b} E_ib, all in a fixed
  *   summation order (no float atomics) so that 1-GPU and N-GPU runs agree.
- *   With several ranks the caller all-reduces (sum) rowsum and pos between the phases.
- *   scratch1: fp32 [2 * ceil(n_total/32) * b_local].
- * Phase 2 (rz_mpnce_finish): loss terms and dL/dZ for the local columns.
+ *   With several ranks the caller all-reduces (sum) rowsum and pos between the launches.
+ *   scratch1: fp32 [rz_mpnce_partials_scratch_floats(n_total, b_local)].
+ * Launch 2 (rz_mpnce_finish): loss terms and dL/dZ for the local columns.
  *   loss_terms[0] = sum of the row terms this rank owns (rows whose positive column is
  *   local; images, when row_sum), loss_terms[1] = sum of its column terms,
  *   loss_terms[2] = sum_ib dZ_ib * Z_ib over the local block (= -dL/dlog(tau) share),
- *   loss_terms[3] = unused (0).  loss = (sum_ranks terms[0]/n_row + sum_ranks terms[1]/n_col)/2
+ *   loss_terms[3] = this rank's share of the loss = terms[0]/(2 n_row) + terms[1]/(2 n_col)
+ *   (the loss itself on one rank; summed over ranks otherwise)
  *   with n_row = b_global if row_sum else n_total, n_col = b_global if col_sum else n_total;
  *   dZ already carries the 1/(2*n_row), 1/(2*n_col) factors.
  *   row_sum / col_sum select the MIL-NCE variants (losses.py:303-315, 331-336).
  *   z, dz    [n_total, ldz] fp32 (b_local valid columns per row); dz may be NULL (loss only)
  *   group_map int64 [n_total] GLOBAL image index
- *   scratch2 fp32 [4 * n_total + 3 * b_local + 2 * b_global]
+ *   scratch2 fp32 [rz_mpnce_finish_scratch_floats(n_total, b_local, b_global)]
  */
+size_t rz_mpnce_partials_scratch_floats(int n_total, int b_local);
+size_t rz_mpnce_finish_scratch_floats(int n_total, int b_local, int b_global);
 int rz_mpnce_partials(const float* z, long long ldz, int n_total, int b_local,
-                      const long long* group_map, int col0, float inv_tau,
+                      const long long* group_map, int col0, float inv_tau, const float* log_tau,
                       float* rowsum, float* pos, float* colneg, float* colpos,
                       float* scratch1, void* stream);
 int rz_mpnce_finish(const float* z, long long ldz, int n_total, int b_local, int b_global,
-                    const long long* group_map, int col0, float inv_tau, float eps,
-                    int row_sum, int col_sum,
+                    const long long* group_map, int col0, float inv_tau, const float* log_tau,
+                    float eps, int row_sum, int col_sum,
                     const float* rowsum, const float* pos, const float* colneg,
                     const float* colpos, float* scratch2, float* dz, float* loss_terms,
                     void* stream);

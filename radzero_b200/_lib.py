@@ -45,8 +45,10 @@ SIGNATURES: Dict[str, tuple] = {
     "rz_prep_rows_bwd": (_i, [_vp, _i, _vp, _vp, _ll, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _f, _vp]),
     "rz_upsample_maps": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _f, _vp, _vp]),
     "rz_map_threshold_stats": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
-    "rz_mpnce_partials": (_i, [_vp, _ll, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "rz_mpnce_finish": (_i, [_vp, _ll, _i, _i, _i, _vp, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp,
+    "rz_mpnce_partials_scratch_floats": (C.c_size_t, [_i, _i]),
+    "rz_mpnce_finish_scratch_floats": (C.c_size_t, [_i, _i, _i]),
+    "rz_mpnce_partials": (_i, [_vp, _ll, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rz_mpnce_finish": (_i, [_vp, _ll, _i, _i, _i, _vp, _i, _f, _vp, _f, _i, _i, _vp, _vp, _vp, _vp,
                              _vp, _vp, _vp, _vp]),
     "rz_text_pool": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "rz_ln_rows": (_i, [_vp, _i, _vp, _vp, _f, _ll, _vp, _vp]),

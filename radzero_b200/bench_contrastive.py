@@ -53,9 +53,37 @@ def _inputs(rank, world, dev, dtype, b_global=B_GLOBAL):
     return torch.cat(toks), torch.cat(texts), gamma, beta, gm, sum(counts_all)
 
 
+def config(n_total: int):
+    """The `config` object of the contrastive workload -- identical in both arms of bench.py."""
+    return {"workload": f"C4 contrastive step, {B_GLOBAL} images x {n_total} sentences (n_i ~ U{{3..9}}), "
+                        "image batch sharded over the GPUs with text all-gather",
+            "input_dtype": "bf16", "tokens": L, "hidden": D}
+
+
+def _one_rank_record():
+    import json
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "contrastive_1rank.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
+def _key_phrases(counts, dev):
+    """Per-image tokenised sentence batches as the reference's dataset hands them over
+    (dataset.py:172-181); the ids index the rows of the precomputed sentence embeddings."""
+    out, o = [], 0
+    ids_all = torch.arange(sum(counts), device=dev).view(-1, 1)
+    ones = torch.ones_like(ids_all)
+    for c in counts:
+        out.append({"input_ids": ids_all[o:o + c], "attention_mask": ones[o:o + c]})
+        o += c
+    return out
+
+
 def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
     import torch.distributed as dist
-    from radzero_b200 import _lib, losses, training
+    from radzero_b200 import _lib, losses, ops, training
     dev = torch.device("cuda", local)
     steps = steps or max(2, min(args.steps, 10))
     warmup = warmup if warmup is not None else 3
@@ -66,6 +94,8 @@ def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
         fn.layer_norm.weight.copy_(gamma)
         fn.layer_norm.bias.copy_(beta)
     distributed = world > 1
+    b_local = B_GLOBAL // world
+    counts = torch.bincount(gm - rank * b_local, minlength=b_local).tolist()
 
     def step(tk, tx):
         tk = tk.detach().requires_grad_(True)
@@ -73,7 +103,25 @@ def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
         fn.zero_grad(set_to_none=True)
         res = training.contrastive_step(fn, tx, gm, tk, distributed=distributed)
         res["loss"].backward()
-        return res["loss"].detach(), tk.grad
+        return res["loss"].detach(), tk.grad, tx.grad
+
+    # the same step through the reference surface: RadZeroLoss.forward(key_phrases, vision_tokens,
+    # forward_text_model) (losses.py:71-124) -- per-image sentence batches, the text model as a callback
+    key_phrases = _key_phrases(counts, dev)
+    holder = {}
+
+    def text_model(enc):
+        f = holder["text"][enc["input_ids"][:, 0]] if enc["input_ids"].shape[0] != holder["text"].shape[0] \
+            else holder["text"]
+        return {"text_features_wo_l2_norm": f, "text_features": f}
+
+    def surface_step(tk, tx):
+        tk = tk.detach().requires_grad_(True)
+        holder["text"] = tx.detach().requires_grad_(True)
+        fn.zero_grad(set_to_none=True)
+        out = fn(key_phrases, tk, text_model)            # ddp_gather=True: sharded when torch.distributed is up
+        out["losses"]["loss"].backward()
+        return out["losses"]["loss"].detach()
 
     def barrier():
         if distributed:
@@ -81,13 +129,19 @@ def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
         torch.cuda.synchronize()
 
     for _ in range(warmup):
-        loss, _ = step(tok, text)
+        loss, dtok, dtxt = step(tok, text)
+    # loss / gradient fingerprint of THIS global problem: the same numbers at every rank count
+    chk = torch.stack([dtok.double().abs().sum(), dtxt.double().abs().sum()])
+    if distributed:
+        dist.all_reduce(chk)
+    grad_checksum = float(chk.sum().item())
+    del dtok, dtxt
     barrier()
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        loss, _ = step(tok, text)
+        loss, _, _ = step(tok, text)
     e1.record()
     barrier()
     launches = _lib.launch_count() - n0
@@ -129,8 +183,7 @@ def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
             main.wait_event(ev)
             if i + 1 < n:
                 ev = upload(k ^ 1)
-            a, b = d_tok[k], d_txt[k]
-            l, _ = step(a, b)
+            l = surface_step(d_tok[k], d_txt[k])
             last = l.item()                     # D2H read of the step's loss
             used[k] = torch.cuda.Event()
             used[k].record(main)
@@ -138,7 +191,7 @@ def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
 
     e2e_loop(2)
     barrier()
-    ks = 4
+    ks = max(4, min(steps, 8))
     e0.record()
     l_host = e2e_loop(ks)
     e1.record()
@@ -148,43 +201,76 @@ def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
         t = torch.tensor([ms2], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms2 = float(t.item())
+    del d_tok, d_txt
+
+    def dev_time(f, reps=10):
+        for _ in range(3):
+            f()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            f()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
     # the MP-NCE loss kernels on their own (K10): algorithmic bytes = read Z + write dZ
-    from radzero_b200 import ops
-    b_local = B_GLOBAL // world
     zt = torch.randn(n_total, b_local, device=dev) * 0.3
     gm_all = gm if not distributed else torch.arange(n_total, device=dev) % B_GLOBAL
+    lt = fn.loss_temperature.detach()
+
     def nce():
-        rs, ps, cn, cp = ops.mpnce_partials(zt, gm_all, rank * b_local, 1.0 / 0.07)
-        return ops.mpnce_finish(zt, gm_all, rank * b_local, B_GLOBAL, 1.0 / 0.07, rs, ps, cn, cp)
-    for _ in range(3):
-        nce()
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(10):
-        nce()
-    e1.record()
-    torch.cuda.synchronize()
-    nce_ms = e0.elapsed_time(e1) / 10
+        rs, ps, cn, cp = ops.mpnce_partials(zt, gm_all, rank * b_local, log_tau=lt)
+        return ops.mpnce_finish(zt, gm_all, rank * b_local, B_GLOBAL, 1.0, rs, ps, cn, cp, log_tau=lt)
+    n1 = _lib.launch_count()
+    nce()
+    nce_launches = _lib.launch_count() - n1
+    nce_ms = dev_time(nce)
     nce_bytes = 2 * n_total * b_local * 4
-    mpnce = {"ms": nce_ms, "algorithmic_bytes": nce_bytes, "achieved_gbs": nce_bytes / (nce_ms * 1e-3) / 1e9,
+    mpnce = {"ms": nce_ms, "launches": int(nce_launches), "algorithmic_bytes": nce_bytes,
+             "achieved_gbs": nce_bytes / (nce_ms * 1e-3) / 1e9,
              "frac_of_hbm": nce_bytes / (nce_ms * 1e-3) / 1e9 / pk["hbm"],
-             "note": "7 small kernels (two phases + coefficient vectors); Z is 25 MB at C4 and stays in L2, "
-                     "so this is launch/latency-bound, not HBM-bound"}
+             "note": "two persistent cooperative launches (partials | coefficients + dZ + terms); Z is 25 MB at C4 "
+                     "and is read from L2; the fraction is of the HBM copy peak on read-Z + write-dZ bytes"}
+    # the step's collectives on their own (same message sizes, back to back): device time per step
+    comm_us = None
+    if distributed:
+        cap = -(-n_total // world) + 64
+        g_send = torch.empty(cap * (D * 2 + 8), dtype=torch.uint8, device=dev)
+        g_recv = torch.empty(world * g_send.numel(), dtype=torch.uint8, device=dev)
+        rowpos = torch.empty(2 * n_total, device=dev)
+        scal = torch.empty(1, device=dev)
+        dq_send = torch.empty(world * cap, D, device=dev)
+        dq_out = torch.empty(cap, D, device=dev)
+        comm_us = {
+            "all_gather_text": round(dev_time(lambda: dist.all_gather_into_tensor(g_recv, g_send)) * 1e3, 1),
+            "all_reduce_rows": round(dev_time(lambda: dist.all_reduce(rowpos)) * 1e3, 1),
+            "all_reduce_loss": round(dev_time(lambda: dist.all_reduce(scal)) * 1e3, 1),
+            "reduce_scatter_dq": round(dev_time(lambda: dist.reduce_scatter_tensor(dq_out, dq_send)) * 1e3, 1),
+        }
+        comm_us["total"] = round(sum(comm_us.values()), 1)
+        comm_us["frac_of_step"] = round(comm_us["total"] * 1e-3 / ms_step, 4)
+    one = _one_rank_record()
+    match = None
+    if one is not None:
+        match = bool(abs(float(loss.item()) - one["loss"]) <= 1e-5 * abs(one["loss"])
+                     and abs(grad_checksum - one["grad_checksum"]) <= 2e-3 * abs(one["grad_checksum"]))
     out = {
         "metric": "contrastive steps/sec", "value": 1e3 / ms_step, "unit": "steps/s", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "scaling": "strong", "dtype": "f16",
-        "loss": float(loss.item()), "gpu_launches": int(launches),
-        "config": {"workload": f"C4 contrastive step, {B_GLOBAL} images x {n_total} sentences (n_i ~ U{{3..9}}), "
-                               f"image batch sharded x{world} with text all-gather",
-                   "input_dtype": "bf16", "tokens": L, "hidden": D},
+        "loss": float(loss.item()), "grad_checksum": grad_checksum, "matches_1rank": match,
+        "one_rank_record": one, "gpu_launches": int(launches),
+        "config": config(n_total),
+        "notes": {"parallelism": f"images sharded x{world}, text all-gather, dq reduce-scatter"},
         "roofline": {"bound": "tensor", "kernel": "whole step (sim_fwd + rz_sim_bwd GEMM passes)",
                      "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
                      "algorithmic_flops_per_step": flops, "traffic": _traffic(),
                      "peak_source": pk["src"] + " sustained (kernel timed inside a long step)"},
         "e2e": {"value": 1e3 / (ms2 / ks), "unit": "steps/s",
                 "h2d_bytes_per_step": (h_tok.numel() + h_txt.numel()) * 2, "d2h_bytes_per_step": 4,
-                "api": "RadZeroLoss.forward + backward", "steps": ks,
+                "api": "RadZeroLoss.forward(key_phrases, vision_tokens, forward_text_model) + loss.backward()",
+                "steps": ks, "loss": l_host,
                 "note": "inputs of step i+1 are uploaded on a copy stream while step i computes"},
-        "mpnce": mpnce,
+        "mpnce": mpnce, "comm_us": comm_us,
     }
     return out

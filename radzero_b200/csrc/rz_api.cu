@@ -19,12 +19,16 @@ void rz_note_cuda_error(cudaError_t e) {
 void rz_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int rz_sm_count() {
-  static int cached = 0;
-  if (cached > 0) return cached;
+  // cached PER DEVICE: a process may drive several GPUs
+  static std::atomic<int> cached[64];
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64) {
+    const int c = cached[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+  }
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-  cached = n;
+  if (dev >= 0 && dev < 64) cached[dev].store(n, std::memory_order_relaxed);
   return n;
 }
 

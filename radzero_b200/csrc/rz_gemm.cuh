@@ -215,7 +215,10 @@ gemm_kernel(const __grid_constant__ Maps maps, const typename V::Params p) {
 // resident clusters of gemm_kernel<V> on this device (persistent grid size / kCluster)
 template <class V>
 int max_clusters(cudaLaunchConfig_t* cfg) {
-  static int cached = 0;
+  static int cached_all[64] = {0};           // per device (a process may drive several GPUs)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  int& cached = cached_all[dev];
   if (cached > 0) return cached;
   int n = 0;
   if (V::kCluster > 1) {

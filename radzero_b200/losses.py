@@ -119,26 +119,34 @@ class _MpNce(torch.autograd.Function):
         z = logits.detach()
         z = z if (z.dtype == torch.float32 and z.stride(-1) == 1) else z.float().contiguous()
         n, b = z.shape
-        tau = float(temperature)
-        rs, ps, cn, cp = ops.mpnce_partials(z, group_map, 0, 1.0 / tau)
-        terms, dz = ops.mpnce_finish(z, group_map, 0, b, 1.0 / tau, rs, ps, cn, cp, eps=eps,
-                                     row_sum=row_sum, col_sum=col_sum, want_dz=True)
-        n_row = b if row_sum else n
-        n_col = b if col_sum else n
-        loss = (terms[0] / n_row + terms[1] / n_col) * 0.5
-        ctx.save_for_backward(dz, terms)
-        ctx.tau = tau
+        on_device = isinstance(temperature, torch.Tensor) and temperature.is_cuda
+        if on_device:
+            # tau stays on the device (the kernels read log tau through a pointer): no host sync
+            tau = temperature.detach().float().reshape(1)
+            kw = dict(log_tau=tau.log())
+            inv_tau = 1.0
+        else:
+            tau = float(temperature)
+            kw = {}
+            inv_tau = 1.0 / tau
+        rs, ps, cn, cp = ops.mpnce_partials(z, group_map, 0, inv_tau, **kw)
+        terms, dz = ops.mpnce_finish(z, group_map, 0, b, inv_tau, rs, ps, cn, cp, eps=eps,
+                                     row_sum=row_sum, col_sum=col_sum, want_dz=True, **kw)
+        loss = terms[3].clone()
+        ctx.save_for_backward(dz, terms, tau if on_device else None)
+        ctx.tau = None if on_device else tau
         ctx.temp_is_tensor = isinstance(temperature, torch.Tensor)
         ctx.in_dtype = logits.dtype
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        dz, terms = ctx.saved_tensors
+        dz, terms, tau_t = ctx.saved_tensors
         gz = (dz * g).to(ctx.in_dtype)
         gt = None
         if ctx.temp_is_tensor:
-            gt = (-(terms[2] / ctx.tau) * g).reshape(1)
+            tau = tau_t if tau_t is not None else ctx.tau
+            gt = (-(terms[2] / tau) * g).reshape(())
         return gz, None, gt, None, None, None
 
 
@@ -157,6 +165,15 @@ def multi_positive_nce_loss(logits: torch.Tensor, group_map: torch.Tensor, tempe
     else:
         out = _MpNce.apply(logits, group_map, t, eps, row_sum, col_sum)
     return out
+
+
+def _index_tensor(values, device) -> torch.Tensor:
+    """int64 index tensor on ``device``.  CUDA: staged in pinned memory and copied asynchronously (a
+    pageable host-to-device copy would synchronise the stream, i.e. drain the GPU queue)."""
+    t = torch.tensor(values, dtype=torch.int64)
+    if torch.device(device).type != "cuda":
+        return t.to(device)
+    return t.pin_memory().to(device, non_blocking=True)
 
 
 # ------------------------------------------------------------------------------------ a8
@@ -249,14 +266,16 @@ class RadZeroLoss(nn.Module):
         return {"input_ids": torch.cat([pad(t, pad_token_id) for t in ids], dim=0),
                 "attention_mask": torch.cat([pad(t, 0) for t in ams], dim=0)}, [int(t.shape[0]) for t in ids]
 
-    def collect_text_features(self, key_phrases, forward_text_model, rank: int = 0):
+    def collect_text_features(self, key_phrases, forward_text_model, rank: int = 0,
+                              want_group_map: bool = True):
         """Raw (pre-LayerNorm) sentence embeddings + group_map, losses.py:126-153.
 
         The reference calls the text model once per image (B_local sequential calls, :135-151).  With
         ``batch_text_calls`` (default) the per-image token batches are merged into one padded batch and
         the text model runs ONCE; rows are independent, so the features
         are the same.  Inputs that are not plain ``input_ids`` / ``attention_mask`` tensors fall back
-        to the reference's call pattern."""
+        to the reference's call pattern.  ``want_group_map=False`` (inference: nothing reads it) skips
+        building the index tensor, which is a synchronising host-to-device copy."""
         b_local = len(key_phrases)
         merged = self._merge_encodings(key_phrases, self.text_pad_token_id) if self.batch_text_calls else None
         if merged is not None:
@@ -265,8 +284,10 @@ class RadZeroLoss(nn.Module):
             feat = f["text_features"] if self.text_features_l2_norm else f["text_features_wo_l2_norm"]
             if feat.shape[-1] == 2 * self.hidden_dim:
                 feat = feat[:, self.hidden_dim:]
+            if not want_group_map:
+                return feat, None
             group = [i + rank * b_local for i, c in enumerate(counts) for _ in range(c)]
-            return feat, torch.tensor(group, device=feat.device, dtype=torch.int64)
+            return feat, _index_tensor(group, feat.device)
         feats: List[torch.Tensor] = []
         group: List[int] = []
         for i, kp in enumerate(key_phrases):
@@ -277,7 +298,9 @@ class RadZeroLoss(nn.Module):
             feats.append(feat)
             group.extend([i + rank * b_local] * feat.size(0))
         text = torch.cat(feats, dim=0)
-        return text, torch.tensor(group, device=text.device, dtype=torch.int64)
+        if not want_group_map:
+            return text, None
+        return text, _index_tensor(group, text.device)
 
     def compute_text_features(self, key_phrases, forward_text_model, ddp_gather=True):
         """losses.py:126-166 (kept for API parity; forward() uses the fused path instead)."""
@@ -297,16 +320,24 @@ class RadZeroLoss(nn.Module):
         outputs: Dict = {}
         distributed = bool(ddp_gather and dist.is_initialized() and dist.get_world_size() > 1)
         rank = dist.get_rank() if distributed else 0
-        text, group_map = self.collect_text_features(key_phrases, forward_text_model, rank)
+        text, group_map = self.collect_text_features(key_phrases, forward_text_model, rank,
+                                                     want_group_map=bool(compute_loss or distributed))
         tokens = vision_tokens if self.use_vision_cls_token else vision_tokens[:, 1:]
         gamma, beta = self._ln()
-        wants_grad = torch.is_grad_enabled() and compute_loss and (
+        grad_on = torch.is_grad_enabled()
+        if grad_on and not compute_loss and (text.requires_grad or vision_tokens.requires_grad):
+            # the reference would hand back differentiable logits here; this build's inference kernels
+            # keep no autograd state, so refuse instead of silently detaching
+            raise RzError("RadZeroLoss.forward(compute_loss=False) on inputs that require grad: wrap the "
+                          "call in torch.no_grad(), or use compute_loss=True for the training node")
+        wants_grad = grad_on and compute_loss and (
             text.requires_grad or vision_tokens.requires_grad or self.loss_temperature.requires_grad
             or (gamma is not None and gamma.requires_grad))
         if wants_grad or distributed:
             from .training import contrastive_step
             res = contrastive_step(self, text, group_map, tokens, distributed=distributed,
-                                   need_attn_weights=need_attn_weights, compute_loss=compute_loss)
+                                   need_attn_weights=need_attn_weights, compute_loss=compute_loss,
+                                   gather_logits=bool(kwargs.get("gather_logits", False)))
             outputs["t2i_logits"] = _squeeze_quirk(res["z"])
             outputs["t2i_attn_weights"] = [res["scores"]] if need_attn_weights else None
             if compute_loss:
@@ -314,8 +345,12 @@ class RadZeroLoss(nn.Module):
             return outputs
         g = gamma.detach() if gamma is not None else None
         b = beta.detach() if beta is not None else None
-        z, scores = _similarity_forward(text.detach(), tokens.detach(), g, b, self._scale(),
-                                        self.sim_op == "cos", need_attn_weights, drop_cls=False)
+        # the attention temperature is read from the parameter ON THE DEVICE (no host synchronisation)
+        l2 = self.sim_op == "cos"
+        zkw = {"log_tau_scale": self._attn_log_tau()} if l2 else {}
+        scale = 1.0 if l2 else 1.0 / math.sqrt(self.hidden_dim)
+        z, scores = _similarity_forward(text.detach(), tokens.detach(), g, b, scale, l2, need_attn_weights,
+                                        drop_cls=False, **zkw)
         outputs["t2i_logits"] = _squeeze_quirk(z)
         outputs["t2i_attn_weights"] = [scores] if need_attn_weights else None
         if compute_loss:

@@ -26,6 +26,28 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _guard(fn):
+    """Run ``fn`` with the CUDA device of its tensor arguments current (kernels, TMA descriptors and the
+    stream all belong to that device, whatever ``torch.cuda.current_device()`` was) and refuse tensors
+    that live on different devices."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if torch.is_tensor(a) and a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise RzError(f"{fn.__name__}: tensors on different devices ({dev} and {a.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -37,6 +59,7 @@ def _contig(t: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- K1 + K2
+@_guard
 def prep_rows(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], *,
               rows_per_group: Optional[int] = None, rows_per_group_padded: Optional[int] = None,
               want_f16: bool = True, want_f32: bool = False, want_stats: bool = False,
@@ -95,6 +118,7 @@ def _sim_outputs(B, N, tokens, dev, want_scores, drop_cls, want_z, z_out, z_imag
     return drop, scores, z, zs_text, zs_img
 
 
+@_guard
 def sim_fwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, scale: float, *,
             want_scores: bool = False, drop_cls: bool = True, want_z: bool = True,
             want_stats: bool = False, want_pooled: bool = False,
@@ -172,6 +196,7 @@ FUSED_PREP_MAX_TEXT = 16
 USE_FUSED_PREP = True
 
 
+@_guard
 def sim_fwd_tokens(tokens_raw: torch.Tensor, gamma: Optional[torch.Tensor],
                    beta: Optional[torch.Tensor], q_f16: torch.Tensor, scale: float, *, l2: bool = True,
                    want_scores: bool = False, drop_cls: bool = True, want_z: bool = True,
@@ -220,6 +245,7 @@ def padded_tokens_bwd(tokens: int) -> int:
     return (tokens + BWD_TOKEN_TILE - 1) // BWD_TOKEN_TILE * BWD_TOKEN_TILE
 
 
+@_guard
 def sim_bwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, inv_tau: float, z: torch.Tensor,
             dz: torch.Tensor, lse: Optional[torch.Tensor], onorm: torch.Tensor, pooled: torch.Tensor, *,
             log_tau: Optional[torch.Tensor] = None, p: Optional[torch.Tensor] = None,
@@ -248,6 +274,7 @@ def sim_bwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, inv_tau: floa
     return dq, dk, dlt
 
 
+@_guard
 def prep_rows_bwd(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor],
                   dnorm: torch.Tensor, *, rows_per_group: Optional[int] = None,
                   rows_per_group_padded: Optional[int] = None, l2: bool = True,
@@ -304,6 +331,7 @@ def _as_maps(t: torch.Tensor) -> torch.Tensor:
     return t.as_strided((maps, t.shape[-1]), (strides[-1], 1), t.storage_offset())
 
 
+@_guard
 def upsample_maps(scores: torch.Tensor, out_hw: Tuple[int, int], *, mode: int = _lib.RZ_UP_RAW,
                   interp_hw: Optional[Tuple[int, int]] = None, offset: Tuple[int, int] = (0, 0),
                   fill: float = -999.0, threshold: float = 0.5, grid: Optional[int] = None):
@@ -337,6 +365,7 @@ def upsample_maps(scores: torch.Tensor, out_hw: Tuple[int, int], *, mode: int = 
     return out
 
 
+@_guard
 def map_threshold_stats(scores: torch.Tensor, out_hw: Tuple[int, int], thresholds_logit: torch.Tensor, *,
                         gt_masks: Optional[torch.Tensor] = None,
                         interp_hw: Optional[Tuple[int, int]] = None, offset: Tuple[int, int] = (0, 0),
@@ -375,47 +404,58 @@ def map_threshold_stats(scores: torch.Tensor, out_hw: Tuple[int, int], threshold
 
 
 # ----------------------------------------------------------------------------- K10
-def mpnce_partials(z: torch.Tensor, group_map: torch.Tensor, col0: int, inv_tau: float):
-    """Phase 1 of MP-NCE on the local column block.  Returns (rowsum, pos, colneg, colpos)."""
+@_guard
+def mpnce_partials(z: torch.Tensor, group_map: torch.Tensor, col0: int, inv_tau: float = 1.0, *,
+                   log_tau: Optional[torch.Tensor] = None, rowpos: Optional[torch.Tensor] = None):
+    """Launch 1 of MP-NCE on the local column block.  Returns (rowsum, pos, colneg, colpos).
+    ``log_tau`` (1-element fp32 CUDA tensor): temperature read on the device instead of ``inv_tau``.
+    ``rowpos`` (2, n) fp32: caller-owned buffer for rowsum / pos (one all-reduce message)."""
     _need_cuda(z, group_map)
     assert z.dtype == torch.float32 and z.dim() == 2 and z.stride(1) == 1
     n, bl = z.shape
-    gm = _contig(group_map.to(torch.int64))
+    gm = group_map if (group_map.dtype == torch.int64 and group_map.is_contiguous()) \
+        else _contig(group_map.to(torch.int64))
     dev = z.device
-    rowsum = torch.empty(n, dtype=torch.float32, device=dev)
-    pos = torch.empty(n, dtype=torch.float32, device=dev)
-    colneg = torch.empty(bl, dtype=torch.float32, device=dev)
-    colpos = torch.empty(bl, dtype=torch.float32, device=dev)
-    scratch = torch.empty(2 * ((n + 31) // 32) * bl, dtype=torch.float32, device=dev)
-    rc = _lib.load().rz_mpnce_partials(_p(z), z.stride(0), n, bl, _p(gm), int(col0), float(inv_tau),
-                                       _p(rowsum), _p(pos), _p(colneg), _p(colpos), _p(scratch),
-                                       _stream())
+    if rowpos is None:
+        rowpos = torch.empty((2, n), dtype=torch.float32, device=dev)
+    rowsum, pos = rowpos[0], rowpos[1]
+    col = torch.empty((2, bl), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    scratch = torch.empty(int(lib.rz_mpnce_partials_scratch_floats(n, bl)), dtype=torch.float32, device=dev)
+    rc = lib.rz_mpnce_partials(_p(z), z.stride(0), n, bl, _p(gm), int(col0), float(inv_tau),
+                               _p(_log_tau_ptr(log_tau)), _p(rowsum), _p(pos), _p(col[0]), _p(col[1]),
+                               _p(scratch), _stream())
     _lib.check(rc, "rz_mpnce_partials")
-    return rowsum, pos, colneg, colpos
+    return rowsum, pos, col[0], col[1]
 
 
+@_guard
 def mpnce_finish(z: torch.Tensor, group_map: torch.Tensor, col0: int, b_global: int, inv_tau: float,
                  rowsum, pos, colneg, colpos, *, eps: float = 1e-8, row_sum: bool = False,
-                 col_sum: bool = False, want_dz: bool = True):
-    """Phase 2: returns (loss_terms[4], dz or None) for the local column block."""
+                 col_sum: bool = False, want_dz: bool = True, log_tau: Optional[torch.Tensor] = None):
+    """Launch 2: returns (loss_terms[4], dz or None) for the local column block."""
     _need_cuda(z, group_map, rowsum, pos, colneg, colpos)
     n, bl = z.shape
-    gm = _contig(group_map.to(torch.int64))
+    gm = group_map if (group_map.dtype == torch.int64 and group_map.is_contiguous()) \
+        else _contig(group_map.to(torch.int64))
     dev = z.device
     dz = torch.empty_like(z) if want_dz else None
     if dz is not None:
         assert dz.stride(0) == z.stride(0)
     terms = torch.empty(4, dtype=torch.float32, device=dev)
-    scratch = torch.empty(4 * n + 3 * bl + 2 * b_global, dtype=torch.float32, device=dev)
-    rc = _lib.load().rz_mpnce_finish(_p(z), z.stride(0), n, bl, int(b_global), _p(gm), int(col0),
-                                     float(inv_tau), float(eps), int(row_sum), int(col_sum),
-                                     _p(rowsum), _p(pos), _p(colneg), _p(colpos), _p(scratch),
-                                     _p(dz), _p(terms), _stream())
+    lib = _lib.load()
+    scratch = torch.empty(int(lib.rz_mpnce_finish_scratch_floats(n, bl, int(b_global))), dtype=torch.float32,
+                          device=dev)
+    rc = lib.rz_mpnce_finish(_p(z), z.stride(0), n, bl, int(b_global), _p(gm), int(col0),
+                             float(inv_tau), _p(_log_tau_ptr(log_tau)), float(eps), int(row_sum),
+                             int(col_sum), _p(rowsum), _p(pos), _p(colneg), _p(colpos), _p(scratch),
+                             _p(dz), _p(terms), _stream())
     _lib.check(rc, "rz_mpnce_finish")
     return terms, dz
 
 
 # ----------------------------------------------------------------------------- diagnostics
+@_guard
 def umma_probe(a_image: torch.Tensor, b_image: torch.Tensor, a_desc: int, b_desc: int,
                a_step_bytes: int, b_step_bytes: int, k_steps: int, idesc: int,
                d_tmem_offset: int = 0, ncols: int = 32) -> torch.Tensor:
@@ -431,6 +471,7 @@ def umma_probe(a_image: torch.Tensor, b_image: torch.Tensor, a_desc: int, b_desc
 
 
 # ----------------------------------------------------------------------------- A0 - A2
+@_guard
 def ln_rows(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> torch.Tensor:
     """nn.LayerNorm(768, eps) of the rows of ``x`` (..., 768) -> fp16 rows (a GEMM operand)."""
     _need_cuda(x, gamma, beta)
@@ -446,6 +487,7 @@ def ln_rows(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float
     return out.view(x.shape)
 
 
+@_guard
 def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogue: str = "bias", *,
            scale: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
            out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -484,6 +526,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilo
     return out
 
 
+@_guard
 def attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
     """softmax(q k^T) v per (image, head); qkv (B, L, 3 * heads * 64) fp16 = [q | k | v] with the
     1/sqrt(64) scale folded into q.  Returns (B, L, heads * 64) fp16."""
@@ -500,6 +543,7 @@ def attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- T0
+@_guard
 def text_pool(hidden: torch.Tensor, attention_mask: torch.Tensor, gamma: Optional[torch.Tensor] = None,
               beta: Optional[torch.Tensor] = None, *, l2: bool = True, want_feats: bool = True,
               want_q16: bool = True):

@@ -10,9 +10,13 @@ Multi-GPU: the reference all-gathers the vision tokens of
 computes the full (N_total x B_global) problem on each of them (losses.py:87-88, 156-161).
 Here the IMAGES stay where they are -- rank r owns columns [r*B_local, (r+1)*B_local) of the
 logit matrix -- and only small tensors cross NVLink:
-    forward   all-gather of the fp16 normalised sentence embeddings (N_total x 768) + group_map,
-              all-reduce(sum) of the per-sentence row sums / positives, all-reduce of 3 scalars
-    backward  all-reduce(sum) of dL/dq (N_total x 768 fp32); each rank keeps its own rows
+    forward   ONE all-gather of the fp16 normalised sentence embeddings (N_total x 768) + group_map
+              (fixed-capacity records, on a side stream under the token prep; the sentence counts
+              travel over a CPU-side gloo channel, so the GPU queue is never drained),
+              all-reduce(sum) of the per-sentence row sums / positives, all-reduce of the loss scalar
+    backward  reduce-scatter(sum) of dL/dq (N_total x 768 fp32) to the ranks that own the rows
+No call in the step reads device memory from the host: the temperatures are read by the kernels from
+the parameters (``log_tau`` pointers).
 Gradients returned to autograd are multiplied by the world size when ``ddp_compatible`` (the
 default under torch.distributed): the reference's ``dist.nn.all_gather`` backward sums the
 identical global loss of all W ranks and DDP then averages parameter gradients over W; the
@@ -20,7 +24,7 @@ scale makes this sharded step a drop-in under the same DDP wrapper.
 """
 from __future__ import annotations
 
-from typing import Optional
+from typing import List, Optional
 
 import torch
 import torch.distributed as dist
@@ -29,20 +33,116 @@ from . import ops
 from ._lib import RzError
 
 
-def _gather_rows(t: torch.Tensor, group=None):
-    """Ragged all-gather along dim 0 -> (cat, sizes list)."""
-    world = dist.get_world_size(group)
-    n_local = torch.tensor([t.shape[0]], device=t.device, dtype=torch.int64)
-    sizes = torch.empty(world, device=t.device, dtype=torch.int64)
-    dist.all_gather_into_tensor(sizes, n_local, group=group)
-    sizes_l = [int(s) for s in sizes.tolist()]
-    n_max = max(sizes_l)
-    padded = t.new_zeros((n_max,) + tuple(t.shape[1:]))
-    padded[: t.shape[0]] = t
-    out = t.new_empty((world * n_max,) + tuple(t.shape[1:]))
-    dist.all_gather_into_tensor(out, padded, group=group)
-    out = out.view((world, n_max) + tuple(t.shape[1:]))
-    return torch.cat([out[r, : sizes_l[r]] for r in range(world)], dim=0), sizes_l
+class _Comm:
+    """Per-process helper of the sharded step: a CPU-side (gloo) channel for the sentence counts, so the
+    ragged exchange needs NO device-to-host read (the GPU queue is never drained), and a side stream on
+    which the text all-gather overlaps the token prep."""
+
+    _inst = None
+
+    def __init__(self):
+        self.side_group = None
+        self.side_failed = False
+        self.stream = {}
+
+    @classmethod
+    def get(cls):
+        if cls._inst is None or cls._inst.world != dist.get_world_size():
+            cls._inst = cls()
+            cls._inst.world = dist.get_world_size()
+        return cls._inst
+
+    def sizes(self, n_local: int, device) -> List[int]:
+        """Sentence counts of all ranks.  gloo default group: a CPU all-gather; NCCL: a gloo side group
+        created once (collective on first use); only if that fails, the NCCL exchange + a host read."""
+        world = dist.get_world_size()
+        backend = dist.get_backend()
+        grp = None
+        if backend != "gloo" and not self.side_failed:
+            if self.side_group is None:
+                try:
+                    self.side_group = dist.new_group(backend="gloo")
+                except Exception:          # pragma: no cover - gloo not built in
+                    self.side_failed = True
+            grp = self.side_group
+        if backend == "gloo" or grp is not None:
+            mine = torch.tensor([int(n_local)], dtype=torch.int64)
+            out = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(out, mine, group=grp)
+            return [int(t.item()) for t in out]
+        n = torch.tensor([n_local], device=device, dtype=torch.int64)
+        sizes = torch.empty(world, device=device, dtype=torch.int64)
+        dist.all_gather_into_tensor(sizes, n)
+        return [int(v) for v in sizes.tolist()]
+
+    def side_stream(self, device):
+        if device.type != "cuda":
+            return None
+        st = self.stream.get(device.index)
+        if st is None:
+            st = self.stream[device.index] = torch.cuda.Stream(device=device)
+        return st
+
+
+def _gather_text(q_local: torch.Tensor, gm_local: torch.Tensor, sizes: List[int], side=None):
+    """ONE all-gather for the ragged (rows, group_map) pair: each rank contributes a fixed-capacity
+    byte record [cap rows | cap int64 indices]; the valid prefixes are concatenated afterwards.  With
+    ``side`` (a CUDA stream) the collective runs there; the caller waits on the returned event."""
+    world = len(sizes)
+    cap = max(max(sizes), 1)
+    n_local = q_local.shape[0]
+    row_b = q_local.shape[1] * q_local.element_size()
+    rec = cap * (row_b + 8)
+    send = torch.empty(rec, dtype=torch.uint8, device=q_local.device)
+    recv = torch.empty((world, rec), dtype=torch.uint8, device=q_local.device)
+    gm_local = gm_local.to(torch.int64)
+
+    def run():
+        send[: n_local * row_b].copy_(q_local.reshape(-1).view(torch.uint8))
+        send[cap * row_b: cap * row_b + n_local * 8].copy_(gm_local.view(torch.uint8))
+        dist.all_gather_into_tensor(recv.view(-1), send)
+
+    ev = None
+    if side is not None:
+        side.wait_stream(torch.cuda.current_stream(q_local.device))
+        with torch.cuda.stream(side):
+            run()
+            ev = torch.cuda.Event()
+            ev.record(side)
+    else:
+        run()
+
+    def unpack():
+        if ev is not None:
+            torch.cuda.current_stream(q_local.device).wait_event(ev)
+        rows = [recv[r, : sizes[r] * row_b].view(q_local.dtype).view(sizes[r], -1) for r in range(world)]
+        gms = [recv[r, cap * row_b: cap * row_b + sizes[r] * 8].view(torch.int64) for r in range(world)]
+        return torch.cat(rows, dim=0), torch.cat(gms, dim=0)
+
+    return unpack
+
+
+def _scatter_dq(dq: torch.Tensor, sizes: List[int], rank: int) -> torch.Tensor:
+    """dL/dq rows back to their owners: reduce-scatter (sum) of the per-rank sections, padded to a
+    common capacity.  Half the NVLink traffic of the round-1 all-reduce."""
+    world = len(sizes)
+    cap = max(max(sizes), 1)
+    if all(s == cap for s in sizes):
+        send = dq
+    else:
+        send = torch.empty((world * cap,) + tuple(dq.shape[1:]), dtype=dq.dtype, device=dq.device)
+        o = 0
+        for r, s in enumerate(sizes):
+            send[r * cap: r * cap + s].copy_(dq[o: o + s])
+            o += s
+    out = torch.empty((cap,) + tuple(dq.shape[1:]), dtype=dq.dtype, device=dq.device)
+    if dist.get_backend() == "gloo":       # CPU tests: gloo has no reduce_scatter
+        tmp = send.clone()
+        dist.all_reduce(tmp)
+        out.copy_(tmp[rank * cap: (rank + 1) * cap])
+    else:
+        dist.reduce_scatter_tensor(out, send)
+    return out[: sizes[rank]]
 
 
 class _ContrastiveStep(torch.autograd.Function):
@@ -58,13 +158,19 @@ class _ContrastiveStep(torch.autograd.Function):
         Lp = K.padded_tokens_bwd(L)
         g = gamma.detach() if gamma is not None else None
         b = beta.detach() if beta is not None else None
-        k16, _, _ = K.prep_rows(tokens.detach(), g, b, rows_per_group=L, rows_per_group_padded=Lp)
-        k16 = k16.view(B, Lp, ops.HIDDEN)
         q16_local, _, _ = K.prep_rows(text.detach(), g, b)
         n_local = q16_local.shape[0]
+        sizes = None
+        unpack = None
         if distributed:
-            q16, sizes = _gather_rows(q16_local)
-            gm, _ = _gather_rows(group_map)
+            comm = _Comm.get()
+            sizes = comm.sizes(n_local, q16_local.device)
+            # the text all-gather runs on a side stream while this stream normalises the tokens
+            unpack = _gather_text(q16_local, group_map, sizes, comm.side_stream(q16_local.device))
+        k16, _, _ = K.prep_rows(tokens.detach(), g, b, rows_per_group=L, rows_per_group_padded=Lp)
+        k16 = k16.view(B, Lp, ops.HIDDEN)
+        if distributed:
+            q16, gm = unpack()
             row0 = sum(sizes[:rank])
         else:
             q16, gm, row0 = q16_local, group_map, 0
@@ -78,41 +184,46 @@ class _ContrastiveStep(torch.autograd.Function):
         loss = None
         dz = terms = None
         if cfg["compute_loss"]:
-            inv_tau = float(torch.exp(-log_tau.detach()))
-            rs, ps, cn, cp = K.mpnce_partials(z, gm, col0, inv_tau)
+            # temperature read from the parameter on the device: no host synchronisation in the step
+            lt = log_tau.detach().reshape(1)
+            lt = lt.float() if z.is_cuda else lt
+            rowpos = torch.empty((2, n_total), dtype=torch.float32 if z.is_cuda else z.dtype,
+                                 device=z.device)      # rowsum | pos: ONE all-reduce message
+            rs, ps, cn, cp = K.mpnce_partials(z, gm, col0, log_tau=lt, rowpos=rowpos)
             if distributed:
-                both = torch.stack([rs, ps])
-                dist.all_reduce(both)
-                rs, ps = both[0], both[1]
-            terms, dz = K.mpnce_finish(z, gm, col0, b_global, inv_tau, rs, ps, cn, cp,
+                dist.all_reduce(rowpos)
+            terms, dz = K.mpnce_finish(z, gm, col0, b_global, 1.0, rs, ps, cn, cp, log_tau=lt,
                                        row_sum=cfg["row_sum"], col_sum=cfg["col_sum"], want_dz=True)
-            tsum = terms.clone()
+            loss = terms[3].clone()            # this rank's share; the sum over ranks is the loss
             if distributed:
-                dist.all_reduce(tsum)
-            n_row = b_global if cfg["row_sum"] else n_total
-            n_col = b_global if cfg["col_sum"] else n_total
-            loss = (tsum[0] / n_row + tsum[1] / n_col) * 0.5
+                dist.all_reduce(loss)
         ctx.K = K
         ctx.cfg = dict(cfg)
-        ctx.meta = (B, L, Lp, n_local, row0, world, attn_log_tau is not None)
+        ctx.meta = (B, L, Lp, n_local, row0, world, attn_log_tau is not None, sizes, rank)
         ctx.save_for_backward(text, tokens, gamma, beta, log_tau, attn_log_tau, k16, q16, z, dz,
                               fwd["lse"], fwd["onorm"], fwd["pooled"], terms, fwd.get("p"), fwd.get("mref"),
                               fwd.get("lsum"))
-        ctx.mark_non_differentiable(z)
+        z_out = z
+        if distributed and cfg.get("gather_logits"):
+            # the reference returns the full (N_total, B_global) matrix on every rank
+            blocks = torch.empty((world,) + tuple(z.shape), dtype=z.dtype, device=z.device)
+            dist.all_gather_into_tensor(blocks.view(-1), z.contiguous().view(-1))
+            z_out = blocks.permute(1, 0, 2).reshape(n_total, b_global)
+        ctx.mark_non_differentiable(z_out)
         scores = fwd["scores"]
         if scores is None:
             scores = z.new_empty(0)
         ctx.mark_non_differentiable(scores)
         if loss is None:
             loss = z.new_zeros(())
-        return loss, z, scores
+        return loss, z_out, scores
 
     @staticmethod
     def backward(ctx, g_loss, _gz, _gs):
         (text, tokens, gamma, beta, log_tau, attn_log_tau, k16, q16, z, dz, lse, onorm, pooled,
          terms, p_un, mref, lsum) = ctx.saved_tensors
         K = ctx.K
-        B, L, Lp, n_local, row0, world, has_attn = ctx.meta
+        B, L, Lp, n_local, row0, world, has_attn, sizes, rank = ctx.meta
         if dz is None:
             raise RzError("backward through the contrastive step needs compute_loss=True")
         distributed = ctx.cfg["distributed"]
@@ -123,8 +234,9 @@ class _ContrastiveStep(torch.autograd.Function):
         dq, dk, dlt_attn = K.sim_bwd(k16, q16, L, 1.0, z, dzs, lse, onorm, pooled, log_tau=a_lt.detach(),
                                      p=p_un, mref=mref, lsum=lsum)
         if distributed:
-            dist.all_reduce(dq)
-        dq_local = dq[row0: row0 + n_local].contiguous()
+            dq_local = _scatter_dq(dq, sizes, rank).contiguous()
+        else:
+            dq_local = dq
         dgamma = dbeta = None
         g = gamma.detach() if gamma is not None else None
         b = beta.detach() if beta is not None else None
@@ -148,13 +260,14 @@ class _ContrastiveStep(torch.autograd.Function):
 
 def contrastive_step(loss_fn, text: torch.Tensor, group_map: torch.Tensor, tokens: torch.Tensor, *,
                      distributed: bool, need_attn_weights: bool = False, compute_loss: bool = True,
-                     ddp_compatible: Optional[bool] = None, kernel_ops=None):
+                     ddp_compatible: Optional[bool] = None, kernel_ops=None, gather_logits: bool = False):
     """Run the fused step for a ``RadZeroLoss`` module; returns dict(loss, z, scores)."""
     gamma, beta = (loss_fn.layer_norm.weight, loss_fn.layer_norm.bias) if loss_fn.layer_norm is not None \
         else (None, None)
     cfg = dict(distributed=distributed, sim_op=loss_fn.sim_op, need_scores=need_attn_weights,
                compute_loss=compute_loss, row_sum=loss_fn.mpnce_row_sum, col_sum=loss_fn.mpnce_col_sum,
-               ddp_compatible=distributed if ddp_compatible is None else ddp_compatible)
+               ddp_compatible=distributed if ddp_compatible is None else ddp_compatible,
+               gather_logits=gather_logits)
     if kernel_ops is not None:
         cfg["ops"] = kernel_ops
     loss, z, scores = _ContrastiveStep.apply(text, tokens, gamma, beta, loss_fn.loss_temperature,

@@ -47,7 +47,9 @@ def sim_fwd(k16, q16, tokens, scale, *, log_tau_scale=None, want_scores=False, d
                 lse=torch.logsumexp(s, -1), onorm=o.norm(dim=-1), pooled=o)
 
 
-def mpnce_partials(z, group_map, col0, inv_tau):
+def mpnce_partials(z, group_map, col0, inv_tau=1.0, *, log_tau=None, rowpos=None):
+    if log_tau is not None:
+        inv_tau = float(torch.exp(-log_tau.double()))
     n, bl = z.shape
     E = torch.exp(z * inv_tau)
     g = group_map - col0
@@ -57,14 +59,21 @@ def mpnce_partials(z, group_map, col0, inv_tau):
     pos[idx] = E[idx, g[idx]]
     onehot = torch.zeros_like(E)
     onehot[idx, g[idx]] = 1.0
-    return E.sum(1), pos, (E * (1 - onehot)).sum(0), (E * onehot).sum(0)
+    rs = E.sum(1)
+    if rowpos is not None:          # the caller's (2, n) all-reduce buffer (fp32 in the product)
+        rowpos[0].copy_(rs)
+        rowpos[1].copy_(pos)
+        rs, pos = rowpos[0].to(z.dtype), rowpos[1].to(z.dtype)
+    return rs, pos, (E * (1 - onehot)).sum(0), (E * onehot).sum(0)
 
 
 def mpnce_finish(z, group_map, col0, b_global, inv_tau, rowsum, pos, colneg, colpos, *, eps=1e-8,
-                 row_sum=False, col_sum=False, want_dz=True):
+                 row_sum=False, col_sum=False, want_dz=True, log_tau=None):
     assert not row_sum and not col_sum, "the CPU stand-in covers the radzero configuration"
+    if log_tau is not None:
+        inv_tau = float(torch.exp(-log_tau.double()))
     with torch.enable_grad():
-        return _mpnce_finish(z, group_map, col0, inv_tau, rowsum, pos, eps)
+        return _mpnce_finish(z, group_map, col0, inv_tau, rowsum.to(z.dtype), pos.to(z.dtype), eps)
 
 
 def _mpnce_finish(z, group_map, col0, inv_tau, rowsum, pos, eps):
@@ -87,8 +96,8 @@ def _mpnce_finish(z, group_map, col0, inv_tau, rowsum, pos, eps):
     total = (row_terms.sum() + col_terms.sum()) / (2 * n)
     total.backward()
     dz = zz.grad
-    terms = torch.stack([row_terms[idx].sum().detach(), col_terms.sum().detach(), (dz * z).sum(),
-                         torch.zeros((), dtype=z.dtype)])
+    rt, ct = row_terms[idx].sum().detach(), col_terms.sum().detach()
+    terms = torch.stack([rt, ct, (dz * z).sum(), (rt + ct) / (2 * n)])
     return terms, dz
 
 
