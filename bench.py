@@ -379,6 +379,88 @@ def measure_inference(workload, steps, warmup, world, rank, local, pk):
                 fast_api="RadZeroLoss.similarity_prob" if workload == "cls" else "RadZeroLoss.similarity")
 
 
+def measure_preprocess(steps, world, rank, local, pk, cpu=True):
+    """the evaluators' image preprocessing (min-max -> uint8 -> bicubic 518 ->
+    normalise) for 256 synthetic 1024 x 1024 uint8 radiographs per step.  HBM-bound on its output."""
+    from radzero_b200 import ops
+    dev = torch.device("cuda", local)
+    B, H, W, OH, OW = 256, 1024, 1024, 518, 518
+    g = torch.Generator(device=dev)
+    g.manual_seed(7 + rank)
+    yy = torch.linspace(0, 1, H, device=dev).view(1, H, 1)
+    xx = torch.linspace(0, 1, W, device=dev).view(1, 1, W)
+    raw = ((0.6 * torch.sin(3 * yy) * torch.cos(2 * xx) + 0.3 * yy + 0.4) * 200
+           + 20 * torch.rand(B, H, W, device=dev, generator=g)).clamp_(0, 255).to(torch.uint8)
+    mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+    f = lambda r: ops.preprocess_images(r, (OH, OW), mean=mean, std=std)
+    for _ in range(3):
+        out = f(raw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = f(raw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    alg = B * (H * W + 3 * OH * OW * 4)
+    h_raw = raw.cpu().pin_memory()
+    d_raw = torch.empty_like(raw)
+    for _ in range(2):
+        d_raw.copy_(h_raw, non_blocking=True)
+        f(d_raw)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        d_raw.copy_(h_raw, non_blocking=True)
+        out = f(d_raw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1) / 3
+    res = {"workload": "256 x (1024 x 1024 uint8) -> pixel_values (256, 3, 518, 518) fp32", "value": _r(B / (ms * 1e-3), 5),
+           "unit": "images/s", "ms_per_step": _r(ms), "e2e": _r(B / (ms2 * 1e-3), 5),
+           "e2e_note": "pinned host uint8 -> H2D -> kernels; pixel_values stay on the GPU for the encoder",
+           "roofline": {"bound": "hbm", "frac": _r(alg / (ms * 1e-3) / 1e9 / pk["hbm"], 3),
+                        "achieved": _r(alg / (ms * 1e-3) / 1e9), "unit": "GB/s",
+                        "algorithmic_bytes": alg}}
+    if cpu and rank == 0:
+        res["cpu_baseline"] = preprocess_cpu_sample()
+    return res
+
+
+def preprocess_cpu_sample(n=4):
+    """The reference's own host chain (cv2 + Pillow + transformers) when importable, else the oracle port."""
+    import numpy as np
+    from radzero_b200 import synthetic
+    imgs = [synthetic.synthetic_cxr(1024, 1024, seed=s).numpy() for s in range(n)]
+    try:
+        import cv2
+        from PIL import Image
+        try:
+            from transformers import BlipImageProcessorPil as Proc
+        except ImportError:
+            from transformers import BlipImageProcessor as Proc
+        proc = Proc(size={"height": 518, "width": 518})
+
+        def chain(batch):
+            pil = [Image.fromarray(cv2.normalize(np.array(b), None, 0, 255, norm_type=cv2.NORM_MINMAX, dtype=cv2.CV_8U))
+                   for b in batch]
+            return torch.FloatTensor(np.array(proc(pil)["pixel_values"]))
+        kind = "reference"
+    except Exception:
+        from oracle import preprocess as opre
+
+        def chain(batch):
+            return torch.from_numpy(np.stack([opre.preprocess_image(b) for b in batch]))
+        kind = "port"
+    chain(imgs[:1])
+    t0 = time.perf_counter()
+    chain(imgs)
+    dt = time.perf_counter() - t0
+    return {"value": _r(n / dt, 4), "unit": "images/s", "cores": 1, "kind": kind,
+            "sample": f"{n} images through collate_fn's chain (cv2.normalize + BlipImageProcessor) in one process"}
+
+
 def compact_inference(m, workload):
     """Short form of an inference measurement for the add-on objects of the default line."""
     r = m["roofline"]
@@ -396,7 +478,7 @@ def compact_contrastive(c):
            "scaling": "strong", "steps": c["steps"], "ms_per_step": _r(c["ms_per_step"], 5), "loss": _r(c["loss"], 7),
            "grad_checksum": _r(c.get("grad_checksum"), 7), "matches_1rank": c.get("matches_1rank"),
            "roofline_frac": _r(c["roofline"]["frac"], 3), "tflops_per_gpu": _r(c["roofline"]["achieved"]),
-           "e2e": _r(c["e2e"]["value"], 5), "comm_us": c.get("comm_us"), "mpnce_us": _r(c["mpnce"]["ms"] * 1e3, 3),
+           "e2e": _r(c["e2e"]["value"], 5), "surface_ms": _r(c["surface"]["ms_per_step"], 5), "comm_us": c.get("comm_us"), "mpnce_us": _r(c["mpnce"]["ms"] * 1e3, 3),
            "mpnce_frac_of_hbm": _r(c["mpnce"]["frac_of_hbm"], 3), "mpnce_launches": c["mpnce"].get("launches"),
            "clocks": c.get("clocks")}
     return out
@@ -420,6 +502,13 @@ def run_ours(args):
             out["cpu_baseline"] = {"value": pairs / dt / full, "unit": "steps/s", "cores": os.cpu_count(),
                                    "kind": "port", "sample": f"fwd+bwd at 16 images x {pairs // 16} sentences on the "
                                    "fp32 CPU oracle, extrapolated by pair count"}
+        if rank == 0:
+            print(json.dumps(out))
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    if args.workload == "preprocess":
+        out = measure_preprocess(max(3, min(args.steps, 50)), world, rank, local, pk, cpu=not args.no_cpu)
         if rank == 0:
             print(json.dumps(out))
         if world > 1:
@@ -464,6 +553,11 @@ def run_ours(args):
             except Exception as e:  # never lose the main line to an add-on
                 addons[wl] = {"error": repr(e)[:200]}
             torch.cuda.empty_cache()
+        try:
+            addons["preprocess"] = measure_preprocess(10, world, rank, local, pk, cpu=(world == 1 and not args.no_cpu))
+        except Exception as e:
+            addons["preprocess"] = {"error": repr(e)[:200]}
+        torch.cuda.empty_cache()
         if not args.no_align:
             try:
                 from radzero_b200 import bench_align
@@ -684,7 +778,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cls", choices=list(WORKLOADS) + ["contrastive", "align"])
+    ap.add_argument("--workload", default="cls", choices=list(WORKLOADS) + ["contrastive", "align", "preprocess"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-align", action="store_true",
                     help="skip the AlignTransformer add-on of the default workload")

@@ -270,6 +270,29 @@ int rz_mpnce_finish(const float* z, long long ldz, int n_total, int b_local, int
                     const float* colpos, float* scratch2, float* dz, float* loss_terms,
                     void* stream);
 
+/* ---- K11: image preprocessing of the zero-shot evaluators ------------
+ * Replaces, for `images` same-sized raw images resident in device memory, the host-side chain
+ *   collate_fn (exp/cxr_pt/inference/dataset.py:31-51): cv2.normalize(img, None, 0, 255, NORM_MINMAX, CV_8U)
+ *   image_processor (exp/cxr_pt/model/processing.py:85-101, BlipImageProcessor at 518): convert to RGB,
+ *     PIL bicubic resize, * rescale_factor, (x - mean) / std, channels first
+ * with BIT-IDENTICAL results (oracle/preprocess.py pins the arithmetic against cv2 / Pillow / transformers).
+ *   raw          [images, height, width, channels] of `raw_dtype`, contiguous; channels = 1 (grey, replicated
+ *                to RGB) or 3 (interleaved RGB); min / max are taken over all channels, as cv2 does
+ *   mean_host, std_host  HOST pointers to 3 floats (image_mean / image_std as float32)
+ *   pixel_values [images, 3, out_h, out_w] of `out_dtype` (RZ_F32 is the reference's; RZ_F16 / RZ_BF16 round it)
+ *   workspace    rz_preprocess_workspace_bytes(...) bytes, 256-byte aligned
+ */
+#define RZ_IMG_U8 0
+#define RZ_IMG_U16 1
+#define RZ_IMG_I16 2
+#define RZ_IMG_I32 3
+#define RZ_IMG_F32 4
+size_t rz_preprocess_workspace_bytes(int images, int height, int width, int channels, int out_h, int out_w);
+int rz_preprocess_images(const void* raw, int raw_dtype, int images, int height, int width, int channels,
+                         int out_h, int out_w, const float* mean_host, const float* std_host,
+                         double rescale_factor, void* pixel_values, int out_dtype, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* ---- T0: text side ------------------------------------------
  * Masked mean pooling of the text encoder's token embeddings (exp/cxr_pt/model/modeling.py:147-156,
  * text_encoders.py:32-41) fused with the path's LayerNorm + L2 normalisation of the pooled vector

@@ -41,6 +41,7 @@ __all__ = [
     "grounding_point",
     "zero_shot_labels",
     "dice_sweep_stats",
+    "dice_score_samplewise",
     "compute_specificity",
     "contrastive_step_reference",
 ]
@@ -355,6 +356,23 @@ def dice_sweep_stats(similarity_scores: torch.Tensor, masks: torch.Tensor, origi
         mx.append(prob.max())
     return {"pred": torch.stack(pred), "inter": torch.stack(inter), "gt": (masks != 0).flatten(1).sum(1),
             "max_prob": torch.stack(mx), "thresholds": torch.as_tensor(thresholds)}
+
+
+def dice_score_samplewise(pred_masks: torch.Tensor, target_masks: torch.Tensor) -> torch.Tensor:
+    """What ``DiceScore(num_classes=1)(preds, target)`` of the reference's sweep returns
+    (segmentation_utils.py:255-258).  torchmetrics is a third-party dependency the reference does not
+    vendor (``torchmetrics==1.6.1``, requirements.txt:242) and is absent here, so its published algorithm
+    is restated (functional/segmentation/dice.py): per sample and class, numerator = 2 * sum(preds *
+    target), denominator = sum(preds) + sum(target) over the spatial axes; ``average="micro"`` sums both
+    over the class axis (one class here); dice = numerator / denominator with 1.0 where the denominator is
+    0; the metric is the nan-mean over samples.  Parity unpinned against the library itself -- the
+    formula is pinned by a hand-computed case in tests/test_oracle_golden.py."""
+    p = (pred_masks != 0).flatten(1).double()
+    g = (target_masks != 0).flatten(1).double()
+    num = 2.0 * (p * g).sum(1)
+    den = p.sum(1) + g.sum(1)
+    dice = torch.where(den > 0, num / den.clamp_min(1.0), torch.ones_like(den))
+    return dice.nanmean()
 
 
 def compute_specificity(negative_probs: torch.Tensor, threshold: float) -> float:

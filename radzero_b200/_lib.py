@@ -18,6 +18,7 @@ RZ_OK = 0
 RZ_F32, RZ_BF16, RZ_F16 = 0, 1, 2
 RZ_UP_RAW, RZ_UP_SIGMOID, RZ_UP_MASK, RZ_UP_ARGMAX = 0, 1, 2, 3
 RZ_LIN_BIAS, RZ_LIN_GELU, RZ_LIN_RESIDUAL = 0, 1, 2
+RZ_IMG_U8, RZ_IMG_U16, RZ_IMG_I16, RZ_IMG_I32, RZ_IMG_F32 = 0, 1, 2, 3, 4
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 _ull, _u = C.c_ulonglong, C.c_uint
@@ -50,6 +51,9 @@ SIGNATURES: Dict[str, tuple] = {
     "rz_mpnce_partials": (_i, [_vp, _ll, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rz_mpnce_finish": (_i, [_vp, _ll, _i, _i, _i, _vp, _i, _f, _vp, _f, _i, _i, _vp, _vp, _vp, _vp,
                              _vp, _vp, _vp, _vp]),
+    "rz_preprocess_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i, _i, _i]),
+    "rz_preprocess_images": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, C.c_double, _vp, _i, _vp,
+                                  C.c_size_t, _vp]),
     "rz_text_pool": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "rz_ln_rows": (_i, [_vp, _i, _vp, _vp, _f, _ll, _vp, _vp]),
     "rz_linear": (_i, [_vp, _ll, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
@@ -80,7 +84,7 @@ def load(build_if_missing: bool = True):
         if not build_if_missing:
             raise RzError(f"{LIB_PATH} is missing; run `python -m radzero_b200.build`")
         from . import build as _build
-        _build.build()
+        _build.build()          # serialised across processes by a file lock (torchrun ranks)
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError = ABI mismatch, fail loudly

@@ -100,7 +100,9 @@ class AlignTransformer(nn.Module):
 
     def _stamp(self):
         # (identity, in-place version) of every parameter: load_state_dict / optimizer steps bump versions
-        return tuple((id(p), p._version) for p in self.parameters())
+        # data_ptr catches `p.data = other` swaps (EMA, sharded optimizers) that leave the version untouched;
+        # `p.data.copy_()` into the same storage is invisible to both: call refresh() after such writes
+        return tuple((id(p), p._version, p.data_ptr()) for p in self.parameters())
 
     def _weights(self, device) -> List[Dict[str, torch.Tensor]]:
         stamp = self._stamp()
@@ -123,19 +125,24 @@ class AlignTransformer(nn.Module):
         return x
 
     def _needs_grad(self, vision_tokens: torch.Tensor) -> bool:
-        # only a module in TRAIN mode under autograd takes the stock path; in eval mode (the state
-        # every inference script of the reference puts the model in) the kernels always run, so a
-        # missing torch.no_grad() cannot silently select the slow path
-        if not (self.training and torch.is_grad_enabled()):
+        # a module in TRAIN mode under autograd takes the stock path; in eval mode (the state every
+        # inference script of the reference puts the model in) the kernels run, so a missing
+        # torch.no_grad() cannot silently select the slow path -- unless the INPUT itself asks for a
+        # gradient (saliency / Grad-CAM in eval mode), which only the stock path can provide
+        if not torch.is_grad_enabled():
             return False
-        return vision_tokens.requires_grad or any(p.requires_grad for p in self.parameters())
+        if vision_tokens.requires_grad:
+            return True
+        return self.training and any(p.requires_grad for p in self.parameters())
 
     def forward(self, vision_tokens: torch.Tensor, inplace: bool = False) -> torch.Tensor:
-        """``inplace=True`` lets the kernels update the caller's fp32 token buffer (no copy)."""
+        """``inplace=True`` lets the kernels update the caller's fp32 token buffer (no copy).  The result
+        comes back in the input's dtype, as the reference's module does (bf16 / fp16 models)."""
         if self._needs_grad(vision_tokens):
             return self.stock_forward(vision_tokens)
         with torch.no_grad():
-            return self._forward_kernels(vision_tokens, inplace)
+            out = self._forward_kernels(vision_tokens, inplace)
+        return out if out.dtype == vision_tokens.dtype else out.to(vision_tokens.dtype)
 
     def _forward_kernels(self, vision_tokens: torch.Tensor, inplace: bool) -> torch.Tensor:
         if not vision_tokens.is_cuda:

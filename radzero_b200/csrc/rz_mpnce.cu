@@ -42,96 +42,123 @@ __device__ __forceinline__ float inv_temperature(const float* log_tau, float inv
 }
 
 // ---- launch 1 --------------------------------------------------------------------------
-// Phase A: a CTA takes chunks of 32 rows x all local columns (256 at a time).  Thread t owns column
-// c0+t: it walks the 32 rows, accumulating the column partials; E is parked in smem so that warp w
-// can then reduce rows 4w..4w+3 across the tile.  Phase B (after the grid barrier): one warp per
-// column adds the chunk partials in a fixed order.
+// Phase A: a CTA takes chunks of 32 rows; warp w owns rows 4w..4w+3 and walks them across the local
+// columns in blocks of 1024: a lane reads eight float4 per row (all loads of a row are issued before
+// the first exponential: memory-level parallelism), adds them to its 32 column accumulators and to
+// the row sum, and the lane that holds the positive column records pos[i].  The eight warps' column
+// accumulators are then combined through shared memory in a fixed order -> colpart[chunk][column].
+// Phase B (after the grid barrier): one warp per column adds the chunk partials and the positives of
+// that column (lanes stride the chunks / sentences, then an xor butterfly: a fixed order).
 struct PartialsParams {
   const float* z; long long ldz; int n_total, b_local;
   const long long* group_map; int col0; float inv_tau; const float* log_tau;
   float *rowsum, *pos, *colneg, *colpos;
-  float* colpart;            // [chunks][2][b_local]
+  float* colpart;            // [chunks][b_local]: sum over the chunk's rows of E (negatives AND positives)
   unsigned int* barrier;
 };
 
+constexpr int kColBlock = 1024;      // columns per pass: 32 lanes x 8 groups x 4
+
+template <bool VEC>
+__device__ __forceinline__ float4 load4(const float* row, int c, int b_local) {
+  if (VEC) {
+    return c < b_local ? __ldg(reinterpret_cast<const float4*>(row + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4 v;
+  v.x = c + 0 < b_local ? __ldg(row + c + 0) : 0.f;
+  v.y = c + 1 < b_local ? __ldg(row + c + 1) : 0.f;
+  v.z = c + 2 < b_local ? __ldg(row + c + 2) : 0.f;
+  v.w = c + 3 < b_local ? __ldg(row + c + 3) : 0.f;
+  return v;
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(kThreads)
 mpnce_partials_kernel(PartialsParams p) {
-  __shared__ float tile[kRowChunk][kThreads + 1];
-  __shared__ int gcol[kRowChunk];
+  __shared__ float colbuf[kWarps][kColBlock];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const float inv_tau = inv_temperature(p.log_tau, p.inv_tau);
   const int chunks = (p.n_total + kRowChunk - 1) / kRowChunk;
   const int b_local = p.b_local;
   for (int chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
-    const int r0 = chunk * kRowChunk;
-    const int nrows = min(kRowChunk, p.n_total - r0);
-    __syncthreads();
-    if (t < kRowChunk) {
-      int g = -1;
-      if (t < nrows) {
-        const long long gg = p.group_map[r0 + t] - (long long)p.col0;
-        g = (gg >= 0 && gg < b_local) ? (int)gg : -1;
-        if (g < 0) p.pos[r0 + t] = 0.f;
-      }
-      gcol[t] = g;
-    }
-    __syncthreads();
+    const int r0 = chunk * kRowChunk + warp * 4;
     float racc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c0 = 0; c0 < b_local; c0 += kThreads) {
-      const int c = c0 + t;
-      float cneg = 0.f, cpos = 0.f;
-      // loads of 8 rows are issued before their exponentials (memory-level parallelism)
-      for (int rb = 0; rb < nrows; rb += 8) {
-        float zz[8];
+    int gloc[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          zz[u] = (c < b_local && rb + u < nrows) ? __ldg(p.z + (long long)(r0 + rb + u) * p.ldz + c) : 0.f;
+    for (int rr = 0; rr < 4; ++rr) {
+      gloc[rr] = -1;
+      if (r0 + rr < p.n_total) {
+        const long long gg = __ldg(p.group_map + r0 + rr) - (long long)p.col0;
+        gloc[rr] = (gg >= 0 && gg < b_local) ? (int)gg : -1;
+        if (gloc[rr] < 0 && lane == 0) p.pos[r0 + rr] = 0.f;
+      }
+    }
+    for (int cb = 0; cb < b_local; cb += kColBlock) {
+      float cacc[8][4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int r = rb + u;
-          if (r >= nrows) break;
-          float e = 0.f;
-          if (c < b_local) {
-            e = __expf(zz[u] * inv_tau);
-            if (gcol[r] == c) { cpos += e; p.pos[r0 + r] = e; } else { cneg += e; }
+      for (int j = 0; j < 8; ++j) { cacc[j][0] = cacc[j][1] = cacc[j][2] = cacc[j][3] = 0.f; }
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        if (r0 + rr >= p.n_total) continue;                 // warp-uniform
+        const float* row = p.z + (long long)(r0 + rr) * p.ldz;
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = load4<VEC>(row, cb + 128 * j + 4 * lane, b_local);
+        float rs = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = cb + 128 * j + 4 * lane;
+          float e[4] = {__expf(v[j].x * inv_tau), __expf(v[j].y * inv_tau), __expf(v[j].z * inv_tau),
+                        __expf(v[j].w * inv_tau)};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (c + u >= b_local) e[u] = 0.f;
+            cacc[j][u] += e[u];
+            rs += e[u];
+            if (c + u == gloc[rr]) p.pos[r0 + rr] = e[u];
           }
-          tile[r][t] = e;
+        }
+        racc[rr] += rz::warp_sum(rs);
+      }
+      __syncthreads();                                       // colbuf free (previous block consumed)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(&colbuf[warp][128 * j + 4 * lane]) =
+            make_float4(cacc[j][0], cacc[j][1], cacc[j][2], cacc[j][3]);
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < kColBlock / kThreads; ++k) {
+        const int c = t + k * kThreads;
+        if (cb + c < b_local) {
+          float sum = 0.f;
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) sum += colbuf[w][c];
+          p.colpart[(long long)chunk * b_local + cb + c] = sum;
         }
       }
-      if (c < b_local) {
-        p.colpart[((long long)chunk * 2 + 0) * b_local + c] = cneg;
-        p.colpart[((long long)chunk * 2 + 1) * b_local + c] = cpos;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = warp * 4 + k;
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < kThreads / 32; ++j) s += tile[r][lane + 32 * j];
-        racc[k] += rz::warp_sum(s);
-      }
-      __syncthreads();
     }
     if (lane == 0) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = warp * 4 + k;
-        if (r < nrows) p.rowsum[r0 + r] = racc[k];
-      }
+      for (int rr = 0; rr < 4; ++rr)
+        if (r0 + rr < p.n_total) p.rowsum[r0 + rr] = racc[rr];
     }
   }
   grid_barrier(p.barrier);
-  // column sums: lanes stride the chunks, then an xor butterfly -- the same order on every run
   for (int c = blockIdx.x * kWarps + warp; c < b_local; c += gridDim.x * kWarps) {
-    float n = 0.f, q = 0.f;
-    for (int k = lane; k < chunks; k += 32) {
-      n += __ldcg(p.colpart + ((long long)k * 2 + 0) * b_local + c);
-      q += __ldcg(p.colpart + ((long long)k * 2 + 1) * b_local + c);
+    float all = 0.f, cp = 0.f;
+    for (int k = lane; k < chunks; k += 32) all += __ldcg(p.colpart + (long long)k * b_local + c);
+    const long long gcol = (long long)p.col0 + c;
+    for (int i0 = lane; i0 < p.n_total; i0 += 128) {
+      long long g[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) g[u] = i0 + 32 * u < p.n_total ? __ldg(p.group_map + i0 + 32 * u) : -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (g[u] == gcol) cp += __ldcg(p.pos + i0 + 32 * u);
     }
-    n = rz::warp_sum(n);
-    q = rz::warp_sum(q);
-    if (lane == 0) { p.colneg[c] = n; p.colpos[c] = q; }
+    all = rz::warp_sum(all);
+    cp = rz::warp_sum(cp);
+    if (lane == 0) { p.colneg[c] = all - cp; p.colpos[c] = cp; }
   }
 }
 
@@ -150,6 +177,7 @@ struct FinishParams {
 };
 
 // dZ_ib = E_ib/tau * (ca_i + [b==g_i](cb_i + apos_b) + [b!=g_i] acol_b)
+template <bool VEC>
 __global__ void __launch_bounds__(kThreads)
 mpnce_finish_kernel(FinishParams p) {
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -172,14 +200,20 @@ mpnce_finish_kernel(FinishParams p) {
     } else {
       // MP-NCE: one term per sentence i of this image: p = pos_i/(pos_i + Cneg + eps)  :337-342
       const float cn = p.colneg[c];
-      for (int i = lane; i < p.n_total; i += 32) {
-        if (__ldg(p.group_map + i) != gcol) continue;
-        const float ps = p.pos[i];
-        const float den = ps + cn + p.eps;
-        const float pc = ps / den;
-        const float u = 1.0f / (pc + p.eps);
-        l += -logf(pc + p.eps);
-        a += u * ps / (den * den);
+      for (int i0 = lane; i0 < p.n_total; i0 += 128) {
+        long long g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) g[u] = i0 + 32 * u < p.n_total ? __ldg(p.group_map + i0 + 32 * u) : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (g[u] != gcol) continue;
+          const float ps = p.pos[i0 + 32 * u];
+          const float den = ps + cn + p.eps;
+          const float pc = ps / den;
+          const float w = 1.0f / (pc + p.eps);
+          l += -logf(pc + p.eps);
+          a += w * ps / (den * den);
+        }
       }
       a = rz::warp_sum(a);
       l = rz::warp_sum(l);
@@ -227,25 +261,48 @@ mpnce_finish_kernel(FinishParams p) {
       const float u = 1.0f / (pc + p.eps);
       cb += -u * (den - ps) / (den * den) * p.inv_2ncol;
     }
+    const float pos_coef = gl >= 0 ? ca + cb + __ldcg(p.apos + gl) : 0.f;   // the positive's own column
     const float* zr = p.z + (long long)r * p.ldz;
     float* dr = p.dz != nullptr ? p.dz + (long long)r * p.ldz : nullptr;
     float acc = 0.f;
-    for (int c0 = 0; c0 < p.b_local; c0 += 128) {
-      float zz[4];
+    for (int c0 = 0; c0 < p.b_local; c0 += kColBlock) {
+      float4 v[8], ac[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = c0 + u * 32 + lane;
-        zz[u] = c < p.b_local ? __ldg(zr + c) : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + 128 * j + 4 * lane;
+        v[j] = load4<VEC>(zr, c, p.b_local);
+        if (VEC) {
+          ac[j] = c < p.b_local ? __ldcg(reinterpret_cast<const float4*>(p.acol + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          ac[j].x = c + 0 < p.b_local ? __ldcg(p.acol + c + 0) : 0.f;
+          ac[j].y = c + 1 < p.b_local ? __ldcg(p.acol + c + 1) : 0.f;
+          ac[j].z = c + 2 < p.b_local ? __ldcg(p.acol + c + 2) : 0.f;
+          ac[j].w = c + 3 < p.b_local ? __ldcg(p.acol + c + 3) : 0.f;
+        }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = c0 + u * 32 + lane;
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + 128 * j + 4 * lane;
         if (c >= p.b_local) continue;
-        const float e = __expf(zz[u] * inv_tau);
-        const float coef = ca + (c == gl ? cb + __ldcg(p.apos + c) : __ldcg(p.acol + c));
-        const float d = e * inv_tau * coef;
-        if (dr != nullptr) dr[c] = d;
-        acc = fmaf(d, zz[u], acc);
+        const float zz[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+        const float aa[4] = {ac[j].x, ac[j].y, ac[j].z, ac[j].w};
+        float d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float e = __expf(zz[u] * inv_tau);
+          const float coef = (c + u == gl) ? pos_coef : ca + aa[u];
+          d[u] = c + u < p.b_local ? e * inv_tau * coef : 0.f;
+          acc = fmaf(d[u], zz[u], acc);
+        }
+        if (dr != nullptr) {
+          if (VEC) {
+            *reinterpret_cast<float4*>(dr + c) = make_float4(d[0], d[1], d[2], d[3]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (c + u < p.b_local) dr[c + u] = d[u];
+          }
+        }
       }
     }
     acc = rz::warp_sum(acc);
@@ -294,11 +351,11 @@ int coop_grid(K kernel, int wanted) {
 
 extern "C" size_t rz_mpnce_partials_scratch_floats(int n_total, int b_local) {
   const long long chunks = (n_total + kRowChunk - 1) / kRowChunk;
-  return (size_t)(2 * chunks * (long long)b_local + 4);
+  return (size_t)(chunks * (long long)b_local + 4);
 }
 
 extern "C" size_t rz_mpnce_finish_scratch_floats(int n_total, int b_local, int b_global) {
-  return (size_t)(2LL * n_total + 3LL * b_local + 2LL * b_global + 4);
+  return (size_t)(2LL * n_total + 3LL * ((b_local + 3) / 4 * 4) + 2LL * b_global + 4);
 }
 
 extern "C" int rz_mpnce_partials(const float* z, long long ldz, int n_total, int b_local,
@@ -314,11 +371,14 @@ extern "C" int rz_mpnce_partials(const float* z, long long ldz, int n_total, int
   p.col0 = col0; p.inv_tau = inv_tau; p.log_tau = log_tau;
   p.rowsum = rowsum; p.pos = pos; p.colneg = colneg; p.colpos = colpos;
   p.colpart = scratch1;
-  p.barrier = reinterpret_cast<unsigned int*>(scratch1 + 2LL * chunks * b_local);
+  p.barrier = reinterpret_cast<unsigned int*>(scratch1 + (long long)chunks * b_local);
   RZ_CUDA_OK(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned int), s));
-  const int grid = coop_grid(mpnce_partials_kernel, chunks);
+  // float4 path: 16-byte aligned rows (the usual case: b_local a multiple of 4)
+  const bool vec = (reinterpret_cast<uintptr_t>(z) % 16 == 0) && (ldz % 4 == 0);
+  const void* kern = vec ? (const void*)mpnce_partials_kernel<true> : (const void*)mpnce_partials_kernel<false>;
+  const int grid = vec ? coop_grid(mpnce_partials_kernel<true>, chunks) : coop_grid(mpnce_partials_kernel<false>, chunks);
   void* args[] = {&p};
-  RZ_CUDA_OK(cudaLaunchCooperativeKernel((const void*)mpnce_partials_kernel, dim3(grid), dim3(kThreads), args, 0, s));
+  RZ_CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kThreads), args, 0, s));
   rz_count_launch(1);
   return RZ_OK;
 }
@@ -341,9 +401,10 @@ extern "C" int rz_mpnce_finish(const float* z, long long ldz, int n_total, int b
   p.row_sum = row_sum; p.col_sum = col_sum;
   p.rowsum = rowsum; p.pos = pos; p.colneg = colneg; p.colpos = colpos;
   float* w = scratch2;
-  p.acol = w; w += b_local;
-  p.apos = w; w += b_local;
-  p.lcol = w; w += b_local;
+  const int bl4 = (b_local + 3) / 4 * 4;
+  p.acol = w; w += bl4;
+  p.apos = w; w += bl4;
+  p.lcol = w; w += bl4;
   p.img_rs = w; w += b_global;
   p.img_ps = w; w += b_global;
   p.lrow = w; w += n_total;
@@ -353,9 +414,14 @@ extern "C" int rz_mpnce_finish(const float* z, long long ldz, int n_total, int b
   p.inv_2nrow = 0.5f / (float)(row_sum ? b_global : n_total);
   p.inv_2ncol = 0.5f / (float)(col_sum ? b_global : n_total);
   RZ_CUDA_OK(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned int), s));
-  const int grid = coop_grid(mpnce_finish_kernel, (n_total + kWarps - 1) / kWarps);
+  const bool vec = (reinterpret_cast<uintptr_t>(z) % 16 == 0) && (ldz % 4 == 0) &&
+                   (reinterpret_cast<uintptr_t>(scratch2) % 16 == 0) &&
+                   (dz == nullptr || reinterpret_cast<uintptr_t>(dz) % 16 == 0);
+  const int want = (n_total + kWarps - 1) / kWarps;
+  const void* kern = vec ? (const void*)mpnce_finish_kernel<true> : (const void*)mpnce_finish_kernel<false>;
+  const int grid = vec ? coop_grid(mpnce_finish_kernel<true>, want) : coop_grid(mpnce_finish_kernel<false>, want);
   void* args[] = {&p};
-  RZ_CUDA_OK(cudaLaunchCooperativeKernel((const void*)mpnce_finish_kernel, dim3(grid), dim3(kThreads), args, 0, s));
+  RZ_CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kThreads), args, 0, s));
   rz_count_launch(1);
   return RZ_OK;
 }

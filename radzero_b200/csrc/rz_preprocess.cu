@@ -1,0 +1,309 @@
+// K11: image preprocessing of the zero-shot evaluators on the GPU.
+//
+// Replaces, for a batch of same-sized raw images already in device memory,
+//   collate_fn  exp/cxr_pt/inference/dataset.py:31-51  cv2.normalize(.., 0, 255, NORM_MINMAX, CV_8U)
+//   image_processor(...)  exp/cxr_pt/model/processing.py:85-101  BlipImageProcessor at 518: convert to RGB,
+//               PIL bicubic resize of the uint8 image, * 1/255, (x - mean) / std, channels first
+// with results BIT-IDENTICAL to OpenCV + Pillow + transformers (oracle/preprocess.py restates and pins the
+// arithmetic): the min-max stretch is one float FMA rounded half-to-even, the resize is Pillow's 8-bit
+// fixed-point separable filter (22 fractional bits, uint8 intermediate, horizontal pass first), the
+// normalisation is a 256-entry table per channel.
+//
+//   pp_coeff_kernel     filter taps of both passes, in double, no FMA contraction   (2 tiny CTAs)
+//   pp_minmax_kernel    per-image min / max partials                               read raw once
+//   pp_horizontal_kernel  raw row -> uint8 (FMA) in shared memory -> W_out outputs  read raw, write tmp
+//   pp_vertical_kernel  tmp rows -> uint8 -> table -> 3 x H_out x W_out floats      write pixel_values
+// HBM-bound on the output (3 x 518 x 518 x 4 B per image); the uint8 intermediate stays in L2.
+#include <cfloat>
+
+#include "rz_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kPrecisionBits = 32 - 8 - 2;    // Pillow Resample.c
+constexpr int kMinMaxSplit = 16;              // partial (min, max) pairs per image
+
+struct Taps {        // one pass: for output index o, source window [xmin[o], xmin[o] + cnt[o]) and its weights
+  int* xmin; int* cnt; int* w; int ksize;
+};
+
+__host__ __device__ inline int pil_ksize(int in_size, int out_size) {
+  double scale = (double)in_size / (double)out_size;
+  double filterscale = scale < 1.0 ? 1.0 : scale;
+  double support = 2.0 * filterscale;
+  return (int)ceil(support) * 2 + 1;
+}
+
+// Pillow's bicubic_filter with a = -0.5, every operation rounded separately (as x86-64 C without FMA)
+__device__ double bicubic_filter(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) {
+    double t = __dsub_rn(__dmul_rn(__dadd_rn(a, 2.0), x), __dadd_rn(a, 3.0));
+    return __dadd_rn(__dmul_rn(__dmul_rn(t, x), x), 1.0);
+  }
+  if (x < 2.0) {
+    double t = __dadd_rn(__dmul_rn(__dsub_rn(x, 5.0), x), 8.0);
+    t = __dsub_rn(__dmul_rn(t, x), 4.0);
+    return __dmul_rn(t, a);
+  }
+  return 0.0;
+}
+
+// precompute_coeffs + normalize_coeffs_8bpc (Resample.c) for the full-image box.  blockIdx.x = pass.
+__global__ void pp_coeff_kernel(Taps th, int w_in, int w_out, Taps tv, int h_in, int h_out) {
+  const Taps t = blockIdx.x == 0 ? th : tv;
+  const int in_size = blockIdx.x == 0 ? w_in : h_in;
+  const int out_size = blockIdx.x == 0 ? w_out : h_out;
+  const double scale = (double)in_size / (double)out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = __dmul_rn(2.0, filterscale);
+  const double ss = 1.0 / filterscale;
+  for (int xx = threadIdx.x; xx < out_size; xx += blockDim.x) {
+    const double center = __dmul_rn(__dadd_rn((double)xx, 0.5), scale);
+    int lo = (int)__dadd_rn(__dsub_rn(center, support), 0.5);
+    if (lo < 0) lo = 0;
+    int hi = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
+    if (hi > in_size) hi = in_size;
+    const int n = hi - lo;
+    int* wk = t.w + (long long)xx * t.ksize;
+    double ww = 0.0;
+    for (int x = 0; x < n; ++x) {
+      const double arg = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + lo), center), 0.5), ss);
+      ww = __dadd_rn(ww, bicubic_filter(arg));
+    }
+    for (int x = 0; x < t.ksize; ++x) {
+      int q = 0;
+      if (x < n) {
+        const double arg = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + lo), center), 0.5), ss);
+        double v = bicubic_filter(arg);
+        if (ww != 0.0) v = __ddiv_rn(v, ww);
+        q = (int)__dadd_rn(__dmul_rn(v, (double)(1 << kPrecisionBits)), v < 0.0 ? -0.5 : 0.5);
+      }
+      wk[x] = q;
+    }
+    t.xmin[xx] = lo;
+    t.cnt[xx] = n;
+  }
+}
+
+template <typename T> __device__ __forceinline__ float as_float(T v) { return (float)v; }
+
+// per-image min / max over all channels (cv::minMaxIdx); values compared as double (exact for every type)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+pp_minmax_kernel(const T* __restrict__ raw, long long per_image, double* __restrict__ part) {
+  const int img = blockIdx.y, split = blockIdx.x;
+  const T* src = raw + (long long)img * per_image;
+  const long long per = (per_image + kMinMaxSplit - 1) / kMinMaxSplit;
+  const long long i0 = (long long)split * per, i1 = min(per_image, i0 + per);
+  double lo = DBL_MAX, hi = -DBL_MAX;
+  for (long long i = i0 + threadIdx.x; i < i1; i += kThreads) {
+    const double v = (double)src[i];
+    lo = fmin(lo, v);
+    hi = fmax(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ double slo[kThreads / 32], shi[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < kThreads / 32; ++k) { lo = fmin(lo, slo[k]); hi = fmax(hi, shi[k]); }
+    part[((long long)img * kMinMaxSplit + split) * 2 + 0] = lo;
+    part[((long long)img * kMinMaxSplit + split) * 2 + 1] = hi;
+  }
+}
+
+__device__ __forceinline__ uint8_t clip8(int v) {
+  v >>= kPrecisionBits;
+  return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// Horizontal pass.  One CTA handles `rows` consecutive rows of one image: the raw row is stretched to uint8
+// (saturate(rint(fma(src, a, b)))) into shared memory, then thread o accumulates output column o.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+pp_horizontal_kernel(const T* __restrict__ raw, int H, int W, int C, const double* __restrict__ part,
+                     Taps t, int w_out, int pitch, uint8_t* __restrict__ tmp, int rows) {
+  extern __shared__ uint8_t srow[];          // [C][W] planar
+  const int img = blockIdx.y;
+  __shared__ float sa, sb;
+  if (threadIdx.x == 0) {
+    double lo = DBL_MAX, hi = -DBL_MAX;
+    for (int k = 0; k < kMinMaxSplit; ++k) {
+      lo = fmin(lo, part[((long long)img * kMinMaxSplit + k) * 2 + 0]);
+      hi = fmax(hi, part[((long long)img * kMinMaxSplit + k) * 2 + 1]);
+    }
+    // cv::normalize, NORM_MINMAX: scale = (255 - 0) * (1 / (smax - smin)), shift = 0 - smin * scale
+    const double scale = __dmul_rn(255.0, (hi - lo > DBL_EPSILON) ? __ddiv_rn(1.0, __dsub_rn(hi, lo)) : 0.0);
+    const double shift = __dsub_rn(0.0, __dmul_rn(lo, scale));
+    sa = (float)scale;
+    sb = (float)shift;
+  }
+  __syncthreads();
+  const float a = sa, b = sb;
+  const int y0 = blockIdx.x * rows;
+  for (int y = y0; y < min(H, y0 + rows); ++y) {
+    const T* src = raw + (((long long)img * H + y) * W) * C;
+    __syncthreads();
+    for (int i = threadIdx.x; i < W * C; i += kThreads) {
+      const float v = __fmaf_rn(as_float(src[i]), a, b);
+      int q = __float2int_rn(v);                         // cvRound: round half to even
+      q = q < 0 ? 0 : (q > 255 ? 255 : q);
+      const int x = i / C, c = i - x * C;
+      srow[c * W + x] = (uint8_t)q;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < w_out * C; o += kThreads) {
+      const int c = o / w_out, xo = o - c * w_out;
+      const int lo = __ldg(t.xmin + xo), n = __ldg(t.cnt + xo);
+      const int* wk = t.w + (long long)xo * t.ksize;
+      const uint8_t* s = srow + c * W + lo;
+      int acc = 1 << (kPrecisionBits - 1);
+      for (int k = 0; k < n; ++k) acc += (int)s[k] * __ldg(wk + k);
+      tmp[(((long long)img * C + c) * H + y) * pitch + xo] = clip8(acc);
+    }
+  }
+}
+
+struct NormParams { float mean[3], std[3]; double rescale; };
+
+template <typename TOut> __device__ __forceinline__ TOut to_out(float v);
+template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half to_out<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// Vertical pass + rescale + normalise.  One CTA = `rows` output rows of one image; thread x walks the taps of
+// its column (coalesced across the warp), then maps the uint8 result through the per-channel table.
+template <typename TOut>
+__global__ void __launch_bounds__(kThreads)
+pp_vertical_kernel(const uint8_t* __restrict__ tmp, int H, int C, int pitch, Taps t, int h_out, int w_out,
+                   NormParams np, TOut* __restrict__ out, int rows) {
+  __shared__ float lut[3][256];
+  for (int i = threadIdx.x; i < 768; i += kThreads) {
+    const int c = i >> 8, v = i & 255;
+    // image_transforms.rescale: float64 product cast to float32; normalize: (x - mean) / std in float32
+    const float r = (float)__dmul_rn((double)v, np.rescale);
+    lut[c][v] = __fdiv_rn(__fsub_rn(r, np.mean[c]), np.std[c]);
+  }
+  __syncthreads();
+  const int img = blockIdx.y;
+  const int y0 = blockIdx.x * rows;
+  for (int yo = y0; yo < min(h_out, y0 + rows); ++yo) {
+    const int lo = __ldg(t.xmin + yo), n = __ldg(t.cnt + yo);
+    const int* wk = t.w + (long long)yo * t.ksize;
+    for (int x = threadIdx.x; x < w_out; x += kThreads) {
+      uint8_t q[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (c < C) {
+          const uint8_t* s = tmp + (((long long)img * C + c) * H + lo) * pitch + x;
+          int acc = 1 << (kPrecisionBits - 1);
+          for (int k = 0; k < n; ++k) acc += (int)s[(long long)k * pitch] * __ldg(wk + k);
+          q[c] = clip8(acc);
+        } else {
+          q[c] = q[0];                                     // convert_to_rgb replicates a grey plane
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        out[(((long long)img * 3 + c) * h_out + yo) * w_out + x] = to_out<TOut>(lut[c][q[c]]);
+    }
+  }
+}
+
+struct Plan {
+  int ks_h, ks_v, pitch;
+  size_t off_part, off_taps, off_tmp, total;
+};
+
+Plan make_plan(int images, int H, int W, int C, int h_out, int w_out) {
+  Plan p;
+  p.ks_h = pil_ksize(W, w_out);
+  p.ks_v = pil_ksize(H, h_out);
+  p.pitch = (w_out + 15) / 16 * 16;
+  size_t o = 0;
+  p.off_part = o; o += (size_t)images * kMinMaxSplit * 2 * sizeof(double);
+  p.off_taps = o; o += ((size_t)w_out * (2 + p.ks_h) + (size_t)h_out * (2 + p.ks_v)) * sizeof(int);
+  o = (o + 255) / 256 * 256;
+  p.off_tmp = o; o += (size_t)images * C * H * p.pitch;
+  p.total = o;
+  return p;
+}
+
+template <typename T>
+int run(const T* raw, int images, int H, int W, int C, int h_out, int w_out, const NormParams& np,
+        void* out, int out_dtype, uint8_t* ws, cudaStream_t s) {
+  const Plan pl = make_plan(images, H, W, C, h_out, w_out);
+  double* part = reinterpret_cast<double*>(ws + pl.off_part);
+  int* ti = reinterpret_cast<int*>(ws + pl.off_taps);
+  Taps th, tv;
+  th.xmin = ti; ti += w_out; th.cnt = ti; ti += w_out; th.w = ti; ti += (size_t)w_out * pl.ks_h; th.ksize = pl.ks_h;
+  tv.xmin = ti; ti += h_out; tv.cnt = ti; ti += h_out; tv.w = ti; tv.ksize = pl.ks_v;
+  uint8_t* tmp = ws + pl.off_tmp;
+  pp_coeff_kernel<<<2, kThreads, 0, s>>>(th, W, w_out, tv, H, h_out);
+  RZ_LAUNCH_OK();
+  pp_minmax_kernel<T><<<dim3(kMinMaxSplit, images), kThreads, 0, s>>>(raw, (long long)H * W * C, part);
+  RZ_LAUNCH_OK();
+  const int rows_h = 4;
+  const size_t smem = (size_t)W * C;
+  if (smem > 96 * 1024) return RZ_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    RZ_CUDA_OK(cudaFuncSetAttribute(pp_horizontal_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pp_horizontal_kernel<T><<<dim3((H + rows_h - 1) / rows_h, images), kThreads, smem, s>>>(
+      raw, H, W, C, part, th, w_out, pl.pitch, tmp, rows_h);
+  RZ_LAUNCH_OK();
+  const int rows_v = 2;
+  const dim3 gv((h_out + rows_v - 1) / rows_v, images);
+  if (out_dtype == RZ_F32)
+    pp_vertical_kernel<float><<<gv, kThreads, 0, s>>>(tmp, H, C, pl.pitch, tv, h_out, w_out, np, (float*)out, rows_v);
+  else if (out_dtype == RZ_F16)
+    pp_vertical_kernel<__half><<<gv, kThreads, 0, s>>>(tmp, H, C, pl.pitch, tv, h_out, w_out, np, (__half*)out, rows_v);
+  else
+    pp_vertical_kernel<__nv_bfloat16><<<gv, kThreads, 0, s>>>(tmp, H, C, pl.pitch, tv, h_out, w_out, np,
+                                                             (__nv_bfloat16*)out, rows_v);
+  RZ_LAUNCH_OK();
+  rz_count_launch(4);
+  return RZ_OK;
+}
+
+}  // namespace
+
+extern "C" size_t rz_preprocess_workspace_bytes(int images, int height, int width, int channels, int out_h,
+                                                int out_w) {
+  if (images <= 0 || height <= 0 || width <= 0 || (channels != 1 && channels != 3) || out_h <= 0 || out_w <= 0)
+    return 0;
+  return make_plan(images, height, width, channels, out_h, out_w).total;
+}
+
+extern "C" int rz_preprocess_images(const void* raw, int raw_dtype, int images, int height, int width,
+                                    int channels, int out_h, int out_w, const float* mean_host,
+                                    const float* std_host, double rescale_factor, void* pixel_values,
+                                    int out_dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!raw || !pixel_values || !workspace || !mean_host || !std_host) return RZ_ERR_INVALID;
+  if (images <= 0 || height <= 0 || width <= 0 || out_h <= 0 || out_w <= 0) return RZ_ERR_INVALID;
+  if (channels != 1 && channels != 3) return RZ_ERR_INVALID;
+  if (images > 65535) return RZ_ERR_INVALID;
+  if (out_dtype != RZ_F32 && out_dtype != RZ_F16 && out_dtype != RZ_BF16) return RZ_ERR_INVALID;
+  if (workspace_bytes < rz_preprocess_workspace_bytes(images, height, width, channels, out_h, out_w))
+    return RZ_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return RZ_ERR_ALIGNMENT;
+  NormParams np;
+  for (int c = 0; c < 3; ++c) { np.mean[c] = mean_host[c]; np.std[c] = std_host[c]; }
+  np.rescale = rescale_factor;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  switch (raw_dtype) {
+    case RZ_IMG_U8: return run<uint8_t>((const uint8_t*)raw, images, height, width, channels, out_h, out_w, np, pixel_values, out_dtype, ws, s);
+    case RZ_IMG_U16: return run<uint16_t>((const uint16_t*)raw, images, height, width, channels, out_h, out_w, np, pixel_values, out_dtype, ws, s);
+    case RZ_IMG_I16: return run<int16_t>((const int16_t*)raw, images, height, width, channels, out_h, out_w, np, pixel_values, out_dtype, ws, s);
+    case RZ_IMG_I32: return run<int32_t>((const int32_t*)raw, images, height, width, channels, out_h, out_w, np, pixel_values, out_dtype, ws, s);
+    case RZ_IMG_F32: return run<float>((const float*)raw, images, height, width, channels, out_h, out_w, np, pixel_values, out_dtype, ws, s);
+    default: return RZ_ERR_INVALID;
+  }
+}

@@ -16,6 +16,8 @@ from . import _lib, ops
 _KIND_BY_CLASSNAME = {
     "AspectRatioBlipImageProcessor": "aspect_blip",
     "BlipImageProcessor": "blip",
+    "BlipImageProcessorPil": "blip",      # transformers >= 5: the PIL-backed class of the same processor
+    "BlipImageProcessorFast": "blip",
     "BitImageProcessor": "bit",
     "M3AEImageProcessor": "m3ae",
 }
@@ -132,14 +134,29 @@ def dice_sweep_stats(similarity_scores: torch.Tensor, masks: torch.Tensor, origi
             "thresholds": torch.as_tensor(thresholds)}
 
 
-def best_dice_and_specificity(pos_stats, neg_stats=None):
-    """The reference's selection loop (segmentation_utils.py:255-270) on the statistics above: the
-    threshold maximising the Dice of the positive maps -- micro-averaged over the batch, i.e. the
-    confusion counts are summed over images before the ratio -- and the image-level specificity
-    of the negative maps at that threshold."""
-    pred, inter, gt = pos_stats["pred"].sum(0).double(), pos_stats["inter"].sum(0).double(), pos_stats["gt"].sum().double()
-    dice = 2.0 * inter / (pred + gt).clamp_min(1.0)
-    j = int(dice.argmax())                      # first maximum, as `if cur_dice > best_dice`
+def best_dice_and_specificity(pos_stats, neg_stats=None, aggregate: str = "samplewise"):
+    """The reference's selection loop (segmentation_utils.py:255-270) on the statistics above.
+
+    The reference scores each threshold with ``torchmetrics.segmentation.DiceScore(num_classes=1)``
+    (``torchmetrics==1.6.1``, requirements.txt:242; defaults ``average="micro"``, ``include_background=
+    True``): Dice is computed PER IMAGE -- ``2 |P & G| / (|P| + |G|)``, 1.0 when the denominator is 0 --
+    and then nan-averaged over the images.  That is ``aggregate="samplewise"`` (default).
+    ``aggregate="pooled"`` sums the confusion counts over the batch before the ratio (a different
+    metric, kept as an explicit option).  Returns the first threshold maximising the Dice of the
+    positive maps (``if cur_dice > best_dice``) and the image-level specificity of the negative maps
+    at that threshold."""
+    pred, inter = pos_stats["pred"].double(), pos_stats["inter"].double()          # (maps, thresholds)
+    gt = pos_stats["gt"].double()
+    if aggregate == "samplewise":
+        den = pred + gt[:, None]
+        per_map = torch.where(den > 0, 2.0 * inter / den.clamp_min(1.0), torch.ones_like(den))
+        dice = per_map.nanmean(dim=0)
+    elif aggregate == "pooled":
+        dice = 2.0 * inter.sum(0) / (pred.sum(0) + gt.sum()).clamp_min(1.0)
+    else:
+        raise ValueError(f"aggregate must be 'samplewise' or 'pooled', got {aggregate!r}")
+    # `best_dice = 0.0; if cur_dice > best_dice`: the first strict maximum (nothing selected if all are 0)
+    j = int(dice.argmax())
     t = float(pos_stats["thresholds"][j])
     out = {"dice": float(dice[j]), "best_threshold": t}
     if neg_stats is not None:

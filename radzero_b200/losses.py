@@ -170,7 +170,7 @@ def multi_positive_nce_loss(logits: torch.Tensor, group_map: torch.Tensor, tempe
 def _index_tensor(values, device) -> torch.Tensor:
     """int64 index tensor on ``device``.  CUDA: staged in pinned memory and copied asynchronously (a
     pageable host-to-device copy would synchronise the stream, i.e. drain the GPU queue)."""
-    t = torch.tensor(values, dtype=torch.int64)
+    t = values.to(torch.int64) if torch.is_tensor(values) else torch.tensor(values, dtype=torch.int64)
     if torch.device(device).type != "cuda":
         return t.to(device)
     return t.pin_memory().to(device, non_blocking=True)
@@ -257,14 +257,20 @@ class RadZeroLoss(nn.Module):
             ams = [kp["attention_mask"] for kp in key_phrases]
         except (KeyError, TypeError, IndexError):
             return None
-        if not ids or not all(torch.is_tensor(t) and t.dim() == 2 for t in ids + ams):
+        if not ids:
             return None
-        if any(set(kp.keys()) - {"input_ids", "attention_mask"} for kp in key_phrases if hasattr(kp, "keys")):
-            return None                               # token_type_ids etc.: keep the reference's call pattern
+        for kp, a, b in zip(key_phrases, ids, ams):
+            if not (torch.is_tensor(a) and torch.is_tensor(b) and a.dim() == 2 and b.dim() == 2):
+                return None
+            if len(kp) != 2:
+                return None                           # token_type_ids etc.: keep the reference's call pattern
+        counts = [int(t.shape[0]) for t in ids]
         t_max = max(t.shape[1] for t in ids)
-        pad = lambda t, v: t if t.shape[1] == t_max else torch.nn.functional.pad(t, (0, t_max - t.shape[1]), value=v)
-        return {"input_ids": torch.cat([pad(t, pad_token_id) for t in ids], dim=0),
-                "attention_mask": torch.cat([pad(t, 0) for t in ams], dim=0)}, [int(t.shape[0]) for t in ids]
+        if any(t.shape[1] != t_max for t in ids):
+            pad = torch.nn.functional.pad
+            ids = [t if t.shape[1] == t_max else pad(t, (0, t_max - t.shape[1]), value=pad_token_id) for t in ids]
+            ams = [t if t.shape[1] == t_max else pad(t, (0, t_max - t.shape[1]), value=0) for t in ams]
+        return {"input_ids": torch.cat(ids, dim=0), "attention_mask": torch.cat(ams, dim=0)}, counts
 
     def collect_text_features(self, key_phrases, forward_text_model, rank: int = 0,
                               want_group_map: bool = True):
@@ -286,7 +292,8 @@ class RadZeroLoss(nn.Module):
                 feat = feat[:, self.hidden_dim:]
             if not want_group_map:
                 return feat, None
-            group = [i + rank * b_local for i, c in enumerate(counts) for _ in range(c)]
+            group = torch.from_numpy(np.repeat(np.arange(rank * b_local, (rank + 1) * b_local, dtype=np.int64),
+                                               np.asarray(counts, dtype=np.int64)))
             return feat, _index_tensor(group, feat.device)
         feats: List[torch.Tensor] = []
         group: List[int] = []

@@ -15,6 +15,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+from transformers import AutoConfig, AutoModel, PretrainedConfig, PreTrainedModel
 
 from .losses import RadZeroLoss
 
@@ -30,20 +31,114 @@ def mean_pooling(last_hidden_state: torch.Tensor, attention_mask: torch.Tensor) 
     return (last_hidden_state * m).sum(1) / m.sum(1).clamp(min=1e-9)
 
 
-class CxrAlignModel(nn.Module):
-    def __init__(self, vision_model: nn.Module, align_transformer: nn.Module, text_model: nn.Module,
-                 loss_cfg: Optional[Dict] = None, compute_logits_type: str = "radzero"):
-        super().__init__()
-        self.vision_model = vision_model
-        self.align_transformer = align_transformer
-        self.text_model = text_model
-        self.loss_fns = nn.ModuleDict({"RadZeroLoss": RadZeroLoss(**(loss_cfg or RADZERO_LOSS_CFG))})
-        self.loss_ratio = {"RadZeroLoss": 1.0}
+# exp/cxr_pt/configs/radzero.yaml:16-35 restated as explicit sub-configs.  The reference resolves the
+# vision / text sub-configs from the hub at construction time (configuration.py:25-27: network); here every
+# field needed to BUILD the architecture offline is spelled out.
+VISION_CONFIG = dict(model_type="dinov2", hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                     image_size=518, patch_size=14, img_size=518)
+TEXT_CONFIG = dict(model_type="mpnet", use_text_projection=False, use_cls_token=False, num_hidden_layers=12)
+ALIGN_TRANSFORMER_CONFIG = dict(model_type="align_transformer", hidden_size=768, num_hidden_layers=2,
+                                num_attention_heads=12, projector_config=None, use_layer_norm=False)
+
+
+class CxrAlignConfig(PretrainedConfig):
+    """Mirror of exp/cxr_pt/model/configuration.py:108-131 (``CxrAlignConfig``: vision_config, text_config,
+    align_transformer_config + ``loss`` / ``compute_logits_type`` kwargs), serialisable to config.json so that
+    ``save_pretrained`` / ``AutoModel.from_pretrained`` round-trip.  Sub-configs are plain dicts."""
+
+    model_type = "radzero"
+
+    def __init__(self, vision_config=None, text_config=None, align_transformer_config=None, loss=None,
+                 compute_logits_type="radzero", **kwargs):
+        super().__init__(**kwargs)
+        self.vision_config = dict(VISION_CONFIG, **(vision_config or {}))
+        self.text_config = dict(TEXT_CONFIG, **(text_config or {}))
+        self.align_transformer_config = dict(ALIGN_TRANSFORMER_CONFIG, **(align_transformer_config or {}))
+        self.loss = loss or {"apply": ["RadZeroLoss"], "ratio": [1.0], "RadZeroLoss": dict(RADZERO_LOSS_CFG)}
         self.compute_logits_type = compute_logits_type
 
-    @property
-    def device(self):
-        return next(self.parameters()).device
+
+def _build_vision(cfg: Dict) -> nn.Module:
+    from transformers import Dinov2Config, Dinov2Model
+    if cfg.get("model_type", "dinov2") != "dinov2":
+        raise NotImplementedError(cfg.get("model_type"))          # modeling.py:107-108
+    keys = ("hidden_size", "num_hidden_layers", "num_attention_heads", "image_size", "patch_size")
+    return Dinov2Model(Dinov2Config(**{k: cfg[k] for k in keys if k in cfg}))
+
+
+def _build_align(cfg: Dict) -> nn.Module:
+    from transformers import Dinov2Config
+    from transformers.models.dinov2.modeling_dinov2 import Dinov2Encoder
+    from .align import AlignTransformer
+    if cfg.get("model_type", "align_transformer") != "align_transformer":
+        raise NotImplementedError(cfg.get("model_type"))          # align_transformers.py:9-21
+    enc = Dinov2Encoder(Dinov2Config(hidden_size=cfg["hidden_size"], num_hidden_layers=cfg["num_hidden_layers"],
+                                     num_attention_heads=cfg.get("num_attention_heads", 12)))
+    return AlignTransformer(enc, nn.LayerNorm(cfg["hidden_size"]) if cfg.get("use_layer_norm", False) else None)
+
+
+def _build_text(cfg: Dict) -> nn.Module:
+    from transformers import MPNetConfig, MPNetModel
+    if cfg.get("model_type", "mpnet") != "mpnet":
+        raise NotImplementedError(cfg.get("model_type"))          # modeling.py:205-206
+    return MPNetModel(MPNetConfig(num_hidden_layers=cfg.get("num_hidden_layers", 12)))
+
+
+class CxrAlignModel(PreTrainedModel):
+    """``CxrAlignModel(PreTrainedModel)`` with ``config_class = CxrAlignConfig`` (modeling.py:23-25), registered
+    with ``AutoConfig`` / ``AutoModel`` below so that ``AutoModel.from_pretrained(path)`` (README.md:77-82)
+    resolves to this class once ``radzero_b200`` is imported.  State-dict keys follow the reference:
+    ``vision_model.*``, ``text_model.*``, ``align_transformer.transformer_layers.*``,
+    ``loss_fns.RadZeroLoss.{loss_temperature, layer_norm.weight, layer_norm.bias}``."""
+
+    config_class = CxrAlignConfig
+    base_model_prefix = "cxr_align"
+    main_input_name = "pixel_values"
+    supports_gradient_checkpointing = False
+    _no_split_modules = []
+
+    def __init__(self, config: Optional[CxrAlignConfig] = None, vision_model: Optional[nn.Module] = None,
+                 align_transformer: Optional[nn.Module] = None, text_model: Optional[nn.Module] = None,
+                 loss_cfg: Optional[Dict] = None, compute_logits_type: Optional[str] = None):
+        if isinstance(config, nn.Module):      # round-1 call style: CxrAlignModel(vision, align, text[, loss_cfg])
+            config, vision_model, align_transformer, text_model, loss_cfg = (
+                None, config, vision_model, align_transformer, text_model if isinstance(text_model, dict) else loss_cfg)
+        config = config or CxrAlignConfig()
+        super().__init__(config)
+        given = vision_model is not None or align_transformer is not None or text_model is not None
+        self.vision_model = vision_model if vision_model is not None else _build_vision(config.vision_config)
+        self.text_model = text_model if text_model is not None else _build_text(config.text_config)
+        self.hidden_size = int(config.align_transformer_config["hidden_size"])
+        self.text_projector = None               # use_text_projection: False (radzero.yaml:23)
+        self.align_transformer = (align_transformer if align_transformer is not None
+                                  else _build_align(config.align_transformer_config))
+        self.loss_ratio = {}
+        self.loss_fns = nn.ModuleDict()
+        lc = config.loss
+        for loss_type, ratio in zip(lc["apply"], lc["ratio"]):
+            if loss_type != "RadZeroLoss":
+                raise NotImplementedError(f"{loss_type}: only the VL-CABS loss is on this path (DESIGN.md section 8)")
+            self.loss_fns[loss_type] = RadZeroLoss(**(loss_cfg or lc.get(loss_type) or RADZERO_LOSS_CFG))
+            self.loss_ratio[loss_type] = ratio
+        self.compute_logits_type = compute_logits_type or config.compute_logits_type
+        if not given:
+            self.post_init()
+
+    def _init_weights(self, module):
+        """exp/cxr_pt/model/common_layers.py:13-28.  Parameters already filled by ``from_pretrained`` carry
+        transformers' ``_is_hf_initialized`` mark and are left alone."""
+        fresh = lambda p: p is not None and not getattr(p, "_is_hf_initialized", False)
+        with torch.no_grad():
+            if isinstance(module, (nn.Conv2d, nn.Embedding, nn.Linear)):
+                if fresh(module.weight):
+                    module.weight.normal_(mean=0.0, std=0.02)
+                if fresh(getattr(module, "bias", None)):
+                    module.bias.zero_()
+            elif isinstance(module, nn.LayerNorm):
+                if fresh(module.bias):
+                    module.bias.zero_()
+                if fresh(module.weight):
+                    module.weight.fill_(1.0)
 
     # ------------------------------------------------------------------ encoders (stock HF)
     def forward_vision_model(self, pixel_values):
@@ -77,7 +172,14 @@ class CxrAlignModel(nn.Module):
     # ------------------------------------------------------------------ training forward
     def forward(self, pixel_values, encoded_findings=None, encoded_key_phrases=None,
                 encoded_negative_phrases=None, encoded_random_key_phrases=None, return_loss=True,
-                **kwargs):
+                input_ids=None, attention_mask=None, **kwargs):
+        """modeling.py:213-276 (training forward).  Called hub-style -- ``model(pixel_values=...,
+        input_ids=..., attention_mask=...)`` with no key phrases -- it is the released model's inference
+        forward and returns ``(similarity_prob, similarity_map)`` (README.md:104-111)."""
+        if input_ids is not None and encoded_key_phrases is None:
+            if attention_mask is None:
+                attention_mask = torch.ones_like(input_ids)
+            return self.similarity(pixel_values, {"input_ids": input_ids, "attention_mask": attention_mask})
         outputs = {}
         outputs.update(self.forward_vision_model(pixel_values))
         if return_loss:
@@ -118,10 +220,19 @@ class CxrAlignModel(nn.Module):
             text = mean_pooling(hidden, enc["attention_mask"])
             if text.shape[-1] == 2 * loss_fn.hidden_dim:
                 text = text[:, loss_fn.hidden_dim:]
-        logits, scores, z = loss_fn.similarity(text, vision["vision_tokens"], want_scores=True, q16=q16)
-        scores_with_cls = None  # the reference also returns the pre-drop tensor; not materialised here
-        return {"logits": logits, "similarity_scores": scores, "t2i_logits": z,
-                "t2i_attn_weights": scores_with_cls}
+        # the scores are produced WITH the CLS column, exactly the tensor the reference passes through as
+        # ``t2i_attn_weights`` (modeling.py:300-308); ``similarity_scores`` is its ``[:, :, 1:]`` view
+        # (modeling.py:316-317 slices the same way), so the passthrough costs nothing
+        keep_cls = bool(kwargs.get("return_attn_weights", True)) and loss_fn.use_vision_cls_token
+        logits, scores, z = loss_fn.similarity(text, vision["vision_tokens"], want_scores=True, q16=q16,
+                                               drop_cls=not keep_cls)
+        attn = None
+        if keep_cls:
+            attn = [scores]
+            scores = scores[:, :, 1:]
+        elif not loss_fn.use_vision_cls_token:
+            attn = [scores]
+        return {"logits": logits, "similarity_scores": scores, "t2i_logits": z, "t2i_attn_weights": attn}
 
     @torch.no_grad()
     def similarity(self, pixel_values, encoded_text):
@@ -146,16 +257,12 @@ def build_random_init_model(device="cuda", dtype=torch.float32, seed: int = 42,
     (exp/cxr_pt/model/align_transformers.py:23-45), MPNet-base text encoder
     (exp/cxr_pt/configs/radzero.yaml:16-35).  No checkpoints exist offline.
     """
-    from transformers import Dinov2Config, Dinov2Model, MPNetConfig, MPNetModel
-    from transformers.models.dinov2.modeling_dinov2 import Dinov2Encoder
     torch.manual_seed(seed)
-    vcfg = Dinov2Config(hidden_size=768, num_hidden_layers=vision_layers, num_attention_heads=12,
-                        image_size=518, patch_size=14)
-    vision = Dinov2Model(vcfg)
-    acfg = Dinov2Config(hidden_size=768, num_hidden_layers=2, num_attention_heads=12)
-    from .align import AlignTransformer
-    align = AlignTransformer(Dinov2Encoder(acfg))     # align_transformers.py:23-45, use_layer_norm=False
-    tcfg = MPNetConfig(num_hidden_layers=text_layers)
-    text = MPNetModel(tcfg)
-    model = CxrAlignModel(vision, align, text)
+    cfg = CxrAlignConfig(vision_config={"num_hidden_layers": vision_layers},
+                         text_config={"num_hidden_layers": text_layers})
+    model = CxrAlignModel(cfg)
     return model.to(device=device, dtype=dtype).eval()
+
+
+AutoConfig.register(CxrAlignConfig.model_type, CxrAlignConfig)
+AutoModel.register(CxrAlignConfig, CxrAlignModel)

@@ -569,3 +569,49 @@ def text_pool(hidden: torch.Tensor, attention_mask: torch.Tensor, gamma: Optiona
                                   _p(feats), _p(q16), _stream())
     _lib.check(rc, "rz_text_pool")
     return feats, q16
+
+
+# ----------------------------------------------------------------------------- K11
+_IMG_DTYPES = {torch.uint8: _lib.RZ_IMG_U8, torch.uint16: _lib.RZ_IMG_U16, torch.int16: _lib.RZ_IMG_I16,
+               torch.int32: _lib.RZ_IMG_I32, torch.float32: _lib.RZ_IMG_F32}
+
+
+@_guard
+def preprocess_images(raw: torch.Tensor, out_hw: Tuple[int, int] = (518, 518), *, mean, std,
+                      rescale_factor: float = 1.0 / 255.0, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """min-max stretch to uint8 (cv2.normalize) -> RGB -> PIL bicubic resize -> rescale -> normalise, on the
+    GPU, bit-identical to the reference's host chain.  raw (B, H, W) or (B, H, W, 3) uint8 / uint16 / int16 /
+    int32 / float32 on CUDA -> pixel_values (B, 3, out_h, out_w)."""
+    _need_cuda(raw)
+    if raw.dtype not in _IMG_DTYPES:
+        raise RzError(f"unsupported raw image dtype {raw.dtype}")
+    if raw.dim() == 3:
+        ch = 1
+    elif raw.dim() == 4 and raw.shape[-1] in (1, 3):
+        ch = int(raw.shape[-1])
+    else:
+        raise RzError("raw images must be (B, H, W) or (B, H, W, 3)")
+    if out_dtype not in _DTYPES:
+        raise RzError(f"unsupported output dtype {out_dtype}")
+    x = _contig(raw)
+    B, H, W = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+    out = torch.empty((B, 3, oh, ow), dtype=out_dtype, device=x.device)
+    if B == 0:
+        return out
+    import numpy as np
+    m = np.ascontiguousarray(np.broadcast_to(np.asarray(mean, dtype=np.float32), (3,)))
+    sd = np.ascontiguousarray(np.broadcast_to(np.asarray(std, dtype=np.float32), (3,)))
+    lib = _lib.load()
+    step = 4096                                   # images per launch (gridDim.y)
+    for b0 in range(0, B, step):
+        b1 = min(B, b0 + step)
+        nbytes = int(lib.rz_preprocess_workspace_bytes(b1 - b0, H, W, ch, oh, ow))
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=x.device)
+        off = (-ws.data_ptr()) % 256
+        rc = lib.rz_preprocess_images(_p(x[b0:]), _IMG_DTYPES[x.dtype], b1 - b0, H, W, ch, oh, ow,
+                                      m.ctypes.data_as(C.c_void_p), sd.ctypes.data_as(C.c_void_p),
+                                      C.c_double(float(rescale_factor)), _p(out[b0:]), _DTYPES[out_dtype],
+                                      C.c_void_p(ws.data_ptr() + off), C.c_size_t(nbytes), _stream())
+        _lib.check(rc, "rz_preprocess_images")
+    return out

@@ -192,9 +192,17 @@ def test_dice_sweep_stats_vs_oracle(kind, size):
     pos = {k: (v[:-1] if v.dim() and v.shape[0] == M else v) for k, v in got.items()}
     neg = {k: (v[-1:] if v.dim() and v.shape[0] == M else v) for k, v in got.items()}
     res = inference.best_dice_and_specificity(pos, neg)
+    # checker: the reference's loop itself -- DiceScore(num_classes=1)((probs > t).long(), masks) per threshold
+    # (torchmetrics' samplewise Dice restated in the oracle), on the oracle's pixel maps
+    probs = torch.stack([torch.sigmoid(oracle.interpolate_similarity_scores(scores[m], size, kind)[0])
+                         for m in range(M - 1)])
+    sweep = torch.stack([oracle.dice_score_samplewise(probs > float(t), masks[:-1]) for t in thr])
+    assert abs(res["dice"] - float(sweep.max())) < 1e-3
+    assert abs(float(sweep[int(round(res["best_threshold"] * 100))]) - float(sweep.max())) < 1e-3
+    # the pooled aggregation is a different number and stays available as an explicit option
     wp, wi, wg = want["pred"][:-1].sum(0).double(), want["inter"][:-1].sum(0).double(), want["gt"][:-1].sum().double()
-    wdice = 2 * wi / (wp + wg).clamp_min(1.0)
-    assert abs(res["dice"] - float(wdice.max())) < 1e-3
+    pooled = inference.best_dice_and_specificity(pos, neg, aggregate="pooled")
+    assert abs(pooled["dice"] - float((2 * wi / (wp + wg).clamp_min(1.0)).max())) < 1e-3
     negprob = torch.sigmoid(oracle.interpolate_similarity_scores(scores[-1], size, kind))
     assert res["specificity"] == oracle.compute_specificity(negprob, res["best_threshold"])
 

@@ -114,3 +114,29 @@ def test_masked_mean_pool_known_answers():
     assert torch.allclose(out[0], h[0, :3].mean(0))
     assert torch.equal(out[1], torch.zeros(8, dtype=torch.float64))
     assert torch.allclose(out[2], h[2].mean(0))
+
+
+def test_samplewise_dice_known_answer():
+    """torchmetrics 1.6.1 DiceScore(num_classes=1): per-image Dice, zero denominator -> 1, nan-mean over images.
+    Hand-computed: image 0: |P|=4, |G|=2, |P&G|=2 -> 2*2/6; image 1: |P|=0, |G|=3 -> 0; image 2: empty both -> 1."""
+    pred = torch.zeros(3, 1, 4, 4, dtype=torch.long)
+    gt = torch.zeros(3, 1, 4, 4, dtype=torch.long)
+    pred[0, 0, 0, :4] = 1
+    gt[0, 0, 0, :2] = 1
+    gt[1, 0, 1, :3] = 1
+    got = oracle.dice_score_samplewise(pred, gt)
+    assert abs(float(got) - (2 * 2 / 6 + 0.0 + 1.0) / 3) < 1e-12
+    # pooling the counts first would give 2*2 / (4 + 5): a different number
+    assert abs(float(got) - 4 / 9) > 0.1
+
+
+def test_best_dice_selection_is_samplewise_on_cpu_statistics():
+    """radzero_b200.inference.best_dice_and_specificity on hand-made count tables (pure host logic)."""
+    from radzero_b200 import inference
+    pos = {"pred": torch.tensor([[10, 4, 0], [100, 50, 2]]), "inter": torch.tensor([[2, 2, 0], [50, 40, 2]]),
+           "gt": torch.tensor([2, 60]), "thresholds": torch.tensor([0.0, 0.5, 0.9])}
+    res = inference.best_dice_and_specificity(pos)
+    per = torch.tensor([[4 / 12, 4 / 6, 0.0], [100 / 160, 80 / 110, 4 / 62]], dtype=torch.float64).mean(0)
+    assert res["best_threshold"] == 0.5 and abs(res["dice"] - float(per[1])) < 1e-12
+    pooled = inference.best_dice_and_specificity(pos, aggregate="pooled")
+    assert abs(pooled["dice"] - max(2 * 52 / 172, 2 * 42 / 116, 2 * 2 / 64)) < 1e-12
