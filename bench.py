@@ -480,6 +480,7 @@ def compact_contrastive(c):
            "roofline_frac": _r(c["roofline"]["frac"], 3), "tflops_per_gpu": _r(c["roofline"]["achieved"]),
            "e2e": _r(c["e2e"]["value"], 5), "surface_ms": _r(c["surface"]["ms_per_step"], 5), "comm_us": c.get("comm_us"), "mpnce_us": _r(c["mpnce"]["ms"] * 1e3, 3),
            "mpnce_frac_of_hbm": _r(c["mpnce"]["frac_of_hbm"], 3), "mpnce_launches": c["mpnce"].get("launches"),
+           "mpnce_parts_us": [c["mpnce"].get("partials_us"), c["mpnce"].get("finish_us")],
            "clocks": c.get("clocks")}
     return out
 

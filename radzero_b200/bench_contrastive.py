@@ -215,9 +215,12 @@ def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
     del d_tok, d_txt
 
     def dev_time(f, reps=10):
+        """Device time per call of a few-microsecond operation: the launches are queued behind a ~20 ms
+        spin kernel so that the host's launch overhead (Python + ctypes, tens of us) is not what is timed."""
         for _ in range(3):
             f()
         torch.cuda.synchronize()
+        torch.cuda._sleep(40_000_000)
         e0.record()
         for _ in range(reps):
             f()
@@ -237,8 +240,12 @@ def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
     nce()
     nce_launches = _lib.launch_count() - n1
     nce_ms = dev_time(nce)
+    rs_, ps_, cn_, cp_ = ops.mpnce_partials(zt, gm_all, rank * b_local, log_tau=lt)
+    nce_parts = {"partials_us": round(dev_time(lambda: ops.mpnce_partials(zt, gm_all, rank * b_local, log_tau=lt)) * 1e3, 1),
+                 "finish_us": round(dev_time(lambda: ops.mpnce_finish(zt, gm_all, rank * b_local, B_GLOBAL, 1.0, rs_, ps_,
+                                                                      cn_, cp_, log_tau=lt)) * 1e3, 1)}
     nce_bytes = 2 * n_total * b_local * 4
-    mpnce = {"ms": nce_ms, "launches": int(nce_launches), "algorithmic_bytes": nce_bytes,
+    mpnce = {"ms": nce_ms, "launches": int(nce_launches), **nce_parts, "algorithmic_bytes": nce_bytes,
              "achieved_gbs": nce_bytes / (nce_ms * 1e-3) / 1e9,
              "frac_of_hbm": nce_bytes / (nce_ms * 1e-3) / 1e9 / pk["hbm"],
              "note": "two persistent cooperative launches (partials | coefficients + dZ + terms); Z is 25 MB at C4 "

@@ -90,19 +90,38 @@ __global__ void pp_coeff_kernel(Taps th, int w_in, int w_out, Taps tv, int h_in,
 
 template <typename T> __device__ __forceinline__ float as_float(T v) { return (float)v; }
 
-// per-image min / max over all channels (cv::minMaxIdx); values compared as double (exact for every type)
+// per-image min / max over all channels (cv::minMaxIdx); values compared as double (exact for every type).
+// 16-byte loads over the aligned body of this CTA's slice, scalar head / tail.
+template <typename T>
+__device__ __forceinline__ void minmax_acc(T v, double& lo, double& hi) {
+  const double d = (double)v;
+  lo = fmin(lo, d);
+  hi = fmax(hi, d);
+}
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 pp_minmax_kernel(const T* __restrict__ raw, long long per_image, double* __restrict__ part) {
+  constexpr int kVec = 16 / (int)sizeof(T);
   const int img = blockIdx.y, split = blockIdx.x;
   const T* src = raw + (long long)img * per_image;
   const long long per = (per_image + kMinMaxSplit - 1) / kMinMaxSplit;
   const long long i0 = (long long)split * per, i1 = min(per_image, i0 + per);
   double lo = DBL_MAX, hi = -DBL_MAX;
-  for (long long i = i0 + threadIdx.x; i < i1; i += kThreads) {
-    const double v = (double)src[i];
-    lo = fmin(lo, v);
-    hi = fmax(hi, v);
+  if (i0 < i1) {
+    // first element of the slice whose address is 16-byte aligned
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(src + i0);
+    long long v0 = i0 + (long long)(((16 - (a0 & 15)) & 15) / sizeof(T));
+    if (v0 > i1) v0 = i1;
+    const long long nvec = (i1 - v0) / kVec;
+    for (long long i = i0 + threadIdx.x; i < v0; i += kThreads) minmax_acc(src[i], lo, hi);
+    const uint4* vp = reinterpret_cast<const uint4*>(src + v0);
+    for (long long j = threadIdx.x; j < nvec; j += kThreads) {
+      const uint4 q = rz::ldg_stream_u4(vp + j);
+      const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+      for (int u = 0; u < kVec; ++u) minmax_acc(e[u], lo, hi);
+    }
+    for (long long i = v0 + nvec * kVec + threadIdx.x; i < i1; i += kThreads) minmax_acc(src[i], lo, hi);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -124,46 +143,59 @@ __device__ __forceinline__ uint8_t clip8(int v) {
   return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
-// Horizontal pass.  One CTA handles `rows` consecutive rows of one image: the raw row is stretched to uint8
-// (saturate(rint(fma(src, a, b)))) into shared memory, then thread o accumulates output column o.
+__device__ __forceinline__ uint8_t stretch8(float v, float a, float b) {
+  int q = __float2int_rn(__fmaf_rn(v, a, b));              // one float FMA, cvRound: round half to even
+  return (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+}
+
+// Horizontal pass.  One WARP owns a row at a time (no block-level synchronisation): it stretches the raw
+// row to uint8 (saturate(rint(fma(src, a, b)))) into its private shared-memory row, planar per channel,
+// then each lane accumulates output columns lane, lane + 32, ...  A CTA's warps take consecutive rows.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 pp_horizontal_kernel(const T* __restrict__ raw, int H, int W, int C, const double* __restrict__ part,
-                     Taps t, int w_out, int pitch, uint8_t* __restrict__ tmp, int rows) {
-  extern __shared__ uint8_t srow[];          // [C][W] planar
-  const int img = blockIdx.y;
-  __shared__ float sa, sb;
-  if (threadIdx.x == 0) {
+                     Taps t, int w_out, int pitch, uint8_t* __restrict__ tmp, int rows_per_warp) {
+  extern __shared__ uint8_t srow_all[];      // [warps][C][Wp] planar
+  const int img = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Wp = (W + 15) & ~15;
+  uint8_t* srow = srow_all + (size_t)warp * C * Wp;
+  float a, b;
+  {
     double lo = DBL_MAX, hi = -DBL_MAX;
-    for (int k = 0; k < kMinMaxSplit; ++k) {
-      lo = fmin(lo, part[((long long)img * kMinMaxSplit + k) * 2 + 0]);
-      hi = fmax(hi, part[((long long)img * kMinMaxSplit + k) * 2 + 1]);
+    if (lane < kMinMaxSplit) {
+      lo = part[((long long)img * kMinMaxSplit + lane) * 2 + 0];
+      hi = part[((long long)img * kMinMaxSplit + lane) * 2 + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
     // cv::normalize, NORM_MINMAX: scale = (255 - 0) * (1 / (smax - smin)), shift = 0 - smin * scale
     const double scale = __dmul_rn(255.0, (hi - lo > DBL_EPSILON) ? __ddiv_rn(1.0, __dsub_rn(hi, lo)) : 0.0);
     const double shift = __dsub_rn(0.0, __dmul_rn(lo, scale));
-    sa = (float)scale;
-    sb = (float)shift;
+    a = (float)scale;
+    b = (float)shift;
   }
-  __syncthreads();
-  const float a = sa, b = sb;
-  const int y0 = blockIdx.x * rows;
-  for (int y = y0; y < min(H, y0 + rows); ++y) {
-    const T* src = raw + (((long long)img * H + y) * W) * C;
-    __syncthreads();
-    for (int i = threadIdx.x; i < W * C; i += kThreads) {
-      const float v = __fmaf_rn(as_float(src[i]), a, b);
-      int q = __float2int_rn(v);                         // cvRound: round half to even
-      q = q < 0 ? 0 : (q > 255 ? 255 : q);
-      const int x = i / C, c = i - x * C;
-      srow[c * W + x] = (uint8_t)q;
+  const int y0 = (blockIdx.x * (kThreads / 32) + warp) * rows_per_warp;
+  const int n_el = W * C;
+  for (int y = y0; y < min(H, y0 + rows_per_warp); ++y) {
+    const T* src = raw + ((long long)img * H + y) * n_el;
+    __syncwarp();
+    if (C == 1) {
+      for (int i = lane; i < n_el; i += 32) srow[i] = stretch8(as_float(src[i]), a, b);
+    } else {
+      for (int i = lane; i < n_el; i += 32) {
+        const int x = i / C, c = i - x * C;
+        srow[c * Wp + x] = stretch8(as_float(src[i]), a, b);
+      }
     }
-    __syncthreads();
-    for (int o = threadIdx.x; o < w_out * C; o += kThreads) {
+    __syncwarp();
+    for (int o = lane; o < w_out * C; o += 32) {
       const int c = o / w_out, xo = o - c * w_out;
       const int lo = __ldg(t.xmin + xo), n = __ldg(t.cnt + xo);
       const int* wk = t.w + (long long)xo * t.ksize;
-      const uint8_t* s = srow + c * W + lo;
+      const uint8_t* s = srow + c * Wp + lo;
       int acc = 1 << (kPrecisionBits - 1);
       for (int k = 0; k < n; ++k) acc += (int)s[k] * __ldg(wk + k);
       tmp[(((long long)img * C + c) * H + y) * pitch + xo] = clip8(acc);
@@ -178,12 +210,14 @@ template <> __device__ __forceinline__ float to_out<float>(float v) { return v; 
 template <> __device__ __forceinline__ __half to_out<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-// Vertical pass + rescale + normalise.  One CTA = `rows` output rows of one image; thread x walks the taps of
-// its column (coalesced across the warp), then maps the uint8 result through the per-channel table.
+// Vertical pass + rescale + normalise.  One CTA = `rows` consecutive output rows of one image.  The source
+// rows those outputs tap (a contiguous band of the uint8 intermediate) are staged in shared memory once;
+// thread x then walks the taps of its column and maps the uint8 result through the per-channel table.
 template <typename TOut>
 __global__ void __launch_bounds__(kThreads)
 pp_vertical_kernel(const uint8_t* __restrict__ tmp, int H, int C, int pitch, Taps t, int h_out, int w_out,
-                   NormParams np, TOut* __restrict__ out, int rows) {
+                   NormParams np, TOut* __restrict__ out, int rows, int band_cap) {
+  extern __shared__ uint8_t band[];          // [C][band_cap][pitch]
   __shared__ float lut[3][256];
   for (int i = threadIdx.x; i < 768; i += kThreads) {
     const int c = i >> 8, v = i & 255;
@@ -191,20 +225,29 @@ pp_vertical_kernel(const uint8_t* __restrict__ tmp, int H, int C, int pitch, Tap
     const float r = (float)__dmul_rn((double)v, np.rescale);
     lut[c][v] = __fdiv_rn(__fsub_rn(r, np.mean[c]), np.std[c]);
   }
-  __syncthreads();
   const int img = blockIdx.y;
-  const int y0 = blockIdx.x * rows;
-  for (int yo = y0; yo < min(h_out, y0 + rows); ++yo) {
-    const int lo = __ldg(t.xmin + yo), n = __ldg(t.cnt + yo);
+  const int y0 = blockIdx.x * rows, y1 = min(h_out, y0 + rows);
+  const int b0 = __ldg(t.xmin + y0);
+  const int b1 = __ldg(t.xmin + y1 - 1) + __ldg(t.cnt + y1 - 1);       // xmin is non-decreasing
+  const int nb = b1 - b0;                                              // <= band_cap by construction
+  const int vec = pitch / 16;
+  for (int c = 0; c < C; ++c) {
+    const uint4* src = reinterpret_cast<const uint4*>(tmp + (((long long)img * C + c) * H + b0) * pitch);
+    uint4* dst = reinterpret_cast<uint4*>(band + (size_t)c * band_cap * pitch);
+    for (int i = threadIdx.x; i < nb * vec; i += kThreads) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  for (int yo = y0; yo < y1; ++yo) {
+    const int lo = __ldg(t.xmin + yo) - b0, n = __ldg(t.cnt + yo);
     const int* wk = t.w + (long long)yo * t.ksize;
     for (int x = threadIdx.x; x < w_out; x += kThreads) {
       uint8_t q[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         if (c < C) {
-          const uint8_t* s = tmp + (((long long)img * C + c) * H + lo) * pitch + x;
+          const uint8_t* s = band + ((size_t)c * band_cap + lo) * pitch + x;
           int acc = 1 << (kPrecisionBits - 1);
-          for (int k = 0; k < n; ++k) acc += (int)s[(long long)k * pitch] * __ldg(wk + k);
+          for (int k = 0; k < n; ++k) acc += (int)s[k * pitch] * __ldg(wk + k);
           q[c] = clip8(acc);
         } else {
           q[c] = q[0];                                     // convert_to_rgb replicates a grey plane
@@ -250,23 +293,36 @@ int run(const T* raw, int images, int H, int W, int C, int h_out, int w_out, con
   RZ_LAUNCH_OK();
   pp_minmax_kernel<T><<<dim3(kMinMaxSplit, images), kThreads, 0, s>>>(raw, (long long)H * W * C, part);
   RZ_LAUNCH_OK();
+  // horizontal: one warp per row, `rows_h` rows per warp; shared memory = one stretched row per warp
   const int rows_h = 4;
-  const size_t smem = (size_t)W * C;
-  if (smem > 96 * 1024) return RZ_ERR_UNSUPPORTED;
+  const int warps = kThreads / 32;
+  const size_t smem = (size_t)warps * C * ((W + 15) & ~15);
+  if (smem > 200 * 1024) return RZ_ERR_UNSUPPORTED;
   if (smem > 48 * 1024)
     RZ_CUDA_OK(cudaFuncSetAttribute(pp_horizontal_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pp_horizontal_kernel<T><<<dim3((H + rows_h - 1) / rows_h, images), kThreads, smem, s>>>(
+  pp_horizontal_kernel<T><<<dim3((H + rows_h * warps - 1) / (rows_h * warps), images), kThreads, smem, s>>>(
       raw, H, W, C, part, th, w_out, pl.pitch, tmp, rows_h);
   RZ_LAUNCH_OK();
-  const int rows_v = 2;
+  // vertical: `rows_v` output rows per CTA share a band of at most ceil(rows_v * H / h_out) + ksize source rows
+  const int rows_v = 8;
+  const int band_cap = (int)(((long long)rows_v * H + h_out - 1) / h_out) + pl.ks_v + 2;
+  const size_t smem_v = (size_t)C * band_cap * pl.pitch;
+  if (smem_v > 200 * 1024) return RZ_ERR_UNSUPPORTED;
   const dim3 gv((h_out + rows_v - 1) / rows_v, images);
-  if (out_dtype == RZ_F32)
-    pp_vertical_kernel<float><<<gv, kThreads, 0, s>>>(tmp, H, C, pl.pitch, tv, h_out, w_out, np, (float*)out, rows_v);
-  else if (out_dtype == RZ_F16)
-    pp_vertical_kernel<__half><<<gv, kThreads, 0, s>>>(tmp, H, C, pl.pitch, tv, h_out, w_out, np, (__half*)out, rows_v);
-  else
-    pp_vertical_kernel<__nv_bfloat16><<<gv, kThreads, 0, s>>>(tmp, H, C, pl.pitch, tv, h_out, w_out, np,
-                                                             (__nv_bfloat16*)out, rows_v);
+  if (out_dtype == RZ_F32) {
+    if (smem_v > 48 * 1024)
+      RZ_CUDA_OK(cudaFuncSetAttribute(pp_vertical_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
+    pp_vertical_kernel<float><<<gv, kThreads, smem_v, s>>>(tmp, H, C, pl.pitch, tv, h_out, w_out, np, (float*)out, rows_v, band_cap);
+  } else if (out_dtype == RZ_F16) {
+    if (smem_v > 48 * 1024)
+      RZ_CUDA_OK(cudaFuncSetAttribute(pp_vertical_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
+    pp_vertical_kernel<__half><<<gv, kThreads, smem_v, s>>>(tmp, H, C, pl.pitch, tv, h_out, w_out, np, (__half*)out, rows_v, band_cap);
+  } else {
+    if (smem_v > 48 * 1024)
+      RZ_CUDA_OK(cudaFuncSetAttribute(pp_vertical_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
+    pp_vertical_kernel<__nv_bfloat16><<<gv, kThreads, smem_v, s>>>(tmp, H, C, pl.pitch, tv, h_out, w_out, np,
+                                                                   (__nv_bfloat16*)out, rows_v, band_cap);
+  }
   RZ_LAUNCH_OK();
   rz_count_launch(4);
   return RZ_OK;

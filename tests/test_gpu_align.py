@@ -188,9 +188,13 @@ def test_inplace_and_grad_dispatch():
     buf = tok.clone()
     got = mod(buf, inplace=True)
     assert got.data_ptr() == buf.data_ptr() and torch.equal(got, want)
-    # bf16 tokens (the reference's training / bf16_full_eval dtype) are accepted; output is fp32
+    # bf16 tokens (the reference's training / bf16_full_eval dtype) are accepted and come back as bf16,
+    # the dtype the reference's module would return
     got16 = mod(tok.to(torch.bfloat16))
-    assert got16.dtype == torch.float32 and (got16 - want).abs().max().item() <= 0.25
+    assert got16.dtype == torch.bfloat16 and (got16.float() - want).abs().max().item() <= 0.25
+    # an input that itself requires grad (eval-mode saliency) is served by the stock path, not detached
+    with torch.enable_grad():
+        assert mod(tok.clone().requires_grad_(True)).requires_grad
     # eval mode never leaves the kernels, with or without torch.no_grad()
     with torch.enable_grad():
         assert not mod(tok).requires_grad
