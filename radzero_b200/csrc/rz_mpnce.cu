@@ -37,6 +37,18 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter) {
   __syncthreads();
 }
 
+// The sentence -> image map as int32 in shared memory (cooperative, coalesced, all loads in flight at once):
+// the per-column phases scan it once per column, and a scan over global memory is a chain of ~50 L2
+// latencies per warp.  Values outside int32 can match no column and become -1.
+constexpr int kGroupCap = 8192;
+__device__ __forceinline__ void stage_group_map(const long long* __restrict__ gm, int n, int* sm) {
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    const long long g = __ldg(gm + i);
+    sm[i] = (g >= 0 && g <= 0x7fffffffLL) ? (int)g : -1;
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ float inv_temperature(const float* log_tau, float inv_tau) {
   return log_tau != nullptr ? expf(-__ldg(log_tau)) : inv_tau;
 }
@@ -144,17 +156,27 @@ mpnce_partials_kernel(PartialsParams p) {
     }
   }
   grid_barrier(p.barrier);
+  // phase B.  colbuf is free now: it holds the int32 sentence -> image map for the column scans
+  int* gsm = reinterpret_cast<int*>(&colbuf[0][0]);
+  const bool staged = p.n_total <= kGroupCap;
+  const bool any_col = (int)blockIdx.x * kWarps < b_local;
+  if (staged && any_col) stage_group_map(p.group_map, p.n_total, gsm);
   for (int c = blockIdx.x * kWarps + warp; c < b_local; c += gridDim.x * kWarps) {
     float all = 0.f, cp = 0.f;
     for (int k = lane; k < chunks; k += 32) all += __ldcg(p.colpart + (long long)k * b_local + c);
     const long long gcol = (long long)p.col0 + c;
-    for (int i0 = lane; i0 < p.n_total; i0 += 128) {
-      long long g[4];
+    if (staged) {
+      for (int i = lane; i < p.n_total; i += 32)
+        if (gsm[i] == (int)gcol) cp += __ldcg(p.pos + i);
+    } else {
+      for (int i0 = lane; i0 < p.n_total; i0 += 128) {
+        long long g[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) g[u] = i0 + 32 * u < p.n_total ? __ldg(p.group_map + i0 + 32 * u) : -1;
+        for (int u = 0; u < 4; ++u) g[u] = i0 + 32 * u < p.n_total ? __ldg(p.group_map + i0 + 32 * u) : -1;
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (g[u] == gcol) cp += __ldcg(p.pos + i0 + 32 * u);
+        for (int u = 0; u < 4; ++u)
+          if (g[u] == gcol) cp += __ldcg(p.pos + i0 + 32 * u);
+      }
     }
     all = rz::warp_sum(all);
     cp = rz::warp_sum(cp);
@@ -183,6 +205,10 @@ mpnce_finish_kernel(FinishParams p) {
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int gw = blockIdx.x * kWarps + warp, nw = gridDim.x * kWarps;
   const float inv_tau = inv_temperature(p.log_tau, p.inv_tau);
+  __shared__ int gsm[kGroupCap];
+  const bool staged = p.n_total <= kGroupCap;
+  const bool scans = (int)blockIdx.x * kWarps < p.b_local || (p.row_sum && (int)blockIdx.x * kWarps < p.b_global);
+  if (staged && scans) stage_group_map(p.group_map, p.n_total, gsm);
   // ---- phase 0a: per local column, the coefficient applied to the negatives / positives of that
   // column and the column loss terms it owns.  One WARP per column: the lanes stride over the
   // sentences and are combined in a fixed order (bit-reproducible, independent of the rank count).
@@ -200,20 +226,15 @@ mpnce_finish_kernel(FinishParams p) {
     } else {
       // MP-NCE: one term per sentence i of this image: p = pos_i/(pos_i + Cneg + eps)  :337-342
       const float cn = p.colneg[c];
-      for (int i0 = lane; i0 < p.n_total; i0 += 128) {
-        long long g[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) g[u] = i0 + 32 * u < p.n_total ? __ldg(p.group_map + i0 + 32 * u) : -1;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (g[u] != gcol) continue;
-          const float ps = p.pos[i0 + 32 * u];
-          const float den = ps + cn + p.eps;
-          const float pc = ps / den;
-          const float w = 1.0f / (pc + p.eps);
-          l += -logf(pc + p.eps);
-          a += w * ps / (den * den);
-        }
+      for (int i = lane; i < p.n_total; i += 32) {
+        const bool hit = staged ? gsm[i] == (int)gcol : __ldg(p.group_map + i) == gcol;
+        if (!hit) continue;
+        const float ps = p.pos[i];
+        const float den = ps + cn + p.eps;
+        const float pc = ps / den;
+        const float w = 1.0f / (pc + p.eps);
+        l += -logf(pc + p.eps);
+        a += w * ps / (den * den);
       }
       a = rz::warp_sum(a);
       l = rz::warp_sum(l);
@@ -225,8 +246,10 @@ mpnce_finish_kernel(FinishParams p) {
   if (p.row_sum) {
     for (int b = gw; b < p.b_global; b += nw) {
       float rs = 0.f, ps = 0.f;
-      for (int i = lane; i < p.n_total; i += 32)
-        if (__ldg(p.group_map + i) == (long long)b) { rs += p.rowsum[i]; ps += p.pos[i]; }
+      for (int i = lane; i < p.n_total; i += 32) {
+        const bool hit = staged ? gsm[i] == b : __ldg(p.group_map + i) == (long long)b;
+        if (hit) { rs += p.rowsum[i]; ps += p.pos[i]; }
+      }
       rs = rz::warp_sum(rs);
       ps = rz::warp_sum(ps);
       if (lane == 0) { p.img_rs[b] = rs; p.img_ps[b] = ps; }
@@ -234,6 +257,7 @@ mpnce_finish_kernel(FinishParams p) {
   }
   grid_barrier(p.barrier);
   // ---- phase 1: one warp per row: row coefficients, dZ, sum dZ*Z
+  float l_acc = 0.f, z_acc = 0.f;
   for (int r = gw; r < p.n_total; r += nw) {
     const long long g = __ldg(p.group_map + r);
     const int gl = (g >= p.col0 && g - p.col0 < p.b_local) ? (int)(g - p.col0) : -1;
@@ -306,7 +330,19 @@ mpnce_finish_kernel(FinishParams p) {
       }
     }
     acc = rz::warp_sum(acc);
-    if (lane == 0) { p.lrow[r] = l; p.dzz_part[r] = acc; }
+    l_acc += l;                      // this warp's rows, in row order
+    z_acc += acc;
+  }
+  // per-CTA partials (fixed warp order), so that the final reduction reads gridDim.x values, not n_total
+  __shared__ float wl[kWarps], wz[kWarps];
+  if (lane == 0) { wl[warp] = l_acc; wz[warp] = z_acc; }
+  __syncthreads();
+  if (t == 0) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < kWarps; ++k) { a += wl[k]; b += wz[k]; }
+    p.lrow[blockIdx.x] = a;
+    p.dzz_part[blockIdx.x] = b;
   }
   grid_barrier(p.barrier);
   // ---- phase 2 (CTA 0): fixed-order tree: loss_terms = {sum row terms, sum col terms, sum dZ*Z,
@@ -321,10 +357,10 @@ mpnce_finish_kernel(FinishParams p) {
       a += -logf(__ldcg(p.img_ps + p.col0 + i) / rs + p.eps);
     }
   } else {
-    for (int i = t; i < p.n_total; i += kThreads) a += __ldcg(p.lrow + i);
+    for (int i = t; i < (int)gridDim.x; i += kThreads) a += __ldcg(p.lrow + i);
   }
   for (int i = t; i < p.b_local; i += kThreads) b += __ldcg(p.lcol + i);
-  for (int i = t; i < p.n_total; i += kThreads) c += __ldcg(p.dzz_part + i);
+  for (int i = t; i < (int)gridDim.x; i += kThreads) c += __ldcg(p.dzz_part + i);
   sh[0][t] = a; sh[1][t] = b; sh[2][t] = c;
   __syncthreads();
   for (int s = kThreads / 2; s > 0; s >>= 1) {

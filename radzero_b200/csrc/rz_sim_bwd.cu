@@ -289,6 +289,10 @@ struct PassD2 : PolicyBase {
       else if (next_tile >= 0) fetch(p, maps, next_tile, c + 2 - nch, warp, stg, bars, g + 2);
     }
     st.g = g + 1;
+    // packed fp32 pairs: the epilogue warp is alone on its scheduler, so its time is instructions x latency
+    const P2 kLn2 = p2(0.6931471805599453f), m2 = p2(r.m), linv2 = p2(r.linv), nrt2 = p2(-r.rt),
+             aS2 = p2(r.aS), c22 = p2(r.c2);
+    P2 u2 = p2(0.f);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {                      // two halves of 32 columns
       uint32_t o1[16], o2[16];
@@ -296,21 +300,16 @@ struct PassD2 : PolicyBase {
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         const float2 pp = __half22float2(*reinterpret_cast<const __half2*>(&pw[16 * h + (i >> 1)]));
-        float w1v[2], w2v[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const float pt = q == 0 ? pp.x : pp.y;
-          const float t = __uint_as_float(tv[i + q]);
-          const float s = fmaf(__log2f(fmaxf(pt, 5.9604645e-8f)), 0.6931471805599453f, r.m);
-          const float pr = pt * r.linv;
-          const float e = fmaf(-r.rt, t, s);          // s - (r/tau) T
-          const float x = r.aS * pr;
-          w1v[q] = fmaf(x, e, x);                     // aS p (1 + e)
-          w2v[q] = r.c2 * pr;                         // -aS r p
-          u = fmaf(pr * e, s, u);                     // dL/dlog tau = -a tau sum p e s
-        }
-        o1[i >> 1] = pack_h2(w1v[0], w1v[1]);
-        o2[i >> 1] = pack_h2(w2v[0], w2v[1]);
+        const P2 pt = p2(pp.x, pp.y);
+        const P2 lg = p2(__log2f(fmaxf(pp.x, 5.9604645e-8f)), __log2f(fmaxf(pp.y, 5.9604645e-8f)));
+        const P2 t = p2(__uint_as_float(tv[i]), __uint_as_float(tv[i + 1]));
+        const P2 s = p2_fma(lg, kLn2, m2);             // s = m + ln P~
+        const P2 pr = p2_mul(pt, linv2);               // p = P~ / l  (exactly 0 where P~ underflowed)
+        const P2 e = p2_fma(nrt2, t, s);               // s - (r/tau) T
+        const P2 x = p2_mul(aS2, pr);
+        o1[i >> 1] = p2_pack_h2(p2_fma(x, e, x));      // aS p (1 + e)
+        o2[i >> 1] = p2_pack_h2(p2_mul(c22, pr));      // -aS r p
+        u2 = p2_fma(p2_mul(pr, e), s, u2);             // dL/dlog tau = -a tau sum p e s
       }
       if (h == 0) {
         // the output boxes were last read by the bulk stores of the previous chunk
@@ -322,6 +321,11 @@ struct PassD2 : PolicyBase {
         sts_v4(stg + 8192 + stage_off(lane, 4 * h + j), o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
         sts_v4(stg + 12288 + stage_off(lane, 4 * h + j), o2[4 * j], o2[4 * j + 1], o2[4 * j + 2], o2[4 * j + 3]);
       }
+    }
+    {
+      float ua, ub;
+      p2_unpack(u2, ua, ub);
+      u += ua + ub;
     }
     fence_proxy_async_smem();
     __syncwarp();

@@ -137,23 +137,28 @@ struct PassS2 : PolicyBase {
     // exponentials into registers (the scores box drains meanwhile)
     const float sl2 = scale * kLog2e;                // exp(s - m) = 2^(a * scale*log2e - m*log2e)
     const float mb = st.m * kLog2e;
-    float lacc0 = 0.f, lacc1 = 0.f;
+    // packed fp32 pairs for the affine map and the row sum (one issue slot per two columns)
+    const P2 sl22 = p2(sl2), nmb2 = p2(-mb);
+    P2 lacc = p2(0.f);
     uint32_t pk[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {                    // 8 columns -> one 16-byte chunk of the P~ row
       const uint32_t* src = j < 4 ? &v.lo[8 * j] : &v.hi[8 * (j - 4)];
       const int lc = l0 + 8 * j;
-      float e[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        e[i] = exp2f(fmaf(__uint_as_float(src[i]), sl2, -mb));
-        if (kMasked && lc + i >= p.L) e[i] = 0.f;
+      for (int i = 0; i < 8; i += 2) {
+        float x0, x1;
+        p2_unpack(p2_fma(p2(__uint_as_float(src[i]), __uint_as_float(src[i + 1])), sl22, nmb2), x0, x1);
+        float e0 = exp2f(x0), e1 = exp2f(x1);
+        if (kMasked && lc + i >= p.L) e0 = 0.f;
+        if (kMasked && lc + i + 1 >= p.L) e1 = 0.f;
+        const P2 ee = p2(e0, e1);
+        lacc = p2_add(lacc, ee);
+        pk[4 * j + (i >> 1)] = p2_pack_h2(ee);
       }
-      lacc0 += (e[0] + e[1]) + (e[2] + e[3]);
-      lacc1 += (e[4] + e[5]) + (e[6] + e[7]);
-      pk[4 * j] = pack_h2(e[0], e[1]); pk[4 * j + 1] = pack_h2(e[2], e[3]);
-      pk[4 * j + 2] = pack_h2(e[4], e[5]); pk[4 * j + 3] = pack_h2(e[6], e[7]);
     }
+    float lacc0, lacc1;
+    p2_unpack(lacc, lacc0, lacc1);
     st.l += lacc0 + lacc1;
     if (lane == 0) tma_store_wait_read();            // !kScores: the previous chunk's P~ store
     __syncwarp();
