@@ -76,8 +76,10 @@ struct Ctrl {
   uint64_t s_full[2], p_full[2], o_done[2];
   uint64_t o_free;
   uint32_t tmem_slot;
-  int rescale_flag;
-  float alpha[kNB];
+  // double-buffered by tile parity: warp 0 writes tile lt+1's flag / factors while slower warps may still
+  // be reading tile lt's (they are separated by one named barrier only)
+  int rescale_flag[2];
+  float alpha[2][kNB];
   float m_fin[kNB], l_fin[kNB];
   float red[4][2 * kNB];
 };
@@ -107,9 +109,11 @@ template <> struct RingRow<float> {
     for (int j = 0; j < 6; ++j) {
       const int e = 4 * (lane + 32 * j);
       const uint32_t a = grp + (uint32_t)((e >> 8) * (kGroup * 1024) + r * 1024 + (e & 255) * 4);
+      // "memory": the loads must not be scheduled below the release of the ring slot that follows them
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                    : "=f"(x[4 * j]), "=f"(x[4 * j + 1]), "=f"(x[4 * j + 2]), "=f"(x[4 * j + 3])
-                   : "r"(a));
+                   : "r"(a)
+                   : "memory");
     }
   }
 };
@@ -120,7 +124,7 @@ template <> struct RingRow<__nv_bfloat16> {
       const int e = 4 * (lane + 32 * j);
       const uint32_t a = grp + (uint32_t)((e >> 8) * (kGroup * 512) + r * 512 + (e & 255) * 2);
       uint32_t u, v;
-      asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u), "=r"(v) : "r"(a));
+      asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u), "=r"(v) : "r"(a) : "memory");
       x[4 * j] = __uint_as_float(u << 16); x[4 * j + 1] = __uint_as_float(u & 0xffff0000u);
       x[4 * j + 2] = __uint_as_float(v << 16); x[4 * j + 3] = __uint_as_float(v & 0xffff0000u);
     }
@@ -133,7 +137,7 @@ template <> struct RingRow<__half> {
       const int e = 4 * (lane + 32 * j);
       const uint32_t a = grp + (uint32_t)((e >> 8) * (kGroup * 512) + r * 512 + (e & 255) * 2);
       uint32_t u, v;
-      asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u), "=r"(v) : "r"(a));
+      asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u), "=r"(v) : "r"(a) : "memory");
       const float2 f0 = __half22float2(*reinterpret_cast<__half2*>(&u));
       const float2 f1 = __half22float2(*reinterpret_cast<__half2*>(&v));
       x[4 * j] = f0.x; x[4 * j + 1] = f0.y; x[4 * j + 2] = f1.x; x[4 * j + 3] = f1.y;
@@ -320,8 +324,14 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
       const int r = q4 * kGroup + w;                       // token row within the tile
       float v[24];
       RingRow<TIn>::load(ring_addr + slot * C::kGroupBytes, w, lane, v);
+#ifndef RZ_EXP_LATE_RELEASE
+      // every lane's loads must have RETURNED before the slot goes back to the TMA producer (see
+      // lds_returned in rz_umma.cuh: the arrive can overtake loads still queued in the LSU)
+      const uint32_t dep = lds_returned(__float_as_uint(v[3]), __float_as_uint(v[7]), __float_as_uint(v[11]),
+                                        __float_as_uint(v[15]), __float_as_uint(v[19]), __float_as_uint(v[23]));
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl->ring_empty[slot]);
+      if (lane == 0) mbar_arrive(&ctl->ring_empty[slot] + dep);
+#endif
       const bool ok = j * kTokT + r < p.L;
       rz::ln_l2_row(v, ln ? p.gamma : nullptr, ln ? p.beta : nullptr, lane, RZ_LN_EPS, RZ_L2_EPS, p.l2 != 0);
       // lane's 4 features of group jj: feature 4*(lane + 32 jj) -> chunk (lane + 32 jj) / 16,
@@ -337,6 +347,9 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->k_full[st]);
+#ifdef RZ_EXP_LATE_RELEASE
+      if (lane == 0) mbar_arrive(&ctl->ring_empty[slot] + dep);
+#endif
     }
   } else if (warp < 4) {
     // ================================================================= softmax (warp 0) + epilogue (warps 0-3)
@@ -392,11 +405,11 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
             m = cmax;
           }
           const bool any = __any_sync(0xffffffffu, grow);
-          if (any && lane < kNB) ctl->alpha[lane] = a;
-          if (lane == 0) ctl->rescale_flag = any ? 1 : 0;
+          if (any && lane < kNB) ctl->alpha[lt & 1][lane] = a;
+          if (lane == 0) ctl->rescale_flag[lt & 1] = any ? 1 : 0;
         }
         named_bar_sync(1, 128);
-        if (ctl->rescale_flag != 0) {
+        if (ctl->rescale_flag[lt & 1] != 0) {
           // rare: scale the pooled accumulator columns; it is quiescent once tile lt-1 has pooled
           mbar_wait(&ctl->o_done[st ^ 1], (uint32_t)(((lt - 1) >> 1) & 1));
           tc_fence_after();
@@ -406,7 +419,7 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
             tmem_ld_x16(ta, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < kNB; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) * ctl->alpha[c]);
+            for (int c = 0; c < kNB; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) * ctl->alpha[lt & 1][c]);
             tmem_st_x16(ta, r);
           }
           tmem_st_wait();
