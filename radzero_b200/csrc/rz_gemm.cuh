@@ -74,6 +74,7 @@ struct Ctrl {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint64_t epi_bar[8];      // two per epilogue warp: TMA loads issued by the epilogue itself
+  uint32_t sink[8];         // scratch words of lds_returned (one per epilogue warp), right behind epi_bar
   uint32_t tmem_slot;
 };
 

@@ -283,12 +283,13 @@ struct PassD2 : PolicyBase {
                    : "=r"(pw[4 * j]), "=r"(pw[4 * j + 1]), "=r"(pw[4 * j + 2]), "=r"(pw[4 * j + 3])
                    : "r"(in + stage_off(lane, j)));
     // the loads must have returned before the TMA refill of the same buffer is issued (lds_returned)
-    const uint32_t dep = lds_returned(pw[3], pw[7], pw[11], pw[15], pw[19], pw[23], pw[27], pw[31]);
+    lds_returned(smem_u32(bars + 8) + 4u * (uint32_t)warp, pw[3], pw[7], pw[11], pw[15], pw[19], pw[23], pw[27],
+                 pw[31]);                               // Ctrl::sink sits right behind epi_bar[8]
     __syncwarp();
     // the buffer is free again: fetch the box two chunks ahead (possibly of the next tile)
     if (lane == 0) {
-      if (c + 2 < nch) fetch(p, maps, tile, c + 2, warp, stg + dep, bars, g + 2);
-      else if (next_tile >= 0) fetch(p, maps, next_tile, c + 2 - nch, warp, stg + dep, bars, g + 2);
+      if (c + 2 < nch) fetch(p, maps, tile, c + 2, warp, stg, bars, g + 2);
+      else if (next_tile >= 0) fetch(p, maps, next_tile, c + 2 - nch, warp, stg, bars, g + 2);
     }
     st.g = g + 1;
     // packed fp32 pairs: the epilogue warp is alone on its scheduler, so its time is instructions x latency

@@ -82,6 +82,7 @@ struct Ctrl {
   float alpha[2][kNB];
   float m_fin[kNB], l_fin[kNB];
   float red[4][2 * kNB];
+  uint32_t sink[kConv];            // scratch words of lds_returned (one per converter warp)
 };
 
 template <typename TIn>
@@ -327,10 +328,10 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
 #ifndef RZ_EXP_LATE_RELEASE
       // every lane's loads must have RETURNED before the slot goes back to the TMA producer (see
       // lds_returned in rz_umma.cuh: the arrive can overtake loads still queued in the LSU)
-      const uint32_t dep = lds_returned(__float_as_uint(v[3]), __float_as_uint(v[7]), __float_as_uint(v[11]),
-                                        __float_as_uint(v[15]), __float_as_uint(v[19]), __float_as_uint(v[23]));
+      lds_returned(smem_u32(&ctl->sink[warp - 8]), __float_as_uint(v[3]), __float_as_uint(v[7]),
+                   __float_as_uint(v[11]), __float_as_uint(v[15]), __float_as_uint(v[19]), __float_as_uint(v[23]));
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl->ring_empty[slot] + dep);
+      if (lane == 0) mbar_arrive(&ctl->ring_empty[slot]);
 #endif
       const bool ok = j * kTokT + r < p.L;
       rz::ln_l2_row(v, ln ? p.gamma : nullptr, ln ? p.beta : nullptr, lane, RZ_LN_EPS, RZ_L2_EPS, p.l2 != 0);
@@ -348,7 +349,7 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->k_full[st]);
 #ifdef RZ_EXP_LATE_RELEASE
-      if (lane == 0) mbar_arrive(&ctl->ring_empty[slot] + dep);
+      if (lane == 0) mbar_arrive(&ctl->ring_empty[slot]);
 #endif
     }
   } else if (warp < 4) {

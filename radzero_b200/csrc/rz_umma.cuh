@@ -100,25 +100,23 @@ __device__ __forceinline__ void mbar_wait_warp_relaxed(uint64_t* bar, uint32_t p
   __syncwarp();
 }
 
-// Returns 0 once the shared-memory loads that produced the given registers have RETURNED.
+// Wait until the shared-memory loads that produced the given registers have RETURNED.
 // LDS is issued in order but completes asynchronously; an mbarrier arrive or a TMA issue that follows it
 // in program order takes another path and can overtake loads still queued behind the tensor core's
 // operand fetches.  If that arrive / issue hands the buffer back to the async proxy (a TMA refill), the
 // refill can land before the loads have read the old contents -- measured in sim_small_kernel after a
-// pipeline stall as one corrupted token per ~10^6.  The xor chain is real code consuming one register
-// of each load, so the thread waits on their scoreboards; fold the result into the address that is
-// used for the release (each lane must call this before the __syncwarp that precedes it).
-__device__ __forceinline__ uint32_t lds_returned(uint32_t a, uint32_t b, uint32_t c, uint32_t d,
-                                                 uint32_t e = 0, uint32_t f = 0, uint32_t g = 0, uint32_t h = 0) {
-  uint32_t z;
+// pipeline stall as one corrupted token per ~10^6.  The xor of one register of each load is STORED to a
+// scratch word (`sink`, shared memory, any value, never read): a store cannot be optimised away and
+// cannot issue before its operand -- i.e. all those loads -- has arrived.  Every lane calls this before
+// the __syncwarp that precedes the release.
+__device__ __forceinline__ void lds_returned(uint32_t sink, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                             uint32_t e = 0, uint32_t f = 0, uint32_t g = 0, uint32_t h = 0) {
   asm volatile("{\n\t.reg .b32 t;\n\t"
                "xor.b32 t, %1, %2;\n\txor.b32 t, t, %3;\n\txor.b32 t, t, %4;\n\t"
                "xor.b32 t, t, %5;\n\txor.b32 t, t, %6;\n\txor.b32 t, t, %7;\n\txor.b32 t, t, %8;\n\t"
-               "and.b32 %0, t, 0;\n\t}"
-               : "=r"(z)
-               : "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h)
+               "st.shared.b32 [%0], t;\n\t}"
+               ::"r"(sink), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h)
                : "memory");
-  return z;
 }
 
 // generic-proxy writes to smem -> visible to the async proxy (TMA / tcgen05 operands)
