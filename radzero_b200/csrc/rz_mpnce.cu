@@ -42,11 +42,29 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter) {
 // latencies per warp.  Values outside int32 can match no column and become -1.
 constexpr int kGroupCap = 8192;
 __device__ __forceinline__ void stage_group_map(const long long* __restrict__ gm, int n, int* sm) {
-  for (int i = threadIdx.x; i < n; i += kThreads) {
-    const long long g = __ldg(gm + i);
-    sm[i] = (g >= 0 && g <= 0x7fffffffLL) ? (int)g : -1;
+  // eight independent loads per thread in flight (a plain loop is one L2 latency per element)
+  for (int i0 = threadIdx.x; i0 < n; i0 += 8 * kThreads) {
+    long long g[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) g[u] = i0 + u * kThreads < n ? __ldg(gm + i0 + u * kThreads) : -1;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (i0 + u * kThreads < n) sm[i0 + u * kThreads] = (g[u] >= 0 && g[u] <= 0x7fffffffLL) ? (int)g[u] : -1;
   }
   __syncthreads();
+}
+
+// sum over the sentences i of column `gcol` of f(i), lanes striding the staged map four entries at a time
+template <class F>
+__device__ __forceinline__ void scan_column(const int* gsm, int n, int gcol, int lane, F&& f) {
+  for (int i0 = lane; i0 < n; i0 += 128) {
+    int g[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) g[u] = i0 + 32 * u < n ? gsm[i0 + 32 * u] : -1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (g[u] == gcol) f(i0 + 32 * u);
+  }
 }
 
 __device__ __forceinline__ float inv_temperature(const float* log_tau, float inv_tau) {
@@ -166,8 +184,7 @@ mpnce_partials_kernel(PartialsParams p) {
     for (int k = lane; k < chunks; k += 32) all += __ldcg(p.colpart + (long long)k * b_local + c);
     const long long gcol = (long long)p.col0 + c;
     if (staged) {
-      for (int i = lane; i < p.n_total; i += 32)
-        if (gsm[i] == (int)gcol) cp += __ldcg(p.pos + i);
+      scan_column(gsm, p.n_total, (int)gcol, lane, [&](int i) { cp += __ldcg(p.pos + i); });
     } else {
       for (int i0 = lane; i0 < p.n_total; i0 += 128) {
         long long g[4];
@@ -226,15 +243,19 @@ mpnce_finish_kernel(FinishParams p) {
     } else {
       // MP-NCE: one term per sentence i of this image: p = pos_i/(pos_i + Cneg + eps)  :337-342
       const float cn = p.colneg[c];
-      for (int i = lane; i < p.n_total; i += 32) {
-        const bool hit = staged ? gsm[i] == (int)gcol : __ldg(p.group_map + i) == gcol;
-        if (!hit) continue;
+      auto term = [&](int i) {
         const float ps = p.pos[i];
         const float den = ps + cn + p.eps;
         const float pc = ps / den;
         const float w = 1.0f / (pc + p.eps);
         l += -logf(pc + p.eps);
         a += w * ps / (den * den);
+      };
+      if (staged) {
+        scan_column(gsm, p.n_total, (int)gcol, lane, term);
+      } else {
+        for (int i = lane; i < p.n_total; i += 32)
+          if (__ldg(p.group_map + i) == gcol) term(i);
       }
       a = rz::warp_sum(a);
       l = rz::warp_sum(l);

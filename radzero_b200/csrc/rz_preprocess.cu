@@ -148,17 +148,59 @@ __device__ __forceinline__ uint8_t stretch8(float v, float a, float b) {
   return (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
 }
 
-// Horizontal pass.  One WARP owns a row at a time (no block-level synchronisation): it stretches the raw
-// row to uint8 (saturate(rint(fma(src, a, b)))) into its private shared-memory row, planar per channel,
-// then each lane accumulates output columns lane, lane + 32, ...  A CTA's warps take consecutive rows.
+// Horizontal pass.  A CTA stages the tap table (window start + weights of every output column) in shared
+// memory once and then walks `rows_per_warp` rows per warp.  One WARP owns a row at a time (no block-level
+// synchronisation in the row loop): it stretches the raw row to uint8 (saturate(rint(fma(src, a, b)))) into
+// its private shared-memory row -- 16-byte loads where the row is aligned -- and each lane then accumulates
+// output columns lane, lane + 32, ... with a branch-free tap loop (weights past the window are zero, the
+// row is padded by ksize bytes so the taps stay in bounds).
+template <typename T>
+__device__ __forceinline__ void stretch_row(const T* __restrict__ src, int n_el, int W, int Wp, int C, float a,
+                                            float b, uint8_t* srow, int lane) {
+  constexpr int kVec = 16 / (int)sizeof(T);
+  const bool vec = C == 1 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (n_el % kVec) == 0;
+  if (vec) {
+    const uint4* vp = reinterpret_cast<const uint4*>(src);
+    for (int j = lane; j < n_el / kVec; j += 32) {
+      const uint4 q = rz::ldg_stream_u4(vp + j);
+      const T* e = reinterpret_cast<const T*>(&q);
+      uint8_t o[kVec];
+#pragma unroll
+      for (int u = 0; u < kVec; ++u) o[u] = stretch8(as_float(e[u]), a, b);
+      if (kVec == 16) *reinterpret_cast<uint4*>(srow + 16 * j) = *reinterpret_cast<const uint4*>(o);
+      else if (kVec == 8) *reinterpret_cast<uint2*>(srow + 8 * j) = *reinterpret_cast<const uint2*>(o);
+      else *reinterpret_cast<uint32_t*>(srow + 4 * j) = *reinterpret_cast<const uint32_t*>(o);
+    }
+  } else if (C == 1) {
+    for (int i = lane; i < n_el; i += 32) srow[i] = stretch8(as_float(src[i]), a, b);
+  } else {
+    for (int i = lane; i < n_el; i += 32) {
+      const int x = i / C, c = i - x * C;
+      srow[c * Wp + x] = stretch8(as_float(src[i]), a, b);
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 pp_horizontal_kernel(const T* __restrict__ raw, int H, int W, int C, const double* __restrict__ part,
-                     Taps t, int w_out, int pitch, uint8_t* __restrict__ tmp, int rows_per_warp) {
-  extern __shared__ uint8_t srow_all[];      // [warps][C][Wp] planar
+                     Taps t, int w_out, int pitch, uint8_t* __restrict__ tmp, int rows_per_warp, int taps_in_smem) {
+  extern __shared__ __align__(16) uint8_t hs[];      // [tap table][warps][C][Wp]
   const int img = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int Wp = (W + 15) & ~15;
-  uint8_t* srow = srow_all + (size_t)warp * C * Wp;
+  const int ks = t.ksize;
+  const int Wp = (W + ks + 15) & ~15;                // row + tap padding
+  int* s_xmin = reinterpret_cast<int*>(hs);
+  int* s_w = s_xmin + w_out;
+  const size_t tab_bytes = taps_in_smem ? (((size_t)w_out * (1 + ks) * 4 + 15) & ~(size_t)15) : 0;
+  if (taps_in_smem) {
+    for (int i = threadIdx.x; i < w_out; i += kThreads) s_xmin[i] = __ldg(t.xmin + i);
+    for (int i = threadIdx.x; i < w_out * ks; i += kThreads) s_w[i] = __ldg(t.w + i);
+  }
+  uint8_t* srow = hs + tab_bytes + (size_t)warp * C * Wp;
+  for (int i = lane; i < C * Wp; i += 32) srow[i] = 0;                   // (the padding must be finite)
+  __syncthreads();
+  const int* xm = taps_in_smem ? s_xmin : t.xmin;
+  const int* wt = taps_in_smem ? s_w : t.w;
   float a, b;
   {
     double lo = DBL_MAX, hi = -DBL_MAX;
@@ -182,23 +224,19 @@ pp_horizontal_kernel(const T* __restrict__ raw, int H, int W, int C, const doubl
   for (int y = y0; y < min(H, y0 + rows_per_warp); ++y) {
     const T* src = raw + ((long long)img * H + y) * n_el;
     __syncwarp();
-    if (C == 1) {
-      for (int i = lane; i < n_el; i += 32) srow[i] = stretch8(as_float(src[i]), a, b);
-    } else {
-      for (int i = lane; i < n_el; i += 32) {
-        const int x = i / C, c = i - x * C;
-        srow[c * Wp + x] = stretch8(as_float(src[i]), a, b);
-      }
-    }
+    stretch_row<T>(src, n_el, W, Wp, C, a, b, srow, lane);
     __syncwarp();
-    for (int o = lane; o < w_out * C; o += 32) {
-      const int c = o / w_out, xo = o - c * w_out;
-      const int lo = __ldg(t.xmin + xo), n = __ldg(t.cnt + xo);
-      const int* wk = t.w + (long long)xo * t.ksize;
-      const uint8_t* s = srow + c * Wp + lo;
-      int acc = 1 << (kPrecisionBits - 1);
-      for (int k = 0; k < n; ++k) acc += (int)s[k] * __ldg(wk + k);
-      tmp[(((long long)img * C + c) * H + y) * pitch + xo] = clip8(acc);
+    for (int c = 0; c < C; ++c) {
+      const uint8_t* sc = srow + c * Wp;
+      uint8_t* dst = tmp + (((long long)img * C + c) * H + y) * pitch;
+      for (int xo = lane; xo < w_out; xo += 32) {
+        const uint8_t* s = sc + xm[xo];
+        const int* wk = wt + xo * ks;
+        int acc = 1 << (kPrecisionBits - 1);
+#pragma unroll 4
+        for (int k = 0; k < ks; ++k) acc += (int)s[k] * wk[k];
+        dst[xo] = clip8(acc);
+      }
     }
   }
 }
@@ -293,15 +331,19 @@ int run(const T* raw, int images, int H, int W, int C, int h_out, int w_out, con
   RZ_LAUNCH_OK();
   pp_minmax_kernel<T><<<dim3(kMinMaxSplit, images), kThreads, 0, s>>>(raw, (long long)H * W * C, part);
   RZ_LAUNCH_OK();
-  // horizontal: one warp per row, `rows_h` rows per warp; shared memory = one stretched row per warp
-  const int rows_h = 4;
+  // horizontal: one warp per row at a time, `rows_h` rows per warp; shared memory = tap table + one stretched
+  // (padded) row per warp
+  const int rows_h = 8;
   const int warps = kThreads / 32;
-  const size_t smem = (size_t)warps * C * ((W + 15) & ~15);
+  const size_t tab = (((size_t)w_out * (1 + pl.ks_h) * 4 + 15) & ~(size_t)15);
+  const size_t rows_b = (size_t)warps * C * ((W + pl.ks_h + 15) & ~15);
+  const int taps_in_smem = tab + rows_b <= 160 * 1024 ? 1 : 0;
+  const size_t smem = rows_b + (taps_in_smem ? tab : 0);
   if (smem > 200 * 1024) return RZ_ERR_UNSUPPORTED;
   if (smem > 48 * 1024)
     RZ_CUDA_OK(cudaFuncSetAttribute(pp_horizontal_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pp_horizontal_kernel<T><<<dim3((H + rows_h * warps - 1) / (rows_h * warps), images), kThreads, smem, s>>>(
-      raw, H, W, C, part, th, w_out, pl.pitch, tmp, rows_h);
+      raw, H, W, C, part, th, w_out, pl.pitch, tmp, rows_h, taps_in_smem);
   RZ_LAUNCH_OK();
   // vertical: `rows_v` output rows per CTA share a band of at most ceil(rows_v * H / h_out) + ksize source rows
   const int rows_v = 8;
