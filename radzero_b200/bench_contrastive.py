@@ -134,7 +134,8 @@ def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
     chk = torch.stack([dtok.double().abs().sum(), dtxt.double().abs().sum()])
     if distributed:
         dist.all_reduce(chk)
-    grad_checksum = float(chk.sum().item())
+    # under torch.distributed the node multiplies gradients by W (DDP averages them afterwards): undo it
+    grad_checksum = float(chk.sum().item()) / (world if distributed else 1)
     del dtok, dtxt
     barrier()
     n0 = _lib.launch_count()

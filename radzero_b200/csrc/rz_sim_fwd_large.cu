@@ -239,7 +239,10 @@ struct PassPK : PolicyBase {
   using Params = PKParams;
   static constexpr int kBN = 256, kAccs = 1;
   static constexpr bool kAMn = false, kBMn = true, kTwoPhase = false;
-  static constexpr int kEpiSmem = 4 * 4096;          // per warp: one 64-column fp16 box of pooled rows
+  // per warp: [q in, buffer 0][q in, buffer 1][pooled out], boxes of 32 rows x 128 B (64 fp16 columns)
+  static constexpr int kWarpStage = 3 * 4096;
+  static constexpr int kEpiSmem = 4 * kWarpStage;
+  struct State { uint32_t g; int primed; };         // q boxes consumed so far by this warp
   __host__ __device__ static int num_tiles(const Params& p) { return p.B * p.m_tiles * (kD / kBN); }
   // the three feature tiles of one (image, prompt tile) run back to back on one CTA: the P~ tile
   // they share as A operand is fetched from HBM once and re-read from L2
@@ -258,44 +261,89 @@ struct PassPK : PolicyBase {
     load_kmajor<C>(&m.a, bar, a, ks * kBK, mt * kBM, b);                              // P [B, N, Lp]
     load_mnmajor_shared<C>(&m.b, bar, bsm, ft * kBN, ks * kBK, b, kBN / 64, rank);    // k [B, Lp, 768]
   }
-  __device__ static __forceinline__ void chunk(const Params& p, const Maps& maps, Cols64& v,
-                                               const uint4 (&qv)[8], int f0, int b, int row0, int lane,
-                                               float linv, uint32_t stg, float& osq, float& qo) {
+  // lane 0: fetch the q box (32 prompts x 64 features) of chunk `c` of `tile` for this warp's rows.
+  // (A thread-per-row global load touches 32 different lines per instruction and left the epilogue
+  // waiting on the L2: it was the stall that kept this pass at 75 % of the tensor pipe.)
+  __device__ static __forceinline__ void fetch(const Params& p, const Maps& maps, int tile, int c, int warp,
+                                               uint32_t stg, uint64_t* bars, uint32_t g) {
+    int b, mt, ft;
+    decode(p, tile, b, mt, ft);
+    uint64_t* bar = bars + warp * 2 + (g & 1);
+    mbar_arrive_expect_tx(bar, 4096u);
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(stg + (g & 1) * 4096u),
+        "l"(reinterpret_cast<uint64_t>(&maps.a2)), "r"(smem_u32(bar)), "r"(ft * kBN + c * 64),
+        "r"(mt * kBM + warp * 32), "r"(0), "l"(kEvictLast)
+        : "memory");
+  }
+  template <class S>
+  __device__ static void prologue(const Params& p, const Maps& maps, int tile, int warp, int lane,
+                                  uint64_t* bars, S& st, uint8_t* epi_smem) {
+    if (st.primed) return;
+    st.primed = 1;
+    st.g = 0;
+    if (lane == 0) {
+      const uint32_t stg = smem_u32(epi_smem) + warp * kWarpStage;
+      fetch(p, maps, tile, 0, warp, stg, bars, 0);
+      fetch(p, maps, tile, 1, warp, stg, bars, 1);
+    }
+  }
+  __device__ static __forceinline__ void chunk(const Params& p, const Maps& maps, Cols64& v, int tile,
+                                               int next_tile, int c, int f0, int b, int row0, int warp, int lane,
+                                               float linv, uint32_t stg, uint64_t* bars, State& st, P2& osq,
+                                               P2& qo) {
     const bool store = p.pooled != nullptr;
+    // this chunk's q box: 64 halves of this thread's prompt row
+    const uint32_t g = st.g;
+    const uint32_t in = stg + (g & 1) * 4096u;
+    mbar_wait(bars + warp * 2 + (g & 1), (g >> 1) & 1);
+    uint32_t qw[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(qw[4 * j]), "=r"(qw[4 * j + 1]), "=r"(qw[4 * j + 2]), "=r"(qw[4 * j + 3])
+                   : "r"(in + stage_off(lane, j)));
+    lds_returned(smem_u32(bars + 8) + 4u * (uint32_t)warp, qw[3], qw[7], qw[11], qw[15], qw[19], qw[23], qw[27],
+                 qw[31]);                               // before the refill of the same buffer is issued
+    __syncwarp();
+    if (lane == 0) {
+      constexpr int nch = kBN / 64;
+      if (c + 2 < nch) fetch(p, maps, tile, c + 2, warp, stg, bars, g + 2);
+      else if (next_tile >= 0) fetch(p, maps, next_tile, c + 2 - nch, warp, stg, bars, g + 2);
+    }
+    st.g = g + 1;
+    const uint32_t out = stg + 8192;
     if (store) {
       if (lane == 0) tma_store_wait_read();
       __syncwarp();
     }
+    const P2 linv2 = p2(linv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint32_t* src = j < 4 ? &v.lo[8 * j] : &v.hi[8 * (j - 4)];
-      const uint32_t qw[4] = {qv[j].x, qv[j].y, qv[j].z, qv[j].w};
       uint32_t o[4];
 #pragma unroll
       for (int i = 0; i < 8; i += 2) {
-        const float a0 = __uint_as_float(src[i]) * linv, a1 = __uint_as_float(src[i + 1]) * linv;
-        const float2 qq = __half22float2(*reinterpret_cast<const __half2*>(&qw[i >> 1]));
-        osq = fmaf(a0, a0, fmaf(a1, a1, osq));
-        qo = fmaf(a0, qq.x, fmaf(a1, qq.y, qo));
-        o[i >> 1] = pack_h2(a0, a1);
+        const P2 a = p2_mul(p2(__uint_as_float(src[i]), __uint_as_float(src[i + 1])), linv2);
+        const float2 qq = __half22float2(*reinterpret_cast<const __half2*>(&qw[4 * j + (i >> 1)]));
+        osq = p2_fma(a, a, osq);
+        qo = p2_fma(a, p2(qq.x, qq.y), qo);
+        o[i >> 1] = p2_pack_h2(a);
       }
-      if (store) sts_v4(stg + stage_off(lane, j), o[0], o[1], o[2], o[3]);
+      if (store) sts_v4(out + stage_off(lane, j), o[0], o[1], o[2], o[3]);
     }
     if (store) {
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_3d(&maps.c, stg, f0, row0, b);
+        tma_store_3d(&maps.c, out, f0, row0, b);
         tma_store_commit();
       }
     }
   }
-  __device__ static __forceinline__ void ldq(const __half* qrow, int c0, uint4 (&qv)[8]) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) qv[j] = __ldg(reinterpret_cast<const uint4*>(qrow + c0) + j);
-  }
-  __device__ static void epilogue(const Params& p, const Maps& maps, int tile, int, uint32_t tmem,
-                                  int warp, int lane, uint64_t*, State&, uint8_t* epi_smem) {
+  __device__ static void epilogue(const Params& p, const Maps& maps, int tile, int next_tile, uint32_t tmem,
+                                  int warp, int lane, uint64_t* bars, State& st, uint8_t* epi_smem) {
     int b, mt, ft;
     decode(p, tile, b, mt, ft);
     const int row0 = mt * kBM + warp * 32;
@@ -303,30 +351,27 @@ struct PassPK : PolicyBase {
     const bool row_ok = n < p.N;
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
     const long long pi = (long long)b * p.N + (row_ok ? n : 0);
-    const __half* qrow = p.q + (long long)(row_ok ? n : 0) * kD + ft * kBN;
-    const uint32_t stg = smem_u32(epi_smem) + warp * 4096;
+    const uint32_t stg = smem_u32(epi_smem) + warp * kWarpStage;
     const float linv = row_ok ? 1.0f / p.lsum[pi] : 0.f;
-    float osq = 0.f, qo = 0.f;
+    P2 osq = p2(0.f), qo = p2(0.f);
     Cols64 va, vb;
-    uint4 qa[8], qb[8];
     ld64(taddr, va);
-    ldq(qrow, 0, qa);
 #pragma unroll 1
     for (int c = 0; c < kBN / 64; c += 2) {
       wait64(va);
       ld64(taddr + (c + 1) * 64, vb);
-      ldq(qrow, (c + 1) * 64, qb);
-      chunk(p, maps, va, qa, ft * kBN + c * 64, b, row0, lane, linv, stg, osq, qo);
+      chunk(p, maps, va, tile, next_tile, c, ft * kBN + c * 64, b, row0, warp, lane, linv, stg, bars, st, osq, qo);
       wait64(vb);
-      if (c + 2 < kBN / 64) {
-        ld64(taddr + (c + 2) * 64, va);
-        ldq(qrow, (c + 2) * 64, qa);
-      }
-      chunk(p, maps, vb, qb, ft * kBN + (c + 1) * 64, b, row0, lane, linv, stg, osq, qo);
+      if (c + 2 < kBN / 64) ld64(taddr + (c + 2) * 64, va);
+      chunk(p, maps, vb, tile, next_tile, c + 1, ft * kBN + (c + 1) * 64, b, row0, warp, lane, linv, stg, bars,
+            st, osq, qo);
     }
     if (row_ok) {
+      float o0, o1, q0, q1;
+      p2_unpack(osq, o0, o1);
+      p2_unpack(qo, q0, q1);
       float2* d = reinterpret_cast<float2*>(p.part) + (pi * (kD / kBN) + ft);
-      *d = make_float2(osq, qo);
+      *d = make_float2(o0 + o1, q0 + q1);
     }
   }
 };
@@ -437,7 +482,9 @@ extern "C" int rz_sim_fwd_large(const void* k_f16, int n_images, int tokens, int
     Maps mk = {};
     if (!rz::make_map_3d_sw128(&mk.a, pbuf, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, kBM)) return RZ_ERR_CUDA;
     if (!rz::make_map_3d_sw128(&mk.b, k_f16, B, Lp, kD, kD * 2, (uint64_t)Lp * kD * 2, 64)) return RZ_ERR_CUDA;
-    mk.a2 = mk.a; mk.b2 = mk.b; mk.c = mk.a; mk.c2 = mk.a;
+    mk.b2 = mk.b; mk.c = mk.a; mk.c2 = mk.a;
+    // q boxes of 32 prompts x 64 features for the epilogue warps (rows >= N: zero fill)
+    if (!rz::make_map_3d_sw128(&mk.a2, q_f16, 1, N, kD, kD * 2, (uint64_t)N * kD * 2, 32)) return RZ_ERR_CUDA;
     if (pooled_f16 != nullptr &&
         !rz::make_map_3d_sw128(&mk.c, pooled_f16, B, N, kD, kD * 2, (uint64_t)N * kD * 2, 32))
       return RZ_ERR_CUDA;
