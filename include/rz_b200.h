@@ -332,6 +332,8 @@ int rz_text_pool(const void* hidden, int dtype, const long long* attention_mask,
 #define RZ_LIN_BIAS 0
 #define RZ_LIN_GELU 1
 #define RZ_LIN_RESIDUAL 2
+#define RZ_LIN_RESIDUAL_F16 3 /* residual + scale * (acc + bias) written ONLY as fp16 [m, n]: the last layer's
+                                 tokens handed to rz_sim_fwd_tokens at half the bytes (out must not alias residual) */
 int rz_ln_rows(const void* x, int dtype, const float* gamma, const float* beta, float eps,
                long long rows, void* out_f16, void* stream);
 int rz_linear(const void* a_f16, long long m, int k, const void* w_f16, int n, const float* bias,

@@ -64,12 +64,15 @@ def pack_layer(layer: nn.Module, device=None) -> Dict[str, torch.Tensor]:
     }
 
 
-def layer_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def layer_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], out: Optional[torch.Tensor] = None,
+                  f16_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """One Dinov2Layer on the fp32 residual stream ``x`` (B, L, 768).
 
     ``out`` None: ``x`` is updated in place.  Otherwise ``x`` is only read and the new residual stream
     is written to ``out`` (the first residual GEMM goes out of place, which is how the caller's tokens
-    stay untouched without a copy)."""
+    stay untouched without a copy).  ``f16_out`` (B, L, 768) fp16: the layer's result is written ONLY
+    there by the last GEMM's epilogue (the tokens reach the similarity
+    kernel in fp16, half the bytes); the fp32 stream then holds the intermediate state ``h``."""
     B, L, D = x.shape
     x2 = x.view(B * L, D)
     y2 = x2 if out is None else out.view(B * L, D)
@@ -79,6 +82,9 @@ def layer_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], out: Optional[tor
     ops.linear(a.view(B * L, D), w["wo"], w["bo"], "residual", scale=w["ls1"], residual=x2, out=y2)
     h = ops.ln_rows(y2, w["g2"], w["b2"], w["eps2"])
     g = ops.linear(h, w["w1"], w["bf1"], "gelu")
+    if f16_out is not None:
+        ops.linear(g, w["w2"], w["bf2"], "residual_f16", scale=w["ls2"], residual=y2, out=f16_out.view(B * L, D))
+        return f16_out
     ops.linear(g, w["w2"], w["bf2"], "residual", scale=w["ls2"], residual=y2, out=y2)
     return x if out is None else out
 
@@ -135,16 +141,22 @@ class AlignTransformer(nn.Module):
             return True
         return self.training and any(p.requires_grad for p in self.parameters())
 
-    def forward(self, vision_tokens: torch.Tensor, inplace: bool = False) -> torch.Tensor:
+    def forward(self, vision_tokens: torch.Tensor, inplace: bool = False,
+                handoff_f16: bool = False) -> torch.Tensor:
         """``inplace=True`` lets the kernels update the caller's fp32 token buffer (no copy).  The result
-        comes back in the input's dtype, as the reference's module does (bf16 / fp16 models)."""
+        comes back in the input's dtype, as the reference's module does (bf16 / fp16 models).
+        ``handoff_f16=True`` (inference, when the consumer is the similarity kernel): the last layer's
+        tokens are emitted by its fc2 epilogue as fp16 and returned as such -- the fp32 copy is never
+        written and the similarity kernel reads half the bytes."""
         if self._needs_grad(vision_tokens):
             return self.stock_forward(vision_tokens)
         with torch.no_grad():
-            out = self._forward_kernels(vision_tokens, inplace)
+            out = self._forward_kernels(vision_tokens, inplace, handoff_f16)
+        if handoff_f16 and out.dtype == torch.float16:
+            return out
         return out if out.dtype == vision_tokens.dtype else out.to(vision_tokens.dtype)
 
-    def _forward_kernels(self, vision_tokens: torch.Tensor, inplace: bool) -> torch.Tensor:
+    def _forward_kernels(self, vision_tokens: torch.Tensor, inplace: bool, handoff_f16: bool = False) -> torch.Tensor:
         if not vision_tokens.is_cuda:
             raise RzError("radzero_b200 ops run on CUDA tensors only (there is no CPU fallback)")
         if vision_tokens.dim() != 3 or vision_tokens.shape[-1] != ops.HIDDEN:
@@ -158,11 +170,17 @@ class AlignTransformer(nn.Module):
             fresh = torch.empty_like(x)                           # first layer writes here: no copy of the input
         elif not inplace:
             x = x.clone()
+        f16 = None
+        if handoff_f16 and layers and self.layer_norm is None:
+            f16 = torch.empty(x.shape, dtype=torch.float16, device=x.device)
         for i, w in enumerate(layers):
+            last16 = f16 if i == len(layers) - 1 else None
             if i == 0 and fresh is not None:
-                x = layer_forward(x, w, out=fresh)
+                x = layer_forward(x, w, out=fresh, f16_out=last16)
             else:
-                layer_forward(x, w)
+                x = layer_forward(x, w, f16_out=last16)
+        if f16 is not None:
+            return f16
         if self.layer_norm is not None:
             # use_layer_norm=True (not the released configuration): one more row LayerNorm, fp32 out
             g, b = self.layer_norm.weight.detach(), self.layer_norm.bias.detach()

@@ -48,7 +48,8 @@ def run(args, world, rank, local, pk, steps=None, warmup=None):
     tok = synthetic.make_inputs(B, 1, seed=42 + rank, device=dev)[0]
 
     def step(t):
-        return fn.similarity_prob(text, align(t))
+        # the last layer's tokens reach the similarity kernel in fp16 (RZ_LIN_RESIDUAL_F16): half the bytes
+        return fn.similarity_prob(text, align(t, handoff_f16=True))
 
     def barrier():
         if world > 1:
@@ -109,6 +110,22 @@ def run(args, world, rank, local, pk, steps=None, warmup=None):
         kms[name] = round(t, 4)
         detail[name] = ({"tflops": round(fl / t / 1e9, 1)} if fl else {"gbs": round(by / t / 1e6, 1)})
     del x2, h, qkv, a, g
+    # the similarity stage behind the hand-off: rz_sim_fwd_tokens on fp16 tokens (0.54 GB read once)
+    x16 = align(tok, handoff_f16=True)
+    for _ in range(3):
+        fn.similarity_prob(text, x16)
+    torch.cuda.synchronize()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    for _ in range(20):
+        fn.similarity_prob(text, x16)
+    eb.record()
+    torch.cuda.synchronize()
+    sim_ms = ea.elapsed_time(eb) / 20
+    sim_bytes = B * L * D * 2 + N * D * 4 + B * N * 4
+    sim_stage = {"ms": round(sim_ms, 4), "bytes_read": sim_bytes, "input_dtype": "fp16 (fc2 epilogue hand-off)",
+                 "frac_of_hbm": round(sim_bytes / (sim_ms * 1e-3) / 1e9 / pk["hbm"], 3)}
+    del x16
     flops = align_flops(B)
     ach = flops / (ms_per_step * 1e-3) / 1e12
     roof = {"bound": "tensor", "kernel": "whole step (6 GEMM-shaped kernels per layer x 2 layers + similarity)",
@@ -140,7 +157,7 @@ def run(args, world, rank, local, pk, steps=None, warmup=None):
             main.wait_event(ev)
             if i + 1 < n:
                 ev = upload(k ^ 1)
-            r_host.copy_(fn.similarity_prob(text, align(d_tok[k], inplace=True)), non_blocking=True)
+            r_host.copy_(fn.similarity_prob(text, align(d_tok[k], inplace=True, handoff_f16=True)), non_blocking=True)
             used[k] = torch.cuda.Event()
             used[k].record(main)
         main.synchronize()
@@ -166,4 +183,4 @@ def run(args, world, rank, local, pk, steps=None, warmup=None):
             "config": {"workload": DESC, "images_per_gpu": B, "prompts": N, "tokens": L, "hidden": D,
                        "input_dtype": "fp32", "l2": "activations (>= 0.5 GB per kernel) larger than L2; no flush",
                        "parallelism": f"images sharded x{world}, no collective"},
-            "prob_checksum": float(res.double().sum().item())}
+            "sim_stage": sim_stage, "prob_checksum": float(res.double().sum().item())}

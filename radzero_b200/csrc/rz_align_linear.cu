@@ -8,6 +8,8 @@
 //   RZ_LIN_GELU      out fp16 [M, N] = gelu_erf(acc + bias)             (mlp.fc1 + activation)
 //   RZ_LIN_RESIDUAL  out fp32 [M, N] = residual + scale * (acc + bias)  (attention.output.dense / mlp.fc2
 //                                       + LayerScale + the residual add; out may alias residual)
+//   RZ_LIN_RESIDUAL_F16  the same value, written ONLY as fp16 [M, N]: the hand-off of the last layer's
+//                                       tokens to the similarity kernel at half the bytes
 //
 // Tiles are 128 x 256; the N tiles of one 128-row block run on neighbouring CTAs at the same time (the
 // A block comes from HBM once, the weights stay in L2), and two CTAs of a cluster pair
@@ -92,12 +94,15 @@ struct Lin : PolicyBase {
   // per warp: fp16 outputs two alternating [32 rows x 64 cols] boxes; the residual epilogue a ring of four
   // [32 rows x 32 cols] fp32 boxes (residual in by TMA, result out by TMA from the same box) plus
   // one mbarrier per box
-  static constexpr int kWarpStage = EPI == RZ_LIN_RESIDUAL ? 16384 : 8192;
+  static constexpr bool kRes = EPI == RZ_LIN_RESIDUAL || EPI == RZ_LIN_RESIDUAL_F16;
+  static constexpr bool kF16Out = EPI == RZ_LIN_RESIDUAL_F16;
+  // (fp16 hand-off: the four fp32 residual boxes + two alternating [32 rows x 64 cols] fp16 output boxes)
+  static constexpr int kWarpStage = kF16Out ? 24576 : (kRes ? 16384 : 8192);
   // the GELU epilogue is bound by the instruction issue of its warps: eight epilogue warps, two per
   // TMEM lane quarter, each taking one 128-column half of the tile (fc1 1.51 -> 1.41 ms); the plain
   // bias epilogue is not, and the extra warps cost it tensor-pipe time (90 % -> 81 % active)
   static constexpr int kEpiWarps = EPI == RZ_LIN_GELU ? 8 : 4;
-  static constexpr int kEpiSmem = kEpiWarps * kWarpStage + (EPI == RZ_LIN_RESIDUAL ? 128 : 0);
+  static constexpr int kEpiSmem = kEpiWarps * kWarpStage + (kRes ? 128 : 0);
   struct State { uint32_t g; int ready; };     // g: 32-column boxes this warp has consumed so far
   __host__ __device__ static int num_tiles(const Params& p) { return p.m_tiles * p.n_tiles; }
   __host__ __device__ static int k_steps(const Params& p) { return p.K / kBK; }
@@ -179,7 +184,7 @@ struct Lin : PolicyBase {
   template <class S>
   __device__ static void prologue(const Params& p, const Maps& maps, int tile, int warp, int lane, uint64_t*,
                                   S& st, uint8_t* epi_smem) {
-    if (EPI != RZ_LIN_RESIDUAL || st.ready) return;
+    if (!kRes || st.ready) return;
     st.ready = 1;
     if (lane == 0) {
       for (int i = 0; i < 4; ++i) mbar_init(res_bar(epi_smem, warp, i), 1);
@@ -198,13 +203,22 @@ struct Lin : PolicyBase {
       const int h2 = h + 2;
       const int t2 = h2 < 8 ? tile : next_tile;
       if (t2 >= 0) {
-        tma_store_wait_read_n<1>();
+        // fp32 mode: the box was last the source of the store of box g - 2.  fp16 hand-off: nothing is
+        // stored from the residual boxes; box g - 2 was only read, two halves of arithmetic ago
+        if (!kF16Out) tma_store_wait_read_n<1>();
         res_load(p, maps, t2, h2 & 7, g + 2, warp, epi_smem);
       }
     }
     const int box = (int)(g & 3u);
     const uint32_t stg = smem_u32(epi_smem) + warp * kWarpStage + box * 4096;
     mbar_wait(res_bar(epi_smem, warp, box), (g >> 2) & 1u);
+    // fp16 hand-off: two halves (32 columns each) fill one [32 rows x 64 cols] fp16 box, two boxes alternate
+    const uint32_t out16 = smem_u32(epi_smem) + warp * kWarpStage + 16384 + ((g >> 1) & 1u) * 4096;
+    if (kF16Out && (h & 1) == 0) {
+      if (lane == 0) tma_store_wait_read_n<1>();     // the store issued from this box two pairs ago
+      __syncwarp();
+    }
+    uint32_t pk[16];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float4 r;
@@ -217,14 +231,33 @@ struct Lin : PolicyBase {
       const float o1 = fmaf(s.y, __uint_as_float(a[4 * j + 1]) + b.y, r.y);
       const float o2 = fmaf(s.z, __uint_as_float(a[4 * j + 2]) + b.z, r.z);
       const float o3 = fmaf(s.w, __uint_as_float(a[4 * j + 3]) + b.w, r.w);
-      sts_v4(stg + stage_off(lane, j), __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2),
-             __float_as_uint(o3));
+      if (kF16Out) {
+        pk[2 * j] = pack_h2(o0, o1);
+        pk[2 * j + 1] = pack_h2(o2, o3);
+      } else {
+        sts_v4(stg + stage_off(lane, j), __float_as_uint(o0), __float_as_uint(o1), __float_as_uint(o2),
+               __float_as_uint(o3));
+      }
     }
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_3d(&maps.c, stg, col0, row0, 0);
-      tma_store_commit();
+    if (kF16Out) {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+        sts_v4(out16 + stage_off(lane, 4 * (h & 1) + jj), pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+      if (h & 1) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&maps.c, out16, col0 - 32, row0, 0);
+          tma_store_commit();
+        }
+      }
+    } else {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&maps.c, stg, col0, row0, 0);
+        tma_store_commit();
+      }
     }
     st.g = g + 1;
   }
@@ -238,7 +271,7 @@ struct Lin : PolicyBase {
     const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16);
     const uint32_t stg = smem_u32(epi_smem) + warp * kWarpStage;
     Cols64 va, vb;
-    if (EPI != RZ_LIN_RESIDUAL) {
+    if (!kRes) {
       // warp w takes 64-column chunks [c0, c0 + kChunks) of the tile: all four with 4 epilogue warps,
       // one 128-column half with 8
       constexpr int kChunks = 16 / kEpiWarps;
@@ -284,8 +317,11 @@ extern "C" int rz_linear(const void* a_f16, long long m, int k, const void* w_f1
                          void* out, void* stream) {
   if (!a_f16 || !w_f16 || !out || m < 0 || k <= 0 || n <= 0) return RZ_ERR_INVALID;
   if (k % kBK != 0 || n % 256 != 0) return RZ_ERR_UNSUPPORTED;
-  if (epilogue != RZ_LIN_BIAS && epilogue != RZ_LIN_GELU && epilogue != RZ_LIN_RESIDUAL) return RZ_ERR_INVALID;
-  if (epilogue == RZ_LIN_RESIDUAL && residual == nullptr) return RZ_ERR_INVALID;
+  if (epilogue != RZ_LIN_BIAS && epilogue != RZ_LIN_GELU && epilogue != RZ_LIN_RESIDUAL &&
+      epilogue != RZ_LIN_RESIDUAL_F16)
+    return RZ_ERR_INVALID;
+  const bool res = epilogue == RZ_LIN_RESIDUAL || epilogue == RZ_LIN_RESIDUAL_F16;
+  if (res && residual == nullptr) return RZ_ERR_INVALID;
   if (m == 0) return RZ_OK;
   if (m >= (1ll << 31) - 256) return RZ_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(a_f16) & 15) || (reinterpret_cast<uintptr_t>(w_f16) & 15) ||
@@ -315,12 +351,13 @@ extern "C" int rz_linear(const void* a_f16, long long m, int k, const void* w_f1
       return RZ_ERR_CUDA;
   }
   mp.c2 = mp.c;
-  if (epilogue == RZ_LIN_RESIDUAL &&
+  if (res &&
       !rz::make_map_3d_f32_sw128(&mp.c2, residual, 1, (uint64_t)m, (uint64_t)n, (uint64_t)n * 4, (uint64_t)m * n * 4, 32))
     return RZ_ERR_CUDA;
   switch (epilogue) {
     case RZ_LIN_BIAS: return launch_lin<RZ_LIN_BIAS>(mp, p, pair, s);
     case RZ_LIN_GELU: return launch_lin<RZ_LIN_GELU>(mp, p, pair, s);
+    case RZ_LIN_RESIDUAL_F16: return launch_lin<RZ_LIN_RESIDUAL_F16>(mp, p, pair, s);
     default: return launch_lin<RZ_LIN_RESIDUAL>(mp, p, pair, s);
   }
 }

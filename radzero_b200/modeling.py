@@ -141,11 +141,18 @@ class CxrAlignModel(PreTrainedModel):
                     module.weight.fill_(1.0)
 
     # ------------------------------------------------------------------ encoders (stock HF)
-    def forward_vision_model(self, pixel_values):
+    def forward_vision_model(self, pixel_values, handoff_f16: bool = False):
+        """modeling.py:96-123.  ``handoff_f16`` (used by ``compute_logits``, whose only consumer of the tokens
+        is the similarity kernel): the AlignTransformer emits its last layer in fp16."""
         out = self.vision_model(pixel_values)
         vision_tokens = out["last_hidden_state"] if not torch.is_tensor(out) else out
-        at = self.align_transformer(vision_tokens)
+        if handoff_f16 and hasattr(self.align_transformer, "_forward_kernels") and vision_tokens.is_cuda:
+            at = self.align_transformer(vision_tokens, handoff_f16=True)
+        else:
+            at = self.align_transformer(vision_tokens)
         vision_tokens = at["last_hidden_state"] if not torch.is_tensor(at) else at
+        if handoff_f16:          # compute_logits reads nothing but the tokens (image_features are unused there)
+            return {"vision_tokens": vision_tokens}
         cls_token = vision_tokens[:, 0]
         patch_tokens = vision_tokens[:, 1:]
         image_features = F.normalize(torch.cat([cls_token, patch_tokens.mean(dim=1)], dim=1), p=2, dim=1)
@@ -206,7 +213,7 @@ class CxrAlignModel(PreTrainedModel):
         """
         if self.compute_logits_type != "radzero":
             raise NotImplementedError(self.compute_logits_type)
-        vision = self.forward_vision_model(pixel_values)
+        vision = self.forward_vision_model(pixel_values, handoff_f16=bool(kwargs.get("handoff_f16", True)))
         loss_fn: RadZeroLoss = self.loss_fns["RadZeroLoss"]
         enc = encoded_key_phrases[0]
         hidden = self._text_hidden(enc)

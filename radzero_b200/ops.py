@@ -495,7 +495,8 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilo
 
     a (M, K) fp16, w (N, K) fp16 (nn.Linear.weight layout), bias fp32 (N,).  ``epilogue``:
     "bias" / "gelu" -> fp16 (M, N); "residual" -> fp32 ``residual + scale * (a @ w.T + bias)``
-    (``out`` may be ``residual`` itself: in-place update of the residual stream).
+    (``out`` may be ``residual`` itself: in-place update of the residual stream); "residual_f16" -> the
+    same value written only as fp16 (the last layer's hand-off to the similarity kernel).
     """
     _need_cuda(a, w, bias, scale, residual, out)
     if a.dtype != torch.float16 or w.dtype != torch.float16 or a.dim() != 2 or w.dim() != 2:
@@ -504,15 +505,16 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilo
         raise RzError("linear operands must be contiguous (M, K) and (N, K)")
     m, k = a.shape
     n = w.shape[0]
-    ep = {"bias": _lib.RZ_LIN_BIAS, "gelu": _lib.RZ_LIN_GELU, "residual": _lib.RZ_LIN_RESIDUAL}[epilogue]
+    ep = {"bias": _lib.RZ_LIN_BIAS, "gelu": _lib.RZ_LIN_GELU, "residual": _lib.RZ_LIN_RESIDUAL,
+          "residual_f16": _lib.RZ_LIN_RESIDUAL_F16}[epilogue]
     for v in (bias, scale):
         if v is not None and (v.dtype != torch.float32 or v.numel() != n or not v.is_contiguous()):
             raise RzError("bias / scale must be contiguous fp32 (N,)")
-    if ep == _lib.RZ_LIN_RESIDUAL:
+    if ep in (_lib.RZ_LIN_RESIDUAL, _lib.RZ_LIN_RESIDUAL_F16):
         if residual is None or residual.dtype != torch.float32 or tuple(residual.shape) != (m, n) \
                 or not residual.is_contiguous():
             raise RzError("residual must be contiguous fp32 (M, N)")
-        odt = torch.float32
+        odt = torch.float32 if ep == _lib.RZ_LIN_RESIDUAL else torch.float16
     else:
         odt = torch.float16
     if out is None:

@@ -280,3 +280,40 @@ def test_attention_score_ranges(scale):
     want = _attn_ref(qkv, heads)
     assert torch.isfinite(got).all()
     assert (got - want).abs().max().item() <= 4e-3, (got - want).abs().max().item()
+
+
+def test_f16_handoff_of_the_last_layer():
+    """the last fc2 epilogue hands the tokens over as fp16 (RZ_LIN_RESIDUAL_F16)
+    and the small-N similarity kernel consumes them directly -- same values as the fp32 path rounded once,
+    and the similarity within the north star's tolerances."""
+    from radzero_b200 import losses
+    torch.manual_seed(5)
+    m, k, n = 2 * 1370 + 5, 3072, 768
+    a = torch.randn(m, k, device=DEV).half()
+    w = (torch.randn(n, k, device=DEV) * 0.05).half()
+    bias = torch.randn(n, device=DEV) * 0.1
+    scale = torch.rand(n, device=DEV) + 0.5
+    res = torch.randn(m, n, device=DEV) * 3
+    full = ops.linear(a, w, bias, "residual", scale=scale, residual=res)
+    half = ops.linear(a, w, bias, "residual_f16", scale=scale, residual=res)
+    assert half.dtype == torch.float16 and torch.equal(half, full.to(torch.float16))
+    # the assembled module + the similarity behind it
+    B, N, seed = 3, 14, 23
+    enc, _ = _gpu_weights(seed)
+    tok, text, gamma, beta, log_tau = [t.to(DEV) for t in synthetic.make_inputs(B, N, seed=seed)]
+    mod = AlignTransformer(enc).eval()
+    keep = tok.clone()
+    x32 = mod(tok)
+    x16 = mod(tok, handoff_f16=True)
+    assert torch.equal(tok, keep) and x16.dtype == torch.float16 and x16.shape == x32.shape
+    assert torch.equal(x16, x32.to(torch.float16))
+    fn = losses.RadZeroLoss(sim_op="cos").to(DEV)
+    with torch.no_grad():
+        fn.layer_norm.weight.copy_(gamma)
+        fn.layer_norm.bias.copy_(beta)
+    p32 = fn.similarity_prob(text, x32)
+    p16 = fn.similarity_prob(text, x16)
+    assert ((p16 - p32) / p32).abs().max().item() < 1e-3
+    _, s32, _ = fn.similarity(text, x32, want_scores=True)
+    _, s16, _ = fn.similarity(text, x16, want_scores=True)
+    assert (s16 - s32).abs().max().item() < 2e-3
