@@ -119,6 +119,47 @@ template <> struct RowLoad<__half> {
   }
 };
 
+// Packed fp32 pairs (Blackwell fma.rn.f32x2 / mul.rn.f32x2): one issue slot for two lanes of epilogue
+// arithmetic.  The persistent GEMMs run ONE epilogue warp per scheduler, so their epilogues are bound by
+// instruction issue latency, not by any pipe: halving the instruction count is a direct speed-up.
+struct P2 { uint64_t v; };
+__device__ __forceinline__ P2 p2(float a, float b) {
+  P2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ P2 p2(float a) { return p2(a, a); }
+__device__ __forceinline__ void p2_unpack(P2 x, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v));
+}
+__device__ __forceinline__ P2 p2_fma(P2 a, P2 b, P2 c) {
+  P2 r;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ P2 p2_mul(P2 a, P2 b) {
+  P2 r;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ P2 p2_add(P2 a, P2 b) {
+  P2 r;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ uint32_t p2_pack_h2(P2 x) {
+  float a, b;
+  p2_unpack(x, a, b);
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ P2 p2_sub(P2 a, P2 b) {            // a - b  (fma with -1: there is no sub.f32x2)
+  P2 r;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(b.v), "l"(p2(-1.0f).v), "l"(a.v));
+  return r;
+}
+
 struct RowStats { float mean, rstd, inv_norm; };
 
 // LayerNorm (biased variance, eps_ln) then L2 normalisation (x / max(|x|, eps_l2)) of the
@@ -161,6 +202,58 @@ __device__ __forceinline__ RowStats ln_l2_row(float (&x)[24], const float* __res
 #pragma unroll
     for (int i = 0; i < 24; ++i) x[i] *= inv;
   }
+  return st;
+}
+
+// ln_l2_row with packed fp32 pairs: the same operations in the same order on two neighbouring elements
+// per instruction (FADD2 / FFMA2 / FMUL2), i.e. bit-identical results at about half the FP32 issue slots.
+// For kernels whose row loop is bound by instruction issue (the converter warps of sim_small_kernel).
+__device__ __forceinline__ RowStats ln_l2_row_packed(float (&x)[24], const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, int lane,
+                                                     float eps_ln, float eps_l2, bool do_l2 = true) {
+  RowStats st;
+  st.mean = 0.f; st.rstd = 1.f; st.inv_norm = 1.f;
+  P2 v[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) v[i] = p2(x[2 * i], x[2 * i + 1]);
+  if (gamma != nullptr) {
+    P2 s2 = v[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) s2 = p2_add(s2, v[i]);
+    float s0, s1;
+    p2_unpack(s2, s0, s1);
+    const float mu = warp_sum(s0 + s1) * (1.0f / RZ_HIDDEN);
+    const P2 mu2 = p2(mu);
+    P2 q2 = p2(0.f);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { v[i] = p2_sub(v[i], mu2); q2 = p2_fma(v[i], v[i], q2); }
+    float q0, q1;
+    p2_unpack(q2, q0, q1);
+    const float rstd = rsqrtf(warp_sum(q0 + q1) * (1.0f / RZ_HIDDEN) + eps_ln);
+    st.mean = mu; st.rstd = rstd;
+    const P2 r2 = p2(rstd);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * (lane + 32 * j));
+      const float4 b = *reinterpret_cast<const float4*>(beta + 4 * (lane + 32 * j));
+      v[2 * j] = p2_fma(p2_mul(v[2 * j], r2), p2(g.x, g.y), p2(b.x, b.y));
+      v[2 * j + 1] = p2_fma(p2_mul(v[2 * j + 1], r2), p2(g.z, g.w), p2(b.z, b.w));
+    }
+  }
+  if (do_l2) {
+    P2 n2 = p2(0.f);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) n2 = p2_fma(v[i], v[i], n2);
+    float n0, n1;
+    p2_unpack(n2, n0, n1);
+    const float inv = 1.0f / fmaxf(sqrtf(warp_sum(n0 + n1)), eps_l2);
+    st.inv_norm = inv;
+    const P2 i2 = p2(inv);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) v[i] = p2_mul(v[i], i2);
+  }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) p2_unpack(v[i], x[2 * i], x[2 * i + 1]);
   return st;
 }
 

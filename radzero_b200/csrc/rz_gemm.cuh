@@ -316,40 +316,9 @@ __device__ __forceinline__ void wait64(Cols64& v) {
   tmem_ld_wait_x32(v.hi);
 }
 
-// Packed fp32 pairs (Blackwell fma.rn.f32x2 / mul.rn.f32x2): one issue slot for two lanes of epilogue
-// arithmetic.  The persistent GEMMs run ONE epilogue warp per scheduler, so their epilogues are bound by
-// instruction issue latency, not by any pipe: halving the instruction count is a direct speed-up.
-struct P2 { uint64_t v; };
-__device__ __forceinline__ P2 p2(float a, float b) {
-  P2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ P2 p2(float a) { return p2(a, a); }
-__device__ __forceinline__ void p2_unpack(P2 x, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v));
-}
-__device__ __forceinline__ P2 p2_fma(P2 a, P2 b, P2 c) {
-  P2 r;
-  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
-  return r;
-}
-__device__ __forceinline__ P2 p2_mul(P2 a, P2 b) {
-  P2 r;
-  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-  return r;
-}
-__device__ __forceinline__ P2 p2_add(P2 a, P2 b) {
-  P2 r;
-  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-  return r;
-}
-__device__ __forceinline__ uint32_t p2_pack_h2(P2 x) {
-  float a, b;
-  p2_unpack(x, a, b);
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
+// packed fp32 pairs (rz_common.cuh), visible to the policies that `use namespace rz::gemm`
+using rz::P2; using rz::p2; using rz::p2_unpack; using rz::p2_fma; using rz::p2_mul; using rz::p2_add;
+using rz::p2_sub; using rz::p2_pack_h2;
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);

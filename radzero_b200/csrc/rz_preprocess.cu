@@ -90,14 +90,50 @@ __global__ void pp_coeff_kernel(Taps th, int w_in, int w_out, Taps tv, int h_in,
 
 template <typename T> __device__ __forceinline__ float as_float(T v) { return (float)v; }
 
-// per-image min / max over all channels (cv::minMaxIdx); values compared as double (exact for every type).
-// 16-byte loads over the aligned body of this CTA's slice, scalar head / tail.
-template <typename T>
-__device__ __forceinline__ void minmax_acc(T v, double& lo, double& hi) {
-  const double d = (double)v;
-  lo = fmin(lo, d);
-  hi = fmax(hi, d);
-}
+// per-image min / max over all channels (cv::minMaxIdx), exact for every type: the reduction runs in the
+// element's own domain (packed SIMD min / max for 8- and 16-bit pixels: four or two per instruction) and is
+// widened to double only at the end.  16-byte loads over the aligned body of this CTA's slice.
+template <typename T> struct MinMax;
+template <> struct MinMax<uint8_t> {
+  uint32_t lo = 0xffffffffu, hi = 0u;
+  __device__ __forceinline__ void word(uint32_t w) { lo = __vminu4(lo, w); hi = __vmaxu4(hi, w); }
+  __device__ __forceinline__ void one(uint8_t v) { word(v * 0x01010101u); }
+  __device__ __forceinline__ void fin(double& a, double& b) const {
+    uint32_t l = min(min(lo & 255u, (lo >> 8) & 255u), min((lo >> 16) & 255u, lo >> 24));
+    uint32_t h = max(max(hi & 255u, (hi >> 8) & 255u), max((hi >> 16) & 255u, hi >> 24));
+    a = (double)l; b = (double)h;
+  }
+};
+template <> struct MinMax<uint16_t> {
+  uint32_t lo = 0xffffffffu, hi = 0u;
+  __device__ __forceinline__ void word(uint32_t w) { lo = __vminu2(lo, w); hi = __vmaxu2(hi, w); }
+  __device__ __forceinline__ void one(uint16_t v) { word(v * 0x00010001u); }
+  __device__ __forceinline__ void fin(double& a, double& b) const {
+    a = (double)min(lo & 0xffffu, lo >> 16); b = (double)max(hi & 0xffffu, hi >> 16);
+  }
+};
+template <> struct MinMax<int16_t> {
+  uint32_t lo = 0x7fff7fffu, hi = 0x80008000u;
+  __device__ __forceinline__ void word(uint32_t w) { lo = __vmins2(lo, w); hi = __vmaxs2(hi, w); }
+  __device__ __forceinline__ void one(int16_t v) { word((uint32_t)(uint16_t)v * 0x00010001u); }
+  __device__ __forceinline__ void fin(double& a, double& b) const {
+    a = (double)min((int)(int16_t)(lo & 0xffffu), (int)(int16_t)(lo >> 16));
+    b = (double)max((int)(int16_t)(hi & 0xffffu), (int)(int16_t)(hi >> 16));
+  }
+};
+template <> struct MinMax<int32_t> {
+  int lo = 0x7fffffff, hi = (int)0x80000000;
+  __device__ __forceinline__ void word(uint32_t w) { lo = min(lo, (int)w); hi = max(hi, (int)w); }
+  __device__ __forceinline__ void one(int32_t v) { word((uint32_t)v); }
+  __device__ __forceinline__ void fin(double& a, double& b) const { a = (double)lo; b = (double)hi; }
+};
+template <> struct MinMax<float> {
+  float lo = FLT_MAX, hi = -FLT_MAX;
+  __device__ __forceinline__ void word(uint32_t w) { const float f = __uint_as_float(w); lo = fminf(lo, f); hi = fmaxf(hi, f); }
+  __device__ __forceinline__ void one(float v) { lo = fminf(lo, v); hi = fmaxf(hi, v); }
+  __device__ __forceinline__ void fin(double& a, double& b) const { a = (double)lo; b = (double)hi; }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 pp_minmax_kernel(const T* __restrict__ raw, long long per_image, double* __restrict__ part) {
@@ -106,23 +142,26 @@ pp_minmax_kernel(const T* __restrict__ raw, long long per_image, double* __restr
   const T* src = raw + (long long)img * per_image;
   const long long per = (per_image + kMinMaxSplit - 1) / kMinMaxSplit;
   const long long i0 = (long long)split * per, i1 = min(per_image, i0 + per);
-  double lo = DBL_MAX, hi = -DBL_MAX;
+  MinMax<T> mm;
   if (i0 < i1) {
     // first element of the slice whose address is 16-byte aligned
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(src + i0);
     long long v0 = i0 + (long long)(((16 - (a0 & 15)) & 15) / sizeof(T));
     if (v0 > i1) v0 = i1;
     const long long nvec = (i1 - v0) / kVec;
-    for (long long i = i0 + threadIdx.x; i < v0; i += kThreads) minmax_acc(src[i], lo, hi);
+    for (long long i = i0 + threadIdx.x; i < v0; i += kThreads) mm.one(src[i]);
     const uint4* vp = reinterpret_cast<const uint4*>(src + v0);
-    for (long long j = threadIdx.x; j < nvec; j += kThreads) {
+    for (long long j = threadIdx.x; j < nvec; j += 2 * kThreads) {
       const uint4 q = rz::ldg_stream_u4(vp + j);
-      const T* e = reinterpret_cast<const T*>(&q);
-#pragma unroll
-      for (int u = 0; u < kVec; ++u) minmax_acc(e[u], lo, hi);
+      const bool two = j + kThreads < nvec;
+      const uint4 r = two ? rz::ldg_stream_u4(vp + j + kThreads) : q;
+      mm.word(q.x); mm.word(q.y); mm.word(q.z); mm.word(q.w);
+      mm.word(r.x); mm.word(r.y); mm.word(r.z); mm.word(r.w);
     }
-    for (long long i = v0 + nvec * kVec + threadIdx.x; i < i1; i += kThreads) minmax_acc(src[i], lo, hi);
+    for (long long i = v0 + nvec * kVec + threadIdx.x; i < i1; i += kThreads) mm.one(src[i]);
   }
+  double lo, hi;
+  mm.fin(lo, hi);            // a thread that saw no element holds the type's (max, min): neutral for the reduction
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));

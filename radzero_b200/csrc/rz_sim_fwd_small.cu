@@ -334,7 +334,7 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
       if (lane == 0) mbar_arrive(&ctl->ring_empty[slot]);
 #endif
       const bool ok = j * kTokT + r < p.L;
-      rz::ln_l2_row(v, ln ? p.gamma : nullptr, ln ? p.beta : nullptr, lane, RZ_LN_EPS, RZ_L2_EPS, p.l2 != 0);
+      rz::ln_l2_row_packed(v, ln ? p.gamma : nullptr, ln ? p.beta : nullptr, lane, RZ_LN_EPS, RZ_L2_EPS, p.l2 != 0);
       // lane's 4 features of group jj: feature 4*(lane + 32 jj) -> chunk (lane + 32 jj) / 16,
       // byte 8 * ((lane + 32 jj) % 16) of the token's 128-byte row
       uint8_t* tile = k_s + st * kKStage + rz::sw128_offset((uint32_t)r, (uint32_t)(8 * (lane & 15))) +
