@@ -24,23 +24,43 @@ using namespace rz::umma;
 
 constexpr int kD = RZ_HIDDEN;            // 768
 constexpr int kNB = 16;                  // prompts per CTA (MMA N of the pooling GEMM)
-constexpr int kTokT = 16;                // tokens per tile
+#ifndef RZ_SMALL_TOKT
+#define RZ_SMALL_TOKT 16
+#endif
+constexpr int kTokT = RZ_SMALL_TOKT;     // tokens per tile.  The S^T GEMM is a chain of 48 dependent MMAs per tile
+                                         // whatever its width: 32 tokens per tile halve that chain per token
 constexpr int kChunks = kD / 64;         // 12 K-chunks of 64 features (128 B of fp16)
 constexpr int kSlabs = kD / 128;         // 6 feature slabs (MMA M = 128) of the pooled accumulator
 constexpr int kGroup = 4;                // rows per ring group (one TMA transaction set)
-constexpr int kRing = 6;                 // ring slots = teams (fp32: 6 x 4 x 3 KB = 72 KB): a slot always belongs
-                                         // to the same team, so its barrier phases are observed by every waiter
-constexpr int kTeams = 6;                // converter teams of kGroup warps; team t takes groups t, t+6, ...
-constexpr int kStages = 5;               // fp16 token tiles (24 KB each): 1-2 in the MMA chain, the rest being filled
-static_assert(kTokT == 16, "the softmax warp reads its tile with tcgen05.ld.x16");
-static_assert(kRing == kTeams, "parity barriers: every waiter must observe every phase of its slot");
-constexpr int kConv = kGroup * kTeams;   // 24 converter warps: rows in flight hide the ~2k-cycle row latency
+// Ring of raw-token groups: kSlotsPerTeam slots per converter team (slot s belongs to team s % kTeams, so
+// every waiter observes every phase of its slots' barriers).  Shapes measured in round 2 at C2 (0.229 ms
+// baseline = 6 teams x 1 slot, 16-token tiles, 5 fp16 stages): 5 teams x 2 slots x 3 stages 0.246 ms;
+// 6 x 2 x 5 (16-bit tokens only: shared memory) 0.219 ms; 32-token tiles with 2 / 3 stages 0.342 / 0.223 ms.
+// Ablations (results wrong, time only): no LayerNorm arithmetic 0.209 ms, no exponentials 0.224 ms, 1/12 of
+// the S-GEMM chain 0.228 ms -- no single stage bounds the kernel; it sits ~10 % above what its fixed per-row
+// protocol (two barrier waits, 6 LDS, 6 STS, a proxy fence and two arrives per row) costs by itself.
+#ifndef RZ_SMALL_TEAMS
+#define RZ_SMALL_TEAMS 6
+#endif
+#ifndef RZ_SMALL_SPT
+#define RZ_SMALL_SPT 1
+#endif
+#ifndef RZ_SMALL_STAGES
+#define RZ_SMALL_STAGES 5
+#endif
+constexpr int kTeams = RZ_SMALL_TEAMS;   // converter teams of kGroup warps; team t takes groups t, t + kTeams, ...
+constexpr int kSlotsPerTeam = RZ_SMALL_SPT;
+constexpr int kRing = kTeams * kSlotsPerTeam;    // fp32: 10 x 4 x 3 KB = 120 KB
+constexpr int kStages = RZ_SMALL_STAGES; // fp16 token tiles (24 KB each): 1-2 in the MMA chain, the rest being filled
+static_assert(kTokT % 16 == 0 && kTokT <= 64, "the softmax warp reads its tile in tcgen05.ld.x16 halves");
+static_assert(kRing % kTeams == 0, "parity barriers: every waiter must observe every phase of its slots");
+constexpr int kConv = kGroup * kTeams;   // converter warps: rows in flight hide the row latency
 constexpr int kThreads = 256 + 32 * kConv;      // WG0 softmax/epilogue, WG1 TMA + MMA (+2 spare warps), converters
 // register budget per warpgroup after setmaxnreg: the pool is what the CTA got at launch
-// (64 registers x 1024 threads = 8 warpgroups x 64), so the sum over warpgroups must stay 512
+// (64 registers x kThreads), so the sum over warpgroups must stay inside it
 constexpr int kRegsEpi = 56, kRegsCtl = 24, kRegsConv = 72;
-static_assert(kConv == 24, "the setmaxnreg budget assumes 24 converter warps");
-static_assert(kRegsEpi + kRegsCtl + 6 * kRegsConv <= 8 * 64, "register pool");
+static_assert((kRegsEpi + kRegsCtl) * 128 + kRegsConv * 32 * kConv <= 64 * kThreads, "register pool");
+static_assert(kConv % 4 == 0, "setmaxnreg works on whole warpgroups");
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kGrow = 8.0f;            // the reference maximum moves when exceeded by this much
 
@@ -48,7 +68,7 @@ constexpr int kQBytes = kChunks * kNB * 128;            // 24 KB
 constexpr int kKChunk = kTokT * 128;                    // 2 KB: [16 tokens x 64 features] fp16
 constexpr int kKStage = kChunks * kKChunk;              // 24 KB
 constexpr int kPBuf = 2048;                             // [16 prompts x 128 B] (32 B used)
-constexpr int kTmemCols = 128;                          // 96 (O^T) + 2 x 16 (S^T)
+constexpr int kTmemCols = kTokT <= 16 ? 128 : 256;      // 96 (O^T) + 2 x kTokT (S^T), a power of two
 constexpr int kSCol = kSlabs * kNB;                     // 96
 constexpr int kPartFloats = 2 * kNB + kD * kNB;         // m[16], l[16], O[768][16]
 
@@ -285,10 +305,13 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
             // (the leading-dimension offset = kKChunk sits in bits 16-29 of the LOW descriptor word)
             const uint32_t ka_lo = (((k_addr + st * kKStage) & 0x3FFFFu) >> 4) | ((uint32_t)(kKChunk >> 4) << 16);
             const uint32_t pb_lo = ((p_addr + sb * kPBuf) & 0x3FFFFu) >> 4;
+            // K = the tile's tokens, 16 per MMA: A advances 16 token rows (2 KB) inside each chunk, B 32 bytes
 #pragma unroll
-            for (int s = 0; s < kSlabs; ++s)
-              mma(tmem_base + s * kNB, ka_lo + ((2 * s * kKChunk) >> 4), d_hi, pb_lo, d_hi, idesc_o,
-                  i > 0 ? 1u : 0u);
+            for (int kk = 0; kk < kTokT / 16; ++kk)
+#pragma unroll
+              for (int s = 0; s < kSlabs; ++s)
+                mma(tmem_base + s * kNB, ka_lo + ((2 * s * kKChunk) >> 4) + kk * (2048 >> 4), d_hi, pb_lo + 2 * kk, d_hi,
+                    idesc_o, (i > 0 || kk > 0) ? 1u : 0u);
           }
           mma_commit(&ctl->k_empty[st]);
           mma_commit(&ctl->o_done[sb]);
@@ -379,21 +402,22 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
           // pass A over the scores: maximum (+ the optional similarity map); the values are read
           // again from TMEM for the exponentials, which keeps this kernel inside 64 registers
           float cmax = -INFINITY;
-          {
-            uint32_t v[kTokT];
-            tmem_ld_x16(tmem_base + lane_base + kSCol + st * kTokT, v);
+#pragma unroll
+          for (int hh = 0; hh < kTokT; hh += 16) {         // 16 columns at a time (register budget)
+            uint32_t v[16];
+            tmem_ld_x16(tmem_base + lane_base + kSCol + st * kTokT + hh, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < kTokT; ++c) {
+            for (int c = 0; c < 16; ++c) {
               const float s = __uint_as_float(v[c]) * scale;
-              if (full || l0 + c < p.L) cmax = fmaxf(cmax, s);
+              if (full || l0 + hh + c < p.L) cmax = fmaxf(cmax, s);
               if (p.scores != nullptr) v[c] = __float_as_uint(s);
             }
             if (row && p.scores != nullptr && lane < p.N) {
               float* dst = p.scores + (long long)b * p.scores_sb + (long long)lane * p.scores_sn - p.drop_cls;
 #pragma unroll
-              for (int c = 0; c < kTokT; ++c) {
-                const int tkn = l0 + c;
+              for (int c = 0; c < 16; ++c) {
+                const int tkn = l0 + hh + c;
                 if (tkn < p.L && tkn >= p.drop_cls) __stcs(dst + tkn, __uint_as_float(v[c]));
               }
             }
@@ -431,28 +455,29 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
           // P (fp16) for the pooling GEMM; its buffer was last read by the pooling MMAs of tile lt-2
           if (lt >= 2) mbar_wait(&ctl->o_done[st], (uint32_t)(((lt - 2) >> 1) & 1));
           const float sl2 = scale * kLog2e, mb = m * kLog2e;
-          uint32_t pk[kTokT / 2];
-          {
-            uint32_t v[kTokT];
-            tmem_ld_x16(tmem_base + lane_base + kSCol + st * kTokT, v);
+#pragma unroll
+          for (int hh = 0; hh < kTokT; hh += 16) {
+            uint32_t pk[8];
+            uint32_t v[16];
+            tmem_ld_x16(tmem_base + lane_base + kSCol + st * kTokT + hh, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < kTokT; c += 2) {
+            for (int c = 0; c < 16; c += 2) {
               float e0 = exp2f(fmaf(__uint_as_float(v[c]), sl2, -mb));
               float e1 = exp2f(fmaf(__uint_as_float(v[c + 1]), sl2, -mb));
               if (!full) {
-                if (l0 + c >= p.L) e0 = 0.f;
-                if (l0 + c + 1 >= p.L) e1 = 0.f;
+                if (l0 + hh + c >= p.L) e0 = 0.f;
+                if (l0 + hh + c + 1 >= p.L) e1 = 0.f;
               }
               pk[c >> 1] = rz::pack_half2(e0, e1);
             }
-          }
-          if (row) {
-            uint8_t* prow = p_s + st * kPBuf;
+            if (row) {
+              uint8_t* prow = p_s + st * kPBuf;
 #pragma unroll
-            for (int u = 0; u < kTokT / 8; ++u)
-              *reinterpret_cast<uint4*>(prow + rz::sw128_offset((uint32_t)lane, (uint32_t)(16 * u))) =
-                  make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+              for (int u = 0; u < 2; ++u)
+                *reinterpret_cast<uint4*>(prow + rz::sw128_offset((uint32_t)lane, (uint32_t)(2 * hh + 16 * u))) =
+                    make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
