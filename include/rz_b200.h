@@ -239,9 +239,12 @@ int rz_map_threshold_stats(const float* scores, long long map_stride, int maps, 
  * (the loss_temperature parameter: no host synchronisation), else 1 / inv_tau.
  *
  * Launch 1 (rz_mpnce_partials): E = exp(Z/tau); per-row local sums rowsum[i] = sum_b E_ib,
- *   pos[i] = E[i, group_map[i]] if that column is local else 0, per-column sums
- *   colneg[b] = sum_{i: g_i != b} E_ib and colpos[b] = sum_{i: g_i = b} E_ib, all in a fixed
- *   summation order (no float atomics) so that 1-GPU and N-GPU runs agree.
+ *   pos[i] = E[i, group_map[i]] if that column is local else 0, and the column state
+ *   colstate[5][b4] (b4 = b_local rounded up to 4): colneg[b] = sum_{i: g_i != b} E_ib,
+ *   colpos[b] = sum_{i: g_i = b} E_ib, and the column coefficients acol / apos / lcol of the
+ *   backward and the column loss terms (they depend on local quantities only), all in a fixed
+ *   summation order (no float atomics) so that 1-GPU and N-GPU runs agree.  eps / col_sum / b_global
+ *   must be the values launch 2 is given.
  *   With several ranks the caller all-reduces (sum) rowsum and pos between the launches.
  *   scratch1: fp32 [rz_mpnce_partials_scratch_floats(n_total, b_local)].
  * Launch 2 (rz_mpnce_finish): loss terms and dL/dZ for the local columns.
@@ -255,20 +258,20 @@ int rz_map_threshold_stats(const float* scores, long long map_stride, int maps, 
  *   row_sum / col_sum select the MIL-NCE variants (losses.py:303-315, 331-336).
  *   z, dz    [n_total, ldz] fp32 (b_local valid columns per row); dz may be NULL (loss only)
  *   group_map int64 [n_total] GLOBAL image index
+ *   colstate the block launch 1 wrote (16-byte aligned)
  *   scratch2 fp32 [rz_mpnce_finish_scratch_floats(n_total, b_local, b_global)]
  */
 size_t rz_mpnce_partials_scratch_floats(int n_total, int b_local);
 size_t rz_mpnce_finish_scratch_floats(int n_total, int b_local, int b_global);
-int rz_mpnce_partials(const float* z, long long ldz, int n_total, int b_local,
+int rz_mpnce_partials(const float* z, long long ldz, int n_total, int b_local, int b_global,
                       const long long* group_map, int col0, float inv_tau, const float* log_tau,
-                      float* rowsum, float* pos, float* colneg, float* colpos,
+                      float eps, int col_sum, float* rowsum, float* pos, float* colstate,
                       float* scratch1, void* stream);
 int rz_mpnce_finish(const float* z, long long ldz, int n_total, int b_local, int b_global,
                     const long long* group_map, int col0, float inv_tau, const float* log_tau,
                     float eps, int row_sum, int col_sum,
-                    const float* rowsum, const float* pos, const float* colneg,
-                    const float* colpos, float* scratch2, float* dz, float* loss_terms,
-                    void* stream);
+                    const float* rowsum, const float* pos, const float* colstate,
+                    float* scratch2, float* dz, float* loss_terms, void* stream);
 
 /* ---- K11: image preprocessing of the zero-shot evaluators ------------
  * Replaces, for `images` same-sized raw images resident in device memory, the host-side chain

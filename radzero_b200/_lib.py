@@ -48,8 +48,8 @@ SIGNATURES: Dict[str, tuple] = {
     "rz_map_threshold_stats": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "rz_mpnce_partials_scratch_floats": (C.c_size_t, [_i, _i]),
     "rz_mpnce_finish_scratch_floats": (C.c_size_t, [_i, _i, _i]),
-    "rz_mpnce_partials": (_i, [_vp, _ll, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "rz_mpnce_finish": (_i, [_vp, _ll, _i, _i, _i, _vp, _i, _f, _vp, _f, _i, _i, _vp, _vp, _vp, _vp,
+    "rz_mpnce_partials": (_i, [_vp, _ll, _i, _i, _i, _vp, _i, _f, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "rz_mpnce_finish": (_i, [_vp, _ll, _i, _i, _i, _vp, _i, _f, _vp, _f, _i, _i, _vp, _vp, _vp,
                              _vp, _vp, _vp, _vp]),
     "rz_preprocess_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i, _i, _i]),
     "rz_preprocess_images": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, C.c_double, _vp, _i, _vp,

@@ -245,14 +245,14 @@ def run(args, world, rank, local, pk, steps=None, warmup=None, quiet=False):
     lt = fn.loss_temperature.detach()
 
     def nce():
-        rs, ps, cn, cp = ops.mpnce_partials(zt, gm_all, rank * b_local, log_tau=lt)
+        rs, ps, cn, cp = ops.mpnce_partials(zt, gm_all, rank * b_local, log_tau=lt, b_global=B_GLOBAL)
         return ops.mpnce_finish(zt, gm_all, rank * b_local, B_GLOBAL, 1.0, rs, ps, cn, cp, log_tau=lt)
     n1 = _lib.launch_count()
     nce()
     nce_launches = _lib.launch_count() - n1
     nce_ms = dev_time(nce)
-    rs_, ps_, cn_, cp_ = ops.mpnce_partials(zt, gm_all, rank * b_local, log_tau=lt)
-    nce_parts = {"partials_us": round(dev_time(lambda: ops.mpnce_partials(zt, gm_all, rank * b_local, log_tau=lt)) * 1e3, 1),
+    rs_, ps_, cn_, cp_ = ops.mpnce_partials(zt, gm_all, rank * b_local, log_tau=lt, b_global=B_GLOBAL)
+    nce_parts = {"partials_us": round(dev_time(lambda: ops.mpnce_partials(zt, gm_all, rank * b_local, log_tau=lt, b_global=B_GLOBAL)) * 1e3, 1),
                  "finish_us": round(dev_time(lambda: ops.mpnce_finish(zt, gm_all, rank * b_local, B_GLOBAL, 1.0, rs_, ps_,
                                                                       cn_, cp_, log_tau=lt)) * 1e3, 1)}
     nce_bytes = 2 * n_total * b_local * 4

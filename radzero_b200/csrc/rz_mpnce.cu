@@ -83,6 +83,8 @@ struct PartialsParams {
   const float* z; long long ldz; int n_total, b_local;
   const long long* group_map; int col0; float inv_tau; const float* log_tau;
   float *rowsum, *pos, *colneg, *colpos;
+  float *acol, *apos, *lcol; // per local column: negatives / positives coefficient, column loss terms
+  float eps, inv_2ncol; int col_sum;
   float* colpart;            // [chunks][b_local]: sum over the chunk's rows of E (negatives AND positives)
   unsigned int* barrier;
 };
@@ -197,54 +199,24 @@ mpnce_partials_kernel(PartialsParams p) {
     }
     all = rz::warp_sum(all);
     cp = rz::warp_sum(cp);
-    if (lane == 0) { p.colneg[c] = all - cp; p.colpos[c] = cp; }
-  }
-}
-
-// ---- launch 2 --------------------------------------------------------------------------
-struct FinishParams {
-  const float* z; long long ldz; int n_total, b_local, b_global;
-  const long long* group_map; int col0; float inv_tau, eps; int row_sum, col_sum;
-  const float* log_tau;
-  const float* rowsum; const float* pos; const float* colneg; const float* colpos;
-  float *acol, *apos, *lcol; // per local column: negatives / positives coefficient, loss part
-  float *img_rs, *img_ps;    // per global image (row_sum)
-  float *lrow, *dzz_part;    // per row: loss term, sum_b dZ*Z
-  float* dz; float* loss_terms;
-  float inv_2nrow, inv_2ncol;
-  unsigned int* barrier;
-};
-
-// dZ_ib = E_ib/tau * (ca_i + [b==g_i](cb_i + apos_b) + [b!=g_i] acol_b)
-template <bool VEC>
-__global__ void __launch_bounds__(kThreads)
-mpnce_finish_kernel(FinishParams p) {
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int gw = blockIdx.x * kWarps + warp, nw = gridDim.x * kWarps;
-  const float inv_tau = inv_temperature(p.log_tau, p.inv_tau);
-  __shared__ int gsm[kGroupCap];
-  const bool staged = p.n_total <= kGroupCap;
-  const bool scans = (int)blockIdx.x * kWarps < p.b_local || (p.row_sum && (int)blockIdx.x * kWarps < p.b_global);
-  if (staged && scans) stage_group_map(p.group_map, p.n_total, gsm);
-  // ---- phase 0a: per local column, the coefficient applied to the negatives / positives of that
-  // column and the column loss terms it owns.  One WARP per column: the lanes stride over the
-  // sentences and are combined in a fixed order (bit-reproducible, independent of the rank count).
-  for (int c = gw; c < p.b_local; c += nw) {
-    const long long gcol = (long long)p.col0 + c;
+    const float cn = all - cp;
+    // the coefficient applied to the negatives / positives of this column and the column loss terms it
+    // owns: they depend on local quantities only (every sentence is present for a local column), so they
+    // are computed here, before the cross-rank reduction, and launch 2 starts with the rows right away.
+    // The lanes stride over the sentences and are combined in a fixed order (bit-reproducible).
     float a = 0.f, ap = 0.f, l = 0.f;
     if (p.col_sum) {
       // MIL-NCE column term: p = colpos / (colneg + colpos + eps)        losses.py:331-336
-      const float cs = p.colneg[c] + p.colpos[c] + p.eps;
-      const float pc = p.colpos[c] / cs;
+      const float cs = cn + cp + p.eps;
+      const float pc = cp / cs;
       const float u = 1.0f / (pc + p.eps);
       l = -logf(pc + p.eps);
-      a = u * p.colpos[c] / (cs * cs) * p.inv_2ncol;
-      ap = -u * (1.0f / cs - p.colpos[c] / (cs * cs)) * p.inv_2ncol;
+      a = u * cp / (cs * cs) * p.inv_2ncol;
+      ap = -u * (1.0f / cs - cp / (cs * cs)) * p.inv_2ncol;
     } else {
       // MP-NCE: one term per sentence i of this image: p = pos_i/(pos_i + Cneg + eps)  :337-342
-      const float cn = p.colneg[c];
       auto term = [&](int i) {
-        const float ps = p.pos[i];
+        const float ps = __ldcg(p.pos + i);
         const float den = ps + cn + p.eps;
         const float pc = ps / den;
         const float w = 1.0f / (pc + p.eps);
@@ -261,10 +233,39 @@ mpnce_finish_kernel(FinishParams p) {
       l = rz::warp_sum(l);
       a *= p.inv_2ncol;
     }
-    if (lane == 0) { p.acol[c] = a; p.apos[c] = ap; p.lcol[c] = l; }
+    if (lane == 0) {
+      p.colneg[c] = cn; p.colpos[c] = cp;
+      p.acol[c] = a; p.apos[c] = ap; p.lcol[c] = l;
+    }
   }
+}
+
+// ---- launch 2 --------------------------------------------------------------------------
+struct FinishParams {
+  const float* z; long long ldz; int n_total, b_local, b_global;
+  const long long* group_map; int col0; float inv_tau, eps; int row_sum, col_sum;
+  const float* log_tau;
+  const float* rowsum; const float* pos; const float* colneg; const float* colpos;
+  const float *acol, *apos, *lcol; // per local column (from launch 1)
+  float *img_rs, *img_ps;    // per global image (row_sum)
+  float *lrow, *dzz_part;    // per row: loss term, sum_b dZ*Z
+  float* dz; float* loss_terms;
+  float inv_2nrow, inv_2ncol;
+  unsigned int* barrier;
+};
+
+// dZ_ib = E_ib/tau * (ca_i + [b==g_i](cb_i + apos_b) + [b!=g_i] acol_b)
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads)
+mpnce_finish_kernel(FinishParams p) {
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int gw = blockIdx.x * kWarps + warp, nw = gridDim.x * kWarps;
+  const float inv_tau = inv_temperature(p.log_tau, p.inv_tau);
+  __shared__ int gsm[kGroupCap];
+  const bool staged = p.n_total <= kGroupCap;
   // ---- phase 0b (row_sum only): Rs_b = sum_{i in b} R_i, Ps_b = sum_{i in b} pos_i, every GLOBAL image
   if (p.row_sum) {
+    if (staged && (int)blockIdx.x * kWarps < p.b_global) stage_group_map(p.group_map, p.n_total, gsm);
     for (int b = gw; b < p.b_global; b += nw) {
       float rs = 0.f, ps = 0.f;
       for (int i = lane; i < p.n_total; i += 32) {
@@ -275,8 +276,8 @@ mpnce_finish_kernel(FinishParams p) {
       ps = rz::warp_sum(ps);
       if (lane == 0) { p.img_rs[b] = rs; p.img_ps[b] = ps; }
     }
+    grid_barrier(p.barrier);           // (the only grid-wide barrier of this launch, MIL-NCE rows only)
   }
-  grid_barrier(p.barrier);
   // ---- phase 1: one warp per row: row coefficients, dZ, sum dZ*Z
   float l_acc = 0.f, z_acc = 0.f;
   for (int r = gw; r < p.n_total; r += nw) {
@@ -365,10 +366,16 @@ mpnce_finish_kernel(FinishParams p) {
     p.lrow[blockIdx.x] = a;
     p.dzz_part[blockIdx.x] = b;
   }
-  grid_barrier(p.barrier);
-  // ---- phase 2 (CTA 0): fixed-order tree: loss_terms = {sum row terms, sum col terms, sum dZ*Z,
-  // this rank's share of the loss}
-  if (blockIdx.x != 0) return;
+  // ---- phase 2: the LAST CTA to get here reduces the per-CTA partials in a fixed order (a ticket instead of
+  // a grid barrier: nobody waits): loss_terms = {sum row terms, sum col terms, sum dZ*Z, this rank's share}
+  __shared__ unsigned int ticket;
+  if (t == 0) {
+    __threadfence();
+    ticket = atomicAdd(p.barrier + 1, 1u);
+  }
+  __syncthreads();
+  if (ticket != gridDim.x - 1) return;
+  __threadfence();
   __shared__ float sh[3][kThreads];
   float a = 0.f, b = 0.f, c = 0.f;
   if (p.row_sum) {
@@ -412,21 +419,27 @@ extern "C" size_t rz_mpnce_partials_scratch_floats(int n_total, int b_local) {
 }
 
 extern "C" size_t rz_mpnce_finish_scratch_floats(int n_total, int b_local, int b_global) {
-  return (size_t)(2LL * n_total + 3LL * ((b_local + 3) / 4 * 4) + 2LL * b_global + 4);
+  (void)b_local;
+  return (size_t)(2LL * n_total + 2LL * b_global + 4);
 }
 
-extern "C" int rz_mpnce_partials(const float* z, long long ldz, int n_total, int b_local,
+extern "C" int rz_mpnce_partials(const float* z, long long ldz, int n_total, int b_local, int b_global,
                                  const long long* group_map, int col0, float inv_tau,
-                                 const float* log_tau, float* rowsum, float* pos, float* colneg,
-                                 float* colpos, float* scratch1, void* stream) {
-  if (!z || !group_map || !rowsum || !pos || !colneg || !colpos || !scratch1) return RZ_ERR_INVALID;
-  if (n_total <= 0 || b_local <= 0 || ldz < b_local) return RZ_ERR_INVALID;
+                                 const float* log_tau, float eps, int col_sum, float* rowsum, float* pos,
+                                 float* colstate, float* scratch1, void* stream) {
+  if (!z || !group_map || !rowsum || !pos || !colstate || !scratch1) return RZ_ERR_INVALID;
+  if (n_total <= 0 || b_local <= 0 || ldz < b_local || b_global < b_local) return RZ_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(colstate) % 16 != 0) return RZ_ERR_ALIGNMENT;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int chunks = (n_total + kRowChunk - 1) / kRowChunk;
   PartialsParams p;
   p.z = z; p.ldz = ldz; p.n_total = n_total; p.b_local = b_local; p.group_map = group_map;
   p.col0 = col0; p.inv_tau = inv_tau; p.log_tau = log_tau;
-  p.rowsum = rowsum; p.pos = pos; p.colneg = colneg; p.colpos = colpos;
+  const long long bl4 = (b_local + 3) / 4 * 4;            // rows of colstate are 16-byte aligned
+  p.rowsum = rowsum; p.pos = pos;
+  p.colneg = colstate; p.colpos = colstate + bl4; p.acol = colstate + 2 * bl4; p.apos = colstate + 3 * bl4;
+  p.lcol = colstate + 4 * bl4;
+  p.eps = eps; p.col_sum = col_sum; p.inv_2ncol = 0.5f / (float)(col_sum ? b_global : n_total);
   p.colpart = scratch1;
   p.barrier = reinterpret_cast<unsigned int*>(scratch1 + (long long)chunks * b_local);
   RZ_CUDA_OK(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned int), s));
@@ -443,10 +456,9 @@ extern "C" int rz_mpnce_partials(const float* z, long long ldz, int n_total, int
 extern "C" int rz_mpnce_finish(const float* z, long long ldz, int n_total, int b_local,
                                int b_global, const long long* group_map, int col0, float inv_tau,
                                const float* log_tau, float eps, int row_sum, int col_sum,
-                               const float* rowsum, const float* pos, const float* colneg,
-                               const float* colpos, float* scratch2, float* dz, float* loss_terms,
-                               void* stream) {
-  if (!z || !group_map || !rowsum || !pos || !colneg || !colpos || !scratch2 || !loss_terms)
+                               const float* rowsum, const float* pos, const float* colstate,
+                               float* scratch2, float* dz, float* loss_terms, void* stream) {
+  if (!z || !group_map || !rowsum || !pos || !colstate || !scratch2 || !loss_terms)
     return RZ_ERR_INVALID;
   if (n_total <= 0 || b_local <= 0 || b_global < b_local || col0 < 0 || col0 + b_local > b_global ||
       ldz < b_local)
@@ -456,12 +468,11 @@ extern "C" int rz_mpnce_finish(const float* z, long long ldz, int n_total, int b
   p.z = z; p.ldz = ldz; p.n_total = n_total; p.b_local = b_local; p.b_global = b_global;
   p.group_map = group_map; p.col0 = col0; p.inv_tau = inv_tau; p.eps = eps; p.log_tau = log_tau;
   p.row_sum = row_sum; p.col_sum = col_sum;
-  p.rowsum = rowsum; p.pos = pos; p.colneg = colneg; p.colpos = colpos;
+  const long long bl4 = (b_local + 3) / 4 * 4;
+  p.rowsum = rowsum; p.pos = pos;
+  p.colneg = colstate; p.colpos = colstate + bl4; p.acol = colstate + 2 * bl4; p.apos = colstate + 3 * bl4;
+  p.lcol = colstate + 4 * bl4;
   float* w = scratch2;
-  const int bl4 = (b_local + 3) / 4 * 4;
-  p.acol = w; w += bl4;
-  p.apos = w; w += bl4;
-  p.lcol = w; w += bl4;
   p.img_rs = w; w += b_global;
   p.img_ps = w; w += b_global;
   p.lrow = w; w += n_total;
@@ -470,9 +481,9 @@ extern "C" int rz_mpnce_finish(const float* z, long long ldz, int n_total, int b
   p.dz = dz; p.loss_terms = loss_terms;
   p.inv_2nrow = 0.5f / (float)(row_sum ? b_global : n_total);
   p.inv_2ncol = 0.5f / (float)(col_sum ? b_global : n_total);
-  RZ_CUDA_OK(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned int), s));
+  RZ_CUDA_OK(cudaMemsetAsync(p.barrier, 0, 2 * sizeof(unsigned int), s));     // [barrier counter, ticket]
   const bool vec = (reinterpret_cast<uintptr_t>(z) % 16 == 0) && (ldz % 4 == 0) &&
-                   (reinterpret_cast<uintptr_t>(scratch2) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(colstate) % 16 == 0) &&
                    (dz == nullptr || reinterpret_cast<uintptr_t>(dz) % 16 == 0);
   const int want = (n_total + kWarps - 1) / kWarps;
   const void* kern = vec ? (const void*)mpnce_finish_kernel<true> : (const void*)mpnce_finish_kernel<false>;

@@ -129,7 +129,7 @@ class _MpNce(torch.autograd.Function):
             tau = float(temperature)
             kw = {}
             inv_tau = 1.0 / tau
-        rs, ps, cn, cp = ops.mpnce_partials(z, group_map, 0, inv_tau, **kw)
+        rs, ps, cn, cp = ops.mpnce_partials(z, group_map, 0, inv_tau, eps=eps, col_sum=col_sum, b_global=b, **kw)
         terms, dz = ops.mpnce_finish(z, group_map, 0, b, inv_tau, rs, ps, cn, cp, eps=eps,
                                      row_sum=row_sum, col_sum=col_sum, want_dz=True, **kw)
         loss = terms[3].clone()

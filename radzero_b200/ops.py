@@ -404,12 +404,20 @@ def map_threshold_stats(scores: torch.Tensor, out_hw: Tuple[int, int], threshold
 
 
 # ----------------------------------------------------------------------------- K10
+def _colstate_rows(bl: int) -> int:
+    return (bl + 3) // 4 * 4
+
+
 @_guard
 def mpnce_partials(z: torch.Tensor, group_map: torch.Tensor, col0: int, inv_tau: float = 1.0, *,
-                   log_tau: Optional[torch.Tensor] = None, rowpos: Optional[torch.Tensor] = None):
-    """Launch 1 of MP-NCE on the local column block.  Returns (rowsum, pos, colneg, colpos).
+                   log_tau: Optional[torch.Tensor] = None, rowpos: Optional[torch.Tensor] = None,
+                   eps: float = 1e-8, col_sum: bool = False, b_global: Optional[int] = None):
+    """Launch 1 of MP-NCE on the local column block.  Returns (rowsum, pos, colneg, colpos); colneg / colpos
+    are the first two rows of the (5, b4) column-state block this launch writes (the backward's column
+    coefficients sit behind them and are picked up by ``mpnce_finish`` through the same buffer).
     ``log_tau`` (1-element fp32 CUDA tensor): temperature read on the device instead of ``inv_tau``.
-    ``rowpos`` (2, n) fp32: caller-owned buffer for rowsum / pos (one all-reduce message)."""
+    ``rowpos`` (2, n) fp32: caller-owned buffer for rowsum / pos (one all-reduce message).
+    ``eps`` / ``col_sum`` / ``b_global`` must be what ``mpnce_finish`` is given."""
     _need_cuda(z, group_map)
     assert z.dtype == torch.float32 and z.dim() == 2 and z.stride(1) == 1
     n, bl = z.shape
@@ -419,23 +427,27 @@ def mpnce_partials(z: torch.Tensor, group_map: torch.Tensor, col0: int, inv_tau:
     if rowpos is None:
         rowpos = torch.empty((2, n), dtype=torch.float32, device=dev)
     rowsum, pos = rowpos[0], rowpos[1]
-    col = torch.empty((2, bl), dtype=torch.float32, device=dev)
+    col = torch.empty((5, _colstate_rows(bl)), dtype=torch.float32, device=dev)
     lib = _lib.load()
     scratch = torch.empty(int(lib.rz_mpnce_partials_scratch_floats(n, bl)), dtype=torch.float32, device=dev)
-    rc = lib.rz_mpnce_partials(_p(z), z.stride(0), n, bl, _p(gm), int(col0), float(inv_tau),
-                               _p(_log_tau_ptr(log_tau)), _p(rowsum), _p(pos), _p(col[0]), _p(col[1]),
-                               _p(scratch), _stream())
+    rc = lib.rz_mpnce_partials(_p(z), z.stride(0), n, bl, int(b_global if b_global is not None else bl), _p(gm),
+                               int(col0), float(inv_tau), _p(_log_tau_ptr(log_tau)), float(eps), int(col_sum),
+                               _p(rowsum), _p(pos), _p(col), _p(scratch), _stream())
     _lib.check(rc, "rz_mpnce_partials")
-    return rowsum, pos, col[0], col[1]
+    return rowsum, pos, col[0, :bl], col[1, :bl]
 
 
 @_guard
 def mpnce_finish(z: torch.Tensor, group_map: torch.Tensor, col0: int, b_global: int, inv_tau: float,
                  rowsum, pos, colneg, colpos, *, eps: float = 1e-8, row_sum: bool = False,
                  col_sum: bool = False, want_dz: bool = True, log_tau: Optional[torch.Tensor] = None):
-    """Launch 2: returns (loss_terms[4], dz or None) for the local column block."""
+    """Launch 2: returns (loss_terms[4], dz or None) for the local column block.  ``colneg`` / ``colpos`` must
+    be the views ``mpnce_partials`` returned (rows 0 and 1 of its column-state block)."""
     _need_cuda(z, group_map, rowsum, pos, colneg, colpos)
     n, bl = z.shape
+    b4 = _colstate_rows(bl)
+    if colpos.data_ptr() != colneg.data_ptr() + 4 * b4 or colneg.dtype != torch.float32:
+        raise RzError("colneg / colpos must be the column-state views returned by mpnce_partials")
     gm = group_map if (group_map.dtype == torch.int64 and group_map.is_contiguous()) \
         else _contig(group_map.to(torch.int64))
     dev = z.device
@@ -448,7 +460,7 @@ def mpnce_finish(z: torch.Tensor, group_map: torch.Tensor, col0: int, b_global: 
                           device=dev)
     rc = lib.rz_mpnce_finish(_p(z), z.stride(0), n, bl, int(b_global), _p(gm), int(col0),
                              float(inv_tau), _p(_log_tau_ptr(log_tau)), float(eps), int(row_sum),
-                             int(col_sum), _p(rowsum), _p(pos), _p(colneg), _p(colpos), _p(scratch),
+                             int(col_sum), _p(rowsum), _p(pos), _p(colneg), _p(scratch),
                              _p(dz), _p(terms), _stream())
     _lib.check(rc, "rz_mpnce_finish")
     return terms, dz

@@ -189,7 +189,8 @@ class _ContrastiveStep(torch.autograd.Function):
             lt = lt.float() if z.is_cuda else lt
             rowpos = torch.empty((2, n_total), dtype=torch.float32 if z.is_cuda else z.dtype,
                                  device=z.device)      # rowsum | pos: ONE all-reduce message
-            rs, ps, cn, cp = K.mpnce_partials(z, gm, col0, log_tau=lt, rowpos=rowpos)
+            rs, ps, cn, cp = K.mpnce_partials(z, gm, col0, log_tau=lt, rowpos=rowpos, col_sum=cfg["col_sum"],
+                                              b_global=b_global)
             if distributed:
                 dist.all_reduce(rowpos)
             terms, dz = K.mpnce_finish(z, gm, col0, b_global, 1.0, rs, ps, cn, cp, log_tau=lt,

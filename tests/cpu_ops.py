@@ -47,7 +47,8 @@ def sim_fwd(k16, q16, tokens, scale, *, log_tau_scale=None, want_scores=False, d
                 lse=torch.logsumexp(s, -1), onorm=o.norm(dim=-1), pooled=o)
 
 
-def mpnce_partials(z, group_map, col0, inv_tau=1.0, *, log_tau=None, rowpos=None):
+def mpnce_partials(z, group_map, col0, inv_tau=1.0, *, log_tau=None, rowpos=None, eps=1e-8, col_sum=False,
+                   b_global=None):
     if log_tau is not None:
         inv_tau = float(torch.exp(-log_tau.double()))
     n, bl = z.shape

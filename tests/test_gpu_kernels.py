@@ -110,7 +110,7 @@ def test_upsample_constant_and_strided_input():
 # ------------------------------------------------------------------------------- MP-NCE
 def _mpnce_cuda(z, gm, tau, b_global=None, col0=0, row_sum=False, col_sum=False):
     b_global = b_global or z.shape[1]
-    rs, ps, cn, cp = ops.mpnce_partials(z, gm, col0, 1.0 / tau)
+    rs, ps, cn, cp = ops.mpnce_partials(z, gm, col0, 1.0 / tau, col_sum=col_sum, b_global=b_global)
     terms, dz = ops.mpnce_finish(z, gm, col0, b_global, 1.0 / tau, rs, ps, cn, cp,
                                  row_sum=row_sum, col_sum=col_sum)
     return terms, dz, (rs, ps, cn, cp)
@@ -152,7 +152,7 @@ def test_mpnce_vs_oracle_and_sharded(n, b):
     if W > 1:
         bl = b // W
         zc = z.to(DEV)
-        parts = [ops.mpnce_partials(zc[:, r * bl:(r + 1) * bl].contiguous(), gm.to(DEV), r * bl, 1 / 0.07)
+        parts = [ops.mpnce_partials(zc[:, r * bl:(r + 1) * bl].contiguous(), gm.to(DEV), r * bl, 1 / 0.07, b_global=b)
                  for r in range(W)]
         rowsum = sum(p[0] for p in parts)
         pos = sum(p[1] for p in parts)
