@@ -273,6 +273,14 @@ int rz_mpnce_finish(const float* z, long long ldz, int n_total, int b_local, int
                     const float* rowsum, const float* pos, const float* colstate,
                     float* scratch2, float* dz, float* loss_terms, void* stream);
 
+/* ---- group_map ---------------------------------------------------------------------------
+ * group_map[j] = first_image + (image of sentence j), from the per-image sentence counts
+ * (compute_text_features, losses.py:131-151: `global_index = i + local_rank * B_local`).
+ * counts_host is a HOST array; the counts reach the device as kernel parameters, so nothing queues on
+ * the copy engine.  out: int64 [sum(counts)].  counts must be in [0, 65535].
+ */
+int rz_group_map(const int* counts_host, int n_images, long long first_image, long long* out, void* stream);
+
 /* ---- K11: image preprocessing of the zero-shot evaluators ------------
  * Replaces, for `images` same-sized raw images resident in device memory, the host-side chain
  *   collate_fn (exp/cxr_pt/inference/dataset.py:31-51): cv2.normalize(img, None, 0, 255, NORM_MINMAX, CV_8U)

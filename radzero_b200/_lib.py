@@ -51,6 +51,7 @@ SIGNATURES: Dict[str, tuple] = {
     "rz_mpnce_partials": (_i, [_vp, _ll, _i, _i, _i, _vp, _i, _f, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp]),
     "rz_mpnce_finish": (_i, [_vp, _ll, _i, _i, _i, _vp, _i, _f, _vp, _f, _i, _i, _vp, _vp, _vp,
                              _vp, _vp, _vp, _vp]),
+    "rz_group_map": (_i, [_vp, _i, _ll, _vp, _vp]),
     "rz_preprocess_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i, _i, _i]),
     "rz_preprocess_images": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, C.c_double, _vp, _i, _vp,
                                   C.c_size_t, _vp]),

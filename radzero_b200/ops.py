@@ -629,3 +629,22 @@ def preprocess_images(raw: torch.Tensor, out_hw: Tuple[int, int] = (518, 518), *
                                       C.c_void_p(ws.data_ptr() + off), C.c_size_t(nbytes), _stream())
         _lib.check(rc, "rz_preprocess_images")
     return out
+
+
+# ----------------------------------------------------------------------------- group map
+def group_map_from_counts(counts, first_image: int, device) -> torch.Tensor:
+    """int64 (sum(counts),) tensor on ``device``: sentence j -> first_image + its image (losses.py:131-151),
+    written by a kernel that receives the counts as launch parameters (no host-to-device copy)."""
+    import numpy as np
+    c = np.ascontiguousarray(np.asarray(counts, dtype=np.int32))
+    total = int(c.sum())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RzError("radzero_b200 ops run on CUDA tensors only (there is no CPU fallback)")
+    out = torch.empty(total, dtype=torch.int64, device=device)
+    if total == 0:
+        return out
+    with torch.cuda.device(device):
+        rc = _lib.load().rz_group_map(c.ctypes.data_as(C.c_void_p), int(c.size), int(first_image), _p(out), _stream())
+    _lib.check(rc, "rz_group_map")
+    return out

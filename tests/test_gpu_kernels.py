@@ -236,3 +236,18 @@ def test_text_pool_matches_oracle(n, T, dtype):
     # no LayerNorm / no L2 variants
     _, q_plain = ops.text_pool(hidden, mask, None, None, l2=False, want_feats=False)
     assert (q_plain.double() - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_images,first", [(1, 0), (7, 14), (1024, 1024), (2500, 3)])
+def test_group_map_from_counts(n_images, first):
+    """rz_group_map: counts travel as launch parameters; result = np.repeat (losses.py:131-151)."""
+    import numpy as np
+    from radzero_b200 import ops
+    rng = np.random.default_rng(n_images)
+    counts = rng.integers(0, 12, size=n_images)
+    counts[rng.integers(0, n_images)] = 300
+    got = ops.group_map_from_counts(counts.tolist(), first, "cuda").cpu().numpy()
+    want = np.repeat(np.arange(first, first + n_images, dtype=np.int64), counts)
+    assert np.array_equal(got, want)
+    assert ops.group_map_from_counts([0, 0], 0, "cuda").numel() == 0
