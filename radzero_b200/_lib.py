@@ -86,7 +86,8 @@ def load(build_if_missing: bool = True):
             raise RzError(f"{LIB_PATH} is missing; run `python -m radzero_b200.build`")
         from . import build as _build
         _build.build()          # serialised across processes by a file lock (torchrun ranks)
-    lib = C.CDLL(LIB_PATH)
+    # RZ_B200_LIB: load another build of the same ABI (kernel-variant experiments under profiles/experiments/)
+    lib = C.CDLL(os.environ.get("RZ_B200_LIB") or LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError = ABI mismatch, fail loudly
         fn.restype = res

@@ -208,6 +208,11 @@ struct D2Params {
   float* dtau_part;              // [tiles * 4]
 };
 
+// Timing-only ablations of pass D2 (results WRONG; profiles/experiments/r2_d2_ablate.sh): bit 0 = no W2 bulk
+// store, bit 1 = no W1 bulk store, bit 2 = P~ boxes fetched once and reused, bit 3 = no staging stores at all
+#ifndef RZ_EXP_D2
+#define RZ_EXP_D2 0
+#endif
 template <int C>
 struct PassD2 : PolicyBase {
   static constexpr int kCluster = C;   // prompt tiles (2i, 2i+1) sweep the same tokens
@@ -275,7 +280,7 @@ struct PassD2 : PolicyBase {
     // this chunk's P~ box: 64 halves of this thread's row
     const uint32_t g = st.g;
     const uint32_t in = stg + (g & 1) * 4096u;
-    mbar_wait(bars + warp * 2 + (g & 1), (g >> 1) & 1);
+    if (!(RZ_EXP_D2 & 4) || g < 2) mbar_wait(bars + warp * 2 + (g & 1), (g >> 1) & 1);
     uint32_t pw[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -287,7 +292,7 @@ struct PassD2 : PolicyBase {
                  pw[31]);                               // Ctrl::sink sits right behind epi_bar[8]
     __syncwarp();
     // the buffer is free again: fetch the box two chunks ahead (possibly of the next tile)
-    if (lane == 0) {
+    if (lane == 0 && !(RZ_EXP_D2 & 4)) {
       if (c + 2 < nch) fetch(p, maps, tile, c + 2, warp, stg, bars, g + 2);
       else if (next_tile >= 0) fetch(p, maps, next_tile, c + 2 - nch, warp, stg, bars, g + 2);
     }
@@ -321,6 +326,10 @@ struct PassD2 : PolicyBase {
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
+        if (RZ_EXP_D2 & 8) {        // keep the arithmetic alive without the staging stores
+          if (o1[4 * j] == 0x12345678u && o2[4 * j + 3] == 0x9abcdef0u) u += 1.f;
+          continue;
+        }
         sts_v4(stg + 8192 + stage_off(lane, 4 * h + j), o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
         sts_v4(stg + 12288 + stage_off(lane, 4 * h + j), o2[4 * j], o2[4 * j + 1], o2[4 * j + 2], o2[4 * j + 3]);
       }
@@ -333,8 +342,8 @@ struct PassD2 : PolicyBase {
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_store_3d(&maps.c, stg + 8192, tok0 + c * 64, row0, b);       // W1 [B, N, Lp]
-      tma_store_3d(&maps.c2, stg + 12288, tok0 + c * 64, row0, b);     // W2 [B, N, Lp]
+      if (!(RZ_EXP_D2 & 2)) tma_store_3d(&maps.c, stg + 8192, tok0 + c * 64, row0, b);       // W1 [B, N, Lp]
+      if (!(RZ_EXP_D2 & 1)) tma_store_3d(&maps.c2, stg + 12288, tok0 + c * 64, row0, b);     // W2 [B, N, Lp]
       tma_store_commit();
     }
   }
@@ -536,6 +545,10 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
   // CTA pairs need an even number of prompt tiles, and pay off only while the streamed P~ / W1
   // operands are small enough for their re-reads to hit L2 (see rz_sim_fwd_large.cu)
   const int C = (m_tiles % 2 == 0 && pairs * Lp * sizeof(__half) <= ((size_t)2 << 30)) ? 2 : 1;
+  const char* exp_pair = getenv("RZ_EXP_PAIR");     // experiment: bit 0 = D2, bit 1 = Q as pairs regardless of size
+  const int xp = exp_pair ? atoi(exp_pair) : 0;
+  const int Cd = (m_tiles % 2 == 0 && (xp & 1)) ? 2 : C;
+  const int Cq = (m_tiles % 2 == 0 && (xp & 2)) ? 2 : C;
   const int d_tiles = B * m_tiles * n_tiles;
   float* scale = dtau_part + 4 * (size_t)d_tiles;          // [2]
   unsigned int* amax = reinterpret_cast<unsigned int*>(scale + 2);
@@ -556,7 +569,7 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
     if (reinterpret_cast<uintptr_t>(p_f16) & 15) return RZ_ERR_ALIGNMENT;
     Maps m = {};
     if (!rz::make_map_3d_sw128(&m.a, pooled_f16, B, N, kD, kD * 2, (uint64_t)N * kD * 2, kBM)) return RZ_ERR_CUDA;
-    if (!rz::make_map_3d_sw128(&m.b, k_f16, B, Lp, kD, kD * 2, (uint64_t)Lp * kD * 2, 256 / C)) return RZ_ERR_CUDA;
+    if (!rz::make_map_3d_sw128(&m.b, k_f16, B, Lp, kD, kD * 2, (uint64_t)Lp * kD * 2, 256 / Cd)) return RZ_ERR_CUDA;
     m.b2 = m.b;
     if (!rz::make_map_3d_sw128(&m.a2, p_f16, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, 32)) return RZ_ERR_CUDA;
     if (!rz::make_map_3d_sw128(&m.c, w1, B, N, Lp, (uint64_t)Lp * 2, (uint64_t)N * Lp * 2, 32)) return RZ_ERR_CUDA;
@@ -566,7 +579,7 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
     p.inv_tau = inv_tau; p.log_tau = log_tau; p.mref = mref; p.lsum = lsum; p.coef_a = coef_a;
     p.coef_r = coef_r; p.scale = scale; p.dtau_part = dtau_part;
     const int t2 = B * m_tiles * p.n_tiles;
-    int rc = C == 2 ? launch<PassD2<2>>(m, p, s) : launch<PassD2<1>>(m, p, s);
+    int rc = Cd == 2 ? launch<PassD2<2>>(m, p, s) : launch<PassD2<1>>(m, p, s);
     if (rc != RZ_OK) return rc;
     sum_partials_kernel<<<1, 1024, 0, s>>>(dtau_part, 4 * t2, dlog_tau);
     RZ_LAUNCH_OK();
@@ -598,7 +611,7 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
     m.a2 = m.a; m.b2 = m.b;
     QParams p;
     p.B = B; p.N = N; p.Lp = Lp; p.m_tiles = m_tiles; p.scale = scale; p.dq = dq;
-    int rc = C == 2 ? launch<PassQ<2>>(m, p, s) : launch<PassQ<1>>(m, p, s);
+    int rc = Cq == 2 ? launch<PassQ<2>>(m, p, s) : launch<PassQ<1>>(m, p, s);
     if (rc != RZ_OK) return rc;
   }
   // ---- pass K
