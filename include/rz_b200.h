@@ -159,13 +159,17 @@ int rz_sim_fwd_large(const void* k_f16, int n_images, int tokens, int tokens_pad
  *   dk    fp32 [n_images, tokens_padded, 768] = dL/dk (normalised tokens), overwritten
  *   dlog_tau fp32 [1] = dL/dlog(tau_attn) through the softmax scores
  *   inv_tau / log_tau as in rz_sim_fwd (log_tau: optional device scalar)
+ *   q_inv_norm  optional fp32 [n_text]: sim_op "dot" (losses.py:214-215, 226) -- q_f16 / k_f16 are the
+ *          rows WITHOUT L2 normalisation, inv_tau = 1/sqrt(768), q_inv_norm = 1/|q_n|.  dq then lacks
+ *          the radial term -(sum_b dZ Z) q_n / |q_n|^2, which the caller adds (radzero_b200/training.py);
+ *          dlog_tau is meaningless in this mode.
  * workspace: rz_sim_bwd_workspace_bytes(...) bytes, 256-byte aligned.
  */
 size_t rz_sim_bwd_workspace_bytes(int n_images, int n_text, int tokens_padded);
 int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int tokens_padded, const void* q_f16,
                int n_text, float inv_tau, const float* log_tau, const float* z, const float* dz,
                long long ldz, const float* lse, const float* onorm, const void* pooled_f16,
-               const void* p_f16, const float* mref, const float* lsum,
+               const void* p_f16, const float* mref, const float* lsum, const float* q_inv_norm,
                float* dq, float* dk, float* dlog_tau, void* workspace, size_t workspace_bytes,
                void* stream);
 

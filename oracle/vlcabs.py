@@ -87,7 +87,8 @@ def similarity_logit(queries: torch.Tensor, local_tokens: torch.Tensor, *,
                      ) -> Tuple[torch.Tensor, Optional[List[torch.Tensor]]]:
     """SimilarityLogit.forward, losses.py:192-240.
 
-    queries (N, D) [already LayerNorm-ed], local_tokens (B, L, D) [already LayerNorm-ed].
+    queries (N, D) [already LayerNorm-ed] -- or (B, N, D), one set per image: the reference's
+    ``repeat=False`` (losses.py:204-206) --, local_tokens (B, L, D) [already LayerNorm-ed].
     Returns (Z, [S] or None) with Z of shape (N, B).  With ``squeeze_quirk`` the
     reference's ``.squeeze()`` then ``.T`` (losses.py:229-233) is reproduced: B == 1 or
     N == 1 collapses Z to 1-d, B == N == 1 to 0-d.
@@ -106,12 +107,13 @@ def similarity_logit(queries: torch.Tensor, local_tokens: torch.Tensor, *,
     else:
         raise NotImplementedError(sim_op)          # losses.py:216-217
 
-    scores = torch.einsum("nd,bld->bnl", q, k) / denom          # losses.py:219-221
+    per_image = q.dim() == 3                                     # repeat=False, losses.py:204-206
+    scores = torch.einsum("bnd,bld->bnl" if per_image else "nd,bld->bnl", q, k) / denom   # losses.py:219-221
     probs = torch.softmax(scores, dim=-1)                        # losses.py:222
     pooled = torch.einsum("bnl,bld->bnd", probs, k)              # losses.py:224
     qn = l2_normalize_rows(q)                                    # losses.py:226
     on = l2_normalize_rows(pooled)                               # losses.py:227
-    z_bn = (qn.unsqueeze(0).expand(B, -1, -1) * on).sum(dim=-1)  # losses.py:229-231
+    z_bn = ((qn if per_image else qn.unsqueeze(0).expand(B, -1, -1)) * on).sum(dim=-1)    # losses.py:229-231
     if squeeze_quirk:
         z = z_bn.squeeze().T if z_bn.squeeze().dim() == 2 else z_bn.squeeze()
     else:
@@ -315,7 +317,7 @@ def zero_shot_labels(logits: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------- C4 helper
 def contrastive_step_reference(text: torch.Tensor, group_map: torch.Tensor,
                                vision_tokens: torch.Tensor, gamma: torch.Tensor,
-                               beta: torch.Tensor, log_tau: torch.Tensor):
+                               beta: torch.Tensor, log_tau: torch.Tensor, sim_op: str = "cos"):
     """Forward + backward of the contrastive step through autograd on the oracle.
 
     Returns (loss, dict of grads for text / vision_tokens / gamma / beta / log_tau).
@@ -327,7 +329,7 @@ def contrastive_step_reference(text: torch.Tensor, group_map: torch.Tensor,
     tn = layer_norm_rows(t, g, b)
     xn = layer_norm_rows(x, g, b)
     tau = torch.exp(lt)
-    z, _ = similarity_logit(tn, xn, temperature=tau, sim_op="cos", squeeze_quirk=False)
+    z, _ = similarity_logit(tn, xn, temperature=tau, sim_op=sim_op, squeeze_quirk=False)
     loss = multi_positive_nce_loss(z, group_map, temperature=tau)
     loss.backward()
     return loss.detach(), {

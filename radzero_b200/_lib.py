@@ -40,7 +40,7 @@ SIGNATURES: Dict[str, tuple] = {
     "rz_sim_fwd_large": (_i, [_vp, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _ll, _ll, _i, _vp, _ll, _ll,
                               _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, C.c_size_t, _vp]),
     "rz_sim_bwd_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
-    "rz_sim_bwd": (_i, [_vp, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp,
+    "rz_sim_bwd": (_i, [_vp, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                         _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "rz_prep_rows_bwd_blocks": (_i, [_ll]),
     "rz_prep_rows_bwd": (_i, [_vp, _i, _vp, _vp, _ll, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _f, _vp]),

@@ -26,6 +26,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 struct CoefParams {
   const float* g; const float* z; long long ldz;    // [N, ldz] (column = local image)
   const float* onorm;                               // [B, N]
+  const float* q_inv_norm;                          // [N] or null: sim_op "dot" (operands not L2-normalised)
   float* coef_a; float* coef_r;                     // [B, N]
   unsigned int* amax_bits;                          // max |a| as float bits
   int B, N;
@@ -37,9 +38,13 @@ __global__ void pair_coef_kernel(CoefParams p) {
   if (i < (long long)p.B * p.N) {
     const int b = (int)(i / p.N), n = (int)(i - (long long)b * p.N);
     const float on = fmaxf(p.onorm[i], RZ_L2_EPS);
-    const float a = p.g[(long long)n * p.ldz + b] / on;
+    // sim_op "dot": Z = <q/|q|, o/|o|> and s = c <q, k>.  With a' = a / |q| and r' = r |q| the cosine
+    // formulas hold unchanged (1/tau' = c |q| per prompt, folded into r'); the radial term of dq is
+    // added by the caller.
+    const float qin = p.q_inv_norm != nullptr ? p.q_inv_norm[n] : 1.0f;
+    const float a = p.g[(long long)n * p.ldz + b] / on * qin;
     p.coef_a[i] = a;
-    p.coef_r[i] = p.z[(long long)n * p.ldz + b] / on;
+    p.coef_r[i] = p.z[(long long)n * p.ldz + b] / (on * qin);
     a_abs = fabsf(a);
   }
   a_abs = rz::warp_max(a_abs);
@@ -520,7 +525,7 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
                           const void* q_f16, int n_text, float inv_tau, const float* log_tau,
                           const float* z, const float* dz, long long ldz, const float* lse,
                           const float* onorm, const void* pooled_f16, const void* p_f16,
-                          const float* mref, const float* lsum, float* dq, float* dk,
+                          const float* mref, const float* lsum, const float* q_inv_norm, float* dq, float* dk,
                           float* dlog_tau, void* workspace, size_t workspace_bytes, void* stream) {
   if (!k_f16 || !q_f16 || !z || !dz || !onorm || !pooled_f16 || !dq || !dk || !dlog_tau ||
       !workspace)
@@ -555,7 +560,7 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
 
   RZ_CUDA_OK(cudaMemsetAsync(amax, 0, sizeof(unsigned int), s));
   CoefParams cp;
-  cp.g = dz; cp.z = z; cp.ldz = ldz; cp.onorm = onorm; cp.coef_a = coef_a; cp.coef_r = coef_r;
+  cp.g = dz; cp.z = z; cp.ldz = ldz; cp.onorm = onorm; cp.q_inv_norm = q_inv_norm; cp.coef_a = coef_a; cp.coef_r = coef_r;
   cp.amax_bits = amax; cp.B = B; cp.N = N;
   pair_coef_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, s>>>(cp);
   RZ_LAUNCH_OK();

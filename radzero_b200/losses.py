@@ -64,9 +64,7 @@ class SimilarityLogit(nn.Module):
     def forward(self, queries: torch.Tensor, local_tokens: torch.Tensor,
                 need_attn_weights: bool = False, repeat: bool = True, **kwargs):
         if not repeat:
-            # per-image queries (B, N, D) are never used by the radzero configuration
             assert queries.dim() == 3
-            raise NotImplementedError("repeat=False (per-image queries) is not on the VL-CABS path")
         if self.sim_op == "cos":
             temperature = kwargs.get("temperature")
             assert temperature is not None
@@ -77,7 +75,18 @@ class SimilarityLogit(nn.Module):
             l2 = False
         else:
             raise NotImplementedError
-        if torch.is_grad_enabled() and (queries.requires_grad or local_tokens.requires_grad):
+        if not repeat:
+            # per-image queries (B, N, D), losses.py:204-206: no caller in the reference (radzero.yaml always
+            # shares the prompts), so one launch per image of the shared-prompt kernel; inference only
+            if torch.is_grad_enabled() and (queries.requires_grad or local_tokens.requires_grad):
+                raise NotImplementedError("repeat=False (per-image queries) has no backward on the VL-CABS path")
+            if queries.shape[0] != local_tokens.shape[0]:
+                raise RzError("repeat=False needs one (N, D) query set per image")
+            per = [_similarity_forward(queries[b], local_tokens[b:b + 1], None, None, scale, l2,
+                                       need_attn_weights, drop_cls=False) for b in range(queries.shape[0])]
+            z = torch.cat([zb for zb, _ in per], dim=1)
+            scores = torch.cat([sb for _, sb in per], dim=0) if need_attn_weights else None
+        elif torch.is_grad_enabled() and (queries.requires_grad or local_tokens.requires_grad):
             from .training import similarity_logit_autograd
             z, scores = similarity_logit_autograd(queries, local_tokens, scale, l2, need_attn_weights)
         else:

@@ -249,10 +249,13 @@ def padded_tokens_bwd(tokens: int) -> int:
 def sim_bwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, inv_tau: float, z: torch.Tensor,
             dz: torch.Tensor, lse: Optional[torch.Tensor], onorm: torch.Tensor, pooled: torch.Tensor, *,
             log_tau: Optional[torch.Tensor] = None, p: Optional[torch.Tensor] = None,
-            mref: Optional[torch.Tensor] = None, lsum: Optional[torch.Tensor] = None):
+            mref: Optional[torch.Tensor] = None, lsum: Optional[torch.Tensor] = None,
+            q_inv_norm: Optional[torch.Tensor] = None):
     """Closed-form backward of the fused similarity.  Returns (dq (N,768), dk (B,Lp,768), dlog_tau (1,)).
-    ``p`` / ``mref`` / ``lsum`` (kept by the large-N forward) select the single-GEMM coefficient pass."""
-    _need_cuda(k_f16, q_f16, z, dz, lse, onorm, pooled)
+    ``p`` / ``mref`` / ``lsum`` (kept by the large-N forward) select the single-GEMM coefficient pass.
+    ``q_inv_norm`` (N,) = 1/|q_n|: sim_op "dot" -- operands without L2 normalisation, ``inv_tau`` = 1/sqrt(768);
+    the radial term of dq is added here."""
+    _need_cuda(k_f16, q_f16, z, dz, lse, onorm, pooled, q_inv_norm)
     B, Lp, _ = k_f16.shape
     N = q_f16.shape[0]
     if Lp % BWD_TOKEN_TILE:
@@ -266,11 +269,16 @@ def sim_bwd(k_f16: torch.Tensor, q_f16: torch.Tensor, tokens: int, inv_tau: floa
     dq = torch.empty((N, HIDDEN), dtype=torch.float32, device=dev)
     dk = torch.empty((B, Lp, HIDDEN), dtype=torch.float32, device=dev)
     dlt = torch.empty(1, dtype=torch.float32, device=dev)
+    qin = _contig(q_inv_norm.float()) if q_inv_norm is not None else None
     rc = lib.rz_sim_bwd(_p(k_f16), B, int(tokens), Lp, _p(q_f16), N, float(inv_tau),
                         _p(_log_tau_ptr(log_tau)), _p(z), _p(dz), z.stride(0), _p(lse), _p(onorm),
-                        _p(pooled), _p(p), _p(mref), _p(lsum), _p(dq), _p(dk), _p(dlt), _p(ws),
+                        _p(pooled), _p(p), _p(mref), _p(lsum), _p(qin), _p(dq), _p(dk), _p(dlt), _p(ws),
                         C.c_size_t(nbytes), _stream())
     _lib.check(rc, "rz_sim_bwd")
+    if qin is not None:
+        # Z = <q/|q|, .>: the derivative of the query normalisation (losses.py:226), a rank-one term per prompt
+        radial = (dz[:, :B] * z[:, :B]).sum(dim=1) * qin * qin
+        dq.addcmul_(q_f16.float(), radial.unsqueeze(1), value=-1.0)
     return dq, dk, dlt
 
 

@@ -26,6 +26,8 @@ from __future__ import annotations
 
 from typing import List, Optional
 
+import math
+
 import torch
 import torch.distributed as dist
 
@@ -145,20 +147,32 @@ def _scatter_dq(dq: torch.Tensor, sizes: List[int], rank: int) -> torch.Tensor:
     return out[: sizes[rank]]
 
 
+_DOT_SCALE = 1.0 / math.sqrt(ops.HIDDEN)          # losses.py:215
+
+
+def _inv_norms(q16: torch.Tensor) -> torch.Tensor:
+    """1/|q_n| of the fp16 rows the kernels multiply with (F.normalize of the queries, losses.py:226)."""
+    return 1.0 / q16.float().norm(dim=-1).clamp_min(1e-12)
+
+
 class _ContrastiveStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, text, tokens, gamma, beta, log_tau, attn_log_tau, group_map, cfg):
         distributed = cfg["distributed"]
         K = cfg.get("ops", ops)                   # kernels; tests of the host logic inject a stand-in
-        if cfg["sim_op"] != "cos":
-            raise NotImplementedError("the fused training step implements sim_op='cos' (radzero.yaml:44)")
+        if cfg["sim_op"] not in ("cos", "dot"):
+            raise NotImplementedError(cfg["sim_op"])           # losses.py:216-217
+        # sim_op "dot" (the constructor default, losses.py:45, 214-215): rows are LayerNorm-ed but not
+        # L2-normalised, scores are divided by sqrt(768) and no attention temperature exists
+        dot = cfg["sim_op"] == "dot"
+        l2kw = dict(l2=False) if dot else {}
         world = dist.get_world_size() if distributed else 1
         rank = dist.get_rank() if distributed else 0
         B, L, _ = tokens.shape
         Lp = K.padded_tokens_bwd(L)
         g = gamma.detach() if gamma is not None else None
         b = beta.detach() if beta is not None else None
-        q16_local, _, _ = K.prep_rows(text.detach(), g, b)
+        q16_local, _, _ = K.prep_rows(text.detach(), g, b, **l2kw)
         n_local = q16_local.shape[0]
         sizes = None
         unpack = None
@@ -167,16 +181,20 @@ class _ContrastiveStep(torch.autograd.Function):
             sizes = comm.sizes(n_local, q16_local.device)
             # the text all-gather runs on a side stream while this stream normalises the tokens
             unpack = _gather_text(q16_local, group_map, sizes, comm.side_stream(q16_local.device))
-        k16, _, _ = K.prep_rows(tokens.detach(), g, b, rows_per_group=L, rows_per_group_padded=Lp)
+        k16, _, _ = K.prep_rows(tokens.detach(), g, b, rows_per_group=L, rows_per_group_padded=Lp, **l2kw)
         k16 = k16.view(B, Lp, ops.HIDDEN)
         if distributed:
             q16, gm = unpack()
             row0 = sum(sizes[:rank])
         else:
             q16, gm, row0 = q16_local, group_map, 0
-        a_lt = attn_log_tau if attn_log_tau is not None else log_tau
-        fwd = K.sim_fwd(k16, q16, L, 1.0, log_tau_scale=a_lt.detach(), want_scores=cfg["need_scores"],
-                        drop_cls=False, want_stats=True, want_pooled=True)
+        if dot:
+            fwd = K.sim_fwd(k16, q16, L, _DOT_SCALE, q_inv_norm=_inv_norms(q16), want_scores=cfg["need_scores"],
+                            drop_cls=False, want_stats=True, want_pooled=True)
+        else:
+            a_lt = attn_log_tau if attn_log_tau is not None else log_tau
+            fwd = K.sim_fwd(k16, q16, L, 1.0, log_tau_scale=a_lt.detach(), want_scores=cfg["need_scores"],
+                            drop_cls=False, want_stats=True, want_pooled=True)
         z = fwd["z"]                                   # (N_total, B_local)
         n_total = z.shape[0]
         b_global = B * world
@@ -231,9 +249,16 @@ class _ContrastiveStep(torch.autograd.Function):
         ddp_scale = float(world) if (distributed and ctx.cfg["ddp_compatible"]) else 1.0
         gl = g_loss.reshape(()).float() * ddp_scale
         dzs = dz * gl
-        a_lt = attn_log_tau if has_attn else log_tau
-        dq, dk, dlt_attn = K.sim_bwd(k16, q16, L, 1.0, z, dzs, lse, onorm, pooled, log_tau=a_lt.detach(),
-                                     p=p_un, mref=mref, lsum=lsum)
+        dot = ctx.cfg["sim_op"] == "dot"
+        l2kw = dict(l2=False) if dot else {}
+        if dot:
+            dq, dk, _ = K.sim_bwd(k16, q16, L, _DOT_SCALE, z, dzs, lse, onorm, pooled, p=p_un, mref=mref,
+                                  lsum=lsum, q_inv_norm=_inv_norms(q16))
+            dlt_attn = None                        # no temperature inside the attention (losses.py:214-215)
+        else:
+            a_lt = attn_log_tau if has_attn else log_tau
+            dq, dk, dlt_attn = K.sim_bwd(k16, q16, L, 1.0, z, dzs, lse, onorm, pooled, log_tau=a_lt.detach(),
+                                         p=p_un, mref=mref, lsum=lsum)
         if distributed:
             dq_local = _scatter_dq(dq, sizes, rank).contiguous()
         else:
@@ -242,13 +267,15 @@ class _ContrastiveStep(torch.autograd.Function):
         g = gamma.detach() if gamma is not None else None
         b = beta.detach() if beta is not None else None
         dx_tok, dgamma, dbeta = K.prep_rows_bwd(tokens.detach(), g, b, dk, rows_per_group=L,
-                                                rows_per_group_padded=Lp, native_dx=True)
+                                                rows_per_group_padded=Lp, native_dx=True, **l2kw)
         dx_txt, dgamma, dbeta = K.prep_rows_bwd(text.detach(), g, b, dq_local, dgamma=dgamma,
-                                                dbeta=dbeta, accumulate=True, native_dx=True)
+                                                dbeta=dbeta, accumulate=True, native_dx=True, **l2kw)
         # d/dlog(tau): the loss temperature through exp(Z/tau) (= -sum dZ*Z) and, when the
         # attention shares it (attn_temperature: null, radzero.yaml:43), the softmax scores
         d_loss_lt = -(terms[2] * gl).reshape(1)
-        if has_attn:
+        if dlt_attn is None:
+            d_lt, d_alt = d_loss_lt, None
+        elif has_attn:
             d_lt, d_alt = d_loss_lt, dlt_attn.reshape(1)
         else:
             d_lt, d_alt = d_loss_lt + dlt_attn.reshape(1), None
@@ -256,6 +283,8 @@ class _ContrastiveStep(torch.autograd.Function):
         dtxt = dx_txt.to(text.dtype)
         dgm = dgamma.to(gamma.dtype) if gamma is not None else None
         dbt = dbeta.to(beta.dtype) if beta is not None else None
+        if d_alt is None and has_attn:
+            d_alt = torch.zeros_like(attn_log_tau)
         return dtxt, dtok, dgm, dbt, d_lt.to(log_tau.dtype), d_alt, None, None
 
 
@@ -278,20 +307,20 @@ def contrastive_step(loss_fn, text: torch.Tensor, group_map: torch.Tensor, token
 
 
 class _SimilarityLogitFn(torch.autograd.Function):
-    """SimilarityLogit alone under autograd (inputs already LayerNorm-ed, sim_op 'cos')."""
+    """SimilarityLogit alone under autograd (inputs already LayerNorm-ed; sim_op 'cos' = l2, 'dot' = not)."""
 
     @staticmethod
-    def forward(ctx, queries, tokens, scale, need_scores):
+    def forward(ctx, queries, tokens, scale, need_scores, l2):
         B, L, _ = tokens.shape
         Lp = ops.padded_tokens_bwd(L)
-        k16, _, _ = ops.prep_rows(tokens.detach(), None, None, rows_per_group=L, rows_per_group_padded=Lp)
+        k16, _, _ = ops.prep_rows(tokens.detach(), None, None, rows_per_group=L, rows_per_group_padded=Lp, l2=l2)
         k16 = k16.view(B, Lp, ops.HIDDEN)
-        q16, _, _ = ops.prep_rows(queries.detach(), None, None)
+        q16, _, _ = ops.prep_rows(queries.detach(), None, None, l2=l2)
         fwd = ops.sim_fwd(k16, q16, L, scale, want_scores=need_scores, drop_cls=False, want_stats=True,
-                          want_pooled=True)
+                          want_pooled=True, q_inv_norm=None if l2 else _inv_norms(q16))
         ctx.save_for_backward(queries, tokens, k16, q16, fwd["z"], fwd["lse"], fwd["onorm"], fwd["pooled"],
                               fwd.get("p"), fwd.get("mref"), fwd.get("lsum"))
-        ctx.meta = (B, L, Lp, scale)
+        ctx.meta = (B, L, Lp, scale, l2)
         scores = fwd["scores"] if fwd["scores"] is not None else fwd["z"].new_empty(0)
         ctx.mark_non_differentiable(scores)
         return fwd["z"], scores
@@ -299,17 +328,19 @@ class _SimilarityLogitFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gz, _gs):
         queries, tokens, k16, q16, z, lse, onorm, pooled, p_un, mref, lsum = ctx.saved_tensors
-        B, L, Lp, scale = ctx.meta
-        dq, dk, _ = ops.sim_bwd(k16, q16, L, scale, z, gz.float().contiguous(), lse, onorm, pooled,
-                                p=p_un, mref=mref, lsum=lsum)
+        B, L, Lp, scale, l2 = ctx.meta
+        gz = gz.float()
+        if gz.stride() != z.stride():
+            gz = gz.contiguous()
+            z = z.contiguous()
+        dq, dk, _ = ops.sim_bwd(k16, q16, L, scale, z, gz, lse, onorm, pooled, p=p_un, mref=mref, lsum=lsum,
+                                q_inv_norm=None if l2 else _inv_norms(q16))
         dxt, _, _ = ops.prep_rows_bwd(tokens.detach(), None, None, dk, rows_per_group=L,
-                                      rows_per_group_padded=Lp)
-        dxq, _, _ = ops.prep_rows_bwd(queries.detach(), None, None, dq)
-        return dxq.to(queries.dtype), dxt.view(B, L, ops.HIDDEN).to(tokens.dtype), None, None
+                                      rows_per_group_padded=Lp, l2=l2)
+        dxq, _, _ = ops.prep_rows_bwd(queries.detach(), None, None, dq, l2=l2)
+        return dxq.to(queries.dtype), dxt.view(B, L, ops.HIDDEN).to(tokens.dtype), None, None, None
 
 
 def similarity_logit_autograd(queries, tokens, scale: float, l2: bool, need_scores: bool):
-    if not l2:
-        raise NotImplementedError("training through sim_op='dot' is not implemented on the B200 path")
-    z, scores = _SimilarityLogitFn.apply(queries, tokens, scale, need_scores)
+    z, scores = _SimilarityLogitFn.apply(queries, tokens, scale, need_scores, l2)
     return z, (scores if need_scores else None)

@@ -122,6 +122,25 @@ def test_sim_fwd_golden(name):
     assert torch.equal(logits.argmax(1), l_ref.argmax(1))
 
 
+@pytest.mark.parametrize("sim_op", ["cos", "dot"])
+@pytest.mark.parametrize("B,N", [(3, 5), (1, 4), (2, 1), (2, 20)])
+def test_per_image_queries(sim_op, B, N):
+    """SimilarityLogit(..., repeat=False): queries (B, N, D) (losses.py:204-206), incl. the squeeze quirk."""
+    from radzero_b200 import losses
+    g = torch.Generator().manual_seed(40 + B * 7 + N)
+    q = torch.randn(B, N, 768, generator=g)
+    tok = torch.randn(B, 90, 768, generator=g)
+    sl = losses.SimilarityLogit(sim_op)
+    with torch.no_grad():
+        z, sc = sl(q.to(DEV), tok.to(DEV), need_attn_weights=True, repeat=False, temperature=torch.tensor(TAU))
+    want, ws = oracle.similarity_logit(q.double(), tok.double(), sim_op=sim_op, temperature=TAU, need_scores=True)
+    assert tuple(z.shape) == tuple(want.shape)
+    assert (z.cpu().double() - want).abs().max() < 3e-4
+    assert (sc[0].cpu().double() - ws[0]).abs().max() < (2e-3 if sim_op == "cos" else 2e-2)
+    with pytest.raises(NotImplementedError):
+        sl(q.to(DEV).requires_grad_(True), tok.to(DEV), repeat=False, temperature=torch.tensor(TAU))
+
+
 def test_sim_fwd_dot_mode():
     """sim_op='dot' (the RadZeroLoss constructor default, losses.py:45, 214-215)."""
     B, N, L = 2, 7, 150

@@ -90,8 +90,8 @@ def test_sim_bwd_vs_autograd(B, N, L, use_p):
 
 
 # ------------------------------------------------------------------------------ the fused step
-def _loss_fn(gamma, beta, log_tau):
-    fn = losses.RadZeroLoss(sim_op="cos").to(DEV)
+def _loss_fn(gamma, beta, log_tau, sim_op="cos"):
+    fn = losses.RadZeroLoss(sim_op=sim_op).to(DEV)
     with torch.no_grad():
         fn.layer_norm.weight.copy_(gamma)
         fn.layer_norm.bias.copy_(beta)
@@ -119,6 +119,48 @@ def test_contrastive_step_vs_oracle(B, counts, L):
     assert _rel(fn.layer_norm.weight.grad, grads["gamma"]) < 1e-2
     assert _rel(fn.layer_norm.bias.grad, grads["beta"]) < 1e-2
     assert abs(fn.loss_temperature.grad.item() - grads["log_tau"].item()) < 1e-2 * abs(grads["log_tau"].item())
+
+
+@pytest.mark.parametrize("B,counts,L", [(3, [2, 1, 3], 50), (4, [40, 35, 50, 25], 300), (2, [70, 90], 257)])
+def test_contrastive_step_dot_vs_oracle(B, counts, L):
+    """sim_op='dot' (the RadZeroLoss constructor default, losses.py:45, 214-215) through the same kernels:
+    operands without L2 normalisation, per-prompt 1/|q| folded into the pair coefficients."""
+    tok, text, gamma, beta, log_tau = synthetic.make_inputs(B, sum(counts), tokens_per_image=L, seed=77)
+    fn = _loss_fn(gamma, beta, log_tau, sim_op="dot")
+    t = text.to(DEV).requires_grad_(True)
+    x = tok.to(DEV).requires_grad_(True)
+    feats = split(t, counts)
+    out = fn(list(range(B)), x, lambda i: {"text_features_wo_l2_norm": feats[i]})
+    loss = out["losses"]["loss"]
+    loss.backward()
+    want, grads = oracle.contrastive_step_reference(text.double(), oracle.build_group_map(counts), tok.double(),
+                                                    gamma.double(), beta.double(), log_tau.double(), sim_op="dot")
+    assert abs(loss.item() - want.item()) < 1e-3 * abs(want.item())
+    assert (out["t2i_logits"].cpu().double() - grads["t2i_logits"]).abs().max() < 3e-4
+    assert _rel(t.grad, grads["text"]) < 1e-2
+    assert _rel(x.grad, grads["vision_tokens"]) < 1e-2
+    assert _rel(fn.layer_norm.weight.grad, grads["gamma"]) < 1e-2
+    assert _rel(fn.layer_norm.bias.grad, grads["beta"]) < 1e-2
+    assert abs(fn.loss_temperature.grad.item() - grads["log_tau"].item()) < 1e-2 * abs(grads["log_tau"].item())
+
+
+def test_similarity_logit_autograd_dot():
+    B, N, L = 2, 6, 90
+    tok, text, gamma, beta, _ = synthetic.make_inputs(B, N, tokens_per_image=L, seed=4)
+    tn = oracle.layer_norm_rows(text, gamma, beta)
+    xn = oracle.layer_norm_rows(tok, gamma, beta)
+    q = tn.to(DEV).requires_grad_(True)
+    k = xn.to(DEV).requires_grad_(True)
+    z, _ = losses.SimilarityLogit("dot")(q, k)
+    w = torch.randn(N, B, generator=torch.Generator().manual_seed(1))
+    (z * w.to(DEV)).sum().backward()
+    qd = tn.double().requires_grad_(True)
+    kd = xn.double().requires_grad_(True)
+    zd, _ = oracle.similarity_logit(qd, kd, sim_op="dot", squeeze_quirk=False)
+    (zd * w.double()).sum().backward()
+    assert (z.detach().cpu().double() - zd.detach()).abs().max() < 3e-4
+    assert _rel(q.grad, qd.grad) < 1e-2
+    assert _rel(k.grad, kd.grad) < 1e-2
 
 
 def test_contrastive_step_golden_full():

@@ -63,6 +63,20 @@ def test_squeeze_quirk_shapes(reference_losses, B, N):
     assert torch.allclose(r, o, atol=2e-6)
 
 
+@pytest.mark.parametrize("sim_op", ["cos", "dot"])
+@pytest.mark.parametrize("B,N", [(3, 4), (1, 5), (4, 1)])
+def test_per_image_queries(reference_losses, sim_op, B, N):
+    """repeat=False (losses.py:204-206): queries (B, N, D), one prompt set per image."""
+    g = torch.Generator().manual_seed(B * 10 + N)
+    q = torch.randn(B, N, 768, generator=g, dtype=torch.float64)
+    tok = torch.randn(B, 37, 768, generator=g, dtype=torch.float64)
+    sl = reference_losses.SimilarityLogit(sim_op)
+    r, rs = sl(q, tok, need_attn_weights=True, repeat=False, temperature=torch.tensor(0.07, dtype=torch.float64))
+    o, os_ = oracle.similarity_logit(q, tok, sim_op=sim_op, temperature=0.07, need_scores=True)
+    assert tuple(r.shape) == tuple(o.shape)
+    assert (r - o).abs().max() < 1e-10 and (rs[0] - os_[0]).abs().max() < 1e-8
+
+
 def test_dot_branch(reference_losses):
     tok, text, gamma, beta, log_tau = synthetic.make_inputs(2, 3, tokens_per_image=40, seed=5,
                                                             dtype=torch.float64)
@@ -83,18 +97,19 @@ def test_mpnce_variants(reference_losses, row_sum, col_sum):
     assert abs(r.item() - o.item()) < 2e-6 * max(1.0, abs(r.item()))
 
 
-def test_contrastive_grads_match_reference(reference_losses):
+@pytest.mark.parametrize("sim_op", ["cos", "dot"])
+def test_contrastive_grads_match_reference(reference_losses, sim_op):
     B, counts = 3, [2, 1, 3]
     tok, text, gamma, beta, log_tau = synthetic.make_inputs(B, 6, tokens_per_image=50, seed=9,
                                                             dtype=torch.float64)
     log_tau = log_tau.double()
-    ref = make_reference_loss(reference_losses, gamma, beta, log_tau)
+    ref = make_reference_loss(reference_losses, gamma, beta, log_tau, sim_op=sim_op)
     t = text.clone().requires_grad_(True)
     x = tok.clone().requires_grad_(True)
     r = ref(list(range(B)), x, text_callback(_split(t, counts)), ddp_gather=False)
     r["losses"]["loss"].backward()
     loss, grads = oracle.contrastive_step_reference(
-        text, oracle.build_group_map(counts), tok, gamma, beta, log_tau)
+        text, oracle.build_group_map(counts), tok, gamma, beta, log_tau, sim_op=sim_op)
     assert abs(loss.item() - r["losses"]["loss"].item()) < 1e-10
     assert (grads["text"] - t.grad).abs().max() < 1e-10
     assert (grads["vision_tokens"] - x.grad).abs().max() < 1e-10
