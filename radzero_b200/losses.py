@@ -301,7 +301,7 @@ class RadZeroLoss(nn.Module):
                 feat = feat[:, self.hidden_dim:]
             if not want_group_map:
                 return feat, None
-            if feat.is_cuda and max(counts) <= 65535:
+            if feat.is_cuda and max(counts, default=0) <= 65535:
                 # written on the device from launch parameters: no copy-engine traffic on the compute stream
                 return feat, ops.group_map_from_counts(counts, rank * b_local, feat.device)
             group = torch.from_numpy(np.repeat(np.arange(rank * b_local, (rank + 1) * b_local, dtype=np.int64),
