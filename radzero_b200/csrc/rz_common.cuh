@@ -257,6 +257,78 @@ __device__ __forceinline__ RowStats ln_l2_row_packed(float (&x)[24], const float
   return st;
 }
 
+// TWO rows per warp with the lane's gamma / beta resident in registers as packed pairs (g2 / b2: the pairs
+// of load_lane_pairs): the operations and their order per row are those of ln_l2_row_packed (bit-identical
+// results); the two rows' dependent chains (three shuffle reductions each) are interleaved explicitly, and
+// the per-row parameter loads are gone.
+__device__ __forceinline__ void load_lane_pairs(const float* __restrict__ p, int lane, float fill, P2 (&r)[12]) {
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    float4 v = make_float4(fill, fill, fill, fill);
+    if (p != nullptr) v = *reinterpret_cast<const float4*>(p + 4 * (lane + 32 * j));
+    r[2 * j] = p2(v.x, v.y);
+    r[2 * j + 1] = p2(v.z, v.w);
+  }
+}
+__device__ __forceinline__ void warp_sum2(float& a, float& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+}
+__device__ __forceinline__ void ln_l2_rows2_packed(float (&x0)[24], float (&x1)[24], const P2 (&g2)[12],
+                                                   const P2 (&b2)[12], bool do_ln, float eps_ln, float eps_l2,
+                                                   bool do_l2) {
+  P2 u[12], v[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { u[i] = p2(x0[2 * i], x0[2 * i + 1]); v[i] = p2(x1[2 * i], x1[2 * i + 1]); }
+  if (do_ln) {
+    P2 su = u[0], sv = v[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) { su = p2_add(su, u[i]); sv = p2_add(sv, v[i]); }
+    float a0, a1, c0, c1;
+    p2_unpack(su, a0, a1);
+    p2_unpack(sv, c0, c1);
+    float mu0 = a0 + a1, mu1 = c0 + c1;
+    warp_sum2(mu0, mu1);
+    mu0 *= (1.0f / RZ_HIDDEN);
+    mu1 *= (1.0f / RZ_HIDDEN);
+    const P2 m0 = p2(mu0), m1 = p2(mu1);
+    P2 qu = p2(0.f), qv = p2(0.f);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      u[i] = p2_sub(u[i], m0); qu = p2_fma(u[i], u[i], qu);
+      v[i] = p2_sub(v[i], m1); qv = p2_fma(v[i], v[i], qv);
+    }
+    p2_unpack(qu, a0, a1);
+    p2_unpack(qv, c0, c1);
+    float var0 = a0 + a1, var1 = c0 + c1;
+    warp_sum2(var0, var1);
+    const P2 r0 = p2(rsqrtf(var0 * (1.0f / RZ_HIDDEN) + eps_ln)), r1 = p2(rsqrtf(var1 * (1.0f / RZ_HIDDEN) + eps_ln));
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      u[i] = p2_fma(p2_mul(u[i], r0), g2[i], b2[i]);
+      v[i] = p2_fma(p2_mul(v[i], r1), g2[i], b2[i]);
+    }
+  }
+  if (do_l2) {
+    P2 nu = p2(0.f), nv = p2(0.f);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { nu = p2_fma(u[i], u[i], nu); nv = p2_fma(v[i], v[i], nv); }
+    float a0, a1, c0, c1;
+    p2_unpack(nu, a0, a1);
+    p2_unpack(nv, c0, c1);
+    float n0 = a0 + a1, n1 = c0 + c1;
+    warp_sum2(n0, n1);
+    const P2 i0 = p2(1.0f / fmaxf(sqrtf(n0), eps_l2)), i1 = p2(1.0f / fmaxf(sqrtf(n1), eps_l2));
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { u[i] = p2_mul(u[i], i0); v[i] = p2_mul(v[i], i1); }
+  }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { p2_unpack(u[i], x0[2 * i], x0[2 * i + 1]); p2_unpack(v[i], x1[2 * i], x1[2 * i + 1]); }
+}
+
 // Row constants of the LayerNorm parameters used by ln_l2_row_onepass.
 struct LnConsts { float sum_g2, sum_gb, sum_b2; };
 

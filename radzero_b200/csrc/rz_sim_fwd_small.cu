@@ -54,12 +54,26 @@ constexpr int kRing = kTeams * kSlotsPerTeam;    // fp32: 10 x 4 x 3 KB = 120 KB
 constexpr int kStages = RZ_SMALL_STAGES; // fp16 token tiles (24 KB each): 1-2 in the MMA chain, the rest being filled
 static_assert(kTokT % 16 == 0 && kTokT <= 64, "the softmax warp reads its tile in tcgen05.ld.x16 halves");
 static_assert(kRing % kTeams == 0, "parity barriers: every waiter must observe every phase of its slots");
-constexpr int kConv = kGroup * kTeams;   // converter warps: rows in flight hide the row latency
+// Rows per converter warp.  1: a team is 4 warps, gamma / beta are re-read (through L1) for every row -- 47 %
+// of the LSU wavefronts of the kernel.  2: a team is 2 warps that convert two rows each with the lane's
+// gamma / beta resident in registers; the CTA has 640 threads, so the register pool gives the converters 128.
+#ifndef RZ_SMALL_RPW
+#define RZ_SMALL_RPW 2
+#endif
+constexpr int kRpw = RZ_SMALL_RPW;
+static_assert(kRpw == 1 || kRpw == 2, "rows per converter warp");
+constexpr int kTeamWarps = kGroup / kRpw;
+constexpr int kConv = kTeamWarps * kTeams;   // converter warps: rows in flight hide the row latency
 constexpr int kThreads = 256 + 32 * kConv;      // WG0 softmax/epilogue, WG1 TMA + MMA (+2 spare warps), converters
 // register budget per warpgroup after setmaxnreg: the pool is what the CTA got at launch
-// (64 registers x kThreads), so the sum over warpgroups must stay inside it
-constexpr int kRegsEpi = 56, kRegsCtl = 24, kRegsConv = 72;
-static_assert((kRegsEpi + kRegsCtl) * 128 + kRegsConv * 32 * kConv <= 64 * kThreads, "register pool");
+// (kRegsLaunch registers x kThreads), so the sum over warpgroups must stay inside it
+// (ptxas allocates the launch-bound maximum for a kernel that contains setmaxnreg: 64 at 1024 threads, 96 at 640)
+constexpr int kRegsLaunch = (65536 / kThreads) / 8 * 8;
+constexpr int kRegsEpi = 56, kRegsCtl = 24;
+constexpr int kRegsConvFit = (kRegsLaunch * kThreads - (kRegsEpi + kRegsCtl) * 128) / (32 * kConv) / 8 * 8;
+constexpr int kRegsConv = kRegsConvFit > 128 ? 128 : kRegsConvFit;
+static_assert(kRegsLaunch * kThreads <= 65536, "register file");
+static_assert((kRegsEpi + kRegsCtl) * 128 + kRegsConv * 32 * kConv <= kRegsLaunch * kThreads, "register pool");
 static_assert(kConv % 4 == 0, "setmaxnreg works on whole warpgroups");
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kGrow = 8.0f;            // the reference maximum moves when exceeded by this much
@@ -199,9 +213,9 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
 
   if (tid == 0) {
     mbar_init(&ctl->q_full, 1);
-    for (int i = 0; i < kRing; ++i) { mbar_init(&ctl->ring_full[i], 1); mbar_init(&ctl->ring_empty[i], kGroup); }
+    for (int i = 0; i < kRing; ++i) { mbar_init(&ctl->ring_full[i], 1); mbar_init(&ctl->ring_empty[i], kTeamWarps); }
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&ctl->k_full[i], kTokT);                       // one arrival per converted row
+      mbar_init(&ctl->k_full[i], kTokT / kRpw);                // one arrival per converter warp and group
       mbar_init(&ctl->k_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -329,12 +343,17 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
     // A row is ~300 instructions of mostly dependent latency (~3k cycles); 24 rows in flight keep up
     // with HBM exactly as the stand-alone rz_prep_rows kernel does with its 24 resident warps.
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsConv));
-    const int team = (warp - 8) / kGroup, w = (warp - 8) % kGroup;
+    const int team = (warp - 8) / kTeamWarps, w = (warp - 8) % kTeamWarps;
     const uint32_t ring_addr = smem_u32(ring);
     const bool ln = p.gamma != nullptr;
     rz::LnConsts lc;
     lc.sum_g2 = lc.sum_gb = lc.sum_b2 = 0.f;
     (void)lc;
+#if RZ_SMALL_RPW == 2
+    rz::P2 g2[12], b2[12];
+    rz::load_lane_pairs(ln ? p.gamma : nullptr, lane, 1.f, g2);
+    rz::load_lane_pairs(ln ? p.beta : nullptr, lane, 0.f, b2);
+#endif
     constexpr int kGpt = kTokT / kGroup;                   // ring groups per tile
     const int n_groups = (g_end - g_begin) * kGpt;
     for (int rg = team; rg < n_groups; rg += kTeams) {
@@ -345,6 +364,36 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
       mbar_wait(&ctl->k_empty[st], (uint32_t)(((lt / kStages) & 1) ^ 1));
       const int slot = (int)(rg % kRing);
       mbar_wait(&ctl->ring_full[slot], (uint32_t)((rg / kRing) & 1));
+#if RZ_SMALL_RPW == 2
+      // two rows of the group per warp, gamma / beta in registers
+      const int r = q4 * kGroup + 2 * w;                   // first of this warp's two token rows within the tile
+      float v[24], v1[24];
+      RingRow<TIn>::load(ring_addr + slot * C::kGroupBytes, 2 * w, lane, v);
+      RingRow<TIn>::load(ring_addr + slot * C::kGroupBytes, 2 * w + 1, lane, v1);
+      // every lane's loads must have RETURNED before the slot goes back to the TMA producer
+      lds_returned(smem_u32(&ctl->sink[warp - 8]), __float_as_uint(v[3]), __float_as_uint(v[11]),
+                   __float_as_uint(v[19]), __float_as_uint(v[23]), __float_as_uint(v1[3]), __float_as_uint(v1[11]),
+                   __float_as_uint(v1[19]), __float_as_uint(v1[23]));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->ring_empty[slot]);
+      rz::ln_l2_rows2_packed(v, v1, g2, b2, ln, RZ_LN_EPS, RZ_L2_EPS, p.l2 != 0);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const bool ok = j * kTokT + r + h < p.L;
+        uint8_t* tile = k_s + st * kKStage + rz::sw128_offset((uint32_t)(r + h), (uint32_t)(8 * (lane & 15))) +
+                        (lane >> 4) * kKChunk;
+        const float* vv = h == 0 ? v : v1;
+#pragma unroll
+        for (int jj = 0; jj < 6; ++jj) {
+          uint2 o = make_uint2(0u, 0u);
+          if (ok) o = make_uint2(rz::pack_half2(vv[4 * jj], vv[4 * jj + 1]), rz::pack_half2(vv[4 * jj + 2], vv[4 * jj + 3]));
+          *reinterpret_cast<uint2*>(tile + jj * (2 * kKChunk)) = o;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->k_full[st]);
+#else
       const int r = q4 * kGroup + w;                       // token row within the tile
       float v[24];
       RingRow<TIn>::load(ring_addr + slot * C::kGroupBytes, w, lane, v);
@@ -373,6 +422,7 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
       if (lane == 0) mbar_arrive(&ctl->k_full[st]);
 #ifdef RZ_EXP_LATE_RELEASE
       if (lane == 0) mbar_arrive(&ctl->ring_empty[slot]);
+#endif
 #endif
     }
   } else if (warp < 4) {
