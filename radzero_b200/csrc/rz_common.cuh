@@ -257,7 +257,7 @@ __device__ __forceinline__ RowStats ln_l2_row_packed(float (&x)[24], const float
   return st;
 }
 
-// TWO rows per warp with the lane's gamma / beta resident in registers as packed pairs (g2 / b2: the pairs
+// SEVERAL rows per warp with the lane's gamma / beta resident in registers as packed pairs (g2 / b2: the pairs
 // of load_lane_pairs): the operations and their order per row are those of ln_l2_row_packed (bit-identical
 // results); the two rows' dependent chains (three shuffle reductions each) are interleaved explicitly, and
 // the per-row parameter loads are gone.
@@ -270,63 +270,77 @@ __device__ __forceinline__ void load_lane_pairs(const float* __restrict__ p, int
     r[2 * j + 1] = p2(v.z, v.w);
   }
 }
-__device__ __forceinline__ void warp_sum2(float& a, float& b) {
+// R rows per warp, interleaved: reductions of R values share each shuffle stage's latency.
+template <int R>
+__device__ __forceinline__ void warp_sum_rows(float (&a)[R]) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
+#pragma unroll
+    for (int r = 0; r < R; ++r) a[r] += __shfl_xor_sync(0xffffffffu, a[r], o);
   }
 }
-__device__ __forceinline__ void ln_l2_rows2_packed(float (&x0)[24], float (&x1)[24], const P2 (&g2)[12],
-                                                   const P2 (&b2)[12], bool do_ln, float eps_ln, float eps_l2,
-                                                   bool do_l2) {
-  P2 u[12], v[12];
+template <int R>
+__device__ __forceinline__ void ln_l2_rows_packed(float (&x)[R][24], const P2 (&g2)[12], const P2 (&b2)[12],
+                                                  bool do_ln, float eps_ln, float eps_l2, bool do_l2) {
+  P2 v[R][12];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) { u[i] = p2(x0[2 * i], x0[2 * i + 1]); v[i] = p2(x1[2 * i], x1[2 * i + 1]); }
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int i = 0; i < 12; ++i) v[r][i] = p2(x[r][2 * i], x[r][2 * i + 1]);
   if (do_ln) {
-    P2 su = u[0], sv = v[0];
+    float mu[R];
 #pragma unroll
-    for (int i = 1; i < 12; ++i) { su = p2_add(su, u[i]); sv = p2_add(sv, v[i]); }
-    float a0, a1, c0, c1;
-    p2_unpack(su, a0, a1);
-    p2_unpack(sv, c0, c1);
-    float mu0 = a0 + a1, mu1 = c0 + c1;
-    warp_sum2(mu0, mu1);
-    mu0 *= (1.0f / RZ_HIDDEN);
-    mu1 *= (1.0f / RZ_HIDDEN);
-    const P2 m0 = p2(mu0), m1 = p2(mu1);
-    P2 qu = p2(0.f), qv = p2(0.f);
+    for (int r = 0; r < R; ++r) {
+      P2 s = v[r][0];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      u[i] = p2_sub(u[i], m0); qu = p2_fma(u[i], u[i], qu);
-      v[i] = p2_sub(v[i], m1); qv = p2_fma(v[i], v[i], qv);
+      for (int i = 1; i < 12; ++i) s = p2_add(s, v[r][i]);
+      float a0, a1;
+      p2_unpack(s, a0, a1);
+      mu[r] = a0 + a1;
     }
-    p2_unpack(qu, a0, a1);
-    p2_unpack(qv, c0, c1);
-    float var0 = a0 + a1, var1 = c0 + c1;
-    warp_sum2(var0, var1);
-    const P2 r0 = p2(rsqrtf(var0 * (1.0f / RZ_HIDDEN) + eps_ln)), r1 = p2(rsqrtf(var1 * (1.0f / RZ_HIDDEN) + eps_ln));
+    warp_sum_rows<R>(mu);
+    float var[R];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      u[i] = p2_fma(p2_mul(u[i], r0), g2[i], b2[i]);
-      v[i] = p2_fma(p2_mul(v[i], r1), g2[i], b2[i]);
+    for (int r = 0; r < R; ++r) {
+      const P2 m = p2(mu[r] * (1.0f / RZ_HIDDEN));
+      P2 q = p2(0.f);
+#pragma unroll
+      for (int i = 0; i < 12; ++i) { v[r][i] = p2_sub(v[r][i], m); q = p2_fma(v[r][i], v[r][i], q); }
+      float a0, a1;
+      p2_unpack(q, a0, a1);
+      var[r] = a0 + a1;
+    }
+    warp_sum_rows<R>(var);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const P2 rs = p2(rsqrtf(var[r] * (1.0f / RZ_HIDDEN) + eps_ln));
+#pragma unroll
+      for (int i = 0; i < 12; ++i) v[r][i] = p2_fma(p2_mul(v[r][i], rs), g2[i], b2[i]);
     }
   }
   if (do_l2) {
-    P2 nu = p2(0.f), nv = p2(0.f);
+    float n[R];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) { nu = p2_fma(u[i], u[i], nu); nv = p2_fma(v[i], v[i], nv); }
-    float a0, a1, c0, c1;
-    p2_unpack(nu, a0, a1);
-    p2_unpack(nv, c0, c1);
-    float n0 = a0 + a1, n1 = c0 + c1;
-    warp_sum2(n0, n1);
-    const P2 i0 = p2(1.0f / fmaxf(sqrtf(n0), eps_l2)), i1 = p2(1.0f / fmaxf(sqrtf(n1), eps_l2));
+    for (int r = 0; r < R; ++r) {
+      P2 q = p2(0.f);
 #pragma unroll
-    for (int i = 0; i < 12; ++i) { u[i] = p2_mul(u[i], i0); v[i] = p2_mul(v[i], i1); }
+      for (int i = 0; i < 12; ++i) q = p2_fma(v[r][i], v[r][i], q);
+      float a0, a1;
+      p2_unpack(q, a0, a1);
+      n[r] = a0 + a1;
+    }
+    warp_sum_rows<R>(n);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const P2 inv = p2(1.0f / fmaxf(sqrtf(n[r]), eps_l2));
+#pragma unroll
+      for (int i = 0; i < 12; ++i) v[r][i] = p2_mul(v[r][i], inv);
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 12; ++i) { p2_unpack(u[i], x0[2 * i], x0[2 * i + 1]); p2_unpack(v[i], x1[2 * i], x1[2 * i + 1]); }
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int i = 0; i < 12; ++i) p2_unpack(v[r][i], x[r][2 * i], x[r][2 * i + 1]);
 }
 
 // Row constants of the LayerNorm parameters used by ln_l2_row_onepass.

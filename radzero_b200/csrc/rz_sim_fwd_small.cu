@@ -61,7 +61,7 @@ static_assert(kRing % kTeams == 0, "parity barriers: every waiter must observe e
 #define RZ_SMALL_RPW 2
 #endif
 constexpr int kRpw = RZ_SMALL_RPW;
-static_assert(kRpw == 1 || kRpw == 2, "rows per converter warp");
+static_assert(kRpw == 1 || kRpw == 2 || kRpw == 4, "rows per converter warp");
 constexpr int kTeamWarps = kGroup / kRpw;
 constexpr int kConv = kTeamWarps * kTeams;   // converter warps: rows in flight hide the row latency
 constexpr int kThreads = 256 + 32 * kConv;      // WG0 softmax/epilogue, WG1 TMA + MMA (+2 spare warps), converters
@@ -71,7 +71,7 @@ constexpr int kThreads = 256 + 32 * kConv;      // WG0 softmax/epilogue, WG1 TMA
 constexpr int kRegsLaunch = (65536 / kThreads) / 8 * 8;
 constexpr int kRegsEpi = 56, kRegsCtl = 24;
 constexpr int kRegsConvFit = (kRegsLaunch * kThreads - (kRegsEpi + kRegsCtl) * 128) / (32 * kConv) / 8 * 8;
-constexpr int kRegsConv = kRegsConvFit > 128 ? 128 : kRegsConvFit;
+constexpr int kRegsConv = kRegsConvFit > 32 * (kRpw + 2) ? 32 * (kRpw + 2) : kRegsConvFit;   // 24 x + 12 packed / row, 48 parameters
 static_assert(kRegsLaunch * kThreads <= 65536, "register file");
 static_assert((kRegsEpi + kRegsCtl) * 128 + kRegsConv * 32 * kConv <= kRegsLaunch * kThreads, "register pool");
 static_assert(kConv % 4 == 0, "setmaxnreg works on whole warpgroups");
@@ -349,7 +349,7 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
     rz::LnConsts lc;
     lc.sum_g2 = lc.sum_gb = lc.sum_b2 = 0.f;
     (void)lc;
-#if RZ_SMALL_RPW == 2
+#if RZ_SMALL_RPW >= 2
     rz::P2 g2[12], b2[12];
     rz::load_lane_pairs(ln ? p.gamma : nullptr, lane, 1.f, g2);
     rz::load_lane_pairs(ln ? p.beta : nullptr, lane, 0.f, b2);
@@ -364,29 +364,32 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
       mbar_wait(&ctl->k_empty[st], (uint32_t)(((lt / kStages) & 1) ^ 1));
       const int slot = (int)(rg % kRing);
       mbar_wait(&ctl->ring_full[slot], (uint32_t)((rg / kRing) & 1));
-#if RZ_SMALL_RPW == 2
-      // two rows of the group per warp, gamma / beta in registers
-      const int r = q4 * kGroup + 2 * w;                   // first of this warp's two token rows within the tile
-      float v[24], v1[24];
-      RingRow<TIn>::load(ring_addr + slot * C::kGroupBytes, 2 * w, lane, v);
-      RingRow<TIn>::load(ring_addr + slot * C::kGroupBytes, 2 * w + 1, lane, v1);
-      // every lane's loads must have RETURNED before the slot goes back to the TMA producer
-      lds_returned(smem_u32(&ctl->sink[warp - 8]), __float_as_uint(v[3]), __float_as_uint(v[11]),
-                   __float_as_uint(v[19]), __float_as_uint(v[23]), __float_as_uint(v1[3]), __float_as_uint(v1[11]),
-                   __float_as_uint(v1[19]), __float_as_uint(v1[23]));
+#if RZ_SMALL_RPW >= 2
+      // kRpw rows of the group per warp, gamma / beta in registers
+      const int r = q4 * kGroup + kRpw * w;                // first of this warp's token rows within the tile
+      float v[kRpw][24];
+#pragma unroll
+      for (int h = 0; h < kRpw; ++h) RingRow<TIn>::load(ring_addr + slot * C::kGroupBytes, kRpw * w + h, lane, v[h]);
+      // every lane's loads must have RETURNED before the slot goes back to the TMA producer (see
+      // lds_returned in rz_umma.cuh: the arrive can overtake loads still queued in the LSU)
+#pragma unroll
+      for (int h = 0; h < kRpw; h += 2)
+        lds_returned(smem_u32(&ctl->sink[warp - 8]), __float_as_uint(v[h][3]), __float_as_uint(v[h][11]),
+                     __float_as_uint(v[h][19]), __float_as_uint(v[h][23]), __float_as_uint(v[h + 1][3]),
+                     __float_as_uint(v[h + 1][11]), __float_as_uint(v[h + 1][19]), __float_as_uint(v[h + 1][23]));
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->ring_empty[slot]);
-      rz::ln_l2_rows2_packed(v, v1, g2, b2, ln, RZ_LN_EPS, RZ_L2_EPS, p.l2 != 0);
+      rz::ln_l2_rows_packed<kRpw>(v, g2, b2, ln, RZ_LN_EPS, RZ_L2_EPS, p.l2 != 0);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < kRpw; ++h) {
         const bool ok = j * kTokT + r + h < p.L;
         uint8_t* tile = k_s + st * kKStage + rz::sw128_offset((uint32_t)(r + h), (uint32_t)(8 * (lane & 15))) +
                         (lane >> 4) * kKChunk;
-        const float* vv = h == 0 ? v : v1;
 #pragma unroll
         for (int jj = 0; jj < 6; ++jj) {
           uint2 o = make_uint2(0u, 0u);
-          if (ok) o = make_uint2(rz::pack_half2(vv[4 * jj], vv[4 * jj + 1]), rz::pack_half2(vv[4 * jj + 2], vv[4 * jj + 3]));
+          if (ok) o = make_uint2(rz::pack_half2(v[h][4 * jj], v[h][4 * jj + 1]),
+                                 rz::pack_half2(v[h][4 * jj + 2], v[h][4 * jj + 3]));
           *reinterpret_cast<uint2*>(tile + jj * (2 * kKChunk)) = o;
         }
       }
