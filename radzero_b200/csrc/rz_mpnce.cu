@@ -11,6 +11,7 @@
 // (log_tau), so the host never synchronises.  HBM/L2-bound: Z is read twice and dZ written once.
 // All sums use a fixed order -- no float atomics -- so the 1-GPU and N-GPU results agree bit for
 // bit on the local block.
+#include <cstdio>
 #include "rz_common.cuh"
 
 namespace {
@@ -104,10 +105,25 @@ __device__ __forceinline__ float4 load4(const float* row, int c, int b_local) {
   return v;
 }
 
+#ifdef RZ_EXP_MPNCE_TIMING
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+  return v;
+}
+#define RZ_T(i) if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) tt[i] = gtime();
+#else
+#define RZ_T(i)
+#endif
+
 template <bool VEC>
 __global__ void __launch_bounds__(kThreads)
 mpnce_partials_kernel(PartialsParams p) {
   __shared__ float colbuf[kWarps][kColBlock];
+#ifdef RZ_EXP_MPNCE_TIMING
+  unsigned long long tt[6];
+#endif
+  RZ_T(0)
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const float inv_tau = inv_temperature(p.log_tau, p.inv_tau);
   const int chunks = (p.n_total + kRowChunk - 1) / kRowChunk;
@@ -175,12 +191,15 @@ mpnce_partials_kernel(PartialsParams p) {
         if (r0 + rr < p.n_total) p.rowsum[r0 + rr] = racc[rr];
     }
   }
+  RZ_T(1)
   grid_barrier(p.barrier);
+  RZ_T(2)
   // phase B.  colbuf is free now: it holds the int32 sentence -> image map for the column scans
   int* gsm = reinterpret_cast<int*>(&colbuf[0][0]);
   const bool staged = p.n_total <= kGroupCap;
   const bool any_col = (int)blockIdx.x * kWarps < b_local;
   if (staged && any_col) stage_group_map(p.group_map, p.n_total, gsm);
+  RZ_T(3)
   for (int c = blockIdx.x * kWarps + warp; c < b_local; c += gridDim.x * kWarps) {
     float all = 0.f, cp = 0.f;
     for (int k = lane; k < chunks; k += 32) all += __ldcg(p.colpart + (long long)k * b_local + c);
@@ -238,6 +257,12 @@ mpnce_partials_kernel(PartialsParams p) {
       p.acol[c] = a; p.apos[c] = ap; p.lcol[c] = l;
     }
   }
+  RZ_T(4)
+#ifdef RZ_EXP_MPNCE_TIMING
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0)
+    printf("partials grid %d: phaseA %llu ns, barrier %llu, stage %llu, phaseB %llu\n", (int)gridDim.x,
+           tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], tt[4] - tt[3]);
+#endif
 }
 
 // ---- launch 2 --------------------------------------------------------------------------
@@ -448,7 +473,8 @@ extern "C" int rz_mpnce_partials(const float* z, long long ldz, int n_total, int
   const void* kern = vec ? (const void*)mpnce_partials_kernel<true> : (const void*)mpnce_partials_kernel<false>;
   const int grid = vec ? coop_grid(mpnce_partials_kernel<true>, chunks) : coop_grid(mpnce_partials_kernel<false>, chunks);
   void* args[] = {&p};
-  RZ_CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kThreads), args, 0, s));
+  if (getenv("RZ_EXP_MPNCE_PLAIN")) RZ_CUDA_OK(cudaLaunchKernel(kern, dim3(grid), dim3(kThreads), args, 0, s));
+  else RZ_CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kThreads), args, 0, s));
   rz_count_launch(1);
   return RZ_OK;
 }
