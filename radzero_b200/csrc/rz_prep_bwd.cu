@@ -20,9 +20,9 @@ prep_rows_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long warp0 = (long long)blockIdx.x * kWarps + warp;
   const long long nwarps = (long long)gridDim.x * kWarps;
-  float dg[24], db[24];
+  rz::P2 dg2[12], db2[12];
 #pragma unroll
-  for (int i = 0; i < 24; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+  for (int i = 0; i < 12; ++i) { dg2[i] = rz::p2(0.f); db2[i] = rz::p2(0.f); }
   const bool has_ln = gamma != nullptr;
   for (long long row = warp0; row < rows; row += nwarps) {
     const long long g = row / rows_per_group;
@@ -37,66 +37,77 @@ prep_rows_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
         d[4 * j] = t.x; d[4 * j + 1] = t.y; d[4 * j + 2] = t.z; d[4 * j + 3] = t.w;
       }
     }
+    // packed fp32 pairs (fma.rn.f32x2): the row is ~400 dependent FP32 operations per lane between six
+    // shuffle reductions, and 16 warps per SM cannot hide that -- half the instructions, same order of
+    // operations per element
+    using rz::P2; using rz::p2; using rz::p2_fma; using rz::p2_mul; using rz::p2_add; using rz::p2_sub;
+    using rz::p2_unpack;
+    P2 v2[12], d2[12], gm2[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { v2[i] = p2(v[2 * i], v[2 * i + 1]); d2[i] = p2(d[2 * i], d[2 * i + 1]); }
+    auto hsum = [](P2 a) { float x0, x1; p2_unpack(a, x0, x1); return x0 + x1; };
     float rstd = 1.f;
-    float gm[24];
     if (has_ln) {
-      float s = 0.f;
+      P2 s2 = v2[0];
 #pragma unroll
-      for (int i = 0; i < 24; ++i) s += v[i];
-      const float mu = rz::warp_sum(s) * (1.0f / RZ_HIDDEN);
-      float q = 0.f;
+      for (int i = 1; i < 12; ++i) s2 = p2_add(s2, v2[i]);
+      const float mu = rz::warp_sum(hsum(s2)) * (1.0f / RZ_HIDDEN);
+      const P2 mu2 = p2(mu);
+      P2 q2 = p2(0.f);
 #pragma unroll
-      for (int i = 0; i < 24; ++i) { v[i] -= mu; q = fmaf(v[i], v[i], q); }
-      rstd = rsqrtf(rz::warp_sum(q) * (1.0f / RZ_HIDDEN) + RZ_LN_EPS);
+      for (int i = 0; i < 12; ++i) { v2[i] = p2_sub(v2[i], mu2); q2 = p2_fma(v2[i], v2[i], q2); }
+      rstd = rsqrtf(rz::warp_sum(hsum(q2)) * (1.0f / RZ_HIDDEN) + RZ_LN_EPS);
+      const P2 r2 = p2(rstd);
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
         const float4 t = *reinterpret_cast<const float4*>(gamma + 4 * (lane + 32 * j));
-        gm[4 * j] = t.x; gm[4 * j + 1] = t.y; gm[4 * j + 2] = t.z; gm[4 * j + 3] = t.w;
+        gm2[2 * j] = p2(t.x, t.y); gm2[2 * j + 1] = p2(t.z, t.w);
       }
 #pragma unroll
-      for (int i = 0; i < 24; ++i) v[i] *= rstd;            // v = xhat
+      for (int i = 0; i < 12; ++i) v2[i] = p2_mul(v2[i], r2);            // v = xhat
     }
     if (l2) {
       // y (LayerNorm output) -> k = y/|y|;  dy = (d - k <k,d>) / |y|
-      float y[24];
+      P2 y2[12];
       if (has_ln) {
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
           const float4 t = *reinterpret_cast<const float4*>(beta + 4 * (lane + 32 * j));
-          y[4 * j] = fmaf(v[4 * j], gm[4 * j], t.x);
-          y[4 * j + 1] = fmaf(v[4 * j + 1], gm[4 * j + 1], t.y);
-          y[4 * j + 2] = fmaf(v[4 * j + 2], gm[4 * j + 2], t.z);
-          y[4 * j + 3] = fmaf(v[4 * j + 3], gm[4 * j + 3], t.w);
+          y2[2 * j] = p2_fma(v2[2 * j], gm2[2 * j], p2(t.x, t.y));
+          y2[2 * j + 1] = p2_fma(v2[2 * j + 1], gm2[2 * j + 1], p2(t.z, t.w));
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 24; ++i) y[i] = v[i];
+        for (int i = 0; i < 12; ++i) y2[i] = v2[i];
       }
-      float n2 = 0.f, yd = 0.f;
+      P2 n22 = p2(0.f), yd2 = p2(0.f);
 #pragma unroll
-      for (int i = 0; i < 24; ++i) { n2 = fmaf(y[i], y[i], n2); yd = fmaf(y[i], d[i], yd); }
-      n2 = rz::warp_sum(n2);
-      yd = rz::warp_sum(yd);
+      for (int i = 0; i < 12; ++i) { n22 = p2_fma(y2[i], y2[i], n22); yd2 = p2_fma(y2[i], d2[i], yd2); }
+      const float n2 = rz::warp_sum(hsum(n22));
+      const float yd = rz::warp_sum(hsum(yd2));
       const float inv = 1.0f / fmaxf(sqrtf(n2), RZ_L2_EPS);
-      const float c = yd * inv * inv;                       // <k,d>/|y| = <y,d>/|y|^2
+      const P2 nc2 = p2(-yd * inv * inv), inv2 = p2(inv);             // <k,d>/|y| = <y,d>/|y|^2
 #pragma unroll
-      for (int i = 0; i < 24; ++i) d[i] = (d[i] - y[i] * c) * inv;
+      for (int i = 0; i < 12; ++i) d2[i] = p2_mul(p2_fma(y2[i], nc2, d2[i]), inv2);
     }
     if (has_ln) {
-      float m1 = 0.f, m2 = 0.f;
+      P2 m12 = p2(0.f), m22 = p2(0.f);
 #pragma unroll
-      for (int i = 0; i < 24; ++i) {
-        dg[i] = fmaf(d[i], v[i], dg[i]);
-        db[i] += d[i];
-        d[i] *= gm[i];                                      // d = dxhat
-        m1 += d[i];
-        m2 = fmaf(d[i], v[i], m2);
+      for (int i = 0; i < 12; ++i) {
+        dg2[i] = p2_fma(d2[i], v2[i], dg2[i]);
+        db2[i] = p2_add(db2[i], d2[i]);
+        d2[i] = p2_mul(d2[i], gm2[i]);                                  // d = dxhat
+        m12 = p2_add(m12, d2[i]);
+        m22 = p2_fma(d2[i], v2[i], m22);
       }
-      m1 = rz::warp_sum(m1) * (1.0f / RZ_HIDDEN);
-      m2 = rz::warp_sum(m2) * (1.0f / RZ_HIDDEN);
+      const float m1 = rz::warp_sum(hsum(m12)) * (1.0f / RZ_HIDDEN);
+      const float m2 = rz::warp_sum(hsum(m22)) * (1.0f / RZ_HIDDEN);
+      const P2 nm1 = p2(-m1), nm2 = p2(-m2), r2 = p2(rstd);
 #pragma unroll
-      for (int i = 0; i < 24; ++i) d[i] = rstd * (d[i] - m1 - v[i] * m2);
+      for (int i = 0; i < 12; ++i) d2[i] = p2_mul(r2, p2_fma(v2[i], nm2, p2_add(d2[i], nm1)));
     }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) p2_unpack(d2[i], d[2 * i], d[2 * i + 1]);
     if (dx_native && sizeof(T) == 2) {
       // dL/dx in the input's own 16-bit type: no fp32 round trip + conversion pass afterwards
       uint2* o = reinterpret_cast<uint2*>(static_cast<T*>(dx_out) + row * RZ_HIDDEN) + lane;
@@ -109,6 +120,9 @@ prep_rows_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
     }
   }
   if (part == nullptr) return;
+  float dg[24], db[24];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { rz::p2_unpack(dg2[i], dg[2 * i], dg[2 * i + 1]); rz::p2_unpack(db2[i], db[2 * i], db[2 * i + 1]); }
   // CTA reduction of the parameter gradients, 384 floats (= 12 of the 48 per-lane values) a pass
   float* out = part + (long long)blockIdx.x * 2 * RZ_HIDDEN;
   for (int pass = 0; pass < 4; ++pass) {
