@@ -241,13 +241,14 @@ def measure_inference(workload, steps, warmup, world, rank, local, pk):
 
     def run_sim():
         if fused:
-            return ops.sim_fwd_tokens(tok, g, bta, q16, 1.0, want_scores=want_scores, **zkw)
+            # the step's own call: the prompts are LayerNorm-ed + normalised inside the kernel (text_raw)
+            return ops.sim_fwd_tokens(tok, g, bta, None, 1.0, text_raw=text, want_scores=want_scores, **zkw)
         return ops.sim_fwd(k16.view(B, Lp, D), q16, L, 1.0, want_scores=want_scores, **zkw)
 
     o = run_sim()
     stages = [
         (lambda: ops.prep_rows(tok, g, bta, rows_per_group=L, rows_per_group_padded=Lp)) if not fused else None,
-        lambda: ops.prep_rows(text, g, bta),
+        (lambda: ops.prep_rows(text, g, bta)) if not fused else None,
         run_sim,
         (lambda: inference.interpolate_similarity_scores(o["scores"], out_hw, "blip", mode="sigmoid"))
         if workload == "seg" else None,
@@ -273,8 +274,8 @@ def measure_inference(workload, steps, warmup, world, rank, local, pk):
     score_bytes = B * N * (L - 1) * 4 if want_scores else 0
     flops = 2.0 * 2.0 * B * N * L * D          # scores + pooling GEMM
     if fused:
-        sim_name = "sim_small_kernel<float> (raw tokens -> LN+L2 -> tcgen05 S/O GEMMs + softmax pool, one kernel)"
-        sim_bytes = B * L * D * 4 + N * D * 2 + score_bytes + B * N * 4
+        sim_name = "sim_small_kernel<float> (raw tokens + raw prompts -> LN+L2 -> tcgen05 S/O GEMMs + softmax pool, one kernel) + merge_partials_kernel"
+        sim_bytes = B * L * D * 4 + N * D * 4 + score_bytes + B * N * 4
     else:
         if N > ops.LARGE_N_THRESHOLD:
             sim_name = "rz_sim_fwd_large: gemm_kernel<PassS2> + gemm_kernel<PassPK> (two tcgen05 GEMM passes)"

@@ -110,6 +110,10 @@ int rz_sim_fwd(const void* k_f16, int n_images, int tokens, int tokens_padded,
  *   q_f16      [n_text, 768] fp16 rows from rz_prep_rows (the prompts are tiny: 14 x 768)
  *   workspace  rz_sim_fwd_tokens_workspace_bytes(...) bytes, 16-byte aligned
  * Returns RZ_ERR_UNSUPPORTED for n_text > 16 (use rz_prep_rows + rz_sim_fwd).
+  *   text_f32  optional fp32 [n_text, 768]: the prompt embeddings BEFORE LayerNorm + L2 (text_features_wo_l2_norm,
+ *          losses.py:139-142).  When given, q_f16 may be NULL: every CTA normalises the rows in its prologue
+ *          (compute_text_features' LayerNorm + F.normalize, losses.py:163-164, 212) with the same gamma / beta,
+ *          which saves the rz_prep_rows launch of the prompts.  Not with q_inv_norm (sim_op "dot").
  */
 size_t rz_sim_fwd_tokens_workspace_bytes(int n_images, int n_text);
 int rz_sim_fwd_tokens(const void* tokens_raw, int dtype, const float* gamma, const float* beta,
@@ -117,8 +121,8 @@ int rz_sim_fwd_tokens(const void* tokens_raw, int dtype, const float* gamma, con
                       float scale, const float* log_tau_scale, const float* q_inv_norm,
                       float* scores, long long scores_stride_image, long long scores_stride_text,
                       int drop_cls, float* z, long long z_stride_text, long long z_stride_image,
-                      float z_scale, const float* log_tau_z, int z_sigmoid, void* workspace,
-                      size_t workspace_bytes, void* stream);
+                      float z_scale, const float* log_tau_z, int z_sigmoid, const float* text_f32,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* Same computation for LARGE prompt sets (open-vocabulary sweeps, the contrastive step), as
  * two full-rate tcgen05 GEMM passes: pass S computes the scores exactly once, one thread per

@@ -35,7 +35,7 @@ SIGNATURES: Dict[str, tuple] = {
                         _f, _vp, _i, _vp, _vp, _vp, _vp]),
     "rz_sim_fwd_tokens_workspace_bytes": (C.c_size_t, [_i, _i]),
     "rz_sim_fwd_tokens": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _ll, _ll,
-                               _i, _vp, _ll, _ll, _f, _vp, _i, _vp, C.c_size_t, _vp]),
+                               _i, _vp, _ll, _ll, _f, _vp, _i, _vp, _vp, C.c_size_t, _vp]),
     "rz_sim_fwd_large_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "rz_sim_fwd_large": (_i, [_vp, _i, _i, _i, _vp, _i, _f, _vp, _vp, _vp, _ll, _ll, _i, _vp, _ll, _ll,
                               _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, C.c_size_t, _vp]),

@@ -97,6 +97,8 @@ struct Params {
   int l2;
   const float* q_inv_norm;
   const __half* q;                 // [N, 768] (global copy, for the merge kernel)
+  const float* text_raw;           // optional [N, 768] fp32: the prompts BEFORE LayerNorm + L2 -- normalised in the
+  __half* q_out;                   // prologue of every CTA (no prep launch); CTA 0 also writes them here (= q)
   float* scores; long long scores_sb, scores_sn; int drop_cls;
   float* z; long long z_sn, z_sb; float z_scale; int z_sigmoid;
   float* part;                     // [ctas][2][kPartFloats]
@@ -212,7 +214,7 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
   const int T = p.T;
 
   if (tid == 0) {
-    mbar_init(&ctl->q_full, 1);
+    mbar_init(&ctl->q_full, p.text_raw != nullptr ? kConv : 1);
     for (int i = 0; i < kRing; ++i) { mbar_init(&ctl->ring_full[i], 1); mbar_init(&ctl->ring_empty[i], kTeamWarps); }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&ctl->k_full[i], kTokT / kRpw);                // one arrival per converter warp and group
@@ -239,9 +241,11 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
   if (warp == 4) {
     // ================================================================= TMA producer
     if (elect_one()) {
-      mbar_arrive_expect_tx(&ctl->q_full, (uint32_t)kQBytes);
-      for (int c = 0; c < kChunks; ++c)
-        tma_load_2d(&qmap, &ctl->q_full, q_s + c * (kNB * 128), c * 64, 0, kEvictLast);
+      if (p.text_raw == nullptr) {
+        mbar_arrive_expect_tx(&ctl->q_full, (uint32_t)kQBytes);
+        for (int c = 0; c < kChunks; ++c)
+          tma_load_2d(&qmap, &ctl->q_full, q_s + c * (kNB * 128), c * 64, 0, kEvictLast);
+      }
       int rg = 0;                                          // ring groups issued by this CTA
       for (int g = g_begin; g < g_end; ++g) {
         const int b = g / T, j = g - b * T;
@@ -354,6 +358,33 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
     rz::load_lane_pairs(ln ? p.gamma : nullptr, lane, 1.f, g2);
     rz::load_lane_pairs(ln ? p.beta : nullptr, lane, 0.f, b2);
 #endif
+    if (p.text_raw != nullptr) {
+      // The prompts' own LayerNorm + L2 (compute_text_features + F.normalize, losses.py:163-164, 212): the 16
+      // rows of the S-GEMM's A operand are written straight into its swizzled K-major tile -- the same layout
+      // as a converted token tile (kNB = kTokT rows, chunks kKChunk apart) -- instead of being prepared by a
+      // launch of their own and fetched by TMA.  Rows >= N are zero.
+      static_assert(kNB * 128 == kKChunk || kTokT != 16, "q tile = one 16-token tile");
+      for (int r = warp - 8; r < kNB; r += kConv) {
+        float v[24];
+#pragma unroll
+        for (int i = 0; i < 24; ++i) v[i] = 0.f;
+        if (r < p.N) {
+          rz::RowLoad<float>::load(p.text_raw + (long long)r * kD, lane, v);
+          rz::ln_l2_row_packed(v, ln ? p.gamma : nullptr, ln ? p.beta : nullptr, lane, RZ_LN_EPS, RZ_L2_EPS, p.l2 != 0);
+        }
+        uint8_t* tile = q_s + rz::sw128_offset((uint32_t)r, (uint32_t)(8 * (lane & 15))) + (lane >> 4) * (kNB * 128);
+#pragma unroll
+        for (int jj = 0; jj < 6; ++jj) {
+          const uint2 o = make_uint2(rz::pack_half2(v[4 * jj], v[4 * jj + 1]), rz::pack_half2(v[4 * jj + 2], v[4 * jj + 3]));
+          *reinterpret_cast<uint2*>(tile + jj * (2 * kNB * 128)) = o;
+          if (blockIdx.x == 0 && r < p.N)                  // the merge kernel reads the rows from global memory
+            *reinterpret_cast<uint2*>(p.q_out + (long long)r * kD + 4 * (lane + 32 * jj)) = o;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->q_full);
+    }
     constexpr int kGpt = kTokT / kGroup;                   // ring groups per tile
     const int n_groups = (g_end - g_begin) * kGpt;
     for (int rg = team; rg < n_groups; rg += kTeams) {
@@ -704,7 +735,7 @@ int launch_small(const void* tokens_raw, CUtensorMapDataType dt, const CUtensorM
 
 extern "C" size_t rz_sim_fwd_tokens_workspace_bytes(int n_images, int n_text) {
   if (n_images <= 0 || n_text <= 0) return 0;
-  return (size_t)rz_sm_count() * 2 * kPartFloats * sizeof(float) + 256;
+  return (size_t)rz_sm_count() * 2 * kPartFloats * sizeof(float) + 256 + (size_t)kNB * kD * sizeof(__half);
 }
 
 extern "C" int rz_sim_fwd_tokens(const void* tokens_raw, int dtype, const float* gamma,
@@ -714,8 +745,10 @@ extern "C" int rz_sim_fwd_tokens(const void* tokens_raw, int dtype, const float*
                                  long long scores_stride_image, long long scores_stride_text,
                                  int drop_cls, float* z, long long z_stride_text,
                                  long long z_stride_image, float z_scale, const float* log_tau_z,
-                                 int z_sigmoid, void* workspace, size_t workspace_bytes, void* stream) {
-  if (tokens_raw == nullptr || q_f16 == nullptr || workspace == nullptr) return RZ_ERR_INVALID;
+                                 int z_sigmoid, const float* text_f32, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  if (tokens_raw == nullptr || (q_f16 == nullptr && text_f32 == nullptr) || workspace == nullptr) return RZ_ERR_INVALID;
+  if (text_f32 != nullptr && (q_inv_norm != nullptr || (reinterpret_cast<uintptr_t>(text_f32) & 15))) return RZ_ERR_UNSUPPORTED;
   if ((gamma == nullptr) != (beta == nullptr)) return RZ_ERR_INVALID;
   if (n_images <= 0 || n_text <= 0 || tokens <= 0) return RZ_ERR_INVALID;
   if (drop_cls != 0 && drop_cls != 1) return RZ_ERR_INVALID;
@@ -732,6 +765,14 @@ extern "C" int rz_sim_fwd_tokens(const void* tokens_raw, int dtype, const float*
   p.scale = scale; p.log_tau_scale = log_tau_scale; p.log_tau_z = log_tau_z;
   p.gamma = gamma; p.beta = beta; p.l2 = l2; p.q_inv_norm = q_inv_norm;
   p.q = static_cast<const __half*>(q_f16);
+  p.text_raw = text_f32;
+  p.q_out = nullptr;
+  if (text_f32 != nullptr) {       // the normalised rows live behind the partials in the workspace
+    p.q_out = reinterpret_cast<__half*>(static_cast<uint8_t*>(workspace) +
+                                        (size_t)rz_sm_count() * 2 * kPartFloats * sizeof(float) + 256);
+    p.q = p.q_out;
+    q_f16 = p.q_out;
+  }
   p.scores = scores; p.scores_sb = scores_stride_image; p.scores_sn = scores_stride_text;
   p.drop_cls = drop_cls;
   p.z = z; p.z_sn = z_stride_text; p.z_sb = z_stride_image; p.z_scale = z_scale; p.z_sigmoid = z_sigmoid;

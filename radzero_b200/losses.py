@@ -103,6 +103,12 @@ def _similarity_forward(text: torch.Tensor, tokens: torch.Tensor, gamma, beta, s
     if tokens.dim() != 3:
         raise RzError("vision tokens must be (B, L, 768)")
     B, L, _ = tokens.shape
+    if (q16 is None and l2 and ops.USE_FUSED_PREP and text.dim() == 2 and text.shape[0] <= ops.FUSED_PREP_MAX_TEXT
+            and text.dtype == torch.float32):
+        # few prompts, cosine: their LayerNorm + L2 also happen inside the one kernel (no prep launch)
+        out = ops.sim_fwd_tokens(tokens, gamma, beta, None, scale, l2=True, text_raw=text, want_scores=want_scores,
+                                 drop_cls=drop_cls, **zkw)
+        return out["z"], out["scores"]
     if q16 is None:      # else: rows already normalised by ops.text_pool (fused with the mean pooling)
         q16, _, _ = ops.prep_rows(text, gamma, beta, l2=l2)
     qin = None

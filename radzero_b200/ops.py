@@ -198,25 +198,36 @@ USE_FUSED_PREP = True
 
 @_guard
 def sim_fwd_tokens(tokens_raw: torch.Tensor, gamma: Optional[torch.Tensor],
-                   beta: Optional[torch.Tensor], q_f16: torch.Tensor, scale: float, *, l2: bool = True,
+                   beta: Optional[torch.Tensor], q_f16: Optional[torch.Tensor], scale: float, *, l2: bool = True,
+                   text_raw: Optional[torch.Tensor] = None,
                    want_scores: bool = False, drop_cls: bool = True, want_z: bool = True,
                    q_inv_norm: Optional[torch.Tensor] = None, z_out: Optional[torch.Tensor] = None,
                    z_scale: float = 1.0, z_sigmoid: bool = False, z_image_major: bool = False,
                    log_tau_scale: Optional[torch.Tensor] = None,
                    log_tau_z: Optional[torch.Tensor] = None):
     """Small-prompt-set forward straight from the RAW tokens (B, L, 768) fp32/bf16/fp16:
-    LayerNorm + L2 + the whole similarity path in ONE kernel (N <= 16)."""
-    _need_cuda(tokens_raw, gamma, beta, q_f16, q_inv_norm, z_out)
+    LayerNorm + L2 + the whole similarity path in ONE kernel (N <= 16).  ``text_raw`` (N, 768) fp32 instead
+    of ``q_f16``: the prompts' own LayerNorm + L2 also run inside the kernel (no prep launch)."""
+    _need_cuda(tokens_raw, gamma, beta, q_f16, q_inv_norm, z_out, text_raw)
     if tokens_raw.dtype not in _DTYPES:
         raise RzError(f"unsupported token dtype {tokens_raw.dtype}")
     if tokens_raw.dim() != 3 or tokens_raw.shape[-1] != HIDDEN:
         raise RzError("tokens must be (B, L, 768)")
     x = _contig(tokens_raw)
     B, L, _ = x.shape
-    N = q_f16.shape[0]
+    if (q_f16 is None) == (text_raw is None):
+        raise RzError("give either q_f16 (prepared rows) or text_raw (fp32 rows before LayerNorm + L2)")
+    txt = None
+    if text_raw is not None:
+        if q_inv_norm is not None:
+            raise RzError("text_raw is for sim_op 'cos' (no q_inv_norm)")
+        if text_raw.dtype != torch.float32 or text_raw.dim() != 2 or text_raw.shape[1] != HIDDEN:
+            raise RzError("text_raw must be fp32 (N, 768)")
+        txt = _contig(text_raw.detach())
+    N = (q_f16 if q_f16 is not None else txt).shape[0]
     if N > FUSED_PREP_MAX_TEXT:
         raise RzError(f"sim_fwd_tokens handles at most {FUSED_PREP_MAX_TEXT} prompts")
-    if q_f16.dtype != torch.float16 or not q_f16.is_contiguous():
+    if q_f16 is not None and (q_f16.dtype != torch.float16 or not q_f16.is_contiguous()):
         raise RzError("q_f16 must be contiguous fp16 (N, 768)")
     dev = x.device
     drop, scores, z, zs_text, zs_img = _sim_outputs(B, N, L, dev, want_scores, drop_cls, want_z,
@@ -232,7 +243,7 @@ def sim_fwd_tokens(tokens_raw: torch.Tensor, gamma: Optional[torch.Tensor],
         _p(x), _DTYPES[x.dtype], _p(g), _p(b), 1 if l2 else 0, B, L, _p(q_f16), N, float(scale),
         _p(lts), _p(qin), _p(scores), scores.stride(0) if scores is not None else 0,
         scores.stride(1) if scores is not None else 0, drop, _p(z), zs_text, zs_img,
-        float(z_scale), _p(ltz), 1 if z_sigmoid else 0, _p(ws), C.c_size_t(nbytes), _stream())
+        float(z_scale), _p(ltz), 1 if z_sigmoid else 0, _p(txt), _p(ws), C.c_size_t(nbytes), _stream())
     _lib.check(rc, "rz_sim_fwd_tokens")
     return dict(scores=scores, z=z)
 

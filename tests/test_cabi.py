@@ -30,7 +30,7 @@ def test_argument_validation_without_gpu():
     assert lib.rz_upsample_maps(None, 0, 1, 37, 8, 8, 8, 8, 0, 0, 0.0, 0, 0.5, None, None) == -1
     assert lib.rz_mpnce_partials(None, 0, 1, 1, 1, None, 0, 1.0, None, 1e-8, 0, None, None, None, None, None) == -1
     assert lib.rz_sim_fwd_tokens(None, 0, None, None, 1, 1, 1370, None, 14, 1.0, None, None, None, 0, 0, 1,
-                                 None, 0, 0, 1.0, None, 0, None, 0, None) == -1
+                                 None, 0, 0, 1.0, None, 0, None, None, 0, None) == -1
     assert lib.rz_sim_fwd_tokens_workspace_bytes(0, 14) == 0
     assert lib.rz_sim_fwd_large_workspace_bytes(2, 100, 1408) > 2 * 100 * 1408 * 2
 

@@ -141,6 +141,29 @@ def test_per_image_queries(sim_op, B, N):
         sl(q.to(DEV).requires_grad_(True), tok.to(DEV), repeat=False, temperature=torch.tensor(TAU))
 
 
+@pytest.mark.parametrize("B,N,L", [(3, 14, 1370), (1, 1, 77), (5, 16, 200), (37, 5, 333)])
+@pytest.mark.parametrize("with_ln", [True, False])
+def test_sim_fwd_tokens_with_the_prompts_prepared_in_the_kernel(B, N, L, with_ln):
+    """text_raw: the prompts' LayerNorm + L2 run in the prologue of every CTA (no prep launch); the same
+    results as preparing them with rz_prep_rows up to the fp16 rounding of a prompt element (the two
+    routines sum the row statistics in a different order), and within tolerance of the oracle."""
+    tok, text, gamma, beta, _ = synthetic.make_inputs(B, N, tokens_per_image=L, seed=500 + N)
+    g = gamma.to(DEV) if with_ln else None
+    b = beta.to(DEV) if with_ln else None
+    q16, _, _ = ops.prep_rows(text.to(DEV), g, b)
+    two = ops.sim_fwd_tokens(tok.to(DEV), g, b, q16, 1.0 / TAU, want_scores=True, drop_cls=True)
+    one = ops.sim_fwd_tokens(tok.to(DEV), g, b, None, 1.0 / TAU, text_raw=text.to(DEV), want_scores=True,
+                             drop_cls=True)
+    assert (one["scores"] - two["scores"]).abs().max() < 5e-4          # scores are at the 1/tau = 14.3 scale
+    assert (one["z"] - two["z"]).abs().max() < 2e-5
+    if with_ln:
+        want = _oracle(tok, text, gamma, beta)
+        assert (one["scores"].cpu().double() - want["scores"][:, :, 1:]).abs().max() < 2e-3
+        assert (one["z"].cpu().double() - want["z"]).abs().max() < 2e-4
+    with pytest.raises(Exception):
+        ops.sim_fwd_tokens(tok.to(DEV), g, b, q16, 1.0, text_raw=text.to(DEV))
+
+
 def test_sim_fwd_dot_mode():
     """sim_op='dot' (the RadZeroLoss constructor default, losses.py:45, 214-215)."""
     B, N, L = 2, 7, 150
