@@ -26,7 +26,11 @@ constexpr int kMinMaxSplit = 16;              // partial (min, max) pairs per im
 
 struct Taps {        // one pass: for output index o, source window [xmin[o], xmin[o] + cnt[o]) and its weights
   int* xmin; int* cnt; int* w; int ksize;
+  // ksize <= 12: the weights again as byte planes for dp4a, 9 words per output: planes 0 / 1 (bits 0-7 / 8-15,
+  // unsigned) and 2 (bits 16-23, signed) of taps [4g, 4g + 4), g = 0..2:  w = p0 + 256 p1 + 65536 p2 exactly
+  unsigned* planes;
 };
+constexpr int kPlaneTaps = 12;
 
 __host__ __device__ inline int pil_ksize(int in_size, int out_size) {
   double scale = (double)in_size / (double)out_size;
@@ -85,6 +89,18 @@ __global__ void pp_coeff_kernel(Taps th, int w_in, int w_out, Taps tv, int h_in,
     }
     t.xmin[xx] = lo;
     t.cnt[xx] = n;
+    if (t.ksize <= kPlaneTaps) {
+      for (int pl = 0; pl < 3; ++pl)
+        for (int g = 0; g < 3; ++g) {
+          unsigned word = 0;
+          for (int i = 0; i < 4; ++i) {
+            const int k = 4 * g + i;
+            const int wv = k < t.ksize ? wk[k] : 0;
+            word |= (unsigned)((wv >> (8 * pl)) & 0xff) << (8 * i);
+          }
+          t.planes[(long long)xx * 9 + pl * 3 + g] = word;
+        }
+    }
   }
 }
 
@@ -195,7 +211,7 @@ __device__ __forceinline__ uint8_t stretch8(float v, float a, float b) {
 // row is padded by ksize bytes so the taps stay in bounds).
 template <typename T>
 __device__ __forceinline__ void stretch_row(const T* __restrict__ src, int n_el, int W, int Wp, int C, float a,
-                                            float b, uint8_t* srow, int lane) {
+                                            float b, uint8_t* srow, int lane) {   // Wp = channel stride in srow
   constexpr int kVec = 16 / (int)sizeof(T);
   const bool vec = C == 1 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (n_el % kVec) == 0;
   if (vec) {
@@ -280,6 +296,83 @@ pp_horizontal_kernel(const T* __restrict__ raw, int H, int W, int C, const doubl
   }
 }
 
+__device__ __forceinline__ int dp4a_uu(unsigned a, unsigned b, int c) {
+  int d;
+  asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp4a_us(unsigned a, unsigned b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// Horizontal pass for windows of at most 12 taps (down-sampling by up to 2.75: the chest-X-ray case).  A CTA
+// stretches a band of kBandH rows to uint8 in shared memory; thread t then owns output columns t, t + 256, ...
+// for the whole band: its window start and its nine weight words (byte planes, see Taps) stay in registers,
+// a pixel is four aligned 32-bit loads, three funnel shifts and nine dp4a -- 4 + 12 instead of 18 + 9 load and
+// multiply instructions, with the same 32-bit accumulator bit for bit (the planes recombine modulo 2^32).
+constexpr int kBandH = 16;
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+pp_horizontal_dp4a_kernel(const T* __restrict__ raw, int H, int W, int C, const double* __restrict__ part,
+                          Taps t, int w_out, int pitch, uint8_t* __restrict__ tmp) {
+  extern __shared__ __align__(16) uint8_t hs[];      // [C][kBandH][Wp]
+  const int img = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Wp = (W + 16 + 15) & ~15;                // a 16-byte window may start at the last pixel
+  const int y0 = blockIdx.x * kBandH;
+  const int rows = min(kBandH, H - y0);
+  for (int i = threadIdx.x * 16; i < C * kBandH * Wp; i += kThreads * 16)
+    *reinterpret_cast<uint4*>(hs + i) = make_uint4(0u, 0u, 0u, 0u);
+  float a, b;
+  {
+    double lo = DBL_MAX, hi = -DBL_MAX;
+    if (lane < kMinMaxSplit) {
+      lo = part[((long long)img * kMinMaxSplit + lane) * 2 + 0];
+      hi = part[((long long)img * kMinMaxSplit + lane) * 2 + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    // cv::normalize, NORM_MINMAX: scale = (255 - 0) * (1 / (smax - smin)), shift = 0 - smin * scale
+    const double scale = __dmul_rn(255.0, (hi - lo > DBL_EPSILON) ? __ddiv_rn(1.0, __dsub_rn(hi, lo)) : 0.0);
+    const double shift = __dsub_rn(0.0, __dmul_rn(lo, scale));
+    a = (float)scale;
+    b = (float)shift;
+  }
+  __syncthreads();
+  const int n_el = W * C;
+  for (int r = warp; r < rows; r += kThreads / 32)
+    stretch_row<T>(raw + ((long long)img * H + y0 + r) * n_el, n_el, W, kBandH * Wp, C, a, b, hs + r * Wp, lane);
+  __syncthreads();
+  for (int xo = threadIdx.x; xo < w_out; xo += kThreads) {
+    const int xm = __ldg(t.xmin + xo);
+    const unsigned* pw = t.planes + (long long)xo * 9;
+    unsigned w0[3], w1[3], w2[3];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) { w0[g] = __ldg(pw + g); w1[g] = __ldg(pw + 3 + g); w2[g] = __ldg(pw + 6 + g); }
+    const int al = xm & ~3;
+    const unsigned sh = 8u * (unsigned)(xm & 3);
+    for (int c = 0; c < C; ++c) {
+      const uint8_t* sc = hs + (size_t)c * kBandH * Wp + al;
+      uint8_t* dst = tmp + (((long long)img * C + c) * H + y0) * pitch + xo;
+#pragma unroll 4
+      for (int r = 0; r < rows; ++r) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(sc + r * Wp);
+        const uint32_t q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+        const uint32_t s0 = __funnelshift_r(q0, q1, sh), s1 = __funnelshift_r(q1, q2, sh), s2 = __funnelshift_r(q2, q3, sh);
+        const int a0 = dp4a_uu(s2, w0[2], dp4a_uu(s1, w0[1], dp4a_uu(s0, w0[0], 1 << (kPrecisionBits - 1))));
+        const int a1 = dp4a_uu(s2, w1[2], dp4a_uu(s1, w1[1], dp4a_uu(s0, w1[0], 0)));
+        const int a2 = dp4a_us(s2, w2[2], dp4a_us(s1, w2[1], dp4a_us(s0, w2[0], 0)));
+        const int acc = (int)((unsigned)a0 + ((unsigned)a1 << 8) + ((unsigned)a2 << 16));
+        dst[(long long)r * pitch] = clip8(acc);
+      }
+    }
+  }
+}
+
 struct NormParams { float mean[3], std[3]; double rescale; };
 
 template <typename TOut> __device__ __forceinline__ TOut to_out(float v);
@@ -349,7 +442,7 @@ Plan make_plan(int images, int H, int W, int C, int h_out, int w_out) {
   p.pitch = (w_out + 15) / 16 * 16;
   size_t o = 0;
   p.off_part = o; o += (size_t)images * kMinMaxSplit * 2 * sizeof(double);
-  p.off_taps = o; o += ((size_t)w_out * (2 + p.ks_h) + (size_t)h_out * (2 + p.ks_v)) * sizeof(int);
+  p.off_taps = o; o += ((size_t)w_out * (2 + p.ks_h + 9) + (size_t)h_out * (2 + p.ks_v + 9)) * sizeof(int);
   o = (o + 255) / 256 * 256;
   p.off_tmp = o; o += (size_t)images * C * H * p.pitch;
   p.total = o;
@@ -364,7 +457,9 @@ int run(const T* raw, int images, int H, int W, int C, int h_out, int w_out, con
   int* ti = reinterpret_cast<int*>(ws + pl.off_taps);
   Taps th, tv;
   th.xmin = ti; ti += w_out; th.cnt = ti; ti += w_out; th.w = ti; ti += (size_t)w_out * pl.ks_h; th.ksize = pl.ks_h;
-  tv.xmin = ti; ti += h_out; tv.cnt = ti; ti += h_out; tv.w = ti; tv.ksize = pl.ks_v;
+  th.planes = reinterpret_cast<unsigned*>(ti); ti += (size_t)w_out * 9;
+  tv.xmin = ti; ti += h_out; tv.cnt = ti; ti += h_out; tv.w = ti; ti += (size_t)h_out * pl.ks_v; tv.ksize = pl.ks_v;
+  tv.planes = reinterpret_cast<unsigned*>(ti);
   uint8_t* tmp = ws + pl.off_tmp;
   pp_coeff_kernel<<<2, kThreads, 0, s>>>(th, W, w_out, tv, H, h_out);
   RZ_LAUNCH_OK();
@@ -372,6 +467,14 @@ int run(const T* raw, int images, int H, int W, int C, int h_out, int w_out, con
   RZ_LAUNCH_OK();
   // horizontal: one warp per row at a time, `rows_h` rows per warp; shared memory = tap table + one stretched
   // (padded) row per warp
+  const size_t smem_f = (size_t)C * kBandH * ((W + 16 + 15) & ~15);
+  if (pl.ks_h <= kPlaneTaps && smem_f <= 200 * 1024 && !getenv("RZ_PP_GENERIC_H")) {
+    if (smem_f > 48 * 1024)
+      RZ_CUDA_OK(cudaFuncSetAttribute(pp_horizontal_dp4a_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+    pp_horizontal_dp4a_kernel<T><<<dim3((H + kBandH - 1) / kBandH, images), kThreads, smem_f, s>>>(
+        raw, H, W, C, part, th, w_out, pl.pitch, tmp);
+    RZ_LAUNCH_OK();
+  } else {
   const int rows_h = 8;
   const int warps = kThreads / 32;
   const size_t tab = (((size_t)w_out * (1 + pl.ks_h) * 4 + 15) & ~(size_t)15);
@@ -384,6 +487,7 @@ int run(const T* raw, int images, int H, int W, int C, int h_out, int w_out, con
   pp_horizontal_kernel<T><<<dim3((H + rows_h * warps - 1) / (rows_h * warps), images), kThreads, smem, s>>>(
       raw, H, W, C, part, th, w_out, pl.pitch, tmp, rows_h, taps_in_smem);
   RZ_LAUNCH_OK();
+  }
   // vertical: `rows_v` output rows per CTA share a band of at most ceil(rows_v * H / h_out) + ksize source rows
   const int rows_v = 8;
   const int band_cap = (int)(((long long)rows_v * H + h_out - 1) / h_out) + pl.ks_v + 2;
