@@ -234,3 +234,31 @@ def test_many_images_persistent_loop():
     want = _oracle(tok, text, gamma, beta)
     assert (out["z"].cpu().double() - want["z"]).abs().max() < 2e-4
     assert (two["z"].cpu().double() - want["z"]).abs().max() < 2e-4
+
+
+def test_known_answers_on_the_kernels():
+    """SURVEY section 8c's self-made KATs through the CUDA path (the oracle's copies: test_oracle_golden.py)."""
+    from radzero_b200 import losses
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(3, 768, generator=g)
+    one = torch.randn(1, 1, 768, generator=g)
+    sl = losses.SimilarityLogit("cos")
+    tau = torch.tensor(0.07)
+    with torch.no_grad():
+        # (i) all tokens identical -> Z = cos(q, k);  (ii) scores within +-1/tau
+        z, sc = sl(q.to(DEV), one.expand(2, 137, 768).contiguous().to(DEV), need_attn_weights=True, temperature=tau)
+        cos = torch.nn.functional.cosine_similarity(q.double(), one[0].double().expand(3, 768), dim=-1)
+        assert (z[:, 0].cpu().double() - cos).abs().max() < 3e-4
+        assert sc[0].abs().max().item() <= 1 / 0.07 + 2e-3
+        # (iv) permuting the images permutes the columns
+        tok = torch.randn(5, 300, 768, generator=g)
+        perm = torch.tensor([2, 0, 4, 1, 3])
+        z1, _ = sl(q.to(DEV), tok.to(DEV), temperature=tau)
+        z2, _ = sl(q.to(DEV), tok[perm].contiguous().to(DEV), temperature=tau)
+        # (not bit for bit: the stream-K cut points and the lazy softmax references move with the image order)
+        assert (z1[:, perm] - z2).abs().max().item() < 1e-4
+    # (iii) one sentence per image, perfectly separated logits -> loss = log(1 + (B - 1) e^{-2/tau})
+    B = 4
+    zi = (2 * torch.eye(B) - 1).to(DEV)
+    loss = losses.multi_positive_nce_loss(zi, torch.arange(B, device=DEV), temperature=0.07)
+    assert abs(loss.item() - math.log(1 + (B - 1) * math.exp(-2 / 0.07))) < 1e-6
