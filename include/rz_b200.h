@@ -208,12 +208,16 @@ int rz_prep_rows_bwd(const void* x, int dtype, const float* gamma, const float* 
  *            RZ_UP_SIGMOID  out fp32 = sigmoid(score)
  *            RZ_UP_MASK     out uint8 = sigmoid(score) > threshold
  *            RZ_UP_ARGMAX   out int64 [maps,2] = (x, y) of the first global maximum; no map
+ *            RZ_UP_MASK_BITS out uint32 [maps,out_h,ceil(out_w/32)]: the same mask, one bit per pixel (bit x%32 of
+ *                           word x/32, padding bits zero) -- 131 072 masks of 518 x 518 (BASELINE config 5 at
+ *                           pixel level) are 4.6 GB instead of 35 GB
  *                           is written
  */
 #define RZ_UP_RAW 0
 #define RZ_UP_SIGMOID 1
 #define RZ_UP_MASK 2
 #define RZ_UP_ARGMAX 3
+#define RZ_UP_MASK_BITS 4
 int rz_upsample_maps(const float* scores, long long map_stride, int maps, int grid,
                      int out_h, int out_w, int interp_h, int interp_w, int off_y, int off_x,
                      float fill, int mode, float threshold, void* out, void* stream);

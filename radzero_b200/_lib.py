@@ -16,7 +16,7 @@ HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "rz_b200.h")
 
 RZ_OK = 0
 RZ_F32, RZ_BF16, RZ_F16 = 0, 1, 2
-RZ_UP_RAW, RZ_UP_SIGMOID, RZ_UP_MASK, RZ_UP_ARGMAX = 0, 1, 2, 3
+RZ_UP_RAW, RZ_UP_SIGMOID, RZ_UP_MASK, RZ_UP_ARGMAX, RZ_UP_MASK_BITS = 0, 1, 2, 3, 4
 RZ_LIN_BIAS, RZ_LIN_GELU, RZ_LIN_RESIDUAL, RZ_LIN_RESIDUAL_F16 = 0, 1, 2, 3
 RZ_IMG_U8, RZ_IMG_U16, RZ_IMG_I16, RZ_IMG_I32, RZ_IMG_F32 = 0, 1, 2, 3, 4
 

@@ -121,6 +121,14 @@ upsample_kernel(UpParams p) {
   const float* g = p.scores + (long long)map * p.map_stride;
 
   band_setup<MODE == RZ_UP_SIGMOID>(p, g, G, wpad, y_first, rows_here, xtab, rowbuf, gbuf);
+  // RZ_UP_MASK_BITS: the band's mask as a bitmap in shared memory ([kBand][words per row]); threads OR their
+  // V bits in, the band then leaves as whole 32-bit words (32 pixels per word instead of 32 bytes)
+  const int wpw = (p.out_w + 31) >> 5;
+  unsigned int* bitrows = reinterpret_cast<unsigned int*>(gbuf + G * G);
+  if constexpr (MODE == RZ_UP_MASK_BITS) {
+    for (int i = threadIdx.x; i < kBand * wpw; i += kThreads) bitrows[i] = 0u;
+    __syncthreads();
+  }
 
   // work item = V adjacent canvas columns x kRowGroup consecutive rows: the x-table entry is
   // loaded once per item and the row loop is unrolled with immediate shared-memory offsets
@@ -196,6 +204,12 @@ upsample_kernel(UpParams p) {
         } else {
           out[0] = val[0] > p.thr_logit ? 1 : 0;
         }
+      } else if constexpr (MODE == RZ_UP_MASK_BITS) {
+        unsigned int nib = 0;
+#pragma unroll
+        for (int k = 0; k < V; ++k) nib |= (xv * V + k < p.out_w && val[k] > p.thr_logit ? 1u : 0u) << k;
+        const int x0 = xv * V;                               // a multiple of V <= 4: the bits stay in one word
+        if (nib) atomicOr(bitrows + (grp * kRowGroup + rr) * wpw + (x0 >> 5), nib << (x0 & 31));
       } else {  // ARGMAX
 #pragma unroll
         for (int k = 0; k < V; ++k) {
@@ -207,6 +221,11 @@ upsample_kernel(UpParams p) {
     }
     xv += kThreads;
     while (xv >= vec_per_row) { xv -= vec_per_row; ++grp; }
+  }
+  if constexpr (MODE == RZ_UP_MASK_BITS) {
+    __syncthreads();
+    unsigned int* out = static_cast<unsigned int*>(p.out) + ((long long)map * p.out_h + y_first) * wpw;
+    for (int i = threadIdx.x; i < rows_here * wpw; i += kThreads) __stcs(out + i, bitrows[i]);
   }
   if constexpr (MODE == RZ_UP_ARGMAX) {
 #pragma unroll
@@ -331,7 +350,8 @@ template <int MODE, int V>
 int launch_v(const UpParams& p, int maps, cudaStream_t s) {
   dim3 grid((p.out_h + kBand - 1) / kBand, maps), block(kThreads);
   const int wpad = (p.out_w + V - 1) / V * V;
-  const size_t smem = (size_t)(2 * wpad + 2 * kBand * kRowStride + p.grid * p.grid) * sizeof(float);
+  const size_t smem = (size_t)(2 * wpad + 2 * kBand * kRowStride + p.grid * p.grid +
+                               (MODE == RZ_UP_MASK_BITS ? kBand * ((p.out_w + 31) / 32) : 0)) * sizeof(float);
   // PLAIN: the resized grid covers the canvas exactly (BlipImageProcessor branch) -- no fill
   const bool plain = p.off_x == 0 && p.off_y == 0 && p.interp_h == p.out_h && p.interp_w == p.out_w;
   if (plain) {
@@ -354,6 +374,10 @@ int launch_mode(const UpParams& p, int maps, cudaStream_t s) {
   // vector stores need every canvas row to start on a vector boundary
   const uintptr_t base = reinterpret_cast<uintptr_t>(p.out);
   const int esz = (MODE == RZ_UP_MASK) ? 1 : 4;
+  if (MODE == RZ_UP_MASK_BITS) {      // no per-pixel stores: only the column padding of the item grid matters
+    if (base % 4) return RZ_ERR_ALIGNMENT;
+    return launch_v<MODE, 4>(p, maps, s);
+  }
   if (p.out_w % 4 == 0 && base % (4 * esz) == 0) return launch_v<MODE, 4>(p, maps, s);
   if (p.out_w % 2 == 0 && base % (2 * esz) == 0) return launch_v<MODE, 2>(p, maps, s);
   return launch_v<MODE, 1>(p, maps, s);
@@ -390,6 +414,7 @@ extern "C" int rz_upsample_maps(const float* scores, long long map_stride, int m
     case RZ_UP_RAW: return launch_mode<RZ_UP_RAW>(p, maps, s);
     case RZ_UP_SIGMOID: return launch_mode<RZ_UP_SIGMOID>(p, maps, s);
     case RZ_UP_MASK: return launch_mode<RZ_UP_MASK>(p, maps, s);
+    case RZ_UP_MASK_BITS: return launch_mode<RZ_UP_MASK_BITS>(p, maps, s);
     case RZ_UP_ARGMAX: {
       unsigned long long* keys = static_cast<unsigned long long*>(out);
       RZ_CUDA_OK(cudaMemsetAsync(keys, 0, 2 * sizeof(unsigned long long) * (size_t)maps, s));

@@ -66,12 +66,14 @@ def interpolate_similarity_scores(similarity_scores: torch.Tensor, origin_size, 
     """Drop-in for the reference function: ``similarity_scores`` (P*P,) -> (1, H, W).
 
     Extension: a 2-d ``(M, P*P)`` input upsamples M maps in one launch and returns
-    ``(M, H, W)``; ``mode`` in {"raw", "sigmoid", "mask"} fuses the consumer
+    ``(M, H, W)``; ``mode`` in {"raw", "sigmoid", "mask", "mask_bits"} fuses the consumer ("mask_bits": one bit per pixel,
+    ``(M, H, ceil(W / 32))`` int32 -- what a 128 x 1024 open-vocabulary sweep can afford to keep)
     (torch.sigmoid, segmentation_utils.py:225; ``> t``, :258).
     """
     kind = processor_kind(image_processor)
     kw = interpolate_params(origin_size, kind)
-    m = {"raw": _lib.RZ_UP_RAW, "sigmoid": _lib.RZ_UP_SIGMOID, "mask": _lib.RZ_UP_MASK}[mode]
+    m = {"raw": _lib.RZ_UP_RAW, "sigmoid": _lib.RZ_UP_SIGMOID, "mask": _lib.RZ_UP_MASK,
+         "mask_bits": _lib.RZ_UP_MASK_BITS}[mode]
     s = similarity_scores
     out = ops.upsample_maps(s.float(), (int(origin_size[0]), int(origin_size[1])), mode=m,
                             threshold=threshold, **kw)

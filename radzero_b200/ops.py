@@ -354,7 +354,8 @@ def _as_maps(t: torch.Tensor) -> torch.Tensor:
 def upsample_maps(scores: torch.Tensor, out_hw: Tuple[int, int], *, mode: int = _lib.RZ_UP_RAW,
                   interp_hw: Optional[Tuple[int, int]] = None, offset: Tuple[int, int] = (0, 0),
                   fill: float = -999.0, threshold: float = 0.5, grid: Optional[int] = None):
-    """Upsample ``scores`` (maps, grid*grid) fp32 -> (maps, H, W) (or (maps, 2) for argmax)."""
+    """Upsample ``scores`` (maps, grid*grid) fp32 -> (maps, H, W) (or (maps, 2) for argmax, or the bit-packed
+    mask (maps, H, ceil(W / 32)) int32 for RZ_UP_MASK_BITS: bit x % 32 of word x // 32)."""
     _need_cuda(scores)
     if scores.dtype != torch.float32:
         raise RzError("scores must be fp32")
@@ -369,6 +370,8 @@ def upsample_maps(scores: torch.Tensor, out_hw: Tuple[int, int], *, mode: int = 
         out = torch.empty((maps, H, W), dtype=torch.float32, device=scores.device)
     elif mode == _lib.RZ_UP_MASK:
         out = torch.empty((maps, H, W), dtype=torch.uint8, device=scores.device)
+    elif mode == _lib.RZ_UP_MASK_BITS:
+        out = torch.empty((maps, H, (W + 31) // 32), dtype=torch.int32, device=scores.device)
     elif mode == _lib.RZ_UP_ARGMAX:
         out = torch.empty((maps, 2), dtype=torch.int64, device=scores.device)
     else:

@@ -251,3 +251,24 @@ def test_group_map_from_counts(n_images, first):
     want = np.repeat(np.arange(first, first + n_images, dtype=np.int64), counts)
     assert np.array_equal(got, want)
     assert ops.group_map_from_counts([0, 0], 0, "cuda").numel() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,kind", [((518, 518), "blip"), ((300, 417), "blip"), ((64, 80), "bit"), ((1024, 1024), "blip"),
+                                       ((37, 33), "blip")])
+def test_upsample_bit_packed_mask(size, kind):
+    """RZ_UP_MASK_BITS: the thresholded mask with one bit per pixel (bit x % 32 of word x // 32, padding bits
+    zero) equals the byte mask of RZ_UP_MASK (sigmoid(score) > t, segmentation_utils.py:225, 258)."""
+    import numpy as np
+    from radzero_b200 import inference, ops, _lib
+    g = torch.Generator().manual_seed(size[0] + size[1])
+    scores = torch.randn(5, 37 * 37, generator=g).cuda() * 3
+    kw = inference.interpolate_params(size, kind)
+    for thr in (0.5, 0.7, 0.0, 1.0):
+        byte = ops.upsample_maps(scores, size, mode=_lib.RZ_UP_MASK, threshold=thr, **kw).cpu().numpy()
+        bits = ops.upsample_maps(scores, size, mode=_lib.RZ_UP_MASK_BITS, threshold=thr, **kw).cpu().numpy()
+        H, W = size
+        assert bits.shape == (5, H, (W + 31) // 32) and bits.dtype == np.int32
+        un = np.unpackbits(bits.view(np.uint8).reshape(5, H, -1), axis=-1, bitorder="little")
+        assert np.array_equal(un[:, :, :W], byte)
+        assert not un[:, :, W:].any()
