@@ -364,6 +364,35 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
       // as a converted token tile (kNB = kTokT rows, chunks kKChunk apart) -- instead of being prepared by a
       // launch of their own and fetched by TMA.  Rows >= N are zero.
       static_assert(kNB * 128 == kKChunk || kTokT != 16, "q tile = one 16-token tile");
+#if RZ_SMALL_RPW >= 2
+      // rows (warp, warp + kConv) together: both rows' loads are in flight before the arithmetic starts, the
+      // two dependent chains interleave, and gamma / beta are the register copies
+      static_assert(2 * kConv >= kNB, "two prompt rows per converter warp cover the tile");
+      {
+        const int r0 = warp - 8, r1 = r0 + kConv;
+        float v[2][24];
+#pragma unroll
+        for (int i = 0; i < 24; ++i) { v[0][i] = 0.f; v[1][i] = 0.f; }
+        if (r0 < p.N) rz::RowLoad<float>::load(p.text_raw + (long long)r0 * kD, lane, v[0]);
+        if (r1 < p.N) rz::RowLoad<float>::load(p.text_raw + (long long)r1 * kD, lane, v[1]);
+        rz::ln_l2_rows_packed<2>(v, g2, b2, ln, RZ_LN_EPS, RZ_L2_EPS, p.l2 != 0);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = h == 0 ? r0 : r1;
+          if (r >= kNB) continue;
+          uint8_t* tile = q_s + rz::sw128_offset((uint32_t)r, (uint32_t)(8 * (lane & 15))) + (lane >> 4) * (kNB * 128);
+#pragma unroll
+          for (int jj = 0; jj < 6; ++jj) {
+            uint2 o = make_uint2(0u, 0u);                   // rows >= N stay zero (not LN(0) = beta)
+            if (r < p.N) o = make_uint2(rz::pack_half2(v[h][4 * jj], v[h][4 * jj + 1]),
+                                        rz::pack_half2(v[h][4 * jj + 2], v[h][4 * jj + 3]));
+            *reinterpret_cast<uint2*>(tile + jj * (2 * kNB * 128)) = o;
+            if (blockIdx.x == 0 && r < p.N)                // the merge kernel reads the rows from global memory
+              *reinterpret_cast<uint2*>(p.q_out + (long long)r * kD + 4 * (lane + 32 * jj)) = o;
+          }
+        }
+      }
+#else
       for (int r = warp - 8; r < kNB; r += kConv) {
         float v[24];
 #pragma unroll
@@ -381,6 +410,7 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
             *reinterpret_cast<uint2*>(p.q_out + (long long)r * kD + 4 * (lane + 32 * jj)) = o;
         }
       }
+#endif
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->q_full);
