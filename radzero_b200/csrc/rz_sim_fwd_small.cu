@@ -434,10 +434,10 @@ sim_small_kernel(const __grid_constant__ CUtensorMap tokmap, const __grid_consta
       // every lane's loads must have RETURNED before the slot goes back to the TMA producer (see
       // lds_returned in rz_umma.cuh: the arrive can overtake loads still queued in the LSU)
 #pragma unroll
-      for (int h = 0; h < kRpw; h += 2)
-        lds_returned(smem_u32(&ctl->sink[warp - 8]), __float_as_uint(v[h][3]), __float_as_uint(v[h][11]),
-                     __float_as_uint(v[h][19]), __float_as_uint(v[h][23]), __float_as_uint(v[h + 1][3]),
-                     __float_as_uint(v[h + 1][11]), __float_as_uint(v[h + 1][19]), __float_as_uint(v[h + 1][23]));
+      for (int h = 0; h < kRpw; ++h)                       // one register of EVERY load of the row
+        lds_returned(smem_u32(&ctl->sink[warp - 8]), __float_as_uint(v[h][3]), __float_as_uint(v[h][7]),
+                     __float_as_uint(v[h][11]), __float_as_uint(v[h][15]), __float_as_uint(v[h][19]),
+                     __float_as_uint(v[h][23]));
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->ring_empty[slot]);
       rz::ln_l2_rows_packed<kRpw>(v, g2, b2, ln, RZ_LN_EPS, RZ_L2_EPS, p.l2 != 0);
