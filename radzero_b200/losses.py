@@ -394,8 +394,8 @@ class RadZeroLoss(nn.Module):
     def similarity_prob(self, text_features: torch.Tensor, vision_tokens: torch.Tensor) -> torch.Tensor:
         """similarity_prob (B, N) = sigmoid(Z^T / tau) only (zero-shot classification).  The
         temperatures are read from the parameters ON THE DEVICE and the ``/ tau`` + sigmoid run
-        in the kernel epilogue: no host synchronisation, two launches (prep of the prompts and
-        the fused kernel) for N <= 16."""
+        in the kernel epilogue: no host synchronisation; for N <= 16 fp32 prompts ONE fused kernel (the
+        prompts' LayerNorm + L2 run in its prologue) plus its merge launch."""
         tokens = vision_tokens if self.use_vision_cls_token else vision_tokens[:, 1:]
         gamma, beta = self._ln()
         l2 = self.sim_op == "cos"
