@@ -325,6 +325,10 @@ class RadZeroLoss(nn.Module):
         text = torch.cat(feats, dim=0)
         if not want_group_map:
             return text, None
+        counts = [int(f.size(0)) for f in feats]
+        if text.is_cuda and max(counts, default=0) <= 65535:
+            # written on the device from launch parameters: no copy-engine traffic on the compute stream
+            return text, ops.group_map_from_counts(counts, rank * b_local, text.device)
         return text, _index_tensor(group, text.device)
 
     def compute_text_features(self, key_phrases, forward_text_model, ddp_gather=True):
