@@ -510,9 +510,19 @@ def run_ours(args):
             torch.distributed.destroy_process_group()
         return
     if args.workload == "preprocess":
-        out = measure_preprocess(max(3, min(args.steps, 50)), world, rank, local, pk, cpu=not args.no_cpu)
+        k = max(3, min(args.steps, 50))
+        out = measure_preprocess(k, world, rank, local, pk, cpu=not args.no_cpu)
         if rank == 0:
-            print(json.dumps(out))
+            # the same line layout as the other workloads (each rank preprocesses its own 256 images)
+            line = {"metric": "preprocessed images/sec", "value": out["value"] * world, "unit": "images/s",
+                    "n_gpus": world, "steps": k, "warmup": 3, "ms_per_step": out["ms_per_step"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 -> f32",
+                    "data": "synthetic", "impl": "ours", "config": {"workload": out["workload"]},
+                    "gpu_launches": 4 * k,
+                    "e2e": {"value": out["e2e"] * world, "unit": "images/s", "h2d_bytes_per_step": 256 * 1024 * 1024,
+                            "d2h_bytes_per_step": 0, "note": out["e2e_note"]},
+                    "roofline": out["roofline"], "cpu_baseline": out.get("cpu_baseline")}
+            print(json.dumps(line))
         if world > 1:
             torch.distributed.destroy_process_group()
         return
