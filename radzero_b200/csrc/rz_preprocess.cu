@@ -307,6 +307,17 @@ __device__ __forceinline__ int dp4a_us(unsigned a, unsigned b, int c) {
   return d;
 }
 
+// one output pixel from a 16-byte aligned window: realign by `sh` bits, nine dp4a (three byte planes of the
+// weights), recombine modulo 2^32, round, shift, clip -- Pillow's 32-bit accumulator bit for bit
+__device__ __forceinline__ uint32_t tap12(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3, unsigned sh,
+                                          const unsigned (&w0)[3], const unsigned (&w1)[3], const unsigned (&w2)[3]) {
+  const uint32_t s0 = __funnelshift_r(q0, q1, sh), s1 = __funnelshift_r(q1, q2, sh), s2 = __funnelshift_r(q2, q3, sh);
+  const int a0 = dp4a_uu(s2, w0[2], dp4a_uu(s1, w0[1], dp4a_uu(s0, w0[0], 1 << (kPrecisionBits - 1))));
+  const int a1 = dp4a_uu(s2, w1[2], dp4a_uu(s1, w1[1], dp4a_uu(s0, w1[0], 0)));
+  const int a2 = dp4a_us(s2, w2[2], dp4a_us(s1, w2[1], dp4a_us(s0, w2[0], 0)));
+  return (uint32_t)clip8((int)((unsigned)a0 + ((unsigned)a1 << 8) + ((unsigned)a2 << 16)));
+}
+
 // Horizontal pass for windows of at most 12 taps (down-sampling by up to 2.75: the chest-X-ray case).  A CTA
 // stretches a band of kBandH rows to uint8 in shared memory; thread t then owns output columns t, t + 256, ...
 // for the whole band: its window start and its nine weight words (byte planes, see Taps) stay in registers,
@@ -316,7 +327,10 @@ constexpr int kBandH = 16;
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 pp_horizontal_dp4a_kernel(const T* __restrict__ raw, int H, int W, int C, const double* __restrict__ part,
-                          Taps t, int w_out, int pitch, uint8_t* __restrict__ tmp) {
+                          Taps t, int w_out, int pitch, uint8_t* __restrict__ tmp, int Hp) {
+  // Hp > 0: the intermediate is written TRANSPOSED, [image][channel][output column][Hp source rows] -- a
+  // thread's 16 band rows of one column are one 16-byte store, and the vertical pass finds a column's taps in
+  // consecutive bytes (pp_vertical_dp4a_kernel).  Hp = 0: row-major [image][channel][row][pitch].
   extern __shared__ __align__(16) uint8_t hs[];      // [C][kBandH][Wp]
   const int img = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Wp = (W + 16 + 15) & ~15;                // a 16-byte window may start at the last pixel
@@ -357,17 +371,24 @@ pp_horizontal_dp4a_kernel(const T* __restrict__ raw, int H, int W, int C, const 
     const unsigned sh = 8u * (unsigned)(xm & 3);
     for (int c = 0; c < C; ++c) {
       const uint8_t* sc = hs + (size_t)c * kBandH * Wp + al;
-      uint8_t* dst = tmp + (((long long)img * C + c) * H + y0) * pitch + xo;
+      if (Hp > 0) {
+        uint32_t packed[kBandH / 4];
+#pragma unroll
+        for (int r = 0; r < kBandH; ++r) {               // rows past the image read the zeroed band: result 0
+          const uint32_t* q = reinterpret_cast<const uint32_t*>(sc + r * Wp);
+          const uint32_t q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+          const uint32_t v = tap12(q0, q1, q2, q3, sh, w0, w1, w2);
+          packed[r >> 2] = (r & 3) == 0 ? v : (packed[r >> 2] | (v << (8 * (r & 3))));
+        }
+        uint8_t* dst = tmp + (((long long)img * C + c) * w_out + xo) * Hp + y0;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      } else {
+        uint8_t* dst = tmp + (((long long)img * C + c) * H + y0) * pitch + xo;
 #pragma unroll 4
-      for (int r = 0; r < rows; ++r) {
-        const uint32_t* q = reinterpret_cast<const uint32_t*>(sc + r * Wp);
-        const uint32_t q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
-        const uint32_t s0 = __funnelshift_r(q0, q1, sh), s1 = __funnelshift_r(q1, q2, sh), s2 = __funnelshift_r(q2, q3, sh);
-        const int a0 = dp4a_uu(s2, w0[2], dp4a_uu(s1, w0[1], dp4a_uu(s0, w0[0], 1 << (kPrecisionBits - 1))));
-        const int a1 = dp4a_uu(s2, w1[2], dp4a_uu(s1, w1[1], dp4a_uu(s0, w1[0], 0)));
-        const int a2 = dp4a_us(s2, w2[2], dp4a_us(s1, w2[1], dp4a_us(s0, w2[0], 0)));
-        const int acc = (int)((unsigned)a0 + ((unsigned)a1 << 8) + ((unsigned)a2 << 16));
-        dst[(long long)r * pitch] = clip8(acc);
+        for (int r = 0; r < rows; ++r) {
+          const uint32_t* q = reinterpret_cast<const uint32_t*>(sc + r * Wp);
+          dst[(long long)r * pitch] = (uint8_t)tap12(q[0], q[1], q[2], q[3], sh, w0, w1, w2);
+        }
       }
     }
   }
@@ -430,6 +451,82 @@ pp_vertical_kernel(const uint8_t* __restrict__ tmp, int H, int C, int pitch, Tap
   }
 }
 
+// Vertical pass over the TRANSPOSED intermediate (both windows <= 12 taps): a column's taps are consecutive
+// bytes, so a pixel is the dp4a tap of the horizontal pass; then the per-channel normalisation table.
+// (kernel below) CTA = (image, kRowBandV output rows, ALL columns): whole output rows are written by one CTA
+// within microseconds, so L2 sees complete lines (column stripes per CTA left half-written sectors behind).
+constexpr int kRowBandV = 16;
+__host__ __device__ inline int transposed_pitch(int H) { return (H + 64 + 15) & ~15; }   // kWinV bytes of slack
+constexpr int kWinV = 64;                            // staged bytes per column: the band's source window, 16-byte aligned
+template <typename TOut, int CH>
+__global__ void __launch_bounds__(512)
+pp_vertical_dp4a_kernel(const uint8_t* __restrict__ tmpT, int Hp, Taps t, int h_out, int w_out,
+                        NormParams np, TOut* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t vs[];      // [kRowBandV][12 words] tap table, then [CH][w_out][kWinS] windows
+  __shared__ float lut[3][256];
+  for (int i = threadIdx.x; i < 768; i += (int)blockDim.x) {
+    const int c = i >> 8, v = i & 255;
+    const float r = (float)__dmul_rn((double)v, np.rescale);
+    lut[c][v] = __fdiv_rn(__fsub_rn(r, np.mean[c]), np.std[c]);
+  }
+  constexpr int kWinS = kWinV + 4;                   // column pitch in shared memory: 17 words (odd) -> no bank conflicts
+  const int img = blockIdx.y, y0 = blockIdx.x * kRowBandV, y1 = min(h_out, y0 + kRowBandV);
+  uint32_t* tab = reinterpret_cast<uint32_t*>(vs);   // per band row: ymin (relative to the window), 9 plane words, pad
+  uint8_t* cols = vs + kRowBandV * 48;
+  const int b0 = __ldg(t.xmin + y0) & ~15;           // the window starts on a 16-byte boundary of the column
+  for (int i = threadIdx.x; i < CH * w_out * (kWinV / 16); i += (int)blockDim.x) {
+    const int cc = i >> 2, v = i & 3;                // cc = channel * w_out + column
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(tmpT + ((long long)img * CH * w_out + cc) * Hp + b0) + v);
+    uint32_t* d = reinterpret_cast<uint32_t*>(cols + (size_t)cc * kWinS + 16 * v);
+    d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+  }
+  for (int i = threadIdx.x; i < (y1 - y0) * 12; i += (int)blockDim.x) {
+    const int r = i / 12, k = i - r * 12, yo = y0 + r;
+    tab[i] = k == 0 ? (uint32_t)(__ldg(t.xmin + yo) - b0) : (k < 10 ? __ldg(t.planes + (long long)yo * 9 + k - 1) : 0u);
+  }
+  __syncthreads();
+  // warp = (block of 128 columns, row lane); lane l owns columns 128 cb + 32 k + l, k = 0..3: neighbouring lanes
+  // read neighbouring columns (pitch 17 words: conflict-free) and every store instruction writes 128
+  // consecutive bytes of one output row
+  const int nblk = (w_out + 127) >> 7;
+  const int lane = threadIdx.x & 31;
+  for (int wi = threadIdx.x >> 5; wi < nblk * 2; wi += (int)blockDim.x >> 5) {
+    const int rl = wi >= nblk ? 1 : 0;                // row lane 0 / 1: rows y0 + rl, y0 + rl + 2, ...
+    const int xb = (wi - rl * nblk) * 128 + lane;
+    const uint8_t* cbase = cols + (size_t)xb * kWinS;
+    for (int yo = y0 + rl; yo < y1; yo += 2) {
+      const uint32_t* trow = tab + (yo - y0) * 12;
+      const uint4 ta = *reinterpret_cast<const uint4*>(trow);
+      const uint4 tb = *reinterpret_cast<const uint4*>(trow + 4);
+      const uint2 tc = *reinterpret_cast<const uint2*>(trow + 8);
+      const unsigned w0[3] = {ta.y, ta.z, ta.w}, w1[3] = {tb.x, tb.y, tb.z}, w2[3] = {tb.w, tc.x, tc.y};
+      const int ym = (int)ta.x;
+      const uint8_t* win = cbase + (ym & ~3);
+      const unsigned sh = 8u * (unsigned)(ym & 3);
+      uint32_t px[CH][4];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          px[c][k] = 0u;
+          if (xb + 32 * k < w_out) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(win + ((size_t)c * w_out + 32 * k) * kWinS);
+            px[c][k] = tap12(q[0], q[1], q[2], q[3], sh, w0, w1, w2);
+          }
+        }
+      }
+      TOut* o = out + ((long long)img * 3 * h_out + yo) * w_out + xb;
+#pragma unroll
+      for (int c = 0; c < 3; ++c, o += (long long)h_out * w_out) {
+        const uint32_t* p4 = px[CH == 3 ? c : 0];    // convert_to_rgb replicates a grey plane
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (xb + 32 * k < w_out) o[32 * k] = to_out<TOut>(lut[c][p4[k]]);
+      }
+    }
+  }
+}
+
 struct Plan {
   int ks_h, ks_v, pitch;
   size_t off_part, off_taps, off_tmp, total;
@@ -444,7 +541,9 @@ Plan make_plan(int images, int H, int W, int C, int h_out, int w_out) {
   p.off_part = o; o += (size_t)images * kMinMaxSplit * 2 * sizeof(double);
   p.off_taps = o; o += ((size_t)w_out * (2 + p.ks_h + 9) + (size_t)h_out * (2 + p.ks_v + 9)) * sizeof(int);
   o = (o + 255) / 256 * 256;
-  p.off_tmp = o; o += (size_t)images * C * H * p.pitch;
+  const size_t row_major = (size_t)images * C * H * p.pitch;
+  const size_t transposed = (size_t)images * C * w_out * (size_t)((H + 64 + 15) & ~15);
+  p.off_tmp = o; o += row_major > transposed ? row_major : transposed;
   p.total = o;
   return p;
 }
@@ -468,11 +567,18 @@ int run(const T* raw, int images, int H, int W, int C, int h_out, int w_out, con
   // horizontal: one warp per row at a time, `rows_h` rows per warp; shared memory = tap table + one stretched
   // (padded) row per warp
   const size_t smem_f = (size_t)C * kBandH * ((W + 16 + 15) & ~15);
-  if (pl.ks_h <= kPlaneTaps && smem_f <= 200 * 1024 && !getenv("RZ_PP_GENERIC_H")) {
+  const int Hp = transposed_pitch(H);
+  const size_t smem_vt = (size_t)C * w_out * (kWinV + 4) + (size_t)kRowBandV * 48;
+  // the source window of kRowBandV output rows (+ 15 bytes of alignment slack + a 16-byte tap read) fits kWinV
+  const bool win_ok = (long long)(kRowBandV - 1) * H / h_out + 2 + 15 + 16 <= kWinV;
+  const bool fast_h = pl.ks_h <= kPlaneTaps && smem_f <= 200 * 1024 && !getenv("RZ_PP_GENERIC_H");
+  // both windows short: transposed intermediate + dp4a vertical pass
+  const bool fast_v = fast_h && pl.ks_v <= kPlaneTaps && win_ok && smem_vt <= 200 * 1024 && !getenv("RZ_PP_GENERIC_V");
+  if (fast_h) {
     if (smem_f > 48 * 1024)
       RZ_CUDA_OK(cudaFuncSetAttribute(pp_horizontal_dp4a_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
     pp_horizontal_dp4a_kernel<T><<<dim3((H + kBandH - 1) / kBandH, images), kThreads, smem_f, s>>>(
-        raw, H, W, C, part, th, w_out, pl.pitch, tmp);
+        raw, H, W, C, part, th, w_out, pl.pitch, tmp, fast_v ? Hp : 0);
     RZ_LAUNCH_OK();
   } else {
   const int rows_h = 8;
@@ -487,6 +593,24 @@ int run(const T* raw, int images, int H, int W, int C, int h_out, int w_out, con
   pp_horizontal_kernel<T><<<dim3((H + rows_h * warps - 1) / (rows_h * warps), images), kThreads, smem, s>>>(
       raw, H, W, C, part, th, w_out, pl.pitch, tmp, rows_h, taps_in_smem);
   RZ_LAUNCH_OK();
+  }
+  if (fast_v) {
+    const dim3 gt((h_out + kRowBandV - 1) / kRowBandV, images);
+    const int vwarps = 2 * ((w_out + 127) / 128);          // one warp per (128-column block, row lane)
+    const int vthreads = 32 * (vwarps > 16 ? 16 : vwarps);
+#define RZ_PP_LAUNCH_V(TO, CHN)                                                                                   \
+  do {                                                                                                            \
+    RZ_CUDA_OK(cudaFuncSetAttribute(pp_vertical_dp4a_kernel<TO, CHN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)smem_vt));                                                               \
+    pp_vertical_dp4a_kernel<TO, CHN><<<gt, vthreads, smem_vt, s>>>(tmp, Hp, tv, h_out, w_out, np, (TO*)out);      \
+  } while (0)
+    if (out_dtype == RZ_F32) { if (C == 1) RZ_PP_LAUNCH_V(float, 1); else RZ_PP_LAUNCH_V(float, 3); }
+    else if (out_dtype == RZ_F16) { if (C == 1) RZ_PP_LAUNCH_V(__half, 1); else RZ_PP_LAUNCH_V(__half, 3); }
+    else { if (C == 1) RZ_PP_LAUNCH_V(__nv_bfloat16, 1); else RZ_PP_LAUNCH_V(__nv_bfloat16, 3); }
+#undef RZ_PP_LAUNCH_V
+    RZ_LAUNCH_OK();
+    rz_count_launch(4);
+    return RZ_OK;
   }
   // vertical: `rows_v` output rows per CTA share a band of at most ceil(rows_v * H / h_out) + ksize source rows
   const int rows_v = 8;
