@@ -455,6 +455,10 @@ pp_vertical_kernel(const uint8_t* __restrict__ tmp, int H, int C, int pitch, Tap
 // bytes, so a pixel is the dp4a tap of the horizontal pass; then the per-channel normalisation table.
 // (kernel below) CTA = (image, kRowBandV output rows, ALL columns): whole output rows are written by one CTA
 // within microseconds, so L2 sees complete lines (column stripes per CTA left half-written sectors behind).
+#ifndef RZ_PP_ROWLANES
+#define RZ_PP_ROWLANES 2
+#endif
+constexpr int kRowLanesV = RZ_PP_ROWLANES;
 constexpr int kRowBandV = 16;
 __host__ __device__ inline int transposed_pitch(int H) { return (H + 64 + 15) & ~15; }   // kWinV bytes of slack
 constexpr int kWinV = 64;                            // staged bytes per column: the band's source window, 16-byte aligned
@@ -490,11 +494,11 @@ pp_vertical_dp4a_kernel(const uint8_t* __restrict__ tmpT, int Hp, Taps t, int h_
   // consecutive bytes of one output row
   const int nblk = (w_out + 127) >> 7;
   const int lane = threadIdx.x & 31;
-  for (int wi = threadIdx.x >> 5; wi < nblk * 2; wi += (int)blockDim.x >> 5) {
-    const int rl = wi >= nblk ? 1 : 0;                // row lane 0 / 1: rows y0 + rl, y0 + rl + 2, ...
+  for (int wi = threadIdx.x >> 5; wi < nblk * kRowLanesV; wi += (int)blockDim.x >> 5) {
+    const int rl = wi / nblk;                         // row lane: rows y0 + rl, y0 + rl + kRowLanesV, ...
     const int xb = (wi - rl * nblk) * 128 + lane;
     const uint8_t* cbase = cols + (size_t)xb * kWinS;
-    for (int yo = y0 + rl; yo < y1; yo += 2) {
+    for (int yo = y0 + rl; yo < y1; yo += kRowLanesV) {
       const uint32_t* trow = tab + (yo - y0) * 12;
       const uint4 ta = *reinterpret_cast<const uint4*>(trow);
       const uint4 tb = *reinterpret_cast<const uint4*>(trow + 4);
@@ -596,7 +600,7 @@ int run(const T* raw, int images, int H, int W, int C, int h_out, int w_out, con
   }
   if (fast_v) {
     const dim3 gt((h_out + kRowBandV - 1) / kRowBandV, images);
-    const int vwarps = 2 * ((w_out + 127) / 128);          // one warp per (128-column block, row lane)
+    const int vwarps = kRowLanesV * ((w_out + 127) / 128);   // one warp per (128-column block, row lane)
     const int vthreads = 32 * (vwarps > 16 ? 16 : vwarps);
 #define RZ_PP_LAUNCH_V(TO, CHN)                                                                                   \
   do {                                                                                                            \
