@@ -456,14 +456,17 @@ pp_vertical_kernel(const uint8_t* __restrict__ tmp, int H, int C, int pitch, Tap
 // (kernel below) CTA = (image, kRowBandV output rows, ALL columns): whole output rows are written by one CTA
 // within microseconds, so L2 sees complete lines (column stripes per CTA left half-written sectors behind).
 #ifndef RZ_PP_ROWLANES
-#define RZ_PP_ROWLANES 2
+#define RZ_PP_ROWLANES 4
 #endif
 constexpr int kRowLanesV = RZ_PP_ROWLANES;
 constexpr int kRowBandV = 16;
 __host__ __device__ inline int transposed_pitch(int H) { return (H + 64 + 15) & ~15; }   // kWinV bytes of slack
 constexpr int kWinV = 64;                            // staged bytes per column: the band's source window, 16-byte aligned
+#ifndef RZ_PP_VWARPS
+#define RZ_PP_VWARPS 16
+#endif
 template <typename TOut, int CH>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(32 * RZ_PP_VWARPS)
 pp_vertical_dp4a_kernel(const uint8_t* __restrict__ tmpT, int Hp, Taps t, int h_out, int w_out,
                         NormParams np, TOut* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t vs[];      // [kRowBandV][12 words] tap table, then [CH][w_out][kWinS] windows
@@ -601,7 +604,7 @@ int run(const T* raw, int images, int H, int W, int C, int h_out, int w_out, con
   if (fast_v) {
     const dim3 gt((h_out + kRowBandV - 1) / kRowBandV, images);
     const int vwarps = kRowLanesV * ((w_out + 127) / 128);   // one warp per (128-column block, row lane)
-    const int vthreads = 32 * (vwarps > 16 ? 16 : vwarps);
+    const int vthreads = 32 * (vwarps > RZ_PP_VWARPS ? RZ_PP_VWARPS : vwarps);
 #define RZ_PP_LAUNCH_V(TO, CHN)                                                                                   \
   do {                                                                                                            \
     RZ_CUDA_OK(cudaFuncSetAttribute(pp_vertical_dp4a_kernel<TO, CHN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
