@@ -11,6 +11,8 @@ CASES = {
     "padchest_i32": dict(shape=(2021, 2500), dtype="int32", hi=65535, size=(518, 518), seed=5),
     "float_identity_w": dict(shape=(600, 518), dtype="float32", hi=None, size=(518, 518), seed=6),
     "signed_i16": dict(shape=(512, 640), dtype="int16", hi=3000, size=(518, 518), seed=7),
+    "rgb_u8_mild": dict(shape=(600, 700, 3), dtype="uint8", hi=255, size=(518, 518), seed=10),   # short windows, 3 channels
+    "u16_tall": dict(shape=(1100, 640), dtype="uint16", hi=65535, size=(518, 320), seed=11),      # odd band edges
     "constant": dict(shape=(64, 64), dtype="uint8", hi=0, size=(37, 41), seed=8),
     "levels": dict(shape=(16, 16), dtype="uint8", hi=-1, size=(16, 16), seed=9, keep_pv=True),
 }
