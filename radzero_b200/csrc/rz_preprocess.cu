@@ -356,10 +356,32 @@ pp_horizontal_dp4a_kernel(const T* __restrict__ raw, int H, int W, int C, const 
     a = (float)scale;
     b = (float)shift;
   }
+  // 8-bit sources: the stretch has 256 possible inputs -- one table per CTA (the same stretch8, bit for bit)
+  // replaces a convert / FMA / round / clamp chain per pixel by a byte lookup
+  __shared__ uint8_t s8[256];
+  constexpr bool kByteSrc = sizeof(T) == 1;
+  if (kByteSrc) s8[threadIdx.x & 255] = stretch8((float)(threadIdx.x & 255), a, b);
   __syncthreads();
   const int n_el = W * C;
-  for (int r = warp; r < rows; r += kThreads / 32)
-    stretch_row<T>(raw + ((long long)img * H + y0 + r) * n_el, n_el, W, kBandH * Wp, C, a, b, hs + r * Wp, lane);
+  for (int r = warp; r < rows; r += kThreads / 32) {
+    const T* src = raw + ((long long)img * H + y0 + r) * n_el;
+    if (kByteSrc && C == 1 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (n_el & 15) == 0) {
+      const uint4* vp = reinterpret_cast<const uint4*>(src);
+      uint8_t* srow = hs + r * Wp;
+      for (int j = lane; j < n_el / 16; j += 32) {
+        const uint4 q = rz::ldg_stream_u4(vp + j);
+        const uint32_t in[4] = {q.x, q.y, q.z, q.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+          o[w] = (uint32_t)s8[in[w] & 255u] | ((uint32_t)s8[(in[w] >> 8) & 255u] << 8) |
+                 ((uint32_t)s8[(in[w] >> 16) & 255u] << 16) | ((uint32_t)s8[in[w] >> 24] << 24);
+        *reinterpret_cast<uint4*>(srow + 16 * j) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    } else {
+      stretch_row<T>(src, n_el, W, kBandH * Wp, C, a, b, hs + r * Wp, lane);
+    }
+  }
   __syncthreads();
   for (int xo = threadIdx.x; xo < w_out; xo += kThreads) {
     const int xm = __ldg(t.xmin + xo);
