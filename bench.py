@@ -261,13 +261,16 @@ def measure_inference(workload, steps, warmup, world, rank, local, pk):
         for _ in range(2):
             stage()
         torch.cuda.synchronize()
-        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ea.record()
-        for _ in range(reps):
-            stage()
-        eb.record()
-        torch.cuda.synchronize()
-        kt.append(ea.elapsed_time(eb) / reps)
+        best = float("inf")
+        for _ in range(3):                  # best of three averages: a clock dip in one window is not the kernel
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            for _ in range(reps):
+                stage()
+            eb.record()
+            torch.cuda.synchronize()
+            best = min(best, ea.elapsed_time(eb) / reps)
+        kt.append(best)
     del o, k16
     out_bytes = {"cls": B * N * 4, "seg": B * N * out_hw[0] * out_hw[1] * 4,
                  "openvocab": B * N * (L - 1) * 4 + B * N * 4}[workload]
