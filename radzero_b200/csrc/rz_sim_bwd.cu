@@ -512,17 +512,36 @@ struct PassK : PolicyBase {
   }
 };
 
-__global__ void sum_partials_kernel(const float* part, int n, float* out) {
+// fixed-order sum of n partials: kSumBlocks blocks sum contiguous slices (each thread a strided sub-sequence,
+// then a shared-memory tree), the last block to finish (ticket) adds the kSumBlocks slice sums in index order
+constexpr int kSumBlocks = 128;
+__global__ void __launch_bounds__(1024) sum_partials_kernel(const float* part, int n, float* out, float* slice,
+                                                            unsigned int* ticket) {
   __shared__ float sh[1024];
+  __shared__ bool last;
+  const int per = (n + kSumBlocks - 1) / kSumBlocks;
+  const int i0 = blockIdx.x * per, i1 = min(n, i0 + per);
   float a = 0.f;
-  for (int i = threadIdx.x; i < n; i += 1024) a += part[i];
+  for (int i = i0 + threadIdx.x; i < i1; i += 1024) a += part[i];
   sh[threadIdx.x] = a;
   __syncthreads();
   for (int s = 512; s > 0; s >>= 1) {
     if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[0] = sh[0];
+  if (threadIdx.x == 0) {
+    slice[blockIdx.x] = sh[0];
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == kSumBlocks - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float t = 0.f;
+    for (int k = 0; k < kSumBlocks; ++k) t += __ldcg(slice + k);
+    out[0] = t;
+    *ticket = 0u;
+  }
 }
 
 }  // namespace
@@ -532,7 +551,7 @@ extern "C" size_t rz_sim_bwd_workspace_bytes(int n_images, int n_text, int token
   const size_t pairs = (size_t)n_images * n_text;
   const size_t w = pairs * (size_t)tokens_padded * sizeof(__half);     // one of W1 / W2
   const size_t tiles = (size_t)n_images * ((n_text + 127) / 128) * (tokens_padded / 128);
-  return 2 * w + 2 * pairs * sizeof(float) + 4 * tiles * sizeof(float) + 256;
+  return 2 * w + 2 * pairs * sizeof(float) + 4 * tiles * sizeof(float) + 1024;   // + scale, amax, ticket, 128 slice sums
 }
 
 extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int tokens_padded,
@@ -571,8 +590,10 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
   const int d_tiles = B * m_tiles * n_tiles;
   float* scale = dtau_part + 4 * (size_t)d_tiles;          // [2]
   unsigned int* amax = reinterpret_cast<unsigned int*>(scale + 2);
+  unsigned int* sum_ticket = amax + 1;
+  float* sum_slice = reinterpret_cast<float*>(amax + 2);                 // [kSumBlocks]
 
-  RZ_CUDA_OK(cudaMemsetAsync(amax, 0, sizeof(unsigned int), s));
+  RZ_CUDA_OK(cudaMemsetAsync(amax, 0, 2 * sizeof(unsigned int), s));        // amax and the ticket of sum_partials_kernel
   CoefParams cp;
   cp.g = dz; cp.z = z; cp.ldz = ldz; cp.onorm = onorm; cp.q_inv_norm = q_inv_norm; cp.coef_a = coef_a; cp.coef_r = coef_r;
   cp.amax_bits = amax; cp.B = B; cp.N = N;
@@ -600,7 +621,7 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
     const int t2 = B * m_tiles * p.n_tiles;
     int rc = Cd == 2 ? launch<PassD2<2>>(m, p, s) : launch<PassD2<1>>(m, p, s);
     if (rc != RZ_OK) return rc;
-    sum_partials_kernel<<<1, 1024, 0, s>>>(dtau_part, 4 * t2, dlog_tau);
+    sum_partials_kernel<<<kSumBlocks, 1024, 0, s>>>(dtau_part, 4 * t2, dlog_tau, sum_slice, sum_ticket);
     RZ_LAUNCH_OK();
     rz_count_launch();
   } else {
@@ -618,7 +639,7 @@ extern "C" int rz_sim_bwd(const void* k_f16, int n_images, int tokens, int token
     p.scale = scale; p.w1 = w1; p.w2 = w2; p.dtau_part = dtau_part;
     int rc = C == 2 ? launch<PassD<2>>(m, p, s) : launch<PassD<1>>(m, p, s);
     if (rc != RZ_OK) return rc;
-    sum_partials_kernel<<<1, 1024, 0, s>>>(dtau_part, 4 * d_tiles, dlog_tau);
+    sum_partials_kernel<<<kSumBlocks, 1024, 0, s>>>(dtau_part, 4 * d_tiles, dlog_tau, sum_slice, sum_ticket);
     RZ_LAUNCH_OK();
     rz_count_launch();
   }
