@@ -13,6 +13,7 @@ CASES = {
     "signed_i16": dict(shape=(512, 640), dtype="int16", hi=3000, size=(518, 518), seed=7),
     "rgb_u8_mild": dict(shape=(600, 700, 3), dtype="uint8", hi=255, size=(518, 518), seed=10),   # short windows, 3 channels
     "u16_tall": dict(shape=(1100, 640), dtype="uint16", hi=65535, size=(518, 320), seed=11),      # odd band edges
+    "odd_sizes_u8": dict(shape=(333, 257), dtype="uint8", hi=255, size=(199, 131), seed=12),      # partial column blocks / bands
     "constant": dict(shape=(64, 64), dtype="uint8", hi=0, size=(37, 41), seed=8),
     "levels": dict(shape=(16, 16), dtype="uint8", hi=-1, size=(16, 16), seed=9, keep_pv=True),
 }
