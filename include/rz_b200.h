@@ -364,6 +364,43 @@ int rz_linear(const void* a_f16, long long m, int k, const void* w_f16, int n, c
 int rz_attention(const void* qkv_f16, int n_images, int tokens, int heads, void* out_f16,
                  void* stream);
 
+/* ---- backward of the AlignTransformer layers ------------------------------------------------
+ * Autograd of transformers' Dinov2Layer as AlignTransformer.forward runs it
+ * (exp/cxr_pt/model/align_transformers.py:37-45; trained by radzero.yaml `module_to_update`).  The
+ * GEMM-shaped products go through rz_linear (dX = dY . W with the weight pre-transposed, dW = dY^T . X
+ * with both operands transposed by rz_transpose_pad and the fp32 RZ_LIN_RESIDUAL epilogue accumulating
+ * into the gradient); these entry points are the steps between them.  All fp16 gradients carry one
+ * power-of-two factor 2^k chosen on the device from max|dL/dtokens| (rz_grad_scale); every fp32
+ * result is multiplied by 2^-k.
+ *
+ * rz_grad_scale     sc fp32 [rz_grad_scale_floats()]: sc[0] = 2^k, sc[1] = 2^-k, sc[2] = max|grad|,
+ *                   sc[3] = k, sc[4 ..] = 2^-k repeated (the `scale` vector of rz_linear).
+ * rz_ls_cast_bwd    Dinov2LayerScale: do_f16 [rows, 768] = fp16(2^k ls dy); dls [768] += sum_rows dy * o
+ *                   (o_f16 = the recomputed output of the scaled linear layer; o_f16 / dls may be NULL).
+ * rz_transpose_pad  in fp16 [rows, cols] -> out fp16 [cols, rows_padded] (zero for rows >= `rows`;
+ *                   cols % 64 == 0, rows_padded % 64 == 0); colsum [cols] += 2^-k sum_rows in
+ *                   (the bias gradient; out or colsum may be NULL).
+ * rz_gelu_bwd       du = dg * gelu_erf'(u), n fp16 elements (n % 8 == 0).
+ * rz_ln_rows_bwd    nn.LayerNorm(768, eps): dx fp32 [rows, 768] = dres + 2^-k LN'(dh_f16) (dres NULL = 0, dx
+ *                   may alias dres); dgamma / dbeta [768] += the parameter gradients (NULL = skipped).
+ * rz_attention_bwd  backward of rz_attention: qkv / out as there, dout fp16 [n_images, tokens, heads * 64];
+ *                   dqkv fp16 like qkv, its q block multiplied by q_scale (the 1/sqrt(64) the host folded
+ *                   into the query projection: dqkv is then the gradient of the UNSCALED projections);
+ *                   lse, delta fp32 [n_images * heads * tokens] scratch.
+ */
+size_t rz_grad_scale_floats(void);
+int rz_grad_scale(const float* grad, long long n, float* sc, void* stream);
+int rz_ls_cast_bwd(const float* dy, const float* ls, const void* o_f16, const float* sc, long long rows,
+                   void* do_f16, float* dls, void* stream);
+int rz_transpose_pad(const void* in_f16, long long rows, int cols, long long rows_padded, void* out_f16,
+                     float* colsum, const float* sc, void* stream);
+int rz_gelu_bwd(const void* dg_f16, const void* u_f16, long long n, void* du_f16, void* stream);
+int rz_ln_rows_bwd(const float* x, const void* dh_f16, const float* gamma, float eps, const float* dres,
+                   const float* sc, long long rows, float* dx, float* dgamma, float* dbeta, void* stream);
+int rz_attention_bwd(const void* qkv_f16, const void* out_f16, const void* dout_f16, int n_images,
+                     int tokens, int heads, float q_scale, float* lse, float* delta, void* dqkv_f16,
+                     void* stream);
+
 /* ---- diagnostics: one tcgen05.mma probe -------------------------------------------------
  * Copies caller-built shared-memory images of A and B into smem, issues `k_steps`
  * tcgen05.mma (kind::f16, fp32 accumulate) with the given descriptors and dumps all 128

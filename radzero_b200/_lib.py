@@ -59,6 +59,13 @@ SIGNATURES: Dict[str, tuple] = {
     "rz_ln_rows": (_i, [_vp, _i, _vp, _vp, _f, _ll, _vp, _vp]),
     "rz_linear": (_i, [_vp, _ll, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "rz_attention": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "rz_grad_scale_floats": (C.c_size_t, []),
+    "rz_grad_scale": (_i, [_vp, _ll, _vp, _vp]),
+    "rz_ls_cast_bwd": (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp]),
+    "rz_transpose_pad": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _vp, _vp]),
+    "rz_gelu_bwd": (_i, [_vp, _vp, _ll, _vp, _vp]),
+    "rz_ln_rows_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _ll, _vp, _vp, _vp, _vp]),
+    "rz_attention_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "rz_umma_probe": (_i, [_vp, _i, _vp, _i, _ull, _ull, _i, _i, _i, _u, _u, _i, _vp, _vp]),
 }
 

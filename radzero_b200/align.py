@@ -18,9 +18,16 @@ kernels behind the C ABI (``rz_ln_rows``, ``rz_linear``, ``rz_attention``):
     g16 = gelu(h16 W1^T + b1)          rz_linear  "gelu"
     x   = x + ls2 * (g16 W2^T + b2)    rz_linear  "residual"
 
-Inference only (the packed weights are detached): when the module is in train mode and autograd needs
-gradients through it (`module_to_update: [align_transformer, ...]`) ``forward`` runs the reference's own stock
-forward instead (``stock_forward``), which is outside this round's scope.  No CPU fallback: CPU tensors raise ``RzError``.
+Training (`module_to_update: [align_transformer, ...]`, radzero.yaml): when autograd needs gradients
+through the module, ``forward`` runs the same kernels under ``_AlignFn`` (a ``torch.autograd.Function``
+that keeps each layer's activations) and its backward runs the hand-written chain of ``layer_backward``:
+the twelve GEMM-shaped products per layer on ``rz_linear`` (dX = dY W with pre-transposed weights;
+dW = dY^T X with both operands transposed to K-major by ``rz_transpose_pad``, accumulated in fp32 by the
+residual epilogue), ``rz_attention_bwd``, ``rz_ln_rows_bwd``, ``rz_gelu_bwd``, ``rz_ls_cast_bwd``.  The fp16
+gradient chain carries one power-of-two scale chosen on the device (``rz_grad_scale``), so small loss
+gradients do not fall into fp16 subnormals and no host synchronisation is needed.  The stock HF modules
+are never called (``kernel_backward = False`` restores ``stock_forward`` for comparisons).
+No CPU fallback: CPU tensors raise ``RzError``.
 """
 from __future__ import annotations
 
@@ -61,7 +68,139 @@ def pack_layer(layer: nn.Module, device=None) -> Dict[str, torch.Tensor]:
         "w1": f16(layer.mlp.fc1.weight), "bf1": f32(layer.mlp.fc1.bias),
         "w2": f16(layer.mlp.fc2.weight), "bf2": f32(layer.mlp.fc2.bias),
         "ls2": f32(layer.layer_scale2.lambda1),
+        "q_scale": s,
     }
+
+
+def pack_layer_bwd(layer: nn.Module, device=None) -> Dict[str, torch.Tensor]:
+    """The transposed fp16 weights the dX = dY W products read ((in, out) row-major = rz_linear's
+    (N, K) operand).  The query block is the UNSCALED weight: ``rz_attention_bwd`` hands back the gradient
+    of the unscaled projections."""
+    att = layer.attention.attention
+    dev = device or att.query.weight.device
+    t16 = lambda t: t.detach().to(device=dev, dtype=torch.float32).t().to(torch.float16).contiguous()
+    return {
+        "wqkv_t": t16(torch.cat([att.query.weight, att.key.weight, att.value.weight], dim=0)),   # (768, 2304)
+        "wo_t": t16(layer.attention.output.dense.weight),                                       # (768, 768)
+        "w1_t": t16(layer.mlp.fc1.weight),                                                      # (768, 3072)
+        "w2_t": t16(layer.mlp.fc2.weight),                                                      # (3072, 768)
+    }
+
+
+def layer_params(layer: nn.Module) -> List[Optional[nn.Parameter]]:
+    """The parameters of one Dinov2Layer in the order ``layer_backward`` returns their gradients."""
+    att = layer.attention.attention
+    return [layer.norm1.weight, layer.norm1.bias,
+            att.query.weight, att.query.bias, att.key.weight, att.key.bias, att.value.weight, att.value.bias,
+            layer.attention.output.dense.weight, layer.attention.output.dense.bias, layer.layer_scale1.lambda1,
+            layer.norm2.weight, layer.norm2.bias,
+            layer.mlp.fc1.weight, layer.mlp.fc1.bias, layer.mlp.fc2.weight, layer.mlp.fc2.bias,
+            layer.layer_scale2.lambda1]
+
+
+def layer_forward_train(x2: torch.Tensor, B: int, L: int, w: Dict[str, torch.Tensor]):
+    """``layer_forward`` out of place, keeping what the backward reads: returns (z (B L, 768) fp32, saved)."""
+    D = x2.shape[1]
+    h1 = ops.ln_rows(x2, w["g1"], w["b1"], w["eps1"])
+    qkv = ops.linear(h1, w["wqkv"], w["bqkv"], "bias")
+    a = ops.attention(qkv.view(B, L, 3 * D), w["heads"]).view(B * L, D)
+    y = ops.linear(a, w["wo"], w["bo"], "residual", scale=w["ls1"], residual=x2)
+    h2 = ops.ln_rows(y, w["g2"], w["b2"], w["eps2"])
+    g = ops.linear(h2, w["w1"], w["bf1"], "gelu")
+    z = ops.linear(g, w["w2"], w["bf2"], "residual", scale=w["ls2"], residual=y)
+    return z, (x2, h1, qkv, a, y, h2, g)
+
+
+def _dweight(dyT: torch.Tensor, xT: torch.Tensor, sc: torch.Tensor) -> torch.Tensor:
+    """dW (out, in) fp32 = 2^-k dY^T X from the K-major transposes (K = rows, zero padded)."""
+    out = torch.zeros((dyT.shape[0], xT.shape[0]), dtype=torch.float32, device=dyT.device)
+    return ops.linear(dyT, xT, None, "residual", scale=sc[4:4 + xT.shape[0]], residual=out, out=out)
+
+
+def layer_backward(dz: torch.Tensor, saved, B: int, L: int, w: Dict[str, torch.Tensor],
+                   wb: Dict[str, torch.Tensor], sc: torch.Tensor):
+    """Autograd of one Dinov2Layer.  ``dz`` (B L, 768) fp32 = dL/d(layer output); returns
+    (dL/d(layer input) fp32, gradients in ``layer_params`` order, fp32)."""
+    x2, h1, qkv, a, y, h2, g = saved
+    D = x2.shape[1]
+    dev = dz.device
+    zeros = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
+    # ---- x = y + ls2 * (gelu(h2 W1^T + b1) W2^T + b2)
+    o2 = ops.linear(g, w["w2"], w["bf2"], "bias")                    # recomputed: only dls2 needs it
+    dls2, db2, db1 = zeros(D), zeros(D), zeros(4 * D)
+    do2 = ops.ls_cast_bwd(dz, w["ls2"], o2, sc, dls2)
+    del o2
+    dw2 = _dweight(ops.transpose_pad(do2, sc, db2), ops.transpose_pad(g), sc)
+    dg = ops.linear(do2, wb["w2_t"], None, "bias")
+    del do2
+    u = ops.linear(h2, w["w1"], w["bf1"], "bias")                    # recomputed pre-activation
+    du = ops.gelu_bwd(dg, u)
+    del dg, u
+    dw1 = _dweight(ops.transpose_pad(du, sc, db1), ops.transpose_pad(h2), sc)
+    dh2 = ops.linear(du, wb["w1_t"], None, "bias")
+    del du
+    dg2, dbeta2 = zeros(D), zeros(D)
+    dy = ops.ln_rows_bwd(y, dh2, w["g2"], w["eps2"], dz, sc, dg2, dbeta2)
+    del dh2
+    # ---- y = x + ls1 * (attention(LN1(x)) Wo^T + bo)
+    o1 = ops.linear(a, w["wo"], w["bo"], "bias")
+    dls1, dbo, dbqkv = zeros(D), zeros(D), zeros(3 * D)
+    do1 = ops.ls_cast_bwd(dy, w["ls1"], o1, sc, dls1)
+    del o1
+    dwo = _dweight(ops.transpose_pad(do1, sc, dbo), ops.transpose_pad(a), sc)
+    da = ops.linear(do1, wb["wo_t"], None, "bias")
+    del do1
+    dqkv = ops.attention_bwd(qkv.view(B, L, 3 * D), a.view(B, L, D), da.view(B, L, D), w["heads"],
+                             w["q_scale"]).view(B * L, 3 * D)
+    del da
+    dwqkv = _dweight(ops.transpose_pad(dqkv, sc, dbqkv), ops.transpose_pad(h1), sc)
+    dh1 = ops.linear(dqkv, wb["wqkv_t"], None, "bias")
+    del dqkv
+    dg1, dbeta1 = zeros(D), zeros(D)
+    dx = ops.ln_rows_bwd(x2, dh1, w["g1"], w["eps1"], dy, sc, dg1, dbeta1, out=dy)
+    grads = [dg1, dbeta1,
+             dwqkv[:D], dbqkv[:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:], dbqkv[2 * D:],
+             dwo, dbo, dls1, dg2, dbeta2, dw1, db1, dw2, db2, dls2]
+    return dx, grads
+
+
+class _AlignFn(torch.autograd.Function):
+    """The encoder layers under autograd on the B200 kernels (forward keeps the activations)."""
+
+    @staticmethod
+    def forward(ctx, tokens, module, *params):
+        B, L, D = tokens.shape
+        layers = module._weights(tokens.device)
+        x = tokens.detach()
+        x = (x if x.dtype == torch.float32 else x.to(torch.float32)).contiguous().view(B * L, D)
+        saved = []
+        for w in layers:
+            x, sv = layer_forward_train(x, B, L, w)
+            saved.append(sv)
+        ctx.module, ctx.saved, ctx.shape, ctx.params = module, saved, (B, L, D), params
+        ctx.in_dtype = tokens.dtype
+        return x.view(B, L, D).to(tokens.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        B, L, D = ctx.shape
+        module = ctx.module
+        layers = module._weights(dout.device)
+        back = module._weights_bwd(dout.device)
+        dz = dout.to(torch.float32).contiguous().view(B * L, D)
+        sc = ops.grad_scale(dz)
+        per_layer = []
+        for w, wb, sv in zip(reversed(layers), reversed(back), reversed(ctx.saved)):
+            dz, grads = layer_backward(dz, sv, B, L, w, wb, sc)
+            per_layer.append(grads)
+        ctx.saved = None
+        flat = [g for grads in reversed(per_layer) for g in grads]
+        out = []
+        for p, g, need in zip(ctx.params, flat, ctx.needs_input_grad[2:]):
+            out.append(None if (p is None or not need) else g.to(p.dtype).view(p.shape))
+        dx = dz.view(B, L, D).to(ctx.in_dtype) if ctx.needs_input_grad[0] else None
+        return (dx, None, *out)
 
 
 def layer_forward(x: torch.Tensor, w: Dict[str, torch.Tensor], out: Optional[torch.Tensor] = None,
@@ -98,11 +237,15 @@ class AlignTransformer(nn.Module):
         self.layer_norm = layer_norm
         self._packed: Optional[List[Dict[str, torch.Tensor]]] = None
         self._packed_stamp = None
+        self._packed_bwd: Optional[List[Dict[str, torch.Tensor]]] = None
+        self._packed_bwd_stamp = None
+        self.kernel_backward = True      # False: gradients through the stock HF modules (comparisons only)
 
     def refresh(self) -> None:
         """Drop the packed fp16 operands.  Not normally needed: in-place weight changes (load_state_dict,
         optimizer steps) are detected through the parameters' version counters."""
         self._packed = None
+        self._packed_bwd = None
 
     def _stamp(self):
         # (identity, in-place version) of every parameter: load_state_dict / optimizer steps bump versions
@@ -120,9 +263,33 @@ class AlignTransformer(nn.Module):
             self._packed_stamp = stamp
         return self._packed
 
+    def _weights_bwd(self, device) -> List[Dict[str, torch.Tensor]]:
+        stamp = self._stamp()
+        if self._packed_bwd is None or self._packed_bwd_stamp != stamp or (
+                self._packed_bwd and self._packed_bwd[0]["wo_t"].device != device):
+            layers = [] if self.transformer_layers is None else list(self.transformer_layers.layer)
+            self._packed_bwd = [pack_layer_bwd(l, device) for l in layers]
+            self._packed_bwd_stamp = stamp
+        return self._packed_bwd
+
+    def train_forward(self, vision_tokens: torch.Tensor) -> torch.Tensor:
+        """Forward under autograd on the kernels (``_AlignFn``); the optional final ``layer_norm``
+        (use_layer_norm=True, not the released configuration) stays a torch module on top."""
+        if not vision_tokens.is_cuda:
+            raise RzError("radzero_b200 ops run on CUDA tensors only (there is no CPU fallback)")
+        if vision_tokens.dim() != 3 or vision_tokens.shape[-1] != ops.HIDDEN:
+            raise RzError("vision tokens must be (B, L, 768)")
+        x = vision_tokens
+        if self.transformer_layers is not None and len(self.transformer_layers.layer):
+            params = [p for l in self.transformer_layers.layer for p in layer_params(l)]
+            x = _AlignFn.apply(x, self, *params)
+        if self.layer_norm is not None:
+            x = self.layer_norm(x)
+        return x
+
     def stock_forward(self, vision_tokens: torch.Tensor) -> torch.Tensor:
-        """The reference's own forward (align_transformers.py:37-45) through the stock HF modules: used
-        when gradients are needed -- training THROUGH the AlignTransformer is outside this round's scope."""
+        """The reference's own forward (align_transformers.py:37-45) through the stock HF modules
+        (``kernel_backward = False``: the comparison arm of the backward tests and benches)."""
         x = vision_tokens
         if self.transformer_layers is not None:
             x = self.transformer_layers(x)["last_hidden_state"]
@@ -134,7 +301,7 @@ class AlignTransformer(nn.Module):
         # a module in TRAIN mode under autograd takes the stock path; in eval mode (the state every
         # inference script of the reference puts the model in) the kernels run, so a missing
         # torch.no_grad() cannot silently select the slow path -- unless the INPUT itself asks for a
-        # gradient (saliency / Grad-CAM in eval mode), which only the stock path can provide
+        # gradient (saliency / Grad-CAM in eval mode): both cases run `train_forward`
         if not torch.is_grad_enabled():
             return False
         if vision_tokens.requires_grad:
@@ -149,7 +316,7 @@ class AlignTransformer(nn.Module):
         tokens are emitted by its fc2 epilogue as fp16 and returned as such -- the fp32 copy is never
         written and the similarity kernel reads half the bytes."""
         if self._needs_grad(vision_tokens):
-            return self.stock_forward(vision_tokens)
+            return self.train_forward(vision_tokens) if self.kernel_backward else self.stock_forward(vision_tokens)
         with torch.no_grad():
             out = self._forward_kernels(vision_tokens, inplace, handoff_f16)
         if handoff_f16 and out.dtype == torch.float16:

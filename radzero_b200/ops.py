@@ -578,6 +578,105 @@ def attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
     return out
 
 
+# ----------------------------------------------------------------------------- A3 (AlignTransformer backward)
+def _f16c(t, what):
+    if t.dtype != torch.float16 or not t.is_contiguous():
+        raise RzError(f"{what} must be contiguous fp16")
+
+
+@_guard
+def grad_scale(grad: torch.Tensor) -> torch.Tensor:
+    """Power-of-two scale of the fp16 gradient chain from max|grad| (on the device, no sync):
+    returns sc fp32 with sc[0] = 2^k, sc[1] = 2^-k, sc[2] = max|grad|, sc[3] = k, sc[4:] = 2^-k."""
+    _need_cuda(grad)
+    if grad.dtype != torch.float32 or not grad.is_contiguous():
+        raise RzError("grad must be contiguous fp32")
+    lib = _lib.load()
+    sc = torch.empty(int(lib.rz_grad_scale_floats()), dtype=torch.float32, device=grad.device)
+    _lib.check(lib.rz_grad_scale(_p(grad), grad.numel(), _p(sc), _stream()), "rz_grad_scale")
+    return sc
+
+
+@_guard
+def ls_cast_bwd(dy: torch.Tensor, ls: torch.Tensor, o16: Optional[torch.Tensor], sc: torch.Tensor,
+                dls: Optional[torch.Tensor]) -> torch.Tensor:
+    """Dinov2LayerScale backward: returns fp16(2^k ls dy) (rows, 768); ``dls`` (768,) += sum_rows dy * o16."""
+    _need_cuda(dy, ls, o16, sc, dls)
+    if dy.dtype != torch.float32 or not dy.is_contiguous() or dy.dim() != 2 or dy.shape[1] != HIDDEN:
+        raise RzError("dy must be contiguous fp32 (rows, 768)")
+    if o16 is not None:
+        _f16c(o16, "o16")
+    out = torch.empty(dy.shape, dtype=torch.float16, device=dy.device)
+    rc = _lib.load().rz_ls_cast_bwd(_p(dy), _p(ls), _p(o16), _p(sc), dy.shape[0], _p(out), _p(dls), _stream())
+    _lib.check(rc, "rz_ls_cast_bwd")
+    return out
+
+
+@_guard
+def transpose_pad(x16: torch.Tensor, sc: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
+                  want_out: bool = True) -> Optional[torch.Tensor]:
+    """(rows, cols) fp16 -> (cols, rows padded to 64) fp16, the K-major operand of a dW GEMM (K = rows);
+    ``colsum`` (cols,) += 2^-k sum_rows x16 (the bias gradient) from the same read."""
+    _need_cuda(x16, sc, colsum)
+    _f16c(x16, "x16")
+    rows, cols = x16.shape
+    rp = (rows + 63) // 64 * 64
+    out = torch.empty((cols, rp), dtype=torch.float16, device=x16.device) if want_out else None
+    rc = _lib.load().rz_transpose_pad(_p(x16), rows, cols, rp, _p(out), _p(colsum), _p(sc), _stream())
+    _lib.check(rc, "rz_transpose_pad")
+    return out
+
+
+@_guard
+def gelu_bwd(dg16: torch.Tensor, u16: torch.Tensor) -> torch.Tensor:
+    """dg * gelu_erf'(u), fp16 in and out."""
+    _need_cuda(dg16, u16)
+    _f16c(dg16, "dg16")
+    _f16c(u16, "u16")
+    if dg16.shape != u16.shape:
+        raise RzError("gelu_bwd operands differ in shape")
+    out = torch.empty_like(dg16)
+    _lib.check(_lib.load().rz_gelu_bwd(_p(dg16), _p(u16), dg16.numel(), _p(out), _stream()), "rz_gelu_bwd")
+    return out
+
+
+@_guard
+def ln_rows_bwd(x: torch.Tensor, dh16: torch.Tensor, gamma: torch.Tensor, eps: float, dres: Optional[torch.Tensor],
+                sc: torch.Tensor, dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor],
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.LayerNorm backward: ``dres + 2^-k LN'(dh16)`` fp32 (rows, 768); dgamma / dbeta accumulated."""
+    _need_cuda(x, dh16, gamma, dres, sc, dgamma, dbeta, out)
+    if x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 2 or x.shape[1] != HIDDEN:
+        raise RzError("x must be contiguous fp32 (rows, 768)")
+    _f16c(dh16, "dh16")
+    if dres is not None and (dres.dtype != torch.float32 or not dres.is_contiguous() or dres.shape != x.shape):
+        raise RzError("dres must be contiguous fp32 like x")
+    if out is None:
+        out = torch.empty_like(x)
+    rc = _lib.load().rz_ln_rows_bwd(_p(x), _p(dh16), _p(gamma), float(eps), _p(dres), _p(sc), x.shape[0],
+                                    _p(out), _p(dgamma), _p(dbeta), _stream())
+    _lib.check(rc, "rz_ln_rows_bwd")
+    return out
+
+
+@_guard
+def attention_bwd(qkv: torch.Tensor, out16: torch.Tensor, dout16: torch.Tensor, heads: int,
+                  q_scale: float) -> torch.Tensor:
+    """Backward of ``attention``: dqkv fp16 like qkv (q block times ``q_scale``)."""
+    _need_cuda(qkv, out16, dout16)
+    for t, n in ((qkv, "qkv"), (out16, "out16"), (dout16, "dout16")):
+        _f16c(t, n)
+    B, L, W = qkv.shape
+    if W != 3 * heads * 64 or tuple(out16.shape) != (B, L, heads * 64) or out16.shape != dout16.shape:
+        raise RzError("attention_bwd shapes: qkv (B, L, 3 * heads * 64), out / dout (B, L, heads * 64)")
+    dqkv = torch.empty_like(qkv)
+    ws = torch.empty((2, B * heads * L), dtype=torch.float32, device=qkv.device)
+    rc = _lib.load().rz_attention_bwd(_p(qkv), _p(out16), _p(dout16), B, L, heads, float(q_scale),
+                                      _p(ws[0]), _p(ws[1]), _p(dqkv), _stream())
+    _lib.check(rc, "rz_attention_bwd")
+    return dqkv
+
+
 # ----------------------------------------------------------------------------- T0
 @_guard
 def text_pool(hidden: torch.Tensor, attention_mask: torch.Tensor, gamma: Optional[torch.Tensor] = None,

@@ -62,7 +62,7 @@ def test_packed_weights_follow_in_place_parameter_changes(enc):
     assert mod._weights(torch.device("cpu")) is not b
 
 
-def test_cpu_tensors_raise_and_train_mode_uses_the_stock_forward(enc):
+def test_cpu_tensors_raise_in_both_modes_and_the_stock_arm_is_opt_in(enc):
     mod = AlignTransformer(enc).eval()
     with pytest.raises(RzError):
         mod(torch.zeros(1, 4, 768))                                  # no CPU fallback for the kernels
@@ -70,7 +70,10 @@ def test_cpu_tensors_raise_and_train_mode_uses_the_stock_forward(enc):
         mod(torch.zeros(1, 4, 512, device="cpu"))
     mod.train()
     x = torch.randn(1, 5, 768)
-    y = mod(x)                                                       # autograd needed -> reference's own forward
+    with pytest.raises(RzError):
+        mod(x)                                                       # training runs on the kernels too: no CPU path
+    mod.kernel_backward = False
+    y = mod(x)                                                       # the comparison arm: reference's own forward
     assert y.requires_grad and y.shape == x.shape
     want = enc(x)["last_hidden_state"]
     assert torch.allclose(y, want)

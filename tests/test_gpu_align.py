@@ -192,13 +192,13 @@ def test_inplace_and_grad_dispatch():
     # the dtype the reference's module would return
     got16 = mod(tok.to(torch.bfloat16))
     assert got16.dtype == torch.bfloat16 and (got16.float() - want).abs().max().item() <= 0.25
-    # an input that itself requires grad (eval-mode saliency) is served by the stock path, not detached
+    # an input that itself requires grad (eval-mode saliency) is served under autograd, not detached
     with torch.enable_grad():
         assert mod(tok.clone().requires_grad_(True)).requires_grad
     # eval mode never leaves the kernels, with or without torch.no_grad()
     with torch.enable_grad():
         assert not mod(tok).requires_grad
-    # train mode + gradients needed -> the reference's own stock forward (out of this round's scope)
+    # train mode + gradients needed -> the same kernels under autograd (tests/test_gpu_align_bwd.py)
     mod.train()
     with torch.enable_grad():
         y = mod(tok)
