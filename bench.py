@@ -529,6 +529,21 @@ def run_ours(args):
         if world > 1:
             torch.distributed.destroy_process_group()
         return
+    if args.workload == "align_train":
+        # the training step of the widened row: AlignTransformer forward + backward on the kernels
+        from radzero_b200 import bench_align
+        sampler = ClockSampler(local)
+        sampler.start()
+        t = bench_align.run_train(args, world, rank, local, pk, steps=max(3, min(args.steps, 10)), warmup=3)
+        if rank == 0:
+            print(json.dumps({"metric": "AlignTransformer training images/sec", "value": t["images_per_s"] * world,
+                              "unit": "images/s", "n_gpus": world, "ms_per_step": t["ms_per_step"],
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+                              "data": "synthetic", "impl": "ours", "config": {"workload": t["workload"]},
+                              "gpu_launches": t["gpu_launches_per_step"], "clocks": sampler.stop(), "detail": t}))
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
     if args.workload == "align":
         # the widened path: AlignTransformer -> similarity_prob
         from radzero_b200 import bench_align
@@ -580,6 +595,10 @@ def run_ours(args):
                 addons["upstream_align"] = {"value": _r(u["value"], 5), "unit": "maps/s", "ms_per_step": _r(u["ms_per_step"]),
                                             "e2e": _r(u["e2e"]["value"], 5), "roofline_frac": _r(u["roofline"]["frac"], 3),
                                             "bound": "tensor (sustained)", "sim_stage": u.get("sim_stage")}
+                torch.cuda.empty_cache()
+                t = bench_align.run_train(args, world, rank, local, pk, images=32, steps=3, warmup=2, stock=False)
+                addons["upstream_align"]["train_fwd_bwd"] = {k: t[k] for k in ("ms_per_step", "images_per_s", "tflops",
+                                                                               "gpu_launches_per_step")}
             except Exception as e:
                 addons["upstream_align"] = {"error": repr(e)[:200]}
             torch.cuda.empty_cache()
@@ -793,7 +812,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cls", choices=list(WORKLOADS) + ["contrastive", "align", "preprocess"])
+    ap.add_argument("--workload", default="cls", choices=list(WORKLOADS) + ["contrastive", "align", "align_train", "preprocess"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-align", action="store_true",
                     help="skip the AlignTransformer add-on of the default workload")

@@ -184,3 +184,104 @@ def run(args, world, rank, local, pk, steps=None, warmup=None):
                        "input_dtype": "fp32", "l2": "activations (>= 0.5 GB per kernel) larger than L2; no flush",
                        "parallelism": f"images sharded x{world}, no collective"},
             "sim_stage": sim_stage, "prob_checksum": float(res.double().sum().item())}
+
+
+# ----------------------------------------------------------------------------- training step (forward + backward)
+def train_flops(b: int) -> float:
+    """Forward + backward of the two layers: the twelve linear products per layer cost 2 M K N each way
+    (forward, dX, dW) = 3x the forward's, the attention backward five L x L x 64 products per head (the
+    recomputation of the scores counted, as FlashAttention does) next to the forward's two."""
+    m = b * L
+    return LAYERS * (3 * 24.0 * m * D * D + (4.0 + 10.0) * b * HEADS * L * L * 64)
+
+
+def run_train(args, world, rank, local, pk, images: int = 64, steps: int = 5, warmup: int = 3, stock: bool = True):
+    """One step = ``AlignTransformer.forward`` under autograd + ``backward`` of a linear loss on ``images``
+    images per GPU (config 4 trains the module on 128 images a GPU; 64 keeps the stock arm's materialised
+    attention matrices small).  Reports the step on the kernels, the same step through the stock HF modules
+    (``kernel_backward = False``: torch eager + cuBLAS, fp32 and under bf16 autocast as the reference trains,
+    radzero.yaml ``bf16: true``) and the device time of every backward kernel."""
+    from radzero_b200 import _lib, ops, synthetic
+    from radzero_b200.align import AlignTransformer, layer_forward_train, pack_layer, pack_layer_bwd
+    dev = torch.device("cuda", local)
+    enc = synthetic.build_align_encoder(seed=42, device=dev)
+    mod = AlignTransformer(enc).train()
+    tok = synthetic.make_inputs(images, 1, seed=42 + rank, device=dev)[0]
+    up = torch.randn(tok.shape, device=dev, generator=torch.Generator(dev).manual_seed(7)) * 1e-3
+
+    def step():
+        for p in mod.parameters():
+            p.grad = None
+        (mod(tok) * up).sum().backward()
+
+    def timed(fn, n, w):
+        for _ in range(w):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    n0 = _lib.launch_count()
+    ms = timed(step, steps, warmup)
+    launches = (_lib.launch_count() - n0) // (steps + warmup)
+    flops = train_flops(images)
+    out = {"workload": f"AlignTransformer forward + backward, {images} images x {L} tokens, 2 layers",
+           "ms_per_step": round(ms, 3), "images_per_s": round(images / (ms * 1e-3), 1), "gpu_launches_per_step": int(launches),
+           "tflops": round(flops / ms / 1e9, 1), "frac_of_tensor_sustained": round(flops / ms / 1e9 / pk["tf_sust"], 3)}
+    if stock:
+        mod.kernel_backward = False
+        try:
+            out["stock_fp32_ms"] = round(timed(step, 2, 1), 3)
+
+            def step_bf16():
+                for p in mod.parameters():
+                    p.grad = None
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    y = mod(tok)
+                (y.float() * up).sum().backward()
+            out["stock_bf16_autocast_ms"] = round(timed(step_bf16, 3, 2), 3)
+        except Exception as e:      # the stock arm materialises B x 12 x L x L matrices
+            out["stock_error"] = repr(e)[:160]
+        mod.kernel_backward = True
+        for p in mod.parameters():
+            p.grad = None
+        torch.cuda.empty_cache()
+    # per-kernel device times of one layer's backward
+    layer = enc.layer[0]
+    w, wb = pack_layer(layer, dev), pack_layer_bwd(layer, dev)
+    m = images * L
+    with torch.no_grad():
+        x2 = tok.view(m, D).clone()
+        _, (x2, h1, qkv, a, y, h2, g) = layer_forward_train(x2, images, L, w)
+        dz = up.view(m, D).contiguous()
+        sc = ops.grad_scale(dz)
+        do2 = ops.ls_cast_bwd(dz, w["ls2"], None, sc, None)
+        doT, gT = ops.transpose_pad(do2), ops.transpose_pad(g)
+        dg = ops.linear(do2, wb["w2_t"], None, "bias")
+        u = ops.linear(h2, w["w1"], w["bf1"], "bias")
+        da = ops.linear(do2, wb["wo_t"], None, "bias")
+        acc = torch.zeros(D, 4 * D, device=dev)
+        zero = torch.zeros(4 * D, device=dev)
+        att_fl = 10.0 * images * HEADS * L * L * 64
+        stages = [
+            ("attn_bwd_dq_kernel + attn_bwd_dkv_kernel (mma.sync)", lambda: ops.attention_bwd(
+                qkv.view(images, L, 3 * D), a.view(images, L, D), da.view(images, L, D), HEADS, 0.125), att_fl, None),
+            ("gemm_kernel<Lin BIAS> dX 768->3072 (fc2^T)", lambda: ops.linear(do2, wb["w2_t"], None, "bias"), 2.0 * m * D * 4 * D, None),
+            ("gemm_kernel<Lin RESIDUAL> dW 768 x 3072, K = rows", lambda: ops.linear(doT, gT, None, "residual", scale=sc[4:4 + 4 * D],
+                                                                                    residual=acc, out=acc), 2.0 * m * D * 4 * D, None),
+            ("transpose_kernel 3072 columns (+ bias gradient)", lambda: ops.transpose_pad(g, sc, zero), None, m * 4 * D * 4.0),
+            ("gelu_bwd_kernel", lambda: ops.gelu_bwd(dg, u), None, m * 4 * D * 6.0),
+            ("ln_bwd_kernel", lambda: ops.ln_rows_bwd(y, do2, w["g2"], w["eps2"], dz, sc, zero[:D], zero[D:2 * D]), None, m * D * 14.0),
+            ("ls_cast_kernel", lambda: ops.ls_cast_bwd(dz, w["ls2"], do2, sc, zero[:D]), None, m * D * 8.0),
+        ]
+        kms = {}
+        for name, fnk, fl, by in stages:
+            t = timed(fnk, 3, 1)
+            kms[name] = {"ms": round(t, 4), **({"tflops": round(fl / t / 1e9, 1)} if fl else {"gbs": round(by / t / 1e6, 1)})}
+    out["backward_kernels_one_layer"] = kms
+    return out
