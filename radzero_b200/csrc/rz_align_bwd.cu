@@ -16,7 +16,8 @@
 //   rz_ln_rows_bwd     nn.LayerNorm backward of one row per warp + the residual-path gradient
 //   rz_attention_bwd   softmax(q k^T) v backward per (image, head), head dim 64, warp-level
 //                      mma.sync.m16n8k16 (fp16 in, fp32 accumulate), recomputing the probabilities:
-//                        kernel 1 (64 query rows / CTA): row log-sum-exp, delta = rowsum(dO o), dQ
+//                        kernel 1 (64 query rows / CTA): delta = rowsum(dO o), dQ against a running maximum
+//                                 (one pass over the keys, the log-sum-exp falls out at the end)
 //                        kernel 2 (64 key rows / CTA):   dK, dV
 //                      No atomics: every output element has one owner, the result is run-to-run identical.
 //                      This is the one kernel of the repo on the legacy tensor-core path; a tcgen05 version
@@ -319,19 +320,44 @@ __device__ __forceinline__ void zero_acc(float (&c)[8][4]) {
 
 // rows w16 + g and w16 + g + 8 of the tile starting at global row r0, 64 columns at `dst` (row pitch ld)
 __device__ __forceinline__ void store_acc(__half* dst, long long ld, int r0, int w16, int L, const float (&c)[8][4],
-                                          float mul) {
+                                          float mul_a, float mul_b) {
   const int lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
   const int ra = r0 + w16 + g, rb = ra + 8;
 #pragma unroll
   for (int nb = 0; nb < 8; ++nb) {
-    if (ra < L) *reinterpret_cast<uint32_t*>(dst + (long long)ra * ld + 8 * nb + 2 * tig) = rz::pack_half2(c[nb][0] * mul, c[nb][1] * mul);
-    if (rb < L) *reinterpret_cast<uint32_t*>(dst + (long long)rb * ld + 8 * nb + 2 * tig) = rz::pack_half2(c[nb][2] * mul, c[nb][3] * mul);
+    if (ra < L) *reinterpret_cast<uint32_t*>(dst + (long long)ra * ld + 8 * nb + 2 * tig) = rz::pack_half2(c[nb][0] * mul_a, c[nb][1] * mul_a);
+    if (rb < L) *reinterpret_cast<uint32_t*>(dst + (long long)rb * ld + 8 * nb + 2 * tig) = rz::pack_half2(c[nb][2] * mul_b, c[nb][3] * mul_b);
   }
 }
 
-// kernel 1: grid (q tiles, B * H), 4 warps x 16 query rows
+// 16-byte asynchronous copy global -> shared; `valid` false zero-fills (src-size 0: nothing is read)
+__device__ __forceinline__ void cp_async16(__half* dst, const __half* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// load_tile without waiting: the streamed tiles are double buffered under the MMAs of the previous tile
+__device__ __forceinline__ void prefetch_tile(__half* tile, const __half* base, long long ld, int r0, int L) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ch = threadIdx.x + 128 * i, r = ch >> 3, c = (ch & 7) * 8;
+    const bool in = r0 + r < L;
+    cp_async16(tile + r * kLd + c, base + (long long)(in ? r0 + r : 0) * ld + c, in);
+  }
+}
+
+// kernel 1: grid (q tiles, B * H), 4 warps x 16 query rows.  ONE pass over the keys: the softmax
+// normaliser is not known yet, so dQ is accumulated against a running maximum exactly as the forward
+// accumulates O,   dQ_i = (1 / l_i) sum_j e^{s_ij - m_i} (dP_ij - delta_i) k_j,
+// rescaled when the maximum moves (delta_i = dO_i . o_i does not depend on the normaliser); the row's
+// log-sum-exp m_i + ln l_i falls out at the end and is what kernel 2 reads.
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwd p) {
-  __shared__ __align__(16) __half Qs[kT * kLd], Ks[kT * kLd], Vs[kT * kLd], Gs[kT * kLd];
+  __shared__ __align__(16) __half Ta[kT * kLd], Tb[kT * kLd], Tc[kT * kLd], Td[kT * kLd];
   __shared__ float delta_s[kT];
   const int tid = threadIdx.x, lane = tid & 31, w16 = (tid >> 5) * 16, g = lane >> 2, tig = lane & 3;
   const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H, q0 = blockIdx.x * kT, L = p.L;
@@ -342,15 +368,15 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwd p) {
   const __half* ob = p.o + (long long)b * L * ldo + h * 64;
   const __half* gb = p.dout + (long long)b * L * ldo + h * 64;
 
-  load_tile(Qs, qb, ld, q0, L);
-  load_tile(Gs, gb, ldo, q0, L);
-  load_tile(Ks, ob, ldo, q0, L);                       // the forward output, only for delta
+  load_tile(Tc, qb, ld, q0, L);
+  load_tile(Td, gb, ldo, q0, L);
+  load_tile(Ta, ob, ldo, q0, L);                       // the forward output, only for delta
   __syncthreads();
   {
     const int r = tid >> 1, c0 = (tid & 1) * 32;
     float s = 0.f;
 #pragma unroll 8
-    for (int c = 0; c < 32; ++c) s += __half2float(Gs[r * kLd + c0 + c]) * __half2float(Ks[r * kLd + c0 + c]);
+    for (int c = 0; c < 32; ++c) s += __half2float(Td[r * kLd + c0 + c]) * __half2float(Ta[r * kLd + c0 + c]);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     if ((tid & 1) == 0) {
       delta_s[r] = s;
@@ -358,19 +384,38 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwd p) {
     }
   }
   uint32_t qf[4][4], gf[4][4];
-  load_a_frags(Qs, w16, qf);
-  load_a_frags(Gs, w16, gf);
-  __syncthreads();
+  load_a_frags(Tc, w16, qf);
+  load_a_frags(Td, w16, gf);
+  __syncthreads();                                     // Q / dO / O tiles are free: all four tiles stream K, V
   const float d0 = delta_s[w16 + g], d1 = delta_s[w16 + g + 8];
+  auto kbuf = [&](int i) { return i ? Tc : Ta; };
+  auto vbuf = [&](int i) { return i ? Td : Tb; };
+  const int nt = (L + kT - 1) / kT;
+  prefetch_tile(kbuf(0), kb, ld, 0, L);
+  prefetch_tile(vbuf(0), vb, ld, 0, L);
+  cp_async_commit();
 
-  // pass 1: row log-sum-exp of q k^T (online maximum)
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  for (int kv0 = 0; kv0 < L; kv0 += kT) {
-    load_tile(Ks, kb, ld, kv0, L);
+  float acc[8][4];
+  zero_acc(acc);
+  for (int it = 0; it < nt; ++it) {
+    const int kv0 = it * kT;
+    if (it + 1 < nt) {
+      prefetch_tile(kbuf((it + 1) & 1), kb, ld, kv0 + kT, L);
+      prefetch_tile(vbuf((it + 1) & 1), vb, ld, kv0 + kT, L);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
-    float s[8][4];
+    const __half* Ks = kbuf(it & 1);
+    const __half* Vs = vbuf(it & 1);
+    float s[8][4], dp[8][4];
     zero_acc(s);
+    zero_acc(dp);
     gemm_nt(s, qf, Ks);
+    gemm_nt(dp, gf, Vs);
     float x0 = -INFINITY, x1 = -INFINITY;
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb)
@@ -382,41 +427,19 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwd p) {
     x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
     x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
     const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);
-    l0 *= __expf(m0 - n0); l1 *= __expf(m1 - n1);
-    m0 = n0; m1 = n1;
+    if (n0 != m0 || n1 != m1) {                        // warp-divergent only in the first few tiles
+      const float r0 = __expf(m0 - n0), r1 = __expf(m1 - n1);
+      l0 *= r0; l1 *= r1;
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
-      l0 += __expf(s[nb][0] - m0) + __expf(s[nb][1] - m0);
-      l1 += __expf(s[nb][2] - m1) + __expf(s[nb][3] - m1);
+      for (int nb = 0; nb < 8; ++nb) { acc[nb][0] *= r0; acc[nb][1] *= r0; acc[nb][2] *= r1; acc[nb][3] *= r1; }
+      m0 = n0; m1 = n1;
     }
-    __syncthreads();
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float lse0 = m0 + __logf(l0), lse1 = m1 + __logf(l1);
-  if (tig == 0) {
-    if (q0 + w16 + g < L) p.lse[(long long)bh * L + q0 + w16 + g] = lse0;
-    if (q0 + w16 + g + 8 < L) p.lse[(long long)bh * L + q0 + w16 + g + 8] = lse1;
-  }
-
-  // pass 2: dS = P (dP - delta), dQ += dS K
-  float acc[8][4];
-  zero_acc(acc);
-  for (int kv0 = 0; kv0 < L; kv0 += kT) {
-    load_tile(Ks, kb, ld, kv0, L);
-    load_tile(Vs, vb, ld, kv0, L);
-    __syncthreads();
-    float s[8][4], dp[8][4];
-    zero_acc(s);
-    zero_acc(dp);
-    gemm_nt(s, qf, Ks);
-    gemm_nt(dp, gf, Vs);
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const bool in = kv0 + 8 * nb + 2 * tig + (e & 1) < L;
-        const float pv = in ? __expf(s[nb][e] - (e < 2 ? lse0 : lse1)) : 0.f;
+        const float pv = __expf(s[nb][e] - (e < 2 ? m0 : m1));       // masked keys: e^{-inf} = 0
+        if (e < 2) l0 += pv; else l1 += pv;
         s[nb][e] = pv * (dp[nb][e] - (e < 2 ? d0 : d1));
       }
     uint32_t af[4][4];
@@ -424,13 +447,19 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwd p) {
     gemm_nn(acc, af, Ks);
     __syncthreads();
   }
-  store_acc(p.dqkv + (long long)b * L * ld + h * 64, ld, q0, w16, L, acc, p.q_scale);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  if (tig == 0) {
+    if (q0 + w16 + g < L) p.lse[(long long)bh * L + q0 + w16 + g] = m0 + __logf(l0);
+    if (q0 + w16 + g + 8 < L) p.lse[(long long)bh * L + q0 + w16 + g + 8] = m1 + __logf(l1);
+  }
+  store_acc(p.dqkv + (long long)b * L * ld + h * 64, ld, q0, w16, L, acc, p.q_scale / l0, p.q_scale / l1);
 }
 
 // kernel 2: grid (key tiles, B * H), 4 warps x 16 key rows; everything is held transposed (keys are rows)
 __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwd p) {
-  __shared__ __align__(16) __half Qs[kT * kLd], Ks[kT * kLd], Vs[kT * kLd], Gs[kT * kLd];
-  __shared__ float lse_s[kT], delta_s[kT];
+  __shared__ __align__(16) __half Ta[kT * kLd], Tb[kT * kLd], Tc[kT * kLd], Td[kT * kLd];
+  __shared__ float lse_s[2][kT], delta_s[2][kT];
   const int tid = threadIdx.x, lane = tid & 31, w16 = (tid >> 5) * 16, tig = lane & 3;
   const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H, k0 = blockIdx.x * kT, L = p.L;
   const long long ld = 3ll * p.H * 64, ldo = (long long)p.H * 64;
@@ -438,25 +467,47 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwd p) {
   const __half* kb = qb + ldo;
   const __half* vb = qb + 2 * ldo;
   const __half* gb = p.dout + (long long)b * L * ldo + h * 64;
+  const float* lse = p.lse + (long long)bh * L;
+  const float* delta = p.delta + (long long)bh * L;
 
-  load_tile(Ks, kb, ld, k0, L);
-  load_tile(Vs, vb, ld, k0, L);
+  load_tile(Tc, kb, ld, k0, L);
+  load_tile(Td, vb, ld, k0, L);
+  auto qbuf = [&](int i) { return i ? Tc : Ta; };
+  auto gbuf = [&](int i) { return i ? Td : Tb; };
+  const int nt = (L + kT - 1) / kT;
+  prefetch_tile(qbuf(0), qb, ld, 0, L);
+  prefetch_tile(gbuf(0), gb, ldo, 0, L);
+  cp_async_commit();
+  if (tid < kT) {
+    lse_s[0][tid] = tid < L ? lse[tid] : INFINITY;     // e^{s - inf} = 0: padded queries drop out
+    delta_s[0][tid] = tid < L ? delta[tid] : 0.f;
+  }
   __syncthreads();
   uint32_t kf[4][4], vf[4][4];
-  load_a_frags(Ks, w16, kf);
-  load_a_frags(Vs, w16, vf);
+  load_a_frags(Tc, w16, kf);
+  load_a_frags(Td, w16, vf);
+  __syncthreads();                                     // K / V tiles are free: second buffer of the stream
   float dk[8][4], dv[8][4];
   zero_acc(dk);
   zero_acc(dv);
-  for (int q0 = 0; q0 < L; q0 += kT) {
-    load_tile(Qs, qb, ld, q0, L);
-    load_tile(Gs, gb, ldo, q0, L);
-    if (tid < kT) {
-      const bool in = q0 + tid < L;
-      lse_s[tid] = in ? p.lse[(long long)bh * L + q0 + tid] : INFINITY;    // exp(s - inf) = 0: padded queries drop out
-      delta_s[tid] = in ? p.delta[(long long)bh * L + q0 + tid] : 0.f;
+  for (int it = 0; it < nt; ++it) {
+    const int q0 = it * kT, cur = it & 1;
+    if (it + 1 < nt) {
+      prefetch_tile(qbuf(cur ^ 1), qb, ld, q0 + kT, L);
+      prefetch_tile(gbuf(cur ^ 1), gb, ldo, q0 + kT, L);
+      cp_async_commit();
+      if (tid < kT) {
+        const int r = q0 + kT + tid;
+        lse_s[cur ^ 1][tid] = r < L ? lse[r] : INFINITY;
+        delta_s[cur ^ 1][tid] = r < L ? delta[r] : 0.f;
+      }
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
+    const __half* Qs = qbuf(cur);
+    const __half* Gs = gbuf(cur);
     float s[8][4], dp[8][4];
     zero_acc(s);
     zero_acc(dp);
@@ -467,8 +518,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwd p) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int c = 8 * nb + 2 * tig + (e & 1);      // query index inside the tile = column
-        const float pv = __expf(s[nb][e] - lse_s[c]);
-        dp[nb][e] = pv * (dp[nb][e] - delta_s[c]);     // dS^T
+        const float pv = __expf(s[nb][e] - lse_s[cur][c]);
+        dp[nb][e] = pv * (dp[nb][e] - delta_s[cur][c]);   // dS^T
         s[nb][e] = pv;                                 // P^T
       }
     uint32_t af[4][4];
@@ -479,8 +530,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwd p) {
     __syncthreads();
   }
   // q carries the folded 1/sqrt(64): dK = dS^T q_packed is already the gradient of the true key projection
-  store_acc(p.dqkv + (long long)b * L * ld + ldo + h * 64, ld, k0, w16, L, dk, 1.f);
-  store_acc(p.dqkv + (long long)b * L * ld + 2 * ldo + h * 64, ld, k0, w16, L, dv, 1.f);
+  store_acc(p.dqkv + (long long)b * L * ld + ldo + h * 64, ld, k0, w16, L, dk, 1.f, 1.f);
+  store_acc(p.dqkv + (long long)b * L * ld + 2 * ldo + h * 64, ld, k0, w16, L, dv, 1.f, 1.f);
 }
 
 inline bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; }
