@@ -386,7 +386,7 @@ int rz_attention(const void* qkv_f16, int n_images, int tokens, int heads, void*
  * rz_attention_bwd  backward of rz_attention: qkv / out as there, dout fp16 [n_images, tokens, heads * 64];
  *                   dqkv fp16 like qkv, its q block multiplied by q_scale (the 1/sqrt(64) the host folded
  *                   into the query projection: dqkv is then the gradient of the UNSCALED projections);
- *                   lse, delta fp32 [n_images * heads * tokens] scratch.
+ *                   lse, delta fp32 [n_images * heads * tokens rounded up to 64] scratch, 16-byte aligned.
  */
 size_t rz_grad_scale_floats(void);
 int rz_grad_scale(const float* grad, long long n, float* sc, void* stream);

@@ -236,7 +236,7 @@ constexpr int kLd = 72;       // shared-memory row pitch in halfs: 144 B, ldmatr
 struct AttnBwd {
   const __half* qkv; const __half* o; const __half* dout;
   __half* dqkv; float* lse; float* delta;
-  int B, L, H; float q_scale;
+  int B, L, H, Lp; float q_scale;      // Lp = L rounded up to the tile: row pitch of lse / delta
 };
 
 __device__ __forceinline__ void ldsm_x4(const __half* p, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -274,17 +274,20 @@ __device__ __forceinline__ void load_a_frags(const __half* tile, int w16, uint32
     ldsm_x4(tile + (w16 + (lane & 15)) * kLd + 16 * t + (lane >> 4) * 8, f[t][0], f[t][1], f[t][2], f[t][3]);
 }
 
-// c[nb] (16 x 8 blocks, nb < 8) += A (16 x 64, fragments) . T^T, T = a [64][72] tile holding [n][k]
+// c[nb] (16 x 8 blocks, nb < 8) += A (16 x 64, fragments) . T^T, T = a [64][72] tile holding [n][k].
+// One ldmatrix.x4 = the B fragments of TWO column blocks for one k-step, so that consecutive MMAs write
+// different accumulators (an accumulator comes round again after eight MMAs, not back to back).
 __device__ __forceinline__ void gemm_nt(float (&c)[8][4], const uint32_t (&a)[4][4], const __half* tile) {
   const int lane = threadIdx.x & 31;
+  const __half* base = tile + (8 * (lane >> 4) + (lane & 7)) * kLd + ((lane >> 3) & 1) * 8;
 #pragma unroll
-  for (int nb = 0; nb < 8; ++nb)
+  for (int t = 0; t < 4; ++t)
 #pragma unroll
-    for (int tp = 0; tp < 2; ++tp) {
+    for (int np = 0; np < 4; ++np) {
       uint32_t b0, b1, b2, b3;
-      ldsm_x4(tile + (8 * nb + (lane & 7)) * kLd + 32 * tp + (lane >> 3) * 8, b0, b1, b2, b3);
-      mma16816(c[nb], a[2 * tp], b0, b1);
-      mma16816(c[nb], a[2 * tp + 1], b2, b3);
+      ldsm_x4(base + 16 * np * kLd + 16 * t, b0, b1, b2, b3);
+      mma16816(c[2 * np], a[t], b0, b1);
+      mma16816(c[2 * np + 1], a[t], b2, b3);
     }
 }
 
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwd p) {
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     if ((tid & 1) == 0) {
       delta_s[r] = s;
-      if (q0 + r < L) p.delta[(long long)bh * L + q0 + r] = s;
+      p.delta[(long long)bh * p.Lp + q0 + r] = s;       // rows >= L: zero-filled tiles give 0
     }
   }
   uint32_t qf[4][4], gf[4][4];
@@ -449,9 +452,9 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwd p) {
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  if (tig == 0) {
-    if (q0 + w16 + g < L) p.lse[(long long)bh * L + q0 + w16 + g] = m0 + __logf(l0);
-    if (q0 + w16 + g + 8 < L) p.lse[(long long)bh * L + q0 + w16 + g + 8] = m1 + __logf(l1);
+  if (tig == 0) {                                      // padded queries get +inf: e^{s - inf} = 0 drops them in kernel 2
+    p.lse[(long long)bh * p.Lp + q0 + w16 + g] = q0 + w16 + g < L ? m0 + __logf(l0) : INFINITY;
+    p.lse[(long long)bh * p.Lp + q0 + w16 + g + 8] = q0 + w16 + g + 8 < L ? m1 + __logf(l1) : INFINITY;
   }
   store_acc(p.dqkv + (long long)b * L * ld + h * 64, ld, q0, w16, L, acc, p.q_scale / l0, p.q_scale / l1);
 }
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwd p) {
 // kernel 2: grid (key tiles, B * H), 4 warps x 16 key rows; everything is held transposed (keys are rows)
 __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwd p) {
   __shared__ __align__(16) __half Ta[kT * kLd], Tb[kT * kLd], Tc[kT * kLd], Td[kT * kLd];
-  __shared__ float lse_s[2][kT], delta_s[2][kT];
+  __shared__ __align__(16) float lse_s[2][kT], delta_s[2][kT];
   const int tid = threadIdx.x, lane = tid & 31, w16 = (tid >> 5) * 16, tig = lane & 3;
   const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H, k0 = blockIdx.x * kT, L = p.L;
   const long long ld = 3ll * p.H * 64, ldo = (long long)p.H * 64;
@@ -467,8 +470,17 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwd p) {
   const __half* kb = qb + ldo;
   const __half* vb = qb + 2 * ldo;
   const __half* gb = p.dout + (long long)b * L * ldo + h * 64;
-  const float* lse = p.lse + (long long)bh * L;
-  const float* delta = p.delta + (long long)bh * L;
+  const float* lse = p.lse + (long long)bh * p.Lp;
+  const float* delta = p.delta + (long long)bh * p.Lp;
+  // 64 floats of lse (threads 0-15) and of delta (threads 16-31) ride in the tile's cp.async group
+  auto prefetch_stats = [&](int buf, int q0) {
+    if (tid < 32) {
+      const float* src = (tid < 16 ? lse : delta) + q0 + (tid & 15) * 4;
+      float* dst = (tid < 16 ? lse_s[buf] : delta_s[buf]) + (tid & 15) * 4;
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    }
+  };
 
   load_tile(Tc, kb, ld, k0, L);
   load_tile(Td, vb, ld, k0, L);
@@ -477,11 +489,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwd p) {
   const int nt = (L + kT - 1) / kT;
   prefetch_tile(qbuf(0), qb, ld, 0, L);
   prefetch_tile(gbuf(0), gb, ldo, 0, L);
+  prefetch_stats(0, 0);
   cp_async_commit();
-  if (tid < kT) {
-    lse_s[0][tid] = tid < L ? lse[tid] : INFINITY;     // e^{s - inf} = 0: padded queries drop out
-    delta_s[0][tid] = tid < L ? delta[tid] : 0.f;
-  }
   __syncthreads();
   uint32_t kf[4][4], vf[4][4];
   load_a_frags(Tc, w16, kf);
@@ -495,12 +504,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwd p) {
     if (it + 1 < nt) {
       prefetch_tile(qbuf(cur ^ 1), qb, ld, q0 + kT, L);
       prefetch_tile(gbuf(cur ^ 1), gb, ldo, q0 + kT, L);
+      prefetch_stats(cur ^ 1, q0 + kT);
       cp_async_commit();
-      if (tid < kT) {
-        const int r = q0 + kT + tid;
-        lse_s[cur ^ 1][tid] = r < L ? lse[r] : INFINITY;
-        delta_s[cur ^ 1][tid] = r < L ? delta[r] : 0.f;
-      }
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
@@ -617,7 +622,8 @@ extern "C" int rz_attention_bwd(const void* qkv_f16, const void* out_f16, const 
                                 void* stream) {
   if (!qkv_f16 || !out_f16 || !dout_f16 || !lse || !delta || !dqkv_f16 || n_images < 0 || tokens < 0 || heads <= 0)
     return RZ_ERR_INVALID;
-  if (misaligned(qkv_f16) || misaligned(out_f16) || misaligned(dout_f16) || misaligned(dqkv_f16))
+  if (misaligned(qkv_f16) || misaligned(out_f16) || misaligned(dout_f16) || misaligned(dqkv_f16) ||
+      misaligned(lse) || misaligned(delta))
     return RZ_ERR_ALIGNMENT;
   if (n_images == 0 || tokens == 0) return RZ_OK;
   if ((long long)n_images * heads > 65535) return RZ_ERR_UNSUPPORTED;
@@ -625,6 +631,7 @@ extern "C" int rz_attention_bwd(const void* qkv_f16, const void* out_f16, const 
   p.qkv = static_cast<const __half*>(qkv_f16); p.o = static_cast<const __half*>(out_f16);
   p.dout = static_cast<const __half*>(dout_f16); p.dqkv = static_cast<__half*>(dqkv_f16);
   p.lse = lse; p.delta = delta; p.B = n_images; p.L = tokens; p.H = heads; p.q_scale = q_scale;
+  p.Lp = (tokens + kT - 1) / kT * kT;
   const dim3 grid((unsigned)((tokens + kT - 1) / kT), (unsigned)(n_images * heads));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   attn_bwd_dq_kernel<<<grid, 128, 0, s>>>(p);

@@ -670,7 +670,7 @@ def attention_bwd(qkv: torch.Tensor, out16: torch.Tensor, dout16: torch.Tensor, 
     if W != 3 * heads * 64 or tuple(out16.shape) != (B, L, heads * 64) or out16.shape != dout16.shape:
         raise RzError("attention_bwd shapes: qkv (B, L, 3 * heads * 64), out / dout (B, L, heads * 64)")
     dqkv = torch.empty_like(qkv)
-    ws = torch.empty((2, B * heads * L), dtype=torch.float32, device=qkv.device)
+    ws = torch.empty((2, B * heads * ((L + 63) // 64 * 64)), dtype=torch.float32, device=qkv.device)
     rc = _lib.load().rz_attention_bwd(_p(qkv), _p(out16), _p(dout16), B, L, heads, float(q_scale),
                                       _p(ws[0]), _p(ws[1]), _p(dqkv), _stream())
     _lib.check(rc, "rz_attention_bwd")
