@@ -377,6 +377,11 @@ int rz_attention(const void* qkv_f16, int n_images, int tokens, int heads, void*
  *                   sc[3] = k, sc[4 ..] = 2^-k repeated (the `scale` vector of rz_linear).
  * rz_ls_cast_bwd    Dinov2LayerScale: do_f16 [rows, 768] = fp16(2^k ls dy); dls [768] += sum_rows dy * o
  *                   (o_f16 = the recomputed output of the scaled linear layer; o_f16 / dls may be NULL).
+ *                   ls NULL = 1 (a plain scaled cast).
+ * rz_ls_weight_bwd  Dinov2LayerScale backward WITHOUT recomputing the scaled product o = x W^T + b: with
+ *                   g fp32 [n, k] = dy^T x (the weight gradient of the unscaled product) and colsum [n] = sum_rows dy,
+ *                   in place g[n, :] *= ls[n] (= dW), colsum[n] *= ls[n] (= db), and
+ *                   dls[n] = sum_k w[n, k] g[n, k] + bias[n] colsum[n] (overwritten).  w fp32 [n, k] = the weight.
  * rz_transpose_pad  in fp16 [rows, cols] -> out fp16 [cols, rows_padded] (zero for rows >= `rows`;
  *                   cols % 64 == 0, rows_padded % 64 == 0); colsum [cols] += 2^-k sum_rows in
  *                   (the bias gradient; out or colsum may be NULL).
@@ -392,6 +397,8 @@ size_t rz_grad_scale_floats(void);
 int rz_grad_scale(const float* grad, long long n, float* sc, void* stream);
 int rz_ls_cast_bwd(const float* dy, const float* ls, const void* o_f16, const float* sc, long long rows,
                    void* do_f16, float* dls, void* stream);
+int rz_ls_weight_bwd(float* g, const float* w, const float* bias, float* colsum, const float* ls, int n, int k,
+                     float* dls, void* stream);
 int rz_transpose_pad(const void* in_f16, long long rows, int cols, long long rows_padded, void* out_f16,
                      float* colsum, const float* sc, void* stream);
 int rz_gelu_bwd(const void* dg_f16, const void* u_f16, long long n, void* du_f16, void* stream);

@@ -62,6 +62,7 @@ SIGNATURES: Dict[str, tuple] = {
     "rz_grad_scale_floats": (C.c_size_t, []),
     "rz_grad_scale": (_i, [_vp, _ll, _vp, _vp]),
     "rz_ls_cast_bwd": (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp]),
+    "rz_ls_weight_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "rz_transpose_pad": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _vp, _vp]),
     "rz_gelu_bwd": (_i, [_vp, _vp, _ll, _vp, _vp]),
     "rz_ln_rows_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _ll, _vp, _vp, _vp, _vp]),

@@ -21,7 +21,7 @@ kernels behind the C ABI (``rz_ln_rows``, ``rz_linear``, ``rz_attention``):
 Training (`module_to_update: [align_transformer, ...]`, radzero.yaml): when autograd needs gradients
 through the module, ``forward`` runs the same kernels under ``_AlignFn`` (a ``torch.autograd.Function``
 that keeps each layer's activations) and its backward runs the hand-written chain of ``layer_backward``:
-the twelve GEMM-shaped products per layer on ``rz_linear`` (dX = dY W with pre-transposed weights;
+the nine GEMM-shaped products per layer on ``rz_linear`` (dX = dY W with pre-transposed weights;
 dW = dY^T X with both operands transposed to K-major by ``rz_transpose_pad``, accumulated in fp32 by the
 residual epilogue), ``rz_attention_bwd``, ``rz_ln_rows_bwd``, ``rz_gelu_bwd``, ``rz_ls_cast_bwd``.  The fp16
 gradient chain carries one power-of-two scale chosen on the device (``rz_grad_scale``), so small loss
@@ -81,9 +81,13 @@ def pack_layer_bwd(layer: nn.Module, device=None) -> Dict[str, torch.Tensor]:
     t16 = lambda t: t.detach().to(device=dev, dtype=torch.float32).t().to(torch.float16).contiguous()
     return {
         "wqkv_t": t16(torch.cat([att.query.weight, att.key.weight, att.value.weight], dim=0)),   # (768, 2304)
-        "wo_t": t16(layer.attention.output.dense.weight),                                       # (768, 768)
+        # the LayerScale factors ride in the transposed weights: (ls * dy) W = dy (diag(ls) W)
+        "wo_t": t16(layer.attention.output.dense.weight * layer.layer_scale1.lambda1[:, None]),  # (768, 768)
         "w1_t": t16(layer.mlp.fc1.weight),                                                      # (768, 3072)
-        "w2_t": t16(layer.mlp.fc2.weight),                                                      # (3072, 768)
+        "w2_t": t16(layer.mlp.fc2.weight * layer.layer_scale2.lambda1[:, None]),                 # (3072, 768)
+        # fp32 weights for dls = rowsum(W * dW_unscaled) (rz_ls_weight_bwd)
+        "wo32": layer.attention.output.dense.weight.detach().to(device=dev, dtype=torch.float32).contiguous(),
+        "w232": layer.mlp.fc2.weight.detach().to(device=dev, dtype=torch.float32).contiguous(),
     }
 
 
@@ -125,12 +129,12 @@ def layer_backward(dz: torch.Tensor, saved, B: int, L: int, w: Dict[str, torch.T
     D = x2.shape[1]
     dev = dz.device
     zeros = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
-    # ---- x = y + ls2 * (gelu(h2 W1^T + b1) W2^T + b2)
-    o2 = ops.linear(g, w["w2"], w["bf2"], "bias")                    # recomputed: only dls2 needs it
-    dls2, db2, db1 = zeros(D), zeros(D), zeros(4 * D)
-    do2 = ops.ls_cast_bwd(dz, w["ls2"], o2, sc, dls2)
-    del o2
+    # ---- x = y + ls2 * (gelu(h2 W1^T + b1) W2^T + b2): LayerScale is folded into w2_t (dX) and finished from
+    # the unscaled weight gradient by rz_ls_weight_bwd (dW, db, dls), so the product is never recomputed
+    db2, db1 = zeros(D), zeros(4 * D)
+    do2 = ops.ls_cast_bwd(dz, None, None, sc, None)
     dw2 = _dweight(ops.transpose_pad(do2, sc, db2), ops.transpose_pad(g), sc)
+    dls2 = ops.ls_weight_bwd(dw2, wb["w232"], w["bf2"], db2, w["ls2"])
     dg = ops.linear(do2, wb["w2_t"], None, "bias")
     del do2
     u = ops.linear(h2, w["w1"], w["bf1"], "bias")                    # recomputed pre-activation
@@ -143,11 +147,10 @@ def layer_backward(dz: torch.Tensor, saved, B: int, L: int, w: Dict[str, torch.T
     dy = ops.ln_rows_bwd(y, dh2, w["g2"], w["eps2"], dz, sc, dg2, dbeta2)
     del dh2
     # ---- y = x + ls1 * (attention(LN1(x)) Wo^T + bo)
-    o1 = ops.linear(a, w["wo"], w["bo"], "bias")
-    dls1, dbo, dbqkv = zeros(D), zeros(D), zeros(3 * D)
-    do1 = ops.ls_cast_bwd(dy, w["ls1"], o1, sc, dls1)
-    del o1
+    dbo, dbqkv = zeros(D), zeros(3 * D)
+    do1 = ops.ls_cast_bwd(dy, None, None, sc, None)
     dwo = _dweight(ops.transpose_pad(do1, sc, dbo), ops.transpose_pad(a), sc)
+    dls1 = ops.ls_weight_bwd(dwo, wb["wo32"], w["bo"], dbo, w["ls1"])
     da = ops.linear(do1, wb["wo_t"], None, "bias")
     del do1
     dqkv = ops.attention_bwd(qkv.view(B, L, 3 * D), a.view(B, L, D), da.view(B, L, D), w["heads"],

@@ -9,7 +9,8 @@
 //   rz_grad_scale      one power-of-two scale for the whole fp16 gradient chain, from max|dL/dtokens|,
 //                      computed on the device (no host sync): every fp16 gradient carries 2^k, every fp32
 //                      result is multiplied by 2^-k (the chain is linear in the incoming gradient)
-//   rz_ls_cast_bwd     Dinov2LayerScale backward: do16 = fp16(2^k ls dy), dls += sum_rows dy o
+//   rz_ls_cast_bwd     do16 = fp16(2^k ls dy) (ls optional), dls += sum_rows dy o (optional)
+//   rz_ls_weight_bwd   Dinov2LayerScale backward from the weight gradient of the unscaled product: no recomputation
 //   rz_transpose_pad   [rows, cols] -> [cols, rows_padded] fp16 (the K-major operands of the dW GEMMs,
 //                      K = rows) + the bias gradients as column sums of the same read
 //   rz_gelu_bwd        du16 = dg16 gelu_erf'(u16)
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(192) ls_cast_kernel(const float* __restrict__ 
                                                       float* __restrict__ dls) {
   const int c = threadIdx.x * 4;
   const float up = sc[0];
-  const float4 l = *reinterpret_cast<const float4*>(ls + c);
+  const float4 l = ls != nullptr ? *reinterpret_cast<const float4*>(ls + c) : make_float4(1.f, 1.f, 1.f, 1.f);
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
     const float4 g = *reinterpret_cast<const float4*>(dy + r * kD + c);
@@ -84,6 +85,37 @@ __global__ void __launch_bounds__(192) ls_cast_kernel(const float* __restrict__ 
   }
   if (dls != nullptr && o16 != nullptr) {
     atomicAdd(dls + c, a0); atomicAdd(dls + c + 1, a1); atomicAdd(dls + c + 2, a2); atomicAdd(dls + c + 3, a3);
+  }
+}
+
+// LayerScale without touching the activations: with G = dy^T x (the weight gradient of the UNSCALED
+// product, one row per output feature n), o = x W^T + b and y = ls * o,
+//   dW[n, :] = ls[n] G[n, :],   db[n] = ls[n] c[n],   dls[n] = sum_k W[n, k] G[n, k] + b[n] c[n],   c = colsum(dy),
+// so the backward never recomputes o: one block per output feature finishes all three from G in place.
+__global__ void __launch_bounds__(256) ls_weight_kernel(float* __restrict__ g, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ cs,
+                                                        const float* __restrict__ ls, int k, float* __restrict__ dls) {
+  __shared__ float red[8];
+  const int n = blockIdx.x;
+  const float l = ls[n];
+  float s = 0.f;
+  for (int i = threadIdx.x * 4; i < k; i += 1024) {
+    float4 gv = *reinterpret_cast<float4*>(g + (long long)n * k + i);
+    const float4 wv = *reinterpret_cast<const float4*>(w + (long long)n * k + i);
+    s += gv.x * wv.x + gv.y * wv.y + gv.z * wv.z + gv.w * wv.w;
+    gv.x *= l; gv.y *= l; gv.z *= l; gv.w *= l;
+    *reinterpret_cast<float4*>(g + (long long)n * k + i) = gv;
+  }
+  s = rz::warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    const float c = cs[n];
+    dls[n] = t + (bias != nullptr ? bias[n] * c : 0.f);
+    cs[n] = l * c;
   }
 }
 
@@ -564,12 +596,23 @@ extern "C" int rz_grad_scale(const float* grad, long long n, float* sc, void* st
 
 extern "C" int rz_ls_cast_bwd(const float* dy, const float* ls, const void* o_f16, const float* sc, long long rows,
                               void* do_f16, float* dls, void* stream) {
-  if (!dy || !ls || !sc || !do_f16 || rows < 0) return RZ_ERR_INVALID;
+  if (!dy || !sc || !do_f16 || rows < 0) return RZ_ERR_INVALID;
   if (misaligned(dy) || misaligned(ls) || misaligned(o_f16) || misaligned(do_f16)) return RZ_ERR_ALIGNMENT;
   if (rows == 0) return RZ_OK;
   const int blocks = (int)std::min<long long>(rows, (long long)rz_sm_count() * 8);
   ls_cast_kernel<<<blocks, 192, 0, static_cast<cudaStream_t>(stream)>>>(
       dy, ls, static_cast<const __half*>(o_f16), sc, rows, static_cast<__half*>(do_f16), dls);
+  RZ_LAUNCH_OK();
+  rz_count_launch();
+  return RZ_OK;
+}
+
+extern "C" int rz_ls_weight_bwd(float* g, const float* w, const float* bias, float* colsum, const float* ls,
+                               int n, int k, float* dls, void* stream) {
+  if (!g || !w || !colsum || !ls || !dls || n <= 0 || k <= 0) return RZ_ERR_INVALID;
+  if (k % 4 != 0) return RZ_ERR_UNSUPPORTED;
+  if (misaligned(g) || misaligned(w)) return RZ_ERR_ALIGNMENT;
+  ls_weight_kernel<<<n, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, w, bias, colsum, ls, k, dls);
   RZ_LAUNCH_OK();
   rz_count_launch();
   return RZ_OK;

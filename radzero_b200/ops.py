@@ -598,7 +598,7 @@ def grad_scale(grad: torch.Tensor) -> torch.Tensor:
 
 
 @_guard
-def ls_cast_bwd(dy: torch.Tensor, ls: torch.Tensor, o16: Optional[torch.Tensor], sc: torch.Tensor,
+def ls_cast_bwd(dy: torch.Tensor, ls: Optional[torch.Tensor], o16: Optional[torch.Tensor], sc: torch.Tensor,
                 dls: Optional[torch.Tensor]) -> torch.Tensor:
     """Dinov2LayerScale backward: returns fp16(2^k ls dy) (rows, 768); ``dls`` (768,) += sum_rows dy * o16."""
     _need_cuda(dy, ls, o16, sc, dls)
@@ -610,6 +610,24 @@ def ls_cast_bwd(dy: torch.Tensor, ls: torch.Tensor, o16: Optional[torch.Tensor],
     rc = _lib.load().rz_ls_cast_bwd(_p(dy), _p(ls), _p(o16), _p(sc), dy.shape[0], _p(out), _p(dls), _stream())
     _lib.check(rc, "rz_ls_cast_bwd")
     return out
+
+
+@_guard
+def ls_weight_bwd(g: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], colsum: torch.Tensor,
+                  ls: torch.Tensor) -> torch.Tensor:
+    """Dinov2LayerScale backward from ``g = dy^T x`` (n, k) fp32 and ``colsum = sum_rows dy``: in place
+    ``g -> dW = ls g``, ``colsum -> db = ls colsum``; returns ``dls`` (n,) = rowsum(w g) + bias colsum."""
+    _need_cuda(g, w, bias, colsum, ls)
+    for t in (g, w):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.dim() != 2:
+            raise RzError("g / w must be contiguous fp32 (n, k)")
+    if g.shape != w.shape:
+        raise RzError("g and w differ in shape")
+    n, k = g.shape
+    dls = torch.empty(n, dtype=torch.float32, device=g.device)
+    rc = _lib.load().rz_ls_weight_bwd(_p(g), _p(w), _p(bias), _p(colsum), _p(ls), n, k, _p(dls), _stream())
+    _lib.check(rc, "rz_ls_weight_bwd")
+    return dls
 
 
 @_guard

@@ -85,6 +85,23 @@ def test_ls_cast_and_gelu_backward():
     assert (got.double() - ud.grad).abs().max().item() <= 4e-3
 
 
+@pytest.mark.parametrize("n,k", [(768, 768), (768, 3072)])
+def test_layer_scale_backward_from_the_weight_gradient(n, k):
+    """y = ls * (x W^T + b): dW, db and dls from G = dy^T x and colsum(dy), against autograd."""
+    torch.manual_seed(n + k)
+    rows = 300
+    x = torch.randn(rows, k, device=DEV, dtype=torch.float64)
+    dy = torch.randn(rows, n, device=DEV, dtype=torch.float64)
+    W = (torch.randn(n, k, device=DEV, dtype=torch.float64) * 0.05).requires_grad_(True)
+    b = torch.randn(n, device=DEV, dtype=torch.float64).requires_grad_(True)
+    ls = (torch.rand(n, device=DEV, dtype=torch.float64) + 0.5).requires_grad_(True)
+    (ls * (x @ W.T + b)).backward(dy)
+    g = (dy.T @ x).float().contiguous()
+    cs = dy.sum(0).float().contiguous()
+    dls = ops.ls_weight_bwd(g, W.detach().float().contiguous(), b.detach().float(), cs, ls.detach().float())
+    assert _rel(g, W.grad) <= 1e-5 and _rel(cs, b.grad) <= 1e-5 and _rel(dls, ls.grad) <= 1e-4
+
+
 @pytest.mark.parametrize("rows", [1, 5, 1370, 2 * 1370 + 3])
 def test_ln_rows_backward(rows):
     torch.manual_seed(rows)
