@@ -243,3 +243,50 @@ def test_training_step_never_calls_the_stock_modules(monkeypatch):
     mod.kernel_backward = False
     with pytest.raises(AssertionError):
         mod(tok)
+
+
+def test_config4_training_step_through_align_transformer_and_loss():
+    """The trainable chain of radzero.yaml (`module_to_update: [align_transformer, ...]`): ViT output ->
+    AlignTransformer (train mode, kernels under autograd) -> RadZeroLoss.forward (contrastive step kernels)
+    -> backward.  Loss and every gradient against the stock HF encoder + the CPU-side oracle of the loss
+    (oracle/vlcabs.py) chained under torch autograd in fp64."""
+    import copy
+
+    import oracle
+    from radzero_b200 import losses
+    from tests.golden_util import split
+    B, counts, L = 3, [4, 2, 5], 257
+    vit, text, gamma, beta, log_tau = synthetic.make_inputs(B, sum(counts), tokens_per_image=L, seed=61)
+    enc = synthetic.build_align_encoder(seed=61, device=DEV)
+    ref_enc = copy.deepcopy(enc).double().train()
+    mod = AlignTransformer(enc).train()
+    fn = losses.RadZeroLoss(sim_op="cos").to(DEV)
+    with torch.no_grad():
+        fn.layer_norm.weight.copy_(gamma)
+        fn.layer_norm.bias.copy_(beta)
+        fn.loss_temperature.copy_(log_tau.reshape(fn.loss_temperature.shape))
+    t = text.to(DEV).requires_grad_(True)
+    x = vit.to(DEV).requires_grad_(True)
+    feats = split(t, counts)
+    out = fn(list(range(B)), mod(x), lambda i: {"text_features_wo_l2_norm": feats[i]})
+    loss = out["losses"]["loss"]
+    loss.backward()
+    # the checker
+    xd = vit.double().to(DEV).requires_grad_(True)
+    td = text.double().to(DEV).requires_grad_(True)
+    gd, bd = gamma.double().to(DEV).requires_grad_(True), beta.double().to(DEV).requires_grad_(True)
+    ltd = log_tau.double().to(DEV).requires_grad_(True)
+    tok = ref_enc(xd)["last_hidden_state"]
+    tau = torch.exp(ltd)
+    z, _ = oracle.similarity_logit(oracle.layer_norm_rows(td, gd, bd), oracle.layer_norm_rows(tok, gd, bd),
+                                   temperature=tau, sim_op="cos", squeeze_quirk=False)
+    want = oracle.multi_positive_nce_loss(z, oracle.build_group_map(counts).to(DEV), temperature=tau)
+    want.backward()
+    assert abs(loss.item() - want.item()) <= 1e-3 * abs(want.item())
+    assert _rel(x.grad, xd.grad) <= 1e-2 and _rel(t.grad, td.grad) <= 1e-2
+    assert _rel(fn.layer_norm.weight.grad, gd.grad) <= 1e-2 and _rel(fn.layer_norm.bias.grad, bd.grad) <= 1e-2
+    got = {n: p.grad for n, p in enc.named_parameters()}
+    want_g = {n: p.grad for n, p in ref_enc.named_parameters()}
+    worst = max((_rel(got[n], want_g[n]), n) for n in want_g if not n.endswith("key.bias"))
+    assert worst[0] <= 1.5e-2, worst
+    assert all(_key_bias_ok(got, n) for n in want_g if n.endswith("key.bias"))
