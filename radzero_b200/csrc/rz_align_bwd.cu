@@ -120,7 +120,10 @@ __global__ void __launch_bounds__(256) ls_weight_kernel(float* __restrict__ g, c
 }
 
 // ------------------------------------------------------------------------------------------ transpose
-// 64 x 64 tiles; rows >= `rows` read as zero (rows_padded % 64 == 0, cols % 64 == 0)
+// 64 x 64 tiles; rows >= `rows` read as zero (rows_padded % 64 == 0, cols % 64 == 0).  The tile's 16-byte
+// column chunks are XOR-swizzled by the row's octet, so that the transposed read -- eight lanes walking rows
+// rh, rh + 8, ... of one column -- hits eight different bank groups instead of one (pitch 72 halfs alone left
+// an 8-way conflict there).
 __global__ void __launch_bounds__(256) transpose_kernel(const __half* __restrict__ in, long long rows, int cols,
                                                         long long rows_padded, __half* __restrict__ out,
                                                         float* __restrict__ colsum, const float* __restrict__ sc) {
@@ -129,26 +132,27 @@ __global__ void __launch_bounds__(256) transpose_kernel(const __half* __restrict
   const int c0 = blockIdx.y * 64, t = threadIdx.x;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const int r = (t >> 3) + 32 * i, ch = (t & 7) * 8;
+    const int r = (t >> 3) + 32 * i, ch = t & 7;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (r0 + r < rows) v = *reinterpret_cast<const uint4*>(in + (r0 + r) * cols + c0 + ch);
-    *reinterpret_cast<uint4*>(&tile[r][ch]) = v;
+    if (r0 + r < rows) v = *reinterpret_cast<const uint4*>(in + (r0 + r) * cols + c0 + ch * 8);
+    *reinterpret_cast<uint4*>(&tile[r][(ch ^ ((r >> 3) & 7)) * 8]) = v;
   }
   __syncthreads();
   if (colsum != nullptr && t < 64) {
     float s = 0.f;
 #pragma unroll 8
-    for (int r = 0; r < 64; ++r) s += __half2float(tile[r][t]);
+    for (int r = 0; r < 64; ++r) s += __half2float(tile[r][(((t >> 3) ^ ((r >> 3) & 7)) << 3) + (t & 7)]);
     atomicAdd(colsum + c0 + t, s * sc[1]);
   }
   if (out != nullptr) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const int c = (t >> 3) + 32 * i, rh = (t & 7) * 8;
+      const int c = (t >> 3) + 32 * i, ro = t & 7;       // ro: the row octet this thread gathers (rows 8 ro .. 8 ro + 7)
+      const int pc = (((c >> 3) ^ ro) << 3) + (c & 7);
       __align__(16) __half v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = tile[rh + j][c];
-      *reinterpret_cast<uint4*>(out + (long long)(c0 + c) * rows_padded + r0 + rh) = *reinterpret_cast<uint4*>(v);
+      for (int j = 0; j < 8; ++j) v[j] = tile[8 * ro + j][pc];
+      *reinterpret_cast<uint4*>(out + (long long)(c0 + c) * rows_padded + r0 + 8 * ro) = *reinterpret_cast<uint4*>(v);
     }
   }
 }
@@ -391,7 +395,7 @@ __device__ __forceinline__ void prefetch_tile(__half* tile, const __half* base, 
 // accumulates O,   dQ_i = (1 / l_i) sum_j e^{s_ij - m_i} (dP_ij - delta_i) k_j,
 // rescaled when the maximum moves (delta_i = dO_i . o_i does not depend on the normaliser); the row's
 // log-sum-exp m_i + ln l_i falls out at the end and is what kernel 2 reads.
-__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwd p) {
+__global__ void __launch_bounds__(128, 3) attn_bwd_dq_kernel(const AttnBwd p) {
   __shared__ __align__(16) __half Ta[kT * kLd], Tb[kT * kLd], Tc[kT * kLd], Td[kT * kLd];
   __shared__ float delta_s[kT];
   const int tid = threadIdx.x, lane = tid & 31, w16 = (tid >> 5) * 16, g = lane >> 2, tig = lane & 3;
