@@ -23,6 +23,12 @@
 //                      No atomics: every output element has one owner, the result is run-to-run identical.
 //                      This is the one kernel of the repo on the legacy tensor-core path; a tcgen05 version
 //                      on the forward kernel's skeleton (rz_align_attn.cu) is the known next step (DESIGN).
+#ifndef RZ_ATTN_BWD_DQ_CTAS
+#define RZ_ATTN_BWD_DQ_CTAS 4      // resident CTAs per SM the two attention-backward kernels are compiled for
+#endif
+#ifndef RZ_ATTN_BWD_DKV_CTAS
+#define RZ_ATTN_BWD_DKV_CTAS 3
+#endif
 #include <algorithm>
 
 #include "rz_common.cuh"
@@ -310,51 +316,54 @@ __device__ __forceinline__ void load_a_frags(const __half* tile, int w16, uint32
     ldsm_x4(tile + (w16 + (lane & 15)) * kLd + 16 * t + (lane >> 4) * 8, f[t][0], f[t][1], f[t][2], f[t][3]);
 }
 
-// c[nb] (16 x 8 blocks, nb < 8) += A (16 x 64, fragments) . T^T, T = a [64][72] tile holding [n][k].
-// One ldmatrix.x4 = the B fragments of TWO column blocks for one k-step, so that consecutive MMAs write
-// different accumulators (an accumulator comes round again after eight MMAs, not back to back).
-__device__ __forceinline__ void gemm_nt(float (&c)[8][4], const uint32_t (&a)[4][4], const __half* tile) {
+__device__ __forceinline__ void zero_acc(float (&c)[8][4]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
+}
+
+// ---- the warp-level products, on HALF of the streamed tile at a time (32 of its 64 rows): the score /
+// probability blocks of a warp are 16 x 32, which keeps the kernels at 3 - 4 resident CTAs per SM (16 x 64
+// blocks: 2).  One ldmatrix.x4 = the B fragments of TWO column blocks for one k-step, so that consecutive
+// MMAs write different accumulators.
+// c[nb] (nb < 4) += A (16 x 64) . T[32 hb .. 32 hb + 31]^T, T = a [64][72] tile holding [n][k]
+__device__ __forceinline__ void gemm_nt_half(float (&c)[4][4], const uint32_t (&a)[4][4], const __half* tile, int hb) {
   const int lane = threadIdx.x & 31;
-  const __half* base = tile + (8 * (lane >> 4) + (lane & 7)) * kLd + ((lane >> 3) & 1) * 8;
+  const __half* base = tile + (32 * hb + 8 * (lane >> 4) + (lane & 7)) * kLd + ((lane >> 3) & 1) * 8;
 #pragma unroll
   for (int t = 0; t < 4; ++t)
 #pragma unroll
-    for (int np = 0; np < 4; ++np) {
+    for (int np = 0; np < 2; ++np) {
       uint32_t b0, b1, b2, b3;
       ldsm_x4(base + 16 * np * kLd + 16 * t, b0, b1, b2, b3);
       mma16816(c[2 * np], a[t], b0, b1);
       mma16816(c[2 * np + 1], a[t], b2, b3);
     }
 }
-
-// c[nb] += A (16 x 64, fragments; K = the tile's 64 rows) . T, T = a [64][72] tile holding [k][n]
-__device__ __forceinline__ void gemm_nn(float (&c)[8][4], const uint32_t (&a)[4][4], const __half* tile) {
+// c[nb] (nb < 8) += A (16 x 32, fragments of two k-steps) . T[32 hb .. 32 hb + 31], T holding [k][n]
+__device__ __forceinline__ void gemm_nn_half(float (&c)[8][4], const uint32_t (&a)[2][4], const __half* tile, int hb) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int t = 0; t < 4; ++t)
+  for (int t = 0; t < 2; ++t)
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
       uint32_t b0, b1, b2, b3;
-      ldsm_x4_t(tile + (16 * t + (lane & 15)) * kLd + 16 * np + (lane >> 4) * 8, b0, b1, b2, b3);
+      ldsm_x4_t(tile + (32 * hb + 16 * t + (lane & 15)) * kLd + 16 * np + (lane >> 4) * 8, b0, b1, b2, b3);
       mma16816(c[2 * np], a[t], b0, b1);
       mma16816(c[2 * np + 1], a[t], b2, b3);
     }
 }
-
-// accumulator blocks (16 x 64 fp32) -> the A fragments of the next product (fp16)
-__device__ __forceinline__ void acc_to_a(const float (&c)[8][4], uint32_t (&a)[4][4]) {
+__device__ __forceinline__ void acc_to_a_half(const float (&c)[4][4], uint32_t (&a)[2][4]) {
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < 2; ++t) {
     a[t][0] = rz::pack_half2(c[2 * t][0], c[2 * t][1]);
     a[t][1] = rz::pack_half2(c[2 * t][2], c[2 * t][3]);
     a[t][2] = rz::pack_half2(c[2 * t + 1][0], c[2 * t + 1][1]);
     a[t][3] = rz::pack_half2(c[2 * t + 1][2], c[2 * t + 1][3]);
   }
 }
-
-__device__ __forceinline__ void zero_acc(float (&c)[8][4]) {
+__device__ __forceinline__ void zero_half(float (&c)[4][4]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
+  for (int i = 0; i < 4; ++i) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
 }
 
 // rows w16 + g and w16 + g + 8 of the tile starting at global row r0, 64 columns at `dst` (row pitch ld)
@@ -395,7 +404,7 @@ __device__ __forceinline__ void prefetch_tile(__half* tile, const __half* base, 
 // accumulates O,   dQ_i = (1 / l_i) sum_j e^{s_ij - m_i} (dP_ij - delta_i) k_j,
 // rescaled when the maximum moves (delta_i = dO_i . o_i does not depend on the normaliser); the row's
 // log-sum-exp m_i + ln l_i falls out at the end and is what kernel 2 reads.
-__global__ void __launch_bounds__(128, 3) attn_bwd_dq_kernel(const AttnBwd p) {
+__global__ void __launch_bounds__(128, RZ_ATTN_BWD_DQ_CTAS) attn_bwd_dq_kernel(const AttnBwd p) {
   __shared__ __align__(16) __half Ta[kT * kLd], Tb[kT * kLd], Tc[kT * kLd], Td[kT * kLd];
   __shared__ float delta_s[kT];
   const int tid = threadIdx.x, lane = tid & 31, w16 = (tid >> 5) * 16, g = lane >> 2, tig = lane & 3;
@@ -450,40 +459,45 @@ __global__ void __launch_bounds__(128, 3) attn_bwd_dq_kernel(const AttnBwd p) {
     __syncthreads();
     const __half* Ks = kbuf(it & 1);
     const __half* Vs = vbuf(it & 1);
-    float s[8][4], dp[8][4];
-    zero_acc(s);
-    zero_acc(dp);
-    gemm_nt(s, qf, Ks);
-    gemm_nt(dp, gf, Vs);
-    float x0 = -INFINITY, x1 = -INFINITY;
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb)
+    for (int hb = 0; hb < 2; ++hb) {                   // two halves of 32 keys, each its own online-softmax step
+      const int c0 = kv0 + 32 * hb;
+      if (c0 >= L) break;                              // a half of nothing but padding (block-uniform)
+      float s[4][4], dp[4][4];
+      zero_half(s);
+      zero_half(dp);
+      gemm_nt_half(s, qf, Ks, hb);
+      gemm_nt_half(dp, gf, Vs, hb);
+      float x0 = -INFINITY, x1 = -INFINITY;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (kv0 + 8 * nb + 2 * tig + (e & 1) >= L) s[nb][e] = -INFINITY;
-        if (e < 2) x0 = fmaxf(x0, s[nb][e]); else x1 = fmaxf(x1, s[nb][e]);
+      for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (c0 + 8 * nb + 2 * tig + (e & 1) >= L) s[nb][e] = -INFINITY;
+          if (e < 2) x0 = fmaxf(x0, s[nb][e]); else x1 = fmaxf(x1, s[nb][e]);
+        }
+      x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
+      x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
+      const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);
+      if (n0 != m0 || n1 != m1) {                      // warp-divergent only in the first few tiles
+        const float r0 = __expf(m0 - n0), r1 = __expf(m1 - n1);
+        l0 *= r0; l1 *= r1;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) { acc[nb][0] *= r0; acc[nb][1] *= r0; acc[nb][2] *= r1; acc[nb][3] *= r1; }
+        m0 = n0; m1 = n1;
       }
-    x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
-    x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
-    const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);
-    if (n0 != m0 || n1 != m1) {                        // warp-divergent only in the first few tiles
-      const float r0 = __expf(m0 - n0), r1 = __expf(m1 - n1);
-      l0 *= r0; l1 *= r1;
 #pragma unroll
-      for (int nb = 0; nb < 8; ++nb) { acc[nb][0] *= r0; acc[nb][1] *= r0; acc[nb][2] *= r1; acc[nb][3] *= r1; }
-      m0 = n0; m1 = n1;
+      for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float pv = __expf(s[nb][e] - (e < 2 ? m0 : m1));     // masked keys: e^{-inf} = 0
+          if (e < 2) l0 += pv; else l1 += pv;
+          s[nb][e] = pv * (dp[nb][e] - (e < 2 ? d0 : d1));
+        }
+      uint32_t af[2][4];
+      acc_to_a_half(s, af);
+      gemm_nn_half(acc, af, Ks, hb);
     }
-#pragma unroll
-    for (int nb = 0; nb < 8; ++nb)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float pv = __expf(s[nb][e] - (e < 2 ? m0 : m1));       // masked keys: e^{-inf} = 0
-        if (e < 2) l0 += pv; else l1 += pv;
-        s[nb][e] = pv * (dp[nb][e] - (e < 2 ? d0 : d1));
-      }
-    uint32_t af[4][4];
-    acc_to_a(s, af);
-    gemm_nn(acc, af, Ks);
     __syncthreads();
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -496,7 +510,7 @@ __global__ void __launch_bounds__(128, 3) attn_bwd_dq_kernel(const AttnBwd p) {
 }
 
 // kernel 2: grid (key tiles, B * H), 4 warps x 16 key rows; everything is held transposed (keys are rows)
-__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwd p) {
+__global__ void __launch_bounds__(128, RZ_ATTN_BWD_DKV_CTAS) attn_bwd_dkv_kernel(const AttnBwd p) {
   __shared__ __align__(16) __half Ta[kT * kLd], Tb[kT * kLd], Tc[kT * kLd], Td[kT * kLd];
   __shared__ __align__(16) float lse_s[2][kT], delta_s[2][kT];
   const int tid = threadIdx.x, lane = tid & 31, w16 = (tid >> 5) * 16, tig = lane & 3;
@@ -549,25 +563,29 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwd p) {
     __syncthreads();
     const __half* Qs = qbuf(cur);
     const __half* Gs = gbuf(cur);
-    float s[8][4], dp[8][4];
-    zero_acc(s);
-    zero_acc(dp);
-    gemm_nt(s, kf, Qs);                                // S^T = K Q^T
-    gemm_nt(dp, vf, Gs);                               // dP^T = V dO^T
 #pragma unroll
-    for (int nb = 0; nb < 8; ++nb)
+    for (int hb = 0; hb < 2; ++hb) {                   // two halves of 32 queries
+      if (q0 + 32 * hb >= L) break;                    // nothing but padded queries (block-uniform)
+      float s[4][4], dp[4][4];
+      zero_half(s);
+      zero_half(dp);
+      gemm_nt_half(s, kf, Qs, hb);                     // S^T = K Q^T
+      gemm_nt_half(dp, vf, Gs, hb);                    // dP^T = V dO^T
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = 8 * nb + 2 * tig + (e & 1);      // query index inside the tile = column
-        const float pv = __expf(s[nb][e] - lse_s[cur][c]);
-        dp[nb][e] = pv * (dp[nb][e] - delta_s[cur][c]);   // dS^T
-        s[nb][e] = pv;                                 // P^T
-      }
-    uint32_t af[4][4];
-    acc_to_a(s, af);
-    gemm_nn(dv, af, Gs);                               // dV += P^T dO
-    acc_to_a(dp, af);
-    gemm_nn(dk, af, Qs);                               // dK += dS^T Q
+      for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = 32 * hb + 8 * nb + 2 * tig + (e & 1);   // query index inside the tile = column
+          const float pv = __expf(s[nb][e] - lse_s[cur][c]);
+          dp[nb][e] = pv * (dp[nb][e] - delta_s[cur][c]);       // dS^T
+          s[nb][e] = pv;                                        // P^T
+        }
+      uint32_t af[2][4];
+      acc_to_a_half(s, af);
+      gemm_nn_half(dv, af, Gs, hb);                    // dV += P^T dO
+      acc_to_a_half(dp, af);
+      gemm_nn_half(dk, af, Qs, hb);                    // dK += dS^T Q
+    }
     __syncthreads();
   }
   // q carries the folded 1/sqrt(64): dK = dS^T q_packed is already the gradient of the true key projection
