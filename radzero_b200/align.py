@@ -31,6 +31,7 @@ No CPU fallback: CPU tensors raise ``RzError``.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -121,42 +122,96 @@ def _dweight(dyT: torch.Tensor, xT: torch.Tensor, sc: torch.Tensor) -> torch.Ten
     return ops.linear(dyT, xT, None, "residual", scale=sc[4:4 + xT.shape[0]], residual=out, out=out)
 
 
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+OVERLAP_WEIGHT_GRADS = os.environ.get("RZ_ALIGN_BWD_OVERLAP", "1") != "0"
+
+
+def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """One high-priority stream per device for the weight-gradient branch of the backward."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _SIDE_STREAMS:
+        _SIDE_STREAMS[idx] = torch.cuda.Stream(device=dev, priority=-1)
+    return _SIDE_STREAMS[idx]
+
+
+class _Branch:
+    """The weight-gradient branch of a layer's backward.  dW = dY^T X (and the bias / LayerScale
+    gradients hanging off it) feeds nothing else in the chain, and its GEMMs are short of CTAs (768 x 768
+    outputs = 18 tiles on 148 SMs), so it runs on a high-priority side stream next to the dX chain and the
+    attention backward instead of leaving SMs idle in line.  Inputs made on the main stream are handed over
+    with an event + ``record_stream`` (the caching allocator must not recycle them while the side stream
+    still reads them); ``join`` makes the main stream wait and hands the results back the same way."""
+
+    def __init__(self, dev: torch.device, enabled: bool):
+        self.main = torch.cuda.current_stream(dev)
+        self.side = _side_stream(dev) if enabled else None
+        self.outs: List[torch.Tensor] = []
+
+    def run(self, fn, *inputs: torch.Tensor):
+        if self.side is None:
+            return fn()
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        self.side.wait_event(ev)
+        for t in inputs:
+            t.record_stream(self.side)
+        with torch.cuda.stream(self.side):
+            res = fn()
+        self.outs.extend(r for r in res if torch.is_tensor(r))
+        return res
+
+    def join(self) -> None:
+        if self.side is None:
+            return
+        self.main.wait_stream(self.side)
+        for t in self.outs:
+            t.record_stream(self.main)
+        self.outs = []
+
+
 def layer_backward(dz: torch.Tensor, saved, B: int, L: int, w: Dict[str, torch.Tensor],
-                   wb: Dict[str, torch.Tensor], sc: torch.Tensor):
+                   wb: Dict[str, torch.Tensor], sc: torch.Tensor, branch: Optional[_Branch] = None):
     """Autograd of one Dinov2Layer.  ``dz`` (B L, 768) fp32 = dL/d(layer output); returns
-    (dL/d(layer input) fp32, gradients in ``layer_params`` order, fp32)."""
+    (dL/d(layer input) fp32, gradients in ``layer_params`` order, fp32).  The caller joins ``branch``
+    before it reads the gradients."""
     x2, h1, qkv, a, y, h2, g = saved
     D = x2.shape[1]
     dev = dz.device
+    br = branch or _Branch(dev, False)
     zeros = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
-    # ---- x = y + ls2 * (gelu(h2 W1^T + b1) W2^T + b2): LayerScale is folded into w2_t (dX) and finished from
-    # the unscaled weight gradient by rz_ls_weight_bwd (dW, db, dls), so the product is never recomputed
-    db2, db1 = zeros(D), zeros(4 * D)
+
+    def wgrad(dy16, x16, bias_n, ls=None, w32=None, bias=None):
+        """(dW, db, dls | None) of ``o = x W^T + b`` (times LayerScale) from dy16 = fp16(2^k dL/do) and x."""
+        db = zeros(bias_n)
+        dw = _dweight(ops.transpose_pad(dy16, sc, db), ops.transpose_pad(x16), sc)
+        # LayerScale is folded into the transposed weights of the dX product and finished here from the
+        # unscaled weight gradient (dW, db, dls), so the scaled product is never recomputed
+        dls = ops.ls_weight_bwd(dw, w32, bias, db, ls) if ls is not None else None
+        return dw, db, dls
+
+    # ---- x = y + ls2 * (gelu(h2 W1^T + b1) W2^T + b2)
     do2 = ops.ls_cast_bwd(dz, None, None, sc, None)
-    dw2 = _dweight(ops.transpose_pad(do2, sc, db2), ops.transpose_pad(g), sc)
-    dls2 = ops.ls_weight_bwd(dw2, wb["w232"], w["bf2"], db2, w["ls2"])
+    dw2, db2, dls2 = br.run(lambda: wgrad(do2, g, D, w["ls2"], wb["w232"], w["bf2"]), do2, g, sc)
     dg = ops.linear(do2, wb["w2_t"], None, "bias")
     del do2
     u = ops.linear(h2, w["w1"], w["bf1"], "bias")                    # recomputed pre-activation
     du = ops.gelu_bwd(dg, u)
     del dg, u
-    dw1 = _dweight(ops.transpose_pad(du, sc, db1), ops.transpose_pad(h2), sc)
+    dw1, db1, _ = br.run(lambda: wgrad(du, h2, 4 * D), du, h2, sc)
     dh2 = ops.linear(du, wb["w1_t"], None, "bias")
     del du
     dg2, dbeta2 = zeros(D), zeros(D)
     dy = ops.ln_rows_bwd(y, dh2, w["g2"], w["eps2"], dz, sc, dg2, dbeta2)
     del dh2
     # ---- y = x + ls1 * (attention(LN1(x)) Wo^T + bo)
-    dbo, dbqkv = zeros(D), zeros(3 * D)
     do1 = ops.ls_cast_bwd(dy, None, None, sc, None)
-    dwo = _dweight(ops.transpose_pad(do1, sc, dbo), ops.transpose_pad(a), sc)
-    dls1 = ops.ls_weight_bwd(dwo, wb["wo32"], w["bo"], dbo, w["ls1"])
+    dwo, dbo, dls1 = br.run(lambda: wgrad(do1, a, D, w["ls1"], wb["wo32"], w["bo"]), do1, a, sc)
     da = ops.linear(do1, wb["wo_t"], None, "bias")
     del do1
     dqkv = ops.attention_bwd(qkv.view(B, L, 3 * D), a.view(B, L, D), da.view(B, L, D), w["heads"],
                              w["q_scale"]).view(B * L, 3 * D)
     del da
-    dwqkv = _dweight(ops.transpose_pad(dqkv, sc, dbqkv), ops.transpose_pad(h1), sc)
+    dwqkv, dbqkv, _ = br.run(lambda: wgrad(dqkv, h1, 3 * D), dqkv, h1, sc)
     dh1 = ops.linear(dqkv, wb["wqkv_t"], None, "bias")
     del dqkv
     dg1, dbeta1 = zeros(D), zeros(D)
@@ -194,9 +249,11 @@ class _AlignFn(torch.autograd.Function):
         dz = dout.to(torch.float32).contiguous().view(B * L, D)
         sc = ops.grad_scale(dz)
         per_layer = []
+        branch = _Branch(dout.device, OVERLAP_WEIGHT_GRADS)
         for w, wb, sv in zip(reversed(layers), reversed(back), reversed(ctx.saved)):
-            dz, grads = layer_backward(dz, sv, B, L, w, wb, sc)
+            dz, grads = layer_backward(dz, sv, B, L, w, wb, sc, branch)
             per_layer.append(grads)
+        branch.join()
         ctx.saved = None
         flat = [g for grads in reversed(per_layer) for g in grads]
         out = []
