@@ -387,7 +387,8 @@ int rz_attention(const void* qkv_f16, int n_images, int tokens, int heads, void*
  *                   (the bias gradient; out or colsum may be NULL).
  * rz_gelu_bwd       du = dg * gelu_erf'(u), n fp16 elements (n % 8 == 0).
  * rz_ln_rows_bwd    nn.LayerNorm(768, eps): dx fp32 [rows, 768] = dres + 2^-k LN'(dh_f16) (dres NULL = 0, dx
- *                   may alias dres); dgamma / dbeta [768] += the parameter gradients (NULL = skipped).
+ *                   may alias dres); dx_f16 (optional) = fp16(2^k dx), the operand of the next product;
+ *                   dgamma / dbeta [768] += the parameter gradients (NULL = skipped).
  * rz_attention_bwd  backward of rz_attention: qkv / out as there, dout fp16 [n_images, tokens, heads * 64];
  *                   dqkv fp16 like qkv, its q block multiplied by q_scale (the 1/sqrt(64) the host folded
  *                   into the query projection: dqkv is then the gradient of the UNSCALED projections);
@@ -403,7 +404,8 @@ int rz_transpose_pad(const void* in_f16, long long rows, int cols, long long row
                      float* colsum, const float* sc, void* stream);
 int rz_gelu_bwd(const void* dg_f16, const void* u_f16, long long n, void* du_f16, void* stream);
 int rz_ln_rows_bwd(const float* x, const void* dh_f16, const float* gamma, float eps, const float* dres,
-                   const float* sc, long long rows, float* dx, float* dgamma, float* dbeta, void* stream);
+                   const float* sc, long long rows, float* dx, void* dx_f16, float* dgamma, float* dbeta,
+                   void* stream);
 int rz_attention_bwd(const void* qkv_f16, const void* out_f16, const void* dout_f16, int n_images,
                      int tokens, int heads, float q_scale, float* lse, float* delta, void* dqkv_f16,
                      void* stream);

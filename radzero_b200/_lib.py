@@ -65,7 +65,7 @@ SIGNATURES: Dict[str, tuple] = {
     "rz_ls_weight_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "rz_transpose_pad": (_i, [_vp, _ll, _i, _ll, _vp, _vp, _vp, _vp]),
     "rz_gelu_bwd": (_i, [_vp, _vp, _ll, _vp, _vp]),
-    "rz_ln_rows_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _ll, _vp, _vp, _vp, _vp]),
+    "rz_ln_rows_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp]),
     "rz_attention_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "rz_umma_probe": (_i, [_vp, _i, _vp, _i, _ull, _ull, _i, _i, _i, _u, _u, _i, _vp, _vp]),
 }

@@ -170,10 +170,13 @@ class _Branch:
 
 
 def layer_backward(dz: torch.Tensor, saved, B: int, L: int, w: Dict[str, torch.Tensor],
-                   wb: Dict[str, torch.Tensor], sc: torch.Tensor, branch: Optional[_Branch] = None):
+                   wb: Dict[str, torch.Tensor], sc: torch.Tensor, branch: Optional[_Branch] = None,
+                   dz16: Optional[torch.Tensor] = None, want_dx16: bool = False):
     """Autograd of one Dinov2Layer.  ``dz`` (B L, 768) fp32 = dL/d(layer output); returns
-    (dL/d(layer input) fp32, gradients in ``layer_params`` order, fp32).  The caller joins ``branch``
-    before it reads the gradients."""
+    (dL/d(layer input) fp32, gradients in ``layer_params`` order, fp32, fp16(2^k dL/d(layer input)) | None).
+    ``dz16`` = fp16(2^k dz) when the layer above already produced it (``want_dx16``: the LayerNorm backward
+    writes the fp16 operand of the next product from the registers that hold the fp32 result).  The caller
+    joins ``branch`` before it reads the gradients."""
     x2, h1, qkv, a, y, h2, g = saved
     D = x2.shape[1]
     dev = dz.device
@@ -190,7 +193,7 @@ def layer_backward(dz: torch.Tensor, saved, B: int, L: int, w: Dict[str, torch.T
         return dw, db, dls
 
     # ---- x = y + ls2 * (gelu(h2 W1^T + b1) W2^T + b2)
-    do2 = ops.ls_cast_bwd(dz, None, None, sc, None)
+    do2 = dz16 if dz16 is not None else ops.ls_cast_bwd(dz, None, None, sc, None)
     dw2, db2, dls2 = br.run(lambda: wgrad(do2, g, D, w["ls2"], wb["w232"], w["bf2"]), do2, g, sc)
     dg = ops.linear(do2, wb["w2_t"], None, "bias")
     del do2
@@ -201,10 +204,10 @@ def layer_backward(dz: torch.Tensor, saved, B: int, L: int, w: Dict[str, torch.T
     dh2 = ops.linear(du, wb["w1_t"], None, "bias")
     del du
     dg2, dbeta2 = zeros(D), zeros(D)
-    dy = ops.ln_rows_bwd(y, dh2, w["g2"], w["eps2"], dz, sc, dg2, dbeta2)
+    do1 = torch.empty((dz.shape[0], D), dtype=torch.float16, device=dev)
+    dy = ops.ln_rows_bwd(y, dh2, w["g2"], w["eps2"], dz, sc, dg2, dbeta2, out16=do1)
     del dh2
     # ---- y = x + ls1 * (attention(LN1(x)) Wo^T + bo)
-    do1 = ops.ls_cast_bwd(dy, None, None, sc, None)
     dwo, dbo, dls1 = br.run(lambda: wgrad(do1, a, D, w["ls1"], wb["wo32"], w["bo"]), do1, a, sc)
     da = ops.linear(do1, wb["wo_t"], None, "bias")
     del do1
@@ -215,11 +218,12 @@ def layer_backward(dz: torch.Tensor, saved, B: int, L: int, w: Dict[str, torch.T
     dh1 = ops.linear(dqkv, wb["wqkv_t"], None, "bias")
     del dqkv
     dg1, dbeta1 = zeros(D), zeros(D)
-    dx = ops.ln_rows_bwd(x2, dh1, w["g1"], w["eps1"], dy, sc, dg1, dbeta1, out=dy)
+    dx16 = torch.empty((dz.shape[0], D), dtype=torch.float16, device=dev) if want_dx16 else None
+    dx = ops.ln_rows_bwd(x2, dh1, w["g1"], w["eps1"], dy, sc, dg1, dbeta1, out=dy, out16=dx16)
     grads = [dg1, dbeta1,
              dwqkv[:D], dbqkv[:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:], dbqkv[2 * D:],
              dwo, dbo, dls1, dg2, dbeta2, dw1, db1, dw2, db2, dls2]
-    return dx, grads
+    return dx, grads, dx16
 
 
 class _AlignFn(torch.autograd.Function):
@@ -250,9 +254,11 @@ class _AlignFn(torch.autograd.Function):
         sc = ops.grad_scale(dz)
         per_layer = []
         branch = _Branch(dout.device, OVERLAP_WEIGHT_GRADS)
-        for w, wb, sv in zip(reversed(layers), reversed(back), reversed(ctx.saved)):
-            dz, grads = layer_backward(dz, sv, B, L, w, wb, sc, branch)
+        dz16 = None
+        for i, (w, wb, sv) in enumerate(zip(reversed(layers), reversed(back), reversed(ctx.saved))):
+            dz, grads, dz16 = layer_backward(dz, sv, B, L, w, wb, sc, branch, dz16, want_dx16=i + 1 < len(layers))
             per_layer.append(grads)
+        del dz16
         branch.join()
         ctx.saved = None
         flat = [g for grads in reversed(per_layer) for g in grads]

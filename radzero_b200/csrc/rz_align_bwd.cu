@@ -198,10 +198,11 @@ __global__ void __launch_bounds__(32 * kLnWarps) ln_bwd_kernel(const float* __re
                                                               const float* __restrict__ gamma, float eps,
                                                               const float* __restrict__ dres, const float* __restrict__ sc,
                                                               long long rows, float* __restrict__ dx,
+                                                              __half* __restrict__ dx16,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
   __shared__ float fold[kLnWarps][kD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float down = sc[1];
+  const float down = sc[1], up = sc[0];
   float g[24], ag[24], ab[24];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
@@ -250,6 +251,8 @@ __global__ void __launch_bounds__(32 * kLnWarps) ln_bwd_kernel(const float* __re
       o.z += k * (dv[4 * i + 2] - s1 - xv[4 * i + 2] * s2);
       o.w += k * (dv[4 * i + 3] - s1 - xv[4 * i + 3] * s2);
       *reinterpret_cast<float4*>(dx + r * kD + lane * 4 + 128 * i) = o;
+      if (dx16 != nullptr)      // the next product's fp16 operand (2^k dx) from the same registers
+        *reinterpret_cast<uint2*>(dx16 + r * kD + lane * 4 + 128 * i) = rz::pack4<__half>(o.x * up, o.y * up, o.z * up, o.w * up);
     }
   }
 #pragma unroll 1
@@ -669,14 +672,16 @@ extern "C" int rz_gelu_bwd(const void* dg_f16, const void* u_f16, long long n, v
 }
 
 extern "C" int rz_ln_rows_bwd(const float* x, const void* dh_f16, const float* gamma, float eps, const float* dres,
-                              const float* sc, long long rows, float* dx, float* dgamma, float* dbeta, void* stream) {
+                              const float* sc, long long rows, float* dx, void* dx_f16, float* dgamma, float* dbeta,
+                              void* stream) {
   if (!x || !dh_f16 || !gamma || !sc || !dx || rows < 0) return RZ_ERR_INVALID;
-  if (misaligned(x) || misaligned(dh_f16) || misaligned(gamma) || misaligned(dres) || misaligned(dx))
+  if (misaligned(x) || misaligned(dh_f16) || misaligned(gamma) || misaligned(dres) || misaligned(dx) ||
+      misaligned(dx_f16))
     return RZ_ERR_ALIGNMENT;
   if (rows == 0) return RZ_OK;
   const int blocks = (int)std::min<long long>((rows + kLnWarps - 1) / kLnWarps, (long long)rz_sm_count() * 2);
   ln_bwd_kernel<<<blocks, 32 * kLnWarps, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, static_cast<const __half*>(dh_f16), gamma, eps, dres, sc, rows, dx, dgamma, dbeta);
+      x, static_cast<const __half*>(dh_f16), gamma, eps, dres, sc, rows, dx, static_cast<__half*>(dx_f16), dgamma, dbeta);
   RZ_LAUNCH_OK();
   rz_count_launch();
   return RZ_OK;

@@ -661,9 +661,10 @@ def gelu_bwd(dg16: torch.Tensor, u16: torch.Tensor) -> torch.Tensor:
 @_guard
 def ln_rows_bwd(x: torch.Tensor, dh16: torch.Tensor, gamma: torch.Tensor, eps: float, dres: Optional[torch.Tensor],
                 sc: torch.Tensor, dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor],
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """nn.LayerNorm backward: ``dres + 2^-k LN'(dh16)`` fp32 (rows, 768); dgamma / dbeta accumulated."""
-    _need_cuda(x, dh16, gamma, dres, sc, dgamma, dbeta, out)
+                out: Optional[torch.Tensor] = None, out16: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.LayerNorm backward: ``dres + 2^-k LN'(dh16)`` fp32 (rows, 768); dgamma / dbeta accumulated;
+    ``out16`` (rows, 768) fp16, optional, receives ``fp16(2^k result)`` (the next product's operand)."""
+    _need_cuda(x, dh16, gamma, dres, sc, dgamma, dbeta, out, out16)
     if x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 2 or x.shape[1] != HIDDEN:
         raise RzError("x must be contiguous fp32 (rows, 768)")
     _f16c(dh16, "dh16")
@@ -671,8 +672,10 @@ def ln_rows_bwd(x: torch.Tensor, dh16: torch.Tensor, gamma: torch.Tensor, eps: f
         raise RzError("dres must be contiguous fp32 like x")
     if out is None:
         out = torch.empty_like(x)
+    if out16 is not None and (out16.dtype != torch.float16 or not out16.is_contiguous() or out16.shape != x.shape):
+        raise RzError("out16 must be contiguous fp16 like x")
     rc = _lib.load().rz_ln_rows_bwd(_p(x), _p(dh16), _p(gamma), float(eps), _p(dres), _p(sc), x.shape[0],
-                                    _p(out), _p(dgamma), _p(dbeta), _stream())
+                                    _p(out), _p(out16), _p(dgamma), _p(dbeta), _stream())
     _lib.check(rc, "rz_ln_rows_bwd")
     return out
 
