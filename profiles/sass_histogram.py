@@ -9,7 +9,8 @@ print("# SASS opcode histogram of librz_b200.so (sm_100a), per object file\n")
 print("`cuobjdump -sass radzero_b200/_build/*.o`, counted by `profiles/sass_histogram.py`.  UTCHMMA = tcgen05.mma "
       "(kind::f16), `.2CTA` = cta_group::2; UTMALDG / UTMASTG = TMA tensor load / store; LDTM / STTM = tcgen05.ld / "
       "tcgen05.st (TMEM); SYNCS = mbarrier; FFMA2 / FMUL2 / FADD2 = packed fp32 pairs.  HMMA / IMMA (legacy "
-      "mma.sync) must be 0.\n")
+      "mma.sync) are 0 everywhere except rz_align_bwd.o: the two attention-backward kernels of the AlignTransformer "
+      "training step are the one place still on the register-operand tensor path (profiles/r2_full_attn_bwd.md).\n")
 print("| object | " + " | ".join(KEYS) + " | kernels |")
 print("|---|" + "---|" * (len(KEYS) + 1))
 tot = collections.Counter()
