@@ -143,7 +143,8 @@ class _Branch:
     still reads them); ``join`` makes the main stream wait and hands the results back the same way."""
 
     def __init__(self, dev: torch.device, enabled: bool):
-        self.main = torch.cuda.current_stream(dev)
+        enabled = enabled and dev.type == "cuda"
+        self.main = torch.cuda.current_stream(dev) if enabled else None
         self.side = _side_stream(dev) if enabled else None
         self.outs: List[torch.Tensor] = []
 
