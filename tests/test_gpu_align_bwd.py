@@ -292,3 +292,19 @@ def test_config4_training_step_through_align_transformer_and_loss():
     worst = max((_rel(got[n], want_g[n]), n) for n in want_g if not n.endswith("key.bias"))
     assert worst[0] <= 1.5e-2, worst
     assert all(_key_bias_ok(got, n) for n in want_g if n.endswith("key.bias"))
+
+
+@pytest.mark.parametrize("B,L", [(8, 1370), (16, 257)])
+def test_attention_backward_is_run_to_run_deterministic(B, L):
+    """The two kernels double-buffer their tiles with cp.async and reuse the fixed operands' tiles as the second
+    buffer: a missing barrier there would show up as run-to-run differences (this is how round 2 found the race
+    in the small-N forward).  No atomics in these kernels, so every launch must be bit-identical."""
+    torch.manual_seed(L)
+    H = 12
+    qkv = (torch.randn(B, L, 3 * H * 64, device=DEV) * 0.6).half()
+    out = ops.attention(qkv, H)
+    dout = torch.randn(B, L, H * 64, device=DEV).half()
+    first = ops.attention_bwd(qkv, out, dout, H, 0.125)
+    assert torch.isfinite(first.float()).all()
+    for _ in range(40):
+        assert torch.equal(ops.attention_bwd(qkv, out, dout, H, 0.125), first)
