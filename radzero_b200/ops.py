@@ -579,6 +579,8 @@ def attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- A3 (AlignTransformer backward)
+_ATTN_BWD_MAX_BH = 65535      # (image, head) pairs per rz_attention_bwd launch
+
 def _f16c(t, what):
     if t.dtype != torch.float16 or not t.is_contiguous():
         raise RzError(f"{what} must be contiguous fp16")
@@ -691,10 +693,18 @@ def attention_bwd(qkv: torch.Tensor, out16: torch.Tensor, dout16: torch.Tensor, 
     if W != 3 * heads * 64 or tuple(out16.shape) != (B, L, heads * 64) or out16.shape != dout16.shape:
         raise RzError("attention_bwd shapes: qkv (B, L, 3 * heads * 64), out / dout (B, L, heads * 64)")
     dqkv = torch.empty_like(qkv)
-    ws = torch.empty((2, B * heads * ((L + 63) // 64 * 64)), dtype=torch.float32, device=qkv.device)
-    rc = _lib.load().rz_attention_bwd(_p(qkv), _p(out16), _p(dout16), B, L, heads, float(q_scale),
-                                      _p(ws[0]), _p(ws[1]), _p(dqkv), _stream())
-    _lib.check(rc, "rz_attention_bwd")
+    if B == 0 or L == 0:
+        return dqkv
+    # one launch covers at most 65 535 (image, head) pairs (the grid's y extent): more images go in slices
+    step = max(1, _ATTN_BWD_MAX_BH // heads)
+    lp = (L + 63) // 64 * 64
+    ws = torch.empty((2, min(B, step) * heads * lp), dtype=torch.float32, device=qkv.device)
+    lib = _lib.load()
+    for i0 in range(0, B, step):
+        i1 = min(B, i0 + step)
+        rc = lib.rz_attention_bwd(_p(qkv[i0:i1]), _p(out16[i0:i1]), _p(dout16[i0:i1]), i1 - i0, L, heads,
+                                  float(q_scale), _p(ws[0]), _p(ws[1]), _p(dqkv[i0:i1]), _stream())
+        _lib.check(rc, "rz_attention_bwd")
     return dqkv
 
 

@@ -308,3 +308,15 @@ def test_attention_backward_is_run_to_run_deterministic(B, L):
     assert torch.isfinite(first.float()).all()
     for _ in range(40):
         assert torch.equal(ops.attention_bwd(qkv, out, dout, H, 0.125), first)
+
+
+def test_attention_backward_in_image_slices(monkeypatch):
+    """More than 65 535 (image, head) pairs go through several launches: forced here with a small limit."""
+    torch.manual_seed(9)
+    B, L, H = 5, 150, 12
+    qkv = (torch.randn(B, L, 3 * H * 64, device=DEV) * 0.5).half()
+    out = ops.attention(qkv, H)
+    dout = torch.randn(B, L, H * 64, device=DEV).half()
+    whole = ops.attention_bwd(qkv, out, dout, H, 0.125)
+    monkeypatch.setattr(ops, "_ATTN_BWD_MAX_BH", 2 * H)          # slices of 2, 2 and 1 images
+    assert torch.equal(ops.attention_bwd(qkv, out, dout, H, 0.125), whole)
