@@ -535,8 +535,16 @@ def run_ours(args):
         sampler = ClockSampler(local)
         sampler.start()
         t = bench_align.run_train(args, world, rank, local, pk, steps=max(3, min(args.steps, 10)), warmup=3)
+        cpu = None
+        if rank == 0 and world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            dt = align_train_cpu_sample(2, cores)
+            cpu = {"value": 2 / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                   "sample": f"forward + autograd backward of 2 images x 1370 tokens on the fp32 torch CPU oracle "
+                             f"(oracle/align.py), best of 2, {dt * 1e3:.0f} ms"}
         if rank == 0:
             print(json.dumps({"metric": "AlignTransformer training images/sec", "value": t["images_per_s"] * world,
+                              "cpu_baseline": cpu,
                               "unit": "images/s", "n_gpus": world, "ms_per_step": t["ms_per_step"],
                               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
                               "data": "synthetic", "impl": "ours", "config": {"workload": t["workload"]},
@@ -716,6 +724,33 @@ def contrastive_run_reference(args):
                                    f"to {B_GLOBAL} x {n_total}"},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def align_train_cpu_sample(b: int = 2, threads=None):
+    """The CPU oracle of the AlignTransformer training step: forward + autograd backward of oracle/align.py
+    (fp32 torch) on ``b`` images: seconds per step (best of 2 after one warm-up)."""
+    from oracle import align as oalign
+    from radzero_b200 import synthetic
+    if threads:
+        torch.set_num_threads(threads)
+    w = [{k: v.clone().requires_grad_(True) for k, v in layer.items()} for layer in synthetic.align_layer_weights(42)]
+    tok = synthetic.make_inputs(b, 1, seed=42)[0].requires_grad_(True)
+    up = torch.randn(tok.shape, generator=torch.Generator().manual_seed(7)) * 1e-3
+
+    def once():
+        for layer in w:
+            for v in layer.values():
+                v.grad = None
+        tok.grad = None
+        (oalign.align_transformer(tok, w) * up).sum().backward()
+
+    once()
+    best = float("inf")
+    for _ in range(2):
+        t0 = time.perf_counter()
+        once()
+        best = min(best, time.perf_counter() - t0)
+    return best
 
 
 def align_cpu_step_sample(b: int = 8, threads=None):
