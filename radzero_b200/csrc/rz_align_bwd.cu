@@ -2,8 +2,8 @@
 // exp/cxr_pt/model/align_transformers.py:37-45) -- the only trainable vision compute of RadZero
 // (radzero.yaml `module_to_update: [align_transformer, ...]`).
 //
-// The twelve GEMM-shaped products of a layer's backward (dX = dY W, dW = dY^T X for the four linear
-// layers, plus the recomputation of three forward products) run on the tcgen05 GEMM of rz_align_linear.cu
+// The nine GEMM-shaped products of a layer's backward (dX = dY W and dW = dY^T X for the four linear
+// layers, plus the recomputation of fc1's pre-activation) run on the tcgen05 GEMM of rz_align_linear.cu
 // (rz_linear); this file holds what sits between them:
 //
 //   rz_grad_scale      one power-of-two scale for the whole fp16 gradient chain, from max|dL/dtokens|,
@@ -14,7 +14,8 @@
 //   rz_transpose_pad   [rows, cols] -> [cols, rows_padded] fp16 (the K-major operands of the dW GEMMs,
 //                      K = rows) + the bias gradients as column sums of the same read
 //   rz_gelu_bwd        du16 = dg16 gelu_erf'(u16)
-//   rz_ln_rows_bwd     nn.LayerNorm backward of one row per warp + the residual-path gradient
+//   rz_ln_rows_bwd     nn.LayerNorm backward of one row per warp + the residual-path gradient (+ the fp16
+//                      operand of the next product from the same registers)
 //   rz_attention_bwd   softmax(q k^T) v backward per (image, head), head dim 64, warp-level
 //                      mma.sync.m16n8k16 (fp16 in, fp32 accumulate), recomputing the probabilities:
 //                        kernel 1 (64 query rows / CTA): delta = rowsum(dO o), dQ against a running maximum
